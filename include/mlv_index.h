@@ -1,0 +1,188 @@
+/*
+ * mlv_index.h -- C ABI of the B200-native exact-search index (libmlvindex.so).
+ *
+ * This is the drop-in boundary for the hot path of SudYar/MLVectorDB: everything the
+ * reference does through `hnswlib.Index` inside
+ * `src/mlvectordb/implementations/index.py` is replaced by the calls below.  Plain pointers
+ * and sizes only; no torch / C++ types cross this boundary.  Every function returns an
+ * `mlv_status` and never throws or aborts across the ABI.
+ *
+ * Arithmetic contract (hnswlib 0.8.0 form, reference index.py:36 selects it):
+ *   MLV_L2      d = sum_i (x_i - q_i)^2        (squared, no sqrt)
+ *   MLV_IP      d = 1 - sum_i x_i q_i
+ *   MLV_COSINE  rows are normalised when added and queries when searched with
+ *               1/(sqrt(sum v_i^2) + 1e-30) in fp32, then d = 1 - sum_i x_i q_i
+ * All results are ascending by (d, row).  The Python shim applies the reference's
+ * `score = 1 - d` for metric == "cosine" (reference index.py:126-127).
+ *
+ * Rows are addressed by their LOCAL row number inside the index (the role hnswlib labels
+ * play at reference index.py:56-63); results carry `row_base + local row` so that shards of
+ * one namespace report global rows.
+ */
+#ifndef MLV_INDEX_H
+#define MLV_INDEX_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MLV_ABI_VERSION 1
+
+typedef struct mlv_index *mlv_index_t;
+
+enum mlv_metric { MLV_L2 = 0, MLV_IP = 1, MLV_COSINE = 2 };
+
+enum mlv_status {
+    MLV_OK = 0,
+    MLV_E_INVALID = 1,      /* bad argument (NULL handle, k == 0, unknown metric ...) */
+    MLV_E_CUDA = 2,         /* a CUDA runtime call failed; see mlv_last_error() */
+    MLV_E_NOMEM = 3,        /* device or host allocation failed */
+    MLV_E_UNSUPPORTED = 4,  /* valid request outside this build's limits (k > MLV_MAX_K, dim too large) */
+    MLV_E_NO_DEVICE = 5     /* no usable CUDA device: there is NO CPU fallback */
+};
+
+#define MLV_MAX_K 1024u   /* reference REST bound is top_k <= 1000 (rest_api.py:24) */
+
+typedef struct mlv_index_info {
+    uint64_t rows;          /* stored rows including tombstoned ones (hnswlib get_current_count, index.py:56) */
+    uint64_t live;          /* rows - tombstoned */
+    uint64_t capacity;      /* rows the current device allocation can hold */
+    uint64_t row_base;      /* added to local rows in every result */
+    uint64_t device_bytes;  /* bytes of HBM held by this index */
+    uint32_t dim;           /* logical dimension d */
+    uint32_t ld;            /* floats per stored row (d rounded up to 4 -> 16-byte aligned rows) */
+    int32_t metric;
+    int32_t device;
+} mlv_index_info_t;
+
+/* ABI version of the loaded library (== MLV_ABI_VERSION of the header it was built from). */
+int mlv_abi_version(void);
+/* Number of visible CUDA devices, or 0.  Never fails. */
+int mlv_device_count(void);
+/* Text for a status code. */
+const char *mlv_status_string(int status);
+/* Last error text of this handle (valid until the next call on it); "" when none. */
+const char *mlv_last_error(mlv_index_t h);
+
+/*
+ * Create an empty index for `dim`-dimensional fp32 rows on CUDA device `device`.
+ * Replaces hnswlib.Index(space, dim) + init_index(...) (reference index.py:36-38); there is
+ * no max_elements cap -- `capacity_hint` rows are pre-allocated and the matrix grows by
+ * doubling.  Fails with MLV_E_NO_DEVICE when no GPU is present.
+ */
+int mlv_index_create(uint32_t dim, int metric, uint64_t capacity_hint, int device, mlv_index_t *out);
+int mlv_index_destroy(mlv_index_t h);
+
+/* Global row number of local row 0 (row shards of one namespace).  Default 0. */
+int mlv_index_set_row_base(mlv_index_t h, uint64_t row_base);
+
+/*
+ * Append n rows (host memory, row-major [n, dim] fp32).  Replaces add_items (reference
+ * index.py:65,158).  The data is copied (ownership stays with the caller, like
+ * np.array(data, dtype=float32) at index.py:65); cosine rows are normalised on the device.
+ * *first_row receives the local row of rows[0]; rows are numbered consecutively and never
+ * reused until mlv_index_compact (reference labels: index.py:56-60).
+ */
+int mlv_index_add(mlv_index_t h, const float *rows, uint64_t n, uint64_t *first_row);
+/* Same, rows already in device memory of this index's device. */
+int mlv_index_add_device(mlv_index_t h, const float *rows_dev, uint64_t n, uint64_t *first_row);
+/*
+ * Append n rows produced on the device by the deterministic counter-based generator that
+ * oracle/exact_scan.c::orc_fill_synthetic and oracle/synthetic.py restate bit for bit
+ * (generator row numbers first_gen_row .. first_gen_row+n-1; `scaled` != 0 multiplies each
+ * row by its per-row scale).  Benchmark / parity-test input path: 10M x 768 rows are
+ * produced in HBM without a 30 GB host copy.
+ */
+int mlv_index_add_synthetic(mlv_index_t h, uint64_t seed, uint64_t first_gen_row, uint64_t n, int scaled,
+                            uint64_t *first_row);
+
+/*
+ * Tombstone rows.  Replaces mark_deleted (reference index.py:80).  Rows >= info.rows or already
+ * tombstoned are ignored (the reference never passes them: index.py:77-82 pops the id map
+ * first).  *newly_deleted (nullable) receives how many rows changed state.
+ */
+int mlv_index_mark_deleted(mlv_index_t h, const uint64_t *rows, uint64_t n, uint64_t *newly_deleted);
+
+/*
+ * Drop tombstoned rows and renumber the survivors 0..live-1 in their old order (the
+ * per-namespace part of reference Index.rebuild, index.py:131-162, without re-uploading).
+ * old_to_new (nullable, host, info.rows entries) receives the new local row of every old
+ * row, or -1 for dropped rows.
+ */
+int mlv_index_compact(mlv_index_t h, int64_t *old_to_new, uint64_t *new_rows);
+/* Remove all rows (keeps the allocation). */
+int mlv_index_clear(mlv_index_t h);
+
+/*
+ * Exact k-nearest-neighbour search of nq queries (host memory, [nq, dim] fp32).  Replaces
+ * knn_query (reference index.py:111,115) and extends it with batches and a filter.
+ *   filter_bitmap  nullable; host uint32 words, bit (r & 31) of word (r >> 5) set = local row r
+ *                  may be returned (hnswlib-0.8 `filter=` semantics).  ceil(rows/32) words.
+ *   out_dists      [nq, k] hnswlib-form distances ascending; +inf padding
+ *   out_rows       [nq, k] row_base + local row; -1 padding
+ *   out_counts     [nq]    min(k, live-and-passing rows): the clamp the reference applies at
+ *                          index.py:103-107 falls out of the scan, hnswlib's "cannot fill k"
+ *                          RuntimeError (index.py:110-119) cannot occur.
+ * 1 <= k <= MLV_MAX_K.  Blocks until the results are in the host buffers.
+ */
+int mlv_index_search(mlv_index_t h, const float *queries, uint32_t nq, uint32_t k, const uint32_t *filter_bitmap,
+                     float *out_dists, int64_t *out_rows, int32_t *out_counts);
+/*
+ * Same with every pointer in device memory, enqueued on `stream` (a cudaStream_t; NULL =
+ * the index's own stream) without synchronising.  Queries must hold nq * dim floats.
+ */
+int mlv_index_search_device(mlv_index_t h, const float *queries_dev, uint32_t nq, uint32_t k,
+                            const uint32_t *filter_bitmap_dev, float *out_dists_dev, int64_t *out_rows_dev,
+                            int32_t *out_counts_dev, void *stream);
+
+/*
+ * Range (radius) search: every live (and passing) row with d <= radius, ascending (d, row).
+ * No reference code exists for it (README.md:121,215 only); semantics are defined by
+ * oracle/exact.py::range_stream.  Each query owns max_hits slots of out_dists / out_rows;
+ * out_counts[q] receives the TOTAL number of hits, which may exceed max_hits -- in that
+ * case the max_hits slots hold an unspecified subset and the caller retries with a larger
+ * buffer (the Python shim does).
+ */
+int mlv_index_range_search(mlv_index_t h, const float *queries, uint32_t nq, float radius,
+                           const uint32_t *filter_bitmap, uint64_t max_hits, float *out_dists, int64_t *out_rows,
+                           uint64_t *out_counts);
+
+/* Copy stored rows (as stored: normalised for cosine) back to the host, [n, dim]. */
+int mlv_index_get_rows(mlv_index_t h, const uint64_t *rows, uint64_t n, float *out);
+
+int mlv_index_info(mlv_index_t h, mlv_index_info_t *info);
+
+/*
+ * Merge the per-shard results of one sharded search: `n_lists`
+ * candidate lists per query, each k entries ascending, laid out [n_lists, nq, k] in device
+ * memory exactly as an NCCL all-gather of every rank's (out_dists, out_rows) leaves them
+ * (rank-major = ascending row_base).  Writes the global top-k per query.  Enqueued on
+ * `stream` of device `device`; does not synchronise.
+ */
+int mlv_merge_topk(int device, const float *dists_dev, const int64_t *rows_dev, uint32_t n_lists, uint32_t nq,
+                   uint32_t k, float *out_dists_dev, int64_t *out_rows_dev, int32_t *out_counts_dev, void *stream);
+
+/*
+ * Measurement hooks (bench.py / profiles): when enabled, every search records CUDA events
+ * around its scan kernel on the launching stream; mlv_index_scan_time_ms returns the sum
+ * of the completed scan-kernel durations since the last call and how many launches that
+ * covers, and resets both.
+ */
+int mlv_index_set_timing(mlv_index_t h, int enabled);
+int mlv_index_scan_time_ms(mlv_index_t h, double *total_ms, uint64_t *launches);
+/*
+ * Experimental scan tuning (profiling sweeps): key in {"cw" consumer warps per CTA, "stage_kb"
+ * ring-stage target size, "max_stages", "r" rows per warp step (0 = auto), "evict_first"
+ * (-1 auto / 0 / 1), "ctas" grid size (0 = one per SM)}.  Results never depend on these.
+ */
+int mlv_index_set_tuning(mlv_index_t h, const char *key, int value);
+/* Kernels launched by this handle since creation (scan + select + maintenance). */
+int mlv_index_kernel_launches(mlv_index_t h, uint64_t *launches);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MLV_INDEX_H */

@@ -1,0 +1,854 @@
+// mlv_index.cu -- C ABI (include/mlv_index.h) and host-side orchestration of the B200 exact-search
+// index.  Everything the reference does through hnswlib inside
+// src/mlvectordb/implementations/index.py (add_items :65, mark_deleted :80, knn_query :111) lands
+// here.  No CPU fallback: without a CUDA device mlv_index_create fails with MLV_E_NO_DEVICE.
+#include "../../include/mlv_index.h"
+
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <limits>
+#include <string>
+#include <utility>
+#include <vector>
+
+#include "common.cuh"
+#include "maint_kernels.cuh"
+#include "scan_kernel.cuh"
+#include "select_kernel.cuh"
+
+using namespace mlv;
+
+namespace {
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t bytes = 0;
+};
+struct HostBuf {
+    void* p = nullptr;
+    size_t bytes = 0;
+};
+
+struct ScanCfg {
+    int R, NQ, CW;
+    uint32_t T, S, stage_f4;
+    size_t smem;
+    int grid, threads;
+    int evict_first;
+};
+
+}  // namespace
+
+struct mlv_index {
+    int device = 0;
+    uint32_t dim = 0, ld = 0;
+    int metric = MLV_L2;
+    uint64_t rows = 0, capacity = 0, n_deleted = 0, row_base = 0;
+    float* d_rows = nullptr;
+    uint32_t* d_live = nullptr;
+    uint64_t live_words = 0;
+    cudaStream_t stream = nullptr;
+    int sm_count = 0;
+    size_t smem_optin = 0;
+    DevBuf d_qraw, d_q, d_keys0, d_keys1, d_filter, d_outd, d_outr, d_outc, d_misc, d_range;
+    HostBuf h_stage;
+    std::string err;
+    bool timing = false;
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> pending;
+    std::vector<cudaEvent_t> event_pool;
+    uint64_t launches = 0;
+    // tuning (mlv_index_set_tuning / MLV_SCAN_* environment)
+    int tune_cw = 8, tune_stage_kb = 32, tune_evict_first = -1, tune_r = 0, tune_max_stages = 8, tune_ctas = 0;
+};
+
+namespace {
+
+struct DeviceGuard {
+    int prev = -1;
+    bool ok = true;
+    explicit DeviceGuard(int dev) {
+        if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+        if (prev != dev) ok = cudaSetDevice(dev) == cudaSuccess;
+    }
+    ~DeviceGuard() {
+        int cur = -1;
+        if (prev >= 0 && cudaGetDevice(&cur) == cudaSuccess && cur != prev) cudaSetDevice(prev);
+    }
+};
+
+int fail(mlv_index* h, int status, const std::string& msg) {
+    if (h) h->err = msg;
+    return status;
+}
+int fail_cuda(mlv_index* h, cudaError_t e, const char* what) {
+    std::string m = std::string(what) + ": " + cudaGetErrorString(e);
+    cudaGetLastError();  // clear sticky-less error state
+    return fail(h, e == cudaErrorMemoryAllocation ? MLV_E_NOMEM : MLV_E_CUDA, m);
+}
+#define CK(h, call)                                        \
+    do {                                                   \
+        cudaError_t e__ = (call);                          \
+        if (e__ != cudaSuccess) return fail_cuda(h, e__, #call); \
+    } while (0)
+
+int ensure_dev(mlv_index* h, DevBuf& b, size_t bytes) {
+    if (b.bytes >= bytes) return MLV_OK;
+    if (b.p) CK(h, cudaFree(b.p));
+    b.p = nullptr;
+    b.bytes = 0;
+    size_t want = std::max(bytes, (size_t)4096);
+    CK(h, cudaMalloc(&b.p, want));
+    b.bytes = want;
+    return MLV_OK;
+}
+int ensure_host(mlv_index* h, HostBuf& b, size_t bytes) {
+    if (b.bytes >= bytes) return MLV_OK;
+    if (b.p) CK(h, cudaFreeHost(b.p));
+    b.p = nullptr;
+    b.bytes = 0;
+    size_t want = std::max(bytes, (size_t)4096);
+    CK(h, cudaMallocHost(&b.p, want));
+    b.bytes = want;
+    return MLV_OK;
+}
+void free_dev(DevBuf& b) {
+    if (b.p) cudaFree(b.p);
+    b.p = nullptr;
+    b.bytes = 0;
+}
+
+uint32_t pow2_ceil(uint32_t v) {
+    uint32_t p = 1;
+    while (p < v) p <<= 1;
+    return p;
+}
+
+int env_int(const char* name, int dflt) {
+    const char* s = getenv(name);
+    return (s && *s) ? atoi(s) : dflt;
+}
+
+// ---- capacity ----------------------------------------------------------------------------------
+int reserve_rows(mlv_index* h, uint64_t need) {
+    if (need <= h->capacity) return MLV_OK;
+    if (need >= 0xFFFFFFFEull) return fail(h, MLV_E_UNSUPPORTED, "more than 2^32-2 rows in one index shard");
+    uint64_t cap = std::max<uint64_t>({need, h->capacity * 2, 1024});
+    cap = (cap + 31) & ~31ull;
+    float* nrows = nullptr;
+    uint32_t* nlive = nullptr;
+    const size_t row_bytes = (size_t)h->ld * 4;
+    cudaError_t e = cudaMalloc(&nrows, cap * row_bytes);
+    if (e != cudaSuccess && cap > need) {  // doubling did not fit: take exactly what is needed
+        cudaGetLastError();
+        cap = (need + 31) & ~31ull;
+        e = cudaMalloc(&nrows, cap * row_bytes);
+    }
+    if (e != cudaSuccess) return fail_cuda(h, e, "cudaMalloc(row matrix)");
+    const uint64_t words = cap / 32;
+    e = cudaMalloc(&nlive, words * 4);
+    if (e != cudaSuccess) {
+        cudaFree(nrows);
+        return fail_cuda(h, e, "cudaMalloc(live bitmap)");
+    }
+    // zero: padding columns must read as 0 forever, unused rows' bits as "not live"
+    CK(h, cudaMemsetAsync(nrows, 0, cap * row_bytes, h->stream));
+    CK(h, cudaMemsetAsync(nlive, 0, words * 4, h->stream));
+    if (h->rows) {
+        CK(h, cudaMemcpyAsync(nrows, h->d_rows, h->rows * row_bytes, cudaMemcpyDeviceToDevice, h->stream));
+        CK(h, cudaMemcpyAsync(nlive, h->d_live, ((h->rows + 31) / 32) * 4, cudaMemcpyDeviceToDevice, h->stream));
+    }
+    CK(h, cudaStreamSynchronize(h->stream));
+    if (h->d_rows) cudaFree(h->d_rows);
+    if (h->d_live) cudaFree(h->d_live);
+    h->d_rows = nrows;
+    h->d_live = nlive;
+    h->capacity = cap;
+    h->live_words = words;
+    return MLV_OK;
+}
+
+int finish_append(mlv_index* h, uint64_t n, uint64_t* first_row) {
+    const uint64_t first = h->rows;
+    if (h->metric == MLV_COSINE) {
+        const int wpb = 8;
+        normalize_rows_kernel<<<(unsigned)((n + wpb - 1) / wpb), wpb * 32, 0, h->stream>>>(h->d_rows, first, n, h->ld);
+        h->launches++;
+    }
+    {
+        const uint64_t words = ((first + n - 1) >> 5) - (first >> 5) + 1;
+        set_live_range_kernel<<<(unsigned)std::min<uint64_t>((words + 255) / 256, 4096), 256, 0, h->stream>>>(h->d_live, first, n);
+        h->launches++;
+    }
+    CK(h, cudaGetLastError());
+    CK(h, cudaStreamSynchronize(h->stream));
+    h->rows += n;
+    if (first_row) *first_row = first;
+    return MLV_OK;
+}
+
+// ---- scan configuration ------------------------------------------------------------------------
+int choose_cfg(mlv_index* h, uint32_t nq, uint32_t k, bool range, ScanCfg* c) {
+    const uint32_t ld4 = h->ld / 4;
+    const size_t rowbytes = (size_t)h->ld * 4;
+    int CW = std::min(std::max(h->tune_cw, 1), SCAN_MAX_CW);
+    int R = h->tune_r ? h->tune_r : (ld4 <= 64 ? 4 : (ld4 <= 256 ? 2 : 1));
+    if (R != 1 && R != 2 && R != 4) R = 1;
+    int NQ = 1;
+    if (!range) {
+        while (NQ < 8 && (uint32_t)NQ < nq) NQ <<= 1;
+        while (NQ > 1 && ((size_t)NQ * k * CW * 8 > 65536 || R * NQ > 32)) NQ >>= 1;
+    }
+    const int max_stages = std::min(std::max(h->tune_max_stages, 2), 16);
+    const size_t fixed = (size_t)NQ * rowbytes + (range ? 0 : (size_t)CW * NQ * k * 8) + (size_t)max_stages * 24 + 256;
+    if (fixed + 2 * rowbytes > h->smem_optin)
+        return fail(h, MLV_E_UNSUPPORTED, "dimension too large for the shared-memory ring of this build");
+    const size_t avail = h->smem_optin - fixed;
+    const size_t group_bytes = (size_t)R * CW * rowbytes;
+    const size_t target = (size_t)std::max(h->tune_stage_kb, 1) * 1024;
+    uint64_t m = std::max<uint64_t>(1, target / group_bytes);
+    uint64_t T = (uint64_t)R * CW * m;
+    if (T * rowbytes * 2 > avail) {
+        T = (avail / 2 / rowbytes) / R * R;
+        if (T == 0) {
+            R = 1;
+            T = avail / 2 / rowbytes;
+        }
+        if (T == 0) return fail(h, MLV_E_UNSUPPORTED, "dimension too large for the shared-memory ring of this build");
+    }
+    const size_t stage = T * rowbytes;
+    if (stage >= (1u << 20)) return fail(h, MLV_E_UNSUPPORTED, "ring stage exceeds the mbarrier tx-count range");
+    uint32_t S = (uint32_t)std::min<size_t>(max_stages, avail / stage);
+    c->R = R;
+    c->NQ = NQ;
+    c->CW = CW;
+    c->T = (uint32_t)T;
+    c->S = S;
+    c->stage_f4 = (uint32_t)(stage / 16);
+    c->smem = (size_t)S * stage + (size_t)NQ * rowbytes + (range ? 0 : (size_t)CW * NQ * k * 8) + (size_t)S * 24;
+    const uint64_t n_tiles = (h->rows + T - 1) / T;
+    const int ctas = h->tune_ctas > 0 ? h->tune_ctas : h->sm_count;
+    c->grid = (int)std::min<uint64_t>(n_tiles, (uint64_t)ctas);
+    if (c->grid < 1) c->grid = 1;
+    c->threads = (CW + 1) * 32;
+    const size_t bytes = h->rows * rowbytes;
+    c->evict_first = h->tune_evict_first >= 0 ? h->tune_evict_first : (bytes > ((size_t)96 << 20) ? 1 : 0);
+    return MLV_OK;
+}
+
+template <int METRIC, int NQ, int R, bool RANGE>
+cudaError_t launch_scan_t(const ScanParams& p, const ScanCfg& c, cudaStream_t st) {
+    auto kern = scan_kernel<METRIC, NQ, R, RANGE>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c.smem);
+    if (e != cudaSuccess) return e;
+    kern<<<c.grid, c.threads, c.smem, st>>>(p);
+    return cudaGetLastError();
+}
+
+template <int METRIC, bool RANGE>
+cudaError_t launch_scan_m(const ScanParams& p, const ScanCfg& c, cudaStream_t st) {
+#define MLV_CASE(NQv, Rv) \
+    if (c.NQ == NQv && c.R == Rv) return launch_scan_t<METRIC, NQv, Rv, RANGE>(p, c, st);
+    MLV_CASE(1, 1) MLV_CASE(1, 2) MLV_CASE(1, 4)
+    if (!RANGE) {
+        MLV_CASE(2, 1) MLV_CASE(2, 2) MLV_CASE(2, 4)
+        MLV_CASE(4, 1) MLV_CASE(4, 2) MLV_CASE(4, 4)
+        MLV_CASE(8, 1) MLV_CASE(8, 2) MLV_CASE(8, 4)
+    }
+#undef MLV_CASE
+    return cudaErrorInvalidValue;
+}
+
+cudaError_t launch_scan(mlv_index* h, const ScanParams& p, const ScanCfg& c, bool range, cudaStream_t st) {
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    if (h->timing) {
+        for (cudaEvent_t* ev : {&e0, &e1}) {
+            if (!h->event_pool.empty()) {
+                *ev = h->event_pool.back();
+                h->event_pool.pop_back();
+            } else {
+                cudaError_t e = cudaEventCreate(ev);
+                if (e != cudaSuccess) return e;
+            }
+        }
+        cudaEventRecord(e0, st);
+    }
+    cudaError_t e;
+    const bool l2 = h->metric == MLV_L2;
+    if (range)
+        e = l2 ? launch_scan_m<METRIC_L2, true>(p, c, st) : launch_scan_m<METRIC_IP, true>(p, c, st);
+    else
+        e = l2 ? launch_scan_m<METRIC_L2, false>(p, c, st) : launch_scan_m<METRIC_IP, false>(p, c, st);
+    h->launches++;
+    if (h->timing) {
+        cudaEventRecord(e1, st);
+        h->pending.emplace_back(e0, e1);
+    }
+    return e;
+}
+
+__global__ void fill_empty_kernel(float* d, int64_t* r, int32_t* c, uint32_t nq, uint32_t k) {
+    const uint32_t total = nq * k;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        d[i] = __int_as_float(0x7f800000);
+        r[i] = -1;
+    }
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < nq; i += gridDim.x * blockDim.x) c[i] = 0;
+}
+
+bool g_select_attr_set[64] = {false};
+cudaError_t ensure_select_attrs(int device) {
+    if (device >= 0 && device < 64 && g_select_attr_set[device]) return cudaSuccess;
+    cudaError_t e = cudaFuncSetAttribute(select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SELECT_MAX_P * 8));
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(merge_pairs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SELECT_MAX_P * 8));
+    if (e != cudaSuccess) return e;
+    if (device >= 0 && device < 64) g_select_attr_set[device] = true;
+    return cudaSuccess;
+}
+
+// queries already prepared in h->d_q ([nq, ld]); all output pointers in device memory
+int search_prepared(mlv_index* h, uint32_t nq, uint32_t k, const uint32_t* filter_dev, float* out_d, int64_t* out_r,
+                    int32_t* out_c, cudaStream_t st) {
+    ScanCfg c;
+    int rc = choose_cfg(h, nq, k, false, &c);
+    if (rc != MLV_OK) return rc;
+    const uint32_t F = SELECT_MAX_P / k;  // lists one select CTA can fold (>= 8)
+    // bound the candidate scratch: chunk * grid * k keys
+    uint32_t chunk = (uint32_t)std::max<size_t>(1, ((size_t)64 << 20) / ((size_t)c.grid * k * 8));
+    chunk = std::max<uint32_t>(chunk / c.NQ * c.NQ, c.NQ);
+    chunk = std::min(chunk, nq);
+    rc = ensure_dev(h, h->d_keys0, (size_t)chunk * c.grid * k * 8);
+    if (rc != MLV_OK) return rc;
+    const uint32_t lists1 = ((uint32_t)c.grid + F - 1) / F;
+    if (lists1 > 1) {
+        rc = ensure_dev(h, h->d_keys1, (size_t)chunk * lists1 * k * 8);
+        if (rc != MLV_OK) return rc;
+    }
+    CK(h, ensure_select_attrs(h->device));
+
+    ScanParams p{};
+    p.rows = reinterpret_cast<const float4*>(h->d_rows);
+    p.n_rows = (uint32_t)h->rows;
+    p.ld4 = h->ld / 4;
+    p.tile_rows = c.T;
+    p.n_tiles = (uint32_t)((h->rows + c.T - 1) / c.T);
+    p.stages = c.S;
+    p.stage_f4 = c.stage_f4;
+    p.k = k;
+    p.live = h->n_deleted ? h->d_live : nullptr;
+    p.filter = filter_dev;
+    p.evict_first = c.evict_first;
+
+    for (uint32_t q0 = 0; q0 < nq; q0 += chunk) {
+        const uint32_t nchunk = std::min(chunk, nq - q0);
+        for (uint32_t g0 = 0; g0 < nchunk; g0 += c.NQ) {
+            p.queries = reinterpret_cast<const float4*>((float*)h->d_q.p + (size_t)(q0 + g0) * h->ld);
+            p.nq_valid = std::min<uint32_t>(c.NQ, nchunk - g0);
+            p.out_keys = (uint64_t*)h->d_keys0.p + (size_t)g0 * c.grid * k;
+            CK(h, launch_scan(h, p, c, false, st));
+        }
+        // fold the grid's lists into one per query
+        const uint64_t* in = (const uint64_t*)h->d_keys0.p;
+        uint64_t* bufs[2] = {(uint64_t*)h->d_keys1.p, (uint64_t*)h->d_keys0.p};
+        uint32_t n_lists = (uint32_t)c.grid;
+        int flip = 0;
+        for (;;) {
+            SelectParams sp{};
+            sp.in_keys = in;
+            sp.n_lists = n_lists;
+            sp.k = k;
+            sp.lists_per_block = std::min(F, n_lists);
+            sp.n_out_lists = (n_lists + sp.lists_per_block - 1) / sp.lists_per_block;
+            sp.P = pow2_ceil(std::max<uint32_t>(sp.lists_per_block * k, 2));
+            sp.final_pass = sp.n_out_lists == 1;
+            sp.out_keys = bufs[flip];
+            sp.out_dists = out_d + (size_t)q0 * k;
+            sp.out_rows = out_r + (size_t)q0 * k;
+            sp.out_counts = out_c + q0;
+            sp.row_base = h->row_base;
+            const int threads = (int)std::min<uint32_t>(SELECT_THREADS, std::max<uint32_t>(sp.P / 2, 32));
+            select_kernel<<<dim3(sp.n_out_lists, nchunk), threads, (size_t)sp.P * 8, st>>>(sp);
+            h->launches++;
+            CK(h, cudaGetLastError());
+            if (sp.final_pass) break;
+            in = sp.out_keys;
+            n_lists = sp.n_out_lists;
+            flip ^= 1;
+        }
+    }
+    return MLV_OK;
+}
+
+int prep_queries(mlv_index* h, const float* q_dev_raw, uint32_t nq, cudaStream_t st) {
+    int rc = ensure_dev(h, h->d_q, (size_t)nq * h->ld * 4);
+    if (rc != MLV_OK) return rc;
+    const int wpb = 4;
+    prep_queries_kernel<<<(nq + wpb - 1) / wpb, wpb * 32, 0, st>>>(q_dev_raw, (float*)h->d_q.p, nq, h->dim, h->ld,
+                                                                 h->metric == MLV_COSINE);
+    h->launches++;
+    CK(h, cudaGetLastError());
+    return MLV_OK;
+}
+
+}  // namespace
+
+// =================================================================================== C ABI
+extern "C" {
+
+int mlv_abi_version(void) { return MLV_ABI_VERSION; }
+
+int mlv_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+const char* mlv_status_string(int s) {
+    switch (s) {
+        case MLV_OK: return "ok";
+        case MLV_E_INVALID: return "invalid argument";
+        case MLV_E_CUDA: return "CUDA error";
+        case MLV_E_NOMEM: return "out of memory";
+        case MLV_E_UNSUPPORTED: return "unsupported by this build";
+        case MLV_E_NO_DEVICE: return "no CUDA device (there is no CPU fallback)";
+        default: return "unknown status";
+    }
+}
+
+const char* mlv_last_error(mlv_index_t h) { return h ? h->err.c_str() : "null handle"; }
+
+int mlv_index_create(uint32_t dim, int metric, uint64_t capacity_hint, int device, mlv_index_t* out) {
+    if (!out) return MLV_E_INVALID;
+    *out = nullptr;
+    if (dim == 0 || metric < MLV_L2 || metric > MLV_COSINE) return MLV_E_INVALID;
+    int ndev = mlv_device_count();
+    if (ndev <= 0) return MLV_E_NO_DEVICE;
+    if (device < 0 || device >= ndev) return MLV_E_INVALID;
+    mlv_index* h = new (std::nothrow) mlv_index();
+    if (!h) return MLV_E_NOMEM;
+    h->device = device;
+    h->dim = dim;
+    h->ld = (dim + 3u) & ~3u;
+    h->metric = metric;
+    h->tune_cw = env_int("MLV_SCAN_CW", h->tune_cw);
+    h->tune_stage_kb = env_int("MLV_SCAN_STAGE_KB", h->tune_stage_kb);
+    h->tune_evict_first = env_int("MLV_SCAN_EVICT_FIRST", h->tune_evict_first);
+    h->tune_r = env_int("MLV_SCAN_R", h->tune_r);
+    h->tune_max_stages = env_int("MLV_SCAN_MAX_STAGES", h->tune_max_stages);
+    h->tune_ctas = env_int("MLV_SCAN_CTAS", h->tune_ctas);
+    DeviceGuard g(device);
+    cudaDeviceProp prop;
+    cudaError_t e = g.ok ? cudaGetDeviceProperties(&prop, device) : cudaErrorInvalidDevice;
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        delete h;
+        return MLV_E_CUDA;
+    }
+    h->sm_count = prop.multiProcessorCount;
+    h->smem_optin = prop.sharedMemPerBlockOptin;
+    if (prop.major != 10) {
+        // sm_100a cubin only: fail loudly instead of at the first launch
+        cudaStreamDestroy(h->stream);
+        delete h;
+        return MLV_E_NO_DEVICE;
+    }
+    if (capacity_hint) {
+        int rc = reserve_rows(h, capacity_hint);
+        if (rc != MLV_OK) {
+            cudaStreamDestroy(h->stream);
+            delete h;
+            return rc;
+        }
+    }
+    *out = h;
+    return MLV_OK;
+}
+
+int mlv_index_destroy(mlv_index_t h) {
+    if (!h) return MLV_E_INVALID;
+    DeviceGuard g(h->device);
+    cudaStreamSynchronize(h->stream);
+    if (h->d_rows) cudaFree(h->d_rows);
+    if (h->d_live) cudaFree(h->d_live);
+    for (DevBuf* b : {&h->d_qraw, &h->d_q, &h->d_keys0, &h->d_keys1, &h->d_filter, &h->d_outd, &h->d_outr, &h->d_outc,
+                      &h->d_misc, &h->d_range})
+        free_dev(*b);
+    if (h->h_stage.p) cudaFreeHost(h->h_stage.p);
+    for (auto& pr : h->pending) {
+        cudaEventDestroy(pr.first);
+        cudaEventDestroy(pr.second);
+    }
+    for (auto ev : h->event_pool) cudaEventDestroy(ev);
+    cudaStreamDestroy(h->stream);
+    delete h;
+    return MLV_OK;
+}
+
+int mlv_index_set_row_base(mlv_index_t h, uint64_t row_base) {
+    if (!h) return MLV_E_INVALID;
+    h->row_base = row_base;
+    return MLV_OK;
+}
+
+int mlv_index_set_tuning(mlv_index_t h, const char* key, int value) {
+    if (!h || !key) return MLV_E_INVALID;
+    std::string k(key);
+    if (k == "cw") h->tune_cw = value;
+    else if (k == "stage_kb") h->tune_stage_kb = value;
+    else if (k == "evict_first") h->tune_evict_first = value;
+    else if (k == "r") h->tune_r = value;
+    else if (k == "max_stages") h->tune_max_stages = value;
+    else if (k == "ctas") h->tune_ctas = value;
+    else return fail(h, MLV_E_INVALID, "unknown tuning key " + k);
+    return MLV_OK;
+}
+
+static int add_common(mlv_index_t h, const float* rows, uint64_t n, uint64_t* first_row, cudaMemcpyKind kind) {
+    if (!h || (!rows && n)) return MLV_E_INVALID;
+    if (n == 0) {
+        if (first_row) *first_row = h->rows;
+        return MLV_OK;
+    }
+    DeviceGuard g(h->device);
+    int rc = reserve_rows(h, h->rows + n);
+    if (rc != MLV_OK) return rc;
+    float* dst = h->d_rows + h->rows * h->ld;
+    // pitched copy straight into the matrix; padding columns were zeroed at allocation
+    const uint64_t max_rows_per_copy = 1u << 20;  // cudaMemcpy2D height limits
+    for (uint64_t r0 = 0; r0 < n; r0 += max_rows_per_copy) {
+        const uint64_t nr = std::min(max_rows_per_copy, n - r0);
+        CK(h, cudaMemcpy2DAsync(dst + r0 * h->ld, (size_t)h->ld * 4, rows + r0 * h->dim, (size_t)h->dim * 4,
+                                (size_t)h->dim * 4, nr, kind, h->stream));
+    }
+    return finish_append(h, n, first_row);
+}
+
+int mlv_index_add(mlv_index_t h, const float* rows, uint64_t n, uint64_t* first_row) {
+    return add_common(h, rows, n, first_row, cudaMemcpyHostToDevice);
+}
+int mlv_index_add_device(mlv_index_t h, const float* rows_dev, uint64_t n, uint64_t* first_row) {
+    return add_common(h, rows_dev, n, first_row, cudaMemcpyDeviceToDevice);
+}
+
+int mlv_index_add_synthetic(mlv_index_t h, uint64_t seed, uint64_t first_gen_row, uint64_t n, int scaled,
+                            uint64_t* first_row) {
+    if (!h) return MLV_E_INVALID;
+    if (n == 0) {
+        if (first_row) *first_row = h->rows;
+        return MLV_OK;
+    }
+    DeviceGuard g(h->device);
+    int rc = reserve_rows(h, h->rows + n);
+    if (rc != MLV_OK) return rc;
+    const uint64_t key = splitmix64(seed), key2 = splitmix64(seed ^ 0xA5A5A5A5A5A5A5A5ull);
+    const uint64_t total = n * h->ld;
+    const unsigned blocks = (unsigned)std::min<uint64_t>((total + 255) / 256, (uint64_t)h->sm_count * 32);
+    fill_synthetic_kernel<<<blocks, 256, 0, h->stream>>>(h->d_rows, h->rows, n, h->dim, h->ld, key, key2, first_gen_row,
+                                                         scaled);
+    h->launches++;
+    CK(h, cudaGetLastError());
+    return finish_append(h, n, first_row);
+}
+
+int mlv_index_mark_deleted(mlv_index_t h, const uint64_t* rows, uint64_t n, uint64_t* newly_deleted) {
+    if (!h || (!rows && n)) return MLV_E_INVALID;
+    if (newly_deleted) *newly_deleted = 0;
+    if (n == 0 || h->rows == 0) return MLV_OK;
+    DeviceGuard g(h->device);
+    int rc = ensure_dev(h, h->d_misc, n * 8 + 8);
+    if (rc != MLV_OK) return rc;
+    unsigned long long* d_changed = (unsigned long long*)h->d_misc.p;
+    uint64_t* d_ids = (uint64_t*)h->d_misc.p + 1;
+    CK(h, cudaMemsetAsync(d_changed, 0, 8, h->stream));
+    CK(h, cudaMemcpyAsync(d_ids, rows, n * 8, cudaMemcpyHostToDevice, h->stream));
+    mark_deleted_kernel<<<(unsigned)std::min<uint64_t>((n + 255) / 256, 1024), 256, 0, h->stream>>>(h->d_live, d_ids, n,
+                                                                                                h->rows, d_changed);
+    h->launches++;
+    CK(h, cudaGetLastError());
+    unsigned long long changed = 0;
+    CK(h, cudaMemcpyAsync(&changed, d_changed, 8, cudaMemcpyDeviceToHost, h->stream));
+    CK(h, cudaStreamSynchronize(h->stream));
+    h->n_deleted += changed;
+    if (newly_deleted) *newly_deleted = changed;
+    return MLV_OK;
+}
+
+int mlv_index_compact(mlv_index_t h, int64_t* old_to_new, uint64_t* new_rows) {
+    if (!h) return MLV_E_INVALID;
+    DeviceGuard g(h->device);
+    const uint64_t n = h->rows;
+    if (n == 0 || h->n_deleted == 0) {
+        if (old_to_new)
+            for (uint64_t i = 0; i < n; i++) old_to_new[i] = (int64_t)i;
+        if (new_rows) *new_rows = n;
+        return MLV_OK;
+    }
+    const uint64_t n_words = (n + 31) / 32;
+    const size_t row_bytes = (size_t)h->ld * 4;
+    int rc = ensure_dev(h, h->d_misc, n_words * 8 + 8 + (old_to_new ? n * 8 : 0));
+    if (rc != MLV_OK) return rc;
+    uint64_t* d_total = (uint64_t*)h->d_misc.p;
+    uint64_t* d_wbase = d_total + 1;
+    int64_t* d_map = old_to_new ? (int64_t*)(d_wbase + n_words) : nullptr;
+    float* nrows = nullptr;
+    CK(h, cudaMalloc(&nrows, h->capacity * row_bytes));
+    cudaError_t e = cudaMemsetAsync(nrows, 0, h->capacity * row_bytes, h->stream);
+    if (e == cudaSuccess) {
+        live_prefix_kernel<<<1, 1024, 0, h->stream>>>(h->d_live, n, d_wbase, d_total);
+        const int wpb = 8;
+        compact_rows_kernel<<<(unsigned)((n + wpb - 1) / wpb), wpb * 32, 0, h->stream>>>(
+            reinterpret_cast<const float4*>(h->d_rows), reinterpret_cast<float4*>(nrows), h->d_live, d_wbase, n, h->ld / 4,
+            d_map);
+        h->launches += 2;
+        e = cudaGetLastError();
+    }
+    uint64_t total = 0;
+    if (e == cudaSuccess) e = cudaMemcpyAsync(&total, d_total, 8, cudaMemcpyDeviceToHost, h->stream);
+    if (e == cudaSuccess && old_to_new) e = cudaMemcpyAsync(old_to_new, d_map, n * 8, cudaMemcpyDeviceToHost, h->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+    if (e != cudaSuccess) {
+        cudaFree(nrows);
+        return fail_cuda(h, e, "compact");
+    }
+    cudaFree(h->d_rows);
+    h->d_rows = nrows;
+    h->rows = total;
+    h->n_deleted = 0;
+    CK(h, cudaMemsetAsync(h->d_live, 0, h->live_words * 4, h->stream));
+    if (total) {
+        const uint64_t words = (total + 31) / 32;
+        set_live_range_kernel<<<(unsigned)std::min<uint64_t>((words + 255) / 256, 4096), 256, 0, h->stream>>>(h->d_live, 0, total);
+        h->launches++;
+        CK(h, cudaGetLastError());
+    }
+    CK(h, cudaStreamSynchronize(h->stream));
+    if (new_rows) *new_rows = total;
+    return MLV_OK;
+}
+
+int mlv_index_clear(mlv_index_t h) {
+    if (!h) return MLV_E_INVALID;
+    DeviceGuard g(h->device);
+    if (h->d_live) {
+        CK(h, cudaMemsetAsync(h->d_live, 0, h->live_words * 4, h->stream));
+        CK(h, cudaStreamSynchronize(h->stream));
+    }
+    h->rows = 0;
+    h->n_deleted = 0;
+    return MLV_OK;
+}
+
+int mlv_index_search_device(mlv_index_t h, const float* queries_dev, uint32_t nq, uint32_t k,
+                            const uint32_t* filter_bitmap_dev, float* out_dists_dev, int64_t* out_rows_dev,
+                            int32_t* out_counts_dev, void* stream) {
+    if (!h || !queries_dev || !out_dists_dev || !out_rows_dev || !out_counts_dev || nq == 0 || k == 0) return fail(h, MLV_E_INVALID, "bad argument");
+    if (k > MLV_MAX_K) return fail(h, MLV_E_UNSUPPORTED, "k exceeds MLV_MAX_K");
+    DeviceGuard g(h->device);
+    cudaStream_t st = stream ? (cudaStream_t)stream : h->stream;
+    if (h->rows == h->n_deleted) {  // nothing live (reference index.py:99-104 returns [])
+        fill_empty_kernel<<<32, 256, 0, st>>>(out_dists_dev, out_rows_dev, out_counts_dev, nq, k);
+        h->launches++;
+        CK(h, cudaGetLastError());
+        return MLV_OK;
+    }
+    int rc = prep_queries(h, queries_dev, nq, st);
+    if (rc != MLV_OK) return rc;
+    return search_prepared(h, nq, k, filter_bitmap_dev, out_dists_dev, out_rows_dev, out_counts_dev, st);
+}
+
+int mlv_index_search(mlv_index_t h, const float* queries, uint32_t nq, uint32_t k, const uint32_t* filter_bitmap,
+                     float* out_dists, int64_t* out_rows, int32_t* out_counts) {
+    if (!h || !queries || !out_dists || !out_rows || !out_counts || nq == 0 || k == 0) return fail(h, MLV_E_INVALID, "bad argument");
+    if (k > MLV_MAX_K) return fail(h, MLV_E_UNSUPPORTED, "k exceeds MLV_MAX_K");
+    DeviceGuard g(h->device);
+    const size_t qbytes = (size_t)nq * h->dim * 4;
+    const size_t nk = (size_t)nq * k;
+    const size_t out_bytes = nk * 4 + nk * 8 + (size_t)nq * 4;
+    int rc;
+    if ((rc = ensure_host(h, h->h_stage, std::max(qbytes, out_bytes))) != MLV_OK) return rc;
+    if ((rc = ensure_dev(h, h->d_qraw, qbytes)) != MLV_OK) return rc;
+    if ((rc = ensure_dev(h, h->d_outr, nk * 8)) != MLV_OK) return rc;
+    if ((rc = ensure_dev(h, h->d_outd, nk * 4)) != MLV_OK) return rc;
+    if ((rc = ensure_dev(h, h->d_outc, (size_t)nq * 4)) != MLV_OK) return rc;
+    const uint32_t* filter_dev = nullptr;
+    if (filter_bitmap && h->rows) {
+        const size_t fb = ((h->rows + 31) / 32) * 4;
+        if ((rc = ensure_dev(h, h->d_filter, fb)) != MLV_OK) return rc;
+        CK(h, cudaMemcpyAsync(h->d_filter.p, filter_bitmap, fb, cudaMemcpyHostToDevice, h->stream));
+        filter_dev = (const uint32_t*)h->d_filter.p;
+    }
+    memcpy(h->h_stage.p, queries, qbytes);
+    CK(h, cudaMemcpyAsync(h->d_qraw.p, h->h_stage.p, qbytes, cudaMemcpyHostToDevice, h->stream));
+    rc = mlv_index_search_device(h, (const float*)h->d_qraw.p, nq, k, filter_dev, (float*)h->d_outd.p, (int64_t*)h->d_outr.p,
+                                 (int32_t*)h->d_outc.p, h->stream);
+    if (rc != MLV_OK) return rc;
+    // results come back through the pinned staging buffer: rows (8-byte aligned) first
+    char* hs = (char*)h->h_stage.p;
+    CK(h, cudaMemcpyAsync(hs, h->d_outr.p, nk * 8, cudaMemcpyDeviceToHost, h->stream));
+    CK(h, cudaMemcpyAsync(hs + nk * 8, h->d_outd.p, nk * 4, cudaMemcpyDeviceToHost, h->stream));
+    CK(h, cudaMemcpyAsync(hs + nk * 12, h->d_outc.p, (size_t)nq * 4, cudaMemcpyDeviceToHost, h->stream));
+    CK(h, cudaStreamSynchronize(h->stream));
+    memcpy(out_rows, hs, nk * 8);
+    memcpy(out_dists, hs + nk * 8, nk * 4);
+    memcpy(out_counts, hs + nk * 12, (size_t)nq * 4);
+    return MLV_OK;
+}
+
+int mlv_index_range_search(mlv_index_t h, const float* queries, uint32_t nq, float radius, const uint32_t* filter_bitmap,
+                           uint64_t max_hits, float* out_dists, int64_t* out_rows, uint64_t* out_counts) {
+    if (!h || !queries || !out_counts || nq == 0 || (max_hits && (!out_dists || !out_rows))) return fail(h, MLV_E_INVALID, "bad argument");
+    DeviceGuard g(h->device);
+    for (uint32_t q = 0; q < nq; q++) out_counts[q] = 0;
+    if (h->rows == h->n_deleted) return MLV_OK;
+    const size_t qbytes = (size_t)nq * h->dim * 4;
+    const uint64_t slots = std::max<uint64_t>(max_hits, 1);
+    int rc;
+    if ((rc = ensure_dev(h, h->d_qraw, qbytes)) != MLV_OK) return rc;
+    if ((rc = ensure_dev(h, h->d_range, (size_t)nq * slots * 8 + (size_t)nq * 8)) != MLV_OK) return rc;
+    unsigned long long* d_counts = (unsigned long long*)h->d_range.p;
+    uint64_t* d_keys = (uint64_t*)h->d_range.p + nq;
+    const uint32_t* filter_dev = nullptr;
+    if (filter_bitmap) {
+        const size_t fb = ((h->rows + 31) / 32) * 4;
+        if ((rc = ensure_dev(h, h->d_filter, fb)) != MLV_OK) return rc;
+        CK(h, cudaMemcpyAsync(h->d_filter.p, filter_bitmap, fb, cudaMemcpyHostToDevice, h->stream));
+        filter_dev = (const uint32_t*)h->d_filter.p;
+    }
+    CK(h, cudaMemcpyAsync(h->d_qraw.p, queries, qbytes, cudaMemcpyHostToDevice, h->stream));
+    CK(h, cudaMemsetAsync(d_counts, 0, (size_t)nq * 8, h->stream));
+    if ((rc = prep_queries(h, (const float*)h->d_qraw.p, nq, h->stream)) != MLV_OK) return rc;
+    ScanCfg c;
+    if ((rc = choose_cfg(h, 1, 1, true, &c)) != MLV_OK) return rc;
+    ScanParams p{};
+    p.rows = reinterpret_cast<const float4*>(h->d_rows);
+    p.n_rows = (uint32_t)h->rows;
+    p.ld4 = h->ld / 4;
+    p.tile_rows = c.T;
+    p.n_tiles = (uint32_t)((h->rows + c.T - 1) / c.T);
+    p.stages = c.S;
+    p.stage_f4 = c.stage_f4;
+    p.k = 1;
+    p.live = h->n_deleted ? h->d_live : nullptr;
+    p.filter = filter_dev;
+    p.evict_first = c.evict_first;
+    p.radius = radius;
+    p.max_hits = max_hits;
+    for (uint32_t q = 0; q < nq; q++) {
+        p.queries = reinterpret_cast<const float4*>((float*)h->d_q.p + (size_t)q * h->ld);
+        p.nq_valid = 1;
+        p.range_counts = d_counts + q;
+        p.range_keys = d_keys + (size_t)q * slots;
+        CK(h, launch_scan(h, p, c, true, h->stream));
+    }
+    std::vector<unsigned long long> counts(nq);
+    CK(h, cudaMemcpyAsync(counts.data(), d_counts, (size_t)nq * 8, cudaMemcpyDeviceToHost, h->stream));
+    CK(h, cudaStreamSynchronize(h->stream));
+    std::vector<uint64_t> keys;
+    for (uint32_t q = 0; q < nq; q++) {
+        out_counts[q] = counts[q];
+        const uint64_t got = std::min<uint64_t>(counts[q], max_hits);
+        if (!got) continue;
+        keys.resize(got);
+        CK(h, cudaMemcpy(keys.data(), d_keys + (size_t)q * slots, got * 8, cudaMemcpyDeviceToHost));
+        std::sort(keys.begin(), keys.end());  // (distance, row) ascending
+        for (uint64_t i = 0; i < got; i++) {
+            out_dists[(size_t)q * max_hits + i] = key_dist(keys[i]);
+            out_rows[(size_t)q * max_hits + i] = (int64_t)(h->row_base + key_row(keys[i]));
+        }
+    }
+    return MLV_OK;
+}
+
+int mlv_index_get_rows(mlv_index_t h, const uint64_t* rows, uint64_t n, float* out) {
+    if (!h || (n && (!rows || !out))) return MLV_E_INVALID;
+    DeviceGuard g(h->device);
+    for (uint64_t i = 0; i < n; i++) {
+        if (rows[i] >= h->rows) return fail(h, MLV_E_INVALID, "row out of range");
+        CK(h, cudaMemcpyAsync(out + i * h->dim, h->d_rows + rows[i] * h->ld, (size_t)h->dim * 4, cudaMemcpyDeviceToHost, h->stream));
+    }
+    CK(h, cudaStreamSynchronize(h->stream));
+    return MLV_OK;
+}
+
+int mlv_index_info(mlv_index_t h, mlv_index_info_t* info) {
+    if (!h || !info) return MLV_E_INVALID;
+    info->rows = h->rows;
+    info->live = h->rows - h->n_deleted;
+    info->capacity = h->capacity;
+    info->row_base = h->row_base;
+    size_t b = (size_t)h->capacity * h->ld * 4 + (size_t)h->live_words * 4;
+    for (const DevBuf* d : {&h->d_qraw, &h->d_q, &h->d_keys0, &h->d_keys1, &h->d_filter, &h->d_outd, &h->d_outr, &h->d_outc,
+                            &h->d_misc, &h->d_range})
+        b += d->bytes;
+    info->device_bytes = b;
+    info->dim = h->dim;
+    info->ld = h->ld;
+    info->metric = h->metric;
+    info->device = h->device;
+    return MLV_OK;
+}
+
+int mlv_merge_topk(int device, const float* dists_dev, const int64_t* rows_dev, uint32_t n_lists, uint32_t nq, uint32_t k,
+                   float* out_dists_dev, int64_t* out_rows_dev, int32_t* out_counts_dev, void* stream) {
+    if (!dists_dev || !rows_dev || !out_dists_dev || !out_rows_dev || !out_counts_dev || !n_lists || !nq || !k) return MLV_E_INVALID;
+    if ((uint64_t)n_lists * k > SELECT_MAX_P) return MLV_E_UNSUPPORTED;
+    DeviceGuard g(device);
+    if (!g.ok) return MLV_E_CUDA;
+    if (ensure_select_attrs(device) != cudaSuccess) return MLV_E_CUDA;
+    MergePairsParams p{};
+    p.dists = dists_dev;
+    p.rows = rows_dev;
+    p.n_lists = n_lists;
+    p.nq = nq;
+    p.k = k;
+    p.P = pow2_ceil(std::max<uint32_t>(n_lists * k, 2));
+    p.out_dists = out_dists_dev;
+    p.out_rows = out_rows_dev;
+    p.out_counts = out_counts_dev;
+    const int threads = (int)std::min<uint32_t>(SELECT_THREADS, std::max<uint32_t>(p.P / 2, 32));
+    merge_pairs_kernel<<<nq, threads, (size_t)p.P * 8, (cudaStream_t)stream>>>(p);
+    return cudaGetLastError() == cudaSuccess ? MLV_OK : MLV_E_CUDA;
+}
+
+int mlv_index_set_timing(mlv_index_t h, int enabled) {
+    if (!h) return MLV_E_INVALID;
+    h->timing = enabled != 0;
+    return MLV_OK;
+}
+
+int mlv_index_scan_time_ms(mlv_index_t h, double* total_ms, uint64_t* launches) {
+    if (!h) return MLV_E_INVALID;
+    DeviceGuard g(h->device);
+    double total = 0;
+    uint64_t n = 0;
+    for (auto& pr : h->pending) {
+        CK(h, cudaEventSynchronize(pr.second));
+        float ms = 0;
+        CK(h, cudaEventElapsedTime(&ms, pr.first, pr.second));
+        total += ms;
+        n++;
+        h->event_pool.push_back(pr.first);
+        h->event_pool.push_back(pr.second);
+    }
+    h->pending.clear();
+    if (total_ms) *total_ms = total;
+    if (launches) *launches = n;
+    return MLV_OK;
+}
+
+int mlv_index_kernel_launches(mlv_index_t h, uint64_t* launches) {
+    if (!h || !launches) return MLV_E_INVALID;
+    *launches = h->launches;
+    return MLV_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,297 @@
+// scan_kernel.cuh -- the hot path: one streaming pass over a namespace's row matrix with the
+// metric transform, tombstone/filter mask and top-k (or radius) selection fused in.
+//
+// Replaces hnswlib's knn_query (reference src/mlvectordb/implementations/index.py:111) by an
+// exact scan.  HBM-bound: every stored row is read once; distances never touch HBM.
+//
+// Structure (sm_100a):
+//   * persistent grid, one CTA per SM; CTA = CW consumer warps + 1 producer warp
+//   * the producer lane streams tiles of T consecutive rows into an S-stage shared-memory ring
+//     with 1-D bulk async copies (cp.async.bulk -> SASS UBLKCP) completing on mbarriers;
+//     consumers never issue a global load for row data
+//   * a consumer warp scores R rows x NQ queries per step: lane l accumulates the float4
+//     columns l, l+32, ... of each row against the queries held in shared memory, then a
+//     transposing butterfly leaves each (row, query) sum in one lane class
+//   * per-warp, per-query candidate lists (unsorted, k entries, shared memory) guarded by a
+//     register threshold: a row costs one compare unless it beats the current k-th best
+//   * at the end the block folds its warps' lists into one list per query and writes
+//     k keys per (query, block); select_kernel.cuh merges the blocks' lists.
+#pragma once
+#include "common.cuh"
+
+namespace mlv {
+
+constexpr int METRIC_L2 = 0;
+constexpr int METRIC_IP = 1;  // cosine == ip over rows/queries normalised at add/query time
+constexpr int SCAN_MAX_CW = 16;                          // consumer warps per CTA (runtime, <= this)
+constexpr int SCAN_MAX_THREADS = (SCAN_MAX_CW + 1) * 32;  // 544 -> ptxas may use up to 120 registers
+
+struct ScanParams {
+    const float4* rows;     // [n_rows, ld4]
+    uint32_t n_rows;
+    uint32_t ld4;           // float4 per row
+    uint32_t tile_rows;     // T (multiple of R)
+    uint32_t n_tiles;
+    uint32_t stages;        // S
+    uint32_t stage_f4;      // float4 per ring stage (= T * ld4)
+    const float4* queries;  // [nq_valid, ld4] device, zero padded, normalised for cosine
+    uint32_t nq_valid;      // <= NQ
+    uint32_t k;
+    const uint32_t* live;    // tombstone bitmap (bit set = live) or nullptr when nothing is deleted
+    const uint32_t* filter;  // caller's filter bitmap or nullptr
+    uint64_t* out_keys;      // top-k mode: [nq_valid][gridDim.x][k]
+    float radius;            // range mode
+    unsigned long long* range_counts;  // [nq_valid]
+    uint64_t* range_keys;              // [nq_valid][max_hits]
+    unsigned long long max_hits;
+    int evict_first;
+};
+
+struct StageMeta {
+    uint32_t row0;
+    int32_t n_rows;  // < 0: no more tiles
+};
+
+template <int METRIC>
+__device__ __forceinline__ float accum4(float acc, const float4& x, const float4& q) {
+    if (METRIC == METRIC_L2) {
+        float t0 = x.x - q.x, t1 = x.y - q.y, t2 = x.z - q.z, t3 = x.w - q.w;
+        acc = fmaf(t0, t0, acc);
+        acc = fmaf(t1, t1, acc);
+        acc = fmaf(t2, t2, acc);
+        acc = fmaf(t3, t3, acc);
+    } else {
+        acc = fmaf(x.x, q.x, acc);
+        acc = fmaf(x.y, q.y, acc);
+        acc = fmaf(x.z, q.z, acc);
+        acc = fmaf(x.w, q.w, acc);
+    }
+    return acc;
+}
+
+// Sum v[i] over the 32 lanes for every i in [0, V).  Afterwards the lane holds the total of
+// index lane_slot<V>(lane); V - 1 + (5 - log2 V) shuffles instead of 5 V.
+template <int V>
+__device__ __forceinline__ float transpose_reduce(float (&v)[V], int lane) {
+    int off = 16;
+#pragma unroll
+    for (int h = V / 2; h >= 1; h >>= 1) {
+        const bool upper = (lane & off) != 0;
+#pragma unroll
+        for (int i = 0; i < h; i++) {
+            float send = upper ? v[i] : v[i + h];
+            float keep = upper ? v[i + h] : v[i];
+            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+        }
+        off >>= 1;
+    }
+    float s = v[0];
+    for (; off >= 1; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+    return s;
+}
+template <int V>
+__device__ __forceinline__ int lane_slot(int lane) {
+    int idx = 0, off = 16;
+#pragma unroll
+    for (int h = V / 2; h >= 1; h >>= 1) {
+        if (lane & off) idx += h;
+        off >>= 1;
+    }
+    return idx;
+}
+
+// Replace the maximum (== oldthr) of list[0..k) by ckey; returns the new maximum.  Whole warp.
+__device__ __forceinline__ uint64_t list_replace_max(uint64_t* list, uint32_t k, uint64_t ckey, uint64_t oldthr,
+                                                     int lane) {
+    int match = -1;
+    for (uint32_t j = lane; j < k; j += 32)
+        if (match < 0 && list[j] == oldthr) match = (int)j;
+    unsigned b = __ballot_sync(0xffffffffu, match >= 0);
+    if (lane == __ffs(b) - 1) list[match] = ckey;
+    __syncwarp();
+    uint64_t m = 0;
+    for (uint32_t j = lane; j < k; j += 32) {
+        uint64_t v = list[j];
+        m = v > m ? v : m;
+    }
+    return warp_max_u64(m);
+}
+
+template <int METRIC, int NQ, int R, bool RANGE>
+__global__ void __launch_bounds__(SCAN_MAX_THREADS, 1) scan_kernel(const ScanParams p) {
+    constexpr int V = R * NQ;
+    static_assert(V <= 32 && (V & (V - 1)) == 0, "R*NQ must be a power of two <= 32");
+    extern __shared__ __align__(128) unsigned char smem[];
+
+    const int tid = threadIdx.x;
+    const int warp = tid >> 5;
+    const int lane = tid & 31;
+    const int CW = (blockDim.x >> 5) - 1;  // consumer warps; warp CW is the producer
+    const uint32_t S = p.stages;
+    const uint32_t ld4 = p.ld4;
+    const uint32_t k = p.k;
+
+    float4* ring = reinterpret_cast<float4*>(smem);
+    float4* qs = ring + (size_t)S * p.stage_f4;                                   // [NQ][ld4]
+    uint64_t* lists = reinterpret_cast<uint64_t*>(qs + (size_t)NQ * ld4);         // [CW][NQ][k]
+    uint64_t* full = lists + (RANGE ? 0 : (size_t)CW * NQ * k);                   // [S]
+    uint64_t* empty = full + S;                                                   // [S]
+    StageMeta* meta = reinterpret_cast<StageMeta*>(empty + S);                    // [S]
+
+    if (tid == 0) {
+        for (uint32_t s = 0; s < S; s++) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], CW);
+        }
+        mbar_fence_init();
+    }
+    // queries -> shared (missing queries of a short group repeat the last one; masked later)
+    for (uint32_t i = tid; i < NQ * ld4; i += blockDim.x) {
+        uint32_t qi = i / ld4, j = i - qi * ld4;
+        uint32_t src = qi < p.nq_valid ? qi : p.nq_valid - 1;
+        qs[i] = p.queries[(size_t)src * ld4 + j];
+    }
+    if (!RANGE)
+        for (uint32_t i = tid; i < (uint32_t)CW * NQ * k; i += blockDim.x) lists[i] = KEY_SENTINEL;
+    __syncthreads();
+
+    if (warp == CW) {
+        // ------------------------------------------------------------------ producer
+        if (lane == 0) {
+            uint32_t stage = 0, phase = 0;
+            const uint64_t pol = policy_evict_first();
+            for (uint32_t tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+                mbar_wait(&empty[stage], phase ^ 1);
+                const uint32_t row0 = tile * p.tile_rows;
+                const uint32_t n = min(p.tile_rows, p.n_rows - row0);
+                meta[stage].row0 = row0;
+                meta[stage].n_rows = (int32_t)n;
+                const uint32_t bytes = n * ld4 * 16u;
+                mbar_arrive_expect_tx(&full[stage], bytes);
+                const float4* src = p.rows + (size_t)row0 * ld4;
+                float4* dst = ring + (size_t)stage * p.stage_f4;
+                if (p.evict_first)
+                    bulk_g2s_hint(dst, src, bytes, &full[stage], pol);
+                else
+                    bulk_g2s(dst, src, bytes, &full[stage]);
+                if (++stage == S) {
+                    stage = 0;
+                    phase ^= 1;
+                }
+            }
+            mbar_wait(&empty[stage], phase ^ 1);
+            meta[stage].n_rows = -1;
+            mbar_arrive(&full[stage]);
+        }
+        return;
+    }
+
+    // ---------------------------------------------------------------------- consumers
+    const int slot = lane_slot<V>(lane);     // which (row-in-group, query) total this lane ends up with
+    const int my_r = slot / NQ;
+    const int my_q = slot - my_r * NQ;
+    const bool rep = (lane & (32 / V - 1)) == 0;  // one representative lane per slot
+    const bool q_ok = (uint32_t)my_q < p.nq_valid;
+    uint64_t thr = KEY_SENTINEL;                  // current k-th best of list (warp, my_q)
+    uint64_t* my_lists = lists + (size_t)warp * NQ * k;
+
+    uint32_t stage = 0, phase = 0, seq = 0;
+    for (;;) {
+        mbar_wait(&full[stage], phase);
+        const int n = meta[stage].n_rows;
+        if (n < 0) break;
+        const uint32_t row0 = meta[stage].row0;
+        const float4* tile = ring + (size_t)stage * p.stage_f4;
+        const uint32_t n_groups = ((uint32_t)n + R - 1) / R;
+        // rotate the group -> warp assignment per tile so short tiles do not always hit warp 0
+        uint32_t g = (uint32_t)(warp + CW - (int)(seq % (uint32_t)CW)) % (uint32_t)CW;
+        for (; g < n_groups; g += CW) {
+            const uint32_t base = g * R;
+            const uint32_t my_local = base + my_r;
+            const uint32_t row = row0 + my_local;
+            const uint32_t rowc = min(row, p.n_rows - 1);
+            uint32_t wl = 0xffffffffu, wf = 0xffffffffu;
+            if (p.live) wl = __ldg(p.live + (rowc >> 5));
+            if (p.filter) wf = __ldg(p.filter + (rowc >> 5));
+
+            float acc[V];
+#pragma unroll
+            for (int i = 0; i < V; i++) acc[i] = 0.f;
+            const float4* trow = tile + (size_t)base * ld4;
+#pragma unroll 2
+            for (uint32_t j = lane; j < ld4; j += 32) {
+                float4 q[NQ];
+#pragma unroll
+                for (int qi = 0; qi < NQ; qi++) q[qi] = qs[qi * ld4 + j];
+#pragma unroll
+                for (int r = 0; r < R; r++) {
+                    const float4 x = trow[r * ld4 + j];
+#pragma unroll
+                    for (int qi = 0; qi < NQ; qi++) acc[r * NQ + qi] = accum4<METRIC>(acc[r * NQ + qi], x, q[qi]);
+                }
+            }
+            const float s = transpose_reduce<V>(acc, lane);
+            const float dist = (METRIC == METRIC_IP) ? 1.0f - s : s;
+            const uint64_t key = make_key(dist, row);
+            const bool ok = rep && q_ok && my_local < (uint32_t)n && ((wl & wf) >> (rowc & 31) & 1u);
+            if (RANGE) {
+                if (ok && dist <= p.radius) {
+                    unsigned long long pos = atomicAdd(p.range_counts + my_q, 1ull);
+                    if (pos < p.max_hits) p.range_keys[(size_t)my_q * p.max_hits + pos] = key;
+                }
+            } else {
+                unsigned m = __ballot_sync(0xffffffffu, ok && key < thr);
+                while (m) {
+                    const int src = __ffs(m) - 1;
+                    m &= m - 1;
+                    const uint64_t ckey = shfl_u64(key, src);
+                    const uint64_t cthr = shfl_u64(thr, src);
+                    const int cq = __shfl_sync(0xffffffffu, my_q, src);
+                    if (ckey < cthr) {
+                        const uint64_t nthr = list_replace_max(my_lists + (size_t)cq * k, k, ckey, cthr, lane);
+                        if (my_q == cq) thr = nthr;
+                    }
+                }
+            }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty[stage]);
+        seq++;
+        if (++stage == S) {
+            stage = 0;
+            phase ^= 1;
+        }
+    }
+    if (RANGE) return;
+
+    // ------------------------------------------------- fold the CW warp lists into one per query
+    named_bar_sync(1, CW * 32);
+    for (int qi = warp; qi < NQ && (uint32_t)qi < p.nq_valid; qi += CW) {
+        uint64_t* home = lists + ((size_t)warp * NQ + qi) * k;
+        uint64_t m = 0;
+        for (uint32_t j = lane; j < k; j += 32) {
+            uint64_t v = home[j];
+            m = v > m ? v : m;
+        }
+        uint64_t hthr = warp_max_u64(m);
+        for (int ow = 0; ow < CW; ow++) {
+            if (ow == warp) continue;
+            const uint64_t* other = lists + ((size_t)ow * NQ + qi) * k;
+            for (uint32_t j0 = 0; j0 < k; j0 += 32) {
+                const uint64_t key = (j0 + lane < k) ? other[j0 + lane] : KEY_SENTINEL;
+                unsigned mm = __ballot_sync(0xffffffffu, key < hthr);
+                while (mm) {
+                    const int src = __ffs(mm) - 1;
+                    mm &= mm - 1;
+                    const uint64_t ckey = shfl_u64(key, src);
+                    if (ckey < hthr) hthr = list_replace_max(home, k, ckey, hthr, lane);
+                }
+            }
+        }
+        __syncwarp();
+        uint64_t* out = p.out_keys + ((size_t)qi * gridDim.x + blockIdx.x) * k;
+        for (uint32_t j = lane; j < k; j += 32) out[j] = home[j];
+    }
+}
+
+}  // namespace mlv

@@ -1,0 +1,201 @@
+"""``DeviceShard``: one namespace's (or one row shard's) device-resident row matrix.
+
+Thin object wrapper over the C ABI (``include/mlv_index.h``); holds no search logic of its own.
+It plays the role the per-namespace ``hnswlib.Index`` object plays in the reference
+(``src/mlvectordb/implementations/index.py:19,32-48``): rows are addressed by local row number
+(hnswlib labels, ``index.py:56-63``), ``add`` = ``add_items`` (``:65``), ``mark_deleted`` (``:80``),
+``search`` = ``knn_query`` (``:111``).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Tuple
+
+import numpy as np
+
+from . import _capi
+from ._capi import METRIC_CODE, IndexInfo, check
+
+ALIASES = {"euclidean": "l2", "dot": "ip", "inner_product": "ip"}
+
+
+def canonical_space(space: str) -> str:
+    s = ALIASES.get(space, space)
+    if s not in METRIC_CODE:
+        raise ValueError(f"unknown space {space!r}; expected one of l2, ip, cosine")
+    return s
+
+
+def pack_bitmap(mask: np.ndarray) -> np.ndarray:
+    """bool[rows] -> uint32 words, bit (r & 31) of word (r >> 5) = mask[r]."""
+    mask = np.ascontiguousarray(mask, dtype=bool)
+    n = mask.shape[0]
+    words = (n + 31) // 32
+    if n != words * 32:
+        padded = np.zeros(words * 32, dtype=bool)
+        padded[:n] = mask
+        mask = padded
+    return np.packbits(mask, bitorder="little").view(np.uint32)
+
+
+class DeviceShard:
+    def __init__(self, dim: int, space: str = "l2", capacity: int = 0, device: int = 0, row_base: int = 0):
+        self.space = canonical_space(space)
+        self.dim = int(dim)
+        self.device = int(device)
+        self._lib = _capi.lib()
+        self._h = C.c_void_p()
+        check(self._lib.mlv_index_create(self.dim, METRIC_CODE[self.space], int(capacity), self.device, C.byref(self._h)))
+        if row_base:
+            self.set_row_base(row_base)
+
+    # -- lifecycle ------------------------------------------------------------------------
+    def close(self) -> None:
+        if getattr(self, "_h", None) and self._h.value:
+            self._lib.mlv_index_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ck(self, status: int) -> None:
+        check(status, self._h)
+
+    def set_row_base(self, row_base: int) -> None:
+        self._ck(self._lib.mlv_index_set_row_base(self._h, int(row_base)))
+
+    def info(self) -> IndexInfo:
+        inf = IndexInfo()
+        self._ck(self._lib.mlv_index_info(self._h, C.byref(inf)))
+        return inf
+
+    @property
+    def rows(self) -> int:
+        return int(self.info().rows)
+
+    @property
+    def live(self) -> int:
+        return int(self.info().live)
+
+    # -- mutation -------------------------------------------------------------------------
+    def add(self, rows: np.ndarray) -> int:
+        x = np.ascontiguousarray(rows, dtype=np.float32)
+        if x.ndim == 1:
+            x = x[None, :]
+        if x.ndim != 2 or x.shape[1] != self.dim:
+            raise ValueError(f"expected rows of dimension {self.dim}, got shape {x.shape}")
+        first = C.c_uint64()
+        self._ck(self._lib.mlv_index_add(self._h, x.ctypes.data, x.shape[0], C.byref(first)))
+        return int(first.value)
+
+    def add_device(self, ptr: int, n: int) -> int:
+        first = C.c_uint64()
+        self._ck(self._lib.mlv_index_add_device(self._h, C.c_void_p(ptr), int(n), C.byref(first)))
+        return int(first.value)
+
+    def add_synthetic(self, seed: int, first_gen_row: int, n: int, scaled: bool = False) -> int:
+        first = C.c_uint64()
+        self._ck(self._lib.mlv_index_add_synthetic(self._h, int(seed), int(first_gen_row), int(n), int(bool(scaled)),
+                                                   C.byref(first)))
+        return int(first.value)
+
+    def mark_deleted(self, rows) -> int:
+        r = np.ascontiguousarray(rows, dtype=np.uint64)
+        changed = C.c_uint64()
+        self._ck(self._lib.mlv_index_mark_deleted(self._h, r.ctypes.data, r.shape[0], C.byref(changed)))
+        return int(changed.value)
+
+    def compact(self) -> np.ndarray:
+        """Drop tombstoned rows; returns old_to_new (int64, -1 for dropped rows)."""
+        n = self.rows
+        mapping = np.empty(n, dtype=np.int64)
+        new_rows = C.c_uint64()
+        self._ck(self._lib.mlv_index_compact(self._h, mapping.ctypes.data if n else None, C.byref(new_rows)))
+        return mapping
+
+    def clear(self) -> None:
+        self._ck(self._lib.mlv_index_clear(self._h))
+
+    # -- query ----------------------------------------------------------------------------
+    def _filter_words(self, filt) -> Optional[np.ndarray]:
+        if filt is None:
+            return None
+        f = np.asarray(filt)
+        n = self.rows
+        if f.dtype == np.uint32:
+            if f.shape[0] < (n + 31) // 32:
+                raise ValueError("filter bitmap shorter than ceil(rows/32) words")
+            return np.ascontiguousarray(f)
+        if f.shape[0] != n:
+            raise ValueError(f"filter mask has {f.shape[0]} entries for {n} rows")
+        return pack_bitmap(f.astype(bool))
+
+    def search(self, queries: np.ndarray, k: int, filt=None) -> Tuple[np.ndarray, np.ndarray, np.ndarray]:
+        """-> (dists f32 [nq,k] hnswlib-form ascending, rows i64 [nq,k], counts i32 [nq])."""
+        q = np.ascontiguousarray(queries, dtype=np.float32)
+        if q.ndim == 1:
+            q = q[None, :]
+        if q.ndim != 2 or q.shape[1] != self.dim:
+            raise ValueError(f"expected queries of dimension {self.dim}, got shape {q.shape}")
+        nq = q.shape[0]
+        dists = np.empty((nq, k), dtype=np.float32)
+        rows = np.empty((nq, k), dtype=np.int64)
+        counts = np.empty(nq, dtype=np.int32)
+        fw = self._filter_words(filt)
+        self._ck(self._lib.mlv_index_search(self._h, q.ctypes.data, nq, int(k), fw.ctypes.data if fw is not None else None,
+                                            dists.ctypes.data, rows.ctypes.data, counts.ctypes.data))
+        return dists, rows, counts
+
+    def search_device(self, q_ptr: int, nq: int, k: int, out_d_ptr: int, out_r_ptr: int, out_c_ptr: int,
+                      filter_ptr: int = 0, stream: int = 0) -> None:
+        """All pointers are device addresses (e.g. ``tensor.data_ptr()``); enqueues on ``stream``."""
+        self._ck(self._lib.mlv_index_search_device(
+            self._h, C.c_void_p(q_ptr), int(nq), int(k), C.c_void_p(filter_ptr) if filter_ptr else None,
+            C.c_void_p(out_d_ptr), C.c_void_p(out_r_ptr), C.c_void_p(out_c_ptr), C.c_void_p(stream) if stream else None))
+
+    def range_search(self, queries: np.ndarray, radius: float, filt=None, max_hits: int = 1024):
+        """-> list per query of (dists f32 [hits], rows i64 [hits]) ascending (d, row)."""
+        q = np.ascontiguousarray(queries, dtype=np.float32)
+        if q.ndim == 1:
+            q = q[None, :]
+        if q.ndim != 2 or q.shape[1] != self.dim:
+            raise ValueError(f"expected queries of dimension {self.dim}, got shape {q.shape}")
+        nq = q.shape[0]
+        fw = self._filter_words(filt)
+        while True:
+            dists = np.empty((nq, max_hits), dtype=np.float32)
+            rows = np.empty((nq, max_hits), dtype=np.int64)
+            counts = np.zeros(nq, dtype=np.uint64)
+            self._ck(self._lib.mlv_index_range_search(
+                self._h, q.ctypes.data, nq, C.c_float(radius), fw.ctypes.data if fw is not None else None, int(max_hits),
+                dists.ctypes.data, rows.ctypes.data, counts.ctypes.data))
+            most = int(counts.max()) if nq else 0
+            if most <= max_hits:
+                return [(dists[i, : int(counts[i])].copy(), rows[i, : int(counts[i])].copy()) for i in range(nq)]
+            max_hits = most  # the call reports the total: one retry with an exact buffer
+
+    def get_rows(self, rows) -> np.ndarray:
+        r = np.ascontiguousarray(rows, dtype=np.uint64)
+        out = np.empty((r.shape[0], self.dim), dtype=np.float32)
+        self._ck(self._lib.mlv_index_get_rows(self._h, r.ctypes.data, r.shape[0], out.ctypes.data))
+        return out
+
+    # -- measurement hooks ------------------------------------------------------------------
+    def set_timing(self, enabled: bool) -> None:
+        self._ck(self._lib.mlv_index_set_timing(self._h, int(enabled)))
+
+    def scan_time_ms(self) -> Tuple[float, int]:
+        ms, n = C.c_double(), C.c_uint64()
+        self._ck(self._lib.mlv_index_scan_time_ms(self._h, C.byref(ms), C.byref(n)))
+        return float(ms.value), int(n.value)
+
+    def set_tuning(self, key: str, value: int) -> None:
+        self._ck(self._lib.mlv_index_set_tuning(self._h, key.encode(), int(value)))
+
+    def kernel_launches(self) -> int:
+        n = C.c_uint64()
+        self._ck(self._lib.mlv_index_kernel_launches(self._h, C.byref(n)))
+        return int(n.value)

@@ -1,0 +1,232 @@
+"""The drop-in boundary on a GPU: ``GpuIndex`` behind the reference's call patterns.
+
+* the reference's own index / query-processor test cases (reference ``tests/test_index.py``,
+  ``tests/test_query_processor.py``) restated with ``Index`` swapped for ``GpuIndex``;
+* replay of ``tests/golden/reference_wrappers.json`` -- what the UNMODIFIED reference wrappers
+  returned (over the exact hnswlib stand-in) for scripted add/remove/rebuild/search sequences.
+"""
+import json
+import os
+from uuid import UUID
+
+import numpy as np
+import pytest
+
+from oracle import exact, synthetic
+from tests._refshim import QueryProcessor, Storage, Vector
+
+pytestmark = pytest.mark.gpu
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "reference_wrappers.json")
+
+
+def _index(space, **kw):
+    from mlvectordb_b200 import GpuIndex
+    return GpuIndex(space=space, **kw)
+
+
+def _dto(values):
+    from mlvectordb_b200 import VectorDTO
+    return VectorDTO(values=values, metadata={})
+
+
+# ------------------------------------------------------------------ reference tests/test_index.py
+@pytest.fixture(params=[2, 5, 100])
+def sample_vectors(request):
+    np.random.seed(42)
+    data = np.random.rand(request.param, 16).astype(np.float32)
+    return [Vector(values=v.tolist(), metadata={"i": i}) for i, v in enumerate(data)]
+
+
+def test_add_and_search_various_sizes(sample_vectors):
+    index = _index("l2")
+    index.add(sample_vectors, "varied_ns")
+    q = sample_vectors[0].values + np.random.normal(0, 0.01, size=sample_vectors[0].values.shape)
+    results = index.search(_dto(q), top_k=5, namespace="varied_ns", metric="l2")   # fp64 query like the reference test
+    assert len(results) > 0
+    ids = {v.id for v in sample_vectors}
+    for r in results:
+        assert r.vector_id in ids
+        assert isinstance(r.score, float)
+        assert r.score >= 0.0
+    assert results[0].vector_id == sample_vectors[0].id
+    assert len(results) == min(5, len(sample_vectors))
+
+
+def test_remove_and_search_various_sizes(sample_vectors):
+    index = _index("l2")
+    index.add(sample_vectors, "remove_ns")
+    to_remove = [v.id for v in sample_vectors[:2]]
+    index.remove(to_remove, "remove_ns")
+    results = index.search(_dto(sample_vectors[0].values), top_k=5, namespace="remove_ns", metric="l2")
+    assert not (set(to_remove) & {r.vector_id for r in results})
+    assert len(results) == min(5, len(sample_vectors) - 2)
+
+
+def test_rebuild_many(sample_vectors):
+    index = _index("l2")
+    half = len(sample_vectors) // 2 or 1
+    source = {"ns1": sample_vectors[:half], "ns2": sample_vectors[half:]}
+    index.rebuild(source, metric="l2")
+    for ns in source:
+        results = index.search(_dto(source[ns][0].values), top_k=3, namespace=ns, metric="l2")
+        assert len(results) > 0
+        assert results[0].vector_id == source[ns][0].id
+
+
+# ------------------------------------------------------- reference tests/test_query_processor.py
+@pytest.fixture
+def processor():
+    return QueryProcessor(Storage(), _index("cosine"))
+
+
+def _v(x, y, z, label):
+    from mlvectordb_b200 import VectorDTO
+    return VectorDTO(values=[x, y, z], metadata={"label": label})
+
+
+def test_find_similar_correctness(processor):
+    processor.upsert_many([_v(1, 0, 0, "A"), _v(0, 1, 0, "B"), _v(0.8, 0.2, 0, "C")])
+    results = processor.find_similar(_dto([0.9, 0.1, 0]), top_k=3)
+    assert [r["metadata"]["label"] for r in results] == ["A", "C", "B"]
+    q = np.array([0.9, 0.1, 0])
+    sims = [float(np.dot(q, r["values"]) / (np.linalg.norm(q) * np.linalg.norm(r["values"]))) for r in results]
+    assert sims == pytest.approx(sorted(sims, reverse=True), rel=1e-4)
+    assert [r["score"] for r in results] == pytest.approx(sims, rel=1e-5, abs=1e-6)
+
+
+def test_namespace_isolation(processor):
+    processor.insert(_v(1, 0, 0, "X"), namespace="alpha")
+    processor.insert(_v(0, 1, 0, "Y"), namespace="beta")
+    r1 = processor.find_similar(_dto([1, 0, 0]), top_k=1, namespace="alpha")
+    r2 = processor.find_similar(_dto([1, 0, 0]), top_k=1, namespace="beta")
+    assert r1[0]["metadata"]["label"] == "X" and r2[0]["metadata"]["label"] == "Y"
+    assert r1[0]["id"] != r2[0]["id"]
+
+
+@pytest.mark.parametrize("auto_compact", [True, False])
+def test_delete_removes_from_storage_and_index(auto_compact):
+    processor = QueryProcessor(Storage(), _index("cosine", auto_compact=auto_compact))
+    processor.upsert_many([_v(1, 0, 0, "A"), _v(0, 1, 0, "B")])
+    processor.insert(_v(0, 0, 1, "other"), namespace="untouched")
+    before = processor.find_similar(_dto([1, 0, 0]), top_k=2)
+    assert len(before) == 2
+    processor.delete([before[0]["id"]])          # ratio 0.5 >= 0.2: compaction or the reference rebuild path
+    after = processor.find_similar(_dto([1, 0, 0]), top_k=2)
+    assert [r["metadata"]["label"] for r in after] == ["B"]
+    other = processor.find_similar(_dto([0, 0, 1]), top_k=1, namespace="untouched")
+    if auto_compact:
+        assert other and other[0]["metadata"]["label"] == "other"   # Q6 fixed: other namespaces survive
+    else:
+        assert other == []                                           # reference behaviour: rebuild wipes them
+
+
+def test_search_with_many_vectors(processor):
+    from mlvectordb_b200 import VectorDTO
+    np.random.seed(42)
+    processor.upsert_many([VectorDTO(values=np.random.rand(10).tolist(), metadata={"label": f"V{i}"}) for i in range(100)])
+    results = processor.find_similar(_dto(np.random.rand(10).tolist()), top_k=5)
+    assert len(results) == 5
+    assert all(isinstance(r["id"], UUID) for r in results)
+
+
+def test_search_with_few_vectors(processor):
+    processor.upsert_many([_v(1, 0, 0, "A"), _v(0, 1, 0, "B")])
+    results = processor.find_similar(_dto([1, 0, 0]), top_k=5)
+    assert len(results) == 2
+    assert results[0]["metadata"]["label"] == "A"
+
+
+# --------------------------------------------------------------------------- golden replay
+def _golden():
+    with open(GOLDEN) as f:
+        return json.load(f)
+
+
+@pytest.mark.parametrize("case", _golden()["cases"], ids=lambda c: c["name"])
+def test_golden_reference_wrapper_replay(case):
+    d, seed = case["dim"], case["seed"]
+    index = _index(case["space"], auto_compact=False)     # strict reference flag behaviour
+    vec_of, ordinal_of = {}, {}
+    records = iter(case["records"])
+    for op in case["ops"]:
+        kind = op["op"]
+        if kind == "add":
+            data = synthetic.rows(seed, op["first"], op["n"], d, scaled=case.get("scaled", False))
+            vs = [Vector(values=row) for row in data]
+            for i, v in enumerate(vs):
+                vec_of[(op["ns"], op["first"] + i)] = v
+                ordinal_of[v.id] = op["first"] + i
+            index.add(vs, op["ns"])
+        elif kind == "remove":
+            ids = [vec_of[(op["ns"], o)].id for o in op["ordinals"] if (op["ns"], o) in vec_of]
+            index.remove(ids, op["ns"])
+            rec = next(records)
+            assert rec["op"] == "rebuild_required"
+            assert index.is_rebuild_required(op["ns"]) == rec["value"]
+        elif kind == "rebuild":
+            index.rebuild({ns: [vec_of[(ns, o)] for o in ords] for ns, ords in op["source"].items()}, metric=op["metric"])
+        elif kind == "search":
+            rec = next(records)
+            if "query_row" in op:
+                qv = synthetic.rows(seed, op["query_row"], 1, d, scaled=case.get("scaled", False))[0]
+            else:
+                qv = synthetic.queries(seed, op["query"] + 1, d)[op["query"]]
+            if op.get("as_list"):
+                qv = [float(x) for x in qv]
+            res = index.search(_dto(qv), top_k=op["k"], namespace=op["ns"], metric=op["metric"])
+            got_ord = [ordinal_of[r.vector_id] for r in res]
+            got_scores = [r.score for r in res]
+            assert len(res) == len(rec["ordinals"])
+            if op["metric"] == "cosine":      # scores are similarities (descending): compare as distances
+                msg = exact.check_topk_parity(got_ord, [1 - s for s in got_scores], rec["ordinals"],
+                                              [1 - s for s in rec["scores"]])
+            else:
+                msg = exact.check_topk_parity(got_ord, got_scores, rec["ordinals"], rec["scores"])
+            assert msg is None, f"{case['name']} {op}: {msg}"
+            assert all(isinstance(s, float) for s in got_scores)
+
+
+def test_golden_query_processor():
+    g = _golden()["query_processor"]
+    from mlvectordb_b200 import VectorDTO
+    qp = QueryProcessor(Storage(), _index("cosine"))
+    qp.upsert_many([VectorDTO(values=v, metadata={"label": l}) for v, l in g["vectors"]])
+    res = qp.find_similar(_dto(g["query"]), top_k=g["k"])
+    assert [r["metadata"]["label"] for r in res] == g["labels"]
+    assert [r["score"] for r in res] == pytest.approx(g["scores"], rel=1e-5, abs=1e-6)
+
+
+# --------------------------------------------------------------------------- additive surface
+def test_additive_surface_batch_filter_range_dimension():
+    index = _index("cosine")
+    X = synthetic.rows(8, 0, 4000, 64, scaled=True)
+    ids = index.add_matrix(X, "bulk")
+    assert ids.shape == (4000, 16) and index.dimension("bulk") == 64 and index.dimension("nope") is None
+    Q = synthetic.queries(8, 6, 64)
+    rows, scores, counts = index.search_batch(Q, 10, "bulk", metric="cosine")
+    L, D = exact.knn(X, Q, 10, "cosine")
+    for i in range(6):
+        assert exact.check_topk_parity(rows[i], 1 - scores[i].astype(np.float64), L[i], D[i]) is None
+    # single-query API agrees with the batch API and returns the bulk-assigned UUIDs
+    res = index.search(_dto(Q[0]), top_k=10, namespace="bulk", metric="cosine")
+    assert [r.vector_id for r in res] == [UUID(bytes=ids[r].tobytes()) for r in rows[0]]
+    # filter by predicate on the id, and by mask
+    allowed = {UUID(bytes=ids[r].tobytes()) for r in range(0, 4000, 7)}
+    res_f = index.search(_dto(Q[0]), top_k=5, namespace="bulk", metric="cosine", filter=lambda u: u in allowed)
+    mask = np.zeros(4000, bool)
+    mask[::7] = True
+    Lf, Df = exact.knn(X, Q[:1], 5, "cosine", allow=mask)
+    assert [r.vector_id for r in res_f] == [UUID(bytes=ids[r].tobytes()) for r in Lf[0]]
+    # range: similarity >= 1 - radius
+    radius = float(D[0][4]) + 1e-4
+    hits = index.range_search(_dto(Q[0]), radius, "bulk", "cosine")
+    assert [h.vector_id for h in hits[:5]] == [r.vector_id for r in res[:5]]
+    assert all(h.score >= 1 - radius - 1e-5 for h in hits)
+    # remove through the lazily built id map of a bulk-loaded namespace
+    index.remove([res[0].vector_id], "bulk")
+    res2 = index.search(_dto(Q[0]), top_k=10, namespace="bulk", metric="cosine")
+    assert res[0].vector_id not in {r.vector_id for r in res2}
+    info = index.info("bulk")
+    assert info["rows"] == 4000 and info["live"] == 3999 and info["tombstones"] == 1
+    index.close()
