@@ -1,0 +1,129 @@
+"""Row-sharded exact search across the GPUs of one box.
+
+One process per GPU (``torch.distributed``, NCCL over NVLink/NVSwitch).  Rank r owns the
+contiguous row block ``[r * ceil(N/G), min(N, (r+1) * ceil(N/G)))`` of the namespace as one
+``DeviceShard`` whose ``row_base`` is the block start, so every local result already carries
+global rows.  A search is:
+
+    local scan + top-k on every rank  ->  all-gather of the k candidates per query
+    ((fp32 distance, int64 row) pairs, ``G * nq * k * 12`` bytes)  ->  ``mlv_merge_topk`` on every rank
+
+The exchange is the only collective on the path; it is latency-bound (120 bytes per rank for a
+batch-1, k=10 query), so it is issued as two ``all_gather_into_tensor`` calls on the stream the
+scan ran on.  The reference has no counterpart (single process, README sketch only:
+``README.md:142-155``); the identity it relies on -- top-k of a union of row shards equals the
+merge of the shards' top-k -- is checked in ``tests/test_gpu_parity.py``.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Callable, Optional, Tuple
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from . import _capi
+
+
+def shard_range(total_rows: int, rank: int, world: int) -> Tuple[int, int]:
+    """Contiguous row block of ``rank``: ceil(N/G) rows each, the tail ranks may be short or empty."""
+    per = -(-total_rows // world)
+    lo = min(total_rows, rank * per)
+    hi = min(total_rows, lo + per)
+    return lo, hi
+
+
+def gather_candidates(dists: torch.Tensor, rows: torch.Tensor, group=None) -> Tuple[torch.Tensor, torch.Tensor]:
+    """All-gather every rank's ``[nq, k]`` candidates -> ``[G, nq, k]`` (rank-major = ascending row_base).
+
+    Works on any backend (NCCL on the GPUs, gloo in the CPU tests): the layout is what
+    ``mlv_merge_topk`` consumes.
+    """
+    world = dist.get_world_size(group)
+    nq, k = dists.shape
+    # concatenation along dim 0 is the one output form every backend accepts; viewed as [G, nq, k]
+    gd = torch.empty((world * nq, k), dtype=dists.dtype, device=dists.device)
+    gr = torch.empty((world * nq, k), dtype=rows.dtype, device=rows.device)
+    dist.all_gather_into_tensor(gd, dists.contiguous(), group=group)
+    dist.all_gather_into_tensor(gr, rows.contiguous(), group=group)
+    return gd.view(world, nq, k), gr.view(world, nq, k)
+
+
+def merge_topk_device(gd: torch.Tensor, gr: torch.Tensor, k: int):
+    """``mlv_merge_topk`` on the current CUDA stream; inputs ``[G, nq, k]`` device tensors."""
+    G, nq, kk = gd.shape
+    assert kk == k and gd.is_cuda and gd.dtype == torch.float32 and gr.dtype == torch.int64
+    out_d = torch.empty((nq, k), dtype=torch.float32, device=gd.device)
+    out_r = torch.empty((nq, k), dtype=torch.int64, device=gd.device)
+    out_c = torch.empty((nq,), dtype=torch.int32, device=gd.device)
+    stream = torch.cuda.current_stream(gd.device).cuda_stream
+    st = _capi.lib().mlv_merge_topk(gd.device.index, C.c_void_p(gd.data_ptr()), C.c_void_p(gr.data_ptr()), G, nq, k,
+                                    C.c_void_p(out_d.data_ptr()), C.c_void_p(out_r.data_ptr()),
+                                    C.c_void_p(out_c.data_ptr()), C.c_void_p(stream))
+    _capi.check(st)
+    return out_d, out_r, out_c
+
+
+class ShardedIndex:
+    """One namespace, rows sharded over the ranks of ``group``.  Every rank calls every method."""
+
+    def __init__(self, dim: int, space: str, total_rows: int, device: Optional[torch.device] = None, group=None,
+                 local_search: Optional[Callable] = None, merge: Optional[Callable] = None):
+        self.dim, self.space, self.total_rows = int(dim), space, int(total_rows)
+        self.group = group
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.lo, self.hi = shard_range(self.total_rows, self.rank, self.world)
+        self.device = device
+        self.shard = None
+        # the two device steps are injectable so the collective plumbing can be exercised on CPU (gloo)
+        self._local_search = local_search or self._device_local_search
+        self._merge = merge or merge_topk_device
+        self.merge_launches = 0
+        if local_search is None:
+            from .shard import DeviceShard
+            self.shard = DeviceShard(dim, space, capacity=max(self.hi - self.lo, 1), device=device.index, row_base=self.lo)
+
+    # -- data -------------------------------------------------------------------------------
+    def add_synthetic(self, seed: int, scaled: bool) -> None:
+        if self.hi > self.lo:
+            self.shard.add_synthetic(seed, self.lo, self.hi - self.lo, scaled)
+
+    def add_rows(self, local_rows: np.ndarray) -> None:
+        assert local_rows.shape[0] == self.hi - self.lo
+        if self.hi > self.lo:
+            self.shard.add(local_rows)
+
+    # -- search -----------------------------------------------------------------------------
+    def _device_local_search(self, q: torch.Tensor, k: int):
+        nq = q.shape[0]
+        d = torch.empty((nq, k), dtype=torch.float32, device=q.device)
+        r = torch.empty((nq, k), dtype=torch.int64, device=q.device)
+        c = torch.empty((nq,), dtype=torch.int32, device=q.device)
+        stream = torch.cuda.current_stream(q.device).cuda_stream
+        self.shard.search_device(q.data_ptr(), nq, k, d.data_ptr(), r.data_ptr(), c.data_ptr(), stream=stream)
+        return d, r, c
+
+    def search_device(self, q: torch.Tensor, k: int):
+        """``q``: [nq, dim] fp32 tensor on this rank's device (same on every rank).  Returns the
+        global top-k ``(dists [nq,k], rows [nq,k], counts [nq])`` on every rank, nothing synchronised."""
+        d, r, c = self._local_search(q, k)
+        if self.world == 1:
+            return d, r, c
+        gd, gr = gather_candidates(d, r, self.group)
+        self.merge_launches += 1
+        return self._merge(gd, gr, k)
+
+    def search(self, queries: np.ndarray, k: int):
+        """Host buffers in, host buffers out (pinned staging, H2D + D2H inside the call)."""
+        q = torch.from_numpy(np.ascontiguousarray(queries, dtype=np.float32).reshape(-1, self.dim))
+        qd = q.pin_memory().to(self.device, non_blocking=True)
+        d, r, c = self.search_device(qd, k)
+        out = (d.cpu().numpy(), r.cpu().numpy(), c.cpu().numpy())  # .cpu() synchronises the stream
+        return out
+
+    def close(self) -> None:
+        if self.shard is not None:
+            self.shard.close()
+            self.shard = None

@@ -6,6 +6,11 @@ import pytest
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
+# helpers (_refshim, _gloo_worker) are imported as top-level modules: the name `tests` can be
+# shadowed by the reference's own `tests` package once /root/reference is on sys.path
+TESTS = os.path.join(ROOT, "tests")
+if TESTS not in sys.path:
+    sys.path.insert(0, TESTS)
 
 
 def pytest_configure(config):

@@ -13,7 +13,7 @@ import numpy as np
 import pytest
 
 from oracle import exact, synthetic
-from tests._refshim import QueryProcessor, Storage, Vector
+from _refshim import QueryProcessor, Storage, Vector
 
 pytestmark = pytest.mark.gpu
 
