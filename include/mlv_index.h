@@ -131,8 +131,10 @@ int mlv_index_clear(mlv_index_t h);
 int mlv_index_search(mlv_index_t h, const float *queries, uint32_t nq, uint32_t k, const uint32_t *filter_bitmap,
                      float *out_dists, int64_t *out_rows, int32_t *out_counts);
 /*
- * Same with every pointer in device memory, enqueued on `stream` (a cudaStream_t; NULL =
- * the index's own stream) without synchronising.  Queries must hold nq * dim floats.
+ * Same with every pointer in device memory, enqueued on `stream` (a cudaStream_t; NULL = the
+ * legacy default stream, as everywhere in CUDA) without synchronising.  Queries must hold
+ * nq * dim floats.  The handle's scratch buffers are reused in stream order: use one stream
+ * at a time per handle.
  */
 int mlv_index_search_device(mlv_index_t h, const float *queries_dev, uint32_t nq, uint32_t k,
                             const uint32_t *filter_bitmap_dev, float *out_dists_dev, int64_t *out_rows_dev,

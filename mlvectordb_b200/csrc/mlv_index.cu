@@ -653,7 +653,7 @@ int mlv_index_search_device(mlv_index_t h, const float* queries_dev, uint32_t nq
     if (!h || !queries_dev || !out_dists_dev || !out_rows_dev || !out_counts_dev || nq == 0 || k == 0) return fail(h, MLV_E_INVALID, "bad argument");
     if (k > MLV_MAX_K) return fail(h, MLV_E_UNSUPPORTED, "k exceeds MLV_MAX_K");
     DeviceGuard g(h->device);
-    cudaStream_t st = stream ? (cudaStream_t)stream : h->stream;
+    cudaStream_t st = (cudaStream_t)stream;  // NULL = the legacy default stream, as everywhere in CUDA
     if (h->rows == h->n_deleted) {  // nothing live (reference index.py:99-104 returns [])
         fill_empty_kernel<<<32, 256, 0, st>>>(out_dists_dev, out_rows_dev, out_counts_dev, nq, k);
         h->launches++;

@@ -151,10 +151,12 @@ class DeviceShard:
 
     def search_device(self, q_ptr: int, nq: int, k: int, out_d_ptr: int, out_r_ptr: int, out_c_ptr: int,
                       filter_ptr: int = 0, stream: int = 0) -> None:
-        """All pointers are device addresses (e.g. ``tensor.data_ptr()``); enqueues on ``stream``."""
+        """All pointers are device addresses (e.g. ``tensor.data_ptr()``); enqueues on ``stream``
+        (a ``cudaStream_t`` value such as ``torch.cuda.current_stream().cuda_stream``; 0 = the
+        legacy default stream) and does not synchronise."""
         self._ck(self._lib.mlv_index_search_device(
             self._h, C.c_void_p(q_ptr), int(nq), int(k), C.c_void_p(filter_ptr) if filter_ptr else None,
-            C.c_void_p(out_d_ptr), C.c_void_p(out_r_ptr), C.c_void_p(out_c_ptr), C.c_void_p(stream) if stream else None))
+            C.c_void_p(out_d_ptr), C.c_void_p(out_r_ptr), C.c_void_p(out_c_ptr), C.c_void_p(stream)))
 
     def range_search(self, queries: np.ndarray, radius: float, filt=None, max_hits: int = 1024):
         """-> list per query of (dists f32 [hits], rows i64 [hits]) ascending (d, row)."""
