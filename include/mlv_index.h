@@ -181,6 +181,12 @@ int mlv_index_scan_time_ms(mlv_index_t h, double *total_ms, uint64_t *launches);
  * (-1 auto / 0 / 1), "ctas" grid size (0 = one per SM)}.  Results never depend on these.
  */
 int mlv_index_set_tuning(mlv_index_t h, const char *key, int value);
+/*
+ * Debug: after set_tuning("timeline", 1) every top-k scan records four %globaltimer stamps (ns)
+ * per CTA: start, first tile landed, last tile consumed, exit.  Copies 4 * n_ctas values of the
+ * most recent scan into `out` (synchronises the device).
+ */
+int mlv_index_debug_timeline(mlv_index_t h, uint64_t *out, uint32_t max_ctas, uint32_t *n_ctas);
 /* Kernels launched by this handle since creation (scan + select + maintenance). */
 int mlv_index_kernel_launches(mlv_index_t h, uint64_t *launches);
 

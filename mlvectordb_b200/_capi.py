@@ -69,6 +69,7 @@ SIGNATURES = {
     "mlv_index_scan_time_ms": (C.c_int, [_h, C.POINTER(C.c_double), _u64p]),
     "mlv_index_set_tuning": (C.c_int, [_h, C.c_char_p, C.c_int]),
     "mlv_index_kernel_launches": (C.c_int, [_h, _u64p]),
+    "mlv_index_debug_timeline": (C.c_int, [_h, _u64p, C.c_uint32, _u32p]),
 }
 
 _lib = None

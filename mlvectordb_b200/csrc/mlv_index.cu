@@ -55,7 +55,7 @@ struct mlv_index {
     cudaStream_t stream = nullptr;
     int sm_count = 0;
     size_t smem_optin = 0;
-    DevBuf d_qraw, d_q, d_keys0, d_keys1, d_filter, d_outd, d_outr, d_outc, d_misc, d_range;
+    DevBuf d_qraw, d_q, d_keys0, d_keys1, d_filter, d_outd, d_outr, d_outc, d_misc, d_range, d_timeline;
     HostBuf h_stage;
     std::string err;
     bool timing = false;
@@ -64,6 +64,8 @@ struct mlv_index {
     uint64_t launches = 0;
     // tuning (mlv_index_set_tuning / MLV_SCAN_* environment)
     int tune_cw = 8, tune_stage_kb = 32, tune_evict_first = -1, tune_r = 0, tune_max_stages = 8, tune_ctas = 0;
+    int tune_timeline = 0;
+    int last_grid = 0;
 };
 
 namespace {
@@ -343,6 +345,12 @@ int search_prepared(mlv_index* h, uint32_t nq, uint32_t k, const uint32_t* filte
     p.live = h->n_deleted ? h->d_live : nullptr;
     p.filter = filter_dev;
     p.evict_first = c.evict_first;
+    if (h->tune_timeline) {
+        rc = ensure_dev(h, h->d_timeline, (size_t)c.grid * 4 * 8);
+        if (rc != MLV_OK) return rc;
+        p.timeline = (unsigned long long*)h->d_timeline.p;
+        h->last_grid = c.grid;
+    }
 
     for (uint32_t q0 = 0; q0 < nq; q0 += chunk) {
         const uint32_t nchunk = std::min(chunk, nq - q0);
@@ -480,7 +488,7 @@ int mlv_index_destroy(mlv_index_t h) {
     if (h->d_rows) cudaFree(h->d_rows);
     if (h->d_live) cudaFree(h->d_live);
     for (DevBuf* b : {&h->d_qraw, &h->d_q, &h->d_keys0, &h->d_keys1, &h->d_filter, &h->d_outd, &h->d_outr, &h->d_outc,
-                      &h->d_misc, &h->d_range})
+                      &h->d_misc, &h->d_range, &h->d_timeline})
         free_dev(*b);
     if (h->h_stage.p) cudaFreeHost(h->h_stage.p);
     for (auto& pr : h->pending) {
@@ -508,6 +516,7 @@ int mlv_index_set_tuning(mlv_index_t h, const char* key, int value) {
     else if (k == "r") h->tune_r = value;
     else if (k == "max_stages") h->tune_max_stages = value;
     else if (k == "ctas") h->tune_ctas = value;
+    else if (k == "timeline") h->tune_timeline = value;
     else return fail(h, MLV_E_INVALID, "unknown tuning key " + k);
     return MLV_OK;
 }
@@ -842,6 +851,17 @@ int mlv_index_scan_time_ms(mlv_index_t h, double* total_ms, uint64_t* launches) 
     h->pending.clear();
     if (total_ms) *total_ms = total;
     if (launches) *launches = n;
+    return MLV_OK;
+}
+
+int mlv_index_debug_timeline(mlv_index_t h, uint64_t* out, uint32_t max_ctas, uint32_t* n_ctas) {
+    if (!h || !out || !n_ctas) return MLV_E_INVALID;
+    DeviceGuard g(h->device);
+    const uint32_t n = std::min<uint32_t>(max_ctas, (uint32_t)h->last_grid);
+    *n_ctas = n;
+    if (n == 0 || !h->d_timeline.p) return MLV_OK;
+    CK(h, cudaDeviceSynchronize());
+    CK(h, cudaMemcpy(out, h->d_timeline.p, (size_t)n * 4 * 8, cudaMemcpyDeviceToHost));
     return MLV_OK;
 }
 

@@ -45,7 +45,14 @@ struct ScanParams {
     uint64_t* range_keys;              // [nq_valid][max_hits]
     unsigned long long max_hits;
     int evict_first;
+    unsigned long long* timeline;  // debug: 4 globaltimer stamps per CTA (nullptr = off)
 };
+
+__device__ __forceinline__ unsigned long long global_timer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
 
 struct StageMeta {
     uint32_t row0;
@@ -154,6 +161,7 @@ __global__ void __launch_bounds__(SCAN_MAX_THREADS, 1) scan_kernel(const ScanPar
     if (!RANGE)
         for (uint32_t i = tid; i < (uint32_t)CW * NQ * k; i += blockDim.x) lists[i] = KEY_SENTINEL;
     __syncthreads();
+    if (p.timeline && tid == 0) p.timeline[blockIdx.x * 4 + 0] = global_timer_ns();
 
     if (warp == CW) {
         // ------------------------------------------------------------------ producer
@@ -198,6 +206,7 @@ __global__ void __launch_bounds__(SCAN_MAX_THREADS, 1) scan_kernel(const ScanPar
     uint32_t stage = 0, phase = 0, seq = 0;
     for (;;) {
         mbar_wait(&full[stage], phase);
+        if (p.timeline && tid == 0 && seq == 0) p.timeline[blockIdx.x * 4 + 1] = global_timer_ns();
         const int n = meta[stage].n_rows;
         if (n < 0) break;
         const uint32_t row0 = meta[stage].row0;
@@ -262,6 +271,7 @@ __global__ void __launch_bounds__(SCAN_MAX_THREADS, 1) scan_kernel(const ScanPar
             phase ^= 1;
         }
     }
+    if (p.timeline && tid == 0) p.timeline[blockIdx.x * 4 + 2] = global_timer_ns();
     if (RANGE) return;
 
     // ------------------------------------------------- fold the CW warp lists into one per query
@@ -292,6 +302,7 @@ __global__ void __launch_bounds__(SCAN_MAX_THREADS, 1) scan_kernel(const ScanPar
         uint64_t* out = p.out_keys + ((size_t)qi * gridDim.x + blockIdx.x) * k;
         for (uint32_t j = lane; j < k; j += 32) out[j] = home[j];
     }
+    if (p.timeline && tid == 0) p.timeline[blockIdx.x * 4 + 3] = global_timer_ns();
 }
 
 }  // namespace mlv

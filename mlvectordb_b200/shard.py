@@ -197,6 +197,13 @@ class DeviceShard:
     def set_tuning(self, key: str, value: int) -> None:
         self._ck(self._lib.mlv_index_set_tuning(self._h, key.encode(), int(value)))
 
+    def debug_timeline(self, max_ctas: int = 1024) -> np.ndarray:
+        """[n_ctas, 4] globaltimer ns stamps of the last scan (needs set_tuning('timeline', 1))."""
+        out = np.zeros((max_ctas, 4), dtype=np.uint64)
+        n = C.c_uint32()
+        self._ck(self._lib.mlv_index_debug_timeline(self._h, out.ctypes.data_as(C.POINTER(C.c_uint64)), max_ctas, C.byref(n)))
+        return out[: n.value]
+
     def kernel_launches(self) -> int:
         n = C.c_uint64()
         self._ck(self._lib.mlv_index_kernel_launches(self._h, C.byref(n)))
