@@ -134,7 +134,8 @@ int mlv_index_search(mlv_index_t h, const float *queries, uint32_t nq, uint32_t 
  * Same with every pointer in device memory, enqueued on `stream` (a cudaStream_t; NULL = the
  * legacy default stream, as everywhere in CUDA) without synchronising.  Queries must hold
  * nq * dim floats.  The handle's scratch buffers are reused in stream order: use one stream
- * at a time per handle.
+ * at a time per handle.  Batches that take the tensor-core path (see mlv_index_gemm_stats)
+ * synchronise `stream` once before returning.
  */
 int mlv_index_search_device(mlv_index_t h, const float *queries_dev, uint32_t nq, uint32_t k,
                             const uint32_t *filter_bitmap_dev, float *out_dists_dev, int64_t *out_rows_dev,
@@ -187,6 +188,29 @@ int mlv_index_set_tuning(mlv_index_t h, const char *key, int value);
  * most recent scan into `out` (synchronises the device).
  */
 int mlv_index_debug_timeline(mlv_index_t h, uint64_t *out, uint32_t max_ctas, uint32_t *n_ctas);
+/*
+ * Tensor-core batch path (csrc/gemm_kernel.cuh): searches with nq >= 32 queries on >= 16384 rows
+ * run as a tcgen05 3xTF32 GEMM that selects k + slack candidates per query, re-scores them in the
+ * reference's arithmetic and certifies the result; queries that fail the certificate are re-run
+ * by the exact scan, so results do not depend on the path.  set_tuning keys: "gemm" (-1 auto,
+ * 0 never, 1 whenever the shape allows), "gemm_min_nq".  This call returns cumulative counters
+ * and, when timing is enabled, the summed device time of the GEMM launches since the last call.
+ */
+typedef struct mlv_gemm_stats {
+    double gemm_ms;               /* CUDA-event time of the GEMM launches since the last call */
+    uint64_t gemm_launches_timed; /* how many launches gemm_ms covers */
+    uint64_t searches;            /* batches that took the GEMM path (cumulative) */
+    uint64_t queries;             /* queries in those batches */
+    uint64_t fallback_queries;    /* of those, re-run by the scan (certificate failed / buffer overflow) */
+    uint64_t rounds;              /* GEMM launches (one per round) */
+} mlv_gemm_stats_t;
+int mlv_index_gemm_stats(mlv_index_t h, mlv_gemm_stats_t *out);
+/*
+ * Debug / parity tests: the APPROXIMATE distances the tensor-core kernel computes (3xTF32 GEMM form,
+ * before the exact re-rank) for nq host queries against every stored row: out_approx[nq, rows],
+ * NaN for tombstoned rows.  1 <= rows <= 8192, dim >= 32.
+ */
+int mlv_index_debug_gemm(mlv_index_t h, const float *queries, uint32_t nq, float *out_approx);
 /* Kernels launched by this handle since creation (scan + select + maintenance). */
 int mlv_index_kernel_launches(mlv_index_t h, uint64_t *launches);
 

@@ -34,6 +34,17 @@ class IndexInfo(C.Structure):
     ]
 
 
+class GemmStats(C.Structure):
+    _fields_ = [
+        ("gemm_ms", C.c_double),
+        ("gemm_launches_timed", C.c_uint64),
+        ("searches", C.c_uint64),
+        ("queries", C.c_uint64),
+        ("fallback_queries", C.c_uint64),
+        ("rounds", C.c_uint64),
+    ]
+
+
 _f32p = C.POINTER(C.c_float)
 _i64p = C.POINTER(C.c_int64)
 _i32p = C.POINTER(C.c_int32)
@@ -70,6 +81,8 @@ SIGNATURES = {
     "mlv_index_set_tuning": (C.c_int, [_h, C.c_char_p, C.c_int]),
     "mlv_index_kernel_launches": (C.c_int, [_h, _u64p]),
     "mlv_index_debug_timeline": (C.c_int, [_h, _u64p, C.c_uint32, _u32p]),
+    "mlv_index_gemm_stats": (C.c_int, [_h, C.POINTER(GemmStats)]),
+    "mlv_index_debug_gemm": (C.c_int, [_h, C.c_void_p, C.c_uint32, C.c_void_p]),
 }
 
 _lib = None

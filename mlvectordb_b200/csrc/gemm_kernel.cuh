@@ -1,0 +1,463 @@
+// gemm_kernel.cuh -- large query batches: the distance matrix as a tensor-core contraction
+// (tcgen05.mma kind::tf32, 3xTF32 split, accumulators in TMEM, operands staged by TMA) with the
+// metric transform, tombstone/filter mask and candidate selection fused into the epilogue.
+//
+// The reference has no batch API (Index.search takes one query: src/mlvectordb/implementations/
+// index.py:91-129); BASELINE.json configs[2] (10M x 768, k=100, 4096-query batches) is this path.
+//
+// A GEMM computes l2 as |x|^2 + |q|^2 - 2 x.q, which is not the reference's arithmetic
+// (hnswlib: sum (x_i - q_i)^2), so this kernel only SELECTS: it keeps, per query, the k' = k + slack
+// rows with the smallest approximate distance `a`.  rerank_kernel then recomputes those rows in the
+// reference's form with the scan kernel's exact summation order (bit-identical scores) and
+// certifies the result:  every row outside the candidate set has a >= a_k', hence an exact distance
+// >= a_k' - delta; if the exact k-th best is below that, no outside row can belong to the top-k.
+// Queries that fail the certificate (or overflow their candidate buffer) are re-run by the exact
+// scan; the host does that, so results never depend on which path ran.
+//
+// Structure (one CTA per SM, 320 threads):
+//   warp 0      TMA producer: per K chunk of 32 floats one X tile [128 rows] and the Qhi/Qlo tiles
+//               [256 queries] -> 128B-swizzled shared memory, 2-stage ring, full/empty mbarriers
+//   warps 2-5   split X in place into hi = x & 0xffffe000 (what kind::tf32 consumes) and
+//               lo = x - hi (second buffer); elementwise, so the swizzle is irrelevant to them
+//   warp 1      MMA issuer: per 8-float K step  D += Xhi.Qhi + Xhi.Qlo + Xlo.Qhi  (M=128, N=256);
+//               two accumulators (2 x 256 TMEM columns) so the epilogue overlaps the next tile
+//   warps 6-9   epilogue: tcgen05.ld 32 columns at a time; thread = row, column = query;
+//               a = metric(dot); rows passing the query's current threshold are appended to the
+//               query's candidate buffer (atomic slot claim)
+// Thresholds only change between launches: the host runs the scan of the rows as a sequence of
+// geometrically growing rounds, each followed by refine_kernel (keep the best k', set thr = a_k').
+#pragma once
+#include <cuda.h>
+
+#include "common.cuh"
+#include "scan_kernel.cuh"
+#include "select_kernel.cuh"
+
+namespace mlv {
+
+constexpr int GEMM_BM = 128;  // rows per tile      (UMMA M)
+constexpr int GEMM_BN = 256;  // queries per tile   (UMMA N)
+constexpr int GEMM_BK = 32;   // floats per K chunk (one 128-byte swizzle row)
+constexpr int GEMM_STAGES = 2;
+constexpr int GEMM_THREADS = 320;
+constexpr uint32_t GEMM_X_BYTES = GEMM_BM * GEMM_BK * 4;   // 16 KB
+constexpr uint32_t GEMM_Q_BYTES = GEMM_BN * GEMM_BK * 4;   // 32 KB
+constexpr uint32_t GEMM_STAGE_BYTES = 2 * GEMM_X_BYTES + 2 * GEMM_Q_BYTES;  // 96 KB
+constexpr uint32_t GEMM_SMEM_BYTES = 1024 + GEMM_STAGES * GEMM_STAGE_BYTES + 2 * GEMM_BN * 4 + 256;
+constexpr float GEMM_DELTA_REL = 1.220703125e-4f;  // 2^-13: bound on |a - exact| / scale (see rerank_kernel)
+
+struct GemmParams {
+    uint32_t n_rows;
+    uint32_t row_tile0, row_tile1;  // row tiles [t0, t1) of this round
+    uint32_t nq;                    // valid queries (padded ones never pass: thr = -inf)
+    uint32_t n_qtiles;
+    uint32_t n_kchunks;
+    const float* row_norms;  // [n_rows] |x|^2   (l2 only)
+    const float* q_norms;    // [nq_pad] |q|^2
+    const float* thr;        // [nq_pad] current threshold on the approximate distance
+    const uint32_t* live;
+    const uint32_t* filter;
+    uint64_t* cand;          // [nq_pad][cap]
+    uint32_t* cand_cnt;      // [nq_pad]
+    uint32_t cap;
+};
+
+// ---- PTX wrappers ---------------------------------------------------------------------------
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* map, int32_t c0, int32_t c1, uint64_t* bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+            smem_u32(smem_dst)),
+        "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tc_mma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// K-major operand tile, rows of 128 bytes, SWIZZLE_128B (what the TMA box {32 floats, rows} writes):
+// 8-row groups are 1024 bytes apart (SBO); LBO is unused for swizzled K-major layouts.
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
+    uint64_t d = (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
+    d |= (uint64_t)1 << 16;
+    d |= (uint64_t)(1024 >> 4) << 32;
+    d |= (uint64_t)1 << 46;  // descriptor version (sm_100)
+    d |= (uint64_t)2 << 61;  // SWIZZLE_128B
+    return d;
+}
+// kind::tf32, fp32 accumulate, A and B K-major, M = 128, N = 256
+constexpr uint32_t GEMM_IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(GEMM_BN >> 3) << 17) | ((uint32_t)(GEMM_BM >> 4) << 24);
+
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n\t"
+        "tcgen05.wait::ld.sync.aligned;"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+          "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+          "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr)
+        : "memory");
+}
+
+// ---- the GEMM + candidate-selection kernel ---------------------------------------------------
+template <int METRIC>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm_topk_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_qhi,
+                 const __grid_constant__ CUtensorMap tm_qlo, const GemmParams p) {
+    extern __shared__ unsigned char gemm_smem_raw[];
+    // SWIZZLE_128B tiles need 1024-byte alignment
+    unsigned char* smem = gemm_smem_raw + ((1024u - (smem_u32(gemm_smem_raw) & 1023u)) & 1023u);
+    float* thr_s = reinterpret_cast<float*>(smem + GEMM_STAGES * GEMM_STAGE_BYTES);  // [256]
+    float* qn_s = thr_s + GEMM_BN;                                                    // [256]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(qn_s + GEMM_BN);
+    uint64_t* full = bars;                      // [S]  TMA bytes landed
+    uint64_t* empty = bars + GEMM_STAGES;       // [S]  MMAs reading the stage retired
+    uint64_t* conv = bars + 2 * GEMM_STAGES;    // [S]  hi/lo split written
+    uint64_t* tfull = bars + 3 * GEMM_STAGES;   // [2]  accumulator complete
+    uint64_t* tempty = tfull + 2;               // [2]  accumulator drained
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+
+    const int tid = threadIdx.x;
+    const int warp = tid >> 5;
+    const int lane = tid & 31;
+
+    if (tid == 0) {
+        for (int s = 0; s < GEMM_STAGES; s++) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], 1);
+            mbar_init(&conv[s], 4);
+        }
+        for (int a = 0; a < 2; a++) {
+            mbar_init(&tfull[a], 1);
+            mbar_init(&tempty[a], 4);
+        }
+        mbar_fence_init();
+        tma_prefetch_desc(&tm_x);
+        tma_prefetch_desc(&tm_qhi);
+        tma_prefetch_desc(&tm_qlo);
+    }
+    if (warp == 1) {  // whole warp: allocate all 512 TMEM columns (two 128 x 256 fp32 accumulators)
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    const uint32_t n_items = (p.row_tile1 - p.row_tile0) * p.n_qtiles;
+
+    if (warp == 0) {
+        // ------------------------------------------------------------------ TMA producer
+        if (lane == 0) {
+            uint32_t stage = 0, phase = 0;
+            for (uint32_t it = blockIdx.x; it < n_items; it += gridDim.x) {
+                const uint32_t rt = p.row_tile0 + it / p.n_qtiles, qt = it % p.n_qtiles;
+                for (uint32_t kc = 0; kc < p.n_kchunks; kc++) {
+                    mbar_wait(&empty[stage], phase ^ 1);
+                    unsigned char* sb = smem + (size_t)stage * GEMM_STAGE_BYTES;
+                    mbar_arrive_expect_tx(&full[stage], GEMM_X_BYTES + 2 * GEMM_Q_BYTES);
+                    tma_load_2d(sb, &tm_x, (int32_t)(kc * GEMM_BK), (int32_t)(rt * GEMM_BM), &full[stage]);
+                    tma_load_2d(sb + 2 * GEMM_X_BYTES, &tm_qhi, (int32_t)(kc * GEMM_BK), (int32_t)(qt * GEMM_BN), &full[stage]);
+                    tma_load_2d(sb + 2 * GEMM_X_BYTES + GEMM_Q_BYTES, &tm_qlo, (int32_t)(kc * GEMM_BK), (int32_t)(qt * GEMM_BN),
+                                &full[stage]);
+                    if (++stage == GEMM_STAGES) {
+                        stage = 0;
+                        phase ^= 1;
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ------------------------------------------------------------------ MMA issuer
+        if (lane == 0) {
+            uint32_t stage = 0, phase = 0, local = 0;
+            for (uint32_t it = blockIdx.x; it < n_items; it += gridDim.x, local++) {
+                const uint32_t acc = local & 1, acc_phase = (local >> 1) & 1;
+                mbar_wait(&tempty[acc], acc_phase ^ 1);
+                tc_fence_after();
+                const uint32_t tmem_d = tmem_base + acc * GEMM_BN;
+                for (uint32_t kc = 0; kc < p.n_kchunks; kc++) {
+                    mbar_wait(&full[stage], phase);
+                    mbar_wait(&conv[stage], phase);
+                    tc_fence_after();
+                    const uint32_t sb = smem_u32(smem + (size_t)stage * GEMM_STAGE_BYTES);
+                    const uint64_t d_xhi = umma_desc_sw128(sb);
+                    const uint64_t d_xlo = umma_desc_sw128(sb + GEMM_X_BYTES);
+                    const uint64_t d_qhi = umma_desc_sw128(sb + 2 * GEMM_X_BYTES);
+                    const uint64_t d_qlo = umma_desc_sw128(sb + 2 * GEMM_X_BYTES + GEMM_Q_BYTES);
+#pragma unroll
+                    for (uint32_t ks = 0; ks < GEMM_BK / 8; ks++) {
+                        const uint64_t adv = (uint64_t)(ks * 2);  // 8 floats = 32 bytes = 2 x 16-byte units
+                        // small terms first, the dominant hi.hi product last
+                        tc_mma_tf32(tmem_d, d_xlo + adv, d_qhi + adv, GEMM_IDESC, (kc | ks) != 0);
+                        tc_mma_tf32(tmem_d, d_xhi + adv, d_qlo + adv, GEMM_IDESC, 1);
+                        tc_mma_tf32(tmem_d, d_xhi + adv, d_qhi + adv, GEMM_IDESC, 1);
+                    }
+                    tc_commit(&empty[stage]);  // stage reusable once these MMAs have read it
+                    if (++stage == GEMM_STAGES) {
+                        stage = 0;
+                        phase ^= 1;
+                    }
+                }
+                tc_commit(&tfull[acc]);
+            }
+        }
+    } else if (warp < 6) {
+        // ------------------------------------------------------------------ hi/lo split of X
+        const int ct = tid - 64;  // 0..127
+        uint32_t stage = 0, phase = 0;
+        for (uint32_t it = blockIdx.x; it < n_items; it += gridDim.x) {
+            for (uint32_t kc = 0; kc < p.n_kchunks; kc++) {
+                mbar_wait(&full[stage], phase);
+                uint4* xh = reinterpret_cast<uint4*>(smem + (size_t)stage * GEMM_STAGE_BYTES);
+                float4* xl = reinterpret_cast<float4*>(smem + (size_t)stage * GEMM_STAGE_BYTES + GEMM_X_BYTES);
+#pragma unroll
+                for (int i = 0; i < (int)(GEMM_X_BYTES / 16 / 128); i++) {
+                    const int idx = ct + 128 * i;
+                    const uint4 v = xh[idx];
+                    uint4 hi;
+                    hi.x = v.x & 0xFFFFE000u;
+                    hi.y = v.y & 0xFFFFE000u;
+                    hi.z = v.z & 0xFFFFE000u;
+                    hi.w = v.w & 0xFFFFE000u;
+                    float4 lo;
+                    lo.x = __uint_as_float(v.x) - __uint_as_float(hi.x);
+                    lo.y = __uint_as_float(v.y) - __uint_as_float(hi.y);
+                    lo.z = __uint_as_float(v.z) - __uint_as_float(hi.z);
+                    lo.w = __uint_as_float(v.w) - __uint_as_float(hi.w);
+                    xh[idx] = hi;
+                    xl[idx] = lo;
+                }
+                fence_proxy_async_smem();  // generic-proxy writes -> visible to the tensor core's async proxy
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&conv[stage]);
+                if (++stage == GEMM_STAGES) {
+                    stage = 0;
+                    phase ^= 1;
+                }
+            }
+        }
+    } else {
+        // ------------------------------------------------------------------ epilogue
+        const int et = tid - 192;        // 0..127
+        const uint32_t quarter = warp & 3;  // TMEM lanes this warp may read: 32*quarter .. +31
+        uint32_t local = 0;
+        for (uint32_t it = blockIdx.x; it < n_items; it += gridDim.x, local++) {
+            const uint32_t rt = p.row_tile0 + it / p.n_qtiles, qt = it % p.n_qtiles;
+            const uint32_t acc = local & 1, acc_phase = (local >> 1) & 1;
+            named_bar_sync(2, 128);  // everyone finished reading thr_s / qn_s of the previous item
+            for (int i = et; i < GEMM_BN; i += 128) {
+                thr_s[i] = p.thr[qt * GEMM_BN + i];
+                qn_s[i] = p.q_norms[qt * GEMM_BN + i];
+            }
+            const uint32_t row = rt * GEMM_BM + quarter * 32 + lane;
+            bool row_ok = row < p.n_rows;
+            float xn = 0.f;
+            if (row_ok) {
+                if (p.live) row_ok = (__ldg(p.live + (row >> 5)) >> (row & 31)) & 1u;
+                if (row_ok && p.filter) row_ok = (__ldg(p.filter + (row >> 5)) >> (row & 31)) & 1u;
+                if (METRIC == METRIC_L2 && row_ok) xn = __ldg(p.row_norms + row);
+            }
+            named_bar_sync(2, 128);
+            mbar_wait(&tfull[acc], acc_phase);
+            tc_fence_after();
+            const uint32_t taddr0 = tmem_base + ((quarter * 32u) << 16) + acc * GEMM_BN;
+            for (uint32_t c = 0; c < GEMM_BN / 32; c++) {
+                uint32_t v[32];
+                tmem_ld32(taddr0 + c * 32, v);
+                if (row_ok) {
+#pragma unroll
+                    for (int j = 0; j < 32; j++) {
+                        const uint32_t ql = c * 32 + j;
+                        const float dot = __uint_as_float(v[j]);
+                        const float a = (METRIC == METRIC_L2) ? fmaf(-2.0f, dot, xn + qn_s[ql]) : 1.0f - dot;
+                        if (a <= thr_s[ql]) {
+                            const uint32_t qg = qt * GEMM_BN + ql;
+                            const uint32_t pos = atomicAdd(p.cand_cnt + qg, 1u);
+                            if (pos < p.cap) p.cand[(size_t)qg * p.cap + pos] = make_key(a, row);
+                        }
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty[acc]);
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+    }
+}
+
+// ---- helpers around the GEMM -------------------------------------------------------------------
+// |x|^2 per row (one warp per row) and the running maximum (non-negative floats order as uints).
+__global__ void row_norms_kernel(const float* __restrict__ rows, uint64_t first, uint64_t n, uint32_t ld, float* norms,
+                                 uint32_t* max_norm2_bits) {
+    const uint64_t w = (uint64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (w >= n) return;
+    const float4* r = reinterpret_cast<const float4*>(rows + (first + w) * ld);
+    const uint32_t ld4 = ld >> 2;
+    float s = 0.f;
+    for (uint32_t j = lane; j < ld4; j += 32) {
+        const float4 x = r[j];
+        s = fmaf(x.x, x.x, s);
+        s = fmaf(x.y, x.y, s);
+        s = fmaf(x.z, x.z, s);
+        s = fmaf(x.w, x.w, s);
+    }
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+    if (lane == 0) {
+        norms[first + w] = s;
+        if (s == s) atomicMax(max_norm2_bits, __float_as_uint(s));
+    }
+}
+
+// Prepared queries [nq, ld] -> Qhi / Qlo [nq_pad, ld] (pad rows zero), |q|^2, initial thresholds,
+// cleared candidate counters and flags.  One warp per (padded) query.
+__global__ void split_queries_kernel(const float* __restrict__ q, float* __restrict__ qhi, float* __restrict__ qlo,
+                                     float* __restrict__ qn, float* __restrict__ thr, uint32_t* __restrict__ cnt,
+                                     uint32_t* __restrict__ flags, uint32_t nq, uint32_t nq_pad, uint32_t ld) {
+    const uint32_t w = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (w >= nq_pad) return;
+    float s = 0.f;
+    for (uint32_t j = lane; j < ld; j += 32) {
+        const float v = w < nq ? q[(size_t)w * ld + j] : 0.f;
+        const float hi = __uint_as_float(__float_as_uint(v) & 0xFFFFE000u);
+        qhi[(size_t)w * ld + j] = hi;
+        qlo[(size_t)w * ld + j] = v - hi;
+        s = fmaf(v, v, s);
+    }
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+    if (lane == 0) {
+        qn[w] = s;
+        thr[w] = w < nq ? __int_as_float(0x7f800000) : __int_as_float(0xff800000);
+        cnt[w] = 0;
+        flags[w] = 0;
+    }
+}
+
+// After a round: keep the kprime smallest keys of each query's buffer and tighten its threshold.
+// flags[q] bit 0 = the buffer overflowed (candidates were lost: the query falls back to the scan).
+__global__ void __launch_bounds__(SELECT_THREADS, 1)
+refine_kernel(uint64_t* cand, uint32_t* cnt, float* thr, uint32_t* flags, uint32_t cap, uint32_t P, uint32_t kprime) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    uint64_t* a = reinterpret_cast<uint64_t*>(smem_raw);
+    const uint32_t q = blockIdx.x;
+    const uint32_t c = cnt[q];
+    const uint32_t n = min(c, cap);
+    if (n < kprime && c <= cap) return;  // fewer than k' candidates: keep all, threshold stays +inf (uniform per block)
+    uint64_t* mine = cand + (size_t)q * cap;
+    for (uint32_t i = threadIdx.x; i < P; i += blockDim.x) a[i] = i < n ? mine[i] : KEY_SENTINEL;
+    bitonic_sort_smem(a, P);
+    const uint32_t keep = min(n, kprime);
+    for (uint32_t i = threadIdx.x; i < keep; i += blockDim.x) mine[i] = a[i];
+    if (threadIdx.x == 0) {
+        cnt[q] = keep;
+        if (c > cap) flags[q] |= 1u;
+        if (n >= kprime) thr[q] = key_dist(a[kprime - 1]);
+    }
+}
+
+struct RerankParams {
+    const float4* rows;
+    uint32_t ld4;
+    const float4* queries;  // prepared [nq, ld]
+    const float* q_norms;
+    const uint32_t* max_norm2_bits;  // max |x|^2 over the rows (null for cosine: unit rows)
+    const uint64_t* cand;
+    const uint32_t* cnt;
+    uint32_t* flags;
+    uint32_t cap, kprime, k, P;
+    float* out_dists;
+    int64_t* out_rows;
+    int32_t* out_counts;
+    uint64_t row_base;
+    int metric;  // MLV metric: 0 l2, 1 ip, 2 cosine
+};
+
+// One CTA per query: exact reference-form distances of the candidates with the scan kernel's
+// summation order (lane l sums float4 columns l, l+32, ...; butterfly over the lanes), final
+// top-k, and the certificate described at the top of this file.  flags[q] bit 1 = not certified.
+template <int METRIC>
+__global__ void __launch_bounds__(256, 1) rerank_kernel(const RerankParams p) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    uint64_t* a = reinterpret_cast<uint64_t*>(smem_raw);
+    const uint32_t q = blockIdx.x;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t n = min(p.cnt[q], p.kprime);  // refine_kernel left them sorted by approximate key
+    const uint64_t* mine = p.cand + (size_t)q * p.cap;
+    const float4* qv = p.queries + (size_t)q * p.ld4;
+    for (uint32_t i = threadIdx.x; i < p.P; i += blockDim.x) a[i] = KEY_SENTINEL;
+    __syncthreads();
+    for (uint32_t i = warp; i < n; i += (blockDim.x >> 5)) {
+        const uint32_t row = key_row(mine[i]);
+        const float4* x = p.rows + (size_t)row * p.ld4;
+        float acc = 0.f;
+        for (uint32_t j = lane; j < p.ld4; j += 32) acc = accum4<METRIC>(acc, x[j], qv[j]);
+#pragma unroll
+        for (int off = 16; off >= 1; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+        const float dist = (METRIC == METRIC_IP) ? 1.0f - acc : acc;
+        if (lane == 0) a[i] = make_key(dist, row);
+    }
+    bitonic_sort_smem(a, p.P);
+    __shared__ int cnt_s;
+    if (threadIdx.x == 0) cnt_s = 0;
+    __syncthreads();
+    int local = 0;
+    for (uint32_t i = threadIdx.x; i < p.k; i += blockDim.x) {
+        const uint64_t key = a[i];
+        const bool valid = key != KEY_SENTINEL;
+        p.out_dists[(size_t)q * p.k + i] = valid ? key_dist(key) : __int_as_float(0x7f800000);
+        p.out_rows[(size_t)q * p.k + i] = valid ? (int64_t)(p.row_base + key_row(key)) : -1;
+        local += valid;
+    }
+    if (local) atomicAdd(&cnt_s, local);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        p.out_counts[q] = cnt_s;
+        bool certified = true;
+        if (n >= p.kprime && p.k <= n) {  // rows may exist outside the candidate set
+            const float qn = p.q_norms[q];
+            float scale;
+            if (p.metric == 2) {
+                scale = 1.0f;
+            } else {
+                const float xmax = sqrtf(__uint_as_float(*p.max_norm2_bits));
+                const float qs = sqrtf(qn);
+                scale = (p.metric == 0) ? (xmax + qs) * (xmax + qs) : xmax * qs;
+            }
+            const float delta = GEMM_DELTA_REL * scale;
+            const float a_last = key_dist(mine[p.kprime - 1]);  // largest approximate distance kept
+            const float e_k = key_dist(a[p.k - 1]);             // exact k-th best among the candidates
+            certified = (a_last - delta > e_k);                 // false for NaN
+        }
+        if (!certified) p.flags[q] |= 2u;
+    }
+}
+
+}  // namespace mlv

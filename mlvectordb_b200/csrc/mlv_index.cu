@@ -17,6 +17,7 @@
 #include <vector>
 
 #include "common.cuh"
+#include "gemm_kernel.cuh"
 #include "maint_kernels.cuh"
 #include "scan_kernel.cuh"
 #include "select_kernel.cuh"
@@ -66,6 +67,13 @@ struct mlv_index {
     int tune_cw = 8, tune_stage_kb = 32, tune_evict_first = -1, tune_r = 0, tune_max_stages = 8, tune_ctas = 0;
     int tune_timeline = 0;
     int last_grid = 0;
+    // tensor-core batch path (gemm_kernel.cuh)
+    DevBuf d_norms, d_gq, d_cand, d_maxn2;
+    uint64_t norms_valid = 0;  // rows [0, norms_valid) of d_norms are current
+    int tune_gemm = -1;        // -1 auto, 0 never, 1 whenever the shape allows it
+    int tune_gemm_min_nq = 32;
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> gemm_pending;
+    uint64_t gemm_searches = 0, gemm_queries = 0, gemm_fallback_queries = 0, gemm_rounds = 0, gemm_launches = 0;
 };
 
 namespace {
@@ -313,9 +321,9 @@ cudaError_t ensure_select_attrs(int device) {
     return cudaSuccess;
 }
 
-// queries already prepared in h->d_q ([nq, ld]); all output pointers in device memory
-int search_prepared(mlv_index* h, uint32_t nq, uint32_t k, const uint32_t* filter_dev, float* out_d, int64_t* out_r,
-                    int32_t* out_c, cudaStream_t st) {
+// qprep: prepared queries [nq, ld] in device memory; all output pointers in device memory
+int search_prepared(mlv_index* h, const float* qprep, uint32_t nq, uint32_t k, const uint32_t* filter_dev, float* out_d,
+                    int64_t* out_r, int32_t* out_c, cudaStream_t st) {
     ScanCfg c;
     int rc = choose_cfg(h, nq, k, false, &c);
     if (rc != MLV_OK) return rc;
@@ -355,7 +363,7 @@ int search_prepared(mlv_index* h, uint32_t nq, uint32_t k, const uint32_t* filte
     for (uint32_t q0 = 0; q0 < nq; q0 += chunk) {
         const uint32_t nchunk = std::min(chunk, nq - q0);
         for (uint32_t g0 = 0; g0 < nchunk; g0 += c.NQ) {
-            p.queries = reinterpret_cast<const float4*>((float*)h->d_q.p + (size_t)(q0 + g0) * h->ld);
+            p.queries = reinterpret_cast<const float4*>(qprep + (size_t)(q0 + g0) * h->ld);
             p.nq_valid = std::min<uint32_t>(c.NQ, nchunk - g0);
             p.out_keys = (uint64_t*)h->d_keys0.p + (size_t)g0 * c.grid * k;
             CK(h, launch_scan(h, p, c, false, st));
@@ -400,6 +408,223 @@ int prep_queries(mlv_index* h, const float* q_dev_raw, uint32_t nq, cudaStream_t
                                                                  h->metric == MLV_COSINE);
     h->launches++;
     CK(h, cudaGetLastError());
+    return MLV_OK;
+}
+
+// ---- tensor-core batch path (gemm_kernel.cuh) ----------------------------------------------------
+typedef CUresult (*encode_tiled_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                    const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+// cuTensorMapEncodeTiled through the runtime's driver entry point: libcuda is not linked, so the
+// library still loads (and exports its symbols) on a box without a driver.
+encode_tiled_fn get_encode_tiled() {
+    static encode_tiled_fn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = (encode_tiled_fn)p;
+        else
+            cudaGetLastError();
+    }
+    return fn;
+}
+
+// fp32 matrix [n_rows, ld] row-major -> boxes of {GEMM_BK floats, box_rows rows}, 128-byte swizzle,
+// out-of-range elements read as zero (ragged last row tile, ld not a multiple of 32)
+int make_tile_map(mlv_index* h, CUtensorMap* map, const float* base, uint64_t n_rows, uint32_t box_rows) {
+    encode_tiled_fn enc = get_encode_tiled();
+    if (!enc) return fail(h, MLV_E_CUDA, "cuTensorMapEncodeTiled is not available from this driver");
+    const cuuint64_t gdim[2] = {h->ld, n_rows};
+    const cuuint64_t gstride[1] = {(cuuint64_t)h->ld * 4};
+    const cuuint32_t box[2] = {(cuuint32_t)GEMM_BK, box_rows};
+    const cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)base, gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(h, MLV_E_CUDA, "cuTensorMapEncodeTiled failed (" + std::to_string((int)r) + ")");
+    return MLV_OK;
+}
+
+uint32_t gemm_kprime(uint32_t k) {
+    const uint32_t slack = std::max<uint32_t>(16, k / 4);
+    return (k + slack + 31) & ~31u;
+}
+
+bool gemm_eligible(const mlv_index* h, uint32_t nq, uint32_t k) {
+    if (h->tune_gemm == 0) return false;
+    if (h->ld < (uint32_t)GEMM_BK) return false;
+    if (gemm_kprime(k) * 4 > SELECT_MAX_P) return false;
+    if (h->tune_gemm == 1) return true;
+    return nq >= (uint32_t)std::max(h->tune_gemm_min_nq, 1) && h->rows >= 16384;
+}
+
+int ensure_row_norms(mlv_index* h, cudaStream_t st) {
+    int rc;
+    if (!h->d_maxn2.p) {
+        if ((rc = ensure_dev(h, h->d_maxn2, 4)) != MLV_OK) return rc;
+        CK(h, cudaMemsetAsync(h->d_maxn2.p, 0, 4, st));
+        h->norms_valid = 0;
+    }
+    if (h->d_norms.bytes < h->rows * 4) {
+        // growing reallocates: recompute everything (rows rarely grow between large batches)
+        if ((rc = ensure_dev(h, h->d_norms, std::max<uint64_t>(h->capacity, h->rows) * 4)) != MLV_OK) return rc;
+        h->norms_valid = 0;
+    }
+    if (h->norms_valid == 0) CK(h, cudaMemsetAsync(h->d_maxn2.p, 0, 4, st));
+    if (h->norms_valid < h->rows) {
+        const uint64_t n = h->rows - h->norms_valid;
+        const int wpb = 8;
+        row_norms_kernel<<<(unsigned)((n + wpb - 1) / wpb), wpb * 32, 0, st>>>(h->d_rows, h->norms_valid, n, h->ld,
+                                                                             (float*)h->d_norms.p, (uint32_t*)h->d_maxn2.p);
+        h->launches++;
+        CK(h, cudaGetLastError());
+        h->norms_valid = h->rows;
+    }
+    return MLV_OK;
+}
+
+template <int METRIC>
+cudaError_t launch_gemm_t(const CUtensorMap& mx, const CUtensorMap& mqh, const CUtensorMap& mql, const GemmParams& gp, int grid,
+                          cudaStream_t st) {
+    auto kern = gemm_topk_kernel<METRIC>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM_SMEM_BYTES);
+    if (e != cudaSuccess) return e;
+    kern<<<grid, GEMM_THREADS, GEMM_SMEM_BYTES, st>>>(mx, mqh, mql, gp);
+    return cudaGetLastError();
+}
+
+// Large batches: tcgen05 GEMM selects k' candidates per query in geometrically growing rounds,
+// rerank_kernel scores them in the reference's arithmetic and certifies; uncertified queries are
+// re-run by the exact scan.  Synchronises `st` once (to read the per-query flags).
+int search_gemm(mlv_index* h, const float* qprep, uint32_t nq, uint32_t k, const uint32_t* filter_dev, float* out_d,
+                int64_t* out_r, int32_t* out_c, cudaStream_t st) {
+    int rc;
+    const uint32_t ld = h->ld;
+    const uint32_t nq_pad = (nq + GEMM_BN - 1) / GEMM_BN * GEMM_BN;
+    const uint32_t kprime = gemm_kprime(k);
+    const uint32_t cap = std::min<uint32_t>(SELECT_MAX_P, pow2_ceil(8 * kprime));
+    const uint32_t P = cap;  // power of two
+    const bool l2 = h->metric == MLV_L2;
+    if (h->metric != MLV_COSINE) {
+        if ((rc = ensure_row_norms(h, st)) != MLV_OK) return rc;
+    }
+    // scratch: Qhi | Qlo | qn | thr | cnt | flags
+    const size_t qmat = (size_t)nq_pad * ld * 4;
+    if ((rc = ensure_dev(h, h->d_gq, 2 * qmat + (size_t)nq_pad * 16)) != MLV_OK) return rc;
+    if ((rc = ensure_dev(h, h->d_cand, (size_t)nq_pad * cap * 8)) != MLV_OK) return rc;
+    float* qhi = (float*)h->d_gq.p;
+    float* qlo = qhi + (size_t)nq_pad * ld;
+    float* qn = qlo + (size_t)nq_pad * ld;
+    float* thr = qn + nq_pad;
+    uint32_t* cnt = (uint32_t*)(thr + nq_pad);
+    uint32_t* flags = cnt + nq_pad;
+    uint64_t* cand = (uint64_t*)h->d_cand.p;
+    {
+        const int wpb = 8;
+        split_queries_kernel<<<(nq_pad + wpb - 1) / wpb, wpb * 32, 0, st>>>(qprep, qhi, qlo, qn, thr, cnt, flags, nq, nq_pad, ld);
+        h->launches++;
+        CK(h, cudaGetLastError());
+    }
+    CUtensorMap mx, mqh, mql;
+    if ((rc = make_tile_map(h, &mx, h->d_rows, h->rows, GEMM_BM)) != MLV_OK) return rc;
+    if ((rc = make_tile_map(h, &mqh, qhi, nq_pad, GEMM_BN)) != MLV_OK) return rc;
+    if ((rc = make_tile_map(h, &mql, qlo, nq_pad, GEMM_BN)) != MLV_OK) return rc;
+    CK(h, cudaFuncSetAttribute(refine_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SELECT_MAX_P * 8)));
+
+    GemmParams gp{};
+    gp.n_rows = (uint32_t)h->rows;
+    gp.nq = nq;
+    gp.n_qtiles = nq_pad / GEMM_BN;
+    gp.n_kchunks = (ld + GEMM_BK - 1) / GEMM_BK;
+    gp.row_norms = l2 ? (const float*)h->d_norms.p : nullptr;
+    gp.q_norms = qn;
+    gp.thr = thr;
+    gp.live = h->n_deleted ? h->d_live : nullptr;
+    gp.filter = filter_dev;
+    gp.cand = cand;
+    gp.cand_cnt = cnt;
+    gp.cap = cap;
+
+    // rounds: the first takes as many rows as a candidate buffer holds (no threshold yet), each
+    // later one (cap - k') / (4 k') times the rows seen so far, so a buffer is expected to stay
+    // at most a quarter full however the thresholds started
+    const uint32_t total_tiles = (uint32_t)((h->rows + GEMM_BM - 1) / GEMM_BM);
+    const double growth = (double)(cap - kprime) / (4.0 * kprime);
+    uint32_t seen = 0;
+    const int refine_threads = (int)std::min<uint32_t>(SELECT_THREADS, std::max<uint32_t>(P / 2, 32));
+    while (seen < total_tiles) {
+        uint32_t take = seen == 0 ? std::max<uint32_t>(1, cap / GEMM_BM) : std::max<uint32_t>(1, (uint32_t)(seen * growth));
+        take = std::min(take, total_tiles - seen);
+        gp.row_tile0 = seen;
+        gp.row_tile1 = seen + take;
+        const uint64_t items = (uint64_t)take * gp.n_qtiles;
+        const int grid = (int)std::min<uint64_t>(items, (uint64_t)h->sm_count);
+        cudaEvent_t e0 = nullptr, e1 = nullptr;
+        if (h->timing) {
+            for (cudaEvent_t* ev : {&e0, &e1}) {
+                if (!h->event_pool.empty()) {
+                    *ev = h->event_pool.back();
+                    h->event_pool.pop_back();
+                } else {
+                    CK(h, cudaEventCreate(ev));
+                }
+            }
+            cudaEventRecord(e0, st);
+        }
+        CK(h, l2 ? launch_gemm_t<METRIC_L2>(mx, mqh, mql, gp, grid, st) : launch_gemm_t<METRIC_IP>(mx, mqh, mql, gp, grid, st));
+        if (h->timing) {
+            cudaEventRecord(e1, st);
+            h->gemm_pending.emplace_back(e0, e1);
+        }
+        refine_kernel<<<nq, refine_threads, (size_t)P * 8, st>>>(cand, cnt, thr, flags, cap, P, kprime);
+        CK(h, cudaGetLastError());
+        h->launches += 2;
+        h->gemm_launches++;
+        h->gemm_rounds++;
+        seen += take;
+    }
+
+    RerankParams rp{};
+    rp.rows = reinterpret_cast<const float4*>(h->d_rows);
+    rp.ld4 = ld / 4;
+    rp.queries = reinterpret_cast<const float4*>(qprep);
+    rp.q_norms = qn;
+    rp.max_norm2_bits = h->metric == MLV_COSINE ? nullptr : (const uint32_t*)h->d_maxn2.p;
+    rp.cand = cand;
+    rp.cnt = cnt;
+    rp.flags = flags;
+    rp.cap = cap;
+    rp.kprime = kprime;
+    rp.k = k;
+    rp.P = pow2_ceil(std::max<uint32_t>(kprime, 2));
+    rp.out_dists = out_d;
+    rp.out_rows = out_r;
+    rp.out_counts = out_c;
+    rp.row_base = h->row_base;
+    rp.metric = h->metric;
+    if (l2)
+        rerank_kernel<METRIC_L2><<<nq, 256, (size_t)rp.P * 8, st>>>(rp);
+    else
+        rerank_kernel<METRIC_IP><<<nq, 256, (size_t)rp.P * 8, st>>>(rp);
+    h->launches++;
+    CK(h, cudaGetLastError());
+
+    // certificate check: the one synchronisation of this path
+    std::vector<uint32_t> hflags(nq);
+    CK(h, cudaMemcpyAsync(hflags.data(), flags, (size_t)nq * 4, cudaMemcpyDeviceToHost, st));
+    CK(h, cudaStreamSynchronize(st));
+    h->gemm_searches++;
+    h->gemm_queries += nq;
+    for (uint32_t q = 0; q < nq; q++) {
+        if (!hflags[q]) continue;
+        h->gemm_fallback_queries++;
+        rc = search_prepared(h, qprep + (size_t)q * ld, 1, k, filter_dev, out_d + (size_t)q * k, out_r + (size_t)q * k, out_c + q, st);
+        if (rc != MLV_OK) return rc;
+    }
     return MLV_OK;
 }
 
@@ -452,6 +677,8 @@ int mlv_index_create(uint32_t dim, int metric, uint64_t capacity_hint, int devic
     h->tune_r = env_int("MLV_SCAN_R", h->tune_r);
     h->tune_max_stages = env_int("MLV_SCAN_MAX_STAGES", h->tune_max_stages);
     h->tune_ctas = env_int("MLV_SCAN_CTAS", h->tune_ctas);
+    h->tune_gemm = env_int("MLV_GEMM", h->tune_gemm);
+    h->tune_gemm_min_nq = env_int("MLV_GEMM_MIN_NQ", h->tune_gemm_min_nq);
     DeviceGuard g(device);
     cudaDeviceProp prop;
     cudaError_t e = g.ok ? cudaGetDeviceProperties(&prop, device) : cudaErrorInvalidDevice;
@@ -488,13 +715,14 @@ int mlv_index_destroy(mlv_index_t h) {
     if (h->d_rows) cudaFree(h->d_rows);
     if (h->d_live) cudaFree(h->d_live);
     for (DevBuf* b : {&h->d_qraw, &h->d_q, &h->d_keys0, &h->d_keys1, &h->d_filter, &h->d_outd, &h->d_outr, &h->d_outc,
-                      &h->d_misc, &h->d_range, &h->d_timeline})
+                      &h->d_misc, &h->d_range, &h->d_timeline, &h->d_norms, &h->d_gq, &h->d_cand, &h->d_maxn2})
         free_dev(*b);
     if (h->h_stage.p) cudaFreeHost(h->h_stage.p);
-    for (auto& pr : h->pending) {
-        cudaEventDestroy(pr.first);
-        cudaEventDestroy(pr.second);
-    }
+    for (auto* vec : {&h->pending, &h->gemm_pending})
+        for (auto& pr : *vec) {
+            cudaEventDestroy(pr.first);
+            cudaEventDestroy(pr.second);
+        }
     for (auto ev : h->event_pool) cudaEventDestroy(ev);
     cudaStreamDestroy(h->stream);
     delete h;
@@ -517,6 +745,8 @@ int mlv_index_set_tuning(mlv_index_t h, const char* key, int value) {
     else if (k == "max_stages") h->tune_max_stages = value;
     else if (k == "ctas") h->tune_ctas = value;
     else if (k == "timeline") h->tune_timeline = value;
+    else if (k == "gemm") h->tune_gemm = value;
+    else if (k == "gemm_min_nq") h->tune_gemm_min_nq = value;
     else return fail(h, MLV_E_INVALID, "unknown tuning key " + k);
     return MLV_OK;
 }
@@ -632,6 +862,7 @@ int mlv_index_compact(mlv_index_t h, int64_t* old_to_new, uint64_t* new_rows) {
     h->d_rows = nrows;
     h->rows = total;
     h->n_deleted = 0;
+    h->norms_valid = 0;
     CK(h, cudaMemsetAsync(h->d_live, 0, h->live_words * 4, h->stream));
     if (total) {
         const uint64_t words = (total + 31) / 32;
@@ -653,6 +884,7 @@ int mlv_index_clear(mlv_index_t h) {
     }
     h->rows = 0;
     h->n_deleted = 0;
+    h->norms_valid = 0;
     return MLV_OK;
 }
 
@@ -671,7 +903,9 @@ int mlv_index_search_device(mlv_index_t h, const float* queries_dev, uint32_t nq
     }
     int rc = prep_queries(h, queries_dev, nq, st);
     if (rc != MLV_OK) return rc;
-    return search_prepared(h, nq, k, filter_bitmap_dev, out_dists_dev, out_rows_dev, out_counts_dev, st);
+    if (gemm_eligible(h, nq, k))
+        return search_gemm(h, (const float*)h->d_q.p, nq, k, filter_bitmap_dev, out_dists_dev, out_rows_dev, out_counts_dev, st);
+    return search_prepared(h, (const float*)h->d_q.p, nq, k, filter_bitmap_dev, out_dists_dev, out_rows_dev, out_counts_dev, st);
 }
 
 int mlv_index_search(mlv_index_t h, const float* queries, uint32_t nq, uint32_t k, const uint32_t* filter_bitmap,
@@ -796,7 +1030,7 @@ int mlv_index_info(mlv_index_t h, mlv_index_info_t* info) {
     info->row_base = h->row_base;
     size_t b = (size_t)h->capacity * h->ld * 4 + (size_t)h->live_words * 4;
     for (const DevBuf* d : {&h->d_qraw, &h->d_q, &h->d_keys0, &h->d_keys1, &h->d_filter, &h->d_outd, &h->d_outr, &h->d_outc,
-                            &h->d_misc, &h->d_range})
+                            &h->d_misc, &h->d_range, &h->d_norms, &h->d_gq, &h->d_cand, &h->d_maxn2})
         b += d->bytes;
     info->device_bytes = b;
     info->dim = h->dim;
@@ -851,6 +1085,90 @@ int mlv_index_scan_time_ms(mlv_index_t h, double* total_ms, uint64_t* launches) 
     h->pending.clear();
     if (total_ms) *total_ms = total;
     if (launches) *launches = n;
+    return MLV_OK;
+}
+
+int mlv_index_gemm_stats(mlv_index_t h, mlv_gemm_stats_t* out) {
+    if (!h || !out) return MLV_E_INVALID;
+    DeviceGuard g(h->device);
+    double total = 0;
+    uint64_t n = 0;
+    for (auto& pr : h->gemm_pending) {
+        CK(h, cudaEventSynchronize(pr.second));
+        float ms = 0;
+        CK(h, cudaEventElapsedTime(&ms, pr.first, pr.second));
+        total += ms;
+        n++;
+        h->event_pool.push_back(pr.first);
+        h->event_pool.push_back(pr.second);
+    }
+    h->gemm_pending.clear();
+    out->gemm_ms = total;
+    out->gemm_launches_timed = n;
+    out->searches = h->gemm_searches;
+    out->queries = h->gemm_queries;
+    out->fallback_queries = h->gemm_fallback_queries;
+    out->rounds = h->gemm_rounds;
+    return MLV_OK;
+}
+
+int mlv_index_debug_gemm(mlv_index_t h, const float* queries, uint32_t nq, float* out_approx) {
+    if (!h || !queries || !out_approx || nq == 0) return fail(h, MLV_E_INVALID, "bad argument");
+    if (h->rows == 0 || h->rows > SELECT_MAX_P || h->ld < (uint32_t)GEMM_BK) return fail(h, MLV_E_UNSUPPORTED, "debug_gemm needs 1..8192 rows and dim >= 32");
+    DeviceGuard g(h->device);
+    cudaStream_t st = h->stream;
+    int rc;
+    const uint32_t ld = h->ld;
+    const size_t qbytes = (size_t)nq * h->dim * 4;
+    if ((rc = ensure_dev(h, h->d_qraw, qbytes)) != MLV_OK) return rc;
+    CK(h, cudaMemcpyAsync(h->d_qraw.p, queries, qbytes, cudaMemcpyHostToDevice, st));
+    if ((rc = prep_queries(h, (const float*)h->d_qraw.p, nq, st)) != MLV_OK) return rc;
+    if (h->metric != MLV_COSINE && (rc = ensure_row_norms(h, st)) != MLV_OK) return rc;
+    const uint32_t nq_pad = (nq + GEMM_BN - 1) / GEMM_BN * GEMM_BN;
+    const uint32_t cap = pow2_ceil((uint32_t)h->rows);
+    const size_t qmat = (size_t)nq_pad * ld * 4;
+    if ((rc = ensure_dev(h, h->d_gq, 2 * qmat + (size_t)nq_pad * 16)) != MLV_OK) return rc;
+    if ((rc = ensure_dev(h, h->d_cand, (size_t)nq_pad * cap * 8)) != MLV_OK) return rc;
+    float* qhi = (float*)h->d_gq.p;
+    float* qlo = qhi + (size_t)nq_pad * ld;
+    float* qn = qlo + (size_t)nq_pad * ld;
+    float* thr = qn + nq_pad;
+    uint32_t* cnt = (uint32_t*)(thr + nq_pad);
+    uint32_t* flags = cnt + nq_pad;
+    split_queries_kernel<<<(nq_pad + 7) / 8, 256, 0, st>>>((const float*)h->d_q.p, qhi, qlo, qn, thr, cnt, flags, nq, nq_pad, ld);
+    CK(h, cudaGetLastError());
+    CUtensorMap mx, mqh, mql;
+    if ((rc = make_tile_map(h, &mx, h->d_rows, h->rows, GEMM_BM)) != MLV_OK) return rc;
+    if ((rc = make_tile_map(h, &mqh, qhi, nq_pad, GEMM_BN)) != MLV_OK) return rc;
+    if ((rc = make_tile_map(h, &mql, qlo, nq_pad, GEMM_BN)) != MLV_OK) return rc;
+    GemmParams gp{};
+    gp.n_rows = (uint32_t)h->rows;
+    gp.nq = nq;
+    gp.n_qtiles = nq_pad / GEMM_BN;
+    gp.n_kchunks = (ld + GEMM_BK - 1) / GEMM_BK;
+    gp.row_norms = h->metric == MLV_L2 ? (const float*)h->d_norms.p : nullptr;
+    gp.q_norms = qn;
+    gp.thr = thr;
+    gp.live = h->n_deleted ? h->d_live : nullptr;
+    gp.cand = (uint64_t*)h->d_cand.p;
+    gp.cand_cnt = cnt;
+    gp.cap = cap;
+    gp.row_tile0 = 0;
+    gp.row_tile1 = (uint32_t)((h->rows + GEMM_BM - 1) / GEMM_BM);
+    const int grid = (int)std::min<uint64_t>((uint64_t)gp.row_tile1 * gp.n_qtiles, (uint64_t)h->sm_count);
+    CK(h, h->metric == MLV_L2 ? launch_gemm_t<METRIC_L2>(mx, mqh, mql, gp, grid, st) : launch_gemm_t<METRIC_IP>(mx, mqh, mql, gp, grid, st));
+    h->launches += 3;
+    std::vector<uint64_t> keys((size_t)nq * cap);
+    std::vector<uint32_t> counts(nq);
+    CK(h, cudaMemcpyAsync(keys.data(), h->d_cand.p, keys.size() * 8, cudaMemcpyDeviceToHost, st));
+    CK(h, cudaMemcpyAsync(counts.data(), cnt, (size_t)nq * 4, cudaMemcpyDeviceToHost, st));
+    CK(h, cudaStreamSynchronize(st));
+    for (size_t i = 0; i < (size_t)nq * h->rows; i++) out_approx[i] = std::numeric_limits<float>::quiet_NaN();
+    for (uint32_t q = 0; q < nq; q++)
+        for (uint32_t i = 0; i < std::min(counts[q], cap); i++) {
+            const uint64_t key = keys[(size_t)q * cap + i];
+            if (key_row(key) < h->rows) out_approx[(size_t)q * h->rows + key_row(key)] = key_dist(key);
+        }
     return MLV_OK;
 }
 

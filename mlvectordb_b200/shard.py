@@ -204,6 +204,20 @@ class DeviceShard:
         self._ck(self._lib.mlv_index_debug_timeline(self._h, out.ctypes.data_as(C.POINTER(C.c_uint64)), max_ctas, C.byref(n)))
         return out[: n.value]
 
+    def gemm_stats(self) -> dict:
+        """Counters of the tensor-core batch path (``mlv_index_gemm_stats``)."""
+        st = _capi.GemmStats()
+        self._ck(self._lib.mlv_index_gemm_stats(self._h, C.byref(st)))
+        return {f: getattr(st, f) for f, _ in st._fields_}
+
+    def debug_gemm(self, queries: np.ndarray) -> np.ndarray:
+        """Approximate (3xTF32 GEMM-form) distances [nq, rows] of the tensor-core kernel (tests only)."""
+        q = np.ascontiguousarray(queries, dtype=np.float32).reshape(-1, self.dim)
+        out = np.empty((q.shape[0], self.rows), dtype=np.float32)
+        self._ck(self._lib.mlv_index_debug_gemm(self._h, q.ctypes.data_as(C.c_void_p), q.shape[0],
+                                                out.ctypes.data_as(C.c_void_p)))
+        return out
+
     def kernel_launches(self) -> int:
         n = C.c_uint64()
         self._ck(self._lib.mlv_index_kernel_launches(self._h, C.byref(n)))

@@ -1,0 +1,153 @@
+"""GPU parity of the tensor-core batch path (csrc/gemm_kernel.cuh) -- BASELINE.json configs[2].
+
+The tcgen05 3xTF32 GEMM only selects candidates; scores come from the exact re-rank in the scan
+kernel's arithmetic and uncertified queries fall back to the scan.  So the bar is stronger than
+the oracle tolerance: the batch path must return BIT-IDENTICAL (rows, scores, counts) to the scan
+path on the same handle, and both must match the CPU oracle within the north_star tolerance
+(|a-b| <= 1e-5*max(|a|,|b|) + 1e-6, ties with the k-th score may swap).
+"""
+import numpy as np
+import pytest
+
+from oracle import exact, synthetic
+
+pytestmark = pytest.mark.gpu
+
+
+def _shard(dim, space, **kw):
+    from mlvectordb_b200 import DeviceShard
+    return DeviceShard(dim, space, **kw)
+
+
+def _both_paths(s, Q, k, filt=None):
+    s.set_tuning("gemm", 0)
+    ref = s.search(Q, k, filt)
+    s.set_tuning("gemm", 1)
+    before = s.gemm_stats()
+    got = s.search(Q, k, filt)
+    after = s.gemm_stats()
+    assert after["searches"] == before["searches"] + 1, "the batch did not take the tensor-core path"
+    fallbacks = after["fallback_queries"] - before["fallback_queries"]
+    for a, b, name in zip(got, ref, ("dists", "rows", "counts")):
+        assert a.dtype == b.dtype and a.shape == b.shape
+        assert np.array_equal(a, b, equal_nan=True), f"{name}: tensor-core path differs from the scan path"
+    return got, fallbacks
+
+
+def _assert_oracle(got, X, Q, k, space, allow=None):
+    d, r, c = got
+    L, D = exact.knn(X, Q, k, space, allow=allow)
+    Xn = exact.normalize_rows(X) if space == "cosine" else X
+    Qn = exact.normalize_rows(Q) if space == "cosine" else np.asarray(Q, np.float32)
+    for i in range(len(L)):
+        assert c[i] == len(L[i])
+        msg = exact.check_topk_parity(
+            r[i, :c[i]], d[i, :c[i]], L[i], D[i],
+            all_ref_scores=lambda l, i=i: exact.distances(Xn[l:l + 1], Qn[i], space)[0])
+        assert msg is None, f"{space} q{i}: {msg}"
+
+
+@pytest.mark.parametrize("space", ["l2", "ip", "cosine"])
+def test_approximate_distances_are_3xtf32_accurate(space):
+    """The GEMM-form distances straight out of TMEM: error far below single-pass TF32 (2^-11)."""
+    n, dim, nq = 1000, 96, 300           # ragged: 8 row tiles (last short), 3 K chunks, 2 query tiles
+    X = synthetic.rows(3, 0, n, dim, scaled=True)
+    Q = synthetic.queries(3, nq, dim)
+    s = _shard(dim, space)
+    s.add(X)
+    A = s.debug_gemm(Q)
+    Xn = exact.normalize_rows(X) if space == "cosine" else X
+    Qn = exact.normalize_rows(Q) if space == "cosine" else Q
+    X64, Q64 = Xn.astype(np.float64), Qn.astype(np.float64)
+    dots = Q64 @ X64.T
+    if space == "l2":
+        true = (Q64 ** 2).sum(1)[:, None] + (X64 ** 2).sum(1)[None, :] - 2 * dots
+        scale = (np.sqrt((Q64 ** 2).sum(1))[:, None] + np.sqrt((X64 ** 2).sum(1))[None, :]) ** 2
+    else:
+        true = 1 - dots
+        scale = np.sqrt((Q64 ** 2).sum(1))[:, None] * np.sqrt((X64 ** 2).sum(1))[None, :] + 1e-30
+    assert not np.isnan(A).any(), "rows missing from the candidate dump"
+    rel = np.abs(A - true) / scale
+    assert rel.max() < 2e-6, f"max |a - true| / scale = {rel.max():.3e} (single-pass TF32 would be ~5e-4)"
+    s.close()
+
+
+@pytest.mark.parametrize("space", ["l2", "ip", "cosine"])
+@pytest.mark.parametrize("k", [10, 100])
+def test_batch_path_equals_scan_and_oracle(space, k):
+    n, dim, nq = 20_000, 96, 300
+    X = synthetic.rows(17, 0, n, dim, scaled=(space != "l2"))
+    Q = synthetic.queries(17, nq, dim)
+    Q[1] = X[n // 2]                      # planted exact match
+    X[7000] = X[123]                      # duplicated row: tie, ordered by row
+    Q[2] = X[123]
+    s = _shard(dim, space)
+    s.add(X)
+    got, fallbacks = _both_paths(s, Q, k)
+    assert fallbacks <= max(3, nq // 50), f"{fallbacks} of {nq} queries failed the certificate on benign data"
+    _assert_oracle(got, X, Q, k, space)
+    s.close()
+
+
+@pytest.mark.parametrize("n,dim,nq", [(16_385, 100, 257), (30_001, 33, 64), (50_000, 768, 40)])
+def test_ragged_shapes(n, dim, nq):
+    X = synthetic.rows(23, 0, n, dim, scaled=True)
+    Q = synthetic.queries(23, nq, dim)
+    s = _shard(dim, "cosine")
+    s.add(X)
+    got, _ = _both_paths(s, Q, 10)
+    _assert_oracle(got, X, Q, 10, "cosine")
+    s.close()
+
+
+def test_tombstones_and_filter_in_the_epilogue():
+    n, dim, nq = 25_000, 64, 280
+    X = synthetic.rows(29, 0, n, dim)
+    Q = synthetic.queries(29, nq, dim)
+    s = _shard(dim, "l2")
+    s.add(X)
+    rng = np.random.default_rng(1)
+    dead = rng.choice(n, size=5000, replace=False)
+    s.mark_deleted(dead)
+    live = np.ones(n, bool)
+    live[dead] = False
+    got, _ = _both_paths(s, Q, 10)
+    _assert_oracle(got, X, Q, 10, "l2", allow=live)
+    filt = rng.random(n) < 0.1
+    got, _ = _both_paths(s, Q, 10, filt)
+    _assert_oracle(got, X, Q, 10, "l2", allow=live & filt)
+    sparse = np.zeros(n, bool)
+    sparse[rng.choice(np.flatnonzero(live), size=7, replace=False)] = True   # fewer passing rows than k
+    got, _ = _both_paths(s, Q, 10, sparse)
+    assert (got[2] == 7).all()
+    _assert_oracle(got, X, Q, 10, "l2", allow=sparse)
+    s.close()
+
+
+def test_adversarial_row_order_falls_back_to_the_scan():
+    """Rows sorted far-to-near for one query: every round's rows beat the threshold, the candidate
+    buffer overflows, the query is re-run by the scan -- results stay exact."""
+    n, dim, nq = 40_000, 32, 64
+    X = synthetic.rows(41, 0, n, dim)
+    Q = synthetic.queries(41, nq, dim)
+    order = np.argsort(-((X - Q[0]) ** 2).sum(1), kind="stable")
+    X = np.ascontiguousarray(X[order])
+    s = _shard(dim, "l2")
+    s.add(X)
+    got, fallbacks = _both_paths(s, Q, 10)
+    assert fallbacks >= 1
+    _assert_oracle(got, X, Q, 10, "l2")
+    s.close()
+
+
+def test_large_batch_on_device_generated_rows():
+    """200k x 768 generated on the device, 512 queries: the batch path equals the scan path bit for bit."""
+    n, dim, nq = 200_000, 768, 512
+    s = _shard(dim, "cosine", capacity=n)
+    s.add_synthetic(42, 0, n, scaled=True)
+    Q = synthetic.queries(43, nq, dim)
+    Q[5] = synthetic.rows(42, 1234, 1, dim, scaled=True)[0]
+    got, fallbacks = _both_paths(s, Q, 10)
+    assert got[1][5, 0] == 1234
+    assert fallbacks <= 10
+    s.close()
