@@ -169,6 +169,35 @@ int mlv_merge_topk(int device, const float *dists_dev, const int64_t *rows_dev, 
                    uint32_t k, float *out_dists_dev, int64_t *out_rows_dev, int32_t *out_counts_dev, void *stream);
 
 /*
+ * Fused multi-GPU exchange (csrc/exchange.cuh): the exchange step of a row-sharded search done
+ * over NVLink peer memory by the search kernel itself.  One process per GPU: every rank creates
+ * an exchange object, the ranks swap the 64-byte CUDA IPC handles (any transport; the Python
+ * host uses torch.distributed.all_gather), connect, and attach the exchange to their shard
+ * together with every rank's row_base.  mlv_index_search_exchange_device then returns the
+ * GLOBAL top-k on every rank from a single kernel launch per group of <= 8 queries: local scan,
+ * last CTA folds the block lists, stores its k best into every peer's buffer, waits for the
+ * peers' lists (release/acquire flags at system scope) and merges.  Collective: every rank must
+ * make the same sequence of calls.  Supported when mlv_index_exchange_supported(h, k) != 0
+ * (k <= 13 on a 148-SM part); larger k uses the all-gather + mlv_merge_topk path.
+ * A peer that does not arrive within 20 s raises an error flag (mlv_exchange_check) instead of
+ * hanging the GPU.
+ */
+typedef struct mlv_exchange *mlv_exchange_t;
+#define MLV_EXCHANGE_HANDLE_BYTES 64
+int mlv_exchange_create(int device, uint32_t world, uint32_t rank, mlv_exchange_t *out, unsigned char *handle_out);
+/* all_handles: world * MLV_EXCHANGE_HANDLE_BYTES bytes, rank-major (this rank's own entry is ignored). */
+int mlv_exchange_connect(mlv_exchange_t x, const unsigned char *all_handles);
+/* MLV_OK, or MLV_E_CUDA when a peer timed out in an earlier search (synchronises the device). */
+int mlv_exchange_check(mlv_exchange_t x);
+int mlv_exchange_destroy(mlv_exchange_t x);
+/* row_bases: world entries, the global row of every rank's local row 0.  x == NULL detaches. */
+int mlv_index_attach_exchange(mlv_index_t h, mlv_exchange_t x, const uint64_t *row_bases);
+int mlv_index_exchange_supported(mlv_index_t h, uint32_t k);
+int mlv_index_search_exchange_device(mlv_index_t h, const float *queries_dev, uint32_t nq, uint32_t k,
+                                     const uint32_t *filter_bitmap_dev, float *out_dists_dev, int64_t *out_rows_dev,
+                                     int32_t *out_counts_dev, void *stream);
+
+/*
  * Measurement hooks (bench.py / profiles): when enabled, every search records CUDA events
  * around its scan kernel on the launching stream; mlv_index_scan_time_ms returns the sum
  * of the completed scan-kernel durations since the last call and how many launches that
@@ -179,7 +208,9 @@ int mlv_index_scan_time_ms(mlv_index_t h, double *total_ms, uint64_t *launches);
 /*
  * Experimental scan tuning (profiling sweeps): key in {"cw" consumer warps per CTA, "stage_kb"
  * ring-stage target size, "max_stages", "r" rows per warp step (0 = auto), "evict_first"
- * (-1 auto / 0 / 1), "ctas" grid size (0 = one per SM)}.  Results never depend on these.
+ * (-1 auto / 0 / 1), "ctas" grid size (0 = one per SM), "dynamic" (1 = work-stealing tile scheduler,
+ * 0 = static round-robin), "tile_batch" tiles claimed per atomic, "fused" (1 = the last CTA does the
+ * final select, 0 = separate select kernel)}.  Results never depend on these.
  */
 int mlv_index_set_tuning(mlv_index_t h, const char *key, int value);
 /*

@@ -81,6 +81,14 @@ SIGNATURES = {
     "mlv_index_set_tuning": (C.c_int, [_h, C.c_char_p, C.c_int]),
     "mlv_index_kernel_launches": (C.c_int, [_h, _u64p]),
     "mlv_index_debug_timeline": (C.c_int, [_h, _u64p, C.c_uint32, _u32p]),
+    "mlv_exchange_create": (C.c_int, [C.c_int, C.c_uint32, C.c_uint32, C.POINTER(_h), C.c_void_p]),
+    "mlv_exchange_connect": (C.c_int, [_h, C.c_void_p]),
+    "mlv_exchange_check": (C.c_int, [_h]),
+    "mlv_exchange_destroy": (C.c_int, [_h]),
+    "mlv_index_attach_exchange": (C.c_int, [_h, _h, C.c_void_p]),
+    "mlv_index_exchange_supported": (C.c_int, [_h, C.c_uint32]),
+    "mlv_index_search_exchange_device": (C.c_int, [_h, C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p,
+                                                   C.c_void_p, C.c_void_p]),
     "mlv_index_gemm_stats": (C.c_int, [_h, C.POINTER(GemmStats)]),
     "mlv_index_debug_gemm": (C.c_int, [_h, C.c_void_p, C.c_uint32, C.c_void_p]),
 }

@@ -1,0 +1,119 @@
+// exchange.cuh -- the one exchange step of a row-sharded search done over
+// NVLink peer memory inside the search kernel instead of an NCCL all-gather + merge launch.
+//
+// Every rank owns one exchange buffer (cudaMalloc, opened by all peers through CUDA IPC).  The
+// last CTA of a rank's scan writes its k best keys per query straight into every peer's buffer
+// (plain stores to peer-mapped addresses), publishes a sequence number with st.release.sys and
+// waits with ld.acquire.sys until every peer's sequence number has arrived in its own buffer;
+// then it merges the world * k candidates.  Two parity slots suffice: a rank can only reach
+// search s+2 after every peer has posted s+1, i.e. after every peer finished reading slot s.
+// The reference has no counterpart (single process; README.md:142-155 sketches sharding only).
+#pragma once
+#include "common.cuh"
+
+namespace mlv {
+
+constexpr uint32_t XCHG_MAX_WORLD = 16;
+constexpr uint32_t XCHG_MAX_NQ = 8;   // queries per scan launch
+constexpr uint32_t XCHG_MAX_K = 16;   // the fused exchange handles k <= 16
+constexpr uint32_t XCHG_SLOT_KEYS = XCHG_MAX_WORLD * XCHG_MAX_NQ * XCHG_MAX_K;  // u64 keys per parity slot
+// buffer layout (u64 words): keys[2][XCHG_MAX_WORLD][XCHG_MAX_NQ][XCHG_MAX_K], flags[2][XCHG_MAX_WORLD]
+constexpr uint32_t XCHG_FLAGS_OFF = 2 * XCHG_SLOT_KEYS;
+constexpr uint32_t XCHG_WORDS = XCHG_FLAGS_OFF + 2 * XCHG_MAX_WORLD;
+constexpr unsigned long long XCHG_TIMEOUT_NS = 20000000000ull;  // a peer that never arrives: flag an error, do not hang
+
+struct ExchangeView {
+    uint64_t* bufs[XCHG_MAX_WORLD];      // every rank's buffer as mapped into THIS process (bufs[rank] is local)
+    uint64_t row_bases[XCHG_MAX_WORLD];  // global row of each rank's local row 0 (ascending with rank)
+    uint32_t world, rank;
+    uint64_t seq;                        // 1-based, identical on all ranks for the same scan launch
+    int* error;                          // set to 1 when a peer did not answer in time
+};
+
+__device__ __forceinline__ unsigned long long global_timer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+
+// Called by `nthr` threads (tid 0..nthr-1, synchronised with named barrier 1).  `top` holds this
+// rank's nq * k keys (local rows, ascending per query, KEY_SENTINEL padded).  Writes the global
+// top-k of every query.  *s_valid is a zeroed shared counter.
+__device__ __forceinline__ void exchange_and_merge(const ExchangeView& x, const uint64_t* top, uint32_t nq, uint32_t k,
+                                                   float* out_dists, int64_t* out_rows, int32_t* out_counts, uint32_t tid,
+                                                   uint32_t nthr, uint32_t* s_valid) {
+    const uint32_t parity = (uint32_t)(x.seq & 1);
+    const uint32_t per_peer = nq * k;
+    for (uint32_t i = tid; i < x.world * per_peer; i += nthr) {
+        const uint32_t dst = i / per_peer, r = i - dst * per_peer;
+        const uint32_t qi = r / k, j = r - qi * k;
+        x.bufs[dst][(size_t)parity * XCHG_SLOT_KEYS + ((size_t)x.rank * XCHG_MAX_NQ + qi) * XCHG_MAX_K + j] = top[r];
+    }
+    __threadfence_system();
+    named_bar_sync(1, nthr);
+    if (tid < x.world) {
+        uint64_t* flag = x.bufs[tid] + XCHG_FLAGS_OFF + (size_t)parity * XCHG_MAX_WORLD + x.rank;
+        asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(flag), "l"(x.seq) : "memory");
+        // ... and wait for rank `tid`'s list in my own buffer
+        const uint64_t* mine = x.bufs[x.rank] + XCHG_FLAGS_OFF + (size_t)parity * XCHG_MAX_WORLD + tid;
+        const unsigned long long t0 = global_timer_ns();
+        for (;;) {
+            uint64_t v;
+            asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(mine) : "memory");
+            if (v >= x.seq) break;
+            if (global_timer_ns() - t0 > XCHG_TIMEOUT_NS) {
+                *x.error = 1;
+                atomicOr(s_valid, 0x80000000u);
+                break;
+            }
+        }
+    }
+    named_bar_sync(1, nthr);
+    if (*s_valid & 0x80000000u) {  // a peer never arrived: report count -1 instead of a partial merge
+        for (uint32_t qi = tid; qi < nq; qi += nthr) out_counts[qi] = -1;
+        return;
+    }
+    const volatile uint64_t* slot = x.bufs[x.rank] + (size_t)parity * XCHG_SLOT_KEYS;
+    const uint32_t mm = x.world * k;
+    for (uint32_t qi = 0; qi < nq; qi++) {
+        for (uint32_t e = tid; e < mm; e += nthr) {
+            const uint32_t se = e / k, je = e - se * k;
+            const uint64_t key = slot[((size_t)se * XCHG_MAX_NQ + qi) * XCHG_MAX_K + je];
+            const uint32_t de = (uint32_t)(key >> 32);
+            uint32_t rank = 0;
+            for (uint32_t i = 0; i < mm; i++) {
+                const uint32_t si = i / k, ji = i - si * k;
+                const uint64_t o = slot[((size_t)si * XCHG_MAX_NQ + qi) * XCHG_MAX_K + ji];
+                const uint32_t d_o = (uint32_t)(o >> 32);
+                // (distance, global row) == (distance, rank, local row); the slot index breaks sentinel ties
+                rank += (d_o < de) ||
+                        (d_o == de && (si < se || (si == se && ((uint32_t)o < (uint32_t)key || ((uint32_t)o == (uint32_t)key && ji < je)))));
+            }
+            if (rank < k) {
+                const bool valid = key != KEY_SENTINEL;
+                out_dists[qi * k + rank] = valid ? key_dist(key) : __int_as_float(0x7f800000);
+                out_rows[qi * k + rank] = valid ? (int64_t)(x.row_bases[se] + key_row(key)) : -1;
+                if (valid) atomicAdd(s_valid, 1u);
+            }
+        }
+        named_bar_sync(1, nthr);
+        if (tid == 0) {
+            out_counts[qi] = (int32_t)*s_valid;
+            *s_valid = 0;
+        }
+        named_bar_sync(1, nthr);
+    }
+}
+
+// A rank with nothing to scan (empty shard, everything tombstoned) still has to take part.
+__global__ void __launch_bounds__(256, 1) exchange_only_kernel(const ExchangeView x, uint32_t nq, uint32_t k, float* out_dists,
+                                                               int64_t* out_rows, int32_t* out_counts) {
+    __shared__ uint64_t top[XCHG_MAX_NQ * XCHG_MAX_K];
+    __shared__ uint32_t s_valid;
+    for (uint32_t i = threadIdx.x; i < nq * k; i += blockDim.x) top[i] = KEY_SENTINEL;
+    if (threadIdx.x == 0) s_valid = 0;
+    __syncthreads();
+    exchange_and_merge(x, top, nq, k, out_dists, out_rows, out_counts, threadIdx.x, blockDim.x, &s_valid);
+}
+
+}  // namespace mlv

@@ -45,6 +45,14 @@ struct ScanCfg {
 
 }  // namespace
 
+struct mlv_exchange {
+    int device = 0;
+    uint32_t world = 1, rank = 0;
+    uint64_t* bufs[XCHG_MAX_WORLD] = {nullptr};  // bufs[rank] = local allocation, others IPC-opened
+    int* d_error = nullptr;
+    bool connected = false;
+};
+
 struct mlv_index {
     int device = 0;
     uint32_t dim = 0, ld = 0;
@@ -67,6 +75,13 @@ struct mlv_index {
     int tune_cw = 8, tune_stage_kb = 32, tune_evict_first = -1, tune_r = 0, tune_max_stages = 8, tune_ctas = 0;
     int tune_timeline = 0;
     int last_grid = 0;
+    // dynamic tile scheduler + fused final select (scan_kernel.cuh tail)
+    DevBuf d_sched;
+    int tune_dynamic = 1, tune_tile_batch = 4, tune_fused = 1;
+    // fused multi-GPU exchange (exchange.cuh)
+    mlv_exchange* xchg = nullptr;
+    uint64_t xchg_row_bases[XCHG_MAX_WORLD] = {0};
+    uint64_t xseq = 0;
     // tensor-core batch path (gemm_kernel.cuh)
     DevBuf d_norms, d_gq, d_cand, d_maxn2;
     uint64_t norms_valid = 0;  // rows [0, norms_valid) of d_norms are current
@@ -321,12 +336,53 @@ cudaError_t ensure_select_attrs(int device) {
     return cudaSuccess;
 }
 
-// qprep: prepared queries [nq, ld] in device memory; all output pointers in device memory
+int ensure_sched(mlv_index* h) {
+    if (h->d_sched.p) return MLV_OK;
+    int rc = ensure_dev(h, h->d_sched, 8);
+    if (rc != MLV_OK) return rc;
+    CK(h, cudaMemset(h->d_sched.p, 0, h->d_sched.bytes));
+    return MLV_OK;
+}
+
+void fill_sched(mlv_index* h, ScanParams& p) {
+    p.sched = h->tune_dynamic ? (uint32_t*)h->d_sched.p : nullptr;
+    p.tile_batch = (uint32_t)std::max(h->tune_tile_batch, 1);
+}
+
+// can the last CTA fold the whole grid's lists (and hold its scratch in the idle ring)?
+bool fused_ok(const mlv_index* h, const ScanCfg& c, uint32_t k) {
+    if (!h->tune_dynamic || !h->tune_fused) return false;
+    if ((uint64_t)c.grid * k > SCAN_FUSED_MAX_KEYS || (uint64_t)c.CW * k > 1024) return false;
+    return (size_t)c.S * c.stage_f4 * 16 >= ((size_t)SCAN_FUSED_MAX_KEYS + (size_t)c.NQ * k) * 8;
+}
+
+// the exchange path must take the same decision on every rank, whatever its shard's grid is
+bool exchange_ok(const mlv_index* h, uint32_t k) {
+    return h->xchg && h->xchg->connected && h->tune_dynamic && h->tune_fused && k <= XCHG_MAX_K &&
+           (uint64_t)h->sm_count * k <= SCAN_FUSED_MAX_KEYS;
+}
+
+void fill_exchange(mlv_index* h, ExchangeView& x) {
+    const mlv_exchange* e = h->xchg;
+    x.world = e->world;
+    x.rank = e->rank;
+    for (uint32_t i = 0; i < e->world; i++) {
+        x.bufs[i] = e->bufs[i];
+        x.row_bases[i] = h->xchg_row_bases[i];
+    }
+    x.error = e->d_error;
+}
+
+// qprep: prepared queries [nq, ld] in device memory; all output pointers in device memory.
+// exchange: merge with the other ranks' results over peer memory (caller checked exchange_ok).
 int search_prepared(mlv_index* h, const float* qprep, uint32_t nq, uint32_t k, const uint32_t* filter_dev, float* out_d,
-                    int64_t* out_r, int32_t* out_c, cudaStream_t st) {
+                    int64_t* out_r, int32_t* out_c, cudaStream_t st, bool exchange = false) {
     ScanCfg c;
     int rc = choose_cfg(h, nq, k, false, &c);
     if (rc != MLV_OK) return rc;
+    if ((rc = ensure_sched(h)) != MLV_OK) return rc;
+    const bool fused = fused_ok(h, c, k);
+    if (exchange && !fused) return fail(h, MLV_E_UNSUPPORTED, "exchange search needs the fused final select");
     const uint32_t F = SELECT_MAX_P / k;  // lists one select CTA can fold (>= 8)
     // bound the candidate scratch: chunk * grid * k keys
     uint32_t chunk = (uint32_t)std::max<size_t>(1, ((size_t)64 << 20) / ((size_t)c.grid * k * 8));
@@ -353,6 +409,10 @@ int search_prepared(mlv_index* h, const float* qprep, uint32_t nq, uint32_t k, c
     p.live = h->n_deleted ? h->d_live : nullptr;
     p.filter = filter_dev;
     p.evict_first = c.evict_first;
+    fill_sched(h, p);
+    p.fused = fused ? 1 : 0;
+    p.row_base = h->row_base;
+    if (exchange) fill_exchange(h, p.xchg);
     if (h->tune_timeline) {
         rc = ensure_dev(h, h->d_timeline, (size_t)c.grid * 4 * 8);
         if (rc != MLV_OK) return rc;
@@ -366,8 +426,15 @@ int search_prepared(mlv_index* h, const float* qprep, uint32_t nq, uint32_t k, c
             p.queries = reinterpret_cast<const float4*>(qprep + (size_t)(q0 + g0) * h->ld);
             p.nq_valid = std::min<uint32_t>(c.NQ, nchunk - g0);
             p.out_keys = (uint64_t*)h->d_keys0.p + (size_t)g0 * c.grid * k;
+            if (fused) {
+                p.out_dists = out_d + (size_t)(q0 + g0) * k;
+                p.out_rows = out_r + (size_t)(q0 + g0) * k;
+                p.out_counts = out_c + (q0 + g0);
+                if (exchange) p.xchg.seq = ++h->xseq;
+            }
             CK(h, launch_scan(h, p, c, false, st));
         }
+        if (fused) continue;  // the last CTA of every launch already wrote the final top-k
         // fold the grid's lists into one per query
         const uint64_t* in = (const uint64_t*)h->d_keys0.p;
         uint64_t* bufs[2] = {(uint64_t*)h->d_keys1.p, (uint64_t*)h->d_keys0.p};
@@ -677,6 +744,9 @@ int mlv_index_create(uint32_t dim, int metric, uint64_t capacity_hint, int devic
     h->tune_r = env_int("MLV_SCAN_R", h->tune_r);
     h->tune_max_stages = env_int("MLV_SCAN_MAX_STAGES", h->tune_max_stages);
     h->tune_ctas = env_int("MLV_SCAN_CTAS", h->tune_ctas);
+    h->tune_dynamic = env_int("MLV_SCAN_DYNAMIC", h->tune_dynamic);
+    h->tune_tile_batch = env_int("MLV_SCAN_TILE_BATCH", h->tune_tile_batch);
+    h->tune_fused = env_int("MLV_SCAN_FUSED", h->tune_fused);
     h->tune_gemm = env_int("MLV_GEMM", h->tune_gemm);
     h->tune_gemm_min_nq = env_int("MLV_GEMM_MIN_NQ", h->tune_gemm_min_nq);
     DeviceGuard g(device);
@@ -715,7 +785,7 @@ int mlv_index_destroy(mlv_index_t h) {
     if (h->d_rows) cudaFree(h->d_rows);
     if (h->d_live) cudaFree(h->d_live);
     for (DevBuf* b : {&h->d_qraw, &h->d_q, &h->d_keys0, &h->d_keys1, &h->d_filter, &h->d_outd, &h->d_outr, &h->d_outc,
-                      &h->d_misc, &h->d_range, &h->d_timeline, &h->d_norms, &h->d_gq, &h->d_cand, &h->d_maxn2})
+                      &h->d_misc, &h->d_range, &h->d_timeline, &h->d_norms, &h->d_gq, &h->d_cand, &h->d_maxn2, &h->d_sched})
         free_dev(*b);
     if (h->h_stage.p) cudaFreeHost(h->h_stage.p);
     for (auto* vec : {&h->pending, &h->gemm_pending})
@@ -745,6 +815,9 @@ int mlv_index_set_tuning(mlv_index_t h, const char* key, int value) {
     else if (k == "max_stages") h->tune_max_stages = value;
     else if (k == "ctas") h->tune_ctas = value;
     else if (k == "timeline") h->tune_timeline = value;
+    else if (k == "dynamic") h->tune_dynamic = value;
+    else if (k == "tile_batch") h->tune_tile_batch = value;
+    else if (k == "fused") h->tune_fused = value;
     else if (k == "gemm") h->tune_gemm = value;
     else if (k == "gemm_min_nq") h->tune_gemm_min_nq = value;
     else return fail(h, MLV_E_INVALID, "unknown tuning key " + k);
@@ -908,6 +981,130 @@ int mlv_index_search_device(mlv_index_t h, const float* queries_dev, uint32_t nq
     return search_prepared(h, (const float*)h->d_q.p, nq, k, filter_bitmap_dev, out_dists_dev, out_rows_dev, out_counts_dev, st);
 }
 
+int mlv_exchange_create(int device, uint32_t world, uint32_t rank, mlv_exchange_t* out, unsigned char* handle_out) {
+    if (!out || !handle_out || world == 0 || world > XCHG_MAX_WORLD || rank >= world) return MLV_E_INVALID;
+    *out = nullptr;
+    int ndev = mlv_device_count();
+    if (ndev <= 0) return MLV_E_NO_DEVICE;
+    if (device < 0 || device >= ndev) return MLV_E_INVALID;
+    DeviceGuard g(device);
+    mlv_exchange* x = new (std::nothrow) mlv_exchange();
+    if (!x) return MLV_E_NOMEM;
+    x->device = device;
+    x->world = world;
+    x->rank = rank;
+    static_assert(sizeof(cudaIpcMemHandle_t) == MLV_EXCHANGE_HANDLE_BYTES, "IPC handle size");
+    cudaIpcMemHandle_t hd;
+    void* buf = nullptr;
+    cudaError_t e = cudaMalloc(&buf, (size_t)XCHG_WORDS * 8 + 64);
+    if (e == cudaSuccess) e = cudaMemset(buf, 0, (size_t)XCHG_WORDS * 8 + 64);
+    if (e == cudaSuccess) e = cudaIpcGetMemHandle(&hd, buf);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        if (buf) cudaFree(buf);
+        delete x;
+        return MLV_E_CUDA;
+    }
+    x->bufs[rank] = (uint64_t*)buf;
+    x->d_error = (int*)((uint64_t*)buf + XCHG_WORDS);  // behind the slots, in the same allocation
+    memcpy(handle_out, &hd, sizeof(hd));
+    x->connected = world == 1;
+    *out = x;
+    return MLV_OK;
+}
+
+int mlv_exchange_connect(mlv_exchange_t x, const unsigned char* all_handles) {
+    if (!x || !all_handles) return MLV_E_INVALID;
+    DeviceGuard g(x->device);
+    for (uint32_t r = 0; r < x->world; r++) {
+        if (r == x->rank || x->bufs[r]) continue;
+        cudaIpcMemHandle_t hd;
+        memcpy(&hd, all_handles + (size_t)r * sizeof(hd), sizeof(hd));
+        void* ptr = nullptr;
+        if (cudaIpcOpenMemHandle(&ptr, hd, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+            cudaGetLastError();
+            return MLV_E_CUDA;
+        }
+        x->bufs[r] = (uint64_t*)ptr;
+    }
+    x->connected = true;
+    return MLV_OK;
+}
+
+int mlv_exchange_check(mlv_exchange_t x) {
+    if (!x) return MLV_E_INVALID;
+    DeviceGuard g(x->device);
+    int err = 0;
+    if (cudaMemcpy(&err, x->d_error, sizeof(int), cudaMemcpyDeviceToHost) != cudaSuccess) {
+        cudaGetLastError();
+        return MLV_E_CUDA;
+    }
+    return err ? MLV_E_CUDA : MLV_OK;
+}
+
+int mlv_exchange_destroy(mlv_exchange_t x) {
+    if (!x) return MLV_E_INVALID;
+    DeviceGuard g(x->device);
+    cudaDeviceSynchronize();
+    for (uint32_t r = 0; r < x->world; r++) {
+        if (!x->bufs[r]) continue;
+        if (r == x->rank)
+            cudaFree(x->bufs[r]);
+        else
+            cudaIpcCloseMemHandle(x->bufs[r]);
+    }
+    cudaGetLastError();
+    delete x;
+    return MLV_OK;
+}
+
+int mlv_index_attach_exchange(mlv_index_t h, mlv_exchange_t x, const uint64_t* row_bases) {
+    if (!h) return MLV_E_INVALID;
+    if (!x) {
+        h->xchg = nullptr;
+        return MLV_OK;
+    }
+    if (!row_bases || x->device != h->device) return fail(h, MLV_E_INVALID, "exchange lives on another device");
+    h->xchg = x;
+    for (uint32_t i = 0; i < x->world; i++) h->xchg_row_bases[i] = row_bases[i];
+    return MLV_OK;
+}
+
+int mlv_index_exchange_supported(mlv_index_t h, uint32_t k) {
+    if (!h) return 0;
+    return exchange_ok(h, k) ? 1 : 0;
+}
+
+int mlv_index_search_exchange_device(mlv_index_t h, const float* queries_dev, uint32_t nq, uint32_t k,
+                                     const uint32_t* filter_bitmap_dev, float* out_dists_dev, int64_t* out_rows_dev,
+                                     int32_t* out_counts_dev, void* stream) {
+    if (!h || !queries_dev || !out_dists_dev || !out_rows_dev || !out_counts_dev || nq == 0 || k == 0) return fail(h, MLV_E_INVALID, "bad argument");
+    if (!exchange_ok(h, k)) return fail(h, MLV_E_UNSUPPORTED, "no connected exchange, or k too large for the fused exchange");
+    DeviceGuard g(h->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (h->rows == h->n_deleted) {
+        // nothing to scan here, but the peers wait for this rank's (empty) lists: same launch grouping
+        // as a scanning rank (groups of up to XCHG_MAX_NQ queries, one sequence number each)
+        ExchangeView x{};
+        fill_exchange(h, x);
+        ScanCfg c;
+        int rc0 = choose_cfg(h, nq, k, false, &c);  // same query grouping as a scanning rank
+        if (rc0 != MLV_OK) return rc0;
+        for (uint32_t g0 = 0; g0 < nq; g0 += c.NQ) {
+            const uint32_t n = std::min<uint32_t>(c.NQ, nq - g0);
+            x.seq = ++h->xseq;
+            exchange_only_kernel<<<1, 256, 0, st>>>(x, n, k, out_dists_dev + (size_t)g0 * k, out_rows_dev + (size_t)g0 * k,
+                                                   out_counts_dev + g0);
+            h->launches++;
+        }
+        CK(h, cudaGetLastError());
+        return MLV_OK;
+    }
+    int rc = prep_queries(h, queries_dev, nq, st);
+    if (rc != MLV_OK) return rc;
+    return search_prepared(h, (const float*)h->d_q.p, nq, k, filter_bitmap_dev, out_dists_dev, out_rows_dev, out_counts_dev, st, true);
+}
+
 int mlv_index_search(mlv_index_t h, const float* queries, uint32_t nq, uint32_t k, const uint32_t* filter_bitmap,
                      float* out_dists, int64_t* out_rows, int32_t* out_counts) {
     if (!h || !queries || !out_dists || !out_rows || !out_counts || nq == 0 || k == 0) return fail(h, MLV_E_INVALID, "bad argument");
@@ -985,6 +1182,8 @@ int mlv_index_range_search(mlv_index_t h, const float* queries, uint32_t nq, flo
     p.evict_first = c.evict_first;
     p.radius = radius;
     p.max_hits = max_hits;
+    if ((rc = ensure_sched(h)) != MLV_OK) return rc;
+    fill_sched(h, p);
     for (uint32_t q = 0; q < nq; q++) {
         p.queries = reinterpret_cast<const float4*>((float*)h->d_q.p + (size_t)q * h->ld);
         p.nq_valid = 1;

@@ -18,6 +18,7 @@
 //     k keys per (query, block); select_kernel.cuh merges the blocks' lists.
 #pragma once
 #include "common.cuh"
+#include "exchange.cuh"
 
 namespace mlv {
 
@@ -25,6 +26,8 @@ constexpr int METRIC_L2 = 0;
 constexpr int METRIC_IP = 1;  // cosine == ip over rows/queries normalised at add/query time
 constexpr int SCAN_MAX_CW = 16;                          // consumer warps per CTA (runtime, <= this)
 constexpr int SCAN_MAX_THREADS = (SCAN_MAX_CW + 1) * 32;  // 544 -> ptxas may use up to 120 registers
+
+constexpr uint32_t SCAN_FUSED_MAX_KEYS = 2048;  // keys the last CTA folds (gridDim.x * k)
 
 struct ScanParams {
     const float4* rows;     // [n_rows, ld4]
@@ -46,13 +49,21 @@ struct ScanParams {
     unsigned long long max_hits;
     int evict_first;
     unsigned long long* timeline;  // debug: 4 globaltimer stamps per CTA (nullptr = off)
+    // dynamic tile scheduler: sched[0] = next batch of `tile_batch` tiles, sched[1] = CTAs finished.
+    // Both are zero between launches (the last CTA to finish resets them).  nullptr = static round-robin.
+    uint32_t* sched;
+    uint32_t tile_batch;
+    // fused final select (top-k mode, needs sched, gridDim.x * k <= SCAN_FUSED_MAX_KEYS): the last
+    // CTA to finish folds the grid's lists into the final ascending top-k instead of select_kernel
+    int fused;
+    float* out_dists;     // [nq_valid][k]
+    int64_t* out_rows;    // [nq_valid][k]
+    int32_t* out_counts;  // [nq_valid]
+    uint64_t row_base;
+    // fused multi-GPU exchange (world > 1): the last CTA also writes its k best into every peer's
+    // exchange buffer over NVLink, waits for the peers' lists and merges -- no NCCL call, no extra launch
+    ExchangeView xchg;
 };
-
-__device__ __forceinline__ unsigned long long global_timer_ns() {
-    unsigned long long t;
-    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
-    return t;
-}
 
 struct StageMeta {
     uint32_t row0;
@@ -168,7 +179,7 @@ __global__ void __launch_bounds__(SCAN_MAX_THREADS, 1) scan_kernel(const ScanPar
         if (lane == 0) {
             uint32_t stage = 0, phase = 0;
             const uint64_t pol = policy_evict_first();
-            for (uint32_t tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+            auto issue = [&](uint32_t tile) {
                 mbar_wait(&empty[stage], phase ^ 1);
                 const uint32_t row0 = tile * p.tile_rows;
                 const uint32_t n = min(p.tile_rows, p.n_rows - row0);
@@ -186,6 +197,20 @@ __global__ void __launch_bounds__(SCAN_MAX_THREADS, 1) scan_kernel(const ScanPar
                     stage = 0;
                     phase ^= 1;
                 }
+            };
+            if (p.sched) {
+                // work stealing: claim `tile_batch` consecutive tiles per atomic; the next claim is
+                // in flight while this batch's copies are issued
+                uint32_t next = atomicAdd(p.sched, 1u);
+                for (;;) {
+                    const uint32_t t0 = next * p.tile_batch;
+                    if (t0 >= p.n_tiles) break;
+                    next = atomicAdd(p.sched, 1u);
+                    const uint32_t t1 = min(t0 + p.tile_batch, p.n_tiles);
+                    for (uint32_t tile = t0; tile < t1; tile++) issue(tile);
+                }
+            } else {
+                for (uint32_t tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) issue(tile);
             }
             mbar_wait(&empty[stage], phase ^ 1);
             meta[stage].n_rows = -1;
@@ -272,37 +297,128 @@ __global__ void __launch_bounds__(SCAN_MAX_THREADS, 1) scan_kernel(const ScanPar
         }
     }
     if (p.timeline && tid == 0) p.timeline[blockIdx.x * 4 + 2] = global_timer_ns();
-    if (RANGE) return;
-
-    // ------------------------------------------------- fold the CW warp lists into one per query
-    named_bar_sync(1, CW * 32);
-    for (int qi = warp; qi < NQ && (uint32_t)qi < p.nq_valid; qi += CW) {
-        uint64_t* home = lists + ((size_t)warp * NQ + qi) * k;
-        uint64_t m = 0;
-        for (uint32_t j = lane; j < k; j += 32) {
-            uint64_t v = home[j];
-            m = v > m ? v : m;
-        }
-        uint64_t hthr = warp_max_u64(m);
-        for (int ow = 0; ow < CW; ow++) {
-            if (ow == warp) continue;
-            const uint64_t* other = lists + ((size_t)ow * NQ + qi) * k;
-            for (uint32_t j0 = 0; j0 < k; j0 += 32) {
-                const uint64_t key = (j0 + lane < k) ? other[j0 + lane] : KEY_SENTINEL;
-                unsigned mm = __ballot_sync(0xffffffffu, key < hthr);
-                while (mm) {
-                    const int src = __ffs(mm) - 1;
-                    mm &= mm - 1;
-                    const uint64_t ckey = shfl_u64(key, src);
-                    if (ckey < hthr) hthr = list_replace_max(home, k, ckey, hthr, lane);
+    const uint32_t nthr = (uint32_t)CW * 32u;  // consumer threads (the producer warp has left)
+    if (!RANGE) {
+        // --------------------------------------------- fold the CW warp lists into one per query
+        named_bar_sync(1, CW * 32);
+        const uint32_t n_in = (uint32_t)CW * k;
+        if (n_in <= 1024) {
+            // rank by counting: the block's k best come out sorted ascending; sentinels tie-break by index
+            for (uint32_t qi = 0; qi < p.nq_valid; qi++) {
+                uint64_t* out = p.out_keys + ((size_t)qi * gridDim.x + blockIdx.x) * k;
+                for (uint32_t e = tid; e < n_in; e += nthr) {
+                    const uint32_t w = e / k, j = e - w * k;
+                    const uint64_t key = lists[((size_t)w * NQ + qi) * k + j];
+                    uint32_t rank = 0;
+                    for (uint32_t w2 = 0; w2 < (uint32_t)CW; w2++) {
+                        const uint64_t* l2 = lists + ((size_t)w2 * NQ + qi) * k;
+                        for (uint32_t j2 = 0; j2 < k; j2++) {
+                            const uint64_t o = l2[j2];
+                            rank += (o < key) || (o == key && (w2 * k + j2) < e);
+                        }
+                    }
+                    if (rank < k) out[rank] = key;
                 }
             }
+        } else {
+            for (int qi = warp; qi < NQ && (uint32_t)qi < p.nq_valid; qi += CW) {
+                uint64_t* home = lists + ((size_t)warp * NQ + qi) * k;
+                uint64_t m = 0;
+                for (uint32_t j = lane; j < k; j += 32) {
+                    uint64_t v = home[j];
+                    m = v > m ? v : m;
+                }
+                uint64_t hthr = warp_max_u64(m);
+                for (int ow = 0; ow < CW; ow++) {
+                    if (ow == warp) continue;
+                    const uint64_t* other = lists + ((size_t)ow * NQ + qi) * k;
+                    for (uint32_t j0 = 0; j0 < k; j0 += 32) {
+                        const uint64_t key = (j0 + lane < k) ? other[j0 + lane] : KEY_SENTINEL;
+                        unsigned mm = __ballot_sync(0xffffffffu, key < hthr);
+                        while (mm) {
+                            const int src = __ffs(mm) - 1;
+                            mm &= mm - 1;
+                            const uint64_t ckey = shfl_u64(key, src);
+                            if (ckey < hthr) hthr = list_replace_max(home, k, ckey, hthr, lane);
+                        }
+                    }
+                }
+                __syncwarp();
+                uint64_t* out = p.out_keys + ((size_t)qi * gridDim.x + blockIdx.x) * k;
+                for (uint32_t j = lane; j < k; j += 32) out[j] = home[j];
+            }
         }
-        __syncwarp();
-        uint64_t* out = p.out_keys + ((size_t)qi * gridDim.x + blockIdx.x) * k;
-        for (uint32_t j = lane; j < k; j += 32) out[j] = home[j];
     }
     if (p.timeline && tid == 0) p.timeline[blockIdx.x * 4 + 3] = global_timer_ns();
+    if (!p.sched) return;
+
+    // ------------------------------------------------- last CTA: scheduler reset, fused final select
+    __shared__ uint32_t s_ticket, s_m, s_valid;
+    __shared__ unsigned long long s_T;
+    named_bar_sync(1, CW * 32);  // every out_keys store of this CTA has been issued
+    if (tid == 0) {
+        __threadfence();
+        s_valid = 0;
+        s_ticket = atomicAdd(p.sched + 1, 1u);
+    }
+    named_bar_sync(1, CW * 32);
+    if (s_ticket != gridDim.x - 1) return;
+    __threadfence();
+    if (!RANGE && p.fused) {
+        // The ring is idle now: reuse it.  cand[SCAN_FUSED_MAX_KEYS] | top[XCHG_MAX_NQ][XCHG_MAX_K or k]
+        uint64_t* cand = reinterpret_cast<uint64_t*>(ring);
+        uint64_t* top = cand + SCAN_FUSED_MAX_KEYS;  // [nq_valid][k]
+        const uint32_t n_lists = gridDim.x, n = n_lists * k;
+        for (uint32_t qi = 0; qi < p.nq_valid; qi++) {
+            const uint64_t* keys = p.out_keys + (size_t)qi * n_lists * k;
+            if (tid == 0) {
+                s_T = KEY_SENTINEL;
+                s_m = 0;
+            }
+            named_bar_sync(1, CW * 32);
+            // every block list is sorted, so its last key is its maximum; the global k-th best is at
+            // most the smallest of those maxima: only keys <= T can be in the final top-k
+            for (uint32_t l = tid; l < n_lists; l += nthr) atomicMin(&s_T, (unsigned long long)__ldcg(keys + (size_t)l * k + k - 1));
+            named_bar_sync(1, CW * 32);
+            const uint64_t T = s_T;
+            for (uint32_t i = tid; i < n; i += nthr) {
+                const uint64_t key = __ldcg(keys + i);
+                if (key <= T) cand[atomicAdd(&s_m, 1u)] = key;
+            }
+            named_bar_sync(1, CW * 32);
+            const uint32_t m = s_m;
+            for (uint32_t e = tid; e < m; e += nthr) {
+                const uint64_t key = cand[e];
+                uint32_t rank = 0;
+                for (uint32_t i = 0; i < m; i++) {
+                    const uint64_t o = cand[i];
+                    rank += (o < key) || (o == key && i < e);
+                }
+                if (rank < k) top[qi * k + rank] = key;
+            }
+            named_bar_sync(1, CW * 32);
+        }
+        const ExchangeView& x = p.xchg;
+        if (x.world <= 1) {
+            for (uint32_t i = tid; i < p.nq_valid * k; i += nthr) {
+                const uint64_t key = top[i];
+                const bool valid = key != KEY_SENTINEL;
+                p.out_dists[i] = valid ? key_dist(key) : __int_as_float(0x7f800000);
+                p.out_rows[i] = valid ? (int64_t)(p.row_base + key_row(key)) : -1;
+            }
+            for (uint32_t qi = tid; qi < p.nq_valid; qi += nthr) {
+                int c = 0;
+                for (uint32_t j = 0; j < k; j++) c += top[qi * k + j] != KEY_SENTINEL;
+                p.out_counts[qi] = c;
+            }
+        } else {
+            exchange_and_merge(x, top, p.nq_valid, k, p.out_dists, p.out_rows, p.out_counts, tid, nthr, &s_valid);
+        }
+    }
+    if (tid == 0) {
+        p.sched[0] = 0;
+        p.sched[1] = 0;
+    }
 }
 
 }  // namespace mlv

@@ -158,6 +158,23 @@ class DeviceShard:
             self._h, C.c_void_p(q_ptr), int(nq), int(k), C.c_void_p(filter_ptr) if filter_ptr else None,
             C.c_void_p(out_d_ptr), C.c_void_p(out_r_ptr), C.c_void_p(out_c_ptr), C.c_void_p(stream)))
 
+    # -- fused multi-GPU exchange (include/mlv_index.h: mlv_exchange_*) ---------------------
+    def attach_exchange(self, exchange: "Exchange", row_bases) -> None:
+        rb = np.ascontiguousarray(row_bases, dtype=np.uint64)
+        assert rb.shape[0] == exchange.world
+        self._ck(self._lib.mlv_index_attach_exchange(self._h, exchange._x, rb.ctypes.data))
+        self._exchange = exchange  # keep it alive as long as the shard uses it
+
+    def exchange_supported(self, k: int) -> bool:
+        return bool(self._lib.mlv_index_exchange_supported(self._h, int(k)))
+
+    def search_exchange_device(self, q_ptr: int, nq: int, k: int, out_d_ptr: int, out_r_ptr: int, out_c_ptr: int,
+                               filter_ptr: int = 0, stream: int = 0) -> None:
+        """Collective: local scan + peer-memory exchange + merge in one kernel; outputs hold the GLOBAL top-k."""
+        self._ck(self._lib.mlv_index_search_exchange_device(
+            self._h, C.c_void_p(q_ptr), int(nq), int(k), C.c_void_p(filter_ptr) if filter_ptr else None,
+            C.c_void_p(out_d_ptr), C.c_void_p(out_r_ptr), C.c_void_p(out_c_ptr), C.c_void_p(stream)))
+
     def range_search(self, queries: np.ndarray, radius: float, filt=None, max_hits: int = 1024):
         """-> list per query of (dists f32 [hits], rows i64 [hits]) ascending (d, row)."""
         q = np.ascontiguousarray(queries, dtype=np.float32)
@@ -222,3 +239,40 @@ class DeviceShard:
         n = C.c_uint64()
         self._ck(self._lib.mlv_index_kernel_launches(self._h, C.byref(n)))
         return int(n.value)
+
+
+class Exchange:
+    """Peer-memory exchange buffers of one rank (``mlv_exchange_*``); see ``csrc/exchange.cuh``."""
+
+    HANDLE_BYTES = 64
+
+    def __init__(self, device: int, world: int, rank: int):
+        self._lib = _capi.lib()
+        self._x = C.c_void_p()
+        self.world, self.rank, self.device = int(world), int(rank), int(device)
+        hb = (C.c_ubyte * self.HANDLE_BYTES)()
+        check(self._lib.mlv_exchange_create(self.device, self.world, self.rank, C.byref(self._x), hb))
+        self.handle = bytes(hb)
+
+    def connect(self, all_handles) -> None:
+        """``all_handles``: the ``handle`` of every rank, rank-major."""
+        blob = b"".join(all_handles)
+        assert len(blob) == self.world * self.HANDLE_BYTES
+        buf = (C.c_ubyte * len(blob)).from_buffer_copy(blob)
+        check(self._lib.mlv_exchange_connect(self._x, buf))
+
+    def check(self) -> None:
+        st = self._lib.mlv_exchange_check(self._x)
+        if st != _capi.MLV_OK:
+            raise RuntimeError("exchange: a peer rank did not post its candidates within the timeout")
+
+    def close(self) -> None:
+        if getattr(self, "_x", None) and self._x.value:
+            self._lib.mlv_exchange_destroy(self._x)
+            self._x = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

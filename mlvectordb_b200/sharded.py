@@ -68,8 +68,12 @@ def merge_topk_device(gd: torch.Tensor, gr: torch.Tensor, k: int):
 class ShardedIndex:
     """One namespace, rows sharded over the ranks of ``group``.  Every rank calls every method."""
 
+    # batches of this many queries or more run the local tensor-core path (csrc/gemm_kernel.cuh) and
+    # merge through NCCL; smaller ones use the fused scan + peer-memory exchange kernel
+    EXCHANGE_MAX_NQ = 32
+
     def __init__(self, dim: int, space: str, total_rows: int, device: Optional[torch.device] = None, group=None,
-                 local_search: Optional[Callable] = None, merge: Optional[Callable] = None):
+                 local_search: Optional[Callable] = None, merge: Optional[Callable] = None, fused_exchange: bool = True):
         self.dim, self.space, self.total_rows = int(dim), space, int(total_rows)
         self.group = group
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
@@ -81,9 +85,42 @@ class ShardedIndex:
         self._local_search = local_search or self._device_local_search
         self._merge = merge or merge_topk_device
         self.merge_launches = 0
+        self.exchange = None
         if local_search is None:
             from .shard import DeviceShard
             self.shard = DeviceShard(dim, space, capacity=max(self.hi - self.lo, 1), device=device.index, row_base=self.lo)
+            if self.world > 1 and fused_exchange:
+                self._setup_exchange()
+
+    def _setup_exchange(self) -> None:
+        """Swap CUDA IPC handles of the per-rank exchange buffers (``csrc/exchange.cuh``) and attach them.
+
+        If any rank cannot map its peers (IPC disabled in the container), every rank stays on the
+        NCCL all-gather path -- still the GPU path, just two collectives and a merge launch more.
+        """
+        from .shard import Exchange
+        ok, ex = 1, None
+        try:
+            ex = Exchange(self.device.index, self.world, self.rank)
+        except RuntimeError:
+            ok = 0
+        handles = [None] * self.world
+        dist.all_gather_object(handles, (ok, ex.handle if ex else b""), group=self.group)
+        if all(h[0] for h in handles):
+            try:
+                ex.connect([h[1] for h in handles])
+            except RuntimeError:
+                ok = 0
+        else:
+            ok = 0
+        flags = [None] * self.world
+        dist.all_gather_object(flags, ok, group=self.group)
+        if all(flags):
+            bases = [shard_range(self.total_rows, r, self.world)[0] for r in range(self.world)]
+            self.shard.attach_exchange(ex, bases)
+            self.exchange = ex
+        elif ex is not None:
+            ex.close()
 
     # -- data -------------------------------------------------------------------------------
     def add_synthetic(self, seed: int, scaled: bool) -> None:
@@ -108,6 +145,15 @@ class ShardedIndex:
     def search_device(self, q: torch.Tensor, k: int):
         """``q``: [nq, dim] fp32 tensor on this rank's device (same on every rank).  Returns the
         global top-k ``(dists [nq,k], rows [nq,k], counts [nq])`` on every rank, nothing synchronised."""
+        if self.exchange is not None and q.shape[0] < self.EXCHANGE_MAX_NQ and self.shard.exchange_supported(k):
+            # one kernel per group of <= 8 queries: scan + peer-memory exchange + merge (csrc/exchange.cuh)
+            nq = q.shape[0]
+            d = torch.empty((nq, k), dtype=torch.float32, device=q.device)
+            r = torch.empty((nq, k), dtype=torch.int64, device=q.device)
+            c = torch.empty((nq,), dtype=torch.int32, device=q.device)
+            stream = torch.cuda.current_stream(q.device).cuda_stream
+            self.shard.search_exchange_device(q.data_ptr(), nq, k, d.data_ptr(), r.data_ptr(), c.data_ptr(), stream=stream)
+            return d, r, c
         d, r, c = self._local_search(q, k)
         if self.world == 1:
             return d, r, c
@@ -121,9 +167,16 @@ class ShardedIndex:
         qd = q.pin_memory().to(self.device, non_blocking=True)
         d, r, c = self.search_device(qd, k)
         out = (d.cpu().numpy(), r.cpu().numpy(), c.cpu().numpy())  # .cpu() synchronises the stream
+        if (out[2] < 0).any():
+            raise RuntimeError("sharded search: a peer rank did not post its candidates within the exchange timeout")
         return out
 
     def close(self) -> None:
         if self.shard is not None:
             self.shard.close()
             self.shard = None
+        if self.exchange is not None:
+            if dist.is_initialized():
+                dist.barrier(group=self.group)  # nobody unmaps a buffer a peer may still write
+            self.exchange.close()
+            self.exchange = None

@@ -1,0 +1,78 @@
+"""One rank of the multi-GPU test (launched by tests/test_gpu_sharded.py, one process per GPU).
+
+usage: _nccl_worker.py RANK WORLD PORT
+Every rank holds a row shard (``ShardedIndex``); rank 0 additionally holds the whole matrix in one
+``DeviceShard`` and checks that the sharded results -- fused peer-memory exchange for k <= 13,
+NCCL all-gather + merge kernel for larger k, tensor-core path for batches -- are bit-identical to
+the unsharded search.
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def main():
+    rank, world, port = (int(x) for x in sys.argv[1:4])
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    device = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=device)
+    from mlvectordb_b200 import DeviceShard
+    from mlvectordb_b200.sharded import ShardedIndex
+    from oracle import synthetic
+
+    def check(total_rows, dim, space, k, nq, expect_exchange, delete_every=0):
+        idx = ShardedIndex(dim, space, total_rows, device=device)
+        idx.add_synthetic(7, scaled=True)
+        assert (idx.exchange is not None) == (world > 1), "peer-memory exchange was not set up"
+        Q = synthetic.queries(9, nq, dim)
+        if total_rows > 5:
+            Q[0] = synthetic.rows(7, total_rows - 2, 1, dim, scaled=True)[0]   # exact match in the last shard
+        if delete_every and idx.hi > idx.lo:
+            dead = np.arange(idx.lo, idx.hi, delete_every, dtype=np.uint64) - idx.lo
+            idx.shard.mark_deleted(dead)
+        assert idx.shard.exchange_supported(k) == expect_exchange
+        launches0 = idx.merge_launches
+        for rep in range(3):                      # repeated: parity slots of the exchange get reused
+            d, r, c = idx.search(Q, k)
+        used_exchange = expect_exchange and nq < ShardedIndex.EXCHANGE_MAX_NQ
+        assert (idx.merge_launches == launches0) == used_exchange
+        if rank == 0:
+            whole = DeviceShard(dim, space, capacity=total_rows, device=rank)
+            whole.add_synthetic(7, 0, total_rows, True)
+            if delete_every:
+                dead_all = np.concatenate([np.arange(lo, hi, delete_every, dtype=np.uint64)
+                                           for lo, hi in (idx_range(total_rows, rr, world) for rr in range(world)) if hi > lo])
+                whole.mark_deleted(dead_all)
+            wd, wr, wc = whole.search(Q, k)
+            assert np.array_equal(c, wc), (c, wc)
+            assert np.array_equal(r, wr), f"rows differ ({space}, n={total_rows}, k={k}, nq={nq})"
+            assert np.array_equal(d, wd, equal_nan=True)
+            if total_rows > 5:
+                assert r[0, 0] == total_rows - 2
+            whole.close()
+        idx.close()
+
+    def idx_range(n, r, w):
+        from mlvectordb_b200.sharded import shard_range
+        return shard_range(n, r, w)
+
+    check(200_003, 64, "cosine", 10, 5, True)              # fused exchange, ragged shards
+    check(200_003, 64, "l2", 10, 19, True)                 # several launch groups per call (nq > 8)
+    check(50_000, 96, "ip", 13, 3, True, delete_every=3)   # tombstones
+    check(1, 32, "l2", 4, 2, True)                         # rank 1.. hold nothing: exchange_only_kernel
+    check(200_003, 64, "cosine", 100, 4, False)            # k too large for the fused exchange: NCCL path
+    check(120_000, 128, "l2", 10, 300, True)               # large batch: local tensor-core path + NCCL merge
+    dist.barrier()
+    print(f"rank {rank} ok", flush=True)
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
