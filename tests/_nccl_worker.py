@@ -54,7 +54,7 @@ def main():
             assert np.array_equal(c, wc), (c, wc)
             assert np.array_equal(r, wr), f"rows differ ({space}, n={total_rows}, k={k}, nq={nq})"
             assert np.array_equal(d, wd, equal_nan=True)
-            if total_rows > 5:
+            if total_rows > 5 and space != "ip" and not delete_every:   # the planted exact match wins (not under ip)
                 assert r[0, 0] == total_rows - 2
             whole.close()
         idx.close()
