@@ -5,8 +5,9 @@
 // last CTA of a rank's scan writes its k best keys per query straight into every peer's buffer
 // (plain stores to peer-mapped addresses), publishes a sequence number with st.release.sys and
 // waits with ld.acquire.sys until every peer's sequence number has arrived in its own buffer;
-// then it merges the world * k candidates.  Two parity slots suffice: a rank can only reach
-// search s+2 after every peer has posted s+1, i.e. after every peer finished reading slot s.
+// then it merges the world * k candidates.  Slots are indexed by seq mod 4: searches alternate
+// between at most two streams per handle, a rank can only reach search s+4 after every peer has
+// posted s+2, and a peer posts s+2 (same stream as s) only after it finished reading slot s.
 // The reference has no counterpart (single process; README.md:142-155 sketches sharding only).
 #pragma once
 #include "common.cuh"
@@ -17,9 +18,10 @@ constexpr uint32_t XCHG_MAX_WORLD = 16;
 constexpr uint32_t XCHG_MAX_NQ = 8;   // queries per scan launch
 constexpr uint32_t XCHG_MAX_K = 16;   // the fused exchange handles k <= 16
 constexpr uint32_t XCHG_SLOT_KEYS = XCHG_MAX_WORLD * XCHG_MAX_NQ * XCHG_MAX_K;  // u64 keys per parity slot
-// buffer layout (u64 words): keys[2][XCHG_MAX_WORLD][XCHG_MAX_NQ][XCHG_MAX_K], flags[2][XCHG_MAX_WORLD]
-constexpr uint32_t XCHG_FLAGS_OFF = 2 * XCHG_SLOT_KEYS;
-constexpr uint32_t XCHG_WORDS = XCHG_FLAGS_OFF + 2 * XCHG_MAX_WORLD;
+constexpr uint32_t XCHG_SLOTS = 4;
+// buffer layout (u64 words): keys[XCHG_SLOTS][XCHG_MAX_WORLD][XCHG_MAX_NQ][XCHG_MAX_K], flags[XCHG_SLOTS][XCHG_MAX_WORLD]
+constexpr uint32_t XCHG_FLAGS_OFF = XCHG_SLOTS * XCHG_SLOT_KEYS;
+constexpr uint32_t XCHG_WORDS = XCHG_FLAGS_OFF + XCHG_SLOTS * XCHG_MAX_WORLD;
 constexpr unsigned long long XCHG_TIMEOUT_NS = 20000000000ull;  // a peer that never arrives: flag an error, do not hang
 
 struct ExchangeView {
@@ -42,7 +44,7 @@ __device__ __forceinline__ unsigned long long global_timer_ns() {
 __device__ __forceinline__ void exchange_and_merge(const ExchangeView& x, const uint64_t* top, uint32_t nq, uint32_t k,
                                                    float* out_dists, int64_t* out_rows, int32_t* out_counts, uint32_t tid,
                                                    uint32_t nthr, uint32_t* s_valid) {
-    const uint32_t parity = (uint32_t)(x.seq & 1);
+    const uint32_t parity = (uint32_t)(x.seq % XCHG_SLOTS);
     const uint32_t per_peer = nq * k;
     for (uint32_t i = tid; i < x.world * per_peer; i += nthr) {
         const uint32_t dst = i / per_peer, r = i - dst * per_peer;

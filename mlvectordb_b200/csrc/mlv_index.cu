@@ -35,6 +35,17 @@ struct HostBuf {
     size_t bytes = 0;
 };
 
+// Scratch of one in-flight search.  A handle keeps MLV_LANES of them, picked by the stream a search
+// is enqueued on, so searches on different streams overlap on the GPU (the next query's scan fills
+// the SMs the previous query's straggling / exchanging CTAs have left).
+constexpr int MLV_LANES = 4;
+struct Lane {
+    cudaStream_t stream = nullptr;
+    bool used = false;
+    uint64_t last_use = 0;
+    DevBuf d_q, d_keys0, d_keys1, d_sched;
+};
+
 struct ScanCfg {
     int R, NQ, CW;
     uint32_t T, S, stage_f4;
@@ -64,7 +75,9 @@ struct mlv_index {
     cudaStream_t stream = nullptr;
     int sm_count = 0;
     size_t smem_optin = 0;
-    DevBuf d_qraw, d_q, d_keys0, d_keys1, d_filter, d_outd, d_outr, d_outc, d_misc, d_range, d_timeline;
+    DevBuf d_qraw, d_filter, d_outd, d_outr, d_outc, d_misc, d_range, d_timeline;
+    Lane lanes[MLV_LANES];
+    uint64_t lane_clock = 0;
     HostBuf h_stage;
     std::string err;
     bool timing = false;
@@ -75,8 +88,7 @@ struct mlv_index {
     int tune_cw = 8, tune_stage_kb = 32, tune_evict_first = -1, tune_r = 0, tune_max_stages = 8, tune_ctas = 0;
     int tune_timeline = 0;
     int last_grid = 0;
-    // dynamic tile scheduler + fused final select (scan_kernel.cuh tail)
-    DevBuf d_sched;
+    // dynamic tile scheduler + fused final select (scan_kernel.cuh tail); counters live in the lanes
     int tune_dynamic = 1, tune_tile_batch = 4, tune_fused = 1;
     // fused multi-GPU exchange (exchange.cuh)
     mlv_exchange* xchg = nullptr;
@@ -336,16 +348,38 @@ cudaError_t ensure_select_attrs(int device) {
     return cudaSuccess;
 }
 
-int ensure_sched(mlv_index* h) {
-    if (h->d_sched.p) return MLV_OK;
-    int rc = ensure_dev(h, h->d_sched, 8);
+// The lane of the stream a search runs on; a new stream takes the least recently used lane
+// (after making sure that lane's previous stream is done with the buffers).
+Lane* lane_for(mlv_index* h, cudaStream_t st) {
+    Lane* lru = &h->lanes[0];
+    for (Lane& l : h->lanes) {
+        if (l.used && l.stream == st) {
+            l.last_use = ++h->lane_clock;
+            return &l;
+        }
+        if (!l.used) {
+            if (lru->used) lru = &l;
+        } else if (lru->used && l.last_use < lru->last_use) {
+            lru = &l;
+        }
+    }
+    if (lru->used) cudaStreamSynchronize(lru->stream);
+    lru->used = true;
+    lru->stream = st;
+    lru->last_use = ++h->lane_clock;
+    return lru;
+}
+
+int ensure_sched(mlv_index* h, Lane* ln) {
+    if (ln->d_sched.p) return MLV_OK;
+    int rc = ensure_dev(h, ln->d_sched, 8);
     if (rc != MLV_OK) return rc;
-    CK(h, cudaMemset(h->d_sched.p, 0, h->d_sched.bytes));
+    CK(h, cudaMemset(ln->d_sched.p, 0, ln->d_sched.bytes));
     return MLV_OK;
 }
 
-void fill_sched(mlv_index* h, ScanParams& p) {
-    p.sched = h->tune_dynamic ? (uint32_t*)h->d_sched.p : nullptr;
+void fill_sched(mlv_index* h, Lane* ln, ScanParams& p) {
+    p.sched = h->tune_dynamic ? (uint32_t*)ln->d_sched.p : nullptr;
     p.tile_batch = (uint32_t)std::max(h->tune_tile_batch, 1);
 }
 
@@ -380,7 +414,8 @@ int search_prepared(mlv_index* h, const float* qprep, uint32_t nq, uint32_t k, c
     ScanCfg c;
     int rc = choose_cfg(h, nq, k, false, &c);
     if (rc != MLV_OK) return rc;
-    if ((rc = ensure_sched(h)) != MLV_OK) return rc;
+    Lane* ln = lane_for(h, st);
+    if ((rc = ensure_sched(h, ln)) != MLV_OK) return rc;
     const bool fused = fused_ok(h, c, k);
     if (exchange && !fused) return fail(h, MLV_E_UNSUPPORTED, "exchange search needs the fused final select");
     const uint32_t F = SELECT_MAX_P / k;  // lists one select CTA can fold (>= 8)
@@ -388,11 +423,11 @@ int search_prepared(mlv_index* h, const float* qprep, uint32_t nq, uint32_t k, c
     uint32_t chunk = (uint32_t)std::max<size_t>(1, ((size_t)64 << 20) / ((size_t)c.grid * k * 8));
     chunk = std::max<uint32_t>(chunk / c.NQ * c.NQ, c.NQ);
     chunk = std::min(chunk, nq);
-    rc = ensure_dev(h, h->d_keys0, (size_t)chunk * c.grid * k * 8);
+    rc = ensure_dev(h, ln->d_keys0, (size_t)chunk * c.grid * k * 8);
     if (rc != MLV_OK) return rc;
     const uint32_t lists1 = ((uint32_t)c.grid + F - 1) / F;
     if (lists1 > 1) {
-        rc = ensure_dev(h, h->d_keys1, (size_t)chunk * lists1 * k * 8);
+        rc = ensure_dev(h, ln->d_keys1, (size_t)chunk * lists1 * k * 8);
         if (rc != MLV_OK) return rc;
     }
     CK(h, ensure_select_attrs(h->device));
@@ -409,7 +444,7 @@ int search_prepared(mlv_index* h, const float* qprep, uint32_t nq, uint32_t k, c
     p.live = h->n_deleted ? h->d_live : nullptr;
     p.filter = filter_dev;
     p.evict_first = c.evict_first;
-    fill_sched(h, p);
+    fill_sched(h, ln, p);
     p.fused = fused ? 1 : 0;
     p.row_base = h->row_base;
     if (exchange) fill_exchange(h, p.xchg);
@@ -425,7 +460,7 @@ int search_prepared(mlv_index* h, const float* qprep, uint32_t nq, uint32_t k, c
         for (uint32_t g0 = 0; g0 < nchunk; g0 += c.NQ) {
             p.queries = reinterpret_cast<const float4*>(qprep + (size_t)(q0 + g0) * h->ld);
             p.nq_valid = std::min<uint32_t>(c.NQ, nchunk - g0);
-            p.out_keys = (uint64_t*)h->d_keys0.p + (size_t)g0 * c.grid * k;
+            p.out_keys = (uint64_t*)ln->d_keys0.p + (size_t)g0 * c.grid * k;
             if (fused) {
                 p.out_dists = out_d + (size_t)(q0 + g0) * k;
                 p.out_rows = out_r + (size_t)(q0 + g0) * k;
@@ -436,8 +471,8 @@ int search_prepared(mlv_index* h, const float* qprep, uint32_t nq, uint32_t k, c
         }
         if (fused) continue;  // the last CTA of every launch already wrote the final top-k
         // fold the grid's lists into one per query
-        const uint64_t* in = (const uint64_t*)h->d_keys0.p;
-        uint64_t* bufs[2] = {(uint64_t*)h->d_keys1.p, (uint64_t*)h->d_keys0.p};
+        const uint64_t* in = (const uint64_t*)ln->d_keys0.p;
+        uint64_t* bufs[2] = {(uint64_t*)ln->d_keys1.p, (uint64_t*)ln->d_keys0.p};
         uint32_t n_lists = (uint32_t)c.grid;
         int flip = 0;
         for (;;) {
@@ -468,10 +503,11 @@ int search_prepared(mlv_index* h, const float* qprep, uint32_t nq, uint32_t k, c
 }
 
 int prep_queries(mlv_index* h, const float* q_dev_raw, uint32_t nq, cudaStream_t st) {
-    int rc = ensure_dev(h, h->d_q, (size_t)nq * h->ld * 4);
+    Lane* ln = lane_for(h, st);
+    int rc = ensure_dev(h, ln->d_q, (size_t)nq * h->ld * 4);
     if (rc != MLV_OK) return rc;
     const int wpb = 4;
-    prep_queries_kernel<<<(nq + wpb - 1) / wpb, wpb * 32, 0, st>>>(q_dev_raw, (float*)h->d_q.p, nq, h->dim, h->ld,
+    prep_queries_kernel<<<(nq + wpb - 1) / wpb, wpb * 32, 0, st>>>(q_dev_raw, (float*)ln->d_q.p, nq, h->dim, h->ld,
                                                                  h->metric == MLV_COSINE);
     h->launches++;
     CK(h, cudaGetLastError());
@@ -784,9 +820,11 @@ int mlv_index_destroy(mlv_index_t h) {
     cudaStreamSynchronize(h->stream);
     if (h->d_rows) cudaFree(h->d_rows);
     if (h->d_live) cudaFree(h->d_live);
-    for (DevBuf* b : {&h->d_qraw, &h->d_q, &h->d_keys0, &h->d_keys1, &h->d_filter, &h->d_outd, &h->d_outr, &h->d_outc,
-                      &h->d_misc, &h->d_range, &h->d_timeline, &h->d_norms, &h->d_gq, &h->d_cand, &h->d_maxn2, &h->d_sched})
+    for (DevBuf* b : {&h->d_qraw, &h->d_filter, &h->d_outd, &h->d_outr, &h->d_outc, &h->d_misc, &h->d_range, &h->d_timeline,
+                      &h->d_norms, &h->d_gq, &h->d_cand, &h->d_maxn2})
         free_dev(*b);
+    for (Lane& l : h->lanes)
+        for (DevBuf* b : {&l.d_q, &l.d_keys0, &l.d_keys1, &l.d_sched}) free_dev(*b);
     if (h->h_stage.p) cudaFreeHost(h->h_stage.p);
     for (auto* vec : {&h->pending, &h->gemm_pending})
         for (auto& pr : *vec) {
@@ -977,8 +1015,8 @@ int mlv_index_search_device(mlv_index_t h, const float* queries_dev, uint32_t nq
     int rc = prep_queries(h, queries_dev, nq, st);
     if (rc != MLV_OK) return rc;
     if (gemm_eligible(h, nq, k))
-        return search_gemm(h, (const float*)h->d_q.p, nq, k, filter_bitmap_dev, out_dists_dev, out_rows_dev, out_counts_dev, st);
-    return search_prepared(h, (const float*)h->d_q.p, nq, k, filter_bitmap_dev, out_dists_dev, out_rows_dev, out_counts_dev, st);
+        return search_gemm(h, (const float*)lane_for(h, st)->d_q.p, nq, k, filter_bitmap_dev, out_dists_dev, out_rows_dev, out_counts_dev, st);
+    return search_prepared(h, (const float*)lane_for(h, st)->d_q.p, nq, k, filter_bitmap_dev, out_dists_dev, out_rows_dev, out_counts_dev, st);
 }
 
 int mlv_exchange_create(int device, uint32_t world, uint32_t rank, mlv_exchange_t* out, unsigned char* handle_out) {
@@ -1102,7 +1140,7 @@ int mlv_index_search_exchange_device(mlv_index_t h, const float* queries_dev, ui
     }
     int rc = prep_queries(h, queries_dev, nq, st);
     if (rc != MLV_OK) return rc;
-    return search_prepared(h, (const float*)h->d_q.p, nq, k, filter_bitmap_dev, out_dists_dev, out_rows_dev, out_counts_dev, st, true);
+    return search_prepared(h, (const float*)lane_for(h, st)->d_q.p, nq, k, filter_bitmap_dev, out_dists_dev, out_rows_dev, out_counts_dev, st, true);
 }
 
 int mlv_index_search(mlv_index_t h, const float* queries, uint32_t nq, uint32_t k, const uint32_t* filter_bitmap,
@@ -1182,10 +1220,11 @@ int mlv_index_range_search(mlv_index_t h, const float* queries, uint32_t nq, flo
     p.evict_first = c.evict_first;
     p.radius = radius;
     p.max_hits = max_hits;
-    if ((rc = ensure_sched(h)) != MLV_OK) return rc;
-    fill_sched(h, p);
+    Lane* ln = lane_for(h, h->stream);
+    if ((rc = ensure_sched(h, ln)) != MLV_OK) return rc;
+    fill_sched(h, ln, p);
     for (uint32_t q = 0; q < nq; q++) {
-        p.queries = reinterpret_cast<const float4*>((float*)h->d_q.p + (size_t)q * h->ld);
+        p.queries = reinterpret_cast<const float4*>((float*)lane_for(h, h->stream)->d_q.p + (size_t)q * h->ld);
         p.nq_valid = 1;
         p.range_counts = d_counts + q;
         p.range_keys = d_keys + (size_t)q * slots;
@@ -1228,9 +1267,11 @@ int mlv_index_info(mlv_index_t h, mlv_index_info_t* info) {
     info->capacity = h->capacity;
     info->row_base = h->row_base;
     size_t b = (size_t)h->capacity * h->ld * 4 + (size_t)h->live_words * 4;
-    for (const DevBuf* d : {&h->d_qraw, &h->d_q, &h->d_keys0, &h->d_keys1, &h->d_filter, &h->d_outd, &h->d_outr, &h->d_outc,
-                            &h->d_misc, &h->d_range, &h->d_norms, &h->d_gq, &h->d_cand, &h->d_maxn2})
+    for (const DevBuf* d : {&h->d_qraw, &h->d_filter, &h->d_outd, &h->d_outr, &h->d_outc, &h->d_misc, &h->d_range, &h->d_norms,
+                            &h->d_gq, &h->d_cand, &h->d_maxn2})
         b += d->bytes;
+    for (const Lane& l : h->lanes)
+        for (const DevBuf* d : {&l.d_q, &l.d_keys0, &l.d_keys1, &l.d_sched}) b += d->bytes;
     info->device_bytes = b;
     info->dim = h->dim;
     info->ld = h->ld;
@@ -1334,7 +1375,7 @@ int mlv_index_debug_gemm(mlv_index_t h, const float* queries, uint32_t nq, float
     float* thr = qn + nq_pad;
     uint32_t* cnt = (uint32_t*)(thr + nq_pad);
     uint32_t* flags = cnt + nq_pad;
-    split_queries_kernel<<<(nq_pad + 7) / 8, 256, 0, st>>>((const float*)h->d_q.p, qhi, qlo, qn, thr, cnt, flags, nq, nq_pad, ld);
+    split_queries_kernel<<<(nq_pad + 7) / 8, 256, 0, st>>>((const float*)lane_for(h, st)->d_q.p, qhi, qlo, qn, thr, cnt, flags, nq, nq_pad, ld);
     CK(h, cudaGetLastError());
     CUtensorMap mx, mqh, mql;
     if ((rc = make_tile_map(h, &mx, h->d_rows, h->rows, GEMM_BM)) != MLV_OK) return rc;

@@ -163,13 +163,32 @@ class ShardedIndex:
 
     def search(self, queries: np.ndarray, k: int):
         """Host buffers in, host buffers out (pinned staging, H2D + D2H inside the call)."""
-        q = torch.from_numpy(np.ascontiguousarray(queries, dtype=np.float32).reshape(-1, self.dim))
-        qd = q.pin_memory().to(self.device, non_blocking=True)
+        q = np.ascontiguousarray(queries, dtype=np.float32).reshape(-1, self.dim)
+        nq = q.shape[0]
+        st = self._staging(nq, k)
+        st["q"][:nq].copy_(torch.from_numpy(q))
+        qd = st["q"][:nq].to(self.device, non_blocking=True)
         d, r, c = self.search_device(qd, k)
-        out = (d.cpu().numpy(), r.cpu().numpy(), c.cpu().numpy())  # .cpu() synchronises the stream
+        st["d"][:nq].copy_(d, non_blocking=True)
+        st["r"][:nq].copy_(r, non_blocking=True)
+        st["c"][:nq].copy_(c, non_blocking=True)
+        torch.cuda.current_stream(self.device).synchronize()   # the one host sync of the call
+        out = (st["d"][:nq].numpy().copy(), st["r"][:nq].numpy().copy(), st["c"][:nq].numpy().copy())
         if (out[2] < 0).any():
             raise RuntimeError("sharded search: a peer rank did not post its candidates within the exchange timeout")
         return out
+
+    def _staging(self, nq: int, k: int):
+        """Pinned host staging reused across calls (one allocation per (nq, k) growth)."""
+        st = getattr(self, "_stage", None)
+        if st is None or st["q"].shape[0] < nq or st["d"].shape[1] != k:
+            cap = max(nq, 8)
+            st = {"q": torch.empty((cap, self.dim), dtype=torch.float32).pin_memory(),
+                  "d": torch.empty((cap, k), dtype=torch.float32).pin_memory(),
+                  "r": torch.empty((cap, k), dtype=torch.int64).pin_memory(),
+                  "c": torch.empty((cap,), dtype=torch.int32).pin_memory()}
+            self._stage = st
+        return st
 
     def close(self) -> None:
         if self.shard is not None:
