@@ -169,6 +169,26 @@ int mlv_merge_topk(int device, const float *dists_dev, const int64_t *rows_dev, 
                    uint32_t k, float *out_dists_dev, int64_t *out_rows_dev, int32_t *out_counts_dev, void *stream);
 
 /*
+ * Prepared filters.  A filter bitmap passed per call (filter_bitmap above) is turned into a list
+ * of passing-and-live rows on the device before every search, and the scan then copies ONLY
+ * those rows out of HBM (row-granular bulk copies), so a selective filter costs
+ * selectivity x the bytes of an unfiltered scan.  For a predicate that is searched repeatedly,
+ * mlv_filter_create uploads the bitmap and builds the list once; mlv_index_set_filter binds
+ * it, and every search / range search on the handle whose own filter_bitmap argument is NULL is
+ * restricted to it until mlv_index_set_filter(h, NULL).  The list follows later adds, deletes
+ * and compaction automatically (rows appended after creation do not pass).  Dense filters
+ * (>= 75 % passing) stream all rows and mask instead.  No reference code exists for filters
+ * (README.md:123,477 only); semantics = hnswlib-0.8 knn_query(filter=...) restated in
+ * oracle/exact.py (`allow`).
+ */
+typedef struct mlv_filter *mlv_filter_t;
+int mlv_filter_create(mlv_index_t h, const uint32_t *bitmap, uint64_t n_words, mlv_filter_t *out);
+/* live rows that pass (synchronises when the count is not known yet) */
+int mlv_filter_passing(mlv_filter_t f, uint64_t *passing);
+int mlv_filter_destroy(mlv_filter_t f);
+int mlv_index_set_filter(mlv_index_t h, mlv_filter_t f);
+
+/*
  * Fused multi-GPU exchange (csrc/exchange.cuh): the exchange step of a row-sharded search done
  * over NVLink peer memory by the search kernel itself.  One process per GPU: every rank creates
  * an exchange object, the ranks swap the 64-byte CUDA IPC handles (any transport; the Python
@@ -210,7 +230,8 @@ int mlv_index_scan_time_ms(mlv_index_t h, double *total_ms, uint64_t *launches);
  * ring-stage target size, "max_stages", "r" rows per warp step (0 = auto), "evict_first"
  * (-1 auto / 0 / 1), "ctas" grid size (0 = one per SM), "dynamic" (1 = work-stealing tile scheduler,
  * 0 = static round-robin), "tile_batch" tiles claimed per atomic, "fused" (1 = the last CTA does the
- * final select, 0 = separate select kernel)}.  Results never depend on these.
+ * final select, 0 = separate select kernel), "gather" (-1 auto, 0 = filters stream every row and mask,
+ * 1 = filters always gather)}.  Results never depend on these.
  */
 int mlv_index_set_tuning(mlv_index_t h, const char *key, int value);
 /*

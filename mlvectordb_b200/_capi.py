@@ -81,6 +81,10 @@ SIGNATURES = {
     "mlv_index_set_tuning": (C.c_int, [_h, C.c_char_p, C.c_int]),
     "mlv_index_kernel_launches": (C.c_int, [_h, _u64p]),
     "mlv_index_debug_timeline": (C.c_int, [_h, _u64p, C.c_uint32, _u32p]),
+    "mlv_filter_create": (C.c_int, [_h, C.c_void_p, C.c_uint64, C.POINTER(_h)]),
+    "mlv_filter_passing": (C.c_int, [_h, _u64p]),
+    "mlv_filter_destroy": (C.c_int, [_h]),
+    "mlv_index_set_filter": (C.c_int, [_h, _h]),
     "mlv_exchange_create": (C.c_int, [C.c_int, C.c_uint32, C.c_uint32, C.POINTER(_h), C.c_void_p]),
     "mlv_exchange_connect": (C.c_int, [_h, C.c_void_p]),
     "mlv_exchange_check": (C.c_int, [_h]),

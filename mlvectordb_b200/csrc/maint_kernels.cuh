@@ -122,8 +122,10 @@ __global__ void mark_deleted_kernel(uint32_t* live, const uint64_t* rows, uint64
 
 // ---- compaction ---------------------------------------------------------------------------------
 // word_base[w] = number of live rows before word w (single CTA, chunked scan with carry).
+// `mask` (nullable) is ANDed in: the prefix of rows that are live AND pass a filter bitmap.
 __global__ void __launch_bounds__(1024, 1) live_prefix_kernel(const uint32_t* live, uint64_t n_rows, uint64_t* word_base,
-                                                              uint64_t* total_live) {
+                                                              uint64_t* total_live, const uint32_t* mask = nullptr,
+                                                              uint64_t mask_words = 0) {
     __shared__ uint32_t warp_sums[32];
     __shared__ uint64_t carry;
     const uint64_t n_words = (n_rows + 31) >> 5;
@@ -134,6 +136,7 @@ __global__ void __launch_bounds__(1024, 1) live_prefix_kernel(const uint32_t* li
         uint32_t word = 0;
         if (w < n_words) {
             word = live[w];
+            if (mask) word &= w < mask_words ? mask[w] : 0u;
             if (w == n_words - 1 && (n_rows & 31)) word &= (1u << (n_rows & 31)) - 1;
         }
         const uint32_t c = __popc(word);
@@ -165,6 +168,23 @@ __global__ void __launch_bounds__(1024, 1) live_prefix_kernel(const uint32_t* li
     }
     if (threadIdx.x == 0) *total_live = carry;
 }
+// rows that are live AND pass `mask` -> ascending row list (the gather list of the scan kernel)
+__global__ void scatter_passing_rows_kernel(const uint32_t* live, const uint32_t* mask, uint64_t mask_words, uint64_t n_rows,
+                                            const uint64_t* word_base, uint32_t* list) {
+    const uint64_t n_words = (n_rows + 31) >> 5;
+    for (uint64_t w = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; w < n_words; w += (uint64_t)gridDim.x * blockDim.x) {
+        uint32_t word = live[w];
+        if (mask) word &= w < mask_words ? mask[w] : 0u;
+        if (w == n_words - 1 && (n_rows & 31)) word &= (1u << (n_rows & 31)) - 1;
+        uint64_t at = word_base[w];
+        while (word) {
+            const int b = __ffs(word) - 1;
+            word &= word - 1;
+            list[at++] = (uint32_t)(w * 32 + b);
+        }
+    }
+}
+
 // one warp per old row: live rows move to their new position, map[old] = new or -1
 __global__ void compact_rows_kernel(const float4* __restrict__ src, float4* __restrict__ dst, const uint32_t* live,
                                     const uint64_t* word_base, uint64_t n_rows, uint32_t ld4, int64_t* map) {

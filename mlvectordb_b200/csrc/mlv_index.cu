@@ -44,6 +44,7 @@ struct Lane {
     bool used = false;
     uint64_t last_use = 0;
     DevBuf d_q, d_keys0, d_keys1, d_sched;
+    DevBuf d_flist, d_fscratch;  // gather list built from a per-call filter bitmap
 };
 
 struct ScanCfg {
@@ -64,6 +65,16 @@ struct mlv_exchange {
     bool connected = false;
 };
 
+struct mlv_filter {
+    mlv_index* owner = nullptr;
+    DevBuf d_bitmap, d_list, d_scratch;
+    uint64_t bitmap_words = 0;   // words the caller supplied (rows appended later do not pass)
+    uint64_t passing = 0;        // live AND passing rows when the list was built
+    uint64_t epoch = ~0ull;      // owner->epoch the list was built at
+    uint64_t compact_gen = 0;    // owner->compact_gen at creation: compaction renumbers rows, the bitmap is void after it
+    bool counted = false;        // `passing` has been read back
+};
+
 struct mlv_index {
     int device = 0;
     uint32_t dim = 0, ld = 0;
@@ -78,6 +89,10 @@ struct mlv_index {
     DevBuf d_qraw, d_filter, d_outd, d_outr, d_outc, d_misc, d_range, d_timeline;
     Lane lanes[MLV_LANES];
     uint64_t lane_clock = 0;
+    uint64_t epoch = 0;          // bumped by every add / delete / compact / clear: prepared filters rebuild their row list
+    mlv_filter* bound_filter = nullptr;  // mlv_index_set_filter
+    uint64_t compact_gen = 0;
+    int tune_gather = -1;        // -1 auto, 0 never (stream + mask), 1 always when a filter is given
     HostBuf h_stage;
     std::string err;
     bool timing = false;
@@ -224,6 +239,7 @@ int finish_append(mlv_index* h, uint64_t n, uint64_t* first_row) {
     CK(h, cudaGetLastError());
     CK(h, cudaStreamSynchronize(h->stream));
     h->rows += n;
+    h->epoch++;
     if (first_row) *first_row = first;
     return MLV_OK;
 }
@@ -370,6 +386,64 @@ Lane* lane_for(mlv_index* h, cudaStream_t st) {
     return lru;
 }
 
+// Build the ascending list of rows that are live AND pass `bm` (device bitmap, `words` words; rows
+// beyond it do not pass) into list/scratch, on `st`.  scratch[0] (u64) receives the list length.
+int build_gather_list(mlv_index* h, DevBuf& list, DevBuf& scratch, const uint32_t* bm, uint64_t words, cudaStream_t st) {
+    const uint64_t n = h->rows, n_words = (n + 31) / 32;
+    int rc;
+    if ((rc = ensure_dev(h, scratch, n_words * 8 + 8)) != MLV_OK) return rc;
+    if ((rc = ensure_dev(h, list, std::max<uint64_t>(n, 1) * 4)) != MLV_OK) return rc;
+    uint64_t* d_total = (uint64_t*)scratch.p;
+    live_prefix_kernel<<<1, 1024, 0, st>>>(h->d_live, n, d_total + 1, d_total, bm, words);
+    scatter_passing_rows_kernel<<<(unsigned)std::min<uint64_t>((n_words + 255) / 256, 2048), 256, 0, st>>>(
+        h->d_live, bm, words, n, d_total + 1, (uint32_t*)list.p);
+    h->launches += 2;
+    CK(h, cudaGetLastError());
+    return MLV_OK;
+}
+
+// What a search reads its rows through: nothing special, a bitmap checked per row, or a gather list.
+struct FilterPlan {
+    const uint32_t* bitmap = nullptr;      // stream + mask
+    const uint32_t* gather = nullptr;      // row list (live AND passing)
+    const uint32_t* n_rows_dev = nullptr;  // its length (device)
+};
+
+// filter_dev: per-call bitmap (ceil(rows/32) words) or null; a bound prepared filter applies when it is null.
+int plan_filter(mlv_index* h, Lane* ln, const uint32_t* filter_dev, cudaStream_t st, FilterPlan* out) {
+    *out = FilterPlan{};
+    mlv_filter* f = filter_dev ? nullptr : h->bound_filter;
+    if (!filter_dev && !f) return MLV_OK;
+    int rc;
+    if (f) {
+        if (f->compact_gen != h->compact_gen)
+            return fail(h, MLV_E_INVALID, "prepared filter predates a compaction / clear of the index (rows were renumbered); create it again");
+        if (f->epoch != h->epoch) {  // rows were added / deleted since: rebuild (device only; count re-read lazily)
+            if ((rc = build_gather_list(h, f->d_list, f->d_scratch, (const uint32_t*)f->d_bitmap.p, f->bitmap_words, st)) != MLV_OK) return rc;
+            f->epoch = h->epoch;
+            f->counted = false;
+        }
+        const bool covers = f->bitmap_words >= (h->rows + 31) / 32;  // only then can the bitmap mask a full stream
+        const bool dense = f->counted && f->passing * 4 >= (h->rows - h->n_deleted) * 3;
+        const bool want_stream = h->tune_gather == 0 || (h->tune_gather < 0 && dense);
+        if (want_stream && covers) {
+            out->bitmap = (const uint32_t*)f->d_bitmap.p;  // stream every row, mask in the epilogue
+            return MLV_OK;
+        }
+        out->gather = (const uint32_t*)f->d_list.p;
+        out->n_rows_dev = (const uint32_t*)f->d_scratch.p;  // low word of the u64 total
+        return MLV_OK;
+    }
+    if (h->tune_gather == 0) {
+        out->bitmap = filter_dev;
+        return MLV_OK;
+    }
+    if ((rc = build_gather_list(h, ln->d_flist, ln->d_fscratch, filter_dev, (h->rows + 31) / 32, st)) != MLV_OK) return rc;
+    out->gather = (const uint32_t*)ln->d_flist.p;
+    out->n_rows_dev = (const uint32_t*)ln->d_fscratch.p;
+    return MLV_OK;
+}
+
 int ensure_sched(mlv_index* h, Lane* ln) {
     if (ln->d_sched.p) return MLV_OK;
     int rc = ensure_dev(h, ln->d_sched, 8);
@@ -441,8 +515,12 @@ int search_prepared(mlv_index* h, const float* qprep, uint32_t nq, uint32_t k, c
     p.stages = c.S;
     p.stage_f4 = c.stage_f4;
     p.k = k;
+    FilterPlan fp;
+    if ((rc = plan_filter(h, ln, filter_dev, st, &fp)) != MLV_OK) return rc;
     p.live = h->n_deleted ? h->d_live : nullptr;
-    p.filter = filter_dev;
+    p.filter = fp.bitmap;
+    p.gather = fp.gather;
+    p.n_rows_dev = fp.n_rows_dev;
     p.evict_first = c.evict_first;
     fill_sched(h, ln, p);
     p.fused = fused ? 1 : 0;
@@ -648,6 +726,12 @@ int search_gemm(mlv_index* h, const float* qprep, uint32_t nq, uint32_t k, const
     gp.thr = thr;
     gp.live = h->n_deleted ? h->d_live : nullptr;
     gp.filter = filter_dev;
+    if (!filter_dev && h->bound_filter) {
+        if (h->bound_filter->compact_gen != h->compact_gen)
+            return fail(h, MLV_E_INVALID, "prepared filter predates a compaction / clear of the index (rows were renumbered); create it again");
+        if (h->bound_filter->bitmap_words < (h->rows + 31) / 32) return fail(h, MLV_E_INVALID, "prepared filter is shorter than the index; re-create it");
+        gp.filter = (const uint32_t*)h->bound_filter->d_bitmap.p;
+    }
     gp.cand = cand;
     gp.cand_cnt = cnt;
     gp.cap = cap;
@@ -824,7 +908,7 @@ int mlv_index_destroy(mlv_index_t h) {
                       &h->d_norms, &h->d_gq, &h->d_cand, &h->d_maxn2})
         free_dev(*b);
     for (Lane& l : h->lanes)
-        for (DevBuf* b : {&l.d_q, &l.d_keys0, &l.d_keys1, &l.d_sched}) free_dev(*b);
+        for (DevBuf* b : {&l.d_q, &l.d_keys0, &l.d_keys1, &l.d_sched, &l.d_flist, &l.d_fscratch}) free_dev(*b);
     if (h->h_stage.p) cudaFreeHost(h->h_stage.p);
     for (auto* vec : {&h->pending, &h->gemm_pending})
         for (auto& pr : *vec) {
@@ -856,6 +940,7 @@ int mlv_index_set_tuning(mlv_index_t h, const char* key, int value) {
     else if (k == "dynamic") h->tune_dynamic = value;
     else if (k == "tile_batch") h->tune_tile_batch = value;
     else if (k == "fused") h->tune_fused = value;
+    else if (k == "gather") h->tune_gather = value;
     else if (k == "gemm") h->tune_gemm = value;
     else if (k == "gemm_min_nq") h->tune_gemm_min_nq = value;
     else return fail(h, MLV_E_INVALID, "unknown tuning key " + k);
@@ -928,6 +1013,7 @@ int mlv_index_mark_deleted(mlv_index_t h, const uint64_t* rows, uint64_t n, uint
     CK(h, cudaMemcpyAsync(&changed, d_changed, 8, cudaMemcpyDeviceToHost, h->stream));
     CK(h, cudaStreamSynchronize(h->stream));
     h->n_deleted += changed;
+    if (changed) h->epoch++;
     if (newly_deleted) *newly_deleted = changed;
     return MLV_OK;
 }
@@ -974,6 +1060,8 @@ int mlv_index_compact(mlv_index_t h, int64_t* old_to_new, uint64_t* new_rows) {
     h->rows = total;
     h->n_deleted = 0;
     h->norms_valid = 0;
+    h->epoch++;
+    h->compact_gen++;
     CK(h, cudaMemsetAsync(h->d_live, 0, h->live_words * 4, h->stream));
     if (total) {
         const uint64_t words = (total + 31) / 32;
@@ -996,6 +1084,8 @@ int mlv_index_clear(mlv_index_t h) {
     h->rows = 0;
     h->n_deleted = 0;
     h->norms_valid = 0;
+    h->epoch++;
+    h->compact_gen++;
     return MLV_OK;
 }
 
@@ -1017,6 +1107,77 @@ int mlv_index_search_device(mlv_index_t h, const float* queries_dev, uint32_t nq
     if (gemm_eligible(h, nq, k))
         return search_gemm(h, (const float*)lane_for(h, st)->d_q.p, nq, k, filter_bitmap_dev, out_dists_dev, out_rows_dev, out_counts_dev, st);
     return search_prepared(h, (const float*)lane_for(h, st)->d_q.p, nq, k, filter_bitmap_dev, out_dists_dev, out_rows_dev, out_counts_dev, st);
+}
+
+int mlv_filter_create(mlv_index_t h, const uint32_t* bitmap, uint64_t n_words, mlv_filter_t* out) {
+    if (!h || !out || (!bitmap && n_words)) return MLV_E_INVALID;
+    *out = nullptr;
+    DeviceGuard g(h->device);
+    mlv_filter* f = new (std::nothrow) mlv_filter();
+    if (!f) return MLV_E_NOMEM;
+    f->owner = h;
+    f->compact_gen = h->compact_gen;
+    f->bitmap_words = n_words;
+    int rc = ensure_dev(h, f->d_bitmap, std::max<uint64_t>(n_words, 1) * 4);
+    if (rc == MLV_OK && n_words) {
+        cudaError_t e = cudaMemcpyAsync(f->d_bitmap.p, bitmap, n_words * 4, cudaMemcpyHostToDevice, h->stream);
+        if (e != cudaSuccess) rc = fail_cuda(h, e, "filter upload");
+    }
+    if (rc == MLV_OK && h->rows) rc = build_gather_list(h, f->d_list, f->d_scratch, (const uint32_t*)f->d_bitmap.p, n_words, h->stream);
+    uint64_t total = 0;
+    if (rc == MLV_OK && h->rows) {
+        cudaError_t e = cudaMemcpyAsync(&total, f->d_scratch.p, 8, cudaMemcpyDeviceToHost, h->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+        if (e != cudaSuccess) rc = fail_cuda(h, e, "filter build");
+    }
+    if (rc != MLV_OK) {
+        for (DevBuf* b : {&f->d_bitmap, &f->d_list, &f->d_scratch}) free_dev(*b);
+        delete f;
+        return rc;
+    }
+    f->passing = total;
+    f->counted = true;
+    f->epoch = h->rows ? h->epoch : ~0ull;
+    *out = f;
+    return MLV_OK;
+}
+
+int mlv_filter_passing(mlv_filter_t f, uint64_t* passing) {
+    if (!f || !passing) return MLV_E_INVALID;
+    mlv_index* h = f->owner;
+    DeviceGuard g(h->device);
+    if (f->epoch != h->epoch && h->rows) {
+        int rc = build_gather_list(h, f->d_list, f->d_scratch, (const uint32_t*)f->d_bitmap.p, f->bitmap_words, h->stream);
+        if (rc != MLV_OK) return rc;
+        f->epoch = h->epoch;
+        f->counted = false;
+    }
+    if (!f->counted && h->rows) {
+        uint64_t total = 0;
+        CK(h, cudaMemcpyAsync(&total, f->d_scratch.p, 8, cudaMemcpyDeviceToHost, h->stream));
+        CK(h, cudaStreamSynchronize(h->stream));
+        f->passing = total;
+        f->counted = true;
+    }
+    *passing = h->rows ? f->passing : 0;
+    return MLV_OK;
+}
+
+int mlv_filter_destroy(mlv_filter_t f) {
+    if (!f) return MLV_E_INVALID;
+    mlv_index* h = f->owner;
+    DeviceGuard g(h->device);
+    if (h->bound_filter == f) h->bound_filter = nullptr;
+    cudaDeviceSynchronize();
+    for (DevBuf* b : {&f->d_bitmap, &f->d_list, &f->d_scratch}) free_dev(*b);
+    delete f;
+    return MLV_OK;
+}
+
+int mlv_index_set_filter(mlv_index_t h, mlv_filter_t f) {
+    if (!h || (f && f->owner != h)) return MLV_E_INVALID;
+    h->bound_filter = f;
+    return MLV_OK;
 }
 
 int mlv_exchange_create(int device, uint32_t world, uint32_t rank, mlv_exchange_t* out, unsigned char* handle_out) {
@@ -1215,12 +1376,16 @@ int mlv_index_range_search(mlv_index_t h, const float* queries, uint32_t nq, flo
     p.stages = c.S;
     p.stage_f4 = c.stage_f4;
     p.k = 1;
+    Lane* ln = lane_for(h, h->stream);
+    FilterPlan fp;
+    if ((rc = plan_filter(h, ln, filter_dev, h->stream, &fp)) != MLV_OK) return rc;
     p.live = h->n_deleted ? h->d_live : nullptr;
-    p.filter = filter_dev;
+    p.filter = fp.bitmap;
+    p.gather = fp.gather;
+    p.n_rows_dev = fp.n_rows_dev;
     p.evict_first = c.evict_first;
     p.radius = radius;
     p.max_hits = max_hits;
-    Lane* ln = lane_for(h, h->stream);
     if ((rc = ensure_sched(h, ln)) != MLV_OK) return rc;
     fill_sched(h, ln, p);
     for (uint32_t q = 0; q < nq; q++) {
@@ -1271,7 +1436,7 @@ int mlv_index_info(mlv_index_t h, mlv_index_info_t* info) {
                             &h->d_gq, &h->d_cand, &h->d_maxn2})
         b += d->bytes;
     for (const Lane& l : h->lanes)
-        for (const DevBuf* d : {&l.d_q, &l.d_keys0, &l.d_keys1, &l.d_sched}) b += d->bytes;
+        for (const DevBuf* d : {&l.d_q, &l.d_keys0, &l.d_keys1, &l.d_sched, &l.d_flist, &l.d_fscratch}) b += d->bytes;
     info->device_bytes = b;
     info->dim = h->dim;
     info->ld = h->ld;

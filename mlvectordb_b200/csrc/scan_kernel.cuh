@@ -42,6 +42,11 @@ struct ScanParams {
     uint32_t k;
     const uint32_t* live;    // tombstone bitmap (bit set = live) or nullptr when nothing is deleted
     const uint32_t* filter;  // caller's filter bitmap or nullptr
+    // gather mode (selective filters): `gather` lists the passing-and-live rows ascending; n_rows is
+    // the length of the list, tiles are runs of list positions and the producer copies row by row,
+    // so only passing rows are read from HBM.  live / filter are already folded into the list.
+    const uint32_t* gather;
+    const uint32_t* n_rows_dev;  // gather mode: length of the list, produced on the device just before (no host sync)
     uint64_t* out_keys;      // top-k mode: [nq_valid][gridDim.x][k]
     float radius;            // range mode
     unsigned long long* range_counts;  // [nq_valid]
@@ -145,6 +150,8 @@ __global__ void __launch_bounds__(SCAN_MAX_THREADS, 1) scan_kernel(const ScanPar
     const int warp = tid >> 5;
     const int lane = tid & 31;
     const int CW = (blockDim.x >> 5) - 1;  // consumer warps; warp CW is the producer
+    const uint32_t n_rows = p.n_rows_dev ? __ldg(p.n_rows_dev) : p.n_rows;
+    const uint32_t n_tiles = p.n_rows_dev ? (n_rows + p.tile_rows - 1) / p.tile_rows : p.n_tiles;
     const uint32_t S = p.stages;
     const uint32_t ld4 = p.ld4;
     const uint32_t k = p.k;
@@ -176,42 +183,56 @@ __global__ void __launch_bounds__(SCAN_MAX_THREADS, 1) scan_kernel(const ScanPar
 
     if (warp == CW) {
         // ------------------------------------------------------------------ producer
-        if (lane == 0) {
-            uint32_t stage = 0, phase = 0;
-            const uint64_t pol = policy_evict_first();
-            auto issue = [&](uint32_t tile) {
-                mbar_wait(&empty[stage], phase ^ 1);
-                const uint32_t row0 = tile * p.tile_rows;
-                const uint32_t n = min(p.tile_rows, p.n_rows - row0);
+        uint32_t stage = 0, phase = 0;
+        const uint64_t pol = policy_evict_first();
+        // whole warp (converged); lane 0 owns the barriers, in gather mode every lane issues copies
+        auto issue = [&](uint32_t tile) {
+            if (lane == 0) mbar_wait(&empty[stage], phase ^ 1);
+            __syncwarp();
+            const uint32_t row0 = tile * p.tile_rows;
+            const uint32_t n = min(p.tile_rows, n_rows - row0);
+            float4* dst = ring + (size_t)stage * p.stage_f4;
+            if (lane == 0) {
                 meta[stage].row0 = row0;
                 meta[stage].n_rows = (int32_t)n;
-                const uint32_t bytes = n * ld4 * 16u;
-                mbar_arrive_expect_tx(&full[stage], bytes);
-                const float4* src = p.rows + (size_t)row0 * ld4;
-                float4* dst = ring + (size_t)stage * p.stage_f4;
-                if (p.evict_first)
-                    bulk_g2s_hint(dst, src, bytes, &full[stage], pol);
-                else
-                    bulk_g2s(dst, src, bytes, &full[stage]);
-                if (++stage == S) {
-                    stage = 0;
-                    phase ^= 1;
-                }
-            };
-            if (p.sched) {
-                // work stealing: claim `tile_batch` consecutive tiles per atomic; the next claim is
-                // in flight while this batch's copies are issued
-                uint32_t next = atomicAdd(p.sched, 1u);
-                for (;;) {
-                    const uint32_t t0 = next * p.tile_batch;
-                    if (t0 >= p.n_tiles) break;
-                    next = atomicAdd(p.sched, 1u);
-                    const uint32_t t1 = min(t0 + p.tile_batch, p.n_tiles);
-                    for (uint32_t tile = t0; tile < t1; tile++) issue(tile);
-                }
-            } else {
-                for (uint32_t tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) issue(tile);
+                mbar_arrive_expect_tx(&full[stage], n * ld4 * 16u);
             }
+            if (p.gather) {
+                __syncwarp();
+                for (uint32_t i = lane; i < n; i += 32) {
+                    const uint32_t r = __ldg(p.gather + row0 + i);
+                    bulk_g2s_hint(dst + (size_t)i * ld4, p.rows + (size_t)r * ld4, ld4 * 16u, &full[stage], pol);
+                }
+            } else if (lane == 0) {
+                const float4* src = p.rows + (size_t)row0 * ld4;
+                if (p.evict_first)
+                    bulk_g2s_hint(dst, src, n * ld4 * 16u, &full[stage], pol);
+                else
+                    bulk_g2s(dst, src, n * ld4 * 16u, &full[stage]);
+            }
+            if (++stage == S) {
+                stage = 0;
+                phase ^= 1;
+            }
+        };
+        if (p.sched) {
+            // work stealing: claim `tile_batch` consecutive tiles per atomic; the next claim is
+            // in flight while this batch's copies are issued
+            uint32_t next = 0;
+            if (lane == 0) next = atomicAdd(p.sched, 1u);
+            next = __shfl_sync(0xffffffffu, next, 0);
+            for (;;) {
+                const uint32_t t0 = next * p.tile_batch;
+                if (t0 >= n_tiles) break;
+                if (lane == 0) next = atomicAdd(p.sched, 1u);
+                const uint32_t t1 = min(t0 + p.tile_batch, n_tiles);
+                for (uint32_t tile = t0; tile < t1; tile++) issue(tile);
+                next = __shfl_sync(0xffffffffu, next, 0);
+            }
+        } else {
+            for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) issue(tile);
+        }
+        if (lane == 0) {
             mbar_wait(&empty[stage], phase ^ 1);
             meta[stage].n_rows = -1;
             mbar_arrive(&full[stage]);
@@ -242,11 +263,15 @@ __global__ void __launch_bounds__(SCAN_MAX_THREADS, 1) scan_kernel(const ScanPar
         for (; g < n_groups; g += CW) {
             const uint32_t base = g * R;
             const uint32_t my_local = base + my_r;
-            const uint32_t row = row0 + my_local;
-            const uint32_t rowc = min(row, p.n_rows - 1);
+            const uint32_t pos = min(row0 + my_local, n_rows - 1);
+            // gather mode: the tile holds list positions; the list has the row numbers and is pre-masked
+            const uint32_t row = p.gather ? __ldg(p.gather + pos) : row0 + my_local;
+            const uint32_t rowc = p.gather ? 0u : pos;
             uint32_t wl = 0xffffffffu, wf = 0xffffffffu;
-            if (p.live) wl = __ldg(p.live + (rowc >> 5));
-            if (p.filter) wf = __ldg(p.filter + (rowc >> 5));
+            if (!p.gather) {
+                if (p.live) wl = __ldg(p.live + (rowc >> 5));
+                if (p.filter) wf = __ldg(p.filter + (rowc >> 5));
+            }
 
             float acc[V];
 #pragma unroll

@@ -33,9 +33,9 @@ import numpy as np
 
 from . import _capi
 from .interfaces import SearchResult, VectorDTO, VectorProtocol
-from .shard import DeviceShard, canonical_space
+from .shard import DeviceShard, PreparedFilter, canonical_space
 
-FilterArg = Union[None, np.ndarray, Callable[[UUID], bool]]
+FilterArg = Union[None, np.ndarray, Callable[[UUID], bool], PreparedFilter]
 
 
 def _random_uuid_bytes(n: int) -> np.ndarray:
@@ -141,6 +141,8 @@ class GpuIndex:
     def _filter_mask(self, ns: _Namespace, filt: FilterArg):
         if filt is None:
             return None
+        if isinstance(filt, PreparedFilter):
+            return filt
         if callable(filt):
             return np.fromiter((bool(filt(ns.uuid_of(r))) for r in range(ns.n)), dtype=bool, count=ns.n)
         return filt
@@ -318,6 +320,14 @@ class GpuIndex:
                 score = 1 - score
             out.append(SearchResult(vector_id=ns.uuid_of(row), score=score))
         return out
+
+    def prepare_filter(self, namespace: str, filter: FilterArg) -> PreparedFilter:
+        """Evaluate a filter (row mask or ``callable(uuid) -> bool``) once and keep it on the device;
+        pass the result as ``filter=`` to ``search`` / ``search_batch`` / ``range_search``.  It follows later
+        adds / removes of the namespace (rows added afterwards do not pass); compaction renumbers rows, so
+        prepare it again after the namespace was compacted."""
+        ns = self._ns[namespace]
+        return ns.shard.prepare_filter(self._filter_mask(ns, filter))
 
     def info(self, namespace: str) -> dict:
         ns = self._ns[namespace]

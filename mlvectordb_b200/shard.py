@@ -120,8 +120,13 @@ class DeviceShard:
         self._ck(self._lib.mlv_index_clear(self._h))
 
     # -- query ----------------------------------------------------------------------------
+    def prepare_filter(self, filt) -> "PreparedFilter":
+        """Upload a filter once (bool mask per row, or packed uint32 words) for repeated searches."""
+        words = self._filter_words(filt)
+        return PreparedFilter(self, words)
+
     def _filter_words(self, filt) -> Optional[np.ndarray]:
-        if filt is None:
+        if filt is None or isinstance(filt, PreparedFilter):
             return None
         f = np.asarray(filt)
         n = self.rows
@@ -145,8 +150,9 @@ class DeviceShard:
         rows = np.empty((nq, k), dtype=np.int64)
         counts = np.empty(nq, dtype=np.int32)
         fw = self._filter_words(filt)
-        self._ck(self._lib.mlv_index_search(self._h, q.ctypes.data, nq, int(k), fw.ctypes.data if fw is not None else None,
-                                            dists.ctypes.data, rows.ctypes.data, counts.ctypes.data))
+        with _bound(self, filt):
+            self._ck(self._lib.mlv_index_search(self._h, q.ctypes.data, nq, int(k), fw.ctypes.data if fw is not None else None,
+                                                dists.ctypes.data, rows.ctypes.data, counts.ctypes.data))
         return dists, rows, counts
 
     def search_device(self, q_ptr: int, nq: int, k: int, out_d_ptr: int, out_r_ptr: int, out_c_ptr: int,
@@ -188,9 +194,10 @@ class DeviceShard:
             dists = np.empty((nq, max_hits), dtype=np.float32)
             rows = np.empty((nq, max_hits), dtype=np.int64)
             counts = np.zeros(nq, dtype=np.uint64)
-            self._ck(self._lib.mlv_index_range_search(
-                self._h, q.ctypes.data, nq, C.c_float(radius), fw.ctypes.data if fw is not None else None, int(max_hits),
-                dists.ctypes.data, rows.ctypes.data, counts.ctypes.data))
+            with _bound(self, filt):
+                self._ck(self._lib.mlv_index_range_search(
+                    self._h, q.ctypes.data, nq, C.c_float(radius), fw.ctypes.data if fw is not None else None, int(max_hits),
+                    dists.ctypes.data, rows.ctypes.data, counts.ctypes.data))
             most = int(counts.max()) if nq else 0
             if most <= max_hits:
                 return [(dists[i, : int(counts[i])].copy(), rows[i, : int(counts[i])].copy()) for i in range(nq)]
@@ -239,6 +246,51 @@ class DeviceShard:
         n = C.c_uint64()
         self._ck(self._lib.mlv_index_kernel_launches(self._h, C.byref(n)))
         return int(n.value)
+
+
+class PreparedFilter:
+    """A filter bitmap resident on the device with its passing-row list (``mlv_filter_*``)."""
+
+    def __init__(self, shard: DeviceShard, words: np.ndarray):
+        self._lib = _capi.lib()
+        self._shard = shard
+        self._f = C.c_void_p()
+        w = np.ascontiguousarray(words, dtype=np.uint32)
+        check(self._lib.mlv_filter_create(shard._h, w.ctypes.data, w.shape[0], C.byref(self._f)), shard._h)
+
+    @property
+    def passing(self) -> int:
+        n = C.c_uint64()
+        check(self._lib.mlv_filter_passing(self._f, C.byref(n)), self._shard._h)
+        return int(n.value)
+
+    def close(self) -> None:
+        if getattr(self, "_f", None) and self._f.value:
+            if self._shard._h.value:          # the shard may already be gone
+                self._lib.mlv_filter_destroy(self._f)
+            self._f = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class _bound:
+    """Context manager: bind a PreparedFilter to the shard for the duration of one call."""
+
+    def __init__(self, shard: DeviceShard, filt):
+        self.shard, self.f = shard, filt if isinstance(filt, PreparedFilter) else None
+
+    def __enter__(self):
+        if self.f is not None:
+            check(self.shard._lib.mlv_index_set_filter(self.shard._h, self.f._f), self.shard._h)
+
+    def __exit__(self, *exc):
+        if self.f is not None:
+            self.shard._lib.mlv_index_set_filter(self.shard._h, None)
+        return False
 
 
 class Exchange:
