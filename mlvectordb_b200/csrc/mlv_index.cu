@@ -48,7 +48,7 @@ struct Lane {
 };
 
 struct ScanCfg {
-    int R, NQ, CW;
+    int R, NQ, CW, PW;
     uint32_t T, S, stage_f4;
     size_t smem;
     int grid, threads;
@@ -100,7 +100,7 @@ struct mlv_index {
     std::vector<cudaEvent_t> event_pool;
     uint64_t launches = 0;
     // tuning (mlv_index_set_tuning / MLV_SCAN_* environment)
-    int tune_cw = 8, tune_stage_kb = 32, tune_evict_first = -1, tune_r = 0, tune_max_stages = 8, tune_ctas = 0;
+    int tune_cw = 0, tune_stage_kb = 0, tune_evict_first = -1, tune_r = 0, tune_max_stages = 8, tune_ctas = 0, tune_pw = 0;
     int tune_timeline = 0;
     int last_grid = 0;
     // dynamic tile scheduler + fused final select (scan_kernel.cuh tail); counters live in the lanes
@@ -245,11 +245,15 @@ int finish_append(mlv_index* h, uint64_t n, uint64_t* first_row) {
 }
 
 // ---- scan configuration ------------------------------------------------------------------------
-int choose_cfg(mlv_index* h, uint32_t nq, uint32_t k, bool range, ScanCfg* c) {
+// Shape of one scan launch.  Defaults come from B200 sweeps (profiles/r01_sweep_*.jsonl): short rows
+// are latency-bound in the consumers, so they get more warps, more rows per warp step and larger
+// stages; a gathering producer is bound by its copy issue rate (~80 cycles per row copy per warp),
+// so short rows get more producer warps.
+int choose_cfg(mlv_index* h, uint32_t nq, uint32_t k, bool range, ScanCfg* c, bool gather = false) {
     const uint32_t ld4 = h->ld / 4;
     const size_t rowbytes = (size_t)h->ld * 4;
-    int CW = std::min(std::max(h->tune_cw, 1), SCAN_MAX_CW);
-    int R = h->tune_r ? h->tune_r : (ld4 <= 64 ? 4 : (ld4 <= 256 ? 2 : 1));
+    int CW = h->tune_cw > 0 ? std::min(h->tune_cw, SCAN_MAX_CW) : (ld4 <= 64 ? 16 : 8);
+    int R = h->tune_r ? h->tune_r : (ld4 <= 128 ? 4 : (ld4 <= 256 ? 2 : 1));
     if (R != 1 && R != 2 && R != 4) R = 1;
     int NQ = 1;
     if (!range) {
@@ -262,7 +266,7 @@ int choose_cfg(mlv_index* h, uint32_t nq, uint32_t k, bool range, ScanCfg* c) {
         return fail(h, MLV_E_UNSUPPORTED, "dimension too large for the shared-memory ring of this build");
     const size_t avail = h->smem_optin - fixed;
     const size_t group_bytes = (size_t)R * CW * rowbytes;
-    const size_t target = (size_t)std::max(h->tune_stage_kb, 1) * 1024;
+    const size_t target = (size_t)(h->tune_stage_kb > 0 ? h->tune_stage_kb : (ld4 <= 32 ? 64 : 32)) * 1024;
     uint64_t m = std::max<uint64_t>(1, target / group_bytes);
     uint64_t T = (uint64_t)R * CW * m;
     if (T * rowbytes * 2 > avail) {
@@ -276,6 +280,12 @@ int choose_cfg(mlv_index* h, uint32_t nq, uint32_t k, bool range, ScanCfg* c) {
     const size_t stage = T * rowbytes;
     if (stage >= (1u << 20)) return fail(h, MLV_E_UNSUPPORTED, "ring stage exceeds the mbarrier tx-count range");
     uint32_t S = (uint32_t)std::min<size_t>(max_stages, avail / stage);
+    int PW = 1;
+    if (gather) PW = h->tune_pw > 0 ? std::min(h->tune_pw, SCAN_MAX_PW) : (rowbytes >= 2048 ? 1 : (rowbytes >= 1024 ? 2 : 4));
+    while (PW > 1 && (uint32_t)PW > S) PW >>= 1;
+    if (PW == 3) PW = 2;
+    S = S / PW * PW;
+    c->PW = PW;
     c->R = R;
     c->NQ = NQ;
     c->CW = CW;
@@ -287,7 +297,7 @@ int choose_cfg(mlv_index* h, uint32_t nq, uint32_t k, bool range, ScanCfg* c) {
     const int ctas = h->tune_ctas > 0 ? h->tune_ctas : h->sm_count;
     c->grid = (int)std::min<uint64_t>(n_tiles, (uint64_t)ctas);
     if (c->grid < 1) c->grid = 1;
-    c->threads = (CW + 1) * 32;
+    c->threads = (CW + PW) * 32;
     const size_t bytes = h->rows * rowbytes;
     c->evict_first = h->tune_evict_first >= 0 ? h->tune_evict_first : (bytes > ((size_t)96 << 20) ? 1 : 0);
     return MLV_OK;
@@ -485,10 +495,12 @@ void fill_exchange(mlv_index* h, ExchangeView& x) {
 // exchange: merge with the other ranks' results over peer memory (caller checked exchange_ok).
 int search_prepared(mlv_index* h, const float* qprep, uint32_t nq, uint32_t k, const uint32_t* filter_dev, float* out_d,
                     int64_t* out_r, int32_t* out_c, cudaStream_t st, bool exchange = false) {
-    ScanCfg c;
-    int rc = choose_cfg(h, nq, k, false, &c);
-    if (rc != MLV_OK) return rc;
     Lane* ln = lane_for(h, st);
+    FilterPlan fp;
+    int rc = plan_filter(h, ln, filter_dev, st, &fp);
+    if (rc != MLV_OK) return rc;
+    ScanCfg c;
+    if ((rc = choose_cfg(h, nq, k, false, &c, fp.gather != nullptr)) != MLV_OK) return rc;
     if ((rc = ensure_sched(h, ln)) != MLV_OK) return rc;
     const bool fused = fused_ok(h, c, k);
     if (exchange && !fused) return fail(h, MLV_E_UNSUPPORTED, "exchange search needs the fused final select");
@@ -513,10 +525,9 @@ int search_prepared(mlv_index* h, const float* qprep, uint32_t nq, uint32_t k, c
     p.tile_rows = c.T;
     p.n_tiles = (uint32_t)((h->rows + c.T - 1) / c.T);
     p.stages = c.S;
+    p.producer_warps = (uint32_t)c.PW;
     p.stage_f4 = c.stage_f4;
     p.k = k;
-    FilterPlan fp;
-    if ((rc = plan_filter(h, ln, filter_dev, st, &fp)) != MLV_OK) return rc;
     p.live = h->n_deleted ? h->d_live : nullptr;
     p.filter = fp.bitmap;
     p.gather = fp.gather;
@@ -864,6 +875,7 @@ int mlv_index_create(uint32_t dim, int metric, uint64_t capacity_hint, int devic
     h->tune_r = env_int("MLV_SCAN_R", h->tune_r);
     h->tune_max_stages = env_int("MLV_SCAN_MAX_STAGES", h->tune_max_stages);
     h->tune_ctas = env_int("MLV_SCAN_CTAS", h->tune_ctas);
+    h->tune_pw = env_int("MLV_SCAN_PW", h->tune_pw);
     h->tune_dynamic = env_int("MLV_SCAN_DYNAMIC", h->tune_dynamic);
     h->tune_tile_batch = env_int("MLV_SCAN_TILE_BATCH", h->tune_tile_batch);
     h->tune_fused = env_int("MLV_SCAN_FUSED", h->tune_fused);
@@ -936,6 +948,7 @@ int mlv_index_set_tuning(mlv_index_t h, const char* key, int value) {
     else if (k == "r") h->tune_r = value;
     else if (k == "max_stages") h->tune_max_stages = value;
     else if (k == "ctas") h->tune_ctas = value;
+    else if (k == "pw") h->tune_pw = value;
     else if (k == "timeline") h->tune_timeline = value;
     else if (k == "dynamic") h->tune_dynamic = value;
     else if (k == "tile_batch") h->tune_tile_batch = value;
@@ -1365,8 +1378,11 @@ int mlv_index_range_search(mlv_index_t h, const float* queries, uint32_t nq, flo
     CK(h, cudaMemcpyAsync(h->d_qraw.p, queries, qbytes, cudaMemcpyHostToDevice, h->stream));
     CK(h, cudaMemsetAsync(d_counts, 0, (size_t)nq * 8, h->stream));
     if ((rc = prep_queries(h, (const float*)h->d_qraw.p, nq, h->stream)) != MLV_OK) return rc;
+    Lane* ln = lane_for(h, h->stream);
+    FilterPlan fp;
+    if ((rc = plan_filter(h, ln, filter_dev, h->stream, &fp)) != MLV_OK) return rc;
     ScanCfg c;
-    if ((rc = choose_cfg(h, 1, 1, true, &c)) != MLV_OK) return rc;
+    if ((rc = choose_cfg(h, 1, 1, true, &c, fp.gather != nullptr)) != MLV_OK) return rc;
     ScanParams p{};
     p.rows = reinterpret_cast<const float4*>(h->d_rows);
     p.n_rows = (uint32_t)h->rows;
@@ -1374,11 +1390,9 @@ int mlv_index_range_search(mlv_index_t h, const float* queries, uint32_t nq, flo
     p.tile_rows = c.T;
     p.n_tiles = (uint32_t)((h->rows + c.T - 1) / c.T);
     p.stages = c.S;
+    p.producer_warps = (uint32_t)c.PW;
     p.stage_f4 = c.stage_f4;
     p.k = 1;
-    Lane* ln = lane_for(h, h->stream);
-    FilterPlan fp;
-    if ((rc = plan_filter(h, ln, filter_dev, h->stream, &fp)) != MLV_OK) return rc;
     p.live = h->n_deleted ? h->d_live : nullptr;
     p.filter = fp.bitmap;
     p.gather = fp.gather;

@@ -25,7 +25,8 @@ namespace mlv {
 constexpr int METRIC_L2 = 0;
 constexpr int METRIC_IP = 1;  // cosine == ip over rows/queries normalised at add/query time
 constexpr int SCAN_MAX_CW = 16;                          // consumer warps per CTA (runtime, <= this)
-constexpr int SCAN_MAX_THREADS = (SCAN_MAX_CW + 1) * 32;  // 544 -> ptxas may use up to 120 registers
+constexpr int SCAN_MAX_PW = 4;                           // producer warps (1 unless gathering short rows)
+constexpr int SCAN_MAX_THREADS = (SCAN_MAX_CW + SCAN_MAX_PW) * 32;  // 640 -> ptxas may use up to 102 registers
 
 constexpr uint32_t SCAN_FUSED_MAX_KEYS = 2048;  // keys the last CTA folds (gridDim.x * k)
 
@@ -35,7 +36,8 @@ struct ScanParams {
     uint32_t ld4;           // float4 per row
     uint32_t tile_rows;     // T (multiple of R)
     uint32_t n_tiles;
-    uint32_t stages;        // S
+    uint32_t stages;        // S (a multiple of producer_warps)
+    uint32_t producer_warps;  // PW: producer warp w owns the stages s with s % PW == w
     uint32_t stage_f4;      // float4 per ring stage (= T * ld4)
     const float4* queries;  // [nq_valid, ld4] device, zero padded, normalised for cosine
     uint32_t nq_valid;      // <= NQ
@@ -149,7 +151,8 @@ __global__ void __launch_bounds__(SCAN_MAX_THREADS, 1) scan_kernel(const ScanPar
     const int tid = threadIdx.x;
     const int warp = tid >> 5;
     const int lane = tid & 31;
-    const int CW = (blockDim.x >> 5) - 1;  // consumer warps; warp CW is the producer
+    const int PW = (int)p.producer_warps;
+    const int CW = (blockDim.x >> 5) - PW;  // consumer warps 0..CW-1; warps CW..CW+PW-1 produce
     const uint32_t n_rows = p.n_rows_dev ? __ldg(p.n_rows_dev) : p.n_rows;
     const uint32_t n_tiles = p.n_rows_dev ? (n_rows + p.tile_rows - 1) / p.tile_rows : p.n_tiles;
     const uint32_t S = p.stages;
@@ -181,16 +184,28 @@ __global__ void __launch_bounds__(SCAN_MAX_THREADS, 1) scan_kernel(const ScanPar
     __syncthreads();
     if (p.timeline && tid == 0) p.timeline[blockIdx.x * 4 + 0] = global_timer_ns();
 
-    if (warp == CW) {
-        // ------------------------------------------------------------------ producer
-        uint32_t stage = 0, phase = 0;
+    if (warp >= CW) {
+        // ------------------------------------------------------------------ producer(s)
+        // Each producer warp fills its own residue class of ring stages and claims tiles on its own, so
+        // which tile lands in which stage is arbitrary; consumers walk the stages in order.
+        uint32_t stage = (uint32_t)(warp - CW), phase = 0;
         const uint64_t pol = policy_evict_first();
         // whole warp (converged); lane 0 owns the barriers, in gather mode every lane issues copies
         auto issue = [&](uint32_t tile) {
-            if (lane == 0) mbar_wait(&empty[stage], phase ^ 1);
-            __syncwarp();
             const uint32_t row0 = tile * p.tile_rows;
             const uint32_t n = min(p.tile_rows, n_rows - row0);
+            // gather mode: fetch this tile's row numbers before waiting for a free stage, so the
+            // lookup latency hides behind the wait (up to 128 rows per tile are prefetched)
+            uint32_t ridx[4] = {0, 0, 0, 0};
+            if (p.gather) {
+#pragma unroll
+                for (int c = 0; c < 4; c++) {
+                    const uint32_t i = lane + 32u * c;
+                    if (i < n) ridx[c] = __ldg(p.gather + row0 + i);
+                }
+            }
+            if (lane == 0) mbar_wait(&empty[stage], phase ^ 1);
+            __syncwarp();
             float4* dst = ring + (size_t)stage * p.stage_f4;
             if (lane == 0) {
                 meta[stage].row0 = row0;
@@ -199,7 +214,12 @@ __global__ void __launch_bounds__(SCAN_MAX_THREADS, 1) scan_kernel(const ScanPar
             }
             if (p.gather) {
                 __syncwarp();
-                for (uint32_t i = lane; i < n; i += 32) {
+#pragma unroll
+                for (int c = 0; c < 4; c++) {
+                    const uint32_t i = lane + 32u * c;
+                    if (i < n) bulk_g2s_hint(dst + (size_t)i * ld4, p.rows + (size_t)ridx[c] * ld4, ld4 * 16u, &full[stage], pol);
+                }
+                for (uint32_t i = lane + 128u; i < n; i += 32) {
                     const uint32_t r = __ldg(p.gather + row0 + i);
                     bulk_g2s_hint(dst + (size_t)i * ld4, p.rows + (size_t)r * ld4, ld4 * 16u, &full[stage], pol);
                 }
@@ -210,8 +230,9 @@ __global__ void __launch_bounds__(SCAN_MAX_THREADS, 1) scan_kernel(const ScanPar
                 else
                     bulk_g2s(dst, src, n * ld4 * 16u, &full[stage]);
             }
-            if (++stage == S) {
-                stage = 0;
+            stage += (uint32_t)PW;
+            if (stage >= S) {
+                stage -= S;
                 phase ^= 1;
             }
         };
@@ -230,7 +251,8 @@ __global__ void __launch_bounds__(SCAN_MAX_THREADS, 1) scan_kernel(const ScanPar
                 next = __shfl_sync(0xffffffffu, next, 0);
             }
         } else {
-            for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) issue(tile);
+            for (uint32_t tile = blockIdx.x * (uint32_t)PW + (uint32_t)(warp - CW); tile < n_tiles; tile += gridDim.x * (uint32_t)PW)
+                issue(tile);
         }
         if (lane == 0) {
             mbar_wait(&empty[stage], phase ^ 1);
@@ -250,11 +272,29 @@ __global__ void __launch_bounds__(SCAN_MAX_THREADS, 1) scan_kernel(const ScanPar
     uint64_t* my_lists = lists + (size_t)warp * NQ * k;
 
     uint32_t stage = 0, phase = 0, seq = 0;
+    uint32_t finished = 0;  // producers (= stage residue classes) that have posted their end mark
+    const uint32_t all_finished = (1u << PW) - 1u;
+    auto advance = [&]() {
+        if (++stage == S) {
+            stage = 0;
+            phase ^= 1;
+        }
+    };
     for (;;) {
+        const uint32_t owner = stage % (uint32_t)PW;
+        if ((finished >> owner) & 1u) {  // nothing will ever land here again
+            advance();
+            continue;
+        }
         mbar_wait(&full[stage], phase);
         if (p.timeline && tid == 0 && seq == 0) p.timeline[blockIdx.x * 4 + 1] = global_timer_ns();
         const int n = meta[stage].n_rows;
-        if (n < 0) break;
+        if (n < 0) {
+            finished |= 1u << owner;
+            if (finished == all_finished) break;
+            advance();
+            continue;
+        }
         const uint32_t row0 = meta[stage].row0;
         const float4* tile = ring + (size_t)stage * p.stage_f4;
         const uint32_t n_groups = ((uint32_t)n + R - 1) / R;
@@ -316,13 +356,10 @@ __global__ void __launch_bounds__(SCAN_MAX_THREADS, 1) scan_kernel(const ScanPar
         __syncwarp();
         if (lane == 0) mbar_arrive(&empty[stage]);
         seq++;
-        if (++stage == S) {
-            stage = 0;
-            phase ^= 1;
-        }
+        advance();
     }
     if (p.timeline && tid == 0) p.timeline[blockIdx.x * 4 + 2] = global_timer_ns();
-    const uint32_t nthr = (uint32_t)CW * 32u;  // consumer threads (the producer warp has left)
+    const uint32_t nthr = (uint32_t)CW * 32u;  // consumer threads (the producer warps have left)
     if (!RANGE) {
         // --------------------------------------------- fold the CW warp lists into one per query
         named_bar_sync(1, CW * 32);

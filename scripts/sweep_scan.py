@@ -21,8 +21,8 @@ def main():
     ap.add_argument("--k", type=int, default=10)
     ap.add_argument("--nq", type=int, default=1)
     ap.add_argument("--reps", type=int, default=20)
-    ap.add_argument("--cw", default="8")
-    ap.add_argument("--stage_kb", default="32")
+    ap.add_argument("--cw", default="0")
+    ap.add_argument("--stage_kb", default="0")
     ap.add_argument("--evict", default="-1")
     ap.add_argument("--r", default="0")
     ap.add_argument("--max_stages", default="8")
