@@ -153,6 +153,15 @@ int mlv_index_range_search(mlv_index_t h, const float *queries, uint32_t nq, flo
                            const uint32_t *filter_bitmap, uint64_t max_hits, float *out_dists, int64_t *out_rows,
                            uint64_t *out_counts);
 
+/*
+ * Same with every pointer in device memory, enqueued on `stream` without synchronising.  Hit lists
+ * of at most 8192 entries come back ordered; longer ones hold the right hits in unspecified order
+ * (the host entry point above orders those itself).  One range search at a time per handle.
+ */
+int mlv_index_range_search_device(mlv_index_t h, const float *queries_dev, uint32_t nq, float radius,
+                                  const uint32_t *filter_bitmap_dev, uint64_t max_hits, float *out_dists_dev,
+                                  int64_t *out_rows_dev, uint64_t *out_counts_dev, void *stream);
+
 /* Copy stored rows (as stored: normalised for cosine) back to the host, [n, dim]. */
 int mlv_index_get_rows(mlv_index_t h, const uint64_t *rows, uint64_t n, float *out);
 

@@ -1355,32 +1355,27 @@ int mlv_index_search(mlv_index_t h, const float* queries, uint32_t nq, uint32_t 
     return MLV_OK;
 }
 
-int mlv_index_range_search(mlv_index_t h, const float* queries, uint32_t nq, float radius, const uint32_t* filter_bitmap,
-                           uint64_t max_hits, float* out_dists, int64_t* out_rows, uint64_t* out_counts) {
-    if (!h || !queries || !out_counts || nq == 0 || (max_hits && (!out_dists || !out_rows))) return fail(h, MLV_E_INVALID, "bad argument");
+int mlv_index_range_search_device(mlv_index_t h, const float* queries_dev, uint32_t nq, float radius,
+                                  const uint32_t* filter_bitmap_dev, uint64_t max_hits, float* out_dists_dev,
+                                  int64_t* out_rows_dev, uint64_t* out_counts_dev, void* stream) {
+    if (!h || !queries_dev || !out_counts_dev || nq == 0 || (max_hits && (!out_dists_dev || !out_rows_dev))) return fail(h, MLV_E_INVALID, "bad argument");
     DeviceGuard g(h->device);
-    for (uint32_t q = 0; q < nq; q++) out_counts[q] = 0;
-    if (h->rows == h->n_deleted) return MLV_OK;
-    const size_t qbytes = (size_t)nq * h->dim * 4;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (h->rows == h->n_deleted) {
+        CK(h, cudaMemsetAsync(out_counts_dev, 0, (size_t)nq * 8, st));
+        return MLV_OK;
+    }
     const uint64_t slots = std::max<uint64_t>(max_hits, 1);
     int rc;
-    if ((rc = ensure_dev(h, h->d_qraw, qbytes)) != MLV_OK) return rc;
+    // the hit keys of one call: handle-level scratch (one range search at a time per handle)
     if ((rc = ensure_dev(h, h->d_range, (size_t)nq * slots * 8 + (size_t)nq * 8)) != MLV_OK) return rc;
     unsigned long long* d_counts = (unsigned long long*)h->d_range.p;
     uint64_t* d_keys = (uint64_t*)h->d_range.p + nq;
-    const uint32_t* filter_dev = nullptr;
-    if (filter_bitmap) {
-        const size_t fb = ((h->rows + 31) / 32) * 4;
-        if ((rc = ensure_dev(h, h->d_filter, fb)) != MLV_OK) return rc;
-        CK(h, cudaMemcpyAsync(h->d_filter.p, filter_bitmap, fb, cudaMemcpyHostToDevice, h->stream));
-        filter_dev = (const uint32_t*)h->d_filter.p;
-    }
-    CK(h, cudaMemcpyAsync(h->d_qraw.p, queries, qbytes, cudaMemcpyHostToDevice, h->stream));
-    CK(h, cudaMemsetAsync(d_counts, 0, (size_t)nq * 8, h->stream));
-    if ((rc = prep_queries(h, (const float*)h->d_qraw.p, nq, h->stream)) != MLV_OK) return rc;
-    Lane* ln = lane_for(h, h->stream);
+    CK(h, cudaMemsetAsync(d_counts, 0, (size_t)nq * 8, st));
+    if ((rc = prep_queries(h, queries_dev, nq, st)) != MLV_OK) return rc;
+    Lane* ln = lane_for(h, st);
     FilterPlan fp;
-    if ((rc = plan_filter(h, ln, filter_dev, h->stream, &fp)) != MLV_OK) return rc;
+    if ((rc = plan_filter(h, ln, filter_bitmap_dev, st, &fp)) != MLV_OK) return rc;
     ScanCfg c;
     if ((rc = choose_cfg(h, 1, 1, true, &c, fp.gather != nullptr)) != MLV_OK) return rc;
     ScanParams p{};
@@ -1403,26 +1398,63 @@ int mlv_index_range_search(mlv_index_t h, const float* queries, uint32_t nq, flo
     if ((rc = ensure_sched(h, ln)) != MLV_OK) return rc;
     fill_sched(h, ln, p);
     for (uint32_t q = 0; q < nq; q++) {
-        p.queries = reinterpret_cast<const float4*>((float*)lane_for(h, h->stream)->d_q.p + (size_t)q * h->ld);
+        p.queries = reinterpret_cast<const float4*>((const float*)ln->d_q.p + (size_t)q * h->ld);
         p.nq_valid = 1;
         p.range_counts = d_counts + q;
         p.range_keys = d_keys + (size_t)q * slots;
-        CK(h, launch_scan(h, p, c, true, h->stream));
+        CK(h, launch_scan(h, p, c, true, st));
     }
-    std::vector<unsigned long long> counts(nq);
-    CK(h, cudaMemcpyAsync(counts.data(), d_counts, (size_t)nq * 8, cudaMemcpyDeviceToHost, h->stream));
+    CK(h, cudaFuncSetAttribute(range_finish_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SELECT_MAX_P * 8)));
+    range_finish_kernel<<<nq, SELECT_THREADS, (size_t)SELECT_MAX_P * 8, st>>>(d_keys, d_counts, slots, max_hits, h->row_base, out_dists_dev,
+                                                                            out_rows_dev, (unsigned long long*)out_counts_dev);
+    h->launches++;
+    CK(h, cudaGetLastError());
+    return MLV_OK;
+}
+
+int mlv_index_range_search(mlv_index_t h, const float* queries, uint32_t nq, float radius, const uint32_t* filter_bitmap,
+                           uint64_t max_hits, float* out_dists, int64_t* out_rows, uint64_t* out_counts) {
+    if (!h || !queries || !out_counts || nq == 0 || (max_hits && (!out_dists || !out_rows))) return fail(h, MLV_E_INVALID, "bad argument");
+    DeviceGuard g(h->device);
+    for (uint32_t q = 0; q < nq; q++) out_counts[q] = 0;
+    if (h->rows == h->n_deleted) return MLV_OK;
+    const size_t qbytes = (size_t)nq * h->dim * 4;
+    const size_t nh = (size_t)nq * max_hits;
+    int rc;
+    if ((rc = ensure_dev(h, h->d_qraw, qbytes)) != MLV_OK) return rc;
+    if ((rc = ensure_dev(h, h->d_outd, std::max<size_t>(nh, 1) * 4)) != MLV_OK) return rc;
+    if ((rc = ensure_dev(h, h->d_outr, std::max<size_t>(nh, 1) * 8)) != MLV_OK) return rc;
+    if ((rc = ensure_dev(h, h->d_outc, (size_t)nq * 8)) != MLV_OK) return rc;
+    const uint32_t* filter_dev = nullptr;
+    if (filter_bitmap) {
+        const size_t fb = ((h->rows + 31) / 32) * 4;
+        if ((rc = ensure_dev(h, h->d_filter, fb)) != MLV_OK) return rc;
+        CK(h, cudaMemcpyAsync(h->d_filter.p, filter_bitmap, fb, cudaMemcpyHostToDevice, h->stream));
+        filter_dev = (const uint32_t*)h->d_filter.p;
+    }
+    CK(h, cudaMemcpyAsync(h->d_qraw.p, queries, qbytes, cudaMemcpyHostToDevice, h->stream));
+    rc = mlv_index_range_search_device(h, (const float*)h->d_qraw.p, nq, radius, filter_dev, max_hits, (float*)h->d_outd.p,
+                                       (int64_t*)h->d_outr.p, (uint64_t*)h->d_outc.p, h->stream);
+    if (rc != MLV_OK) return rc;
+    CK(h, cudaMemcpyAsync(out_counts, h->d_outc.p, (size_t)nq * 8, cudaMemcpyDeviceToHost, h->stream));
     CK(h, cudaStreamSynchronize(h->stream));
-    std::vector<uint64_t> keys;
+    std::vector<std::pair<float, int64_t>> big;
     for (uint32_t q = 0; q < nq; q++) {
-        out_counts[q] = counts[q];
-        const uint64_t got = std::min<uint64_t>(counts[q], max_hits);
+        const uint64_t got = std::min<uint64_t>(out_counts[q], max_hits);
         if (!got) continue;
-        keys.resize(got);
-        CK(h, cudaMemcpy(keys.data(), d_keys + (size_t)q * slots, got * 8, cudaMemcpyDeviceToHost));
-        std::sort(keys.begin(), keys.end());  // (distance, row) ascending
-        for (uint64_t i = 0; i < got; i++) {
-            out_dists[(size_t)q * max_hits + i] = key_dist(keys[i]);
-            out_rows[(size_t)q * max_hits + i] = (int64_t)(h->row_base + key_row(keys[i]));
+        float* od = out_dists + (size_t)q * max_hits;
+        int64_t* orow = out_rows + (size_t)q * max_hits;
+        CK(h, cudaMemcpyAsync(od, (float*)h->d_outd.p + (size_t)q * max_hits, got * 4, cudaMemcpyDeviceToHost, h->stream));
+        CK(h, cudaMemcpyAsync(orow, (int64_t*)h->d_outr.p + (size_t)q * max_hits, got * 8, cudaMemcpyDeviceToHost, h->stream));
+        CK(h, cudaStreamSynchronize(h->stream));
+        if (got > SELECT_MAX_P) {  // larger than one CTA sorts: order (distance, row) here
+            big.resize(got);
+            for (uint64_t i = 0; i < got; i++) big[i] = {od[i], orow[i]};
+            std::sort(big.begin(), big.end());
+            for (uint64_t i = 0; i < got; i++) {
+                od[i] = big[i].first;
+                orow[i] = big[i].second;
+            }
         }
     }
     return MLV_OK;

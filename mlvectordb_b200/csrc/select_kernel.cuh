@@ -79,6 +79,38 @@ __global__ void __launch_bounds__(SELECT_THREADS, 1) select_kernel(const SelectP
     if (threadIdx.x == 0) p.out_counts[q] = cnt;
 }
 
+// ---- range search: order one query's hits -------------------------------------------------------
+// grid = nq.  keys: [nq][slots] as appended by the scan (unordered).  Writes the first
+// min(count, max_hits) hits ascending (distance, row) when they fit one CTA's sort (<= SELECT_MAX_P);
+// larger hit lists are only decoded (the caller orders them).
+__global__ void __launch_bounds__(SELECT_THREADS, 1)
+range_finish_kernel(const uint64_t* keys, const unsigned long long* counts, uint64_t slots, uint64_t max_hits, uint64_t row_base,
+                    float* out_dists, int64_t* out_rows, unsigned long long* out_counts) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    uint64_t* a = reinterpret_cast<uint64_t*>(smem_raw);
+    const uint32_t q = blockIdx.x;
+    const unsigned long long total = counts[q];
+    const uint64_t n = total < max_hits ? total : max_hits;
+    const uint64_t* mine = keys + (size_t)q * slots;
+    if (threadIdx.x == 0) out_counts[q] = total;
+    if (n == 0) return;
+    if (n <= SELECT_MAX_P) {
+        uint32_t P = 2;
+        while (P < n) P <<= 1;
+        for (uint32_t i = threadIdx.x; i < P; i += blockDim.x) a[i] = i < n ? mine[i] : KEY_SENTINEL;
+        bitonic_sort_smem(a, P);
+        for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) {
+            out_dists[(size_t)q * max_hits + i] = key_dist(a[i]);
+            out_rows[(size_t)q * max_hits + i] = (int64_t)(row_base + key_row(a[i]));
+        }
+    } else {
+        for (uint64_t i = threadIdx.x; i < n; i += blockDim.x) {
+            out_dists[(size_t)q * max_hits + i] = key_dist(mine[i]);
+            out_rows[(size_t)q * max_hits + i] = (int64_t)(row_base + key_row(mine[i]));
+        }
+    }
+}
+
 // ---- merge of (distance, row) pair lists from row shards ------------------------------------
 struct MergePairsParams {
     const float* dists;   // [n_lists][nq][k]

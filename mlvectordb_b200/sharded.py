@@ -73,7 +73,8 @@ class ShardedIndex:
     EXCHANGE_MAX_NQ = 32
 
     def __init__(self, dim: int, space: str, total_rows: int, device: Optional[torch.device] = None, group=None,
-                 local_search: Optional[Callable] = None, merge: Optional[Callable] = None, fused_exchange: bool = True):
+                 local_search: Optional[Callable] = None, merge: Optional[Callable] = None, fused_exchange: bool = True,
+                 local_range: Optional[Callable] = None):
         self.dim, self.space, self.total_rows = int(dim), space, int(total_rows)
         self.group = group
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
@@ -84,6 +85,7 @@ class ShardedIndex:
         # the two device steps are injectable so the collective plumbing can be exercised on CPU (gloo)
         self._local_search = local_search or self._device_local_search
         self._merge = merge or merge_topk_device
+        self._local_range = local_range or self._device_local_range
         self.merge_launches = 0
         self.exchange = None
         if local_search is None:
@@ -176,6 +178,47 @@ class ShardedIndex:
         out = (st["d"][:nq].numpy().copy(), st["r"][:nq].numpy().copy(), st["c"][:nq].numpy().copy())
         if (out[2] < 0).any():
             raise RuntimeError("sharded search: a peer rank did not post its candidates within the exchange timeout")
+        return out
+
+    # -- range search ------------------------------------------------------------------------
+    def _device_local_range(self, queries: np.ndarray, radius: float):
+        if self.hi == self.lo:
+            return [(np.empty(0, np.float32), np.empty(0, np.int64)) for _ in range(queries.shape[0])]
+        return self.shard.range_search(queries, radius)   # rows already carry row_base
+
+    def range_search(self, queries: np.ndarray, radius: float):
+        """Collective.  Every live row of every shard with hnswlib-form distance <= radius, per query
+        ascending (distance, global row): the concatenation of the shards' hit lists.
+        The exchange is one all-gather of the hit counts and one of the lists padded to the longest."""
+        q = np.ascontiguousarray(queries, dtype=np.float32).reshape(-1, self.dim)
+        nq = q.shape[0]
+        local = self._local_range(q, float(radius))
+        if self.world == 1:
+            return local
+        dev = self.device if self.device is not None else torch.device("cpu")
+        counts = torch.tensor([len(d) for d, _ in local], dtype=torch.int64, device=dev)
+        all_counts = torch.empty((self.world * nq,), dtype=torch.int64, device=dev)
+        dist.all_gather_into_tensor(all_counts, counts, group=self.group)
+        all_counts = all_counts.view(self.world, nq).cpu().numpy()
+        m = int(all_counts.max())
+        if m == 0:
+            return [(np.empty(0, np.float32), np.empty(0, np.int64)) for _ in range(nq)]
+        pd = np.full((nq, m), np.inf, np.float32)
+        pr = np.full((nq, m), -1, np.int64)
+        for i, (d, r) in enumerate(local):
+            pd[i, :len(d)], pr[i, :len(r)] = d, r
+        gd = torch.empty((self.world * nq, m), dtype=torch.float32, device=dev)
+        gr = torch.empty((self.world * nq, m), dtype=torch.int64, device=dev)
+        dist.all_gather_into_tensor(gd, torch.from_numpy(pd).to(dev), group=self.group)
+        dist.all_gather_into_tensor(gr, torch.from_numpy(pr).to(dev), group=self.group)
+        gd = gd.view(self.world, nq, m).cpu().numpy()
+        gr = gr.view(self.world, nq, m).cpu().numpy()
+        out = []
+        for i in range(nq):
+            d = np.concatenate([gd[g, i, :all_counts[g, i]] for g in range(self.world)])
+            r = np.concatenate([gr[g, i, :all_counts[g, i]] for g in range(self.world)])
+            order = np.lexsort((r, d))
+            out.append((d[order], r[order]))
         return out
 
     def _staging(self, nq: int, k: int):

@@ -54,7 +54,14 @@ def main():
                 d[i, :m], r[i, :m], c[i] = D[i], L[i] + lo, m
         return torch.from_numpy(d), torch.from_numpy(r), torch.from_numpy(c)
 
-    idx = ShardedIndex(dim, space, total_rows, device=None, local_search=local_search, merge=numpy_merge)
+    def local_range(q, radius):
+        if hi == lo:
+            return [(np.empty(0, np.float32), np.empty(0, np.int64)) for _ in range(q.shape[0])]
+        L, D = exact.range_search(X, q, radius, space)
+        return [(np.asarray(D[i], np.float32), np.asarray(L[i], np.int64) + lo) for i in range(q.shape[0])]
+
+    idx = ShardedIndex(dim, space, total_rows, device=None, local_search=local_search, merge=numpy_merge,
+                       local_range=local_range)
     assert (idx.lo, idx.hi) == (lo, hi) and idx.world == world
     Q = synthetic.queries(5, 4, dim)
     d, r, c = idx.search_device(torch.from_numpy(Q), k)
@@ -67,6 +74,13 @@ def main():
         assert c[i] == min(k, total_rows)
         msg = exact.check_topk_parity(r[i, :c[i]].numpy(), d[i, :c[i]].numpy(), L[i], D[i])
         assert msg is None, msg
+    # range search: concatenation of the shards' hit lists == range search over the whole matrix
+    radius = float(np.sort(np.asarray(D[0], np.float64))[-1]) if total_rows >= 1 else 0.5
+    got = idx.range_search(Q, radius)
+    LR, DR = exact.range_search(full, Q, radius, space)
+    for i in range(4):
+        assert np.array_equal(got[i][1], np.asarray(LR[i], np.int64)), "sharded range rows differ"
+        assert np.array_equal(got[i][0], np.asarray(DR[i], np.float32))
     dist.destroy_process_group()
     print(f"rank {rank} ok")
 

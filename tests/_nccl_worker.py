@@ -56,7 +56,21 @@ def main():
             assert np.array_equal(d, wd, equal_nan=True)
             if total_rows > 5 and space != "ip" and not delete_every:   # the planted exact match wins (not under ip)
                 assert r[0, 0] == total_rows - 2
+            if k == 10 and nq <= 8:
+                radius = float(wd[0, min(9, wc[0] - 1)])            # <= 10 hits for query 0, more for none
+                wr_all = whole.range_search(Q, radius)
             whole.close()
+        if k == 10 and nq <= 8:
+            rad = torch.zeros(1, dtype=torch.float64, device=device)
+            if rank == 0:
+                rad[0] = radius
+            dist.broadcast(rad, 0)
+            got = idx.range_search(Q, float(rad.item()))
+            if rank == 0:
+                for (gd, gr), (hd, hr) in zip(got, wr_all):
+                    assert np.array_equal(gr, hr), "sharded range rows differ from unsharded"
+                    assert np.array_equal(gd, hd)
+                assert len(got[0][1]) >= 1
         idx.close()
 
     def idx_range(n, r, w):

@@ -262,3 +262,22 @@ def test_large_planted_matches_and_shard_merge_property():
         assert mr[i][order].tolist() == r[i].tolist()
         assert np.array_equal(md[i][order], d[i])
     s.close()
+
+
+def test_range_search_hit_lists_longer_than_one_sort_block():
+    """> 8192 hits: the device leaves them unordered, the host entry point orders them -- same contract."""
+    n, dim = 40_000, 16
+    X = synthetic.rows(77, 0, n, dim)
+    Q = synthetic.queries(77, 2, dim)
+    s = _shard(dim, "l2")
+    s.add(X)
+    ds = np.sort(exact.distances(X, Q[0], "l2"))
+    radius = float((ds[12_000] + ds[12_001]) / 2)
+    (d0, r0), (d1, r1) = s.range_search(Q, radius, max_hits=64)   # first call reports totals, shim retries
+    assert len(r0) == 12_001
+    L, D = exact.range_search(X, Q, radius, "l2")
+    for got_r, got_d, ref_r, ref_d in ((r0, d0, L[0], D[0]), (r1, d1, L[1], D[1])):
+        assert len(got_r) == len(ref_r)
+        assert set(got_r.tolist()) == set(np.asarray(ref_r).tolist()) or len(set(got_r.tolist()) ^ set(np.asarray(ref_r).tolist())) <= 4
+        assert np.all(np.diff(got_d) >= 0), "hits are not ascending"
+    s.close()
