@@ -225,6 +225,9 @@ int mlv_index_exchange_supported(mlv_index_t h, uint32_t k);
 int mlv_index_search_exchange_device(mlv_index_t h, const float *queries_dev, uint32_t nq, uint32_t k,
                                      const uint32_t *filter_bitmap_dev, float *out_dists_dev, int64_t *out_rows_dev,
                                      int32_t *out_counts_dev, void *stream);
+/* Same with host buffers (pinned staging inside, blocks until the results are back), like mlv_index_search. */
+int mlv_index_search_exchange(mlv_index_t h, const float *queries, uint32_t nq, uint32_t k, const uint32_t *filter_bitmap,
+                              float *out_dists, int64_t *out_rows, int32_t *out_counts);
 
 /*
  * Measurement hooks (bench.py / profiles): when enabled, every search records CUDA events

@@ -36,14 +36,20 @@
 namespace mlv {
 
 constexpr int GEMM_BM = 128;  // rows per tile      (UMMA M)
-constexpr int GEMM_BN = 256;  // queries per tile   (UMMA N)
 constexpr int GEMM_BK = 32;   // floats per K chunk (one 128-byte swizzle row)
-constexpr int GEMM_STAGES = 2;
 constexpr int GEMM_THREADS = 320;
 constexpr uint32_t GEMM_X_BYTES = GEMM_BM * GEMM_BK * 4;   // 16 KB
-constexpr uint32_t GEMM_Q_BYTES = GEMM_BN * GEMM_BK * 4;   // 32 KB
-constexpr uint32_t GEMM_STAGE_BYTES = 2 * GEMM_X_BYTES + 2 * GEMM_Q_BYTES;  // 96 KB
-constexpr uint32_t GEMM_SMEM_BYTES = 1024 + GEMM_STAGES * GEMM_STAGE_BYTES + 2 * GEMM_BN * 4 + 256;
+// Two shapes: BN = 256 queries per tile with a 2-stage ring (96 KB stages), or BN = 128 with a
+// 3-stage ring (64 KB stages): fewer queries share an X tile, but a deeper ring hides the refill latency.
+template <int BN>
+struct GemmShape {
+    static constexpr int STAGES = BN == 256 ? 2 : 3;
+    static constexpr uint32_t Q_BYTES = BN * GEMM_BK * 4;
+    static constexpr uint32_t STAGE_BYTES = 2 * GEMM_X_BYTES + 2 * Q_BYTES;
+    static constexpr uint32_t SMEM_BYTES = 1024 + STAGES * STAGE_BYTES + 2 * BN * 4 + 256;
+    // kind::tf32, fp32 accumulate, A and B K-major, M = 128, N = BN
+    static constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(GEMM_BM >> 4) << 24);
+};
 constexpr float GEMM_DELTA_REL = 1.220703125e-4f;  // 2^-13: bound on |a - exact| / scale (see rerank_kernel)
 
 struct GemmParams {
@@ -97,8 +103,6 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
     d |= (uint64_t)2 << 61;  // SWIZZLE_128B
     return d;
 }
-// kind::tf32, fp32 accumulate, A and B K-major, M = 128, N = 256
-constexpr uint32_t GEMM_IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(GEMM_BN >> 3) << 17) | ((uint32_t)(GEMM_BM >> 4) << 24);
 
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
     asm volatile(
@@ -115,10 +119,14 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
 }
 
 // ---- the GEMM + candidate-selection kernel ---------------------------------------------------
-template <int METRIC>
+template <int METRIC, int GEMM_BN>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_topk_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_qhi,
                  const __grid_constant__ CUtensorMap tm_qlo, const GemmParams p) {
+    constexpr int GEMM_STAGES = GemmShape<GEMM_BN>::STAGES;
+    constexpr uint32_t GEMM_Q_BYTES = GemmShape<GEMM_BN>::Q_BYTES;
+    constexpr uint32_t GEMM_STAGE_BYTES = GemmShape<GEMM_BN>::STAGE_BYTES;
+    constexpr uint32_t GEMM_IDESC = GemmShape<GEMM_BN>::IDESC;
     extern __shared__ unsigned char gemm_smem_raw[];
     // SWIZZLE_128B tiles need 1024-byte alignment
     unsigned char* smem = gemm_smem_raw + ((1024u - (smem_u32(gemm_smem_raw) & 1023u)) & 1023u);

@@ -114,6 +114,7 @@ struct mlv_index {
     uint64_t norms_valid = 0;  // rows [0, norms_valid) of d_norms are current
     int tune_gemm = -1;        // -1 auto, 0 never, 1 whenever the shape allows it
     int tune_gemm_min_nq = 32;
+    int tune_gemm_bn = 256;    // queries per GEMM tile: 256 (2-stage ring) or 128 (3-stage ring)
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> gemm_pending;
     uint64_t gemm_searches = 0, gemm_queries = 0, gemm_fallback_queries = 0, gemm_rounds = 0, gemm_launches = 0;
 };
@@ -253,7 +254,7 @@ int choose_cfg(mlv_index* h, uint32_t nq, uint32_t k, bool range, ScanCfg* c, bo
     const uint32_t ld4 = h->ld / 4;
     const size_t rowbytes = (size_t)h->ld * 4;
     int CW = h->tune_cw > 0 ? std::min(h->tune_cw, SCAN_MAX_CW) : (ld4 <= 64 ? 16 : 8);
-    int R = h->tune_r ? h->tune_r : (ld4 <= 128 ? 4 : (ld4 <= 256 ? 2 : 1));
+    int R = h->tune_r ? h->tune_r : (ld4 <= 256 ? 4 : (ld4 <= 512 ? 2 : 1));
     if (R != 1 && R != 2 && R != 4) R = 1;
     int NQ = 1;
     if (!range) {
@@ -679,14 +680,19 @@ int ensure_row_norms(mlv_index* h, cudaStream_t st) {
     return MLV_OK;
 }
 
+template <int METRIC, int BN>
+cudaError_t launch_gemm_tt(const CUtensorMap& mx, const CUtensorMap& mqh, const CUtensorMap& mql, const GemmParams& gp, int grid,
+                           cudaStream_t st) {
+    auto kern = gemm_topk_kernel<METRIC, BN>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GemmShape<BN>::SMEM_BYTES);
+    if (e != cudaSuccess) return e;
+    kern<<<grid, GEMM_THREADS, GemmShape<BN>::SMEM_BYTES, st>>>(mx, mqh, mql, gp);
+    return cudaGetLastError();
+}
 template <int METRIC>
 cudaError_t launch_gemm_t(const CUtensorMap& mx, const CUtensorMap& mqh, const CUtensorMap& mql, const GemmParams& gp, int grid,
-                          cudaStream_t st) {
-    auto kern = gemm_topk_kernel<METRIC>;
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM_SMEM_BYTES);
-    if (e != cudaSuccess) return e;
-    kern<<<grid, GEMM_THREADS, GEMM_SMEM_BYTES, st>>>(mx, mqh, mql, gp);
-    return cudaGetLastError();
+                          cudaStream_t st, int bn) {
+    return bn == 128 ? launch_gemm_tt<METRIC, 128>(mx, mqh, mql, gp, grid, st) : launch_gemm_tt<METRIC, 256>(mx, mqh, mql, gp, grid, st);
 }
 
 // Large batches: tcgen05 GEMM selects k' candidates per query in geometrically growing rounds,
@@ -696,6 +702,7 @@ int search_gemm(mlv_index* h, const float* qprep, uint32_t nq, uint32_t k, const
                 int64_t* out_r, int32_t* out_c, cudaStream_t st) {
     int rc;
     const uint32_t ld = h->ld;
+    const uint32_t GEMM_BN = h->tune_gemm_bn == 128 ? 128 : 256;
     const uint32_t nq_pad = (nq + GEMM_BN - 1) / GEMM_BN * GEMM_BN;
     const uint32_t kprime = gemm_kprime(k);
     const uint32_t cap = std::min<uint32_t>(SELECT_MAX_P, pow2_ceil(8 * kprime));
@@ -773,7 +780,8 @@ int search_gemm(mlv_index* h, const float* qprep, uint32_t nq, uint32_t k, const
             }
             cudaEventRecord(e0, st);
         }
-        CK(h, l2 ? launch_gemm_t<METRIC_L2>(mx, mqh, mql, gp, grid, st) : launch_gemm_t<METRIC_IP>(mx, mqh, mql, gp, grid, st));
+        CK(h, l2 ? launch_gemm_t<METRIC_L2>(mx, mqh, mql, gp, grid, st, (int)GEMM_BN)
+                 : launch_gemm_t<METRIC_IP>(mx, mqh, mql, gp, grid, st, (int)GEMM_BN));
         if (h->timing) {
             cudaEventRecord(e1, st);
             h->gemm_pending.emplace_back(e0, e1);
@@ -881,6 +889,7 @@ int mlv_index_create(uint32_t dim, int metric, uint64_t capacity_hint, int devic
     h->tune_fused = env_int("MLV_SCAN_FUSED", h->tune_fused);
     h->tune_gemm = env_int("MLV_GEMM", h->tune_gemm);
     h->tune_gemm_min_nq = env_int("MLV_GEMM_MIN_NQ", h->tune_gemm_min_nq);
+    h->tune_gemm_bn = env_int("MLV_GEMM_BN", h->tune_gemm_bn);
     DeviceGuard g(device);
     cudaDeviceProp prop;
     cudaError_t e = g.ok ? cudaGetDeviceProperties(&prop, device) : cudaErrorInvalidDevice;
@@ -956,6 +965,7 @@ int mlv_index_set_tuning(mlv_index_t h, const char* key, int value) {
     else if (k == "gather") h->tune_gather = value;
     else if (k == "gemm") h->tune_gemm = value;
     else if (k == "gemm_min_nq") h->tune_gemm_min_nq = value;
+    else if (k == "gemm_bn") h->tune_gemm_bn = value;
     else return fail(h, MLV_E_INVALID, "unknown tuning key " + k);
     return MLV_OK;
 }
@@ -1317,8 +1327,8 @@ int mlv_index_search_exchange_device(mlv_index_t h, const float* queries_dev, ui
     return search_prepared(h, (const float*)lane_for(h, st)->d_q.p, nq, k, filter_bitmap_dev, out_dists_dev, out_rows_dev, out_counts_dev, st, true);
 }
 
-int mlv_index_search(mlv_index_t h, const float* queries, uint32_t nq, uint32_t k, const uint32_t* filter_bitmap,
-                     float* out_dists, int64_t* out_rows, int32_t* out_counts) {
+static int search_host_common(mlv_index_t h, const float* queries, uint32_t nq, uint32_t k, const uint32_t* filter_bitmap,
+                              float* out_dists, int64_t* out_rows, int32_t* out_counts, bool exchange) {
     if (!h || !queries || !out_dists || !out_rows || !out_counts || nq == 0 || k == 0) return fail(h, MLV_E_INVALID, "bad argument");
     if (k > MLV_MAX_K) return fail(h, MLV_E_UNSUPPORTED, "k exceeds MLV_MAX_K");
     DeviceGuard g(h->device);
@@ -1328,9 +1338,11 @@ int mlv_index_search(mlv_index_t h, const float* queries, uint32_t nq, uint32_t 
     int rc;
     if ((rc = ensure_host(h, h->h_stage, std::max(qbytes, out_bytes))) != MLV_OK) return rc;
     if ((rc = ensure_dev(h, h->d_qraw, qbytes)) != MLV_OK) return rc;
-    if ((rc = ensure_dev(h, h->d_outr, nk * 8)) != MLV_OK) return rc;
-    if ((rc = ensure_dev(h, h->d_outd, nk * 4)) != MLV_OK) return rc;
-    if ((rc = ensure_dev(h, h->d_outc, (size_t)nq * 4)) != MLV_OK) return rc;
+    // one device block for the results (rows | dists | counts): a single copy brings them back
+    if ((rc = ensure_dev(h, h->d_outr, out_bytes)) != MLV_OK) return rc;
+    int64_t* d_rows_out = (int64_t*)h->d_outr.p;
+    float* d_dists_out = (float*)((char*)h->d_outr.p + nk * 8);
+    int32_t* d_counts_out = (int32_t*)((char*)h->d_outr.p + nk * 12);
     const uint32_t* filter_dev = nullptr;
     if (filter_bitmap && h->rows) {
         const size_t fb = ((h->rows + 31) / 32) * 4;
@@ -1340,19 +1352,30 @@ int mlv_index_search(mlv_index_t h, const float* queries, uint32_t nq, uint32_t 
     }
     memcpy(h->h_stage.p, queries, qbytes);
     CK(h, cudaMemcpyAsync(h->d_qraw.p, h->h_stage.p, qbytes, cudaMemcpyHostToDevice, h->stream));
-    rc = mlv_index_search_device(h, (const float*)h->d_qraw.p, nq, k, filter_dev, (float*)h->d_outd.p, (int64_t*)h->d_outr.p,
-                                 (int32_t*)h->d_outc.p, h->stream);
+    if (exchange)
+        rc = mlv_index_search_exchange_device(h, (const float*)h->d_qraw.p, nq, k, filter_dev, d_dists_out, d_rows_out,
+                                              d_counts_out, h->stream);
+    else
+        rc = mlv_index_search_device(h, (const float*)h->d_qraw.p, nq, k, filter_dev, d_dists_out, d_rows_out, d_counts_out,
+                                     h->stream);
     if (rc != MLV_OK) return rc;
-    // results come back through the pinned staging buffer: rows (8-byte aligned) first
     char* hs = (char*)h->h_stage.p;
-    CK(h, cudaMemcpyAsync(hs, h->d_outr.p, nk * 8, cudaMemcpyDeviceToHost, h->stream));
-    CK(h, cudaMemcpyAsync(hs + nk * 8, h->d_outd.p, nk * 4, cudaMemcpyDeviceToHost, h->stream));
-    CK(h, cudaMemcpyAsync(hs + nk * 12, h->d_outc.p, (size_t)nq * 4, cudaMemcpyDeviceToHost, h->stream));
+    CK(h, cudaMemcpyAsync(hs, h->d_outr.p, out_bytes, cudaMemcpyDeviceToHost, h->stream));
     CK(h, cudaStreamSynchronize(h->stream));
     memcpy(out_rows, hs, nk * 8);
     memcpy(out_dists, hs + nk * 8, nk * 4);
     memcpy(out_counts, hs + nk * 12, (size_t)nq * 4);
     return MLV_OK;
+}
+
+int mlv_index_search(mlv_index_t h, const float* queries, uint32_t nq, uint32_t k, const uint32_t* filter_bitmap,
+                     float* out_dists, int64_t* out_rows, int32_t* out_counts) {
+    return search_host_common(h, queries, nq, k, filter_bitmap, out_dists, out_rows, out_counts, false);
+}
+
+int mlv_index_search_exchange(mlv_index_t h, const float* queries, uint32_t nq, uint32_t k, const uint32_t* filter_bitmap,
+                              float* out_dists, int64_t* out_rows, int32_t* out_counts) {
+    return search_host_common(h, queries, nq, k, filter_bitmap, out_dists, out_rows, out_counts, true);
 }
 
 int mlv_index_range_search_device(mlv_index_t h, const float* queries_dev, uint32_t nq, float radius,
@@ -1575,6 +1598,7 @@ int mlv_index_debug_gemm(mlv_index_t h, const float* queries, uint32_t nq, float
     CK(h, cudaMemcpyAsync(h->d_qraw.p, queries, qbytes, cudaMemcpyHostToDevice, st));
     if ((rc = prep_queries(h, (const float*)h->d_qraw.p, nq, st)) != MLV_OK) return rc;
     if (h->metric != MLV_COSINE && (rc = ensure_row_norms(h, st)) != MLV_OK) return rc;
+    const uint32_t GEMM_BN = h->tune_gemm_bn == 128 ? 128 : 256;
     const uint32_t nq_pad = (nq + GEMM_BN - 1) / GEMM_BN * GEMM_BN;
     const uint32_t cap = pow2_ceil((uint32_t)h->rows);
     const size_t qmat = (size_t)nq_pad * ld * 4;
@@ -1607,7 +1631,8 @@ int mlv_index_debug_gemm(mlv_index_t h, const float* queries, uint32_t nq, float
     gp.row_tile0 = 0;
     gp.row_tile1 = (uint32_t)((h->rows + GEMM_BM - 1) / GEMM_BM);
     const int grid = (int)std::min<uint64_t>((uint64_t)gp.row_tile1 * gp.n_qtiles, (uint64_t)h->sm_count);
-    CK(h, h->metric == MLV_L2 ? launch_gemm_t<METRIC_L2>(mx, mqh, mql, gp, grid, st) : launch_gemm_t<METRIC_IP>(mx, mqh, mql, gp, grid, st));
+    CK(h, h->metric == MLV_L2 ? launch_gemm_t<METRIC_L2>(mx, mqh, mql, gp, grid, st, (int)GEMM_BN)
+                              : launch_gemm_t<METRIC_IP>(mx, mqh, mql, gp, grid, st, (int)GEMM_BN));
     h->launches += 3;
     std::vector<uint64_t> keys((size_t)nq * cap);
     std::vector<uint32_t> counts(nq);

@@ -272,6 +272,7 @@ __global__ void __launch_bounds__(SCAN_MAX_THREADS, 1) scan_kernel(const ScanPar
     uint64_t* my_lists = lists + (size_t)warp * NQ * k;
 
     uint32_t stage = 0, phase = 0, seq = 0;
+    uint32_t rot = 0;       // == seq % CW without the division
     uint32_t finished = 0;  // producers (= stage residue classes) that have posted their end mark
     const uint32_t all_finished = (1u << PW) - 1u;
     auto advance = [&]() {
@@ -281,7 +282,7 @@ __global__ void __launch_bounds__(SCAN_MAX_THREADS, 1) scan_kernel(const ScanPar
         }
     };
     for (;;) {
-        const uint32_t owner = stage % (uint32_t)PW;
+        const uint32_t owner = stage & (uint32_t)(PW - 1);  // PW is 1, 2 or 4 and divides S
         if ((finished >> owner) & 1u) {  // nothing will ever land here again
             advance();
             continue;
@@ -299,7 +300,7 @@ __global__ void __launch_bounds__(SCAN_MAX_THREADS, 1) scan_kernel(const ScanPar
         const float4* tile = ring + (size_t)stage * p.stage_f4;
         const uint32_t n_groups = ((uint32_t)n + R - 1) / R;
         // rotate the group -> warp assignment per tile so short tiles do not always hit warp 0
-        uint32_t g = (uint32_t)(warp + CW - (int)(seq % (uint32_t)CW)) % (uint32_t)CW;
+        uint32_t g = (uint32_t)(warp >= (int)rot ? warp - (int)rot : warp + CW - (int)rot);
         for (; g < n_groups; g += CW) {
             const uint32_t base = g * R;
             const uint32_t my_local = base + my_r;
@@ -356,6 +357,7 @@ __global__ void __launch_bounds__(SCAN_MAX_THREADS, 1) scan_kernel(const ScanPar
         __syncwarp();
         if (lane == 0) mbar_arrive(&empty[stage]);
         seq++;
+        if (++rot == (uint32_t)CW) rot = 0;
         advance();
     }
     if (p.timeline && tid == 0) p.timeline[blockIdx.x * 4 + 2] = global_timer_ns();

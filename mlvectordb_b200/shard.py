@@ -181,6 +181,17 @@ class DeviceShard:
             self._h, C.c_void_p(q_ptr), int(nq), int(k), C.c_void_p(filter_ptr) if filter_ptr else None,
             C.c_void_p(out_d_ptr), C.c_void_p(out_r_ptr), C.c_void_p(out_c_ptr), C.c_void_p(stream)))
 
+    def search_exchange(self, queries: np.ndarray, k: int):
+        """Collective, host buffers: like ``search`` but the outputs hold the GLOBAL top-k of all row shards."""
+        q = np.ascontiguousarray(queries, dtype=np.float32).reshape(-1, self.dim)
+        nq = q.shape[0]
+        dists = np.empty((nq, k), dtype=np.float32)
+        rows = np.empty((nq, k), dtype=np.int64)
+        counts = np.empty(nq, dtype=np.int32)
+        self._ck(self._lib.mlv_index_search_exchange(self._h, q.ctypes.data, nq, int(k), None, dists.ctypes.data,
+                                                     rows.ctypes.data, counts.ctypes.data))
+        return dists, rows, counts
+
     def range_search(self, queries: np.ndarray, radius: float, filt=None, max_hits: int = 1024):
         """-> list per query of (dists f32 [hits], rows i64 [hits]) ascending (d, row)."""
         q = np.ascontiguousarray(queries, dtype=np.float32)

@@ -167,6 +167,12 @@ class ShardedIndex:
         """Host buffers in, host buffers out (pinned staging, H2D + D2H inside the call)."""
         q = np.ascontiguousarray(queries, dtype=np.float32).reshape(-1, self.dim)
         nq = q.shape[0]
+        if self.exchange is not None and nq < self.EXCHANGE_MAX_NQ and self.shard.exchange_supported(k):
+            # straight through the C host entry point: one H2D, one kernel per query group, one D2H, one sync
+            out = self.shard.search_exchange(q, k)
+            if (out[2] < 0).any():
+                raise RuntimeError("sharded search: a peer rank did not post its candidates within the exchange timeout")
+            return out
         st = self._staging(nq, k)
         st["q"][:nq].copy_(torch.from_numpy(q))
         qd = st["q"][:nq].to(self.device, non_blocking=True)
