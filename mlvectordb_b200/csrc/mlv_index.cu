@@ -604,6 +604,31 @@ int prep_queries(mlv_index* h, const float* q_dev_raw, uint32_t nq, cudaStream_t
     return MLV_OK;
 }
 
+// Order n > SELECT_MAX_P keys (device, in a scratch copy padded to a power of two) and decode them.
+int sort_big_device(mlv_index* h, const uint64_t* keys, uint64_t n, float* out_d, int64_t* out_r, cudaStream_t st) {
+    uint64_t P = SELECT_MAX_P;
+    while (P < n) P <<= 1;
+    if (P > (1ull << 31)) return fail(h, MLV_E_UNSUPPORTED, "range hit list too long to order");
+    int rc = ensure_dev(h, h->d_misc, P * 8);
+    if (rc != MLV_OK) return rc;
+    uint64_t* a = (uint64_t*)h->d_misc.p;
+    CK(h, cudaMemcpyAsync(a, keys, n * 8, cudaMemcpyDeviceToDevice, st));
+    if (P > n) fill_sentinel_kernel<<<(unsigned)std::min<uint64_t>((P - n + 255) / 256, 1024), 256, 0, st>>>(a, n, P);
+    CK(h, cudaFuncSetAttribute(bitonic_block_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SELECT_MAX_P * 8)));
+    const unsigned blocks = (unsigned)(P / SELECT_MAX_P);
+    bitonic_block_kernel<<<blocks, SELECT_THREADS, (size_t)SELECT_MAX_P * 8, st>>>(a, 2, SELECT_MAX_P);
+    for (uint64_t size = 2ull * SELECT_MAX_P; size <= P; size <<= 1) {
+        for (uint64_t stride = size >> 1; stride >= SELECT_MAX_P; stride >>= 1)
+            bitonic_global_kernel<<<(unsigned)std::min<uint64_t>((P / 2 + 255) / 256, 4096), 256, 0, st>>>(a, (uint32_t)P, (uint32_t)size,
+                                                                                                         (uint32_t)stride);
+        bitonic_block_kernel<<<blocks, SELECT_THREADS, (size_t)SELECT_MAX_P * 8, st>>>(a, (uint32_t)size, (uint32_t)size);
+    }
+    decode_keys_kernel<<<(unsigned)std::min<uint64_t>((n + 255) / 256, 1024), 256, 0, st>>>(a, n, h->row_base, out_d, out_r);
+    h->launches += 3;
+    CK(h, cudaGetLastError());
+    return MLV_OK;
+}
+
 // ---- tensor-core batch path (gemm_kernel.cuh) ----------------------------------------------------
 typedef CUresult (*encode_tiled_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                     const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -1461,25 +1486,20 @@ int mlv_index_range_search(mlv_index_t h, const float* queries, uint32_t nq, flo
     if (rc != MLV_OK) return rc;
     CK(h, cudaMemcpyAsync(out_counts, h->d_outc.p, (size_t)nq * 8, cudaMemcpyDeviceToHost, h->stream));
     CK(h, cudaStreamSynchronize(h->stream));
-    std::vector<std::pair<float, int64_t>> big;
+    const uint64_t slots = std::max<uint64_t>(max_hits, 1);
     for (uint32_t q = 0; q < nq; q++) {
         const uint64_t got = std::min<uint64_t>(out_counts[q], max_hits);
         if (!got) continue;
-        float* od = out_dists + (size_t)q * max_hits;
-        int64_t* orow = out_rows + (size_t)q * max_hits;
-        CK(h, cudaMemcpyAsync(od, (float*)h->d_outd.p + (size_t)q * max_hits, got * 4, cudaMemcpyDeviceToHost, h->stream));
-        CK(h, cudaMemcpyAsync(orow, (int64_t*)h->d_outr.p + (size_t)q * max_hits, got * 8, cudaMemcpyDeviceToHost, h->stream));
-        CK(h, cudaStreamSynchronize(h->stream));
-        if (got > SELECT_MAX_P) {  // larger than one CTA sorts: order (distance, row) here
-            big.resize(got);
-            for (uint64_t i = 0; i < got; i++) big[i] = {od[i], orow[i]};
-            std::sort(big.begin(), big.end());
-            for (uint64_t i = 0; i < got; i++) {
-                od[i] = big[i].first;
-                orow[i] = big[i].second;
-            }
+        float* dd = (float*)h->d_outd.p + (size_t)q * max_hits;
+        int64_t* dr = (int64_t*)h->d_outr.p + (size_t)q * max_hits;
+        if (got > SELECT_MAX_P) {  // more hits than one CTA sorts: global bitonic network over the query's keys
+            uint64_t* keys = (uint64_t*)h->d_range.p + nq + (size_t)q * slots;
+            if ((rc = sort_big_device(h, keys, got, dd, dr, h->stream)) != MLV_OK) return rc;
         }
+        CK(h, cudaMemcpyAsync(out_dists + (size_t)q * max_hits, dd, got * 4, cudaMemcpyDeviceToHost, h->stream));
+        CK(h, cudaMemcpyAsync(out_rows + (size_t)q * max_hits, dr, got * 8, cudaMemcpyDeviceToHost, h->stream));
     }
+    CK(h, cudaStreamSynchronize(h->stream));
     return MLV_OK;
 }
 

@@ -79,10 +79,61 @@ __global__ void __launch_bounds__(SELECT_THREADS, 1) select_kernel(const SelectP
     if (threadIdx.x == 0) p.out_counts[q] = cnt;
 }
 
+// ---- sorting more keys than one CTA holds: bitonic network over global memory ------------------
+// a[0..P) (P a power of two > SELECT_MAX_P, padded with KEY_SENTINEL).  Blocks of SELECT_MAX_P keys are
+// handled in shared memory (all strides < SELECT_MAX_P of the merge steps size_lo..size_hi), the wider
+// strides by one global compare-exchange pass each.  Directions follow the GLOBAL element index.
+__global__ void __launch_bounds__(SELECT_THREADS, 1) bitonic_block_kernel(uint64_t* a, uint32_t size_lo, uint32_t size_hi) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    uint64_t* s = reinterpret_cast<uint64_t*>(smem_raw);
+    const uint32_t base = blockIdx.x * SELECT_MAX_P;
+    for (uint32_t i = threadIdx.x; i < SELECT_MAX_P; i += blockDim.x) s[i] = a[base + i];
+    for (uint32_t size = size_lo; size <= size_hi; size <<= 1) {
+        const uint32_t first = size >> 1 < SELECT_MAX_P ? size >> 1 : SELECT_MAX_P >> 1;
+        for (uint32_t stride = first; stride > 0; stride >>= 1) {
+            __syncthreads();
+            for (uint32_t t = threadIdx.x; t < (SELECT_MAX_P >> 1); t += blockDim.x) {
+                const uint32_t i = 2 * t - (t & (stride - 1));
+                const uint32_t j = i + stride;
+                const bool up = ((base + i) & size) == 0;
+                const uint64_t x = s[i], y = s[j];
+                if ((x > y) == up) {
+                    s[i] = y;
+                    s[j] = x;
+                }
+            }
+        }
+    }
+    __syncthreads();
+    for (uint32_t i = threadIdx.x; i < SELECT_MAX_P; i += blockDim.x) a[base + i] = s[i];
+}
+__global__ void bitonic_global_kernel(uint64_t* a, uint32_t P, uint32_t size, uint32_t stride) {
+    for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < (P >> 1); t += gridDim.x * blockDim.x) {
+        const uint32_t i = 2 * t - (t & (stride - 1));
+        const uint32_t j = i + stride;
+        const bool up = (i & size) == 0;
+        const uint64_t x = a[i], y = a[j];
+        if ((x > y) == up) {
+            a[i] = y;
+            a[j] = x;
+        }
+    }
+}
+// range hits -> (distance, row) arrays once the keys are in order
+__global__ void decode_keys_kernel(const uint64_t* keys, uint64_t n, uint64_t row_base, float* out_dists, int64_t* out_rows) {
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+        out_dists[i] = key_dist(keys[i]);
+        out_rows[i] = (int64_t)(row_base + key_row(keys[i]));
+    }
+}
+__global__ void fill_sentinel_kernel(uint64_t* a, uint64_t from, uint64_t to) {
+    for (uint64_t i = from + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < to; i += (uint64_t)gridDim.x * blockDim.x) a[i] = KEY_SENTINEL;
+}
+
 // ---- range search: order one query's hits -------------------------------------------------------
 // grid = nq.  keys: [nq][slots] as appended by the scan (unordered).  Writes the first
 // min(count, max_hits) hits ascending (distance, row) when they fit one CTA's sort (<= SELECT_MAX_P);
-// larger hit lists are only decoded (the caller orders them).
+// larger hit lists are decoded unordered here and ordered by sort_big_device (mlv_index.cu).
 __global__ void __launch_bounds__(SELECT_THREADS, 1)
 range_finish_kernel(const uint64_t* keys, const unsigned long long* counts, uint64_t slots, uint64_t max_hits, uint64_t row_base,
                     float* out_dists, int64_t* out_rows, unsigned long long* out_counts) {
@@ -103,7 +154,7 @@ range_finish_kernel(const uint64_t* keys, const unsigned long long* counts, uint
             out_dists[(size_t)q * max_hits + i] = key_dist(a[i]);
             out_rows[(size_t)q * max_hits + i] = (int64_t)(row_base + key_row(a[i]));
         }
-    } else {
+    } else {  // decoded in arrival order; the host entry point runs the global bitonic network over them
         for (uint64_t i = threadIdx.x; i < n; i += blockDim.x) {
             out_dists[(size_t)q * max_hits + i] = key_dist(mine[i]);
             out_rows[(size_t)q * max_hits + i] = (int64_t)(row_base + key_row(mine[i]));

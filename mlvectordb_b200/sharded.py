@@ -65,6 +65,25 @@ def merge_topk_device(gd: torch.Tensor, gr: torch.Tensor, k: int):
     return out_d, out_r, out_c
 
 
+def merge_all_device(gd: torch.Tensor, gr: torch.Tensor):
+    """All valid entries of ``[G, nq, m]`` padded hit lists per query, ascending (distance, list position):
+    ``mlv_merge_topk`` asked for every slot (k = G * m)."""
+    G, nq, m = gd.shape
+    k = G * m
+    out_d = torch.empty((nq, k), dtype=torch.float32, device=gd.device)
+    out_r = torch.empty((nq, k), dtype=torch.int64, device=gd.device)
+    out_c = torch.empty((nq,), dtype=torch.int32, device=gd.device)
+    # one "list" of k slots per query: reorder [G, nq, m] -> [1, nq, G*m] (rank-major inside a query)
+    d1 = gd.permute(1, 0, 2).reshape(1, nq, k).contiguous()
+    r1 = gr.permute(1, 0, 2).reshape(1, nq, k).contiguous()
+    stream = torch.cuda.current_stream(gd.device).cuda_stream
+    st = _capi.lib().mlv_merge_topk(gd.device.index, C.c_void_p(d1.data_ptr()), C.c_void_p(r1.data_ptr()), 1, nq, k,
+                                    C.c_void_p(out_d.data_ptr()), C.c_void_p(out_r.data_ptr()),
+                                    C.c_void_p(out_c.data_ptr()), C.c_void_p(stream))
+    _capi.check(st)
+    return out_d, out_r, out_c
+
+
 class ShardedIndex:
     """One namespace, rows sharded over the ranks of ``group``.  Every rank calls every method."""
 
@@ -217,6 +236,11 @@ class ShardedIndex:
         gr = torch.empty((self.world * nq, m), dtype=torch.int64, device=dev)
         dist.all_gather_into_tensor(gd, torch.from_numpy(pd).to(dev), group=self.group)
         dist.all_gather_into_tensor(gr, torch.from_numpy(pr).to(dev), group=self.group)
+        if gd.is_cuda and self.world * m <= 8192:
+            # concatenation of the shards' lists, ordered (distance, global row) by the merge kernel
+            md, mr, mc = merge_all_device(gd.view(self.world, nq, m), gr.view(self.world, nq, m))
+            md, mr, mc = md.cpu().numpy(), mr.cpu().numpy(), mc.cpu().numpy()
+            return [(md[i, :mc[i]].copy(), mr[i, :mc[i]].copy()) for i in range(nq)]
         gd = gd.view(self.world, nq, m).cpu().numpy()
         gr = gr.view(self.world, nq, m).cpu().numpy()
         out = []
