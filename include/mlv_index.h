@@ -253,7 +253,7 @@ int mlv_index_set_tuning(mlv_index_t h, const char *key, int value);
  */
 int mlv_index_debug_timeline(mlv_index_t h, uint64_t *out, uint32_t max_ctas, uint32_t *n_ctas);
 /*
- * Tensor-core batch path (csrc/gemm_kernel.cuh): searches with nq >= 32 queries on >= 16384 rows
+ * Tensor-core batch path (csrc/gemm_kernel.cuh): searches with nq >= 9 queries (more than one scan pass) on >= 16384 rows
  * run as a tcgen05 3xTF32 GEMM that selects k + slack candidates per query, re-scores them in the
  * reference's arithmetic and certifies the result; queries that fail the certificate are re-run
  * by the exact scan, so results do not depend on the path.  set_tuning keys: "gemm" (-1 auto,

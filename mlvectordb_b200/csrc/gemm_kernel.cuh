@@ -39,11 +39,12 @@ constexpr int GEMM_BM = 128;  // rows per tile      (UMMA M)
 constexpr int GEMM_BK = 32;   // floats per K chunk (one 128-byte swizzle row)
 constexpr int GEMM_THREADS = 320;
 constexpr uint32_t GEMM_X_BYTES = GEMM_BM * GEMM_BK * 4;   // 16 KB
-// Two shapes: BN = 256 queries per tile with a 2-stage ring (96 KB stages), or BN = 128 with a
-// 3-stage ring (64 KB stages): fewer queries share an X tile, but a deeper ring hides the refill latency.
+// Three shapes: BN = 256 queries per tile with a 2-stage ring (96 KB stages) for large batches (tensor-
+// bound); BN = 128 / 3 stages and BN = 64 / 4 stages for small batches, where a pass over the rows
+// is HBM-bound and padding the query tile to 256 columns would only burn tensor time.
 template <int BN>
 struct GemmShape {
-    static constexpr int STAGES = BN == 256 ? 2 : 3;
+    static constexpr int STAGES = BN == 256 ? 2 : (BN == 128 ? 3 : 4);
     static constexpr uint32_t Q_BYTES = BN * GEMM_BK * 4;
     static constexpr uint32_t STAGE_BYTES = 2 * GEMM_X_BYTES + 2 * Q_BYTES;
     static constexpr uint32_t SMEM_BYTES = 1024 + STAGES * STAGE_BYTES + 2 * BN * 4 + 256;

@@ -1,0 +1,411 @@
+// host_scan.inl -- host side of the scan path: launch shape, per-stream lanes, filter plans, scheduler / fused tail / exchange set-up, search_prepared, range ordering.
+// Part of the single translation unit mlv_index.cu (included there, in order).
+#pragma once
+
+namespace {
+
+// ---- scan configuration ------------------------------------------------------------------------
+// Shape of one scan launch.  Defaults come from B200 sweeps (profiles/r01_sweep_*.jsonl): short rows
+// are latency-bound in the consumers, so they get more warps, more rows per warp step and larger
+// stages; a gathering producer is bound by its copy issue rate (~80 cycles per row copy per warp),
+// so short rows get more producer warps.
+int choose_cfg(mlv_index* h, uint32_t nq, uint32_t k, bool range, ScanCfg* c, bool gather = false) {
+    const uint32_t ld4 = h->ld / 4;
+    const size_t rowbytes = (size_t)h->ld * 4;
+    int CW = h->tune_cw > 0 ? std::min(h->tune_cw, SCAN_MAX_CW) : (ld4 <= 64 ? 16 : 8);
+    int R = h->tune_r ? h->tune_r : (ld4 <= 256 ? 4 : (ld4 <= 512 ? 2 : 1));
+    if (R != 1 && R != 2 && R != 4) R = 1;
+    int NQ = 1;
+    if (!range) {
+        while (NQ < 8 && (uint32_t)NQ < nq) NQ <<= 1;
+        while (NQ > 1 && ((size_t)NQ * k * CW * 8 > 65536 || R * NQ > 32)) NQ >>= 1;
+    }
+    const int max_stages = std::min(std::max(h->tune_max_stages, 2), 16);
+    const size_t fixed = (size_t)NQ * rowbytes + (range ? 0 : (size_t)CW * NQ * k * 8) + (size_t)max_stages * 24 + 256;
+    if (fixed + 2 * rowbytes > h->smem_optin)
+        return fail(h, MLV_E_UNSUPPORTED, "dimension too large for the shared-memory ring of this build");
+    const size_t avail = h->smem_optin - fixed;
+    const size_t group_bytes = (size_t)R * CW * rowbytes;
+    const size_t target = (size_t)(h->tune_stage_kb > 0 ? h->tune_stage_kb : (ld4 <= 32 ? 64 : 32)) * 1024;
+    uint64_t m = std::max<uint64_t>(1, target / group_bytes);
+    uint64_t T = (uint64_t)R * CW * m;
+    if (T * rowbytes * 2 > avail) {
+        T = (avail / 2 / rowbytes) / R * R;
+        if (T == 0) {
+            R = 1;
+            T = avail / 2 / rowbytes;
+        }
+        if (T == 0) return fail(h, MLV_E_UNSUPPORTED, "dimension too large for the shared-memory ring of this build");
+    }
+    {
+        // small matrices: at least ~2 tiles per SM, otherwise most SMs idle while a few walk several tiles
+        const uint64_t want_tiles = 2ull * (uint64_t)(h->tune_ctas > 0 ? h->tune_ctas : h->sm_count);
+        if (h->rows && (h->rows + T - 1) / T < want_tiles) {
+            uint64_t t2 = (h->rows + want_tiles - 1) / want_tiles;
+            t2 = std::max<uint64_t>((t2 + R - 1) / R * R, (uint64_t)R * 8);  // >= 8 warp steps of R rows per tile
+            T = std::min(T, t2);
+        }
+    }
+    const size_t stage = T * rowbytes;
+    if (stage >= (1u << 20)) return fail(h, MLV_E_UNSUPPORTED, "ring stage exceeds the mbarrier tx-count range");
+    uint32_t S = (uint32_t)std::min<size_t>(max_stages, avail / stage);
+    int PW = 1;
+    if (gather) PW = h->tune_pw > 0 ? std::min(h->tune_pw, SCAN_MAX_PW) : (rowbytes >= 2048 ? 1 : (rowbytes >= 1024 ? 2 : 4));
+    while (PW > 1 && (uint32_t)PW > S) PW >>= 1;
+    if (PW == 3) PW = 2;
+    S = S / PW * PW;
+    c->PW = PW;
+    c->R = R;
+    c->NQ = NQ;
+    c->CW = CW;
+    c->T = (uint32_t)T;
+    c->S = S;
+    c->stage_f4 = (uint32_t)(stage / 16);
+    c->smem = (size_t)S * stage + (size_t)NQ * rowbytes + (range ? 0 : (size_t)CW * NQ * k * 8) + (size_t)S * 24;
+    const uint64_t n_tiles = (h->rows + T - 1) / T;
+    const int ctas = h->tune_ctas > 0 ? h->tune_ctas : h->sm_count;
+    c->grid = (int)std::min<uint64_t>(n_tiles, (uint64_t)ctas);
+    if (c->grid < 1) c->grid = 1;
+    c->threads = (CW + PW) * 32;
+    const size_t bytes = h->rows * rowbytes;
+    c->evict_first = h->tune_evict_first >= 0 ? h->tune_evict_first : (bytes > ((size_t)96 << 20) ? 1 : 0);
+    return MLV_OK;
+}
+
+template <int METRIC, int NQ, int R, bool RANGE>
+cudaError_t launch_scan_t(const ScanParams& p, const ScanCfg& c, cudaStream_t st) {
+    auto kern = scan_kernel<METRIC, NQ, R, RANGE>;
+    // the opt-in shared-memory limit is per function and device: raise it once per (instantiation, device)
+    static size_t raised[64] = {0};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64 || raised[dev] < c.smem) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c.smem);
+        if (e != cudaSuccess) return e;
+        if (dev >= 0 && dev < 64) raised[dev] = c.smem;
+    }
+    kern<<<c.grid, c.threads, c.smem, st>>>(p);
+    return cudaGetLastError();
+}
+
+template <int METRIC, bool RANGE>
+cudaError_t launch_scan_m(const ScanParams& p, const ScanCfg& c, cudaStream_t st) {
+#define MLV_CASE(NQv, Rv) \
+    if (c.NQ == NQv && c.R == Rv) return launch_scan_t<METRIC, NQv, Rv, RANGE>(p, c, st);
+    MLV_CASE(1, 1) MLV_CASE(1, 2) MLV_CASE(1, 4)
+    if (!RANGE) {
+        MLV_CASE(2, 1) MLV_CASE(2, 2) MLV_CASE(2, 4)
+        MLV_CASE(4, 1) MLV_CASE(4, 2) MLV_CASE(4, 4)
+        MLV_CASE(8, 1) MLV_CASE(8, 2) MLV_CASE(8, 4)
+    }
+#undef MLV_CASE
+    return cudaErrorInvalidValue;
+}
+
+cudaError_t launch_scan(mlv_index* h, const ScanParams& p, const ScanCfg& c, bool range, cudaStream_t st) {
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    if (h->timing) {
+        for (cudaEvent_t* ev : {&e0, &e1}) {
+            if (!h->event_pool.empty()) {
+                *ev = h->event_pool.back();
+                h->event_pool.pop_back();
+            } else {
+                cudaError_t e = cudaEventCreate(ev);
+                if (e != cudaSuccess) return e;
+            }
+        }
+        cudaEventRecord(e0, st);
+    }
+    cudaError_t e;
+    const bool l2 = h->metric == MLV_L2;
+    if (range)
+        e = l2 ? launch_scan_m<METRIC_L2, true>(p, c, st) : launch_scan_m<METRIC_IP, true>(p, c, st);
+    else
+        e = l2 ? launch_scan_m<METRIC_L2, false>(p, c, st) : launch_scan_m<METRIC_IP, false>(p, c, st);
+    h->launches++;
+    if (h->timing) {
+        cudaEventRecord(e1, st);
+        h->pending.emplace_back(e0, e1);
+    }
+    return e;
+}
+
+__global__ void fill_empty_kernel(float* d, int64_t* r, int32_t* c, uint32_t nq, uint32_t k) {
+    const uint32_t total = nq * k;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        d[i] = __int_as_float(0x7f800000);
+        r[i] = -1;
+    }
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < nq; i += gridDim.x * blockDim.x) c[i] = 0;
+}
+
+bool g_select_attr_set[64] = {false};
+cudaError_t ensure_select_attrs(int device) {
+    if (device >= 0 && device < 64 && g_select_attr_set[device]) return cudaSuccess;
+    cudaError_t e = cudaFuncSetAttribute(select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SELECT_MAX_P * 8));
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(merge_pairs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SELECT_MAX_P * 8));
+    if (e != cudaSuccess) return e;
+    if (device >= 0 && device < 64) g_select_attr_set[device] = true;
+    return cudaSuccess;
+}
+
+// The lane of the stream a search runs on; a new stream takes the least recently used lane
+// (after making sure that lane's previous stream is done with the buffers).
+Lane* lane_for(mlv_index* h, cudaStream_t st) {
+    Lane* lru = &h->lanes[0];
+    for (Lane& l : h->lanes) {
+        if (l.used && l.stream == st) {
+            l.last_use = ++h->lane_clock;
+            return &l;
+        }
+        if (!l.used) {
+            if (lru->used) lru = &l;
+        } else if (lru->used && l.last_use < lru->last_use) {
+            lru = &l;
+        }
+    }
+    if (lru->used) cudaStreamSynchronize(lru->stream);
+    lru->used = true;
+    lru->stream = st;
+    lru->last_use = ++h->lane_clock;
+    return lru;
+}
+
+// Build the ascending list of rows that are live AND pass `bm` (device bitmap, `words` words; rows
+// beyond it do not pass) into list/scratch, on `st`.  scratch[0] (u64) receives the list length.
+int build_gather_list(mlv_index* h, DevBuf& list, DevBuf& scratch, const uint32_t* bm, uint64_t words, cudaStream_t st) {
+    const uint64_t n = h->rows, n_words = (n + 31) / 32;
+    int rc;
+    if ((rc = ensure_dev(h, scratch, n_words * 8 + 8)) != MLV_OK) return rc;
+    if ((rc = ensure_dev(h, list, std::max<uint64_t>(n, 1) * 4)) != MLV_OK) return rc;
+    uint64_t* d_total = (uint64_t*)scratch.p;
+    live_prefix_kernel<<<1, 1024, 0, st>>>(h->d_live, n, d_total + 1, d_total, bm, words);
+    scatter_passing_rows_kernel<<<(unsigned)std::min<uint64_t>((n_words + 255) / 256, 2048), 256, 0, st>>>(
+        h->d_live, bm, words, n, d_total + 1, (uint32_t*)list.p);
+    h->launches += 2;
+    CK(h, cudaGetLastError());
+    return MLV_OK;
+}
+
+// What a search reads its rows through: nothing special, a bitmap checked per row, or a gather list.
+struct FilterPlan {
+    const uint32_t* bitmap = nullptr;      // stream + mask
+    const uint32_t* gather = nullptr;      // row list (live AND passing)
+    const uint32_t* n_rows_dev = nullptr;  // its length (device)
+};
+
+// filter_dev: per-call bitmap (ceil(rows/32) words) or null; a bound prepared filter applies when it is null.
+int plan_filter(mlv_index* h, Lane* ln, const uint32_t* filter_dev, cudaStream_t st, FilterPlan* out) {
+    *out = FilterPlan{};
+    mlv_filter* f = filter_dev ? nullptr : h->bound_filter;
+    if (!filter_dev && !f) return MLV_OK;
+    int rc;
+    if (f) {
+        if (f->compact_gen != h->compact_gen)
+            return fail(h, MLV_E_INVALID, "prepared filter predates a compaction / clear of the index (rows were renumbered); create it again");
+        if (f->epoch != h->epoch) {  // rows were added / deleted since: rebuild (device only; count re-read lazily)
+            if ((rc = build_gather_list(h, f->d_list, f->d_scratch, (const uint32_t*)f->d_bitmap.p, f->bitmap_words, st)) != MLV_OK) return rc;
+            f->epoch = h->epoch;
+            f->counted = false;
+        }
+        const bool covers = f->bitmap_words >= (h->rows + 31) / 32;  // only then can the bitmap mask a full stream
+        const bool dense = f->counted && f->passing * 4 >= (h->rows - h->n_deleted) * 3;
+        const bool want_stream = h->tune_gather == 0 || (h->tune_gather < 0 && dense);
+        if (want_stream && covers) {
+            out->bitmap = (const uint32_t*)f->d_bitmap.p;  // stream every row, mask in the epilogue
+            return MLV_OK;
+        }
+        out->gather = (const uint32_t*)f->d_list.p;
+        out->n_rows_dev = (const uint32_t*)f->d_scratch.p;  // low word of the u64 total
+        return MLV_OK;
+    }
+    if (h->tune_gather == 0) {
+        out->bitmap = filter_dev;
+        return MLV_OK;
+    }
+    if ((rc = build_gather_list(h, ln->d_flist, ln->d_fscratch, filter_dev, (h->rows + 31) / 32, st)) != MLV_OK) return rc;
+    out->gather = (const uint32_t*)ln->d_flist.p;
+    out->n_rows_dev = (const uint32_t*)ln->d_fscratch.p;
+    return MLV_OK;
+}
+
+int ensure_sched(mlv_index* h, Lane* ln) {
+    if (ln->d_sched.p) return MLV_OK;
+    int rc = ensure_dev(h, ln->d_sched, 8);
+    if (rc != MLV_OK) return rc;
+    CK(h, cudaMemset(ln->d_sched.p, 0, ln->d_sched.bytes));
+    return MLV_OK;
+}
+
+void fill_sched(mlv_index* h, Lane* ln, ScanParams& p) {
+    p.sched = h->tune_dynamic ? (uint32_t*)ln->d_sched.p : nullptr;
+    // several tiles per claim only when there are plenty of claims per SM
+    uint32_t batch = (uint32_t)std::max(h->tune_tile_batch, 1);
+    while (batch > 1 && (uint64_t)p.n_tiles < 16ull * batch * (uint64_t)h->sm_count) batch >>= 1;
+    p.tile_batch = batch;
+}
+
+// can the last CTA fold the whole grid's lists (and hold its scratch in the idle ring)?
+bool fused_ok(const mlv_index* h, const ScanCfg& c, uint32_t k) {
+    if (!h->tune_dynamic || !h->tune_fused) return false;
+    if ((uint64_t)c.grid * k > SCAN_FUSED_MAX_KEYS || (uint64_t)c.CW * k > 1024) return false;
+    return (size_t)c.S * c.stage_f4 * 16 >= ((size_t)SCAN_FUSED_MAX_KEYS + (size_t)c.NQ * k) * 8;
+}
+
+// the exchange path must take the same decision on every rank, whatever its shard's grid is
+bool exchange_ok(const mlv_index* h, uint32_t k) {
+    return h->xchg && h->xchg->connected && h->tune_dynamic && h->tune_fused && k <= XCHG_MAX_K &&
+           (uint64_t)h->sm_count * k <= SCAN_FUSED_MAX_KEYS;
+}
+
+void fill_exchange(mlv_index* h, ExchangeView& x) {
+    const mlv_exchange* e = h->xchg;
+    x.world = e->world;
+    x.rank = e->rank;
+    for (uint32_t i = 0; i < e->world; i++) {
+        x.bufs[i] = e->bufs[i];
+        x.row_bases[i] = h->xchg_row_bases[i];
+    }
+    x.error = e->d_error;
+}
+
+// qprep: prepared queries [nq, ld] in device memory; all output pointers in device memory.
+// exchange: merge with the other ranks' results over peer memory (caller checked exchange_ok).
+int search_prepared(mlv_index* h, const float* qprep, uint32_t nq, uint32_t k, const uint32_t* filter_dev, float* out_d,
+                    int64_t* out_r, int32_t* out_c, cudaStream_t st, bool exchange = false) {
+    Lane* ln = lane_for(h, st);
+    FilterPlan fp;
+    int rc = plan_filter(h, ln, filter_dev, st, &fp);
+    if (rc != MLV_OK) return rc;
+    ScanCfg c;
+    if ((rc = choose_cfg(h, nq, k, false, &c, fp.gather != nullptr)) != MLV_OK) return rc;
+    if ((rc = ensure_sched(h, ln)) != MLV_OK) return rc;
+    const bool fused = fused_ok(h, c, k);
+    if (exchange && !fused) return fail(h, MLV_E_UNSUPPORTED, "exchange search needs the fused final select");
+    const uint32_t F = SELECT_MAX_P / k;  // lists one select CTA can fold (>= 8)
+    // bound the candidate scratch: chunk * grid * k keys
+    uint32_t chunk = (uint32_t)std::max<size_t>(1, ((size_t)64 << 20) / ((size_t)c.grid * k * 8));
+    chunk = std::max<uint32_t>(chunk / c.NQ * c.NQ, c.NQ);
+    chunk = std::min(chunk, nq);
+    rc = ensure_dev(h, ln->d_keys0, (size_t)chunk * c.grid * k * 8);
+    if (rc != MLV_OK) return rc;
+    const uint32_t lists1 = ((uint32_t)c.grid + F - 1) / F;
+    if (lists1 > 1) {
+        rc = ensure_dev(h, ln->d_keys1, (size_t)chunk * lists1 * k * 8);
+        if (rc != MLV_OK) return rc;
+    }
+    CK(h, ensure_select_attrs(h->device));
+
+    ScanParams p{};
+    p.rows = reinterpret_cast<const float4*>(h->d_rows);
+    p.n_rows = (uint32_t)h->rows;
+    p.ld4 = h->ld / 4;
+    p.tile_rows = c.T;
+    p.n_tiles = (uint32_t)((h->rows + c.T - 1) / c.T);
+    p.stages = c.S;
+    p.producer_warps = (uint32_t)c.PW;
+    p.stage_f4 = c.stage_f4;
+    p.k = k;
+    p.live = h->n_deleted ? h->d_live : nullptr;
+    p.filter = fp.bitmap;
+    p.gather = fp.gather;
+    p.n_rows_dev = fp.n_rows_dev;
+    p.evict_first = c.evict_first;
+    fill_sched(h, ln, p);
+    p.fused = fused ? 1 : 0;
+    p.row_base = h->row_base;
+    if (exchange) fill_exchange(h, p.xchg);
+    if (h->tune_timeline) {
+        rc = ensure_dev(h, h->d_timeline, (size_t)c.grid * 4 * 8);
+        if (rc != MLV_OK) return rc;
+        p.timeline = (unsigned long long*)h->d_timeline.p;
+        h->last_grid = c.grid;
+    }
+
+    for (uint32_t q0 = 0; q0 < nq; q0 += chunk) {
+        const uint32_t nchunk = std::min(chunk, nq - q0);
+        for (uint32_t g0 = 0; g0 < nchunk; g0 += c.NQ) {
+            p.queries = reinterpret_cast<const float4*>(qprep + (size_t)(q0 + g0) * h->ld);
+            p.nq_valid = std::min<uint32_t>(c.NQ, nchunk - g0);
+            p.out_keys = (uint64_t*)ln->d_keys0.p + (size_t)g0 * c.grid * k;
+            if (fused) {
+                p.out_dists = out_d + (size_t)(q0 + g0) * k;
+                p.out_rows = out_r + (size_t)(q0 + g0) * k;
+                p.out_counts = out_c + (q0 + g0);
+                if (exchange) p.xchg.seq = ++h->xseq;
+            }
+            CK(h, launch_scan(h, p, c, false, st));
+        }
+        if (fused) continue;  // the last CTA of every launch already wrote the final top-k
+        // fold the grid's lists into one per query
+        const uint64_t* in = (const uint64_t*)ln->d_keys0.p;
+        uint64_t* bufs[2] = {(uint64_t*)ln->d_keys1.p, (uint64_t*)ln->d_keys0.p};
+        uint32_t n_lists = (uint32_t)c.grid;
+        int flip = 0;
+        for (;;) {
+            SelectParams sp{};
+            sp.in_keys = in;
+            sp.n_lists = n_lists;
+            sp.k = k;
+            sp.lists_per_block = std::min(F, n_lists);
+            sp.n_out_lists = (n_lists + sp.lists_per_block - 1) / sp.lists_per_block;
+            sp.P = pow2_ceil(std::max<uint32_t>(sp.lists_per_block * k, 2));
+            sp.final_pass = sp.n_out_lists == 1;
+            sp.out_keys = bufs[flip];
+            sp.out_dists = out_d + (size_t)q0 * k;
+            sp.out_rows = out_r + (size_t)q0 * k;
+            sp.out_counts = out_c + q0;
+            sp.row_base = h->row_base;
+            const int threads = (int)std::min<uint32_t>(SELECT_THREADS, std::max<uint32_t>(sp.P / 2, 32));
+            select_kernel<<<dim3(sp.n_out_lists, nchunk), threads, (size_t)sp.P * 8, st>>>(sp);
+            h->launches++;
+            CK(h, cudaGetLastError());
+            if (sp.final_pass) break;
+            in = sp.out_keys;
+            n_lists = sp.n_out_lists;
+            flip ^= 1;
+        }
+    }
+    return MLV_OK;
+}
+
+int prep_queries(mlv_index* h, const float* q_dev_raw, uint32_t nq, cudaStream_t st) {
+    Lane* ln = lane_for(h, st);
+    int rc = ensure_dev(h, ln->d_q, (size_t)nq * h->ld * 4);
+    if (rc != MLV_OK) return rc;
+    const int wpb = 4;
+    prep_queries_kernel<<<(nq + wpb - 1) / wpb, wpb * 32, 0, st>>>(q_dev_raw, (float*)ln->d_q.p, nq, h->dim, h->ld,
+                                                                 h->metric == MLV_COSINE);
+    h->launches++;
+    CK(h, cudaGetLastError());
+    return MLV_OK;
+}
+
+// Order n > SELECT_MAX_P keys (device, in a scratch copy padded to a power of two) and decode them.
+int sort_big_device(mlv_index* h, const uint64_t* keys, uint64_t n, float* out_d, int64_t* out_r, cudaStream_t st) {
+    uint64_t P = SELECT_MAX_P;
+    while (P < n) P <<= 1;
+    if (P > (1ull << 31)) return fail(h, MLV_E_UNSUPPORTED, "range hit list too long to order");
+    int rc = ensure_dev(h, h->d_misc, P * 8);
+    if (rc != MLV_OK) return rc;
+    uint64_t* a = (uint64_t*)h->d_misc.p;
+    CK(h, cudaMemcpyAsync(a, keys, n * 8, cudaMemcpyDeviceToDevice, st));
+    if (P > n) fill_sentinel_kernel<<<(unsigned)std::min<uint64_t>((P - n + 255) / 256, 1024), 256, 0, st>>>(a, n, P);
+    CK(h, cudaFuncSetAttribute(bitonic_block_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SELECT_MAX_P * 8)));
+    const unsigned blocks = (unsigned)(P / SELECT_MAX_P);
+    bitonic_block_kernel<<<blocks, SELECT_THREADS, (size_t)SELECT_MAX_P * 8, st>>>(a, 2, SELECT_MAX_P);
+    for (uint64_t size = 2ull * SELECT_MAX_P; size <= P; size <<= 1) {
+        for (uint64_t stride = size >> 1; stride >= SELECT_MAX_P; stride >>= 1)
+            bitonic_global_kernel<<<(unsigned)std::min<uint64_t>((P / 2 + 255) / 256, 4096), 256, 0, st>>>(a, (uint32_t)P, (uint32_t)size,
+                                                                                                         (uint32_t)stride);
+        bitonic_block_kernel<<<blocks, SELECT_THREADS, (size_t)SELECT_MAX_P * 8, st>>>(a, (uint32_t)size, (uint32_t)size);
+    }
+    decode_keys_kernel<<<(unsigned)std::min<uint64_t>((n + 255) / 256, 1024), 256, 0, st>>>(a, n, h->row_base, out_d, out_r);
+    h->launches += 3;
+    CK(h, cudaGetLastError());
+    return MLV_OK;
+}
+
+
+}  // namespace

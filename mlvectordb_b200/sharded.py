@@ -87,9 +87,9 @@ def merge_all_device(gd: torch.Tensor, gr: torch.Tensor):
 class ShardedIndex:
     """One namespace, rows sharded over the ranks of ``group``.  Every rank calls every method."""
 
-    # batches of this many queries or more run the local tensor-core path (csrc/gemm_kernel.cuh) and
+    # batches of this many queries or more (mlv gemm_min_nq) run the local tensor-core path (csrc/gemm_kernel.cuh) and
     # merge through NCCL; smaller ones use the fused scan + peer-memory exchange kernel
-    EXCHANGE_MAX_NQ = 32
+    EXCHANGE_MAX_NQ = 9
 
     def __init__(self, dim: int, space: str, total_rows: int, device: Optional[torch.device] = None, group=None,
                  local_search: Optional[Callable] = None, merge: Optional[Callable] = None, fused_exchange: bool = True,
