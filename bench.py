@@ -11,11 +11,14 @@ an NCCL all-gather of the ranks' candidates + the final select kernel.  A "step"
 
 One JSON line on rank 0:
   value     queries/s with queries and results resident in HBM (device pointers through the C ABI,
-            CUDA-event timed on the launching stream, max over ranks)
+            CUDA-event timed, max over ranks).  Every query is its own search (own launch, own
+            result); two are in flight on two streams so one query's scan fills the SMs the
+            previous one's tail has left (roofline.one_query_in_flight has the strictly serial rate)
   e2e       the same through the public host API (``GpuIndex.search`` at N=1,
             ``ShardedIndex.search`` at N>1): host query in, host results out, copies inside
-  roofline  scan kernel: algorithmic bytes per launch / mean launch duration (CUDA events around
-            every scan launch inside the timed region) vs the measured HBM copy peak
+  roofline  scan kernel: algorithmic bytes per launch / average launch duration over the timed
+            region (region device time / scan launches in it) vs the measured HBM copy peak;
+            kernel_alone = CUDA events around every scan launch with one query in flight
   cpu_baseline  the oracle's C port of hnswlib's brute-force arithmetic on the host cores, on a
             bounded row sample, scaled to the full row count (N=1, rank 0 only)
 
@@ -348,6 +351,8 @@ def run_ours(a):
         "bytes_per_launch": bytes_per_launch, "launches_timed": n_queries, "mean_launch_ms": launch_ms,
         "how": "algorithmic bytes per scan launch / (timed-region device time / scan launches in it)",
         "frac_of_nominal_8000": achieved / 8000.0,
+        "one_query_in_flight": {"value": alone_steps * qps_step / (max_over_ranks(alone_ms) / 1e3), "unit": UNIT,
+                                "how": "the same searches strictly one after another on one stream (device-timed)"},
         "kernel_alone": {"mean_launch_ms": scan_ms_avg, "GBps": (bytes_per_launch / (scan_ms_avg * 1e-3) / 1e9) if scan_n else None,
                          "launches": scan_n, "share_of_its_step": (scan_ms / alone_ms) if scan_n else None,
                          "how": "CUDA events around every scan launch, one query in flight"},
