@@ -281,3 +281,36 @@ def test_range_search_hit_lists_longer_than_one_sort_block():
         assert set(got_r.tolist()) == set(np.asarray(ref_r).tolist()) or len(set(got_r.tolist()) ^ set(np.asarray(ref_r).tolist())) <= 4
         assert np.all(np.diff(got_d) >= 0), "hits are not ascending"
     s.close()
+
+
+def test_searches_on_several_streams_share_one_handle():
+    """Device entry point on up to four streams at once (per-stream scratch lanes), then more streams
+    than lanes (a lane is recycled after its previous stream drained): every result equals the
+    single-stream result."""
+    import torch
+
+    n, dim, k = 200_000, 64, 10
+    s = _shard(dim, "cosine", capacity=n)
+    s.add_synthetic(5, 0, n, True)
+    Q = synthetic.queries(6, 24, dim)
+    ref_d, ref_r, ref_c = s.search(Q, k)
+    dev = torch.device("cuda", 0)
+    Qd = torch.from_numpy(Q).to(dev)
+    for n_streams in (2, 4, 6):
+        streams = [torch.cuda.Stream(dev) for _ in range(n_streams)]
+        outs = []
+        torch.cuda.synchronize()
+        for j in range(Q.shape[0]):
+            st = streams[j % n_streams]
+            d = torch.empty((1, k), dtype=torch.float32, device=dev)
+            r = torch.empty((1, k), dtype=torch.int64, device=dev)
+            c = torch.empty((1,), dtype=torch.int32, device=dev)
+            with torch.cuda.stream(st):
+                s.search_device(Qd[j:j + 1].data_ptr(), 1, k, d.data_ptr(), r.data_ptr(), c.data_ptr(), stream=st.cuda_stream)
+            outs.append((d, r, c))
+        torch.cuda.synchronize()
+        for j, (d, r, c) in enumerate(outs):
+            assert int(c.item()) == ref_c[j]
+            assert np.array_equal(r.cpu().numpy()[0], ref_r[j]), f"{n_streams} streams, query {j}"
+            assert np.array_equal(d.cpu().numpy()[0], ref_d[j])
+    s.close()
