@@ -381,8 +381,12 @@ refine_kernel(uint64_t* cand, uint32_t* cnt, float* thr, uint32_t* flags, uint32
     const uint32_t n = min(c, cap);
     if (n < kprime && c <= cap) return;  // fewer than k' candidates: keep all, threshold stays +inf (uniform per block)
     uint64_t* mine = cand + (size_t)q * cap;
-    for (uint32_t i = threadIdx.x; i < P; i += blockDim.x) a[i] = i < n ? mine[i] : KEY_SENTINEL;
-    bitonic_sort_smem(a, P);
+    // sort only as many slots as this query filled (typically k' + a few dozen of the `cap` slots)
+    uint32_t Pn = 2;
+    while (Pn < n) Pn <<= 1;
+    Pn = min(Pn, P);
+    for (uint32_t i = threadIdx.x; i < Pn; i += blockDim.x) a[i] = i < n ? mine[i] : KEY_SENTINEL;
+    bitonic_sort_smem(a, Pn);
     const uint32_t keep = min(n, kprime);
     for (uint32_t i = threadIdx.x; i < keep; i += blockDim.x) mine[i] = a[i];
     if (threadIdx.x == 0) {
