@@ -14,8 +14,9 @@ One JSON line on rank 0:
             CUDA-event timed, max over ranks).  Every query is its own search (own launch, own
             result); two are in flight on two streams so one query's scan fills the SMs the
             previous one's tail has left (roofline.one_query_in_flight has the strictly serial rate)
-  e2e       the same through the public host API (``GpuIndex.search`` at N=1,
-            ``ShardedIndex.search`` at N>1): host query in, host results out, copies inside
+  e2e       the same through the public host API: host query in, host results out, copies inside,
+            two requests in flight (``GpuIndex.search_async`` at N=1, ``ShardedIndex.search_async`` at
+            N>1); e2e.one_request_at_a_time is the plain synchronous ``search`` call
   roofline  scan kernel: algorithmic bytes per launch / average launch duration over the timed
             region (region device time / scan launches in it) vs the measured HBM copy peak;
             kernel_alone = CUDA events around every scan launch with one query in flight
@@ -257,13 +258,25 @@ def run_ours(a):
                 else:
                     last_out[0] = sharded.search_device(Qd[j:j + 1], k)
 
-    def step_e2e():
-        last = None
+    def step_e2e(depth=inflight):
+        # host query in, host results out, per query; `depth` requests in flight through the asynchronous
+        # public API (search_async / .result()), 1 = the plain synchronous search() call
+        last, pending = None, []
         for j in range(qps_step):
+            if depth <= 1:
+                if sharded is None:
+                    last = index.search(VectorDTO(values=Q[j], metadata={}), top_k=k, namespace=ns, metric=a.space)
+                else:
+                    last = sharded.search(Q[j:j + 1], k)
+                continue
             if sharded is None:
-                last = index.search(VectorDTO(values=Q[j], metadata={}), top_k=k, namespace=ns, metric=a.space)
+                pending.append(index.search_async(VectorDTO(values=Q[j], metadata={}), top_k=k, namespace=ns, metric=a.space))
             else:
-                last = sharded.search(Q[j:j + 1], k)
+                pending.append(sharded.search_async(Q[j:j + 1], k))
+            if len(pending) >= depth:
+                last = pending.pop(0).result()
+        for p in pending:
+            last = p.result()
         return last
 
     def timed(fn, n):
@@ -308,18 +321,22 @@ def run_ours(a):
     shard.set_timing(False)
 
     # ---- end-to-end timing through the public host API -----------------------------------------
-    for _ in range(a.warmup):
-        step_e2e()
-    barrier()
-    torch.cuda.synchronize()
-    t0 = time.perf_counter()
-    for _ in range(a.steps):
-        last = step_e2e()
-    torch.cuda.synchronize()
-    e2e_s = max_over_ranks(time.perf_counter() - t0)
-    barrier()
-    e2e_value = n_queries / e2e_s
-    assert last is not None and len(last) > 0
+    def time_e2e(depth):
+        for _ in range(a.warmup):
+            step_e2e(depth)
+        barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(a.steps):
+            out = step_e2e(depth)
+        torch.cuda.synchronize()
+        dt = max_over_ranks(time.perf_counter() - t0)
+        barrier()
+        return n_queries / dt, out
+
+    e2e_value, last = time_e2e(inflight)
+    e2e_sync_value, last_sync = time_e2e(1)
+    assert last is not None and len(last) > 0 and last_sync is not None and len(last_sync) > 0
 
     # ---- roofline of the dominant kernel ---------------------------------------------------------
     peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
@@ -364,8 +381,10 @@ def run_ours(a):
         "dtype": "f32", "data": "synthetic", "config": workload_config(a, n_gpus),
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": qps_step * a.dim * 4,
                 "d2h_bytes_per_step": qps_step * (k * 12 + 4),
-                "api": "GpuIndex.search(VectorDTO, top_k, namespace, metric)" if sharded is None
-                       else "ShardedIndex.search(host ndarray, k)"},
+                "api": ("GpuIndex.search_async(VectorDTO, top_k, namespace, metric).result()" if sharded is None
+                        else "ShardedIndex.search_async(host ndarray, k).result()") + f", {inflight} requests in flight",
+                "one_request_at_a_time": {"value": e2e_sync_value, "unit": UNIT,
+                                          "api": "GpuIndex.search(...)" if sharded is None else "ShardedIndex.search(...)"}},
         "roofline": roofline, "clocks": sampler.summary(), "gpu_launches": total_launches,
     }
     if rank == 0 and world == 1 and not a.no_cpu_baseline:

@@ -142,6 +142,17 @@ int mlv_index_search_device(mlv_index_t h, const float *queries_dev, uint32_t nq
                             int32_t *out_counts_dev, void *stream);
 
 /*
+ * Asynchronous host-buffer search: mlv_index_submit copies the queries, enqueues the search on a stream
+ * of its own and returns a ticket at once; mlv_index_collect blocks until that search is done and
+ * copies the results out (same buffers and meaning as mlv_index_search).  Up to four searches may
+ * be in flight per handle, each on its own scratch lane, so a server overlaps one request's copies,
+ * launch latency and tail with the next request's scan.  exchange != 0 makes it the collective
+ * mlv_index_search_exchange (every rank submits the same sequence of searches).
+ */
+int mlv_index_submit(mlv_index_t h, const float *queries, uint32_t nq, uint32_t k, int exchange, uint32_t *ticket);
+int mlv_index_collect(mlv_index_t h, uint32_t ticket, float *out_dists, int64_t *out_rows, int32_t *out_counts);
+
+/*
  * Range (radius) search: every live (and passing) row with d <= radius, ascending (d, row).
  * No reference code exists for it (README.md:121,215 only); semantics are defined by
  * oracle/exact.py::range_stream.  Each query owns max_hits slots of out_dists / out_rows;

@@ -96,6 +96,8 @@ SIGNATURES = {
     "mlv_index_search_exchange_device": (C.c_int, [_h, C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p,
                                                    C.c_void_p, C.c_void_p]),
     "mlv_index_search_exchange": (C.c_int, [_h, C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "mlv_index_submit": (C.c_int, [_h, C.c_void_p, C.c_uint32, C.c_uint32, C.c_int, _u32p]),
+    "mlv_index_collect": (C.c_int, [_h, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p]),
     "mlv_index_gemm_stats": (C.c_int, [_h, C.POINTER(GemmStats)]),
     "mlv_index_debug_gemm": (C.c_int, [_h, C.c_void_p, C.c_uint32, C.c_void_p]),
 }

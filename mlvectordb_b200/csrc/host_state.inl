@@ -25,6 +25,18 @@ struct Lane {
     DevBuf d_flist, d_fscratch;  // gather list built from a per-call filter bitmap
 };
 
+// One asynchronous host-buffer search in flight (mlv_index_submit / mlv_index_collect): its own
+// stream (hence its own scratch lane), pinned staging, device query / result blocks and a done event.
+constexpr int MLV_ASYNC_SLOTS = 4;
+struct AsyncSlot {
+    cudaStream_t stream = nullptr;
+    cudaEvent_t done = nullptr;
+    HostBuf stage;
+    DevBuf d_q, d_out;
+    uint32_t nq = 0, k = 0;
+    bool busy = false;
+};
+
 struct ScanCfg {
     int R, NQ, CW, PW;
     uint32_t T, S, stage_f4;
@@ -72,6 +84,8 @@ struct mlv_index {
     uint64_t compact_gen = 0;
     int tune_gather = -1;        // -1 auto, 0 never (stream + mask), 1 always when a filter is given
     HostBuf h_stage;
+    AsyncSlot slots[MLV_ASYNC_SLOTS];
+    uint32_t next_slot = 0;
     std::string err;
     bool timing = false;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> pending;

@@ -124,6 +124,14 @@ int mlv_index_destroy(mlv_index_t h) {
     for (Lane& l : h->lanes)
         for (DevBuf* b : {&l.d_q, &l.d_keys0, &l.d_keys1, &l.d_sched, &l.d_flist, &l.d_fscratch}) free_dev(*b);
     if (h->h_stage.p) cudaFreeHost(h->h_stage.p);
+    for (AsyncSlot& sl : h->slots) {
+        if (sl.stream) cudaStreamSynchronize(sl.stream);
+        if (sl.stage.p) cudaFreeHost(sl.stage.p);
+        free_dev(sl.d_q);
+        free_dev(sl.d_out);
+        if (sl.done) cudaEventDestroy(sl.done);
+        if (sl.stream) cudaStreamDestroy(sl.stream);
+    }
     for (auto* vec : {&h->pending, &h->gemm_pending})
         for (auto& pr : *vec) {
             cudaEventDestroy(pr.first);
@@ -569,6 +577,67 @@ int mlv_index_search(mlv_index_t h, const float* queries, uint32_t nq, uint32_t 
 int mlv_index_search_exchange(mlv_index_t h, const float* queries, uint32_t nq, uint32_t k, const uint32_t* filter_bitmap,
                               float* out_dists, int64_t* out_rows, int32_t* out_counts) {
     return search_host_common(h, queries, nq, k, filter_bitmap, out_dists, out_rows, out_counts, true);
+}
+
+int mlv_index_submit(mlv_index_t h, const float* queries, uint32_t nq, uint32_t k, int exchange, uint32_t* ticket) {
+    if (!h || !queries || !ticket || nq == 0 || k == 0) return fail(h, MLV_E_INVALID, "bad argument");
+    if (k > MLV_MAX_K) return fail(h, MLV_E_UNSUPPORTED, "k exceeds MLV_MAX_K");
+    DeviceGuard g(h->device);
+    int idx = -1;
+    for (int i = 0; i < MLV_ASYNC_SLOTS; i++) {
+        const int c = (int)((h->next_slot + i) % MLV_ASYNC_SLOTS);
+        if (!h->slots[c].busy) {
+            idx = c;
+            break;
+        }
+    }
+    if (idx < 0) return fail(h, MLV_E_UNSUPPORTED, "all asynchronous search slots are in flight: collect one first");
+    h->next_slot = (uint32_t)(idx + 1) % MLV_ASYNC_SLOTS;
+    AsyncSlot& sl = h->slots[idx];
+    if (!sl.stream) {
+        CK(h, cudaStreamCreateWithFlags(&sl.stream, cudaStreamNonBlocking));
+        CK(h, cudaEventCreateWithFlags(&sl.done, cudaEventDisableTiming));
+    }
+    const size_t qbytes = (size_t)nq * h->dim * 4;
+    const size_t nk = (size_t)nq * k;
+    const size_t out_bytes = nk * 12 + (size_t)nq * 4;
+    int rc;
+    if ((rc = ensure_host(h, sl.stage, std::max(qbytes, out_bytes))) != MLV_OK) return rc;
+    if ((rc = ensure_dev(h, sl.d_q, qbytes)) != MLV_OK) return rc;
+    if ((rc = ensure_dev(h, sl.d_out, out_bytes)) != MLV_OK) return rc;
+    memcpy(sl.stage.p, queries, qbytes);
+    CK(h, cudaMemcpyAsync(sl.d_q.p, sl.stage.p, qbytes, cudaMemcpyHostToDevice, sl.stream));
+    int64_t* d_rows_out = (int64_t*)sl.d_out.p;
+    float* d_dists_out = (float*)((char*)sl.d_out.p + nk * 8);
+    int32_t* d_counts_out = (int32_t*)((char*)sl.d_out.p + nk * 12);
+    if (exchange)
+        rc = mlv_index_search_exchange_device(h, (const float*)sl.d_q.p, nq, k, nullptr, d_dists_out, d_rows_out, d_counts_out, sl.stream);
+    else
+        rc = mlv_index_search_device(h, (const float*)sl.d_q.p, nq, k, nullptr, d_dists_out, d_rows_out, d_counts_out, sl.stream);
+    if (rc != MLV_OK) return rc;
+    // the queries have left the staging buffer (stream order), so the results may land in it
+    CK(h, cudaMemcpyAsync(sl.stage.p, sl.d_out.p, out_bytes, cudaMemcpyDeviceToHost, sl.stream));
+    CK(h, cudaEventRecord(sl.done, sl.stream));
+    sl.nq = nq;
+    sl.k = k;
+    sl.busy = true;
+    *ticket = (uint32_t)idx;
+    return MLV_OK;
+}
+
+int mlv_index_collect(mlv_index_t h, uint32_t ticket, float* out_dists, int64_t* out_rows, int32_t* out_counts) {
+    if (!h || ticket >= (uint32_t)MLV_ASYNC_SLOTS || !out_dists || !out_rows || !out_counts) return fail(h, MLV_E_INVALID, "bad argument");
+    AsyncSlot& sl = h->slots[ticket];
+    if (!sl.busy) return fail(h, MLV_E_INVALID, "no search in flight under this ticket");
+    DeviceGuard g(h->device);
+    sl.busy = false;
+    CK(h, cudaEventSynchronize(sl.done));
+    const size_t nk = (size_t)sl.nq * sl.k;
+    const char* hs = (const char*)sl.stage.p;
+    memcpy(out_rows, hs, nk * 8);
+    memcpy(out_dists, hs + nk * 8, nk * 4);
+    memcpy(out_counts, hs + nk * 12, (size_t)sl.nq * 4);
+    return MLV_OK;
 }
 
 int mlv_index_range_search_device(mlv_index_t h, const float* queries_dev, uint32_t nq, float radius,

@@ -82,6 +82,25 @@ class _Namespace:
         return UUID(bytes=self.ids[row].tobytes())
 
 
+class PendingResults:
+    """``GpuIndex.search_async`` in flight."""
+
+    def __init__(self, pending, ns, metric: str):
+        self._pending, self._ns, self._metric = pending, ns, metric
+
+    def result(self) -> List[SearchResult]:
+        if self._pending is None:
+            return []
+        dists, rows, counts = self._pending.result()
+        out = []
+        for row, dist in zip(rows[0, : counts[0]].tolist(), dists[0, : counts[0]].tolist()):
+            score = float(dist)
+            if self._metric == "cosine":
+                score = 1 - score
+            out.append(SearchResult(vector_id=self._ns.uuid_of(row), score=score))
+        return out
+
+
 class GpuIndex:
     def __init__(self, space: str = "l2", ef_construction: int = 200, M: int = 16, rebuild_threshold: float = 0.2,
                  device: int = 0, capacity: int = 0, auto_compact: bool = True):
@@ -205,6 +224,17 @@ class GpuIndex:
                 score = 1 - score
             results.append(SearchResult(vector_id=ns.uuid_of(row), score=score))
         return results
+
+    def search_async(self, query: VectorDTO, top_k: int, namespace: str, metric: str) -> "PendingResults":
+        """``search`` that returns at once; ``.result()`` gives the ``List[SearchResult]``.  A server that keeps
+        two requests in flight overlaps one request's copies / launch latency with the other's scan."""
+        ns = self._ns.get(namespace)
+        active = (ns.total - ns.deleted) if ns is not None else 0
+        k = min(int(top_k), active)
+        q = np.asarray(query.values, dtype=np.float32).reshape(-1)
+        if ns is None or k < 1 or q.shape[0] != ns.dim:
+            return PendingResults(None, None, metric)
+        return PendingResults(ns.shard.submit(q[None, :], k), ns, metric)
 
     def rebuild(self, source: Mapping[str, Iterable[VectorProtocol]], metric: str) -> None:
         """reference index.py:131-162: drop everything, re-add ``source`` with ``space=metric``."""

@@ -181,6 +181,14 @@ class DeviceShard:
             self._h, C.c_void_p(q_ptr), int(nq), int(k), C.c_void_p(filter_ptr) if filter_ptr else None,
             C.c_void_p(out_d_ptr), C.c_void_p(out_r_ptr), C.c_void_p(out_c_ptr), C.c_void_p(stream)))
 
+    def submit(self, queries: np.ndarray, k: int, exchange: bool = False) -> "PendingSearch":
+        """Start a search and return at once (``mlv_index_submit``); ``.result()`` blocks for the answer.
+        Up to four may be in flight per shard."""
+        q = np.ascontiguousarray(queries, dtype=np.float32).reshape(-1, self.dim)
+        ticket = C.c_uint32()
+        self._ck(self._lib.mlv_index_submit(self._h, q.ctypes.data, q.shape[0], int(k), int(bool(exchange)), C.byref(ticket)))
+        return PendingSearch(self, int(ticket.value), q.shape[0], int(k))
+
     def search_exchange(self, queries: np.ndarray, k: int):
         """Collective, host buffers: like ``search`` but the outputs hold the GLOBAL top-k of all row shards."""
         q = np.ascontiguousarray(queries, dtype=np.float32).reshape(-1, self.dim)
@@ -257,6 +265,25 @@ class DeviceShard:
         n = C.c_uint64()
         self._ck(self._lib.mlv_index_kernel_launches(self._h, C.byref(n)))
         return int(n.value)
+
+
+class PendingSearch:
+    """A search in flight (``DeviceShard.submit``)."""
+
+    def __init__(self, shard: "DeviceShard", ticket: int, nq: int, k: int):
+        self._shard, self._ticket, self._nq, self._k = shard, ticket, nq, k
+        self._out = None
+
+    def result(self):
+        """-> (dists f32 [nq,k], rows i64 [nq,k], counts i32 [nq]); blocks until the search is done."""
+        if self._out is None:
+            dists = np.empty((self._nq, self._k), dtype=np.float32)
+            rows = np.empty((self._nq, self._k), dtype=np.int64)
+            counts = np.empty(self._nq, dtype=np.int32)
+            s = self._shard
+            s._ck(s._lib.mlv_index_collect(s._h, self._ticket, dists.ctypes.data, rows.ctypes.data, counts.ctypes.data))
+            self._out = (dists, rows, counts)
+        return self._out
 
 
 class PreparedFilter:

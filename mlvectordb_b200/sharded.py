@@ -84,6 +84,14 @@ def merge_all_device(gd: torch.Tensor, gr: torch.Tensor):
     return out_d, out_r, out_c
 
 
+class _Done:
+    def __init__(self, out):
+        self._out = out
+
+    def result(self):
+        return self._out
+
+
 class ShardedIndex:
     """One namespace, rows sharded over the ranks of ``group``.  Every rank calls every method."""
 
@@ -204,6 +212,16 @@ class ShardedIndex:
         if (out[2] < 0).any():
             raise RuntimeError("sharded search: a peer rank did not post its candidates within the exchange timeout")
         return out
+
+    def search_async(self, queries: np.ndarray, k: int):
+        """Collective.  Start a search and return a handle whose ``.result()`` gives what ``search`` returns;
+        a caller that keeps two in flight hides each request's copies and launch latency behind the other's scan.
+        Needs the fused exchange path (k small, batch < EXCHANGE_MAX_NQ); otherwise the search runs synchronously."""
+        q = np.ascontiguousarray(queries, dtype=np.float32).reshape(-1, self.dim)
+        if self.shard is not None and q.shape[0] < self.EXCHANGE_MAX_NQ and (
+                self.world == 1 or (self.exchange is not None and self.shard.exchange_supported(k))):
+            return self.shard.submit(q, k, exchange=self.world > 1)
+        return _Done(self.search(q, k))
 
     # -- range search ------------------------------------------------------------------------
     def _device_local_range(self, queries: np.ndarray, radius: float):

@@ -230,3 +230,24 @@ def test_additive_surface_batch_filter_range_dimension():
     info = index.info("bulk")
     assert info["rows"] == 4000 and info["live"] == 3999 and info["tombstones"] == 1
     index.close()
+
+
+def test_search_async_equals_search():
+    """Additive: requests in flight through search_async return what search returns."""
+    rng = np.random.default_rng(3)
+    vecs = [Vector(values=v.tolist()) for v in rng.standard_normal((300, 24)).astype(np.float32)]
+    index = _index("cosine")
+    index.add(vecs, "ns")
+    queries = [_dto(v.values + 0.01) for v in vecs[:9]]
+    pending = [index.search_async(q, top_k=5, namespace="ns", metric="cosine") for q in queries[:4]]
+    got = [p.result() for p in pending]
+    for q in queries[4:]:                      # more requests than slots, two in flight at a time
+        pending = [index.search_async(q, top_k=5, namespace="ns", metric="cosine"),
+                   index.search_async(queries[0], top_k=5, namespace="ns", metric="cosine")]
+        got.append(pending[0].result())
+        pending[1].result()
+    for q, res in zip(queries, got):
+        want = index.search(q, top_k=5, namespace="ns", metric="cosine")
+        assert [(r.vector_id, r.score) for r in res] == [(r.vector_id, r.score) for r in want]
+    assert index.search_async(_dto([1.0, 2.0]), 5, "ns", "cosine").result() == []          # wrong dimension
+    assert index.search_async(queries[0], 5, "missing", "cosine").result() == []
