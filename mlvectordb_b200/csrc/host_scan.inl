@@ -165,7 +165,8 @@ Lane* lane_for(mlv_index* h, cudaStream_t st) {
             lru = &l;
         }
     }
-    if (lru->used) cudaStreamSynchronize(lru->stream);
+    if (lru->used && cudaStreamSynchronize(lru->stream) != cudaSuccess)
+        cudaGetLastError();  // the previous owner destroyed its stream: nothing of it can still be running
     lru->used = true;
     lru->stream = st;
     lru->last_use = ++h->lane_clock;
