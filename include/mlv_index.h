@@ -218,7 +218,7 @@ int mlv_index_set_filter(mlv_index_t h, mlv_filter_t f);
  * last CTA folds the block lists, stores its k best into every peer's buffer, waits for the
  * peers' lists (release/acquire flags at system scope) and merges.  Collective: every rank must
  * make the same sequence of calls.  Supported when mlv_index_exchange_supported(h, k) != 0
- * (k <= 13 on a 148-SM part); larger k uses the all-gather + mlv_merge_topk path.
+ * (k <= 55 on a 148-SM part); larger k uses the all-gather + mlv_merge_topk path.
  * A peer that does not arrive within 20 s raises an error flag (mlv_exchange_check) instead of
  * hanging the GPU.
  */

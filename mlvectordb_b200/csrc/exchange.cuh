@@ -16,7 +16,7 @@ namespace mlv {
 
 constexpr uint32_t XCHG_MAX_WORLD = 16;
 constexpr uint32_t XCHG_MAX_NQ = 8;   // queries per scan launch
-constexpr uint32_t XCHG_MAX_K = 16;   // the fused exchange handles k <= 16
+constexpr uint32_t XCHG_MAX_K = 64;   // the fused exchange handles k <= 64 (55 in practice: 148 SMs * k <= 8192 keys)
 constexpr uint32_t XCHG_SLOT_KEYS = XCHG_MAX_WORLD * XCHG_MAX_NQ * XCHG_MAX_K;  // u64 keys per parity slot
 constexpr uint32_t XCHG_SLOTS = 4;
 // buffer layout (u64 words): keys[XCHG_SLOTS][XCHG_MAX_WORLD][XCHG_MAX_NQ][XCHG_MAX_K], flags[XCHG_SLOTS][XCHG_MAX_WORLD]

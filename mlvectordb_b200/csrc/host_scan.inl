@@ -247,11 +247,14 @@ void fill_sched(mlv_index* h, Lane* ln, ScanParams& p) {
     p.tile_batch = batch;
 }
 
+// slots of the last CTA's candidate array for a fused final select
+uint32_t fused_cap(const ScanCfg& c, uint32_t k) { return pow2_ceil(std::max<uint32_t>((uint32_t)c.grid * k, 1024)); }
+
 // can the last CTA fold the whole grid's lists (and hold its scratch in the idle ring)?
 bool fused_ok(const mlv_index* h, const ScanCfg& c, uint32_t k) {
     if (!h->tune_dynamic || !h->tune_fused) return false;
     if ((uint64_t)c.grid * k > SCAN_FUSED_MAX_KEYS || (uint64_t)c.CW * k > 1024) return false;
-    return (size_t)c.S * c.stage_f4 * 16 >= ((size_t)SCAN_FUSED_MAX_KEYS + (size_t)c.NQ * k) * 8;
+    return (size_t)c.S * c.stage_f4 * 16 >= ((size_t)fused_cap(c, k) + (size_t)c.NQ * k) * 8;
 }
 
 // the exchange path must take the same decision on every rank, whatever its shard's grid is
@@ -315,6 +318,7 @@ int search_prepared(mlv_index* h, const float* qprep, uint32_t nq, uint32_t k, c
     p.evict_first = c.evict_first;
     fill_sched(h, ln, p);
     p.fused = fused ? 1 : 0;
+    p.fused_cap = fused_cap(c, k);
     p.row_base = h->row_base;
     if (exchange) fill_exchange(h, p.xchg);
     if (h->tune_timeline) {

@@ -28,7 +28,7 @@ constexpr int SCAN_MAX_CW = 16;                          // consumer warps per C
 constexpr int SCAN_MAX_PW = 4;                           // producer warps (1 unless gathering short rows)
 constexpr int SCAN_MAX_THREADS = (SCAN_MAX_CW + SCAN_MAX_PW) * 32;  // 640 -> ptxas may use up to 102 registers
 
-constexpr uint32_t SCAN_FUSED_MAX_KEYS = 2048;  // keys the last CTA folds (gridDim.x * k)
+constexpr uint32_t SCAN_FUSED_MAX_KEYS = 8192;  // keys the last CTA folds (gridDim.x * k): k <= 55 on 148 SMs
 
 struct ScanParams {
     const float4* rows;     // [n_rows, ld4]
@@ -63,6 +63,7 @@ struct ScanParams {
     // fused final select (top-k mode, needs sched, gridDim.x * k <= SCAN_FUSED_MAX_KEYS): the last
     // CTA to finish folds the grid's lists into the final ascending top-k instead of select_kernel
     int fused;
+    uint32_t fused_cap;   // slots of the last CTA's candidate array: power of two >= max(gridDim.x * k, 1024)
     float* out_dists;     // [nq_valid][k]
     int64_t* out_rows;    // [nq_valid][k]
     int32_t* out_counts;  // [nq_valid]
@@ -429,9 +430,9 @@ __global__ void __launch_bounds__(SCAN_MAX_THREADS, 1) scan_kernel(const ScanPar
     if (s_ticket != gridDim.x - 1) return;
     __threadfence();
     if (!RANGE && p.fused) {
-        // The ring is idle now: reuse it.  cand[SCAN_FUSED_MAX_KEYS] | top[XCHG_MAX_NQ][XCHG_MAX_K or k]
+        // The ring is idle now: reuse it.  cand[fused_cap] | top[nq_valid][k]
         uint64_t* cand = reinterpret_cast<uint64_t*>(ring);
-        uint64_t* top = cand + SCAN_FUSED_MAX_KEYS;  // [nq_valid][k]
+        uint64_t* top = cand + p.fused_cap;
         const uint32_t n_lists = gridDim.x, n = n_lists * k;
         for (uint32_t qi = 0; qi < p.nq_valid; qi++) {
             const uint64_t* keys = p.out_keys + (size_t)qi * n_lists * k;
@@ -451,16 +452,42 @@ __global__ void __launch_bounds__(SCAN_MAX_THREADS, 1) scan_kernel(const ScanPar
             }
             named_bar_sync(1, CW * 32);
             const uint32_t m = s_m;
-            for (uint32_t e = tid; e < m; e += nthr) {
-                const uint64_t key = cand[e];
-                uint32_t rank = 0;
-                for (uint32_t i = 0; i < m; i++) {
-                    const uint64_t o = cand[i];
-                    rank += (o < key) || (o == key && i < e);
+            if (m <= 512) {
+                // few survivors: rank by counting
+                for (uint32_t e = tid; e < m; e += nthr) {
+                    const uint64_t key = cand[e];
+                    uint32_t rank = 0;
+                    for (uint32_t i = 0; i < m; i++) {
+                        const uint64_t o = cand[i];
+                        rank += (o < key) || (o == key && i < e);
+                    }
+                    if (rank < k) top[qi * k + rank] = key;
                 }
-                if (rank < k) top[qi * k + rank] = key;
+                named_bar_sync(1, CW * 32);
+            } else {
+                // many survivors (larger k): bitonic network over the consumer threads
+                uint32_t P = 1024;
+                while (P < m) P <<= 1;
+                for (uint32_t i = m + tid; i < P; i += nthr) cand[i] = KEY_SENTINEL;
+                for (uint32_t size = 2; size <= P; size <<= 1) {
+                    for (uint32_t stride = size >> 1; stride > 0; stride >>= 1) {
+                        named_bar_sync(1, CW * 32);
+                        for (uint32_t t = tid; t < (P >> 1); t += nthr) {
+                            const uint32_t i = 2 * t - (t & (stride - 1));
+                            const uint32_t j = i + stride;
+                            const bool up = (i & size) == 0;
+                            const uint64_t a = cand[i], b = cand[j];
+                            if ((a > b) == up) {
+                                cand[i] = b;
+                                cand[j] = a;
+                            }
+                        }
+                    }
+                }
+                named_bar_sync(1, CW * 32);
+                for (uint32_t j = tid; j < k; j += nthr) top[qi * k + j] = cand[j];
+                named_bar_sync(1, CW * 32);
             }
-            named_bar_sync(1, CW * 32);
         }
         const ExchangeView& x = p.xchg;
         if (x.world <= 1) {

@@ -2,7 +2,7 @@
 
 usage: _nccl_worker.py RANK WORLD PORT
 Every rank holds a row shard (``ShardedIndex``); rank 0 additionally holds the whole matrix in one
-``DeviceShard`` and checks that the sharded results -- fused peer-memory exchange for k <= 13,
+``DeviceShard`` and checks that the sharded results -- fused peer-memory exchange for k <= 55,
 NCCL all-gather + merge kernel for larger k, tensor-core path for batches -- are bit-identical to
 the unsharded search.
 """
@@ -81,6 +81,7 @@ def main():
     check(200_003, 64, "l2", 10, 19, True)                 # several launch groups per call (nq > 8)
     check(50_000, 96, "ip", 13, 3, True, delete_every=3)   # tombstones
     check(1, 32, "l2", 4, 2, True)                         # rank 1.. hold nothing: exchange_only_kernel
+    check(200_003, 64, "l2", 40, 3, True)                  # larger k: bitonic final select in the last CTA
     check(200_003, 64, "cosine", 100, 4, False)            # k too large for the fused exchange: NCCL path
     check(120_000, 128, "l2", 10, 300, True)               # large batch: local tensor-core path + NCCL merge
     dist.barrier()
