@@ -285,7 +285,9 @@ int search_prepared(mlv_index* h, const float* qprep, uint32_t nq, uint32_t k, c
     ScanCfg c;
     if ((rc = choose_cfg(h, nq, k, false, &c, fp.gather != nullptr)) != MLV_OK) return rc;
     if ((rc = ensure_sched(h, ln)) != MLV_OK) return rc;
-    const bool fused = fused_ok(h, c, k);
+    // on one GPU the single-CTA sort of more than ~4096 keys costs as much as the select launch it saves;
+    // across GPUs it still replaces two all-gathers and a merge launch
+    const bool fused = fused_ok(h, c, k) && (exchange || (uint64_t)c.grid * k <= 4096);
     if (exchange && !fused) return fail(h, MLV_E_UNSUPPORTED, "exchange search needs the fused final select");
     const uint32_t F = SELECT_MAX_P / k;  // lists one select CTA can fold (>= 8)
     // bound the candidate scratch: chunk * grid * k keys
