@@ -274,6 +274,27 @@ void fill_exchange(mlv_index* h, ExchangeView& x) {
     x.error = e->d_error;
 }
 
+// What every scan launch of one search shares: the matrix, the ring shape, masks / gather list, scheduler.
+ScanParams scan_params(mlv_index* h, const ScanCfg& c, const FilterPlan& fp, Lane* ln, uint32_t k) {
+    ScanParams p{};
+    p.rows = reinterpret_cast<const float4*>(h->d_rows);
+    p.n_rows = (uint32_t)h->rows;
+    p.ld4 = h->ld / 4;
+    p.tile_rows = c.T;
+    p.n_tiles = (uint32_t)((h->rows + c.T - 1) / c.T);
+    p.stages = c.S;
+    p.producer_warps = (uint32_t)c.PW;
+    p.stage_f4 = c.stage_f4;
+    p.k = k;
+    p.live = h->n_deleted ? h->d_live : nullptr;
+    p.filter = fp.bitmap;
+    p.gather = fp.gather;
+    p.n_rows_dev = fp.n_rows_dev;
+    p.evict_first = c.evict_first;
+    fill_sched(h, ln, p);
+    return p;
+}
+
 // qprep: prepared queries [nq, ld] in device memory; all output pointers in device memory.
 // exchange: merge with the other ranks' results over peer memory (caller checked exchange_ok).
 int search_prepared(mlv_index* h, const float* qprep, uint32_t nq, uint32_t k, const uint32_t* filter_dev, float* out_d,
@@ -303,22 +324,7 @@ int search_prepared(mlv_index* h, const float* qprep, uint32_t nq, uint32_t k, c
     }
     CK(h, ensure_select_attrs(h->device));
 
-    ScanParams p{};
-    p.rows = reinterpret_cast<const float4*>(h->d_rows);
-    p.n_rows = (uint32_t)h->rows;
-    p.ld4 = h->ld / 4;
-    p.tile_rows = c.T;
-    p.n_tiles = (uint32_t)((h->rows + c.T - 1) / c.T);
-    p.stages = c.S;
-    p.producer_warps = (uint32_t)c.PW;
-    p.stage_f4 = c.stage_f4;
-    p.k = k;
-    p.live = h->n_deleted ? h->d_live : nullptr;
-    p.filter = fp.bitmap;
-    p.gather = fp.gather;
-    p.n_rows_dev = fp.n_rows_dev;
-    p.evict_first = c.evict_first;
-    fill_sched(h, ln, p);
+    ScanParams p = scan_params(h, c, fp, ln, k);
     p.fused = fused ? 1 : 0;
     p.fused_cap = fused_cap(c, k);
     p.row_base = h->row_base;

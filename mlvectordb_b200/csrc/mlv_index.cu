@@ -663,25 +663,10 @@ int mlv_index_range_search_device(mlv_index_t h, const float* queries_dev, uint3
     if ((rc = plan_filter(h, ln, filter_bitmap_dev, st, &fp)) != MLV_OK) return rc;
     ScanCfg c;
     if ((rc = choose_cfg(h, 1, 1, true, &c, fp.gather != nullptr)) != MLV_OK) return rc;
-    ScanParams p{};
-    p.rows = reinterpret_cast<const float4*>(h->d_rows);
-    p.n_rows = (uint32_t)h->rows;
-    p.ld4 = h->ld / 4;
-    p.tile_rows = c.T;
-    p.n_tiles = (uint32_t)((h->rows + c.T - 1) / c.T);
-    p.stages = c.S;
-    p.producer_warps = (uint32_t)c.PW;
-    p.stage_f4 = c.stage_f4;
-    p.k = 1;
-    p.live = h->n_deleted ? h->d_live : nullptr;
-    p.filter = fp.bitmap;
-    p.gather = fp.gather;
-    p.n_rows_dev = fp.n_rows_dev;
-    p.evict_first = c.evict_first;
+    if ((rc = ensure_sched(h, ln)) != MLV_OK) return rc;
+    ScanParams p = scan_params(h, c, fp, ln, 1);
     p.radius = radius;
     p.max_hits = max_hits;
-    if ((rc = ensure_sched(h, ln)) != MLV_OK) return rc;
-    fill_sched(h, ln, p);
     for (uint32_t q = 0; q < nq; q++) {
         p.queries = reinterpret_cast<const float4*>((const float*)ln->d_q.p + (size_t)q * h->ld);
         p.nq_valid = 1;
