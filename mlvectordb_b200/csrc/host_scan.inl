@@ -9,19 +9,30 @@ namespace {
 // are latency-bound in the consumers, so they get more warps, more rows per warp step and larger
 // stages; a gathering producer is bound by its copy issue rate (~80 cycles per row copy per warp),
 // so short rows get more producer warps.
+// slots of one (warp, query) candidate list: k itself up to 32 (replace-max insertion), else an append
+// buffer of the next power of two >= 2k (scan_kernel.cuh, ScanParams::list_cap)
+uint32_t scan_list_cap(uint32_t k) {
+    if (k <= 32) return k;
+    uint32_t p = 64;
+    while (p < 2 * k) p <<= 1;
+    return p;
+}
+
 int choose_cfg(mlv_index* h, uint32_t nq, uint32_t k, bool range, ScanCfg* c, bool gather = false) {
     const uint32_t ld4 = h->ld / 4;
     const size_t rowbytes = (size_t)h->ld * 4;
+    const uint32_t lcap = scan_list_cap(k);
     int CW = h->tune_cw > 0 ? std::min(h->tune_cw, SCAN_MAX_CW) : (ld4 <= 64 ? 16 : 8);
+    if (!range && k > 512) CW = std::min(CW, 4);  // 2048-slot buffers: 4 warps keep the lists at 64 KB
     int R = h->tune_r ? h->tune_r : (ld4 <= 256 ? 4 : (ld4 <= 512 ? 2 : 1));
     if (R != 1 && R != 2 && R != 4) R = 1;
     int NQ = 1;
     if (!range) {
         while (NQ < 8 && (uint32_t)NQ < nq) NQ <<= 1;
-        while (NQ > 1 && ((size_t)NQ * k * CW * 8 > 65536 || R * NQ > 32)) NQ >>= 1;
+        while (NQ > 1 && ((size_t)NQ * lcap * CW * 8 > 65536 || R * NQ > 32)) NQ >>= 1;
     }
     const int max_stages = std::min(std::max(h->tune_max_stages, 2), 16);
-    const size_t fixed = (size_t)NQ * rowbytes + (range ? 0 : (size_t)CW * NQ * k * 8) + (size_t)max_stages * 24 + 256;
+    const size_t fixed = (size_t)NQ * rowbytes + (range ? 0 : (size_t)CW * NQ * lcap * 8) + (size_t)max_stages * 24 + 256;
     if (fixed + 2 * rowbytes > h->smem_optin)
         return fail(h, MLV_E_UNSUPPORTED, "dimension too large for the shared-memory ring of this build");
     const size_t avail = h->smem_optin - fixed;
@@ -61,7 +72,7 @@ int choose_cfg(mlv_index* h, uint32_t nq, uint32_t k, bool range, ScanCfg* c, bo
     c->T = (uint32_t)T;
     c->S = S;
     c->stage_f4 = (uint32_t)(stage / 16);
-    c->smem = (size_t)S * stage + (size_t)NQ * rowbytes + (range ? 0 : (size_t)CW * NQ * k * 8) + (size_t)S * 24;
+    c->smem = (size_t)S * stage + (size_t)NQ * rowbytes + (range ? 0 : (size_t)CW * NQ * lcap * 8) + (size_t)S * 24;
     const uint64_t n_tiles = (h->rows + T - 1) / T;
     const int ctas = h->tune_ctas > 0 ? h->tune_ctas : h->sm_count;
     c->grid = (int)std::min<uint64_t>(n_tiles, (uint64_t)ctas);
@@ -253,7 +264,7 @@ uint32_t fused_cap(const ScanCfg& c, uint32_t k) { return pow2_ceil(std::max<uin
 // can the last CTA fold the whole grid's lists (and hold its scratch in the idle ring)?
 bool fused_ok(const mlv_index* h, const ScanCfg& c, uint32_t k) {
     if (!h->tune_dynamic || !h->tune_fused) return false;
-    if ((uint64_t)c.grid * k > SCAN_FUSED_MAX_KEYS || (uint64_t)c.CW * k > 1024) return false;
+    if ((uint64_t)c.grid * k > SCAN_FUSED_MAX_KEYS) return false;
     return (size_t)c.S * c.stage_f4 * 16 >= ((size_t)fused_cap(c, k) + (size_t)c.NQ * k) * 8;
 }
 
@@ -286,6 +297,7 @@ ScanParams scan_params(mlv_index* h, const ScanCfg& c, const FilterPlan& fp, Lan
     p.producer_warps = (uint32_t)c.PW;
     p.stage_f4 = c.stage_f4;
     p.k = k;
+    p.list_cap = scan_list_cap(k);
     p.live = h->n_deleted ? h->d_live : nullptr;
     p.filter = fp.bitmap;
     p.gather = fp.gather;

@@ -12,7 +12,8 @@
 //   * a consumer warp scores R rows x NQ queries per step: lane l accumulates the float4
 //     columns l, l+32, ... of each row against the queries held in shared memory, then a
 //     transposing butterfly leaves each (row, query) sum in one lane class
-//   * per-warp, per-query candidate lists (unsorted, k entries, shared memory) guarded by a
+//   * per-warp, per-query candidate lists in shared memory (k <= 32: k unsorted entries with replace-
+//     the-maximum insertion; larger k: an append buffer compacted by a warp-local bitonic sort) guarded by a
 //     register threshold: a row costs one compare unless it beats the current k-th best
 //   * at the end the block folds its warps' lists into one list per query and writes
 //     k keys per (query, block); select_kernel.cuh merges the blocks' lists.
@@ -42,6 +43,12 @@ struct ScanParams {
     const float4* queries;  // [nq_valid, ld4] device, zero padded, normalised for cosine
     uint32_t nq_valid;      // <= NQ
     uint32_t k;
+    // slots of one (warp, query) candidate list.  == k: unsorted list, replace-the-maximum insertion
+    // (k <= 32, one shared-memory pass per insertion).  > k (a power of two >= 2k): append buffer --
+    // rows that beat the threshold are appended, and when fewer than 32 free slots remain the warp
+    // sorts the buffer, keeps the k best and tightens the threshold (amortised O(log^2) per insertion
+    // instead of two passes over k entries).
+    uint32_t list_cap;
     const uint32_t* live;    // tombstone bitmap (bit set = live) or nullptr when nothing is deleted
     const uint32_t* filter;  // caller's filter bitmap or nullptr
     // gather mode (selective filters): `gather` lists the passing-and-live rows ascending; n_rows is
@@ -143,6 +150,43 @@ __device__ __forceinline__ uint64_t list_replace_max(uint64_t* list, uint32_t k,
     return warp_max_u64(m);
 }
 
+// Whole warp: order list[0..n) ascending inside its `cap` (power of two) slots, pad with sentinels.
+__device__ __forceinline__ void warp_sort_list(uint64_t* list, uint32_t n, uint32_t cap, int lane) {
+    uint32_t P = 32;
+    while (P < n) P <<= 1;  // n <= cap, cap is a power of two >= 64
+    for (uint32_t i = n + lane; i < cap; i += 32) list[i] = KEY_SENTINEL;
+    for (uint32_t size = 2; size <= P; size <<= 1) {
+        for (uint32_t stride = size >> 1; stride > 0; stride >>= 1) {
+            __syncwarp();
+            for (uint32_t t = lane; t < (P >> 1); t += 32) {
+                const uint32_t i = 2 * t - (t & (stride - 1));
+                const uint32_t j = i + stride;
+                const bool up = (i & size) == 0;
+                const uint64_t a = list[i], b = list[j];
+                if ((a > b) == up) {
+                    list[i] = b;
+                    list[j] = a;
+                }
+            }
+        }
+    }
+    __syncwarp();
+}
+
+// number of keys of the ascending list[0..k) that are < key (strict) or <= key (!strict)
+__device__ __forceinline__ uint32_t sorted_count_below(const uint64_t* list, uint32_t k, uint64_t key, bool strict) {
+    uint32_t lo = 0, hi = k;
+    while (lo < hi) {
+        const uint32_t mid = (lo + hi) >> 1;
+        const uint64_t v = list[mid];
+        if (strict ? (v < key) : (v <= key))
+            lo = mid + 1;
+        else
+            hi = mid;
+    }
+    return lo;
+}
+
 template <int METRIC, int NQ, int R, bool RANGE>
 __global__ void __launch_bounds__(SCAN_MAX_THREADS, 1) scan_kernel(const ScanParams p) {
     constexpr int V = R * NQ;
@@ -162,8 +206,10 @@ __global__ void __launch_bounds__(SCAN_MAX_THREADS, 1) scan_kernel(const ScanPar
 
     float4* ring = reinterpret_cast<float4*>(smem);
     float4* qs = ring + (size_t)S * p.stage_f4;                                   // [NQ][ld4]
-    uint64_t* lists = reinterpret_cast<uint64_t*>(qs + (size_t)NQ * ld4);         // [CW][NQ][k]
-    uint64_t* full = lists + (RANGE ? 0 : (size_t)CW * NQ * k);                   // [S]
+    const uint32_t lcap = p.list_cap;             // slots per (warp, query) list
+    const bool buffered = lcap > k;               // append buffer + compaction instead of replace-max
+    uint64_t* lists = reinterpret_cast<uint64_t*>(qs + (size_t)NQ * ld4);         // [CW][NQ][lcap]
+    uint64_t* full = lists + (RANGE ? 0 : (size_t)CW * NQ * lcap);                // [S]
     uint64_t* empty = full + S;                                                   // [S]
     StageMeta* meta = reinterpret_cast<StageMeta*>(empty + S);                    // [S]
 
@@ -181,7 +227,7 @@ __global__ void __launch_bounds__(SCAN_MAX_THREADS, 1) scan_kernel(const ScanPar
         qs[i] = p.queries[(size_t)src * ld4 + j];
     }
     if (!RANGE)
-        for (uint32_t i = tid; i < (uint32_t)CW * NQ * k; i += blockDim.x) lists[i] = KEY_SENTINEL;
+        for (uint32_t i = tid; i < (uint32_t)CW * NQ * lcap; i += blockDim.x) lists[i] = KEY_SENTINEL;
     __syncthreads();
     if (p.timeline && tid == 0) p.timeline[blockIdx.x * 4 + 0] = global_timer_ns();
 
@@ -270,7 +316,8 @@ __global__ void __launch_bounds__(SCAN_MAX_THREADS, 1) scan_kernel(const ScanPar
     const bool rep = (lane & (32 / V - 1)) == 0;  // one representative lane per slot
     const bool q_ok = (uint32_t)my_q < p.nq_valid;
     uint64_t thr = KEY_SENTINEL;                  // current k-th best of list (warp, my_q)
-    uint64_t* my_lists = lists + (size_t)warp * NQ * k;
+    uint64_t* my_lists = lists + (size_t)warp * NQ * lcap;
+    uint32_t cnt = 0;                             // buffered mode: entries in list (warp, my_q), same in every lane of a slot class
 
     uint32_t stage = 0, phase = 0, seq = 0;
     uint32_t rot = 0;       // == seq % CW without the division
@@ -342,15 +389,40 @@ __global__ void __launch_bounds__(SCAN_MAX_THREADS, 1) scan_kernel(const ScanPar
                 }
             } else {
                 unsigned m = __ballot_sync(0xffffffffu, ok && key < thr);
-                while (m) {
-                    const int src = __ffs(m) - 1;
-                    m &= m - 1;
-                    const uint64_t ckey = shfl_u64(key, src);
-                    const uint64_t cthr = shfl_u64(thr, src);
-                    const int cq = __shfl_sync(0xffffffffu, my_q, src);
-                    if (ckey < cthr) {
-                        const uint64_t nthr = list_replace_max(my_lists + (size_t)cq * k, k, ckey, cthr, lane);
-                        if (my_q == cq) thr = nthr;
+                if (!buffered) {
+                    while (m) {
+                        const int src = __ffs(m) - 1;
+                        m &= m - 1;
+                        const uint64_t ckey = shfl_u64(key, src);
+                        const uint64_t cthr = shfl_u64(thr, src);
+                        const int cq = __shfl_sync(0xffffffffu, my_q, src);
+                        if (ckey < cthr) {
+                            const uint64_t nthr = list_replace_max(my_lists + (size_t)cq * k, k, ckey, cthr, lane);
+                            if (my_q == cq) thr = nthr;
+                        }
+                    }
+                } else {
+                    while (m) {
+                        // all candidates of one query in this step are appended together
+                        const int src = __ffs(m) - 1;
+                        const int cq = __shfl_sync(0xffffffffu, my_q, src);
+                        const unsigned mq = __ballot_sync(0xffffffffu, ((m >> lane) & 1u) && my_q == cq);
+                        m &= ~mq;
+                        const uint32_t base = __shfl_sync(0xffffffffu, cnt, src);
+                        uint64_t* list = my_lists + (size_t)cq * lcap;
+                        if ((mq >> lane) & 1u) list[base + __popc(mq & ((1u << lane) - 1u))] = key;
+                        uint32_t ncnt = base + __popc(mq);
+                        uint64_t nthr = shfl_u64(thr, src);
+                        if (ncnt + 32 > lcap) {  // fewer than a step's worth of free slots: keep the k best
+                            __syncwarp();
+                            warp_sort_list(list, ncnt, lcap, lane);
+                            ncnt = min(ncnt, k);
+                            nthr = list[k - 1];  // sentinel while fewer than k rows were seen
+                        }
+                        if (my_q == cq) {
+                            cnt = ncnt;
+                            thr = nthr;
+                        }
                     }
                 }
             }
@@ -365,52 +437,40 @@ __global__ void __launch_bounds__(SCAN_MAX_THREADS, 1) scan_kernel(const ScanPar
     const uint32_t nthr = (uint32_t)CW * 32u;  // consumer threads (the producer warps have left)
     if (!RANGE) {
         // --------------------------------------------- fold the CW warp lists into one per query
+        if (buffered) {
+            // last compaction: every list of this warp ascending, k slots valid-or-sentinel
+            for (uint32_t qi = 0; qi < (uint32_t)NQ && qi < p.nq_valid; qi++) {
+                const unsigned owners = __ballot_sync(0xffffffffu, my_q == (int)qi);
+                const uint32_t n = __shfl_sync(0xffffffffu, cnt, __ffs(owners) - 1);
+                warp_sort_list(my_lists + (size_t)qi * lcap, n, lcap, lane);
+            }
+        }
         named_bar_sync(1, CW * 32);
         const uint32_t n_in = (uint32_t)CW * k;
-        if (n_in <= 1024) {
-            // rank by counting: the block's k best come out sorted ascending; sentinels tie-break by index
-            for (uint32_t qi = 0; qi < p.nq_valid; qi++) {
-                uint64_t* out = p.out_keys + ((size_t)qi * gridDim.x + blockIdx.x) * k;
-                for (uint32_t e = tid; e < n_in; e += nthr) {
-                    const uint32_t w = e / k, j = e - w * k;
-                    const uint64_t key = lists[((size_t)w * NQ + qi) * k + j];
-                    uint32_t rank = 0;
+        for (uint32_t qi = 0; qi < p.nq_valid; qi++) {
+            uint64_t* out = p.out_keys + ((size_t)qi * gridDim.x + blockIdx.x) * k;
+            for (uint32_t e = tid; e < n_in; e += nthr) {
+                const uint32_t w = e / k, j = e - w * k;
+                const uint64_t key = lists[((size_t)w * NQ + qi) * lcap + j];
+                uint32_t rank;
+                if (buffered) {
+                    // CW ascending lists: rank = own position + keys below it in the other lists (binary
+                    // search); equal keys (sentinels only) are ordered by list, then position
+                    rank = j;
+                    for (uint32_t w2 = 0; w2 < (uint32_t)CW; w2++)
+                        if (w2 != w) rank += sorted_count_below(lists + ((size_t)w2 * NQ + qi) * lcap, k, key, w2 > w);
+                } else {
+                    // unsorted lists of k <= 32 keys: rank by counting
+                    rank = 0;
                     for (uint32_t w2 = 0; w2 < (uint32_t)CW; w2++) {
-                        const uint64_t* l2 = lists + ((size_t)w2 * NQ + qi) * k;
+                        const uint64_t* l2 = lists + ((size_t)w2 * NQ + qi) * lcap;
                         for (uint32_t j2 = 0; j2 < k; j2++) {
                             const uint64_t o = l2[j2];
                             rank += (o < key) || (o == key && (w2 * k + j2) < e);
                         }
                     }
-                    if (rank < k) out[rank] = key;
                 }
-            }
-        } else {
-            for (int qi = warp; qi < NQ && (uint32_t)qi < p.nq_valid; qi += CW) {
-                uint64_t* home = lists + ((size_t)warp * NQ + qi) * k;
-                uint64_t m = 0;
-                for (uint32_t j = lane; j < k; j += 32) {
-                    uint64_t v = home[j];
-                    m = v > m ? v : m;
-                }
-                uint64_t hthr = warp_max_u64(m);
-                for (int ow = 0; ow < CW; ow++) {
-                    if (ow == warp) continue;
-                    const uint64_t* other = lists + ((size_t)ow * NQ + qi) * k;
-                    for (uint32_t j0 = 0; j0 < k; j0 += 32) {
-                        const uint64_t key = (j0 + lane < k) ? other[j0 + lane] : KEY_SENTINEL;
-                        unsigned mm = __ballot_sync(0xffffffffu, key < hthr);
-                        while (mm) {
-                            const int src = __ffs(mm) - 1;
-                            mm &= mm - 1;
-                            const uint64_t ckey = shfl_u64(key, src);
-                            if (ckey < hthr) hthr = list_replace_max(home, k, ckey, hthr, lane);
-                        }
-                    }
-                }
-                __syncwarp();
-                uint64_t* out = p.out_keys + ((size_t)qi * gridDim.x + blockIdx.x) * k;
-                for (uint32_t j = lane; j < k; j += 32) out[j] = home[j];
+                if (rank < k) out[rank] = key;  // the block's k best, ascending
             }
         }
     }
