@@ -151,3 +151,16 @@ def test_large_batch_on_device_generated_rows():
     assert got[1][5, 0] == 1234
     assert fallbacks <= 10
     s.close()
+
+
+def test_largest_k_on_the_batch_path():
+    """k = 1000 (the REST bound): k' = 1280 candidates per query, 8192-slot buffers, short growth factor."""
+    n, dim, nq, k = 40_000, 48, 24, 1000
+    X = synthetic.rows(71, 0, n, dim)
+    Q = synthetic.queries(71, nq, dim)
+    s = _shard(dim, "l2")
+    s.add(X)
+    got, fallbacks = _both_paths(s, Q, k)
+    assert (got[2] == k).all()
+    _assert_oracle((got[0][:3], got[1][:3], got[2][:3]), X, Q[:3], k, "l2")
+    s.close()
