@@ -169,7 +169,8 @@ int search_gemm(mlv_index* h, const float* qprep, uint32_t nq, uint32_t k, const
     const uint32_t total_tiles = (uint32_t)((h->rows + GEMM_BM - 1) / GEMM_BM);
     const double growth = (double)(cap - kprime) / (4.0 * kprime);
     uint32_t seen = 0;
-    const int refine_threads = (int)std::min<uint32_t>(SELECT_THREADS, std::max<uint32_t>(P / 2, 32));
+    // a query's buffer is typically a quarter full: 256 threads sort it, and many CTAs share an SM
+    const int refine_threads = (int)std::min<uint32_t>(256, std::max<uint32_t>(P / 2, 32));
     while (seen < total_tiles) {
         uint32_t take = seen == 0 ? std::max<uint32_t>(1, cap / GEMM_BM) : std::max<uint32_t>(1, (uint32_t)(seen * growth));
         take = std::min(take, total_tiles - seen);
