@@ -208,6 +208,49 @@ int mlv_filter_passing(mlv_filter_t f, uint64_t *passing);
 int mlv_filter_destroy(mlv_filter_t f);
 int mlv_index_set_filter(mlv_index_t h, mlv_filter_t f);
 
+/* The filter's bitmap as the searches see it (host, n_words uint32 words; words beyond the filter are 0). */
+int mlv_filter_get_bitmap(mlv_filter_t f, uint32_t *out_words, uint64_t n_words);
+
+/*
+ * Columnar metadata (csrc/column_kernels.cuh).  The reference keeps
+ * metadata as a host mapping per vector (implementations/vector.py:15) and sketches filters only as a dict of
+ * equality constraints (README.md:123,477; examples/api_client.py:65-74).  An index may carry up to
+ * MLV_MAX_COLUMNS int32 columns, one value per local row, in device memory beside the rows (how strings or
+ * other values map to codes is the caller's business); rows never written hold MLV_COLUMN_MISSING.  Columns
+ * follow compaction (values move with their rows) and are dropped by mlv_index_clear.
+ * mlv_filter_create_where evaluates a conjunction of comparisons on the device into a prepared filter --
+ * the same object mlv_filter_create builds from a host bitmap: a row passes when, for every predicate, its
+ * value is not MLV_COLUMN_MISSING and `value op a` holds (MLV_OP_BETWEEN: a <= value <= b).  The filter is
+ * the predicate's result at creation: rows appended or columns rewritten afterwards do not change it.
+ * Semantics restated in oracle/exact.py::where_mask.
+ */
+#define MLV_MAX_COLUMNS 16u
+#define MLV_MAX_PREDICATES 8u
+#define MLV_COLUMN_MISSING INT32_MIN
+enum mlv_pred_op { MLV_OP_EQ = 0, MLV_OP_NE = 1, MLV_OP_LT = 2, MLV_OP_LE = 3, MLV_OP_GT = 4, MLV_OP_GE = 5, MLV_OP_BETWEEN = 6 };
+typedef struct mlv_predicate {
+    uint32_t column;
+    int32_t op;      /* enum mlv_pred_op */
+    int32_t a, b;    /* b is used by MLV_OP_BETWEEN only */
+} mlv_predicate_t;
+/* Write values[0..n) of `column` for local rows first_row .. first_row+n-1 (host memory; rows must exist). */
+int mlv_index_set_column(mlv_index_t h, uint32_t column, uint64_t first_row, const int32_t *values, uint64_t n);
+/* Same, values already in device memory of this index's device. */
+int mlv_index_set_column_device(mlv_index_t h, uint32_t column, uint64_t first_row, const int32_t *values_dev, uint64_t n);
+/* Read a column back (MLV_COLUMN_MISSING where never written). */
+int mlv_index_get_column(mlv_index_t h, uint32_t column, uint64_t first_row, uint64_t n, int32_t *out);
+int mlv_filter_create_where(mlv_index_t h, const mlv_predicate_t *preds, uint32_t n_preds, mlv_filter_t *out);
+
+/*
+ * Snapshot support (the reference has no persistence, README.md:240-241 only):
+ * rows exactly as stored (cosine: already normalised), tombstoned ones included, and the tombstone bitmap
+ * (bit set = live).  mlv_index_import_rows appends stored-form rows WITHOUT normalising them again, so an
+ * export -> import round trip reproduces the matrix bit for bit; live_words == NULL marks every row live.
+ */
+int mlv_index_export_rows(mlv_index_t h, uint64_t first_row, uint64_t n, float *out);
+int mlv_index_export_live(mlv_index_t h, uint32_t *out_words, uint64_t n_words);
+int mlv_index_import_rows(mlv_index_t h, const float *rows, uint64_t n, const uint32_t *live_words, uint64_t *first_row);
+
 /*
  * Fused multi-GPU exchange (csrc/exchange.cuh): the exchange step of a row-sharded search done
  * over NVLink peer memory by the search kernel itself.  One process per GPU: every rank creates

@@ -45,6 +45,15 @@ class GemmStats(C.Structure):
     ]
 
 
+class Predicate(C.Structure):
+    """``mlv_predicate_t``"""
+    _fields_ = [("column", C.c_uint32), ("op", C.c_int32), ("a", C.c_int32), ("b", C.c_int32)]
+
+
+MAX_COLUMNS, MAX_PREDICATES = 16, 8
+COLUMN_MISSING = -(2 ** 31)
+PRED_OPS = {"==": 0, "!=": 1, "<": 2, "<=": 3, ">": 4, ">=": 5, "between": 6}
+
 _f32p = C.POINTER(C.c_float)
 _i64p = C.POINTER(C.c_int64)
 _i32p = C.POINTER(C.c_int32)
@@ -87,6 +96,14 @@ SIGNATURES = {
     "mlv_filter_passing": (C.c_int, [_h, _u64p]),
     "mlv_filter_destroy": (C.c_int, [_h]),
     "mlv_index_set_filter": (C.c_int, [_h, _h]),
+    "mlv_filter_get_bitmap": (C.c_int, [_h, C.c_void_p, C.c_uint64]),
+    "mlv_filter_create_where": (C.c_int, [_h, C.POINTER(Predicate), C.c_uint32, C.POINTER(_h)]),
+    "mlv_index_set_column": (C.c_int, [_h, C.c_uint32, C.c_uint64, C.c_void_p, C.c_uint64]),
+    "mlv_index_set_column_device": (C.c_int, [_h, C.c_uint32, C.c_uint64, C.c_void_p, C.c_uint64]),
+    "mlv_index_get_column": (C.c_int, [_h, C.c_uint32, C.c_uint64, C.c_uint64, C.c_void_p]),
+    "mlv_index_export_rows": (C.c_int, [_h, C.c_uint64, C.c_uint64, C.c_void_p]),
+    "mlv_index_export_live": (C.c_int, [_h, C.c_void_p, C.c_uint64]),
+    "mlv_index_import_rows": (C.c_int, [_h, C.c_void_p, C.c_uint64, C.c_void_p, _u64p]),
     "mlv_exchange_create": (C.c_int, [C.c_int, C.c_uint32, C.c_uint32, C.POINTER(_h), C.c_void_p]),
     "mlv_exchange_connect": (C.c_int, [_h, C.c_void_p]),
     "mlv_exchange_check": (C.c_int, [_h]),

@@ -109,6 +109,9 @@ struct mlv_index {
     int tune_gemm_bn = 0;      // queries per GEMM tile: 0 auto, or 64 / 128 / 256
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> gemm_pending;
     uint64_t gemm_searches = 0, gemm_queries = 0, gemm_fallback_queries = 0, gemm_rounds = 0, gemm_launches = 0;
+    // columnar metadata (column_kernels.cuh): int32 code columns, allocated on first use
+    DevBuf d_cols[MLV_MAX_COLUMNS];
+    uint64_t col_rows[MLV_MAX_COLUMNS] = {0};  // rows each allocation covers (<= capacity; grown lazily)
 };
 
 namespace {

@@ -16,6 +16,7 @@
 #include <utility>
 #include <vector>
 
+#include "column_kernels.cuh"
 #include "common.cuh"
 #include "gemm_kernel.cuh"
 #include "maint_kernels.cuh"
@@ -27,6 +28,7 @@ using namespace mlv;
 #include "host_state.inl"
 #include "host_scan.inl"
 #include "host_gemm.inl"
+#include "host_columns.inl"
 
 
 // =================================================================================== C ABI
@@ -123,6 +125,7 @@ int mlv_index_destroy(mlv_index_t h) {
         free_dev(*b);
     for (Lane& l : h->lanes)
         for (DevBuf* b : {&l.d_q, &l.d_keys0, &l.d_keys1, &l.d_sched, &l.d_flist, &l.d_fscratch}) free_dev(*b);
+    drop_columns(h);
     if (h->h_stage.p) cudaFreeHost(h->h_stage.p);
     for (AsyncSlot& sl : h->slots) {
         if (sl.stream) cudaStreamSynchronize(sl.stream);
@@ -271,16 +274,25 @@ int mlv_index_compact(mlv_index_t h, int64_t* old_to_new, uint64_t* new_rows) {
         h->launches += 2;
         e = cudaGetLastError();
     }
+    int32_t* fresh_cols[MLV_MAX_COLUMNS] = {nullptr};
+    if (e == cudaSuccess && (rc = compact_columns(h, d_wbase, n, fresh_cols)) != MLV_OK) {
+        cudaStreamSynchronize(h->stream);
+        cudaFree(nrows);
+        return rc;
+    }
     uint64_t total = 0;
     if (e == cudaSuccess) e = cudaMemcpyAsync(&total, d_total, 8, cudaMemcpyDeviceToHost, h->stream);
     if (e == cudaSuccess && old_to_new) e = cudaMemcpyAsync(old_to_new, d_map, n * 8, cudaMemcpyDeviceToHost, h->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
     if (e != cudaSuccess) {
         cudaFree(nrows);
+        for (int32_t* c : fresh_cols)
+            if (c) cudaFree(c);
         return fail_cuda(h, e, "compact");
     }
     cudaFree(h->d_rows);
     h->d_rows = nrows;
+    adopt_compacted_columns(h, fresh_cols);
     h->rows = total;
     h->n_deleted = 0;
     h->norms_valid = 0;
@@ -310,6 +322,7 @@ int mlv_index_clear(mlv_index_t h) {
     h->norms_valid = 0;
     h->epoch++;
     h->compact_gen++;
+    drop_columns(h);
     return MLV_OK;
 }
 
@@ -347,22 +360,132 @@ int mlv_filter_create(mlv_index_t h, const uint32_t* bitmap, uint64_t n_words, m
         cudaError_t e = cudaMemcpyAsync(f->d_bitmap.p, bitmap, n_words * 4, cudaMemcpyHostToDevice, h->stream);
         if (e != cudaSuccess) rc = fail_cuda(h, e, "filter upload");
     }
-    if (rc == MLV_OK && h->rows) rc = build_gather_list(h, f->d_list, f->d_scratch, (const uint32_t*)f->d_bitmap.p, n_words, h->stream);
-    uint64_t total = 0;
-    if (rc == MLV_OK && h->rows) {
-        cudaError_t e = cudaMemcpyAsync(&total, f->d_scratch.p, 8, cudaMemcpyDeviceToHost, h->stream);
-        if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
-        if (e != cudaSuccess) rc = fail_cuda(h, e, "filter build");
-    }
     if (rc != MLV_OK) {
-        for (DevBuf* b : {&f->d_bitmap, &f->d_list, &f->d_scratch}) free_dev(*b);
+        free_dev(f->d_bitmap);
         delete f;
         return rc;
     }
-    f->passing = total;
-    f->counted = true;
-    f->epoch = h->rows ? h->epoch : ~0ull;
-    *out = f;
+    return finish_filter(h, f, out);
+}
+
+int mlv_filter_create_where(mlv_index_t h, const mlv_predicate_t* preds, uint32_t n_preds, mlv_filter_t* out) {
+    if (!h || !out || (!preds && n_preds)) return MLV_E_INVALID;
+    *out = nullptr;
+    if (n_preds > MLV_MAX_PREDICATES) return fail(h, MLV_E_UNSUPPORTED, "more than MLV_MAX_PREDICATES predicates");
+    WhereArgs args{};
+    args.n = n_preds;
+    for (uint32_t i = 0; i < n_preds; i++) {
+        if (preds[i].column >= MLV_MAX_COLUMNS) return fail(h, MLV_E_UNSUPPORTED, "column index exceeds MLV_MAX_COLUMNS");
+        if (preds[i].op < MLV_OP_EQ || preds[i].op > MLV_OP_BETWEEN) return fail(h, MLV_E_INVALID, "unknown predicate operator");
+        const uint32_t c = preds[i].column;
+        args.p[i].col = (const int32_t*)h->d_cols[c].p;     // never written: every row is missing
+        args.p[i].col_rows = h->d_cols[c].p ? h->col_rows[c] : 0;
+        args.p[i].op = preds[i].op;
+        args.p[i].a = preds[i].a;
+        args.p[i].b = preds[i].b;
+    }
+    DeviceGuard g(h->device);
+    mlv_filter* f = new (std::nothrow) mlv_filter();
+    if (!f) return MLV_E_NOMEM;
+    f->owner = h;
+    f->compact_gen = h->compact_gen;
+    const uint64_t n_words = (h->rows + 31) / 32;
+    f->bitmap_words = n_words;
+    int rc = ensure_dev(h, f->d_bitmap, std::max<uint64_t>(n_words, 1) * 4);
+    if (rc == MLV_OK && n_words) {
+        constexpr int WPS = 4;
+        const uint64_t warps = (n_words + WPS - 1) / WPS;
+        where_kernel<WPS><<<grid_for(h, warps, 8), 256, 0, h->stream>>>(args, h->rows, (uint32_t*)f->d_bitmap.p);
+        h->launches++;
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) rc = fail_cuda(h, e, "where_kernel");
+    }
+    if (rc != MLV_OK) {
+        free_dev(f->d_bitmap);
+        delete f;
+        return rc;
+    }
+    return finish_filter(h, f, out);
+}
+
+int mlv_filter_get_bitmap(mlv_filter_t f, uint32_t* out_words, uint64_t n_words) {
+    if (!f || (!out_words && n_words)) return MLV_E_INVALID;
+    mlv_index* h = f->owner;
+    DeviceGuard g(h->device);
+    const uint64_t have = std::min(n_words, f->bitmap_words);
+    if (have) CK(h, cudaMemcpyAsync(out_words, f->d_bitmap.p, have * 4, cudaMemcpyDeviceToHost, h->stream));
+    CK(h, cudaStreamSynchronize(h->stream));
+    for (uint64_t i = have; i < n_words; i++) out_words[i] = 0;
+    return MLV_OK;
+}
+
+int mlv_index_set_column(mlv_index_t h, uint32_t column, uint64_t first_row, const int32_t* values, uint64_t n) {
+    return set_column_common(h, column, first_row, values, n, cudaMemcpyHostToDevice);
+}
+int mlv_index_set_column_device(mlv_index_t h, uint32_t column, uint64_t first_row, const int32_t* values_dev, uint64_t n) {
+    return set_column_common(h, column, first_row, values_dev, n, cudaMemcpyDeviceToDevice);
+}
+
+int mlv_index_get_column(mlv_index_t h, uint32_t column, uint64_t first_row, uint64_t n, int32_t* out) {
+    if (!h || (!out && n)) return MLV_E_INVALID;
+    if (column >= MLV_MAX_COLUMNS) return fail(h, MLV_E_UNSUPPORTED, "column index exceeds MLV_MAX_COLUMNS");
+    if (first_row + n > h->rows || first_row + n < first_row) return fail(h, MLV_E_INVALID, "column read beyond the stored rows");
+    if (n == 0) return MLV_OK;
+    DeviceGuard g(h->device);
+    const uint64_t have = h->d_cols[column].p ? h->col_rows[column] : 0;
+    const uint64_t from_dev = first_row < have ? std::min(n, have - first_row) : 0;
+    if (from_dev) {
+        CK(h, cudaMemcpyAsync(out, (const int32_t*)h->d_cols[column].p + first_row, from_dev * 4, cudaMemcpyDeviceToHost, h->stream));
+        CK(h, cudaStreamSynchronize(h->stream));
+    }
+    for (uint64_t i = from_dev; i < n; i++) out[i] = MLV_COLUMN_MISSING;
+    return MLV_OK;
+}
+
+int mlv_index_export_rows(mlv_index_t h, uint64_t first_row, uint64_t n, float* out) {
+    if (!h || (!out && n)) return MLV_E_INVALID;
+    if (first_row + n > h->rows || first_row + n < first_row) return fail(h, MLV_E_INVALID, "export beyond the stored rows");
+    if (n == 0) return MLV_OK;
+    DeviceGuard g(h->device);
+    const uint64_t max_rows_per_copy = 1u << 20;
+    for (uint64_t r0 = 0; r0 < n; r0 += max_rows_per_copy) {
+        const uint64_t nr = std::min(max_rows_per_copy, n - r0);
+        CK(h, cudaMemcpy2DAsync(out + r0 * h->dim, (size_t)h->dim * 4, h->d_rows + (first_row + r0) * h->ld, (size_t)h->ld * 4,
+                                (size_t)h->dim * 4, nr, cudaMemcpyDeviceToHost, h->stream));
+    }
+    CK(h, cudaStreamSynchronize(h->stream));
+    return MLV_OK;
+}
+
+int mlv_index_export_live(mlv_index_t h, uint32_t* out_words, uint64_t n_words) {
+    if (!h || (!out_words && n_words)) return MLV_E_INVALID;
+    DeviceGuard g(h->device);
+    const uint64_t have = std::min(n_words, (h->rows + 31) / 32);
+    if (have) CK(h, cudaMemcpyAsync(out_words, h->d_live, have * 4, cudaMemcpyDeviceToHost, h->stream));
+    CK(h, cudaStreamSynchronize(h->stream));
+    for (uint64_t i = have; i < n_words; i++) out_words[i] = 0;
+    return MLV_OK;
+}
+
+int mlv_index_import_rows(mlv_index_t h, const float* rows, uint64_t n, const uint32_t* live_words, uint64_t* first_row) {
+    if (!h || (!rows && n)) return MLV_E_INVALID;
+    if (n == 0) {
+        if (first_row) *first_row = h->rows;
+        return MLV_OK;
+    }
+    const int metric = h->metric;
+    h->metric = metric == MLV_COSINE ? MLV_IP : metric;   // stored form: already normalised, finish_append must not redo it
+    uint64_t first = 0;
+    int rc = add_common(h, rows, n, &first, cudaMemcpyHostToDevice);
+    h->metric = metric;
+    if (rc != MLV_OK) return rc;
+    if (first_row) *first_row = first;
+    if (live_words) {
+        std::vector<uint64_t> gone;
+        for (uint64_t i = 0; i < n; i++)
+            if (!((live_words[i >> 5] >> (i & 31)) & 1u)) gone.push_back(first + i);
+        if (!gone.empty()) return mlv_index_mark_deleted(h, gone.data(), gone.size(), nullptr);
+    }
     return MLV_OK;
 }
 
@@ -748,6 +871,7 @@ int mlv_index_info(mlv_index_t h, mlv_index_info_t* info) {
         b += d->bytes;
     for (const Lane& l : h->lanes)
         for (const DevBuf* d : {&l.d_q, &l.d_keys0, &l.d_keys1, &l.d_sched, &l.d_flist, &l.d_fscratch}) b += d->bytes;
+    for (const DevBuf& c : h->d_cols) b += c.bytes;
     info->device_bytes = b;
     info->dim = h->dim;
     info->ld = h->ld;

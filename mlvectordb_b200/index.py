@@ -32,10 +32,18 @@ from uuid import UUID
 import numpy as np
 
 from . import _capi
+from .columns import ColumnCodec
 from .interfaces import SearchResult, VectorDTO, VectorProtocol
 from .shard import DeviceShard, PreparedFilter, canonical_space
 
-FilterArg = Union[None, np.ndarray, Callable[[UUID], bool], PreparedFilter]
+# row mask / packed bitmap, callable(uuid) -> bool, prepared filter, or a mapping of metadata constraints
+# ({key: value} equality, {key: (op, a)} / {key: ("between", a, b)}) evaluated on the device columns
+FilterArg = Union[None, np.ndarray, Callable[[UUID], bool], PreparedFilter, Mapping]
+
+
+class NotDeviceEvaluable(ValueError):
+    """A metadata constraint the device columns cannot decide (see ``columns.py``); evaluate it on the host
+    and pass a row mask / ``callable(uuid)`` instead (``GpuQueryProcessor`` does)."""
 
 
 def _random_uuid_bytes(n: int) -> np.ndarray:
@@ -59,6 +67,15 @@ class _Namespace:
         self.total = 0
         self.deleted = 0
         self.rebuild_required = False
+        self.codec = ColumnCodec()                                    # metadata key -> device column
+        self.version = 0                                              # bumped by every mutation
+        self.where_cache: Dict[tuple, PreparedFilter] = {}            # constraints -> filter, valid for `version`
+
+    def touch(self) -> None:
+        self.version += 1
+        for f in self.where_cache.values():
+            f.close()
+        self.where_cache.clear()
 
     def reserve(self, extra: int) -> None:
         need = self.n + extra
@@ -134,7 +151,17 @@ class GpuIndex:
         ns.gone[first:first + n] = False
         ns.n += n
         ns.total += n
+        ns.touch()
         return np.arange(first, first + n, dtype=np.int64)
+
+    @staticmethod
+    def _ingest_metadata(ns: _Namespace, first_row: int, vectors) -> None:
+        """Metadata mappings of freshly appended rows -> device columns (``columns.py``)."""
+        mds = [getattr(v, "metadata", None) for v in vectors]
+        if not any(mds):
+            return
+        for column, codes in ns.codec.encode_rows(mds).items():
+            ns.shard.set_column(column, codes, first_row)
 
     def _maybe_compact(self, ns: _Namespace) -> None:
         ratio = ns.deleted / max(1, ns.total)
@@ -156,15 +183,34 @@ class GpuIndex:
         ns.deleted = 0
         ns.rebuild_required = False
         ns.uuid_to_row = None
+        ns.touch()
 
     def _filter_mask(self, ns: _Namespace, filt: FilterArg):
         if filt is None:
             return None
         if isinstance(filt, PreparedFilter):
             return filt
+        if isinstance(filt, Mapping):
+            return self._where(ns, filt)
         if callable(filt):
             return np.fromiter((bool(filt(ns.uuid_of(r))) for r in range(ns.n)), dtype=bool, count=ns.n)
         return filt
+
+    def _where(self, ns: _Namespace, constraints: Mapping) -> PreparedFilter:
+        try:
+            key = tuple(sorted(constraints.items(), key=lambda kv: kv[0]))
+            cached = ns.where_cache.get(key)
+        except TypeError:
+            key, cached = None, None
+        if cached is not None:
+            return cached
+        preds = ns.codec.predicates(constraints)
+        if preds is None:
+            raise NotDeviceEvaluable(f"constraints {dict(constraints)!r} cannot be evaluated on the device columns")
+        prepared = ns.shard.where(preds)
+        if key is not None:
+            ns.where_cache[key] = prepared
+        return prepared
 
     # ------------------------------------------------------------------ IndexProtocol
     def add(self, vectors: Iterable[VectorProtocol], namespace: str) -> None:
@@ -179,6 +225,7 @@ class GpuIndex:
             raise RuntimeError("Wrong dimensionality of the vectors")  # hnswlib's add_items error
         ids = np.frombuffer(b"".join(v.id.bytes for v in vectors), dtype=np.uint8).reshape(-1, 16)
         rows = self._append(ns, data, ids)
+        self._ingest_metadata(ns, int(rows[0]), vectors)
         if ns.uuid_to_row is not None:
             for v, r in zip(vectors, rows.tolist()):
                 ns.uuid_to_row[v.id.bytes] = r
@@ -198,6 +245,7 @@ class GpuIndex:
             changed = ns.shard.mark_deleted(np.asarray(rows, dtype=np.uint64))
             assert changed == len(rows), "device tombstones out of step with the host id map"
             ns.gone[rows] = True
+            ns.touch()
         ns.deleted += len(rows)
         self._maybe_compact(ns)
 
@@ -250,6 +298,7 @@ class GpuIndex:
             data = np.array([v.values for v in vectors], dtype=np.float32)
             ids = np.frombuffer(b"".join(v.id.bytes for v in vectors), dtype=np.uint8).reshape(-1, 16)
             rows = self._append(ns, data, ids)
+            self._ingest_metadata(ns, 0, vectors)
             ns.uuid_to_row = {v.id.bytes: r for v, r in zip(vectors, rows.tolist())}
             ns.total = len(vectors)
             ns.deleted = 0
@@ -265,8 +314,11 @@ class GpuIndex:
         ns = self._ns.get(namespace)
         return ns.dim if ns is not None else None
 
-    def add_matrix(self, matrix: np.ndarray, namespace: str, ids: Optional[Sequence[UUID]] = None) -> np.ndarray:
-        """Bulk ingest without per-row ``Vector`` objects.  Returns the rows' UUID bytes [n, 16]."""
+    def add_matrix(self, matrix: np.ndarray, namespace: str, ids: Optional[Sequence[UUID]] = None,
+                   columns: Optional[Mapping[str, Sequence]] = None) -> np.ndarray:
+        """Bulk ingest without per-row ``Vector`` objects.  Returns the rows' UUID bytes [n, 16].
+        ``columns``: metadata as whole columns ``{key: values[n]}`` (integer arrays are stored as they are, other
+        values dictionary coded) for ``filter={key: ...}`` searches evaluated on the device."""
         data = np.ascontiguousarray(matrix, dtype=np.float32)
         if data.ndim != 2:
             raise ValueError("matrix must be [n, dim]")
@@ -281,7 +333,13 @@ class GpuIndex:
             id_bytes = np.frombuffer(b"".join(u.bytes for u in ids), dtype=np.uint8).reshape(-1, 16)
             if id_bytes.shape[0] != data.shape[0]:
                 raise ValueError("len(ids) != rows")
+        if columns:
+            for name, values in columns.items():
+                if len(values) != data.shape[0]:
+                    raise ValueError(f"column {name!r} has {len(values)} values for {data.shape[0]} rows")
         rows = self._append(ns, data, id_bytes)
+        for name, values in (columns or {}).items():
+            self.set_column(namespace, name, values, first_row=int(rows[0]))
         if data.shape[0] > 100_000:
             ns.uuid_to_row = None          # rebuilt lazily from ns.ids by the first remove()
         elif ns.uuid_to_row is not None:
@@ -304,6 +362,7 @@ class GpuIndex:
         ns.n += n
         ns.total += n
         ns.uuid_to_row = None
+        ns.touch()
 
     def search_batch(self, queries: np.ndarray, top_k: int, namespace: str, metric: Optional[str] = None,
                      filter: FilterArg = None):
@@ -351,6 +410,35 @@ class GpuIndex:
             out.append(SearchResult(vector_id=ns.uuid_of(row), score=score))
         return out
 
+    def set_column(self, namespace: str, name: str, values, first_row: int = 0) -> bool:
+        """Write metadata key ``name`` for rows ``first_row ..`` as one column.  False when the key cannot live on
+        the device (``columns.py``: more than 16 keys, unhashable values) -- constraints on it then raise
+        ``NotDeviceEvaluable``."""
+        ns = self._ns[namespace]
+        if first_row < 0 or first_row + len(values) > ns.n:
+            raise ValueError("column values beyond the stored rows")
+        enc = ns.codec.encode_column(name, values)
+        ns.touch()
+        if enc is None:
+            return False
+        ns.shard.set_column(enc[0], enc[1], first_row)
+        return True
+
+    def where(self, namespace: str, constraints: Mapping) -> Optional[PreparedFilter]:
+        """Prepared filter for metadata constraints evaluated on the device columns, or None when they cannot be
+        (then evaluate on the host and use ``prepare_filter``).  Cached until the namespace changes."""
+        ns = self._ns.get(namespace)
+        if ns is None:
+            return None
+        try:
+            return self._where(ns, constraints)
+        except NotDeviceEvaluable:
+            return None
+
+    def metadata_columns(self, namespace: str) -> List[str]:
+        ns = self._ns.get(namespace)
+        return ns.codec.names() if ns is not None else []
+
     def prepare_filter(self, namespace: str, filter: FilterArg) -> PreparedFilter:
         """Evaluate a filter (row mask or ``callable(uuid) -> bool``) once and keep it on the device;
         pass the result as ``filter=`` to ``search`` / ``search_batch`` / ``range_search``.  It follows later
@@ -368,6 +456,17 @@ class GpuIndex:
 
     def namespaces(self) -> List[str]:
         return list(self._ns)
+
+    def save(self, path: str) -> dict:
+        """Snapshot every namespace under directory ``path`` (``snapshot.py``)."""
+        from .snapshot import save_index
+        return save_index(self, path)
+
+    @classmethod
+    def load(cls, path: str, device: int = 0) -> "GpuIndex":
+        """Index restored from ``save``'s directory; searches return what they returned before the save."""
+        from .snapshot import load_index
+        return load_index(path, device=device, index_cls=cls)
 
     def close(self) -> None:
         for ns in self._ns.values():

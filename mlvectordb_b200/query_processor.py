@@ -25,6 +25,7 @@ from uuid import UUID
 
 import numpy as np
 
+from .columns import host_predicate
 from .index import GpuIndex, _random_uuid_bytes
 from .interfaces import VectorDTO
 from .shard import PreparedFilter
@@ -163,19 +164,23 @@ class GpuQueryProcessor:
 
     def _resolve_filter(self, namespace: str, flt: MetadataFilter):
         """dict of equality constraints / predicate over metadata -> prepared device filter (cached until the
-        namespace changes).  The mask is evaluated on the host against the storage's metadata."""
+        namespace changes).  Constraints over keys the index holds as device columns are evaluated by
+        ``mlv_filter_create_where``; anything else (callables, unhashable / ``None`` values, keys beyond the
+        column limit) is evaluated on the host against the storage's metadata."""
         if flt is None or isinstance(flt, PreparedFilter):
             return flt
         if self._index.dimension(namespace) is None:
             return None
         if isinstance(flt, Mapping):
+            on_device = self._index.where(namespace, flt)   # metadata columns on the device (columns.py)
+            if on_device is not None:
+                return on_device
             items = tuple(sorted(flt.items(), key=lambda kv: kv[0]))
             try:
                 key = (namespace, hash(items), items)
             except TypeError:
                 key = None
-            def pred(md, items=items):
-                return all(md.get(k) == v for k, v in items)
+            pred = host_predicate(flt)
         else:
             key, pred = None, flt
         if key is not None and key in self._filters:

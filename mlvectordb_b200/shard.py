@@ -222,6 +222,60 @@ class DeviceShard:
                 return [(dists[i, : int(counts[i])].copy(), rows[i, : int(counts[i])].copy()) for i in range(nq)]
             max_hits = most  # the call reports the total: one retry with an exact buffer
 
+    # -- columnar metadata + device-evaluated predicates (include/mlv_index.h: mlv_index_set_column ...) ----
+    def set_column(self, column: int, values, first_row: int = 0) -> None:
+        """int32 codes for rows ``first_row ..`` of ``column`` (``_capi.COLUMN_MISSING`` = no value)."""
+        v = np.ascontiguousarray(values, dtype=np.int32)
+        self._ck(self._lib.mlv_index_set_column(self._h, int(column), int(first_row), v.ctypes.data, v.shape[0]))
+
+    def get_column(self, column: int, first_row: int = 0, n: Optional[int] = None) -> np.ndarray:
+        n = self.rows - first_row if n is None else int(n)
+        out = np.empty(n, dtype=np.int32)
+        self._ck(self._lib.mlv_index_get_column(self._h, int(column), int(first_row), n, out.ctypes.data))
+        return out
+
+    def where(self, predicates) -> "PreparedFilter":
+        """Prepared filter from a conjunction of ``(column, op, a[, b])`` with op in
+        ``== != < <= > >= between``, evaluated on the device over the columns."""
+        preds = (_capi.Predicate * max(len(predicates), 1))()
+        for i, p in enumerate(predicates):
+            column, op, a = p[0], p[1], p[2]
+            preds[i] = _capi.Predicate(int(column), _capi.PRED_OPS[op], int(a), int(p[3]) if len(p) > 3 else 0)
+        f = C.c_void_p()
+        self._ck(self._lib.mlv_filter_create_where(self._h, preds, len(predicates), C.byref(f)))
+        return PreparedFilter._adopt(self, f)
+
+    # -- snapshot (include/mlv_index.h: mlv_index_export_rows / export_live / import_rows) ------------------
+    def export_rows(self, first_row: int = 0, n: Optional[int] = None, out: Optional[np.ndarray] = None) -> np.ndarray:
+        """Rows as stored (cosine: normalised), tombstoned ones included."""
+        n = self.rows - first_row if n is None else int(n)
+        if out is None:
+            out = np.empty((n, self.dim), dtype=np.float32)
+        assert out.shape == (n, self.dim) and out.dtype == np.float32 and out.flags.c_contiguous
+        self._ck(self._lib.mlv_index_export_rows(self._h, int(first_row), n, out.ctypes.data))
+        return out
+
+    def export_live(self) -> np.ndarray:
+        """Tombstone bitmap, uint32 words, bit set = live."""
+        words = np.zeros((self.rows + 31) // 32, dtype=np.uint32)
+        self._ck(self._lib.mlv_index_export_live(self._h, words.ctypes.data, words.shape[0]))
+        return words
+
+    def import_rows(self, rows: np.ndarray, live_words: Optional[np.ndarray] = None) -> int:
+        """Append stored-form rows without normalising them again; ``live_words`` restores tombstones."""
+        x = np.ascontiguousarray(rows, dtype=np.float32)
+        if x.ndim != 2 or x.shape[1] != self.dim:
+            raise ValueError(f"expected rows of dimension {self.dim}, got shape {x.shape}")
+        lw = None
+        if live_words is not None:
+            lw = np.ascontiguousarray(live_words, dtype=np.uint32)
+            if lw.shape[0] < (x.shape[0] + 31) // 32:
+                raise ValueError("live bitmap shorter than ceil(rows/32) words")
+        first = C.c_uint64()
+        self._ck(self._lib.mlv_index_import_rows(self._h, x.ctypes.data, x.shape[0], lw.ctypes.data if lw is not None else None,
+                                                 C.byref(first)))
+        return int(first.value)
+
     def get_rows(self, rows) -> np.ndarray:
         r = np.ascontiguousarray(rows, dtype=np.uint64)
         out = np.empty((r.shape[0], self.dim), dtype=np.float32)
@@ -296,6 +350,19 @@ class PreparedFilter:
         w = np.ascontiguousarray(words, dtype=np.uint32)
         check(self._lib.mlv_filter_create(shard._h, w.ctypes.data, w.shape[0], C.byref(self._f)), shard._h)
 
+    @classmethod
+    def _adopt(cls, shard: DeviceShard, handle) -> "PreparedFilter":
+        self = cls.__new__(cls)
+        self._lib, self._shard, self._f = _capi.lib(), shard, handle
+        return self
+
+    def bitmap(self, n_words: Optional[int] = None) -> np.ndarray:
+        """The filter's bitmap words as the searches see them."""
+        n_words = (self._shard.rows + 31) // 32 if n_words is None else int(n_words)
+        out = np.zeros(max(n_words, 1), dtype=np.uint32)
+        check(self._lib.mlv_filter_get_bitmap(self._f, out.ctypes.data, n_words), self._shard._h)
+        return out[:n_words]
+
     @property
     def passing(self) -> int:
         n = C.c_uint64()
@@ -323,6 +390,8 @@ class _bound:
 
     def __enter__(self):
         if self.f is not None:
+            if not self.f._f.value:
+                raise RuntimeError("prepared filter was closed (its namespace changed since it was made); prepare it again")
             check(self.shard._lib.mlv_index_set_filter(self.shard._h, self.f._f), self.shard._h)
 
     def __exit__(self, *exc):

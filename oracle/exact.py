@@ -266,3 +266,38 @@ def check_topk_parity(got_labels: Sequence[int], got_scores: Sequence[float],
         if l not in got_set and abs(s - kth) > 2 * tol:
             return f"oracle label {l} (score {s}) missing and not tied with k-th {kth}"
     return None
+
+
+# --------------------------------------------------------------------------------------
+# Columnar metadata predicates (no reference code: README.md:123,477 and the stale client's
+# ``filter`` dict of equality constraints, examples/api_client.py:65-74).  Semantics of
+# ``mlv_filter_create_where`` (include/mlv_index.h) are *defined* here.
+# --------------------------------------------------------------------------------------
+COLUMN_MISSING = -(2 ** 31)
+
+_WHERE_OPS = {
+    "==": lambda v, a, b: v == a,
+    "!=": lambda v, a, b: v != a,
+    "<": lambda v, a, b: v < a,
+    "<=": lambda v, a, b: v <= a,
+    ">": lambda v, a, b: v > a,
+    ">=": lambda v, a, b: v >= a,
+    "between": lambda v, a, b: (v >= a) & (v <= b),
+}
+
+
+def where_mask(columns, predicates, n_rows: int) -> np.ndarray:
+    """bool[n_rows]: row passes iff for EVERY predicate ``(column, op, a[, b])`` its int32 value is
+    not ``COLUMN_MISSING`` and ``value op a`` holds.  ``columns``: mapping column -> int32 array
+    (shorter than ``n_rows`` or absent = missing for the remaining rows)."""
+    mask = np.ones(n_rows, dtype=bool)
+    for p in predicates:
+        column, op, a = p[0], p[1], int(p[2])
+        b = int(p[3]) if len(p) > 3 else 0
+        v = np.full(n_rows, COLUMN_MISSING, dtype=np.int64)
+        col = columns.get(column)
+        if col is not None:
+            col = np.asarray(col, dtype=np.int64)[:n_rows]
+            v[: col.shape[0]] = col
+        mask &= (v != COLUMN_MISSING) & _WHERE_OPS[op](v, a, b)
+    return mask

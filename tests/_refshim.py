@@ -46,6 +46,17 @@ class Storage:
         return {ns: list(d.values()) for ns, d in self._data.items()}
 
 
+class InMemoryStorage(Storage):
+    """plus the two storage calls ``GpuQueryProcessor`` forwards (``storage_engine_in_memory.py:22-30,61-69``)"""
+
+    @property
+    def list_namespaces(self):
+        return list(self._data)
+
+    def get_storage_info(self):
+        return {"total_vectors": sum(len(d) for d in self._data.values())}
+
+
 class QueryProcessor:
     def __init__(self, storage, index):
         self._storage = storage
