@@ -217,11 +217,8 @@ class ColumnCodec:
             if any(a is None for a in args):
                 return None              # metadata.get(key) == None also matches rows WITHOUT the key
             c = self._cols.get(name)
-            if c is None:                # no row ever carried the key
-                preds.append((0,) + _IMPOSSIBLE)
-                continue
-            if c.kind == "host":
-                return None
+            if c is None or c.kind == "host":
+                return None              # never seen here (rows may have been loaded without their metadata) / host only
             if c.kind == "dict":
                 if op not in ("==", "!="):
                     return None          # codes carry no order

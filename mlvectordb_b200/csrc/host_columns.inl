@@ -91,6 +91,36 @@ int set_column_common(mlv_index* h, uint32_t column, uint64_t first_row, const i
     return MLV_OK;
 }
 
+// a fresh filter starts from the buffers of a destroyed one when there are any
+mlv_filter* new_filter(mlv_index* h, uint64_t n_words) {
+    mlv_filter* f = new (std::nothrow) mlv_filter();
+    if (!f) return nullptr;
+    f->owner = h;
+    f->compact_gen = h->compact_gen;
+    f->bitmap_words = n_words;
+    if (!h->filter_pool.empty()) {
+        FilterBufs b = h->filter_pool.back();
+        h->filter_pool.pop_back();
+        f->d_bitmap = b.bitmap;
+        f->d_list = b.list;
+        f->d_scratch = b.scratch;
+    }
+    return f;
+}
+void retire_filter(mlv_index* h, mlv_filter* f) {
+    if (h->filter_pool.size() < MLV_FILTER_POOL) {
+        h->filter_pool.push_back(FilterBufs{f->d_bitmap, f->d_list, f->d_scratch});
+    } else {
+        for (DevBuf* b : {&f->d_bitmap, &f->d_list, &f->d_scratch}) free_dev(*b);
+    }
+    delete f;
+}
+void drop_filter_pool(mlv_index* h) {
+    for (FilterBufs& b : h->filter_pool)
+        for (DevBuf* d : {&b.bitmap, &b.list, &b.scratch}) free_dev(*d);
+    h->filter_pool.clear();
+}
+
 // Shared tail of mlv_filter_create / mlv_filter_create_where: the bitmap is in f->d_bitmap (work enqueued on
 // h->stream); build the passing-row list and read the count.
 int finish_filter(mlv_index* h, mlv_filter* f, mlv_filter_t* out) {
@@ -104,8 +134,7 @@ int finish_filter(mlv_index* h, mlv_filter* f, mlv_filter_t* out) {
         if (e != cudaSuccess) rc = fail_cuda(h, e, "filter build");
     }
     if (rc != MLV_OK) {
-        for (DevBuf* b : {&f->d_bitmap, &f->d_list, &f->d_scratch}) free_dev(*b);
-        delete f;
+        retire_filter(h, f);
         return rc;
     }
     f->passing = total;

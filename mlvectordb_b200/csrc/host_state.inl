@@ -65,6 +65,13 @@ struct mlv_filter {
     bool counted = false;        // `passing` has been read back
 };
 
+// device buffers of a destroyed prepared filter, kept for the next one: cudaMalloc / cudaFree of the 4-byte-per-row
+// list cost 2 - 30 ms each beside a 30 GB matrix, the kernels that fill it well under 1 ms
+struct FilterBufs {
+    DevBuf bitmap, list, scratch;
+};
+constexpr size_t MLV_FILTER_POOL = 4;
+
 struct mlv_index {
     int device = 0;
     uint32_t dim = 0, ld = 0;
@@ -110,6 +117,7 @@ struct mlv_index {
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> gemm_pending;
     uint64_t gemm_searches = 0, gemm_queries = 0, gemm_fallback_queries = 0, gemm_rounds = 0, gemm_launches = 0;
     // columnar metadata (column_kernels.cuh): int32 code columns, allocated on first use
+    std::vector<FilterBufs> filter_pool;
     DevBuf d_cols[MLV_MAX_COLUMNS];
     uint64_t col_rows[MLV_MAX_COLUMNS] = {0};  // rows each allocation covers (<= capacity; grown lazily)
 };

@@ -126,6 +126,7 @@ int mlv_index_destroy(mlv_index_t h) {
     for (Lane& l : h->lanes)
         for (DevBuf* b : {&l.d_q, &l.d_keys0, &l.d_keys1, &l.d_sched, &l.d_flist, &l.d_fscratch}) free_dev(*b);
     drop_columns(h);
+    drop_filter_pool(h);
     if (h->h_stage.p) cudaFreeHost(h->h_stage.p);
     for (AsyncSlot& sl : h->slots) {
         if (sl.stream) cudaStreamSynchronize(sl.stream);
@@ -350,19 +351,15 @@ int mlv_filter_create(mlv_index_t h, const uint32_t* bitmap, uint64_t n_words, m
     if (!h || !out || (!bitmap && n_words)) return MLV_E_INVALID;
     *out = nullptr;
     DeviceGuard g(h->device);
-    mlv_filter* f = new (std::nothrow) mlv_filter();
+    mlv_filter* f = new_filter(h, n_words);
     if (!f) return MLV_E_NOMEM;
-    f->owner = h;
-    f->compact_gen = h->compact_gen;
-    f->bitmap_words = n_words;
     int rc = ensure_dev(h, f->d_bitmap, std::max<uint64_t>(n_words, 1) * 4);
     if (rc == MLV_OK && n_words) {
         cudaError_t e = cudaMemcpyAsync(f->d_bitmap.p, bitmap, n_words * 4, cudaMemcpyHostToDevice, h->stream);
         if (e != cudaSuccess) rc = fail_cuda(h, e, "filter upload");
     }
     if (rc != MLV_OK) {
-        free_dev(f->d_bitmap);
-        delete f;
+        retire_filter(h, f);
         return rc;
     }
     return finish_filter(h, f, out);
@@ -385,12 +382,9 @@ int mlv_filter_create_where(mlv_index_t h, const mlv_predicate_t* preds, uint32_
         args.p[i].b = preds[i].b;
     }
     DeviceGuard g(h->device);
-    mlv_filter* f = new (std::nothrow) mlv_filter();
-    if (!f) return MLV_E_NOMEM;
-    f->owner = h;
-    f->compact_gen = h->compact_gen;
     const uint64_t n_words = (h->rows + 31) / 32;
-    f->bitmap_words = n_words;
+    mlv_filter* f = new_filter(h, n_words);
+    if (!f) return MLV_E_NOMEM;
     int rc = ensure_dev(h, f->d_bitmap, std::max<uint64_t>(n_words, 1) * 4);
     if (rc == MLV_OK && n_words) {
         constexpr int WPS = 4;
@@ -401,8 +395,7 @@ int mlv_filter_create_where(mlv_index_t h, const mlv_predicate_t* preds, uint32_
         if (e != cudaSuccess) rc = fail_cuda(h, e, "where_kernel");
     }
     if (rc != MLV_OK) {
-        free_dev(f->d_bitmap);
-        delete f;
+        retire_filter(h, f);
         return rc;
     }
     return finish_filter(h, f, out);
@@ -515,9 +508,8 @@ int mlv_filter_destroy(mlv_filter_t f) {
     mlv_index* h = f->owner;
     DeviceGuard g(h->device);
     if (h->bound_filter == f) h->bound_filter = nullptr;
-    cudaDeviceSynchronize();
-    for (DevBuf* b : {&f->d_bitmap, &f->d_list, &f->d_scratch}) free_dev(*b);
-    delete f;
+    cudaDeviceSynchronize();   // searches in flight on other streams may still read the list
+    retire_filter(h, f);
     return MLV_OK;
 }
 
@@ -872,6 +864,7 @@ int mlv_index_info(mlv_index_t h, mlv_index_info_t* info) {
     for (const Lane& l : h->lanes)
         for (const DevBuf* d : {&l.d_q, &l.d_keys0, &l.d_keys1, &l.d_sched, &l.d_flist, &l.d_fscratch}) b += d->bytes;
     for (const DevBuf& c : h->d_cols) b += c.bytes;
+    for (const FilterBufs& fb : h->filter_pool) b += fb.bitmap.bytes + fb.list.bytes + fb.scratch.bytes;
     info->device_bytes = b;
     info->dim = h->dim;
     info->ld = h->ld;

@@ -315,10 +315,12 @@ class GpuIndex:
         return ns.dim if ns is not None else None
 
     def add_matrix(self, matrix: np.ndarray, namespace: str, ids: Optional[Sequence[UUID]] = None,
-                   columns: Optional[Mapping[str, Sequence]] = None) -> np.ndarray:
+                   columns: Optional[Mapping[str, Sequence]] = None,
+                   metadata: Optional[Sequence[Optional[Mapping]]] = None) -> np.ndarray:
         """Bulk ingest without per-row ``Vector`` objects.  Returns the rows' UUID bytes [n, 16].
         ``columns``: metadata as whole columns ``{key: values[n]}`` (integer arrays are stored as they are, other
-        values dictionary coded) for ``filter={key: ...}`` searches evaluated on the device."""
+        values dictionary coded) for ``filter={key: ...}`` searches evaluated on the device; ``metadata``: the same
+        as one mapping per row (what ``add`` reads from ``v.metadata``)."""
         data = np.ascontiguousarray(matrix, dtype=np.float32)
         if data.ndim != 2:
             raise ValueError("matrix must be [n, dim]")
@@ -340,6 +342,11 @@ class GpuIndex:
         rows = self._append(ns, data, id_bytes)
         for name, values in (columns or {}).items():
             self.set_column(namespace, name, values, first_row=int(rows[0]))
+        if metadata is not None:
+            if len(metadata) != data.shape[0]:
+                raise ValueError("len(metadata) != rows")
+            for column, codes in ns.codec.encode_rows(metadata).items():
+                ns.shard.set_column(column, codes, int(rows[0]))
         if data.shape[0] > 100_000:
             ns.uuid_to_row = None          # rebuilt lazily from ns.ids by the first remove()
         elif ns.uuid_to_row is not None:

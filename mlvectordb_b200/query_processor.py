@@ -141,7 +141,7 @@ class GpuQueryProcessor:
         ids = [UUID(bytes=id_bytes[i].tobytes()) for i in range(n)]
         vecs = [StoredVector(data[i], metadata[i] if metadata is not None else None, id=ids[i]) for i in range(n)]
         self._storage.write_vectors(vecs, namespace)
-        self._index.add_matrix(data, namespace, ids=ids)
+        self._index.add_matrix(data, namespace, ids=ids, metadata=metadata)
         self._touch(namespace)
         return ids
 

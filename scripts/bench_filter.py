@@ -27,6 +27,27 @@ s.add_synthetic(42, 0, a.rows, True)
 Q = synthetic.queries(43, a.reps, a.dim)
 bucket = np.random.default_rng([44, 0]).integers(0, 100, a.rows)
 s.set_timing(True)
+# predicate evaluation: metadata column on the device (mlv_filter_create_where) vs the host building the bitmap
+s.set_column(0, bucket.astype(np.int32))
+for sel in (float(x) for x in a.sel.split(",")):
+    cut = int(round(sel * 100))
+    f = s.where([(0, "<", cut)])            # warm-up (allocations)
+    f.close()
+    t0 = time.perf_counter()
+    for _ in range(5):
+        f = s.where([(0, "<", cut)])
+        f.close()
+    dev_ms = (time.perf_counter() - t0) / 5 * 1e3
+    t0 = time.perf_counter()
+    pf = s.prepare_filter(bucket < cut)
+    host_ms = (time.perf_counter() - t0) * 1e3
+    f = s.where([(0, "<", cut)])
+    same = bool(np.array_equal(f.bitmap(), pf.bitmap())) and f.passing == pf.passing
+    print(json.dumps({"selectivity": sel, "mode": "build filter from predicate bucket < %d" % cut, "passing": f.passing,
+                      "device_where_ms": round(dev_ms, 3), "host_mask_upload_ms": round(host_ms, 3),
+                      "bitmaps_identical": same, "column_bytes": a.rows * 4}), flush=True)
+    f.close()
+    pf.close()
 for sel in (float(x) for x in a.sel.split(",")):
     mask = bucket < sel * 100
     passing = int(mask.sum())

@@ -47,7 +47,7 @@ CONSTRAINTS = [
     {"bucket": ("between", -2, 7.5)}, {"bucket": ("between", 7, 2)}, {"bucket": (">", 2 ** 40)}, {"bucket": ("<=", -2 ** 40)},
     {"bucket": ("<", 2 ** 40)}, {"bucket": ("!=", 2 ** 40)}, {"bucket": ("!=", 0.5)},
     {"color": "red"}, {"color": 1}, {"color": ("!=", "red")}, {"color": "purple"}, {"color": ("!=", "purple")}, {"color": (1, 2)},
-    {"bucket": 3, "color": "blue"}, {"bucket": (">=", 0), "color": ("!=", "green"), "w": 1.5}, {"nokey": 1}, {"w": "x"}, {},
+    {"bucket": 3, "color": "blue"}, {"bucket": (">=", 0), "color": ("!=", "green"), "w": 1.5}, {"w": "x"}, {},
 ]
 
 
@@ -75,6 +75,7 @@ def test_what_the_device_cannot_decide_is_reported():
     assert codec.kind("tags") == "host"                     # unhashable values
     assert codec.predicates({"tags": ["x"]}) is None
     assert codec.predicates({"a": None}) is None            # metadata.get(k) == None also matches missing keys
+    assert codec.predicates({"never": 1}) is None           # rows may have been loaded without their metadata
     assert codec.predicates({"s": ("<", "v")}) is None      # dictionary codes carry no order
     assert codec.predicates({"a": 1}) is not None
     # a raw column that later meets a non-integer value is given up (and says so)

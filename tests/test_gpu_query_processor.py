@@ -95,8 +95,11 @@ def test_metadata_filter_dict_and_predicate(loaded):
             assert [r["id"] for r in res] == [ids[j] for j in L[i]]
             assert all(r["metadata"]["bucket"] == 3 for r in res)
     assert p.find_similar(_dto(Q[0].tolist()), 10, namespace="bulk", filter={"bucket": 99}) == []
-    # the dict filter is prepared once and reused until the namespace changes
-    assert sum(1 for k in p._filters if k[0] == "bulk") == 2
+    # dict filters are decided on the device columns, prepared once and reused until the namespace changes
+    assert len(p._index._ns["bulk"].where_cache) == 2 and not p._filters
+    # ... and on the host when the device cannot decide them (None also matches rows without the key)
+    assert p.find_similar(_dto(Q[0].tolist()), 10, namespace="bulk", filter={"nokey": None, "bucket": 3}, enrich=False)
+    assert sum(1 for k in p._filters if k[0] == "bulk") == 1
 
 
 def test_batch_equals_single_and_ids_only(loaded):
