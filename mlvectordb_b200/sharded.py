@@ -161,6 +161,23 @@ class ShardedIndex:
         if self.hi > self.lo:
             self.shard.add(local_rows)
 
+    # -- metadata columns / filters: purely local, a row's values live on the rank that owns the row ------
+    def set_column(self, column: int, local_values) -> None:
+        """int32 codes of this rank's row block for ``column`` (``DeviceShard.set_column``)."""
+        assert len(local_values) == self.hi - self.lo
+        if self.hi > self.lo:
+            self.shard.set_column(column, local_values)
+
+    def where(self, predicates):
+        """Collective only in the sense that every rank prepares the same predicate over its own rows; pass the
+        result as ``filt=`` to ``search`` / ``range_search`` on that rank.  No exchange: the filter restricts the
+        local scan, the candidates merge as before."""
+        return self.shard.where(predicates)
+
+    def _bound(self, filt):
+        from .shard import _bound
+        return _bound(self.shard, filt)
+
     # -- search -----------------------------------------------------------------------------
     def _device_local_search(self, q: torch.Tensor, k: int):
         nq = q.shape[0]
@@ -171,9 +188,13 @@ class ShardedIndex:
         self.shard.search_device(q.data_ptr(), nq, k, d.data_ptr(), r.data_ptr(), c.data_ptr(), stream=stream)
         return d, r, c
 
-    def search_device(self, q: torch.Tensor, k: int):
+    def search_device(self, q: torch.Tensor, k: int, filt=None):
         """``q``: [nq, dim] fp32 tensor on this rank's device (same on every rank).  Returns the
-        global top-k ``(dists [nq,k], rows [nq,k], counts [nq])`` on every rank, nothing synchronised."""
+        global top-k ``(dists [nq,k], rows [nq,k], counts [nq])`` on every rank, nothing synchronised.
+        ``filt``: this rank's prepared filter (``where``), every rank passing its own."""
+        if filt is not None:
+            with self._bound(filt):
+                return self.search_device(q, k)
         if self.exchange is not None and q.shape[0] < self.EXCHANGE_MAX_NQ and self.shard.exchange_supported(k):
             # one kernel per group of <= 8 queries: scan + peer-memory exchange + merge (csrc/exchange.cuh)
             nq = q.shape[0]
@@ -190,8 +211,11 @@ class ShardedIndex:
         self.merge_launches += 1
         return self._merge(gd, gr, k)
 
-    def search(self, queries: np.ndarray, k: int):
+    def search(self, queries: np.ndarray, k: int, filt=None):
         """Host buffers in, host buffers out (pinned staging, H2D + D2H inside the call)."""
+        if filt is not None:
+            with self._bound(filt):
+                return self.search(queries, k)
         q = np.ascontiguousarray(queries, dtype=np.float32).reshape(-1, self.dim)
         nq = q.shape[0]
         if self.exchange is not None and nq < self.EXCHANGE_MAX_NQ and self.shard.exchange_supported(k):
@@ -229,10 +253,13 @@ class ShardedIndex:
             return [(np.empty(0, np.float32), np.empty(0, np.int64)) for _ in range(queries.shape[0])]
         return self.shard.range_search(queries, radius)   # rows already carry row_base
 
-    def range_search(self, queries: np.ndarray, radius: float):
+    def range_search(self, queries: np.ndarray, radius: float, filt=None):
         """Collective.  Every live row of every shard with hnswlib-form distance <= radius, per query
         ascending (distance, global row): the concatenation of the shards' hit lists.
         The exchange is one all-gather of the hit counts and one of the lists padded to the longest."""
+        if filt is not None:
+            with self._bound(filt):
+                return self.range_search(queries, radius)
         q = np.ascontiguousarray(queries, dtype=np.float32).reshape(-1, self.dim)
         nq = q.shape[0]
         local = self._local_range(q, float(radius))

@@ -73,6 +73,33 @@ def main():
                 assert len(got[0][1]) >= 1
         idx.close()
 
+    def check_filtered(total_rows, dim, space, k, nq):
+        """metadata column sharded with the rows, predicate evaluated per rank, filtered sharded search ==
+        filtered unsharded search (fused exchange and NCCL paths)"""
+        idx = ShardedIndex(dim, space, total_rows, device=device)
+        idx.add_synthetic(11, scaled=True)
+        buckets = synthetic.buckets(11, 0, total_rows)
+        idx.set_column(0, buckets[idx.lo:idx.hi])
+        Q = synthetic.queries(12, nq, dim)
+        preds = [(0, "<", 7)]
+        f = idx.where(preds) if idx.hi > idx.lo else None
+        d, r, c = idx.search(Q, k, filt=f)
+        radius = float(d[0, c[0] - 1])                      # every rank holds the same global result
+        hits = idx.range_search(Q[:2], radius, filt=f)
+        if rank == 0:
+            whole = DeviceShard(dim, space, capacity=total_rows, device=rank)
+            whole.add_synthetic(11, 0, total_rows, True)
+            whole.set_column(0, buckets)
+            wf = whole.where(preds)
+            wd, wr, wc = whole.search(Q, k, wf)
+            assert np.array_equal(c, wc) and np.array_equal(r, wr) and np.array_equal(d, wd, equal_nan=True)
+            assert (buckets[r[c[:, None] > np.arange(k)[None, :]]] < 7).all()
+            for (gd, gr), (hd, hr) in zip(hits, whole.range_search(Q[:2], radius, wf)):
+                assert np.array_equal(gr, hr) and np.array_equal(gd, hd)
+            assert len(hits[0][1]) == c[0]
+            whole.close()
+        idx.close()
+
     def idx_range(n, r, w):
         from mlvectordb_b200.sharded import shard_range
         return shard_range(n, r, w)
@@ -84,6 +111,8 @@ def main():
     check(200_003, 64, "l2", 40, 3, True)                  # larger k: bitonic final select in the last CTA
     check(200_003, 64, "cosine", 100, 4, False)            # k too large for the fused exchange: NCCL path
     check(120_000, 128, "l2", 10, 300, True)               # large batch: local tensor-core path + NCCL merge
+    check_filtered(150_001, 64, "cosine", 10, 4)           # filtered, fused exchange
+    check_filtered(150_001, 64, "l2", 100, 3)              # filtered, NCCL merge path
     dist.barrier()
     print(f"rank {rank} ok", flush=True)
     dist.destroy_process_group()
