@@ -188,13 +188,15 @@ Lane* lane_for(mlv_index* h, cudaStream_t st) {
 // beyond it do not pass) into list/scratch, on `st`.  scratch[0] (u64) receives the list length.
 int build_gather_list(mlv_index* h, DevBuf& list, DevBuf& scratch, const uint32_t* bm, uint64_t words, cudaStream_t st) {
     const uint64_t n = h->rows, n_words = (n + 31) / 32;
+    const unsigned blocks = (unsigned)std::max<uint64_t>((n_words + LIST_BLOCK_WORDS - 1) / LIST_BLOCK_WORDS, 1);
     int rc;
-    if ((rc = ensure_dev(h, scratch, n_words * 8 + 8)) != MLV_OK) return rc;
+    if ((rc = ensure_dev(h, scratch, 8 + (size_t)blocks * 4)) != MLV_OK) return rc;
     if ((rc = ensure_dev(h, list, std::max<uint64_t>(n, 1) * 4)) != MLV_OK) return rc;
-    uint64_t* d_total = (uint64_t*)scratch.p;
-    live_prefix_kernel<<<1, 1024, 0, st>>>(h->d_live, n, d_total + 1, d_total, bm, words);
-    scatter_passing_rows_kernel<<<(unsigned)std::min<uint64_t>((n_words + 255) / 256, 2048), 256, 0, st>>>(
-        h->d_live, bm, words, n, d_total + 1, (uint32_t*)list.p);
+    uint64_t* d_total = (uint64_t*)scratch.p;                 // [total u64][block popcounts u32 ...]
+    uint32_t* d_block_sums = (uint32_t*)(d_total + 1);
+    passing_block_sums_kernel<<<blocks, LIST_BLOCK_WORDS, 0, st>>>(h->d_live, bm, words, n, d_block_sums);
+    scatter_passing_rows_kernel<<<blocks, LIST_BLOCK_WORDS, 0, st>>>(h->d_live, bm, words, n, d_block_sums, d_total,
+                                                                    (uint32_t*)list.p);
     h->launches += 2;
     CK(h, cudaGetLastError());
     return MLV_OK;
