@@ -252,6 +252,16 @@ int mlv_index_export_live(mlv_index_t h, uint32_t *out_words, uint64_t n_words);
 int mlv_index_import_rows(mlv_index_t h, const float *rows, uint64_t n, const uint32_t *live_words, uint64_t *first_row);
 
 /*
+ * Response path: the reference answers a search with the k stored vectors as
+ * JSON number lists (rest_api.py:28-32,163), and at GPU search rates encoding k x d floats is the slowest
+ * step of a request.  Writes n fp32 values as a JSON array "[v0,v1,...]" using the shortest decimal text that
+ * round-trips each float32 (non-finite values as NaN / Infinity / -Infinity, like Python's json module).
+ * Host-only helper, no device work.  cap >= 16 * n + 2 always suffices; *len receives the bytes written (no NUL).
+ * MLV_E_INVALID when the buffer is too small.
+ */
+int mlv_format_f32_json(const float *values, uint64_t n, char *out, uint64_t cap, uint64_t *len);
+
+/*
  * Fused multi-GPU exchange (csrc/exchange.cuh): the exchange step of a row-sharded search done
  * over NVLink peer memory by the search kernel itself.  One process per GPU: every rank creates
  * an exchange object, the ranks swap the 64-byte CUDA IPC handles (any transport; the Python

@@ -101,6 +101,7 @@ SIGNATURES = {
     "mlv_index_set_column": (C.c_int, [_h, C.c_uint32, C.c_uint64, C.c_void_p, C.c_uint64]),
     "mlv_index_set_column_device": (C.c_int, [_h, C.c_uint32, C.c_uint64, C.c_void_p, C.c_uint64]),
     "mlv_index_get_column": (C.c_int, [_h, C.c_uint32, C.c_uint64, C.c_uint64, C.c_void_p]),
+    "mlv_format_f32_json": (C.c_int, [C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64, _u64p]),
     "mlv_index_export_rows": (C.c_int, [_h, C.c_uint64, C.c_uint64, C.c_void_p]),
     "mlv_index_export_live": (C.c_int, [_h, C.c_void_p, C.c_uint64]),
     "mlv_index_import_rows": (C.c_int, [_h, C.c_void_p, C.c_uint64, C.c_void_p, _u64p]),
@@ -139,6 +140,16 @@ def lib() -> C.CDLL:
             raise ImportError(f"libmlvindex.so ABI {L.mlv_abi_version()} != binding ABI {ABI_VERSION}; rebuild")
         _lib = L
     return _lib
+
+
+def format_f32_json(values) -> bytes:
+    """``mlv_format_f32_json``: fp32 values -> b"[v0,v1,...]" (shortest round-trip text), C speed."""
+    import numpy as np
+    v = np.ascontiguousarray(values, dtype=np.float32).reshape(-1)
+    buf = C.create_string_buffer(16 * v.shape[0] + 2)
+    n = C.c_uint64()
+    check(lib().mlv_format_f32_json(v.ctypes.data, v.shape[0], buf, len(buf), C.byref(n)))
+    return buf.raw[: n.value]
 
 
 class MlvError(RuntimeError):

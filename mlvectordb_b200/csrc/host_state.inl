@@ -91,6 +91,8 @@ struct mlv_index {
     uint64_t compact_gen = 0;
     int tune_gather = -1;        // -1 auto, 0 never (stream + mask), 1 always when a filter is given
     HostBuf h_stage;
+    HostBuf h_upload;            // two pinned chunks for bulk row uploads (upload_rows_staged)
+    int tune_staged_upload = 1;  // 0 = plain cudaMemcpy from pageable memory
     AsyncSlot slots[MLV_ASYNC_SLOTS];
     uint32_t next_slot = 0;
     std::string err;

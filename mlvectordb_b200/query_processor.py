@@ -47,6 +47,20 @@ class StoredVector:
     def __eq__(self, other):
         return isinstance(other, StoredVector) and self.id == other.id
 
+    @classmethod
+    def rows_of(cls, matrix: np.ndarray, ids: Sequence[UUID], metadata: Optional[Sequence[Optional[Mapping[str, Any]]]]):
+        """One ``StoredVector`` per row of ``matrix`` whose ``values`` are row views of ONE fp32 copy of the matrix
+        (the per-row ``np.array`` copy of ``__init__`` is what makes per-object bulk ingest slow)."""
+        own = np.array(matrix, dtype=np.float32)
+        out = []
+        for i in range(own.shape[0]):
+            v = cls.__new__(cls)
+            v.id = ids[i]
+            v.values = own[i]
+            v.metadata = (metadata[i] if metadata is not None else None) or {}
+            out.append(v)
+        return out
+
 
 class GpuQueryProcessor:
     def __init__(self, storage_engine, index: GpuIndex):
@@ -139,7 +153,7 @@ class GpuQueryProcessor:
             raise ValueError("len(metadata) != rows")
         id_bytes = _random_uuid_bytes(n)
         ids = [UUID(bytes=id_bytes[i].tobytes()) for i in range(n)]
-        vecs = [StoredVector(data[i], metadata[i] if metadata is not None else None, id=ids[i]) for i in range(n)]
+        vecs = StoredVector.rows_of(data, ids, metadata)
         self._storage.write_vectors(vecs, namespace)
         self._index.add_matrix(data, namespace, ids=ids, metadata=metadata)
         self._touch(namespace)

@@ -25,15 +25,17 @@ loop serialises every index call (``rest_api.py:163-193``; SURVEY 8b "Threading"
 """
 from __future__ import annotations
 
+import json
 import logging
 import time
 from contextlib import asynccontextmanager
 from typing import Any, Dict, List, Optional
 from uuid import UUID
 
-from fastapi import FastAPI, HTTPException, Query, Request, status
+from fastapi import FastAPI, HTTPException, Query, Request, Response, status
 from pydantic import BaseModel, Field
 
+from ._capi import format_f32_json
 from .interfaces import VectorDTO
 
 
@@ -110,6 +112,23 @@ def _constraints(raw: Optional[Dict[str, Any]]) -> Optional[Dict[str, Any]]:
     return out
 
 
+def _encode_hits(hits) -> bytes:
+    """The ``List[VectorSearchResult]`` JSON of the reference (rest_api.py:28-32,163), written directly: the k x d
+    stored values go through ``mlv_format_f32_json`` (shortest float32 text, C speed) instead of pydantic
+    validation + ``json.dumps`` of k x d Python floats, which costs several ms per response at d = 768."""
+    parts = []
+    for h in hits:
+        values = h.get("values")
+        parts.append(b'{"id":"%s","values":%s,"metadata":%s,"score":%s}' % (
+            str(h["id"]).encode(), format_f32_json(values) if values is not None and len(values) else b"[]",
+            json.dumps(h.get("metadata") or {}, default=str).encode(), json.dumps(float(h["score"])).encode()))
+    return b"[" + b",".join(parts) + b"]"
+
+
+def _json(payload: bytes) -> Response:
+    return Response(content=payload, media_type="application/json")
+
+
 class GpuRestAPI:
     def __init__(self, query_processor, title: str = "Vector DB API", enable_file_logging: bool = False,
                  log_level: str = "INFO"):
@@ -179,15 +198,17 @@ class GpuRestAPI:
         async def search_similar(search_request: VectorSearchRequest, namespace: str = Query("default")):
             try:
                 r = search_request
-                return self._search(r.query, r.top_k, namespace, r.metric, _constraints(r.filter), r.radius, r.include_values)
+                return _json(_encode_hits(self._search(r.query, r.top_k, namespace, r.metric, _constraints(r.filter), r.radius,
+                                                       r.include_values)))
             except Exception as e:  # noqa: BLE001
                 self._fail("Search failed", e)
 
         @app.post("/search/batch", response_model=List[List[VectorSearchResult]])
         async def search_batch(batch: BatchSearchRequest, namespace: str = Query("default")):
             try:
-                return qp.find_similar_batch(batch.queries, batch.top_k, namespace=namespace, metric=batch.metric,
-                                             filter=_constraints(batch.filter), enrich=batch.include_values)
+                per_query = qp.find_similar_batch(batch.queries, batch.top_k, namespace=namespace, metric=batch.metric,
+                                                  filter=_constraints(batch.filter), enrich=batch.include_values)
+                return _json(b"[" + b",".join(_encode_hits(hits) for hits in per_query) + b"]")
             except Exception as e:  # noqa: BLE001
                 self._fail("Batch search failed", e)
 
@@ -252,7 +273,7 @@ class GpuRestAPI:
                         raise HTTPException(status_code=status.HTTP_400_BAD_REQUEST, detail="filter is required")
                     hits = self._search(req.vector, req.k, req.namespace, req.metric, _constraints(req.filter), radius,
                                         req.include_values)
-                    return {"type": kind, "count": len(hits), "results": [VectorSearchResult(**h).model_dump(mode="json") for h in hits]}
+                    return _json(b'{"type":"%s","count":%d,"results":%s}' % (kind.encode(), len(hits), _encode_hits(hits)))
                 except HTTPException:
                     raise
                 except Exception as e:  # noqa: BLE001

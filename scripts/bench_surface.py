@@ -102,6 +102,18 @@ t = time.perf_counter() - t0
 emit(what="ingest", path="GpuIndex.add_matrix (index only: H2D append + normalise + column)", rows=a.rows,
      rows_per_s=round(a.rows / t), GBps=round(a.rows * a.dim * 4 / t / 1e9, 3))
 
+from mlvectordb_b200 import DeviceShard  # noqa: E402
+for staged in (0, 1):
+    sh = DeviceShard(a.dim, "cosine", capacity=a.rows)
+    sh.set_tuning("staged_upload", staged)
+    sh.add(X[:1000])
+    t0 = time.perf_counter()
+    sh.add(X[1000:])
+    t = time.perf_counter() - t0
+    emit(what="ingest", path="C ABI mlv_index_add, pageable host rows, " + ("two pinned chunks filled by worker threads" if staged
+         else "plain cudaMemcpy2D"), rows=a.rows - 1000, rows_per_s=round((a.rows - 1000) / t), GBps=round((a.rows - 1000) * a.dim * 4 / t / 1e9, 2))
+    sh.close()
+
 # ---- search through the layers ---------------------------------------------------------------------------
 Q = synthetic.queries(43, a.reps + 1, a.dim)
 shard = index._ns["bulk"].shard

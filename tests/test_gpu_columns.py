@@ -200,3 +200,24 @@ def test_bulk_columns_and_snapshot_round_trip(tmp_path):
     back.remove([victim], "big")
     assert victim not in {r.vector_id for r in back.search(VectorDTO(values=Q[0], metadata={}), k, "big", "cosine")}
     back.close()
+
+
+@pytest.mark.parametrize("dim", [70, 768])
+def test_bulk_upload_through_pinned_staging_is_exact(dim):
+    """``mlv_index_add`` of a large block goes through two pinned chunks filled by worker threads
+    (``upload_rows_staged``); what lands in HBM equals the plain copy path and the input, bit for bit."""
+    from mlvectordb_b200 import DeviceShard
+    n = 300_000 if dim == 70 else 60_000          # 84 MB / 184 MB: several 48 MB chunks, ragged last chunk
+    X = synthetic.rows(77, 0, n, dim)
+    a = DeviceShard(dim, "l2")
+    a.add(X[:1000])                               # small block: direct copy
+    a.add(X[1000:])                               # staged
+    b = DeviceShard(dim, "l2")
+    b.set_tuning("staged_upload", 0)
+    b.add(X)
+    got = a.export_rows()
+    assert np.array_equal(got, X) and np.array_equal(b.export_rows(), X)
+    Q = synthetic.queries(78, 3, dim)
+    assert _same(a.search(Q, 10), b.search(Q, 10))
+    a.close()
+    b.close()
