@@ -426,9 +426,7 @@ int mlv_filter_create_where(mlv_index_t h, const mlv_predicate_t* preds, uint32_
         const uint32_t c = preds[i].column;
         args.p[i].col = (const int32_t*)h->d_cols[c].p;     // never written: every row is missing
         args.p[i].col_rows = h->d_cols[c].p ? h->col_rows[c] : 0;
-        args.p[i].op = preds[i].op;
-        args.p[i].a = preds[i].a;
-        args.p[i].b = preds[i].b;
+        where_range(preds[i].op, preds[i].a, preds[i].b, &args.p[i]);
     }
     DeviceGuard g(h->device);
     const uint64_t n_words = (h->rows + 31) / 32;
@@ -436,9 +434,9 @@ int mlv_filter_create_where(mlv_index_t h, const mlv_predicate_t* preds, uint32_
     if (!f) return MLV_E_NOMEM;
     int rc = ensure_dev(h, f->d_bitmap, std::max<uint64_t>(n_words, 1) * 4);
     if (rc == MLV_OK && n_words) {
-        constexpr int WPS = 4;
-        const uint64_t warps = (n_words + WPS - 1) / WPS;
-        where_kernel<WPS><<<grid_for(h, warps, 8), 256, 0, h->stream>>>(args, h->rows, (uint32_t*)f->d_bitmap.p);
+        constexpr int GROUPS = 4;   // 4 x 128 rows per warp step
+        const uint64_t warps = ((h->rows + 127) / 128 + GROUPS - 1) / GROUPS;
+        where_kernel<GROUPS><<<grid_for(h, warps, 8), 256, 0, h->stream>>>(args, h->rows, (uint32_t*)f->d_bitmap.p);
         h->launches++;
         cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess) rc = fail_cuda(h, e, "where_kernel");

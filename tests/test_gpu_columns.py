@@ -26,6 +26,9 @@ PREDICATE_SETS = [
     [(0, "==", 7)], [(0, "!=", 7)], [(0, "<", 10)], [(0, "<=", 10)], [(0, ">", 90)], [(0, ">=", 90)], [(0, "between", 20, 29)],
     [(0, "between", 5, 4)], [(1, "==", -3)], [(0, "<", 50), (1, ">=", 0)], [(0, ">=", 10), (0, "<", 60), (1, "!=", 2), (2, "==", 1)],
     [(5, "==", 0)], [(2, ">=", -(2 ** 31) + 1)], [],
+    # the ends of the int32 range and the missing code itself
+    [(0, "<", -(2 ** 31))], [(0, ">", 2 ** 31 - 1)], [(1, "!=", -(2 ** 31))], [(1, "==", -(2 ** 31))], [(1, ">=", -(2 ** 31))],
+    [(1, "<=", 2 ** 31 - 1)], [(1, "between", -(2 ** 31), 0)], [(1, "<=", -(2 ** 31))], [(1, "between", 3, 2 ** 31 - 1)],
 ]
 
 
