@@ -317,11 +317,13 @@ int mlv_index_set_tuning(mlv_index_t h, const char *key, int value);
  */
 int mlv_index_debug_timeline(mlv_index_t h, uint64_t *out, uint32_t max_ctas, uint32_t *n_ctas);
 /*
- * Tensor-core batch path (csrc/gemm_kernel.cuh): searches with nq >= 9 queries (more than one scan pass) on >= 16384 rows
- * run as a tcgen05 3xTF32 GEMM that selects k + slack candidates per query, re-scores them in the
- * reference's arithmetic and certifies the result; queries that fail the certificate are re-run
- * by the exact scan, so results do not depend on the path.  set_tuning keys: "gemm" (-1 auto,
- * 0 never, 1 whenever the shape allows), "gemm_min_nq".  This call returns cumulative counters
+ * Tensor-core batch path (csrc/gemm_kernel.cuh): searches with nq >= 5 queries on a matrix of >= 1 GB (nq >= 9 on >= 16384 rows otherwise)
+ * run as a tcgen05 GEMM that selects k + slack candidates per query, re-scores them in the
+ * reference's arithmetic and certifies the result.  Two tiers: a one-pass TF32 GEMM (a third of the
+ * tensor work, coarser approximate distances, wider slack), then the 3xTF32 GEMM for the queries the
+ * first tier could not certify; what neither certifies is re-run by the exact scan, so results do
+ * not depend on the path.  set_tuning keys: "gemm" (-1 auto, 0 never, 1 whenever the shape
+ * allows), "gemm_min_nq", "gemm_passes" (0 both tiers, 1 one-pass tier then scan, 3 3xTF32 tier only).  This call returns cumulative counters
  * and, when timing is enabled, the summed device time of the GEMM launches since the last call.
  */
 typedef struct mlv_gemm_stats {
@@ -331,6 +333,7 @@ typedef struct mlv_gemm_stats {
     uint64_t queries;             /* queries in those batches */
     uint64_t fallback_queries;    /* of those, re-run by the scan (certificate failed / buffer overflow) */
     uint64_t rounds;              /* GEMM launches (one per round) */
+    uint64_t fast_queries;        /* of `queries`, certified by the one-pass TF32 tier (no 3xTF32 work spent on them) */
 } mlv_gemm_stats_t;
 int mlv_index_gemm_stats(mlv_index_t h, mlv_gemm_stats_t *out);
 /*

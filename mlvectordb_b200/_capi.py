@@ -42,6 +42,7 @@ class GemmStats(C.Structure):
         ("queries", C.c_uint64),
         ("fallback_queries", C.c_uint64),
         ("rounds", C.c_uint64),
+        ("fast_queries", C.c_uint64),
     ]
 
 

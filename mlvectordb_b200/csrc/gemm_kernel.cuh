@@ -42,16 +42,28 @@ constexpr uint32_t GEMM_X_BYTES = GEMM_BM * GEMM_BK * 4;   // 16 KB
 // Three shapes: BN = 256 queries per tile with a 2-stage ring (96 KB stages) for large batches (tensor-
 // bound); BN = 128 / 3 stages and BN = 64 / 4 stages for small batches, where a pass over the rows
 // is HBM-bound and padding the query tile to 256 columns would only burn tensor time.
-template <int BN>
+//
+// PASSES = 3 is the 3xTF32 split described above.  PASSES = 1 is the fast first tier: ONE kind::tf32 MMA per K
+// step on the raw fp32 tiles (the tensor core reads the top 19 bits of each operand, i.e. the same truncation as
+// `hi`), no split of X, no Qlo tile -- a third of the tensor work and 60 % of the shared-memory fill.  Its
+// approximate distances are coarser (|a - exact| <= 2^-9 |x||q| instead of 2^-13), which the certificate
+// accounts for with a larger delta and the host with a larger candidate slack; queries it cannot certify are
+// re-run by the PASSES = 3 tier, and only what that cannot certify either goes to the scan.
+template <int BN, int PASSES = 3>
 struct GemmShape {
-    static constexpr int STAGES = BN == 256 ? 2 : (BN == 128 ? 3 : 4);
     static constexpr uint32_t Q_BYTES = BN * GEMM_BK * 4;
-    static constexpr uint32_t STAGE_BYTES = 2 * GEMM_X_BYTES + 2 * Q_BYTES;
+    static constexpr uint32_t STAGE_BYTES = PASSES == 3 ? 2 * GEMM_X_BYTES + 2 * Q_BYTES : GEMM_X_BYTES + Q_BYTES;
+    static constexpr int STAGES = PASSES == 3 ? (BN == 256 ? 2 : (BN == 128 ? 3 : 4)) : (BN == 256 ? 4 : 6);
     static constexpr uint32_t SMEM_BYTES = 1024 + STAGES * STAGE_BYTES + 2 * BN * 4 + 256;
     // kind::tf32, fp32 accumulate, A and B K-major, M = 128, N = BN
     static constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(GEMM_BM >> 4) << 24);
 };
-constexpr float GEMM_DELTA_REL = 1.220703125e-4f;  // 2^-13: bound on |a - exact| / scale (see rerank_kernel)
+constexpr float GEMM_DELTA_REL = 1.220703125e-4f;  // 2^-13: bound on |a - exact| / scale (see rerank_kernel), PASSES = 3
+// PASSES = 1: both operands truncated to 10 explicit mantissa bits -> |x~q~ - xq| < 2^-9 |xq|, so the dot product is
+// off by < 2^-9 |x||q| (Cauchy-Schwarz) plus the fp32 accumulation error, far below the 12.5 % margin taken here.
+// ip / cosine: a = 1 - dot, scale = |x|max |q|.  l2: a = |x|^2 + |q|^2 - 2 dot is off by < 2^-8 |x||q| <= 2^-10 (|x|max + |q|)^2.
+constexpr float GEMM_DELTA_REL_1PASS_IP = 1.125f * 1.953125e-3f;    // 1.125 * 2^-9
+constexpr float GEMM_DELTA_REL_1PASS_L2 = 1.125f * 9.765625e-4f;    // 1.125 * 2^-10
 
 struct GemmParams {
     uint32_t n_rows;
@@ -120,14 +132,16 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
 }
 
 // ---- the GEMM + candidate-selection kernel ---------------------------------------------------
-template <int METRIC, int GEMM_BN>
+template <int METRIC, int GEMM_BN, int PASSES>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_topk_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_qhi,
                  const __grid_constant__ CUtensorMap tm_qlo, const GemmParams p) {
-    constexpr int GEMM_STAGES = GemmShape<GEMM_BN>::STAGES;
-    constexpr uint32_t GEMM_Q_BYTES = GemmShape<GEMM_BN>::Q_BYTES;
-    constexpr uint32_t GEMM_STAGE_BYTES = GemmShape<GEMM_BN>::STAGE_BYTES;
-    constexpr uint32_t GEMM_IDESC = GemmShape<GEMM_BN>::IDESC;
+    constexpr int GEMM_STAGES = GemmShape<GEMM_BN, PASSES>::STAGES;
+    constexpr uint32_t GEMM_Q_BYTES = GemmShape<GEMM_BN, PASSES>::Q_BYTES;
+    constexpr uint32_t GEMM_STAGE_BYTES = GemmShape<GEMM_BN, PASSES>::STAGE_BYTES;
+    constexpr uint32_t GEMM_IDESC = GemmShape<GEMM_BN, PASSES>::IDESC;
+    // stage layout: PASSES = 3: Xhi | Xlo | Qhi | Qlo;  PASSES = 1: X | Q
+    constexpr uint32_t GEMM_Q_OFF = PASSES == 3 ? 2 * GEMM_X_BYTES : GEMM_X_BYTES;
     extern __shared__ unsigned char gemm_smem_raw[];
     // SWIZZLE_128B tiles need 1024-byte alignment
     unsigned char* smem = gemm_smem_raw + ((1024u - (smem_u32(gemm_smem_raw) & 1023u)) & 1023u);
@@ -181,11 +195,12 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
                 for (uint32_t kc = 0; kc < p.n_kchunks; kc++) {
                     mbar_wait(&empty[stage], phase ^ 1);
                     unsigned char* sb = smem + (size_t)stage * GEMM_STAGE_BYTES;
-                    mbar_arrive_expect_tx(&full[stage], GEMM_X_BYTES + 2 * GEMM_Q_BYTES);
+                    mbar_arrive_expect_tx(&full[stage], GEMM_X_BYTES + (PASSES == 3 ? 2 : 1) * GEMM_Q_BYTES);
                     tma_load_2d(sb, &tm_x, (int32_t)(kc * GEMM_BK), (int32_t)(rt * GEMM_BM), &full[stage]);
-                    tma_load_2d(sb + 2 * GEMM_X_BYTES, &tm_qhi, (int32_t)(kc * GEMM_BK), (int32_t)(qt * GEMM_BN), &full[stage]);
-                    tma_load_2d(sb + 2 * GEMM_X_BYTES + GEMM_Q_BYTES, &tm_qlo, (int32_t)(kc * GEMM_BK), (int32_t)(qt * GEMM_BN),
-                                &full[stage]);
+                    tma_load_2d(sb + GEMM_Q_OFF, &tm_qhi, (int32_t)(kc * GEMM_BK), (int32_t)(qt * GEMM_BN), &full[stage]);
+                    if (PASSES == 3)
+                        tma_load_2d(sb + GEMM_Q_OFF + GEMM_Q_BYTES, &tm_qlo, (int32_t)(kc * GEMM_BK), (int32_t)(qt * GEMM_BN),
+                                    &full[stage]);
                     if (++stage == GEMM_STAGES) {
                         stage = 0;
                         phase ^= 1;
@@ -204,20 +219,25 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
                 const uint32_t tmem_d = tmem_base + acc * GEMM_BN;
                 for (uint32_t kc = 0; kc < p.n_kchunks; kc++) {
                     mbar_wait(&full[stage], phase);
-                    mbar_wait(&conv[stage], phase);
+                    if (PASSES == 3) mbar_wait(&conv[stage], phase);
                     tc_fence_after();
                     const uint32_t sb = smem_u32(smem + (size_t)stage * GEMM_STAGE_BYTES);
                     const uint64_t d_xhi = umma_desc_sw128(sb);
                     const uint64_t d_xlo = umma_desc_sw128(sb + GEMM_X_BYTES);
-                    const uint64_t d_qhi = umma_desc_sw128(sb + 2 * GEMM_X_BYTES);
-                    const uint64_t d_qlo = umma_desc_sw128(sb + 2 * GEMM_X_BYTES + GEMM_Q_BYTES);
+                    const uint64_t d_qhi = umma_desc_sw128(sb + GEMM_Q_OFF);
+                    const uint64_t d_qlo = umma_desc_sw128(sb + GEMM_Q_OFF + GEMM_Q_BYTES);
 #pragma unroll
                     for (uint32_t ks = 0; ks < GEMM_BK / 8; ks++) {
                         const uint64_t adv = (uint64_t)(ks * 2);  // 8 floats = 32 bytes = 2 x 16-byte units
-                        // small terms first, the dominant hi.hi product last
-                        tc_mma_tf32(tmem_d, d_xlo + adv, d_qhi + adv, GEMM_IDESC, (kc | ks) != 0);
-                        tc_mma_tf32(tmem_d, d_xhi + adv, d_qlo + adv, GEMM_IDESC, 1);
-                        tc_mma_tf32(tmem_d, d_xhi + adv, d_qhi + adv, GEMM_IDESC, 1);
+                        if (PASSES == 3) {
+                            // small terms first, the dominant hi.hi product last
+                            tc_mma_tf32(tmem_d, d_xlo + adv, d_qhi + adv, GEMM_IDESC, (kc | ks) != 0);
+                            tc_mma_tf32(tmem_d, d_xhi + adv, d_qlo + adv, GEMM_IDESC, 1);
+                            tc_mma_tf32(tmem_d, d_xhi + adv, d_qhi + adv, GEMM_IDESC, 1);
+                        } else {
+                            // raw fp32 tiles: the tensor core truncates both operands to TF32 itself
+                            tc_mma_tf32(tmem_d, d_xhi + adv, d_qhi + adv, GEMM_IDESC, (kc | ks) != 0);
+                        }
                     }
                     tc_commit(&empty[stage]);  // stage reusable once these MMAs have read it
                     if (++stage == GEMM_STAGES) {
@@ -229,10 +249,10 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
             }
         }
     } else if (warp < 6) {
-        // ------------------------------------------------------------------ hi/lo split of X
+        // ------------------------------------------------------------------ hi/lo split of X (PASSES = 3 only)
         const int ct = tid - 64;  // 0..127
         uint32_t stage = 0, phase = 0;
-        for (uint32_t it = blockIdx.x; it < n_items; it += gridDim.x) {
+        for (uint32_t it = blockIdx.x; PASSES == 3 && it < n_items; it += gridDim.x) {
             for (uint32_t kc = 0; kc < p.n_kchunks; kc++) {
                 mbar_wait(&full[stage], phase);
                 uint4* xh = reinterpret_cast<uint4*>(smem + (size_t)stage * GEMM_STAGE_BYTES);
@@ -320,6 +340,29 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
 }
 
 // ---- helpers around the GEMM -------------------------------------------------------------------
+// second tier works on the queries the first could not certify: dst[i] = src[idx[i]] (rows of ld floats)
+__global__ void gather_queries_kernel(const float* __restrict__ src, const uint32_t* __restrict__ idx, float* __restrict__ dst,
+                                      uint32_t n, uint32_t ld) {
+    const uint32_t total = n * ld;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        const uint32_t r = i / ld;
+        dst[i] = src[(size_t)idx[r] * ld + (i - r * ld)];
+    }
+}
+// ... and its results go back to the queries' own slots: dst[idx[i]] = src[i]
+__global__ void scatter_results_kernel(const uint32_t* __restrict__ idx, uint32_t n, uint32_t k, const float* __restrict__ sd,
+                                       const int64_t* __restrict__ sr, const int32_t* __restrict__ sc, float* __restrict__ dd,
+                                       int64_t* __restrict__ dr, int32_t* __restrict__ dc) {
+    const uint32_t total = n * k;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        const uint32_t r = i / k, j = i - r * k;
+        const size_t o = (size_t)idx[r] * k + j;
+        dd[o] = sd[i];
+        dr[o] = sr[i];
+        if (j == 0) dc[idx[r]] = sc[r];
+    }
+}
+
 // |x|^2 per row (one warp per row) and the running maximum (non-negative floats order as uints).
 __global__ void row_norms_kernel(const float* __restrict__ rows, uint64_t first, uint64_t n, uint32_t ld, float* norms,
                                  uint32_t* max_norm2_bits) {
@@ -411,6 +454,7 @@ struct RerankParams {
     int32_t* out_counts;
     uint64_t row_base;
     int metric;  // MLV metric: 0 l2, 1 ip, 2 cosine
+    float delta_rel;  // bound on |a - exact| / scale of the GEMM tier that selected the candidates
 };
 
 // One CTA per query: exact reference-form distances of the candidates with the scan kernel's
@@ -464,7 +508,7 @@ __global__ void __launch_bounds__(256, 1) rerank_kernel(const RerankParams p) {
                 const float qs = sqrtf(qn);
                 scale = (p.metric == 0) ? (xmax + qs) * (xmax + qs) : xmax * qs;
             }
-            const float delta = GEMM_DELTA_REL * scale;
+            const float delta = p.delta_rel * scale;
             const float a_last = key_dist(mine[p.kprime - 1]);  // largest approximate distance kept
             const float e_k = key_dist(a[p.k - 1]);             // exact k-th best among the candidates
             certified = (a_last - delta > e_k);                 // false for NaN

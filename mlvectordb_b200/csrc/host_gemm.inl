@@ -54,12 +54,23 @@ uint32_t gemm_kprime(uint32_t k) {
     return (k + slack + 31) & ~31u;
 }
 
+bool gemm_1pass_ok(const mlv_index* h, uint32_t k);
+
+// Smallest batch the tensor-core path takes.  With the one-pass tier a pass over a >= 1 GB matrix costs 1.1x a
+// one-query scan (10M x 768: 4.57 ms vs 4.17 ms), less than the scan's 5 .. 8-query pass (5.4 - 5.6 ms): measured
+// crossover nq = 5 at 1M and 10M rows.  The 3xTF32 tier alone needs more than one 8-query scan pass to pay off.
+uint32_t gemm_min_nq(const mlv_index* h, uint32_t k) {
+    if (h->tune_gemm_min_nq > 0) return (uint32_t)h->tune_gemm_min_nq;
+    const bool big = (uint64_t)h->rows * h->ld * 4 >= (1ull << 30);
+    return gemm_1pass_ok(h, k) && big ? 5u : 9u;
+}
+
 bool gemm_eligible(const mlv_index* h, uint32_t nq, uint32_t k) {
     if (h->tune_gemm == 0) return false;
     if (h->ld < (uint32_t)GEMM_BK) return false;
     if (gemm_kprime(k) * 4 > SELECT_MAX_P) return false;
     if (h->tune_gemm == 1) return true;
-    return nq >= (uint32_t)std::max(h->tune_gemm_min_nq, 1) && h->rows >= 16384;
+    return nq >= gemm_min_nq(h, k) && h->rows >= 16384;
 }
 
 int ensure_row_norms(mlv_index* h, cudaStream_t st) {
@@ -87,33 +98,47 @@ int ensure_row_norms(mlv_index* h, cudaStream_t st) {
     return MLV_OK;
 }
 
-template <int METRIC, int BN>
+template <int METRIC, int BN, int PASSES>
 cudaError_t launch_gemm_tt(const CUtensorMap& mx, const CUtensorMap& mqh, const CUtensorMap& mql, const GemmParams& gp, int grid,
                            cudaStream_t st) {
-    auto kern = gemm_topk_kernel<METRIC, BN>;
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GemmShape<BN>::SMEM_BYTES);
+    auto kern = gemm_topk_kernel<METRIC, BN, PASSES>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GemmShape<BN, PASSES>::SMEM_BYTES);
     if (e != cudaSuccess) return e;
-    kern<<<grid, GEMM_THREADS, GemmShape<BN>::SMEM_BYTES, st>>>(mx, mqh, mql, gp);
+    kern<<<grid, GEMM_THREADS, GemmShape<BN, PASSES>::SMEM_BYTES, st>>>(mx, mqh, mql, gp);
     return cudaGetLastError();
+}
+template <int METRIC, int PASSES>
+cudaError_t launch_gemm_tp(const CUtensorMap& mx, const CUtensorMap& mqh, const CUtensorMap& mql, const GemmParams& gp, int grid,
+                           cudaStream_t st, int bn) {
+    if (bn == 64) return launch_gemm_tt<METRIC, 64, PASSES>(mx, mqh, mql, gp, grid, st);
+    if (bn == 128) return launch_gemm_tt<METRIC, 128, PASSES>(mx, mqh, mql, gp, grid, st);
+    return launch_gemm_tt<METRIC, 256, PASSES>(mx, mqh, mql, gp, grid, st);
 }
 template <int METRIC>
 cudaError_t launch_gemm_t(const CUtensorMap& mx, const CUtensorMap& mqh, const CUtensorMap& mql, const GemmParams& gp, int grid,
-                          cudaStream_t st, int bn) {
-    if (bn == 64) return launch_gemm_tt<METRIC, 64>(mx, mqh, mql, gp, grid, st);
-    if (bn == 128) return launch_gemm_tt<METRIC, 128>(mx, mqh, mql, gp, grid, st);
-    return launch_gemm_tt<METRIC, 256>(mx, mqh, mql, gp, grid, st);
+                          cudaStream_t st, int bn, int passes = 3) {
+    return passes == 1 ? launch_gemm_tp<METRIC, 1>(mx, mqh, mql, gp, grid, st, bn) : launch_gemm_tp<METRIC, 3>(mx, mqh, mql, gp, grid, st, bn);
 }
 
-// Large batches: tcgen05 GEMM selects k' candidates per query in geometrically growing rounds,
-// rerank_kernel scores them in the reference's arithmetic and certifies; uncertified queries are
-// re-run by the exact scan.  Synchronises `st` once (to read the per-query flags).
-int search_gemm(mlv_index* h, const float* qprep, uint32_t nq, uint32_t k, const uint32_t* filter_dev, float* out_d,
-                int64_t* out_r, int32_t* out_c, cudaStream_t st) {
+// candidates kept per query by the fast tier: its approximate distances are 16x coarser, so the exact k-th best must
+// clear a wider margin below the k'-th approximate distance -- twice k (at least k + 64)
+uint32_t gemm_kprime_1pass(uint32_t k) { return (std::max<uint32_t>(2 * k, k + 64) + 31) & ~31u; }
+
+bool gemm_1pass_ok(const mlv_index* h, uint32_t k) {
+    if (h->tune_gemm_passes == 3) return false;
+    return gemm_kprime_1pass(k) * 4 <= SELECT_MAX_P;
+}
+
+// One tier of the batch path: tcgen05 GEMM (PASSES = 1 or 3) selects k' candidates per query in geometrically growing
+// rounds, rerank_kernel scores them in the reference's arithmetic and certifies.  hflags[q] != 0 = not certified
+// (or the candidate buffer overflowed): the caller re-runs those queries.  Synchronises `st` once (to read the flags).
+int search_gemm_tier(mlv_index* h, const float* qprep, uint32_t nq, uint32_t k, int passes, const uint32_t* filter_dev, float* out_d,
+                     int64_t* out_r, int32_t* out_c, cudaStream_t st, std::vector<uint32_t>& hflags) {
     int rc;
     const uint32_t ld = h->ld;
     const uint32_t GEMM_BN = gemm_tile_width(h, nq);
     const uint32_t nq_pad = (nq + GEMM_BN - 1) / GEMM_BN * GEMM_BN;
-    const uint32_t kprime = gemm_kprime(k);
+    const uint32_t kprime = passes == 1 ? gemm_kprime_1pass(k) : gemm_kprime(k);
     const uint32_t cap = std::min<uint32_t>(SELECT_MAX_P, pow2_ceil(8 * kprime));
     const uint32_t P = cap;  // power of two
     const bool l2 = h->metric == MLV_L2;
@@ -190,8 +215,8 @@ int search_gemm(mlv_index* h, const float* qprep, uint32_t nq, uint32_t k, const
             }
             cudaEventRecord(e0, st);
         }
-        CK(h, l2 ? launch_gemm_t<METRIC_L2>(mx, mqh, mql, gp, grid, st, (int)GEMM_BN)
-                 : launch_gemm_t<METRIC_IP>(mx, mqh, mql, gp, grid, st, (int)GEMM_BN));
+        CK(h, l2 ? launch_gemm_t<METRIC_L2>(mx, mqh, mql, gp, grid, st, (int)GEMM_BN, passes)
+                 : launch_gemm_t<METRIC_IP>(mx, mqh, mql, gp, grid, st, (int)GEMM_BN, passes));
         if (h->timing) {
             cudaEventRecord(e1, st);
             h->gemm_pending.emplace_back(e0, e1);
@@ -222,6 +247,7 @@ int search_gemm(mlv_index* h, const float* qprep, uint32_t nq, uint32_t k, const
     rp.out_counts = out_c;
     rp.row_base = h->row_base;
     rp.metric = h->metric;
+    rp.delta_rel = passes == 1 ? (l2 ? GEMM_DELTA_REL_1PASS_L2 : GEMM_DELTA_REL_1PASS_IP) : GEMM_DELTA_REL;
     if (l2)
         rerank_kernel<METRIC_L2><<<nq, 256, (size_t)rp.P * 8, st>>>(rp);
     else
@@ -229,14 +255,57 @@ int search_gemm(mlv_index* h, const float* qprep, uint32_t nq, uint32_t k, const
     h->launches++;
     CK(h, cudaGetLastError());
 
-    // certificate check: the one synchronisation of this path
-    std::vector<uint32_t> hflags(nq);
+    // certificate check: the one synchronisation of this tier
+    hflags.resize(nq);
     CK(h, cudaMemcpyAsync(hflags.data(), flags, (size_t)nq * 4, cudaMemcpyDeviceToHost, st));
     CK(h, cudaStreamSynchronize(st));
+    return MLV_OK;
+}
+
+// Large batches.  Tier 1: one-pass TF32 GEMM (a third of the tensor work) with a wide candidate slack; tier 2: the
+// 3xTF32 GEMM for the queries tier 1 could not certify; what neither certifies is re-run by the exact scan.  Every
+// tier ends in the same exact re-rank, so results never depend on which tier answered.
+int search_gemm(mlv_index* h, const float* qprep, uint32_t nq, uint32_t k, const uint32_t* filter_dev, float* out_d,
+                int64_t* out_r, int32_t* out_c, cudaStream_t st) {
+    int rc;
+    const uint32_t ld = h->ld;
+    std::vector<uint32_t> hflags;
+    std::vector<uint32_t> failing;
     h->gemm_searches++;
     h->gemm_queries += nq;
-    for (uint32_t q = 0; q < nq; q++) {
-        if (!hflags[q]) continue;
+    const bool fast = gemm_1pass_ok(h, k);
+    if ((rc = search_gemm_tier(h, qprep, nq, k, fast ? 1 : 3, filter_dev, out_d, out_r, out_c, st, hflags)) != MLV_OK) return rc;
+    for (uint32_t q = 0; q < nq; q++)
+        if (hflags[q]) failing.push_back(q);
+    if (fast) {
+        h->gemm_fast_queries += nq - failing.size();
+        if (!failing.empty() && h->tune_gemm_passes != 1) {
+            // second tier on the compacted failing queries; results scattered back to their slots
+            const uint32_t nf = (uint32_t)failing.size();
+            const size_t need = (size_t)nf * 4 + (size_t)nf * ld * 4 + (size_t)nf * k * 12 + (size_t)nf * 4 + 64;
+            if ((rc = ensure_dev(h, h->d_sub, need)) != MLV_OK) return rc;
+            uint32_t* d_idx = (uint32_t*)h->d_sub.p;
+            float* sub_q = (float*)(d_idx + ((nf + 3) & ~3u));
+            int64_t* sub_r = (int64_t*)(sub_q + (size_t)nf * ld + ((size_t)nf * ld & 1));
+            float* sub_d = (float*)(sub_r + (size_t)nf * k);
+            int32_t* sub_c = (int32_t*)(sub_d + (size_t)nf * k);
+            CK(h, cudaMemcpyAsync(d_idx, failing.data(), (size_t)nf * 4, cudaMemcpyHostToDevice, st));
+            gather_queries_kernel<<<(unsigned)std::min<uint64_t>(((uint64_t)nf * ld + 255) / 256, 2048), 256, 0, st>>>(qprep, d_idx, sub_q, nf, ld);
+            h->launches++;
+            CK(h, cudaGetLastError());
+            std::vector<uint32_t> f2;
+            if ((rc = search_gemm_tier(h, sub_q, nf, k, 3, filter_dev, sub_d, sub_r, sub_c, st, f2)) != MLV_OK) return rc;
+            scatter_results_kernel<<<(unsigned)std::min<uint64_t>(((uint64_t)nf * k + 255) / 256, 2048), 256, 0, st>>>(
+                d_idx, nf, k, sub_d, sub_r, sub_c, out_d, out_r, out_c);
+            h->launches++;
+            CK(h, cudaGetLastError());
+            std::vector<uint32_t> still;
+            for (uint32_t i = 0; i < nf; i++)
+                if (f2[i]) still.push_back(failing[i]);
+            failing.swap(still);
+        }
+    }
+    for (uint32_t q : failing) {
         h->gemm_fallback_queries++;
         rc = search_prepared(h, qprep + (size_t)q * ld, 1, k, filter_dev, out_d + (size_t)q * k, out_r + (size_t)q * k, out_c + q, st);
         if (rc != MLV_OK) return rc;

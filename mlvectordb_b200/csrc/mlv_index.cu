@@ -87,6 +87,7 @@ int mlv_index_create(uint32_t dim, int metric, uint64_t capacity_hint, int devic
     h->tune_gemm = env_int("MLV_GEMM", h->tune_gemm);
     h->tune_gemm_min_nq = env_int("MLV_GEMM_MIN_NQ", h->tune_gemm_min_nq);
     h->tune_gemm_bn = env_int("MLV_GEMM_BN", h->tune_gemm_bn);
+    h->tune_gemm_passes = env_int("MLV_GEMM_PASSES", h->tune_gemm_passes);
     DeviceGuard g(device);
     cudaDeviceProp prop;
     cudaError_t e = g.ok ? cudaGetDeviceProperties(&prop, device) : cudaErrorInvalidDevice;
@@ -123,7 +124,7 @@ int mlv_index_destroy(mlv_index_t h) {
     if (h->d_rows) cudaFree(h->d_rows);
     if (h->d_live) cudaFree(h->d_live);
     for (DevBuf* b : {&h->d_qraw, &h->d_filter, &h->d_outd, &h->d_outr, &h->d_outc, &h->d_misc, &h->d_range, &h->d_timeline,
-                      &h->d_norms, &h->d_gq, &h->d_cand, &h->d_maxn2})
+                      &h->d_norms, &h->d_gq, &h->d_cand, &h->d_maxn2, &h->d_sub})
         free_dev(*b);
     for (Lane& l : h->lanes)
         for (DevBuf* b : {&l.d_q, &l.d_keys0, &l.d_keys1, &l.d_sched, &l.d_flist, &l.d_fscratch}) free_dev(*b);
@@ -175,6 +176,7 @@ int mlv_index_set_tuning(mlv_index_t h, const char* key, int value) {
     else if (k == "gemm_min_nq") h->tune_gemm_min_nq = value;
     else if (k == "gemm_bn") h->tune_gemm_bn = value;
     else if (k == "staged_upload") h->tune_staged_upload = value;
+    else if (k == "gemm_passes") h->tune_gemm_passes = value;
     else return fail(h, MLV_E_INVALID, "unknown tuning key " + k);
     return MLV_OK;
 }
@@ -1013,6 +1015,7 @@ int mlv_index_gemm_stats(mlv_index_t h, mlv_gemm_stats_t* out) {
     out->searches = h->gemm_searches;
     out->queries = h->gemm_queries;
     out->fallback_queries = h->gemm_fallback_queries;
+    out->fast_queries = h->gemm_fast_queries;
     out->rounds = h->gemm_rounds;
     return MLV_OK;
 }

@@ -31,6 +31,7 @@ def main():
     ap.add_argument("--reps", type=int, default=3)
     ap.add_argument("--paths", default="gemm,scan")
     ap.add_argument("--scan-nq", type=int, default=256, help="queries used to time the scan path (it is slow)")
+    ap.add_argument("--passes", type=int, default=0, help="gemm_passes tuning: 0 = one-pass tier then 3xTF32 (default), 1, 3")
     a = ap.parse_args()
     s = DeviceShard(a.dim, a.space, capacity=a.rows)
     t0 = time.time()
@@ -42,6 +43,7 @@ def main():
     for path in a.paths.split(","):
         gemm = path == "gemm"
         s.set_tuning("gemm", 1 if gemm else 0)
+        s.set_tuning("gemm_passes", a.passes)
         q = Q if gemm else Q[: a.scan_nq]
         nq = q.shape[0]
         out = s.search(q, a.k)  # warm-up (allocations, row norms)
@@ -67,7 +69,13 @@ def main():
                 "gemm_ms_per_batch": round(gms, 3),
                 "rounds_per_batch": (st["rounds"] - before["rounds"]) / a.reps,
                 "fallback_queries_per_batch": (st["fallback_queries"] - before["fallback_queries"]) / a.reps,
-                "tensor_TFLOPs_3xTF32": round(3 * 2.0 * nq_pad * rows_pad * k_pad / (gms * 1e-3) / 1e12, 1),
+                "gemm_passes": a.passes,
+                "fast_tier_queries_per_batch": (st["fast_queries"] - before["fast_queries"]) / a.reps,
+                # tensor-pipe work of the launches: MMAs per product x 2 nq rows d (padded); with both tiers the
+                # second tier's share depends on how many queries it re-ran, so only the pure modes are quoted
+                "tensor_TFLOPs_3xTF32": round(3 * 2.0 * nq_pad * rows_pad * k_pad / (gms * 1e-3) / 1e12, 1) if a.passes == 3 else None,
+                "tensor_TFLOPs_1xTF32": round(2.0 * nq_pad * rows_pad * k_pad / (gms * 1e-3) / 1e12, 1)
+                if (st["fast_queries"] - before["fast_queries"]) == nq * a.reps else None,
                 "gemm_share_of_wall": round(gms / (wall * 1e3), 3),
                 "fallback_scan_ms": round(scan_ms / a.reps, 3),
             })

@@ -19,18 +19,27 @@ def _shard(dim, space, **kw):
     return DeviceShard(dim, space, **kw)
 
 
-def _both_paths(s, Q, k, filt=None):
+def _both_paths(s, Q, k, filt=None, stats=None):
+    """Scan path vs tensor-core path in every tier configuration: 3xTF32 only, one-pass tier + scan, and the
+    default (one-pass tier, 3xTF32 for what it cannot certify, scan for the rest).  Returns the default's results
+    and its scan fallbacks; ``stats`` (dict) receives the default's counter deltas."""
     s.set_tuning("gemm", 0)
     ref = s.search(Q, k, filt)
     s.set_tuning("gemm", 1)
-    before = s.gemm_stats()
-    got = s.search(Q, k, filt)
-    after = s.gemm_stats()
-    assert after["searches"] == before["searches"] + 1, "the batch did not take the tensor-core path"
-    fallbacks = after["fallback_queries"] - before["fallback_queries"]
-    for a, b, name in zip(got, ref, ("dists", "rows", "counts")):
-        assert a.dtype == b.dtype and a.shape == b.shape
-        assert np.array_equal(a, b, equal_nan=True), f"{name}: tensor-core path differs from the scan path"
+    for passes in (3, 1, 0):
+        s.set_tuning("gemm_passes", passes)
+        before = s.gemm_stats()
+        got = s.search(Q, k, filt)
+        after = s.gemm_stats()
+        assert after["searches"] == before["searches"] + 1, "the batch did not take the tensor-core path"
+        fallbacks = after["fallback_queries"] - before["fallback_queries"]
+        fast = after["fast_queries"] - before["fast_queries"]
+        assert fast == 0 if passes == 3 else fast <= len(Q)
+        for a, b, name in zip(got, ref, ("dists", "rows", "counts")):
+            assert a.dtype == b.dtype and a.shape == b.shape
+            assert np.array_equal(a, b, equal_nan=True), f"{name}: tensor-core path (gemm_passes={passes}) differs from the scan path"
+    if stats is not None:
+        stats.update(fast=fast, fallbacks=fallbacks)
     return got, fallbacks
 
 
@@ -83,8 +92,10 @@ def test_batch_path_equals_scan_and_oracle(space, k):
     Q[2] = X[123]
     s = _shard(dim, space)
     s.add(X)
-    got, fallbacks = _both_paths(s, Q, k)
+    st = {}
+    got, fallbacks = _both_paths(s, Q, k, stats=st)
     assert fallbacks <= max(3, nq // 50), f"{fallbacks} of {nq} queries failed the certificate on benign data"
+    assert st["fast"] >= nq * 3 // 4, f"only {st['fast']} of {nq} queries were certified by the one-pass tier"
     _assert_oracle(got, X, Q, k, space)
     s.close()
 
@@ -147,9 +158,31 @@ def test_large_batch_on_device_generated_rows():
     s.add_synthetic(42, 0, n, scaled=True)
     Q = synthetic.queries(43, nq, dim)
     Q[5] = synthetic.rows(42, 1234, 1, dim, scaled=True)[0]
-    got, fallbacks = _both_paths(s, Q, 10)
+    st = {}
+    got, fallbacks = _both_paths(s, Q, 10, stats=st)
     assert got[1][5, 0] == 1234
-    assert fallbacks <= 10
+    assert fallbacks <= 10 and st["fast"] >= nq * 9 // 10
+    s.close()
+
+
+def test_one_pass_tier_hands_near_ties_to_the_3xtf32_tier():
+    """Many near-duplicates of the query's neighbours: the exact k-th best sits within the one-pass tier's error
+    of the (k'+1)-th, so that tier cannot certify; the 3xTF32 tier (or the scan) answers and results stay exact."""
+    n, dim, nq, k = 30_000, 64, 32, 10
+    rng = np.random.default_rng(5)
+    X = synthetic.rows(81, 0, n, dim)
+    Q = synthetic.queries(81, nq, dim)
+    # 400 rows at almost the same distance from Q[0]: Q[0] + a fixed-length offset, directions random
+    off = rng.standard_normal((400, dim)).astype(np.float32)
+    off /= np.linalg.norm(off, axis=1, keepdims=True)
+    X[1000:1400] = Q[0] + 0.5 * off * (1 + 1e-4 * rng.standard_normal((400, 1)).astype(np.float32))
+    s = _shard(dim, "l2")
+    s.add(X)
+    st = {}
+    got, _ = _both_paths(s, Q, k, stats=st)
+    assert st["fast"] < nq, "the crowded query should not have been certified by the one-pass tier"
+    assert set(got[1][0].tolist()) <= set(range(1000, 1400))
+    _assert_oracle(got, X, Q, k, "l2")
     s.close()
 
 
