@@ -273,12 +273,19 @@ int search_gemm(mlv_index* h, const float* qprep, uint32_t nq, uint32_t k, const
     std::vector<uint32_t> failing;
     h->gemm_searches++;
     h->gemm_queries += nq;
-    const bool fast = gemm_1pass_ok(h, k);
+    // data on which the one-pass tier certifies little (neighbours crowded within its error) would pay for both
+    // tiers on every batch: after a batch where it failed for more than half of the queries it sits out 8 batches
+    bool fast = gemm_1pass_ok(h, k);
+    if (fast && h->tune_gemm_passes == 0 && h->gemm_fast_skip > 0) {
+        h->gemm_fast_skip--;
+        fast = false;
+    }
     if ((rc = search_gemm_tier(h, qprep, nq, k, fast ? 1 : 3, filter_dev, out_d, out_r, out_c, st, hflags)) != MLV_OK) return rc;
     for (uint32_t q = 0; q < nq; q++)
         if (hflags[q]) failing.push_back(q);
     if (fast) {
         h->gemm_fast_queries += nq - failing.size();
+        if (h->tune_gemm_passes == 0 && failing.size() * 2 > nq) h->gemm_fast_skip = 8;
         if (!failing.empty() && h->tune_gemm_passes != 1) {
             // second tier on the compacted failing queries; results scattered back to their slots
             const uint32_t nf = (uint32_t)failing.size();

@@ -118,6 +118,7 @@ struct mlv_index {
     int tune_gemm_bn = 0;      // queries per GEMM tile: 0 auto, or 64 / 128 / 256
     int tune_gemm_passes = 0;  // 0 auto (one-pass tier, then 3xTF32 for what it cannot certify), 1 one-pass tier only, 3 3xTF32 only
     uint64_t gemm_fast_queries = 0;  // queries certified by the one-pass tier
+    uint32_t gemm_fast_skip = 0;     // batches the one-pass tier sits out (it certified too little last time)
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> gemm_pending;
     uint64_t gemm_searches = 0, gemm_queries = 0, gemm_fallback_queries = 0, gemm_rounds = 0, gemm_launches = 0;
     // columnar metadata (column_kernels.cuh): int32 code columns, allocated on first use

@@ -197,3 +197,31 @@ def test_largest_k_on_the_batch_path():
     assert (got[2] == k).all()
     _assert_oracle((got[0][:3], got[1][:3], got[2][:3]), X, Q[:3], k, "l2")
     s.close()
+
+
+def test_one_pass_tier_sits_out_when_it_certifies_too_little():
+    """Every query crowded: the one-pass tier fails for all of them once, then is skipped for the next batches
+    (fewer GEMM rounds per batch), and the answers stay bit-identical to the scan."""
+    n, dim, nq, k = 30_000, 64, 16, 10
+    rng = np.random.default_rng(6)
+    X = synthetic.rows(91, 0, n, dim)
+    q0 = synthetic.queries(91, 1, dim)[0]
+    off = rng.standard_normal((600, dim)).astype(np.float32)
+    off /= np.linalg.norm(off, axis=1, keepdims=True)
+    X[2000:2600] = q0 + 0.5 * off * (1 + 1e-4 * rng.standard_normal((600, 1)).astype(np.float32))
+    Q = np.tile(q0, (nq, 1)) + 1e-3 * rng.standard_normal((nq, dim)).astype(np.float32)
+    s = _shard(dim, "l2")
+    s.add(X)
+    s.set_tuning("gemm", 0)
+    ref = s.search(Q, k)
+    s.set_tuning("gemm", 1)
+    rounds = []
+    for _ in range(3):
+        before = s.gemm_stats()
+        got = s.search(Q, k)
+        after = s.gemm_stats()
+        assert all(np.array_equal(a, b, equal_nan=True) for a, b in zip(got, ref))
+        rounds.append(after["rounds"] - before["rounds"])
+        assert after["fast_queries"] - before["fast_queries"] <= nq // 2
+    assert rounds[1] < rounds[0] and rounds[2] == rounds[1], rounds   # batches 2 and 3 ran one tier only
+    s.close()
