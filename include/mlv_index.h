@@ -173,6 +173,15 @@ int mlv_index_range_search_device(mlv_index_t h, const float *queries_dev, uint3
                                   const uint32_t *filter_bitmap_dev, uint64_t max_hits, float *out_dists_dev,
                                   int64_t *out_rows_dev, uint64_t *out_counts_dev, void *stream);
 
+/*
+ * Order n (distance, row) pairs in device memory ascending by (distance, row): the last step of a sharded range
+ * search, whose per-shard hit lists arrive concatenated (and padded with row = -1 entries, which sort last and
+ * come back as distance +inf / row 2^32-1).  Rows are GLOBAL rows < 2^32; any n up to 2^31 (a bitonic network
+ * over the whole list on the device).  Uses the handle's scratch: one ordering at a time per handle.
+ */
+int mlv_index_order_pairs_device(mlv_index_t h, const float *dists_dev, const int64_t *rows_dev, uint64_t n,
+                                 float *out_dists_dev, int64_t *out_rows_dev, void *stream);
+
 /* Copy stored rows (as stored: normalised for cosine) back to the host, [n, dim]. */
 int mlv_index_get_rows(mlv_index_t h, const uint64_t *rows, uint64_t n, float *out);
 

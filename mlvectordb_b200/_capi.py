@@ -84,6 +84,7 @@ SIGNATURES = {
                                          C.c_void_p, C.c_void_p]),
     "mlv_index_range_search_device": (C.c_int, [_h, C.c_void_p, C.c_uint32, C.c_float, C.c_void_p, C.c_uint64, C.c_void_p,
                                                 C.c_void_p, C.c_void_p, C.c_void_p]),
+    "mlv_index_order_pairs_device": (C.c_int, [_h, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p]),
     "mlv_index_get_rows": (C.c_int, [_h, C.c_void_p, C.c_uint64, C.c_void_p]),
     "mlv_index_info": (C.c_int, [_h, C.POINTER(IndexInfo)]),
     "mlv_merge_topk": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p,

@@ -409,6 +409,23 @@ int prep_queries(mlv_index* h, const float* q_dev_raw, uint32_t nq, cudaStream_t
     return MLV_OK;
 }
 
+// Bitonic network over P keys in device memory (P a power of two >= SELECT_MAX_P): CTA-local sorts of 8192 keys,
+// global compare-exchange steps for the strides that span CTAs.
+int sort_keys_device(mlv_index* h, uint64_t* a, uint64_t P, cudaStream_t st) {
+    CK(h, cudaFuncSetAttribute(bitonic_block_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SELECT_MAX_P * 8)));
+    const unsigned blocks = (unsigned)(P / SELECT_MAX_P);
+    bitonic_block_kernel<<<blocks, SELECT_THREADS, (size_t)SELECT_MAX_P * 8, st>>>(a, 2, SELECT_MAX_P);
+    for (uint64_t size = 2ull * SELECT_MAX_P; size <= P; size <<= 1) {
+        for (uint64_t stride = size >> 1; stride >= SELECT_MAX_P; stride >>= 1)
+            bitonic_global_kernel<<<(unsigned)std::min<uint64_t>((P / 2 + 255) / 256, 4096), 256, 0, st>>>(a, (uint32_t)P, (uint32_t)size,
+                                                                                                         (uint32_t)stride);
+        bitonic_block_kernel<<<blocks, SELECT_THREADS, (size_t)SELECT_MAX_P * 8, st>>>(a, (uint32_t)size, (uint32_t)size);
+    }
+    h->launches += 2;
+    CK(h, cudaGetLastError());
+    return MLV_OK;
+}
+
 // Order n > SELECT_MAX_P keys (device, in a scratch copy padded to a power of two) and decode them.
 int sort_big_device(mlv_index* h, const uint64_t* keys, uint64_t n, float* out_d, int64_t* out_r, cudaStream_t st) {
     uint64_t P = SELECT_MAX_P;
@@ -419,17 +436,9 @@ int sort_big_device(mlv_index* h, const uint64_t* keys, uint64_t n, float* out_d
     uint64_t* a = (uint64_t*)h->d_misc.p;
     CK(h, cudaMemcpyAsync(a, keys, n * 8, cudaMemcpyDeviceToDevice, st));
     if (P > n) fill_sentinel_kernel<<<(unsigned)std::min<uint64_t>((P - n + 255) / 256, 1024), 256, 0, st>>>(a, n, P);
-    CK(h, cudaFuncSetAttribute(bitonic_block_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SELECT_MAX_P * 8)));
-    const unsigned blocks = (unsigned)(P / SELECT_MAX_P);
-    bitonic_block_kernel<<<blocks, SELECT_THREADS, (size_t)SELECT_MAX_P * 8, st>>>(a, 2, SELECT_MAX_P);
-    for (uint64_t size = 2ull * SELECT_MAX_P; size <= P; size <<= 1) {
-        for (uint64_t stride = size >> 1; stride >= SELECT_MAX_P; stride >>= 1)
-            bitonic_global_kernel<<<(unsigned)std::min<uint64_t>((P / 2 + 255) / 256, 4096), 256, 0, st>>>(a, (uint32_t)P, (uint32_t)size,
-                                                                                                         (uint32_t)stride);
-        bitonic_block_kernel<<<blocks, SELECT_THREADS, (size_t)SELECT_MAX_P * 8, st>>>(a, (uint32_t)size, (uint32_t)size);
-    }
+    if ((rc = sort_keys_device(h, a, P, st)) != MLV_OK) return rc;
     decode_keys_kernel<<<(unsigned)std::min<uint64_t>((n + 255) / 256, 1024), 256, 0, st>>>(a, n, h->row_base, out_d, out_r);
-    h->launches += 3;
+    h->launches++;
     CK(h, cudaGetLastError());
     return MLV_OK;
 }

@@ -914,6 +914,26 @@ int mlv_index_range_search(mlv_index_t h, const float* queries, uint32_t nq, flo
     return MLV_OK;
 }
 
+int mlv_index_order_pairs_device(mlv_index_t h, const float* dists_dev, const int64_t* rows_dev, uint64_t n, float* out_dists_dev,
+                                 int64_t* out_rows_dev, void* stream) {
+    if (!h || (n && (!dists_dev || !rows_dev || !out_dists_dev || !out_rows_dev))) return fail(h, MLV_E_INVALID, "bad argument");
+    if (n == 0) return MLV_OK;
+    DeviceGuard g(h->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    uint64_t P = SELECT_MAX_P;
+    while (P < n) P <<= 1;
+    if (P > (1ull << 31)) return fail(h, MLV_E_UNSUPPORTED, "too many pairs to order");
+    int rc = ensure_dev(h, h->d_misc, P * 8);
+    if (rc != MLV_OK) return rc;
+    uint64_t* a = (uint64_t*)h->d_misc.p;
+    encode_pairs_kernel<<<(unsigned)std::min<uint64_t>((P + 255) / 256, 2048), 256, 0, st>>>(dists_dev, rows_dev, n, P, a);
+    if ((rc = sort_keys_device(h, a, P, st)) != MLV_OK) return rc;
+    decode_keys_kernel<<<(unsigned)std::min<uint64_t>((n + 255) / 256, 1024), 256, 0, st>>>(a, n, 0, out_dists_dev, out_rows_dev);
+    h->launches += 2;
+    CK(h, cudaGetLastError());
+    return MLV_OK;
+}
+
 int mlv_index_get_rows(mlv_index_t h, const uint64_t* rows, uint64_t n, float* out) {
     if (!h || (n && (!rows || !out))) return MLV_E_INVALID;
     DeviceGuard g(h->device);

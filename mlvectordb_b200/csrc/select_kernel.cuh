@@ -126,6 +126,11 @@ __global__ void decode_keys_kernel(const uint64_t* keys, uint64_t n, uint64_t ro
         out_rows[i] = (int64_t)(row_base + key_row(keys[i]));
     }
 }
+// (distance, GLOBAL row) pairs -> keys; padding entries (row < 0) and slots beyond n become sentinels
+__global__ void encode_pairs_kernel(const float* dists, const int64_t* rows, uint64_t n, uint64_t P, uint64_t* keys) {
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < P; i += (uint64_t)gridDim.x * blockDim.x)
+        keys[i] = (i < n && rows[i] >= 0) ? make_key(dists[i], (uint32_t)rows[i]) : KEY_SENTINEL;
+}
 __global__ void fill_sentinel_kernel(uint64_t* a, uint64_t from, uint64_t to) {
     for (uint64_t i = from + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < to; i += (uint64_t)gridDim.x * blockDim.x) a[i] = KEY_SENTINEL;
 }

@@ -276,6 +276,12 @@ class DeviceShard:
                                                  C.byref(first)))
         return int(first.value)
 
+    def order_pairs_device(self, d_ptr: int, r_ptr: int, n: int, out_d_ptr: int, out_r_ptr: int, stream: int = 0) -> None:
+        """Order n (distance f32, global row i64) pairs in device memory ascending by (distance, row); entries with
+        row < 0 sort last (``mlv_index_order_pairs_device``)."""
+        self._ck(self._lib.mlv_index_order_pairs_device(self._h, C.c_void_p(d_ptr), C.c_void_p(r_ptr), int(n), C.c_void_p(out_d_ptr),
+                                                        C.c_void_p(out_r_ptr), C.c_void_p(stream)))
+
     def get_rows(self, rows) -> np.ndarray:
         r = np.ascontiguousarray(rows, dtype=np.uint64)
         out = np.empty((r.shape[0], self.dim), dtype=np.float32)

@@ -65,25 +65,6 @@ def merge_topk_device(gd: torch.Tensor, gr: torch.Tensor, k: int):
     return out_d, out_r, out_c
 
 
-def merge_all_device(gd: torch.Tensor, gr: torch.Tensor):
-    """All valid entries of ``[G, nq, m]`` padded hit lists per query, ascending (distance, list position):
-    ``mlv_merge_topk`` asked for every slot (k = G * m)."""
-    G, nq, m = gd.shape
-    k = G * m
-    out_d = torch.empty((nq, k), dtype=torch.float32, device=gd.device)
-    out_r = torch.empty((nq, k), dtype=torch.int64, device=gd.device)
-    out_c = torch.empty((nq,), dtype=torch.int32, device=gd.device)
-    # one "list" of k slots per query: reorder [G, nq, m] -> [1, nq, G*m] (rank-major inside a query)
-    d1 = gd.permute(1, 0, 2).reshape(1, nq, k).contiguous()
-    r1 = gr.permute(1, 0, 2).reshape(1, nq, k).contiguous()
-    stream = torch.cuda.current_stream(gd.device).cuda_stream
-    st = _capi.lib().mlv_merge_topk(gd.device.index, C.c_void_p(d1.data_ptr()), C.c_void_p(r1.data_ptr()), 1, nq, k,
-                                    C.c_void_p(out_d.data_ptr()), C.c_void_p(out_r.data_ptr()),
-                                    C.c_void_p(out_c.data_ptr()), C.c_void_p(stream))
-    _capi.check(st)
-    return out_d, out_r, out_c
-
-
 class _Done:
     def __init__(self, out):
         self._out = out
@@ -101,7 +82,7 @@ class ShardedIndex:
 
     def __init__(self, dim: int, space: str, total_rows: int, device: Optional[torch.device] = None, group=None,
                  local_search: Optional[Callable] = None, merge: Optional[Callable] = None, fused_exchange: bool = True,
-                 local_range: Optional[Callable] = None):
+                 local_range: Optional[Callable] = None, order_hits: Optional[Callable] = None):
         self.dim, self.space, self.total_rows = int(dim), space, int(total_rows)
         self.group = group
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
@@ -113,6 +94,7 @@ class ShardedIndex:
         self._local_search = local_search or self._device_local_search
         self._merge = merge or merge_topk_device
         self._local_range = local_range or self._device_local_range
+        self._order_hits = order_hits or self._device_order_hits
         self.merge_launches = 0
         self.exchange = None
         if local_search is None:
@@ -281,20 +263,22 @@ class ShardedIndex:
         gr = torch.empty((self.world * nq, m), dtype=torch.int64, device=dev)
         dist.all_gather_into_tensor(gd, torch.from_numpy(pd).to(dev), group=self.group)
         dist.all_gather_into_tensor(gr, torch.from_numpy(pr).to(dev), group=self.group)
-        if gd.is_cuda and self.world * m <= 8192:
-            # concatenation of the shards' lists, ordered (distance, global row) by the merge kernel
-            md, mr, mc = merge_all_device(gd.view(self.world, nq, m), gr.view(self.world, nq, m))
-            md, mr, mc = md.cpu().numpy(), mr.cpu().numpy(), mc.cpu().numpy()
-            return [(md[i, :mc[i]].copy(), mr[i, :mc[i]].copy()) for i in range(nq)]
-        gd = gd.view(self.world, nq, m).cpu().numpy()
-        gr = gr.view(self.world, nq, m).cpu().numpy()
+        # concatenation of the shards' lists per query, ordered (distance, global row) on the device
+        gd, gr = gd.view(self.world, nq, m), gr.view(self.world, nq, m)
+        totals = all_counts.sum(axis=0)
         out = []
         for i in range(nq):
-            d = np.concatenate([gd[g, i, :all_counts[g, i]] for g in range(self.world)])
-            r = np.concatenate([gr[g, i, :all_counts[g, i]] for g in range(self.world)])
-            order = np.lexsort((r, d))
-            out.append((d[order], r[order]))
+            d, r = self._order_hits(gd[:, i, :].reshape(-1).contiguous(), gr[:, i, :].reshape(-1).contiguous())
+            n = int(totals[i])
+            out.append((d[:n].cpu().numpy().copy(), r[:n].cpu().numpy().copy()))
         return out
+
+    def _device_order_hits(self, d: torch.Tensor, r: torch.Tensor):
+        """(distance, global row) pairs of one query -> ascending; padding (row -1) last.  ``mlv_index_order_pairs_device``."""
+        od, orr = torch.empty_like(d), torch.empty_like(r)
+        stream = torch.cuda.current_stream(d.device).cuda_stream
+        self.shard.order_pairs_device(d.data_ptr(), r.data_ptr(), d.numel(), od.data_ptr(), orr.data_ptr(), stream=stream)
+        return od, orr
 
     def _staging(self, nq: int, k: int):
         """Pinned host staging reused across calls (one allocation per (nq, k) growth)."""

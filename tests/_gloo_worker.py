@@ -60,8 +60,13 @@ def main():
         L, D = exact.range_search(X, q, radius, space)
         return [(np.asarray(D[i], np.float32), np.asarray(L[i], np.int64) + lo) for i in range(q.shape[0])]
 
+    def order_hits(d, r):   # stands in for mlv_index_order_pairs_device: (distance, row) ascending, padding (row -1) last
+        dn, rn = d.numpy(), r.numpy()
+        order = np.lexsort((rn, dn, rn < 0))
+        return torch.from_numpy(dn[order]), torch.from_numpy(rn[order])
+
     idx = ShardedIndex(dim, space, total_rows, device=None, local_search=local_search, merge=numpy_merge,
-                       local_range=local_range)
+                       local_range=local_range, order_hits=order_hits)
     assert (idx.lo, idx.hi) == (lo, hi) and idx.world == world
     Q = synthetic.queries(5, 4, dim)
     d, r, c = idx.search_device(torch.from_numpy(Q), k)

@@ -100,6 +100,32 @@ def main():
             whole.close()
         idx.close()
 
+    def check_big_range(total_rows, dim):
+        """hit lists far longer than one CTA sorts (> 8192 per query): the concatenated shard lists are ordered by the
+        device-wide bitonic network (mlv_index_order_pairs_device) and equal the unsharded range search"""
+        idx = ShardedIndex(dim, "l2", total_rows, device=device)
+        idx.add_synthetic(13, scaled=False)
+        Q = synthetic.queries(14, 2, dim)
+        rad = torch.zeros(1, dtype=torch.float64, device=device)
+        whole = None
+        if rank == 0:
+            whole = DeviceShard(dim, "l2", capacity=total_rows, device=rank)
+            whole.add_synthetic(13, 0, total_rows, False)
+            d1000 = whole.search(Q[:1], 1000)[0][0, 999]
+            for mult in (1.2, 1.5, 2.0, 3.0, 5.0):
+                if len(whole.range_search(Q[:1], float(d1000) * mult)[0][1]) > 12_000:
+                    break
+            rad[0] = float(d1000) * mult
+        dist.broadcast(rad, 0)
+        got = idx.range_search(Q, float(rad.item()))
+        if rank == 0:
+            want = whole.range_search(Q, float(rad.item()))
+            assert len(want[0][1]) > 8192, len(want[0][1])
+            for (gd, gr), (hd, hr) in zip(got, want):
+                assert np.array_equal(gr, hr) and np.array_equal(gd, hd)
+            whole.close()
+        idx.close()
+
     def idx_range(n, r, w):
         from mlvectordb_b200.sharded import shard_range
         return shard_range(n, r, w)
@@ -111,6 +137,7 @@ def main():
     check(200_003, 64, "l2", 40, 3, True)                  # larger k: bitonic final select in the last CTA
     check(200_003, 64, "cosine", 100, 4, False)            # k too large for the fused exchange: NCCL path
     check(120_000, 128, "l2", 10, 300, True)               # large batch: local tensor-core path + NCCL merge
+    check_big_range(120_001, 16)                           # > 8192 hits per query: device-wide ordering
     check_filtered(150_001, 64, "cosine", 10, 4)           # filtered, fused exchange
     check_filtered(150_001, 64, "l2", 100, 3)              # filtered, NCCL merge path
     dist.barrier()
