@@ -343,6 +343,7 @@ typedef struct mlv_gemm_stats {
     uint64_t fallback_queries;    /* of those, re-run by the scan (certificate failed / buffer overflow) */
     uint64_t rounds;              /* GEMM launches (one per round) */
     uint64_t fast_queries;        /* of `queries`, certified by the one-pass TF32 tier (no 3xTF32 work spent on them) */
+    uint64_t gathered_searches;   /* of `searches`, filtered batches that multiplied a compacted copy of the passing rows */
 } mlv_gemm_stats_t;
 int mlv_index_gemm_stats(mlv_index_t h, mlv_gemm_stats_t *out);
 /*

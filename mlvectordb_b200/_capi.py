@@ -43,6 +43,7 @@ class GemmStats(C.Structure):
         ("fallback_queries", C.c_uint64),
         ("rounds", C.c_uint64),
         ("fast_queries", C.c_uint64),
+        ("gathered_searches", C.c_uint64),
     ]
 
 

@@ -340,6 +340,16 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
 }
 
 // ---- helpers around the GEMM -------------------------------------------------------------------
+// dense copy of the listed rows (one warp per row) and of their squared norms: the matrix a filtered batch multiplies
+__global__ void gather_rows_kernel(const float4* __restrict__ src, const uint32_t* __restrict__ list, uint32_t m, uint32_t ld4,
+                                   float4* __restrict__ dst, const float* __restrict__ norms, float* __restrict__ out_norms) {
+    const uint32_t w = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (w >= m) return;
+    const uint32_t r = list[w];
+    for (uint32_t j = lane; j < ld4; j += 32) dst[(size_t)w * ld4 + j] = src[(size_t)r * ld4 + j];
+    if (lane == 0 && norms) out_norms[w] = norms[r];
+}
 // second tier works on the queries the first could not certify: dst[i] = src[idx[i]] (rows of ld floats)
 __global__ void gather_queries_kernel(const float* __restrict__ src, const uint32_t* __restrict__ idx, float* __restrict__ dst,
                                       uint32_t n, uint32_t ld) {
@@ -453,6 +463,7 @@ struct RerankParams {
     int64_t* out_rows;
     int32_t* out_counts;
     uint64_t row_base;
+    const uint32_t* rowmap;  // candidate row (position in `rows`) -> index row; nullptr = identity
     int metric;  // MLV metric: 0 l2, 1 ip, 2 cosine
     float delta_rel;  // bound on |a - exact| / scale of the GEMM tier that selected the candidates
 };
@@ -490,7 +501,7 @@ __global__ void __launch_bounds__(256, 1) rerank_kernel(const RerankParams p) {
         const uint64_t key = a[i];
         const bool valid = key != KEY_SENTINEL;
         p.out_dists[(size_t)q * p.k + i] = valid ? key_dist(key) : __int_as_float(0x7f800000);
-        p.out_rows[(size_t)q * p.k + i] = valid ? (int64_t)(p.row_base + key_row(key)) : -1;
+        p.out_rows[(size_t)q * p.k + i] = valid ? (int64_t)(p.row_base + (p.rowmap ? p.rowmap[key_row(key)] : key_row(key))) : -1;
         local += valid;
     }
     if (local) atomicAdd(&cnt_s, local);

@@ -129,10 +129,22 @@ bool gemm_1pass_ok(const mlv_index* h, uint32_t k) {
     return gemm_kprime_1pass(k) * 4 <= SELECT_MAX_P;
 }
 
+// What a tier multiplies the queries with: the index's own matrix (rows masked by the tombstone / filter bitmaps in the
+// epilogue), or -- for a selective filter -- a compacted copy of the passing-and-live rows, whose positions `rowmap`
+// translates back (the list is ascending, so ordering candidates by position orders them by row).
+struct GemmView {
+    const float* rows = nullptr;
+    uint64_t n_rows = 0;
+    const float* norms = nullptr;      // |x|^2 per view row (l2 only)
+    const uint32_t* live = nullptr;
+    const uint32_t* filter = nullptr;
+    const uint32_t* rowmap = nullptr;  // view row -> index row (nullptr = identity)
+};
+
 // One tier of the batch path: tcgen05 GEMM (PASSES = 1 or 3) selects k' candidates per query in geometrically growing
 // rounds, rerank_kernel scores them in the reference's arithmetic and certifies.  hflags[q] != 0 = not certified
 // (or the candidate buffer overflowed): the caller re-runs those queries.  Synchronises `st` once (to read the flags).
-int search_gemm_tier(mlv_index* h, const float* qprep, uint32_t nq, uint32_t k, int passes, const uint32_t* filter_dev, float* out_d,
+int search_gemm_tier(mlv_index* h, const float* qprep, uint32_t nq, uint32_t k, int passes, const GemmView& view, float* out_d,
                      int64_t* out_r, int32_t* out_c, cudaStream_t st, std::vector<uint32_t>& hflags) {
     int rc;
     const uint32_t ld = h->ld;
@@ -142,9 +154,6 @@ int search_gemm_tier(mlv_index* h, const float* qprep, uint32_t nq, uint32_t k, 
     const uint32_t cap = std::min<uint32_t>(SELECT_MAX_P, pow2_ceil(8 * kprime));
     const uint32_t P = cap;  // power of two
     const bool l2 = h->metric == MLV_L2;
-    if (h->metric != MLV_COSINE) {
-        if ((rc = ensure_row_norms(h, st)) != MLV_OK) return rc;
-    }
     // scratch: Qhi | Qlo | qn | thr | cnt | flags
     const size_t qmat = (size_t)nq_pad * ld * 4;
     if ((rc = ensure_dev(h, h->d_gq, 2 * qmat + (size_t)nq_pad * 16)) != MLV_OK) return rc;
@@ -163,27 +172,21 @@ int search_gemm_tier(mlv_index* h, const float* qprep, uint32_t nq, uint32_t k, 
         CK(h, cudaGetLastError());
     }
     CUtensorMap mx, mqh, mql;
-    if ((rc = make_tile_map(h, &mx, h->d_rows, h->rows, GEMM_BM)) != MLV_OK) return rc;
+    if ((rc = make_tile_map(h, &mx, view.rows, view.n_rows, GEMM_BM)) != MLV_OK) return rc;
     if ((rc = make_tile_map(h, &mqh, qhi, nq_pad, GEMM_BN)) != MLV_OK) return rc;
     if ((rc = make_tile_map(h, &mql, qlo, nq_pad, GEMM_BN)) != MLV_OK) return rc;
     CK(h, cudaFuncSetAttribute(refine_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SELECT_MAX_P * 8)));
 
     GemmParams gp{};
-    gp.n_rows = (uint32_t)h->rows;
+    gp.n_rows = (uint32_t)view.n_rows;
     gp.nq = nq;
     gp.n_qtiles = nq_pad / GEMM_BN;
     gp.n_kchunks = (ld + GEMM_BK - 1) / GEMM_BK;
-    gp.row_norms = l2 ? (const float*)h->d_norms.p : nullptr;
+    gp.row_norms = l2 ? view.norms : nullptr;
     gp.q_norms = qn;
     gp.thr = thr;
-    gp.live = h->n_deleted ? h->d_live : nullptr;
-    gp.filter = filter_dev;
-    if (!filter_dev && h->bound_filter) {
-        if (h->bound_filter->compact_gen != h->compact_gen)
-            return fail(h, MLV_E_INVALID, "prepared filter predates a compaction / clear of the index (rows were renumbered); create it again");
-        if (h->bound_filter->bitmap_words < (h->rows + 31) / 32) return fail(h, MLV_E_INVALID, "prepared filter is shorter than the index; re-create it");
-        gp.filter = (const uint32_t*)h->bound_filter->d_bitmap.p;
-    }
+    gp.live = view.live;
+    gp.filter = view.filter;
     gp.cand = cand;
     gp.cand_cnt = cnt;
     gp.cap = cap;
@@ -191,7 +194,7 @@ int search_gemm_tier(mlv_index* h, const float* qprep, uint32_t nq, uint32_t k, 
     // rounds: the first takes as many rows as a candidate buffer holds (no threshold yet), each
     // later one (cap - k') / (4 k') times the rows seen so far, so a buffer is expected to stay
     // at most a quarter full however the thresholds started
-    const uint32_t total_tiles = (uint32_t)((h->rows + GEMM_BM - 1) / GEMM_BM);
+    const uint32_t total_tiles = (uint32_t)((view.n_rows + GEMM_BM - 1) / GEMM_BM);
     const double growth = (double)(cap - kprime) / (4.0 * kprime);
     uint32_t seen = 0;
     // a query's buffer is typically a quarter full: 256 threads sort it, and many CTAs share an SM
@@ -230,7 +233,8 @@ int search_gemm_tier(mlv_index* h, const float* qprep, uint32_t nq, uint32_t k, 
     }
 
     RerankParams rp{};
-    rp.rows = reinterpret_cast<const float4*>(h->d_rows);
+    rp.rows = reinterpret_cast<const float4*>(view.rows);
+    rp.rowmap = view.rowmap;
     rp.ld4 = ld / 4;
     rp.queries = reinterpret_cast<const float4*>(qprep);
     rp.q_norms = qn;
@@ -273,6 +277,67 @@ int search_gemm(mlv_index* h, const float* qprep, uint32_t nq, uint32_t k, const
     std::vector<uint32_t> failing;
     h->gemm_searches++;
     h->gemm_queries += nq;
+    if (h->metric != MLV_COSINE && (rc = ensure_row_norms(h, st)) != MLV_OK) return rc;
+    GemmView view;
+    view.rows = h->d_rows;
+    view.n_rows = h->rows;
+    view.norms = (const float*)h->d_norms.p;
+    view.live = h->n_deleted ? h->d_live : nullptr;
+    view.filter = filter_dev;
+    mlv_filter* bf = filter_dev ? nullptr : h->bound_filter;
+    if (bf) {
+        if (bf->compact_gen != h->compact_gen)
+            return fail(h, MLV_E_INVALID, "prepared filter predates a compaction / clear of the index (rows were renumbered); create it again");
+        if (bf->bitmap_words < (h->rows + 31) / 32) return fail(h, MLV_E_INVALID, "prepared filter is shorter than the index; re-create it");
+        view.filter = (const uint32_t*)bf->d_bitmap.p;
+    }
+    if (view.filter && h->tune_gather != 0) {
+        // Selective filter: multiply only the passing-and-live rows.  Their list is the scan's gather list (prepared
+        // filters keep it; a per-call bitmap builds it here); the rows are copied once into a dense matrix, which
+        // costs a read + write of s x the matrix against a GEMM over all of it.
+        Lane* ln = lane_for(h, st);
+        FilterPlan fp;
+        const int keep_tune = h->tune_gather;
+        h->tune_gather = 1;   // ask plan_filter for the list whatever the density
+        rc = plan_filter(h, ln, filter_dev, st, &fp);
+        h->tune_gather = keep_tune;
+        if (rc != MLV_OK) return rc;
+        uint32_t m = 0;
+        CK(h, cudaMemcpyAsync(&m, fp.n_rows_dev, 4, cudaMemcpyDeviceToHost, st));
+        CK(h, cudaStreamSynchronize(st));
+        if (m == 0) {
+            fill_empty_kernel<<<32, 256, 0, st>>>(out_d, out_r, out_c, nq, k);
+            h->launches++;
+            CK(h, cudaGetLastError());
+            return MLV_OK;
+        }
+        const uint64_t live_rows = h->rows - h->n_deleted;
+        // up to 60 % passing the copy (read + write of the passing rows at HBM speed) is cheaper than multiplying the rest
+        bool gather = (uint64_t)m * 5 <= live_rows * 3 || keep_tune == 1;
+        if (gather && m < 16384 && keep_tune != 1)   // a few thousand rows: eight queries per gathered scan pass are cheaper than GEMM rounds
+            return search_prepared(h, qprep, nq, k, filter_dev, out_d, out_r, out_c, st);
+        if (gather && ensure_dev(h, h->d_gx, (size_t)m * ld * 4 + (size_t)m * 4) != MLV_OK) {
+            gather = false;   // no room for the copy beside the matrix: mask in the epilogue instead
+            h->err.clear();
+        }
+        if (gather) {
+            float* gx = (float*)h->d_gx.p;
+            float* gn = gx + (size_t)m * ld;
+            const int wpb = 8;
+            gather_rows_kernel<<<(unsigned)((m + wpb - 1) / wpb), wpb * 32, 0, st>>>(
+                reinterpret_cast<const float4*>(h->d_rows), fp.gather, m, ld / 4, reinterpret_cast<float4*>(gx),
+                h->metric == MLV_L2 ? (const float*)h->d_norms.p : nullptr, gn);
+            h->launches++;
+            CK(h, cudaGetLastError());
+            view.rows = gx;
+            view.n_rows = m;
+            view.norms = gn;
+            view.live = nullptr;
+            view.filter = nullptr;
+            view.rowmap = fp.gather;
+            h->gemm_gathered_searches++;
+        }
+    }
     // data on which the one-pass tier certifies little (neighbours crowded within its error) would pay for both
     // tiers on every batch: after a batch where it failed for more than half of the queries it sits out 8 batches
     bool fast = gemm_1pass_ok(h, k);
@@ -280,7 +345,7 @@ int search_gemm(mlv_index* h, const float* qprep, uint32_t nq, uint32_t k, const
         h->gemm_fast_skip--;
         fast = false;
     }
-    if ((rc = search_gemm_tier(h, qprep, nq, k, fast ? 1 : 3, filter_dev, out_d, out_r, out_c, st, hflags)) != MLV_OK) return rc;
+    if ((rc = search_gemm_tier(h, qprep, nq, k, fast ? 1 : 3, view, out_d, out_r, out_c, st, hflags)) != MLV_OK) return rc;
     for (uint32_t q = 0; q < nq; q++)
         if (hflags[q]) failing.push_back(q);
     if (fast) {
@@ -301,7 +366,7 @@ int search_gemm(mlv_index* h, const float* qprep, uint32_t nq, uint32_t k, const
             h->launches++;
             CK(h, cudaGetLastError());
             std::vector<uint32_t> f2;
-            if ((rc = search_gemm_tier(h, sub_q, nf, k, 3, filter_dev, sub_d, sub_r, sub_c, st, f2)) != MLV_OK) return rc;
+            if ((rc = search_gemm_tier(h, sub_q, nf, k, 3, view, sub_d, sub_r, sub_c, st, f2)) != MLV_OK) return rc;
             scatter_results_kernel<<<(unsigned)std::min<uint64_t>(((uint64_t)nf * k + 255) / 256, 2048), 256, 0, st>>>(
                 d_idx, nf, k, sub_d, sub_r, sub_c, out_d, out_r, out_c);
             h->launches++;

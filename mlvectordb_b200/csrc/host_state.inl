@@ -111,13 +111,14 @@ struct mlv_index {
     uint64_t xchg_row_bases[XCHG_MAX_WORLD] = {0};
     uint64_t xseq = 0;
     // tensor-core batch path (gemm_kernel.cuh)
-    DevBuf d_norms, d_gq, d_cand, d_maxn2, d_sub;
+    DevBuf d_norms, d_gq, d_cand, d_maxn2, d_sub, d_gx;
     uint64_t norms_valid = 0;  // rows [0, norms_valid) of d_norms are current
     int tune_gemm = -1;        // -1 auto, 0 never, 1 whenever the shape allows it
     int tune_gemm_min_nq = 0;  // 0 = auto (gemm_min_nq: 5 with the one-pass tier on a >= 1 GB matrix, else 9)
     int tune_gemm_bn = 0;      // queries per GEMM tile: 0 auto, or 64 / 128 / 256
     int tune_gemm_passes = 0;  // 0 auto (one-pass tier, then 3xTF32 for what it cannot certify), 1 one-pass tier only, 3 3xTF32 only
     uint64_t gemm_fast_queries = 0;  // queries certified by the one-pass tier
+    uint64_t gemm_gathered_searches = 0;  // filtered batches that multiplied a compacted copy of the passing rows
     uint32_t gemm_fast_skip = 0;     // batches the one-pass tier sits out (it certified too little last time)
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> gemm_pending;
     uint64_t gemm_searches = 0, gemm_queries = 0, gemm_fallback_queries = 0, gemm_rounds = 0, gemm_launches = 0;

@@ -124,7 +124,7 @@ int mlv_index_destroy(mlv_index_t h) {
     if (h->d_rows) cudaFree(h->d_rows);
     if (h->d_live) cudaFree(h->d_live);
     for (DevBuf* b : {&h->d_qraw, &h->d_filter, &h->d_outd, &h->d_outr, &h->d_outc, &h->d_misc, &h->d_range, &h->d_timeline,
-                      &h->d_norms, &h->d_gq, &h->d_cand, &h->d_maxn2, &h->d_sub})
+                      &h->d_norms, &h->d_gq, &h->d_cand, &h->d_maxn2, &h->d_sub, &h->d_gx})
         free_dev(*b);
     for (Lane& l : h->lanes)
         for (DevBuf* b : {&l.d_q, &l.d_keys0, &l.d_keys1, &l.d_sched, &l.d_flist, &l.d_fscratch}) free_dev(*b);
@@ -1036,6 +1036,7 @@ int mlv_index_gemm_stats(mlv_index_t h, mlv_gemm_stats_t* out) {
     out->queries = h->gemm_queries;
     out->fallback_queries = h->gemm_fallback_queries;
     out->fast_queries = h->gemm_fast_queries;
+    out->gathered_searches = h->gemm_gathered_searches;
     out->rounds = h->gemm_rounds;
     return MLV_OK;
 }

@@ -225,3 +225,43 @@ def test_one_pass_tier_sits_out_when_it_certifies_too_little():
         assert after["fast_queries"] - before["fast_queries"] <= nq // 2
     assert rounds[1] < rounds[0] and rounds[2] == rounds[1], rounds   # batches 2 and 3 ran one tier only
     s.close()
+
+
+@pytest.mark.parametrize("space", ["l2", "cosine"])
+def test_filtered_batch_multiplies_a_compacted_copy_of_the_passing_rows(space):
+    """Selective filter on the tensor-core path: the passing-and-live rows are gathered into a dense matrix, the tiers
+    run on it and candidate positions are mapped back -- bit-identical to the scan (which gathers row by row) for a
+    prepared filter, a per-call mask and a device-evaluated predicate; a dense filter keeps the masked epilogue."""
+    n, dim, nq, k = 200_000, 64, 300, 10
+    X = synthetic.rows(57, 0, n, dim, scaled=True)
+    Q = synthetic.queries(57, nq, dim)
+    rng = np.random.default_rng(9)
+    s = _shard(dim, space)
+    s.add(X)
+    dead = rng.choice(n, size=20_000, replace=False)
+    s.mark_deleted(dead)
+    live = np.ones(n, bool)
+    live[dead] = False
+    buckets = rng.integers(0, 100, n).astype(np.int32)
+    s.set_column(0, buckets)
+    for cut, gathered in ((20, True), (80, False)):
+        mask = buckets < cut
+        Q[0] = X[np.flatnonzero(mask & live)[77]]
+        pf = s.prepare_filter(mask)
+        wf = s.where([(0, "<", cut)])
+        for filt in (pf, mask, wf):
+            before = s.gemm_stats()["gathered_searches"]
+            got, _ = _both_paths(s, Q, k, filt)
+            after = s.gemm_stats()["gathered_searches"]
+            assert (after - before == 3) == gathered, (cut, after - before)     # one per tier configuration
+            assert got[1][0, 0] == np.flatnonzero(mask & live)[77] and mask[got[1]].all() and live[got[1]].all()
+        _assert_oracle((got[0][:4], got[1][:4], got[2][:4]), X, Q[:4], k, space, allow=mask & live)
+        pf.close()
+        wf.close()
+    # fewer passing rows than a GEMM round is worth: the gathered scan answers (same results, no compaction)
+    tiny = buckets < 1
+    before = s.gemm_stats()["gathered_searches"]
+    got, _ = _both_paths(s, Q, k, tiny)
+    assert s.gemm_stats()["gathered_searches"] == before
+    _assert_oracle((got[0][:3], got[1][:3], got[2][:3]), X, Q[:3], k, space, allow=tiny & live)
+    s.close()
