@@ -347,8 +347,8 @@ typedef struct mlv_gemm_stats {
 } mlv_gemm_stats_t;
 int mlv_index_gemm_stats(mlv_index_t h, mlv_gemm_stats_t *out);
 /*
- * Debug / parity tests: the APPROXIMATE distances the tensor-core kernel computes (3xTF32 GEMM form,
- * before the exact re-rank) for nq host queries against every stored row: out_approx[nq, rows],
+ * Debug / parity tests: the APPROXIMATE distances the tensor-core kernel computes (3xTF32 GEMM form, or the
+ * one-pass TF32 form after set_tuning("gemm_passes", 1); before the exact re-rank) for nq host queries against every stored row: out_approx[nq, rows],
  * NaN for tombstoned rows.  1 <= rows <= 8192, dim >= 32.
  */
 int mlv_index_debug_gemm(mlv_index_t h, const float *queries, uint32_t nq, float *out_approx);

@@ -59,11 +59,15 @@ struct GemmShape {
     static constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(GEMM_BM >> 4) << 24);
 };
 constexpr float GEMM_DELTA_REL = 1.220703125e-4f;  // 2^-13: bound on |a - exact| / scale (see rerank_kernel), PASSES = 3
-// PASSES = 1: both operands truncated to 10 explicit mantissa bits -> |x~q~ - xq| < 2^-9 |xq|, so the dot product is
-// off by < 2^-9 |x||q| (Cauchy-Schwarz) plus the fp32 accumulation error, far below the 12.5 % margin taken here.
-// ip / cosine: a = 1 - dot, scale = |x|max |q|.  l2: a = |x|^2 + |q|^2 - 2 dot is off by < 2^-8 |x||q| <= 2^-10 (|x|max + |q|)^2.
-constexpr float GEMM_DELTA_REL_1PASS_IP = 1.125f * 1.953125e-3f;    // 1.125 * 2^-9
-constexpr float GEMM_DELTA_REL_1PASS_L2 = 1.125f * 9.765625e-4f;    // 1.125 * 2^-10
+// PASSES = 1: both operands truncated to 10 explicit mantissa bits -> |x~q~ - xq| < (2^-9 + 2^-20) |xq|, so the dot
+// product is off by < 2^-9 (1 + 2^-11) |x||q| (Cauchy-Schwarz); the products are exact in fp32 and each of the d
+// accumulation steps may lose up to 2 ulp of the running sum (tensor cores align and truncate), <= d 2^-22 |x||q|.
+// ip / cosine: a = 1 - dot, scale = |x|max |q|.  l2: a = |x|^2 + |q|^2 - 2 dot is off by twice that, and
+// 2 |x||q| <= (|x|max + |q|)^2 / 2, so the same bound halves relative to the l2 scale.
+__host__ __device__ inline float gemm_delta_rel_1pass(bool l2, uint32_t d) {
+    const float e = 1.953125e-3f * (1.0f + 4.8828125e-4f) + (float)d * 2.384185791015625e-7f + 9.5367431640625e-7f;
+    return l2 ? 0.5f * e : e;
+}
 
 struct GemmParams {
     uint32_t n_rows;

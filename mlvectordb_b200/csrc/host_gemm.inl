@@ -251,7 +251,7 @@ int search_gemm_tier(mlv_index* h, const float* qprep, uint32_t nq, uint32_t k, 
     rp.out_counts = out_c;
     rp.row_base = h->row_base;
     rp.metric = h->metric;
-    rp.delta_rel = passes == 1 ? (l2 ? GEMM_DELTA_REL_1PASS_L2 : GEMM_DELTA_REL_1PASS_IP) : GEMM_DELTA_REL;
+    rp.delta_rel = passes == 1 ? gemm_delta_rel_1pass(l2, ld) : GEMM_DELTA_REL;
     if (l2)
         rerank_kernel<METRIC_L2><<<nq, 256, (size_t)rp.P * 8, st>>>(rp);
     else

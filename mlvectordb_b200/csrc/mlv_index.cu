@@ -1086,8 +1086,9 @@ int mlv_index_debug_gemm(mlv_index_t h, const float* queries, uint32_t nq, float
     gp.row_tile0 = 0;
     gp.row_tile1 = (uint32_t)((h->rows + GEMM_BM - 1) / GEMM_BM);
     const int grid = (int)std::min<uint64_t>((uint64_t)gp.row_tile1 * gp.n_qtiles, (uint64_t)h->sm_count);
-    CK(h, h->metric == MLV_L2 ? launch_gemm_t<METRIC_L2>(mx, mqh, mql, gp, grid, st, (int)GEMM_BN)
-                              : launch_gemm_t<METRIC_IP>(mx, mqh, mql, gp, grid, st, (int)GEMM_BN));
+    const int passes = h->tune_gemm_passes == 1 ? 1 : 3;   // set_tuning("gemm_passes", 1): the one-pass tier's distances
+    CK(h, h->metric == MLV_L2 ? launch_gemm_t<METRIC_L2>(mx, mqh, mql, gp, grid, st, (int)GEMM_BN, passes)
+                              : launch_gemm_t<METRIC_IP>(mx, mqh, mql, gp, grid, st, (int)GEMM_BN, passes));
     h->launches += 3;
     std::vector<uint64_t> keys((size_t)nq * cap);
     std::vector<uint32_t> counts(nq);

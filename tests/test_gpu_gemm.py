@@ -265,3 +265,40 @@ def test_filtered_batch_multiplies_a_compacted_copy_of_the_passing_rows(space):
     assert s.gemm_stats()["gathered_searches"] == before
     _assert_oracle((got[0][:3], got[1][:3], got[2][:3]), X, Q[:3], k, space, allow=tiny & live)
     s.close()
+
+
+@pytest.mark.parametrize("space", ["l2", "ip"])
+def test_one_pass_distances_stay_inside_the_certificate_bound(space):
+    """The certificate of the one-pass tier assumes |a - exact| <= delta_rel * scale with delta_rel = 2^-9 (1 + 2^-11) +
+    d 2^-22 (ip; half of it on the l2 scale).  Worst case for the truncation: every value just below a TF32 step and all
+    products of one sign -- the measured error must approach the bound from below, random data stays far inside."""
+    n, dim, nq = 2048, 768, 64
+    rng = np.random.default_rng(3)
+    step = 2.0 ** -10                                       # TF32 keeps 10 explicit mantissa bits
+    worst = lambda shape: ((1.0 + rng.integers(0, 1024, shape) * step + step * (1 - 2.0 ** -13))
+                           * 2.0 ** rng.integers(-2, 3, shape)).astype(np.float32)
+    for X, Q, expect_close in ((worst((n, dim)), worst((nq, dim)), True),
+                               (synthetic.rows(4, 0, n, dim, scaled=True), synthetic.queries(4, nq, dim), False)):
+        s = _shard(dim, space)
+        s.add(X)
+        s.set_tuning("gemm_passes", 1)
+        A = s.debug_gemm(Q)
+        X64, Q64 = X.astype(np.float64), Q.astype(np.float64)
+        dots = Q64 @ X64.T
+        xn, qn = np.sqrt((X64 ** 2).sum(1)), np.sqrt((Q64 ** 2).sum(1))
+        if space == "l2":
+            true = (qn ** 2)[:, None] + (xn ** 2)[None, :] - 2 * dots
+            scale = (xn.max() + qn[:, None]) ** 2 * np.ones_like(dots)
+            bound = 0.5 * (2.0 ** -9 * (1 + 2.0 ** -11) + dim * 2.0 ** -22)
+        else:
+            true = 1 - dots
+            scale = xn.max() * qn[:, None] * np.ones_like(dots)
+            bound = 2.0 ** -9 * (1 + 2.0 ** -11) + dim * 2.0 ** -22
+        rel = np.abs(A - true) / scale
+        assert not np.isnan(A).any()
+        assert rel.max() < bound, f"{space}: {rel.max():.3e} exceeds the certificate's delta {bound:.3e}"
+        if expect_close:
+            assert rel.max() > 0.25 * bound, f"worst-case input only reached {rel.max():.3e} of {bound:.3e}"
+        else:
+            assert rel.max() < 0.1 * bound
+        s.close()
