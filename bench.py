@@ -180,7 +180,7 @@ def run_reference(a):
         "e2e": {"value": base["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit_result(line)
 
 
 # --------------------------------------------------------------------------- GPU arm
@@ -391,7 +391,7 @@ def run_ours(a):
         base, _ = cpu_knn_qps(a, 1, 1, a.cpu_queries)
         line["cpu_baseline"] = base
     if rank == 0:
-        print(json.dumps(line), flush=True)
+        emit_result(line)
     if index is not None:
         index.close()
     if sharded is not None:
@@ -400,7 +400,26 @@ def run_ours(a):
         dist.destroy_process_group()
 
 
+_RESULT_FD = None
+
+
+def emit_result(line: dict) -> None:
+    """THE one JSON line of the contract, on the process's original stdout."""
+    text = json.dumps(line) + "\n"
+    if _RESULT_FD is None:
+        sys.stdout.write(text)
+        sys.stdout.flush()
+    else:
+        os.write(_RESULT_FD, text.encode())
+
+
 def main():
+    # Libraries below us write to file descriptor 1 on their own (NCCL prints "NCCL version ..." there when
+    # NCCL_DEBUG=VERSION is set in the environment): keep stdout for the result line, send the rest to stderr.
+    global _RESULT_FD
+    sys.stdout.flush()
+    _RESULT_FD = os.dup(1)
+    os.dup2(2, 1)
     a = parse_args()
     if a.impl == "reference":
         run_reference(a)
