@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define MLV_ABI_VERSION 1
+#define MLV_ABI_VERSION 2
 
 typedef struct mlv_index *mlv_index_t;
 

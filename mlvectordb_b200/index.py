@@ -287,6 +287,7 @@ class GpuIndex:
     def rebuild(self, source: Mapping[str, Iterable[VectorProtocol]], metric: str) -> None:
         """reference index.py:131-162: drop everything, re-add ``source`` with ``space=metric``."""
         for ns in self._ns.values():
+            ns.touch()
             ns.shard.close()
         self._ns.clear()
         for namespace, vectors in source.items():
@@ -477,5 +478,6 @@ class GpuIndex:
 
     def close(self) -> None:
         for ns in self._ns.values():
+            ns.touch()
             ns.shard.close()
         self._ns.clear()

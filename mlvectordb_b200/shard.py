@@ -9,6 +9,7 @@ It plays the role the per-namespace ``hnswlib.Index`` object plays in the refere
 from __future__ import annotations
 
 import ctypes as C
+import weakref
 from typing import Optional, Tuple
 
 import numpy as np
@@ -46,12 +47,15 @@ class DeviceShard:
         self._lib = _capi.lib()
         self._h = C.c_void_p()
         check(self._lib.mlv_index_create(self.dim, METRIC_CODE[self.space], int(capacity), self.device, C.byref(self._h)))
+        self._filters = weakref.WeakSet()   # prepared filters of this shard: released with it (they hold device buffers)
         if row_base:
             self.set_row_base(row_base)
 
     # -- lifecycle ------------------------------------------------------------------------
     def close(self) -> None:
         if getattr(self, "_h", None) and self._h.value:
+            for f in list(getattr(self, "_filters", ())):
+                f.close()
             self._lib.mlv_index_destroy(self._h)
             self._h = C.c_void_p()
 
@@ -355,11 +359,13 @@ class PreparedFilter:
         self._f = C.c_void_p()
         w = np.ascontiguousarray(words, dtype=np.uint32)
         check(self._lib.mlv_filter_create(shard._h, w.ctypes.data, w.shape[0], C.byref(self._f)), shard._h)
+        shard._filters.add(self)
 
     @classmethod
     def _adopt(cls, shard: DeviceShard, handle) -> "PreparedFilter":
         self = cls.__new__(cls)
         self._lib, self._shard, self._f = _capi.lib(), shard, handle
+        shard._filters.add(self)
         return self
 
     def bitmap(self, n_words: Optional[int] = None) -> np.ndarray:
