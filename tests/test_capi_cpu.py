@@ -84,3 +84,24 @@ def test_space_aliases():
     assert canonical_space("euclidean") == "l2" and canonical_space("dot") == "ip" and canonical_space("cosine") == "cosine"
     with pytest.raises(ValueError):
         canonical_space("manhattan")
+
+
+def test_float32_json_encoder_round_trips_without_a_gpu():
+    """``mlv_format_f32_json`` (host-only helper of the response path): shortest text that round-trips every float32,
+    non-finite values as Python's json module writes them, buffer-size contract."""
+    import json
+    rng = np.random.default_rng(0)
+    vals = np.concatenate([rng.standard_normal(5000).astype(np.float32) * np.float32(10.0) ** rng.integers(-20, 20, 5000).astype(np.float32),
+                           np.array([0.0, -0.0, 1.0, 3.0, 1e10, 1e-7, np.float32(1) / 3, np.finfo(np.float32).max,
+                                     np.finfo(np.float32).tiny, 1e-45], dtype=np.float32)])
+    text = _capi.format_f32_json(vals)
+    back = np.array(json.loads(text), dtype=np.float32)
+    assert np.array_equal(back, vals) and np.array_equal(np.signbit(back), np.signbit(vals))
+    assert len(text) < len(json.dumps(vals.tolist())) * 0.7             # float32-shortest, not float64 repr
+    assert _capi.format_f32_json(np.array([np.nan, np.inf, -np.inf], np.float32)) == b"[NaN,Infinity,-Infinity]"
+    assert _capi.format_f32_json(np.empty(0, np.float32)) == b"[]"
+    lib = _capi.lib()
+    n = C.c_uint64()
+    small = C.create_string_buffer(8)
+    one = np.ones(4, np.float32)
+    assert lib.mlv_format_f32_json(one.ctypes.data, 4, small, len(small), C.byref(n)) == _capi.MLV_E_INVALID
