@@ -493,7 +493,12 @@ int mlv_format_f32_json(const float* values, uint64_t n, char* out, uint64_t cap
     for (uint64_t i = 0; i < n; i++) {
         if (i) *p++ = ',';
         const float v = values[i];
-        if (std::isfinite(v)) {
+        if (v == 0.0f) {   // "-0" would parse as the integer 0 and lose the sign
+            const char* t = std::signbit(v) ? "-0.0" : "0.0";
+            const size_t tl = strlen(t);
+            memcpy(p, t, tl);
+            p += tl;
+        } else if (std::isfinite(v)) {
             auto r = std::to_chars(p, end, v);   // shortest text that round-trips the float32
             if (r.ec != std::errc()) return MLV_E_INVALID;
             p = r.ptr;
