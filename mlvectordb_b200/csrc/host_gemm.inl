@@ -298,10 +298,7 @@ int search_gemm(mlv_index* h, const float* qprep, uint32_t nq, uint32_t k, const
         Lane* ln = lane_for(h, st);
         FilterPlan fp;
         const int keep_tune = h->tune_gather;
-        h->tune_gather = 1;   // ask plan_filter for the list whatever the density
-        rc = plan_filter(h, ln, filter_dev, st, &fp);
-        h->tune_gather = keep_tune;
-        if (rc != MLV_OK) return rc;
+        if ((rc = plan_filter(h, ln, filter_dev, st, &fp, /*want_list=*/true)) != MLV_OK) return rc;
         uint32_t m = 0;
         CK(h, cudaMemcpyAsync(&m, fp.n_rows_dev, 4, cudaMemcpyDeviceToHost, st));
         CK(h, cudaStreamSynchronize(st));

@@ -210,7 +210,8 @@ struct FilterPlan {
 };
 
 // filter_dev: per-call bitmap (ceil(rows/32) words) or null; a bound prepared filter applies when it is null.
-int plan_filter(mlv_index* h, Lane* ln, const uint32_t* filter_dev, cudaStream_t st, FilterPlan* out) {
+// want_list: the caller needs the row list whatever the density (the tensor-core path compacts the rows with it).
+int plan_filter(mlv_index* h, Lane* ln, const uint32_t* filter_dev, cudaStream_t st, FilterPlan* out, bool want_list = false) {
     *out = FilterPlan{};
     mlv_filter* f = filter_dev ? nullptr : h->bound_filter;
     if (!filter_dev && !f) return MLV_OK;
@@ -225,7 +226,7 @@ int plan_filter(mlv_index* h, Lane* ln, const uint32_t* filter_dev, cudaStream_t
         }
         const bool covers = f->bitmap_words >= (h->rows + 31) / 32;  // only then can the bitmap mask a full stream
         const bool dense = f->counted && f->passing * 4 >= (h->rows - h->n_deleted) * 3;
-        const bool want_stream = h->tune_gather == 0 || (h->tune_gather < 0 && dense);
+        const bool want_stream = !want_list && (h->tune_gather == 0 || (h->tune_gather < 0 && dense));
         if (want_stream && covers) {
             out->bitmap = (const uint32_t*)f->d_bitmap.p;  // stream every row, mask in the epilogue
             return MLV_OK;
@@ -234,7 +235,7 @@ int plan_filter(mlv_index* h, Lane* ln, const uint32_t* filter_dev, cudaStream_t
         out->n_rows_dev = (const uint32_t*)f->d_scratch.p;  // low word of the u64 total
         return MLV_OK;
     }
-    if (h->tune_gather == 0) {
+    if (h->tune_gather == 0 && !want_list) {
         out->bitmap = filter_dev;
         return MLV_OK;
     }

@@ -234,9 +234,10 @@ int reserve_rows(mlv_index* h, uint64_t need) {
     return MLV_OK;
 }
 
-int finish_append(mlv_index* h, uint64_t n, uint64_t* first_row) {
+// normalize = false: the rows are already in stored form (snapshot import)
+int finish_append(mlv_index* h, uint64_t n, uint64_t* first_row, bool normalize = true) {
     const uint64_t first = h->rows;
-    if (h->metric == MLV_COSINE) {
+    if (h->metric == MLV_COSINE && normalize) {
         const int wpb = 8;
         normalize_rows_kernel<<<(unsigned)((n + wpb - 1) / wpb), wpb * 32, 0, h->stream>>>(h->d_rows, first, n, h->ld);
         h->launches++;

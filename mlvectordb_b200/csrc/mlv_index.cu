@@ -222,7 +222,7 @@ static int upload_rows_staged(mlv_index_t h, float* dst, const float* rows, uint
     return MLV_OK;
 }
 
-static int add_common(mlv_index_t h, const float* rows, uint64_t n, uint64_t* first_row, cudaMemcpyKind kind) {
+static int add_common(mlv_index_t h, const float* rows, uint64_t n, uint64_t* first_row, cudaMemcpyKind kind, bool normalize = true) {
     if (!h || (!rows && n)) return MLV_E_INVALID;
     if (n == 0) {
         if (first_row) *first_row = h->rows;
@@ -235,7 +235,7 @@ static int add_common(mlv_index_t h, const float* rows, uint64_t n, uint64_t* fi
     // pitched copy straight into the matrix; padding columns were zeroed at allocation
     if (kind == cudaMemcpyHostToDevice && n * (uint64_t)h->dim * 4 >= ((uint64_t)8 << 20) && h->tune_staged_upload) {
         if ((rc = upload_rows_staged(h, dst, rows, n)) != MLV_OK) return rc;
-        return finish_append(h, n, first_row);
+        return finish_append(h, n, first_row, normalize);
     }
     const uint64_t max_rows_per_copy = 1u << 20;  // cudaMemcpy2D height limits
     for (uint64_t r0 = 0; r0 < n; r0 += max_rows_per_copy) {
@@ -243,7 +243,7 @@ static int add_common(mlv_index_t h, const float* rows, uint64_t n, uint64_t* fi
         CK(h, cudaMemcpy2DAsync(dst + r0 * h->ld, (size_t)h->ld * 4, rows + r0 * h->dim, (size_t)h->dim * 4,
                                 (size_t)h->dim * 4, nr, kind, h->stream));
     }
-    return finish_append(h, n, first_row);
+    return finish_append(h, n, first_row, normalize);
 }
 
 int mlv_index_add(mlv_index_t h, const float* rows, uint64_t n, uint64_t* first_row) {
@@ -545,11 +545,8 @@ int mlv_index_import_rows(mlv_index_t h, const float* rows, uint64_t n, const ui
         if (first_row) *first_row = h->rows;
         return MLV_OK;
     }
-    const int metric = h->metric;
-    h->metric = metric == MLV_COSINE ? MLV_IP : metric;   // stored form: already normalised, finish_append must not redo it
     uint64_t first = 0;
-    int rc = add_common(h, rows, n, &first, cudaMemcpyHostToDevice);
-    h->metric = metric;
+    int rc = add_common(h, rows, n, &first, cudaMemcpyHostToDevice, /*normalize=*/false);   // stored form: already normalised
     if (rc != MLV_OK) return rc;
     if (first_row) *first_row = first;
     if (live_words) {
