@@ -453,7 +453,10 @@ class GpuIndex:
         adds / removes of the namespace (rows added afterwards do not pass); compaction renumbers rows, so
         prepare it again after the namespace was compacted."""
         ns = self._ns[namespace]
-        return ns.shard.prepare_filter(self._filter_mask(ns, filter))
+        resolved = self._filter_mask(ns, filter)
+        if isinstance(resolved, PreparedFilter):      # already prepared (or metadata constraints decided on the device)
+            return resolved
+        return ns.shard.prepare_filter(resolved)
 
     def info(self, namespace: str) -> dict:
         ns = self._ns[namespace]
