@@ -9,7 +9,8 @@ Public surface: :class:`GpuIndex` (drop-in for the reference ``Index``), :class:
 from .interfaces import IndexProtocol, SearchResult, VectorDTO, VectorProtocol
 from .shard import DeviceShard, PreparedFilter, canonical_space, pack_bitmap
 from .index import GpuIndex
+from .multi import MultiGpuIndex
 from .query_processor import GpuQueryProcessor, StoredVector
 
-__all__ = ["GpuIndex", "GpuQueryProcessor", "StoredVector", "DeviceShard", "PreparedFilter", "SearchResult", "VectorDTO",
+__all__ = ["GpuIndex", "MultiGpuIndex", "GpuQueryProcessor", "StoredVector", "DeviceShard", "PreparedFilter", "SearchResult", "VectorDTO",
            "VectorProtocol", "IndexProtocol", "canonical_space", "pack_bitmap"]

@@ -104,3 +104,97 @@ class _V:
     def __init__(self, values, metadata):
         import uuid
         self.id, self.values, self.metadata = uuid.uuid4(), np.asarray(values, np.float32), metadata
+
+
+# ---------------------------------------------------------------------------- MultiGpuIndex (one process, several GPUs)
+def _numpy_fanout(holders, queries, k, filters):
+    """stands in for MultiGpuIndex._device_fanout: per-part search, candidates merged by (distance, part, row)"""
+    from mlvectordb_b200.multi import PART_SHIFT
+    nq = queries.shape[0]
+    D = np.full((nq, k), np.inf, np.float32)
+    R = np.full((nq, k), -1, np.int64)
+    C = np.zeros(nq, np.int32)
+    per = [ns.shard.search(queries, k, flt) for (_, _, ns), flt in zip(holders, filters)]
+    for q in range(nq):
+        d = np.concatenate([p[0][q, :p[2][q]] for p in per])
+        r = np.concatenate([p[1][q, :p[2][q]] + (h[0] << PART_SHIFT) for p, h in zip(per, holders)])
+        order = np.lexsort((r, d))[:k]
+        D[q, :len(order)], R[q, :len(order)], C[q] = d[order], r[order], len(order)
+    return D, R, C
+
+
+def _numpy_order_pairs(holder, dists, rows):
+    order = np.lexsort((np.arange(len(rows)), dists))
+    return dists[order], rows[order]
+
+
+def _multi(space, n_parts=3, **kw):
+    from mlvectordb_b200 import MultiGpuIndex
+    return MultiGpuIndex(space=space, devices=list(range(n_parts)), fanout=_numpy_fanout, order_pairs=_numpy_order_pairs, **kw)
+
+
+def test_multi_gpu_index_equals_single_index_behind_the_reference_calls(monkeypatch):
+    """Same adds / removes / searches through one GpuIndex and through a 3-part MultiGpuIndex: same ids and scores."""
+    from mlvectordb_b200 import GpuIndex, VectorDTO
+    from oracle import synthetic
+    rng = np.random.default_rng(4)
+    for space in ("cosine", "l2"):
+        one, many = GpuIndex(space=space), _multi(space)
+        X = synthetic.rows(9, 0, 900, 20, scaled=True)
+        vecs = [_V(X[i], {"bucket": i % 7, "color": ["r", "g", "b"][i % 3]}) for i in range(900)]
+        for lo, hi in ((0, 1), (1, 4), (4, 400), (400, 900)):          # single rows, small and large blocks
+            one.add(vecs[lo:hi], "ns")
+            many.add(vecs[lo:hi], "ns")
+        per_part = many.info("ns")["rows_per_device"]
+        assert sum(per_part) == 900 and max(per_part) - min(per_part) <= 1
+        Q = synthetic.queries(9, 5, 20)
+        def same(k, flt=None, metric=space):
+            for q in Q:
+                a = one.search(VectorDTO(values=q), k, "ns", metric, filter=flt)
+                b = many.search(VectorDTO(values=q), k, "ns", metric, filter=flt)
+                assert [r.vector_id for r in a] == [r.vector_id for r in b]
+                assert [r.score for r in a] == pytest.approx([r.score for r in b], rel=1e-6, abs=1e-7)
+        same(10)
+        same(1000)                                                       # clamped to the live count
+        same(5, {"bucket": 3, "color": "g"})
+        same(5, {"bucket": ("<", 2)})
+        allowed = {v.id for v in vecs[::11]}
+        same(5, lambda u: u in allowed)
+        gone = [vecs[i].id for i in rng.choice(900, 150, replace=False)]
+        one.remove(gone, "ns")
+        many.remove(gone + [vecs[0].id.__class__(int=5)], "ns")         # unknown id: ignored
+        assert many.info("ns")["live"] == 750
+        same(10)
+        tenth = one.search(VectorDTO(values=Q[0]), 10, "ns", space)[-1].score
+        radius = (1 - tenth if space == "cosine" else tenth) * (1 + 1e-6) + 1e-7
+        hits_one = one.range_search(VectorDTO(values=Q[0]), radius, "ns", space)
+        hits_many = many.range_search(VectorDTO(values=Q[0]), radius, "ns", space)
+        assert [h.vector_id for h in hits_one] == [h.vector_id for h in hits_many] and len(hits_one) >= 10
+        rows, scores, counts = many.search_batch(Q, 4, "ns")
+        assert [u for u in many.uuids_of("ns", rows[2])] == [r.vector_id for r in one.search(VectorDTO(values=Q[2]), 4, "ns", space)]
+        assert many.search(VectorDTO(values=[1.0, 2.0]), 3, "ns", space) == [] and many.search(VectorDTO(values=Q[0]), 3, "nope", space) == []
+        assert many.dimension("ns") == 20 and many.dimension("nope") is None and sorted(many.metadata_columns("ns")) == ["bucket", "color"]
+        many.rebuild({"a": vecs[:10], "b": vecs[10:13]}, metric=space)
+        assert sorted(many.namespaces()) == ["a", "b"] and many.info("a")["rows"] == 10 and many.info("b")["rows_per_device"] == [1, 1, 1]
+        assert many.search(VectorDTO(values=X[11]), 1, "b", space)[0].vector_id == vecs[11].id
+        assert many.is_rebuild_required("a") is False
+        one.close()
+        many.close()
+
+
+def test_multi_gpu_index_behind_the_query_processors():
+    """The reference-shaped ``QueryProcessor`` and ``GpuQueryProcessor`` over a MultiGpuIndex: the reference's own
+    query-processor cases, plus a metadata filter decided per part."""
+    from mlvectordb_b200 import GpuQueryProcessor, VectorDTO
+    TD.test_find_similar_correctness(QueryProcessor(Storage(), _multi("cosine")))
+    TD.test_namespace_isolation(QueryProcessor(Storage(), _multi("cosine")))
+    TD.test_search_with_many_vectors(QueryProcessor(Storage(), _multi("cosine")))
+    qp = GpuQueryProcessor(InMemoryStorage(), _multi("cosine", n_parts=2))
+    qp.upsert_many([VectorDTO(values=[1, 0, 0], metadata={"t": "x"}), VectorDTO(values=[0.9, 0.1, 0], metadata={"t": "y"}),
+                    VectorDTO(values=[0, 1, 0], metadata={"t": "x"}), VectorDTO(values=[0, 0, 1], metadata={"t": ["unhashable"]})])
+    hits = qp.find_similar(VectorDTO(values=[1, 0, 0]), 3, filter={"t": "x"})
+    assert [h["metadata"]["t"] for h in hits] == ["x", "x"] and hits[0]["score"] == pytest.approx(1.0)
+    hits = qp.find_similar(VectorDTO(values=[1, 0, 0]), 3, filter=lambda md: md["t"] == "y")     # host predicate path
+    assert [h["metadata"]["t"] for h in hits] == ["y"]
+    deleted = qp.delete([hits[0]["id"]])
+    assert deleted == [hits[0]["id"]] and len(qp.find_similar(VectorDTO(values=[1, 0, 0]), 10)) == 3
