@@ -9,11 +9,14 @@ from __future__ import annotations
 import argparse
 
 
-def build_app(storage_engine, space: str = "l2", device: int = 0, log_level: str = "INFO", **index_kw):
+def build_app(storage_engine, space: str = "l2", device: int = 0, log_level: str = "INFO", devices=None, **index_kw):
+    """``devices``: several GPUs behind the one process (``MultiGpuIndex``); otherwise one ``GpuIndex`` on ``device``."""
     from .index import GpuIndex
+    from .multi import MultiGpuIndex
     from .query_processor import GpuQueryProcessor
     from .rest_api import GpuRestAPI
-    processor = GpuQueryProcessor(storage_engine, GpuIndex(space=space, device=device, **index_kw))
+    index = MultiGpuIndex(space=space, devices=list(devices), **index_kw) if devices else GpuIndex(space=space, device=device, **index_kw)
+    processor = GpuQueryProcessor(storage_engine, index)
     return GpuRestAPI(processor, title="Vector DB API (B200 exact index)", log_level=log_level).get_app()
 
 
@@ -25,6 +28,7 @@ def main(argv=None) -> None:
     ap.add_argument("--log-level", default="info", choices=["debug", "info", "warning", "error"])
     ap.add_argument("--space", default="l2", help="hnswlib space of the index: l2 | ip | cosine (reference default: l2)")
     ap.add_argument("--device", type=int, default=0)
+    ap.add_argument("--devices", default="", help="comma-separated GPUs to spread every namespace over (MultiGpuIndex), e.g. 0,1,2,3")
     a = ap.parse_args(argv)
     import uvicorn
     try:
@@ -32,7 +36,8 @@ def main(argv=None) -> None:
     except Exception as e:  # noqa: BLE001
         raise SystemExit("no storage engine: run from the reference's repository root (its StorageEngineInMemory is "
                          f"reused unchanged) or call build_app(storage_engine) yourself ({e})")
-    uvicorn.run(build_app(StorageEngineInMemory(), a.space, a.device, a.log_level.upper()), host=a.host, port=a.port,
+    devices = [int(d) for d in a.devices.split(",") if d.strip() != ""]
+    uvicorn.run(build_app(StorageEngineInMemory(), a.space, a.device, a.log_level.upper(), devices=devices), host=a.host, port=a.port,
                 reload=a.reload, log_config=None)
 
 

@@ -198,3 +198,14 @@ def test_multi_gpu_index_behind_the_query_processors():
     assert [h["metadata"]["t"] for h in hits] == ["y"]
     deleted = qp.delete([hits[0]["id"]])
     assert deleted == [hits[0]["id"]] and len(qp.find_similar(VectorDTO(values=[1, 0, 0]), 10)) == 3
+
+
+def test_http_surface_over_a_multi_gpu_index():
+    """``GpuRestAPI`` -> ``GpuQueryProcessor`` -> ``MultiGpuIndex``: the same HTTP scenario as over one ``GpuIndex``."""
+    from fastapi.testclient import TestClient
+    from mlvectordb_b200 import GpuQueryProcessor
+    from mlvectordb_b200.rest_api import GpuRestAPI
+    import test_gpu_rest as TR
+    qp = GpuQueryProcessor(InMemoryStorage(), _multi("cosine", n_parts=2))
+    client = TestClient(GpuRestAPI(qp, log_level="WARNING").get_app())
+    TR.test_ingest_search_filter_range_delete_over_http((client, qp))
