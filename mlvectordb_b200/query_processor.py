@@ -21,7 +21,7 @@ Works with any storage that implements the reference ``StorageEngine`` protocol
 from __future__ import annotations
 
 from typing import Any, Callable, Dict, Iterable, List, Mapping, Optional, Sequence, Union
-from uuid import UUID
+from uuid import UUID, uuid4
 
 import numpy as np
 
@@ -40,7 +40,7 @@ class StoredVector:
     __slots__ = ("id", "values", "metadata")
 
     def __init__(self, values, metadata: Optional[Mapping[str, Any]] = None, id: Optional[UUID] = None):  # noqa: A002
-        self.id = id if id is not None else UUID(bytes=_random_uuid_bytes(1)[0].tobytes())
+        self.id = id if id is not None else uuid4()
         self.values = np.array(values, dtype=np.float32)
         self.metadata = metadata or {}
 
@@ -80,7 +80,9 @@ class GpuQueryProcessor:
 
     def upsert_many(self, vectors: Iterable[VectorDTO], namespace: str = "default") -> None:
         """reference query_processor.py:21-24 (no upsert semantics there either: every call mints new ids)"""
-        vecs = [StoredVector(v.values, v.metadata) for v in vectors]
+        vectors = list(vectors)
+        raw = _random_uuid_bytes(len(vectors)).tobytes()          # ids minted in one go (uuid4 layout)
+        vecs = [StoredVector(v.values, v.metadata, id=UUID(bytes=raw[16 * i:16 * i + 16])) for i, v in enumerate(vectors)]
         self._storage.write_vectors(vecs, namespace)
         self._index.add(vecs, namespace)
         self._touch(namespace)
