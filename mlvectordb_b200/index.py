@@ -46,6 +46,21 @@ class NotDeviceEvaluable(ValueError):
     and pass a row mask / ``callable(uuid)`` instead (``GpuQueryProcessor`` does)."""
 
 
+from uuid import SafeUUID as _SafeUUID   # noqa: E402
+
+_uuid_new, _uuid_set, _int_from_bytes = object.__new__, object.__setattr__, int.from_bytes
+
+
+def uuid_from_bytes(raw: bytes) -> UUID:
+    """``UUID(bytes=raw)`` without the constructor's argument checks (1.7 us -> 0.4 us): a search builds one UUID per
+    hit, which at k = 10 is half of ``GpuIndex.search``'s host time on a small namespace.  ``raw`` is always 16 bytes
+    taken from the id table, which only holds bytes of valid UUIDs."""
+    u = _uuid_new(UUID)
+    _uuid_set(u, "int", _int_from_bytes(raw, "big"))
+    _uuid_set(u, "is_safe", _SafeUUID.unknown)
+    return u
+
+
 def _random_uuid_bytes(n: int) -> np.ndarray:
     ids = np.frombuffer(os.urandom(16 * n), dtype=np.uint8).reshape(n, 16).copy()
     ids[:, 6] = (ids[:, 6] & 0x0F) | 0x40  # version 4
@@ -96,7 +111,7 @@ class _Namespace:
         return self.uuid_to_row
 
     def uuid_of(self, row: int) -> UUID:
-        return UUID(bytes=self.ids[row].tobytes())
+        return uuid_from_bytes(self.ids[row].tobytes())
 
 
 class PendingResults:
