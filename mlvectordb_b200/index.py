@@ -48,7 +48,7 @@ class NotDeviceEvaluable(ValueError):
 
 from uuid import SafeUUID as _SafeUUID   # noqa: E402
 
-_uuid_new, _uuid_set, _int_from_bytes = object.__new__, object.__setattr__, int.from_bytes
+_uuid_new, _uuid_set, _int_from_bytes, _UNKNOWN = object.__new__, object.__setattr__, int.from_bytes, _SafeUUID.unknown
 
 
 def uuid_from_bytes(raw: bytes) -> UUID:
@@ -57,7 +57,7 @@ def uuid_from_bytes(raw: bytes) -> UUID:
     taken from the id table, which only holds bytes of valid UUIDs."""
     u = _uuid_new(UUID)
     _uuid_set(u, "int", _int_from_bytes(raw, "big"))
-    _uuid_set(u, "is_safe", _SafeUUID.unknown)
+    _uuid_set(u, "is_safe", _UNKNOWN)
     return u
 
 
