@@ -27,6 +27,7 @@ from __future__ import annotations
 
 import json
 import logging
+import math
 import time
 from contextlib import asynccontextmanager
 from typing import Any, Dict, List, Optional
@@ -119,9 +120,12 @@ def _encode_hits(hits) -> bytes:
     parts = []
     for h in hits:
         values = h.get("values")
+        metadata = h.get("metadata")
+        score = float(h["score"])
         parts.append(b'{"id":"%s","values":%s,"metadata":%s,"score":%s}' % (
             str(h["id"]).encode(), format_f32_json(values) if values is not None and len(values) else b"[]",
-            json.dumps(h.get("metadata") or {}, default=str).encode(), json.dumps(float(h["score"])).encode()))
+            json.dumps(metadata, default=str).encode() if metadata else b"{}",
+            repr(score).encode() if math.isfinite(score) else json.dumps(score).encode()))
     return b"[" + b",".join(parts) + b"]"
 
 
