@@ -316,7 +316,9 @@ int mlv_index_scan_time_ms(mlv_index_t h, double *total_ms, uint64_t *launches);
  * (-1 auto / 0 / 1), "ctas" grid size (0 = one per SM), "dynamic" (1 = work-stealing tile scheduler,
  * 0 = static round-robin), "tile_batch" tiles claimed per atomic, "fused" (1 = the last CTA does the
  * final select, 0 = separate select kernel), "gather" (-1 auto, 0 = filters stream every row and mask,
- * 1 = filters always gather)}.  Results never depend on these.
+ * 1 = filters always gather; the tensor-core path compacts the passing rows accordingly), "staged_upload"
+ * (1 = bulk mlv_index_add through two pinned chunks filled by worker threads, 0 = plain copy), and the
+ * tensor-core keys listed at mlv_index_gemm_stats}.  Results never depend on these.
  */
 int mlv_index_set_tuning(mlv_index_t h, const char *key, int value);
 /*
