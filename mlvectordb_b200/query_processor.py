@@ -9,7 +9,7 @@ reference only sketches, so the GPU index's abilities are reachable from the pro
 
 * ``find_similar(..., filter=...)``        metadata-filtered search (``README.md:123,477``; request shape
                                            ``examples/api_client.py:65-74``: a dict of equality constraints)
-* ``find_similar_batch(queries, ...)``     many queries in one call (tensor-core path for >= 9 queries)
+* ``find_similar_batch(queries, ...)``     many queries in one call (tensor-core path from 5 queries on a >= 1 GB matrix)
 * ``find_in_range(query, radius, ...)``    radius query (``README.md:121,215``; ``examples/api_client.py:38-48``)
 * ``upsert_matrix(matrix, ...)``           bulk ingest without one ``Vector`` + ``uuid4()`` per row
 * ``enrich=False``                         ids + scores only: skips the per-hit storage lookup and the k x d

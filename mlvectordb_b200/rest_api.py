@@ -13,7 +13,7 @@ What the GPU index can do beyond the reference becomes reachable from the produc
   (``rest_api.py:22-25``): ``filter`` (metadata constraints, evaluated on the device columns when possible),
   ``radius`` (range search instead of top-k) and ``include_values`` (``false`` skips the k x d float payload
   that dominates a response at GPU speeds -- rank 2);
-* ``POST /search/batch``: many queries per request (tensor-core path for >= 9 queries);
+* ``POST /search/batch``: many queries per request (tensor-core path from 5 queries on a >= 1 GB matrix);
 * the routes the reference only documents (``README.md:325-333``) with the request shapes of its example
   client (``examples/api_client.py:26-74``): ``POST /query/knn`` (``vector``, ``k``), ``POST /query/range``
   (``vector``, ``radius``), ``POST /query/similarity`` (``vector``, ``threshold``, ``metric``: cosine
