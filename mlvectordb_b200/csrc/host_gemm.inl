@@ -309,8 +309,14 @@ int search_gemm(mlv_index* h, const float* qprep, uint32_t nq, uint32_t k, const
             return MLV_OK;
         }
         const uint64_t live_rows = h->rows - h->n_deleted;
-        // up to 60 % passing the copy (read + write of the passing rows at HBM speed) is cheaper than multiplying the rest
-        bool gather = (uint64_t)m * 5 <= live_rows * 3 || keep_tune == 1;
+        // The copy reads and writes the passing rows (2 s B bytes for a matrix of B bytes at selectivity s) and saves
+        // (1 - s) of a GEMM over everything, which takes c passes' worth of time: c ~ 1.1 while a pass is HBM-bound
+        // (<= 64 queries), ~ nq / 120 for wide batches (measured: 256 queries 2.3, 1024 queries 7.7).  Gather when
+        // 2.5 s < (1 - s) c, with a 20 % margin for the allocation: 1024 queries up to ~60 % passing, 256 up to ~37 %,
+        // small batches up to ~24 % (10M x 384: 256 queries at 50 % lost 10.6 vs 5.1 ms to the copy, 1024 won 12.3 vs 18.5).
+        const double c = std::max(1.1, (double)nq / 120.0);
+        const double s_max = 0.8 * c / (2.5 + c);
+        bool gather = (double)m <= s_max * (double)live_rows || keep_tune == 1;
         if (gather && m < 16384 && keep_tune != 1)   // a few thousand rows: eight queries per gathered scan pass are cheaper than GEMM rounds
             return search_prepared(h, qprep, nq, k, filter_dev, out_d, out_r, out_c, st);
         if (gather && ensure_dev(h, h->d_gx, (size_t)m * ld * 4 + (size_t)m * 4) != MLV_OK) {
@@ -379,6 +385,9 @@ int search_gemm(mlv_index* h, const float* qprep, uint32_t nq, uint32_t k, const
         rc = search_prepared(h, qprep + (size_t)q * ld, 1, k, filter_dev, out_d + (size_t)q * k, out_r + (size_t)q * k, out_c + q, st);
         if (rc != MLV_OK) return rc;
     }
+    // the dense copy of a filtered batch's rows can be a large fraction of the matrix: small ones are kept for the next
+    // batch, large ones go back to the allocator (every tier has synchronised `st` after its last use of the copy)
+    if (h->d_gx.bytes > ((size_t)1 << 30)) free_dev(h->d_gx);
     return MLV_OK;
 }
 
