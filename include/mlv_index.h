@@ -281,16 +281,21 @@ int mlv_format_f32_json(const float *values, uint64_t n, char *out, uint64_t cap
  * peers' lists (release/acquire flags at system scope) and merges.  Collective: every rank must
  * make the same sequence of calls.  Supported when mlv_index_exchange_supported(h, k) != 0
  * (k <= 55 on a 148-SM part); larger k uses the all-gather + mlv_merge_topk path.
- * A peer that does not arrive within 20 s raises an error flag (mlv_exchange_check) instead of
- * hanging the GPU.
+ * A peer that does not arrive within the exchange timeout (5 s by default; MLV_EXCHANGE_TIMEOUT_MS in the
+ * environment or mlv_exchange_set_timeout_ms) raises an error flag (mlv_exchange_check) instead of hanging
+ * the GPU; the searches of that launch report count -1.  After a timeout the ranks' sequence numbers are out
+ * of step: destroy and re-create the exchange on every rank.  At most two exchange searches may be in flight
+ * per handle (mlv_index_submit refuses a third).
  */
 typedef struct mlv_exchange *mlv_exchange_t;
 #define MLV_EXCHANGE_HANDLE_BYTES 64
 int mlv_exchange_create(int device, uint32_t world, uint32_t rank, mlv_exchange_t *out, unsigned char *handle_out);
 /* all_handles: world * MLV_EXCHANGE_HANDLE_BYTES bytes, rank-major (this rank's own entry is ignored). */
 int mlv_exchange_connect(mlv_exchange_t x, const unsigned char *all_handles);
-/* MLV_OK, or MLV_E_CUDA when a peer timed out in an earlier search (synchronises the device). */
+/* MLV_OK, or MLV_E_CUDA when a peer timed out in an earlier search (synchronises the device; reported once). */
 int mlv_exchange_check(mlv_exchange_t x);
+/* How long a search waits inside its kernel for a peer's candidates before it gives up (default 5000 ms). */
+int mlv_exchange_set_timeout_ms(mlv_exchange_t x, uint32_t ms);
 int mlv_exchange_destroy(mlv_exchange_t x);
 /* row_bases: world entries, the global row of every rank's local row 0.  x == NULL detaches. */
 int mlv_index_attach_exchange(mlv_index_t h, mlv_exchange_t x, const uint64_t *row_bases);

@@ -111,6 +111,7 @@ SIGNATURES = {
     "mlv_exchange_create": (C.c_int, [C.c_int, C.c_uint32, C.c_uint32, C.POINTER(_h), C.c_void_p]),
     "mlv_exchange_connect": (C.c_int, [_h, C.c_void_p]),
     "mlv_exchange_check": (C.c_int, [_h]),
+    "mlv_exchange_set_timeout_ms": (C.c_int, [_h, C.c_uint32]),
     "mlv_exchange_destroy": (C.c_int, [_h]),
     "mlv_index_attach_exchange": (C.c_int, [_h, _h, C.c_void_p]),
     "mlv_index_exchange_supported": (C.c_int, [_h, C.c_uint32]),

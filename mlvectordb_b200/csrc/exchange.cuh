@@ -5,9 +5,11 @@
 // last CTA of a rank's scan writes its k best keys per query straight into every peer's buffer
 // (plain stores to peer-mapped addresses), publishes a sequence number with st.release.sys and
 // waits with ld.acquire.sys until every peer's sequence number has arrived in its own buffer;
-// then it merges the world * k candidates.  Slots are indexed by seq mod 4: searches alternate
-// between at most two streams per handle, a rank can only reach search s+4 after every peer has
-// posted s+2, and a peer posts s+2 (same stream as s) only after it finished reading slot s.
+// then it merges the world * k candidates.  Slots are indexed by seq mod 4 and at most TWO exchange
+// searches are in flight per handle (mlv_index_submit enforces it; the synchronous entry points run one
+// at a time): a rank can only reach search s+4 after it collected s+2, i.e. after every peer has
+// posted s+2, and a peer posts s+2 only after it finished reading slot s (two in flight: s+2 starts on
+// a slot's stream after s left it, or after the host collected s).
 // The reference has no counterpart (single process; README.md:142-155 sketches sharding only).
 #pragma once
 #include "common.cuh"
@@ -22,7 +24,9 @@ constexpr uint32_t XCHG_SLOTS = 4;
 // buffer layout (u64 words): keys[XCHG_SLOTS][XCHG_MAX_WORLD][XCHG_MAX_NQ][XCHG_MAX_K], flags[XCHG_SLOTS][XCHG_MAX_WORLD]
 constexpr uint32_t XCHG_FLAGS_OFF = XCHG_SLOTS * XCHG_SLOT_KEYS;
 constexpr uint32_t XCHG_WORDS = XCHG_FLAGS_OFF + XCHG_SLOTS * XCHG_MAX_WORLD;
-constexpr unsigned long long XCHG_TIMEOUT_NS = 20000000000ull;  // a peer that never arrives: flag an error, do not hang
+// a peer that never arrives: flag an error, do not hang.  Default; MLV_EXCHANGE_TIMEOUT_MS / mlv_exchange_set_timeout_ms
+// change it (the wait holds the GPU, so a serving process wants it short; a skewed batch job wants it long).
+constexpr unsigned long long XCHG_TIMEOUT_NS = 5000000000ull;
 
 struct ExchangeView {
     uint64_t* bufs[XCHG_MAX_WORLD];      // every rank's buffer as mapped into THIS process (bufs[rank] is local)
@@ -30,6 +34,7 @@ struct ExchangeView {
     uint32_t world, rank;
     uint64_t seq;                        // 1-based, identical on all ranks for the same scan launch
     int* error;                          // set to 1 when a peer did not answer in time
+    unsigned long long timeout_ns;
 };
 
 __device__ __forceinline__ unsigned long long global_timer_ns() {
@@ -63,7 +68,7 @@ __device__ __forceinline__ void exchange_and_merge(const ExchangeView& x, const 
             uint64_t v;
             asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(mine) : "memory");
             if (v >= x.seq) break;
-            if (global_timer_ns() - t0 > XCHG_TIMEOUT_NS) {
+            if (global_timer_ns() - t0 > x.timeout_ns) {
                 *x.error = 1;
                 atomicOr(s_valid, 0x80000000u);
                 break;

@@ -284,14 +284,17 @@ int search_gemm(mlv_index* h, const float* qprep, uint32_t nq, uint32_t k, const
     view.norms = (const float*)h->d_norms.p;
     view.live = h->n_deleted ? h->d_live : nullptr;
     view.filter = filter_dev;
+    bool short_bitmap = false;
     mlv_filter* bf = filter_dev ? nullptr : h->bound_filter;
     if (bf) {
         if (bf->compact_gen != h->compact_gen)
             return fail(h, MLV_E_INVALID, "prepared filter predates a compaction / clear of the index (rows were renumbered); create it again");
-        if (bf->bitmap_words < (h->rows + 31) / 32) return fail(h, MLV_E_INVALID, "prepared filter is shorter than the index; re-create it");
         view.filter = (const uint32_t*)bf->d_bitmap.p;
+        // rows were appended after the filter was made (they do not pass): the bitmap cannot mask a full pass, but the
+        // row list still describes it -- such a batch always multiplies the compacted rows (or takes the gathered scan)
+        short_bitmap = bf->bitmap_words < (h->rows + 31) / 32;
     }
-    if (view.filter && h->tune_gather != 0) {
+    if (view.filter && (h->tune_gather != 0 || short_bitmap)) {
         // Selective filter: multiply only the passing-and-live rows.  Their list is the scan's gather list (prepared
         // filters keep it; a per-call bitmap builds it here); the rows are copied once into a dense matrix, which
         // costs a read + write of s x the matrix against a GEMM over all of it.
@@ -316,12 +319,13 @@ int search_gemm(mlv_index* h, const float* qprep, uint32_t nq, uint32_t k, const
         // small batches up to ~24 % (10M x 384: 256 queries at 50 % lost 10.6 vs 5.1 ms to the copy, 1024 won 12.3 vs 18.5).
         const double c = std::max(1.1, (double)nq / 120.0);
         const double s_max = 0.8 * c / (2.5 + c);
-        bool gather = (double)m <= s_max * (double)live_rows || keep_tune == 1;
+        bool gather = (double)m <= s_max * (double)live_rows || keep_tune == 1 || short_bitmap;
         if (gather && m < 16384 && keep_tune != 1)   // a few thousand rows: eight queries per gathered scan pass are cheaper than GEMM rounds
             return search_prepared(h, qprep, nq, k, filter_dev, out_d, out_r, out_c, st);
         if (gather && ensure_dev(h, h->d_gx, (size_t)m * ld * 4 + (size_t)m * 4) != MLV_OK) {
-            gather = false;   // no room for the copy beside the matrix: mask in the epilogue instead
             h->err.clear();
+            if (short_bitmap) return search_prepared(h, qprep, nq, k, filter_dev, out_d, out_r, out_c, st);   // the scan reads through the list
+            gather = false;   // no room for the copy beside the matrix: mask in the epilogue instead
         }
         if (gather) {
             float* gx = (float*)h->d_gx.p;

@@ -264,12 +264,15 @@ void fill_sched(mlv_index* h, Lane* ln, ScanParams& p) {
 // slots of the last CTA's candidate array for a fused final select
 uint32_t fused_cap(const ScanCfg& c, uint32_t k) { return pow2_ceil(std::max<uint32_t>((uint32_t)c.grid * k, 1024)); }
 
-// can the last CTA fold the whole grid's lists (and hold its scratch in the idle ring)?
+// can the last CTA fold the whole grid's lists?  Its scratch (candidate array + final lists) overlays the CTA's dynamic
+// shared memory from the start -- ring, queries, warp lists and barriers are all dead by then -- and search_prepared
+// pads the allocation when a tiny ring (small dimension x small shard) is shorter than that, so the decision depends
+// on k and the grid only: every rank of an exchange search takes the same one.
 bool fused_ok(const mlv_index* h, const ScanCfg& c, uint32_t k) {
     if (!h->tune_dynamic || !h->tune_fused) return false;
-    if ((uint64_t)c.grid * k > SCAN_FUSED_MAX_KEYS) return false;
-    return (size_t)c.S * c.stage_f4 * 16 >= ((size_t)fused_cap(c, k) + (size_t)c.NQ * k) * 8;
+    return (uint64_t)c.grid * k <= SCAN_FUSED_MAX_KEYS;
 }
+size_t fused_scratch_bytes(const ScanCfg& c, uint32_t k) { return ((size_t)fused_cap(c, k) + (size_t)c.NQ * k) * 8; }
 
 // the exchange path must take the same decision on every rank, whatever its shard's grid is
 bool exchange_ok(const mlv_index* h, uint32_t k) {
@@ -286,6 +289,7 @@ void fill_exchange(mlv_index* h, ExchangeView& x) {
         x.row_bases[i] = h->xchg_row_bases[i];
     }
     x.error = e->d_error;
+    x.timeout_ns = e->timeout_ns;
 }
 
 // What every scan launch of one search shares: the matrix, the ring shape, masks / gather list, scheduler.
@@ -325,6 +329,7 @@ int search_prepared(mlv_index* h, const float* qprep, uint32_t nq, uint32_t k, c
     // across GPUs it still replaces two all-gathers and a merge launch
     const bool fused = fused_ok(h, c, k) && (exchange || (uint64_t)c.grid * k <= 4096);
     if (exchange && !fused) return fail(h, MLV_E_UNSUPPORTED, "exchange search needs the fused final select");
+    if (fused) c.smem = std::max(c.smem, fused_scratch_bytes(c, k));
     const uint32_t F = SELECT_MAX_P / k;  // lists one select CTA can fold (>= 8)
     // bound the candidate scratch: chunk * grid * k keys
     uint32_t chunk = (uint32_t)std::max<size_t>(1, ((size_t)64 << 20) / ((size_t)c.grid * k * 8));

@@ -35,6 +35,7 @@ struct AsyncSlot {
     DevBuf d_q, d_out;
     uint32_t nq = 0, k = 0;
     bool busy = false;
+    bool exchange = false;   // an exchange search: at most two of those may be in flight (exchange.cuh slot reuse)
 };
 
 struct ScanCfg {
@@ -53,6 +54,7 @@ struct mlv_exchange {
     uint64_t* bufs[XCHG_MAX_WORLD] = {nullptr};  // bufs[rank] = local allocation, others IPC-opened
     int* d_error = nullptr;
     bool connected = false;
+    unsigned long long timeout_ns = XCHG_TIMEOUT_NS;
 };
 
 struct mlv_filter {
@@ -218,13 +220,18 @@ int reserve_rows(mlv_index* h, uint64_t need) {
         return fail_cuda(h, e, "cudaMalloc(live bitmap)");
     }
     // zero: padding columns must read as 0 forever, unused rows' bits as "not live"
-    CK(h, cudaMemsetAsync(nrows, 0, cap * row_bytes, h->stream));
-    CK(h, cudaMemsetAsync(nlive, 0, words * 4, h->stream));
-    if (h->rows) {
-        CK(h, cudaMemcpyAsync(nrows, h->d_rows, h->rows * row_bytes, cudaMemcpyDeviceToDevice, h->stream));
-        CK(h, cudaMemcpyAsync(nlive, h->d_live, ((h->rows + 31) / 32) * 4, cudaMemcpyDeviceToDevice, h->stream));
+    e = cudaMemsetAsync(nrows, 0, cap * row_bytes, h->stream);
+    if (e == cudaSuccess) e = cudaMemsetAsync(nlive, 0, words * 4, h->stream);
+    if (e == cudaSuccess && h->rows) {
+        e = cudaMemcpyAsync(nrows, h->d_rows, h->rows * row_bytes, cudaMemcpyDeviceToDevice, h->stream);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(nlive, h->d_live, ((h->rows + 31) / 32) * 4, cudaMemcpyDeviceToDevice, h->stream);
     }
-    CK(h, cudaStreamSynchronize(h->stream));
+    if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+    if (e != cudaSuccess) {   // the old matrix stays in place; the new buffers go back
+        cudaFree(nrows);
+        cudaFree(nlive);
+        return fail_cuda(h, e, "growing the row matrix");
+    }
     if (h->d_rows) cudaFree(h->d_rows);
     if (h->d_live) cudaFree(h->d_live);
     h->d_rows = nrows;

@@ -191,7 +191,14 @@ static int upload_rows_staged(mlv_index_t h, float* dst, const float* rows, uint
     int rc = ensure_host(h, h->h_upload, 2 * chunk_rows * row_bytes);
     if (rc != MLV_OK) return rc;
     cudaEvent_t done[2] = {nullptr, nullptr};
-    for (auto& ev : done) CK(h, cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    for (auto& ev : done) {
+        cudaError_t ce = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
+        if (ce != cudaSuccess) {
+            for (auto& made : done)
+                if (made) cudaEventDestroy(made);
+            return fail_cuda(h, ce, "row upload events");
+        }
+    }
     const unsigned n_threads = std::max(1u, std::min(8u, std::thread::hardware_concurrency() / 2));
     cudaError_t e = cudaSuccess;
     int slot = 0;
@@ -623,7 +630,15 @@ int mlv_exchange_create(int device, uint32_t world, uint32_t rank, mlv_exchange_
     x->d_error = (int*)((uint64_t*)buf + XCHG_WORDS);  // behind the slots, in the same allocation
     memcpy(handle_out, &hd, sizeof(hd));
     x->connected = world == 1;
+    const int ms = env_int("MLV_EXCHANGE_TIMEOUT_MS", 0);
+    if (ms > 0) x->timeout_ns = (unsigned long long)ms * 1000000ull;
     *out = x;
+    return MLV_OK;
+}
+
+int mlv_exchange_set_timeout_ms(mlv_exchange_t x, uint32_t ms) {
+    if (!x || ms == 0) return MLV_E_INVALID;
+    x->timeout_ns = (unsigned long long)ms * 1000000ull;
     return MLV_OK;
 }
 
@@ -653,7 +668,8 @@ int mlv_exchange_check(mlv_exchange_t x) {
         cudaGetLastError();
         return MLV_E_CUDA;
     }
-    return err ? MLV_E_CUDA : MLV_OK;
+    if (err) cudaMemset(x->d_error, 0, sizeof(int));   // reported once; the ranks' sequence numbers are out of step now:
+    return err ? MLV_E_CUDA : MLV_OK;                   // the caller re-creates the exchange (collective) before searching on
 }
 
 int mlv_exchange_destroy(mlv_exchange_t x) {
@@ -783,6 +799,11 @@ int mlv_index_submit(mlv_index_t h, const float* queries, uint32_t nq, uint32_t 
         }
     }
     if (idx < 0) return fail(h, MLV_E_UNSUPPORTED, "all asynchronous search slots are in flight: collect one first");
+    if (exchange) {
+        int flying = 0;
+        for (const AsyncSlot& s2 : h->slots) flying += s2.busy && s2.exchange;
+        if (flying >= 2) return fail(h, MLV_E_UNSUPPORTED, "two exchange searches are in flight already: collect one first");
+    }
     h->next_slot = (uint32_t)(idx + 1) % MLV_ASYNC_SLOTS;
     AsyncSlot& sl = h->slots[idx];
     if (!sl.stream) {
@@ -812,6 +833,7 @@ int mlv_index_submit(mlv_index_t h, const float* queries, uint32_t nq, uint32_t 
     sl.nq = nq;
     sl.k = k;
     sl.busy = true;
+    sl.exchange = exchange != 0;
     *ticket = (uint32_t)idx;
     return MLV_OK;
 }

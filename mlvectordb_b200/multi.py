@@ -159,11 +159,23 @@ class MultiGpuIndex:
             return md.cpu().numpy(), mr.cpu().numpy(), mc.cpu().numpy()
 
     # ------------------------------------------------------------------ IndexProtocol
+    def _check_dim(self, namespace: str, dim: int) -> None:
+        """The namespace's dimension is fixed by its first block on ANY part: a part that does not hold the namespace yet
+        would otherwise create it with whatever dimension its slice has (hnswlib's add_items error, reference
+        index.py:65 / GpuIndex.add)."""
+        have = self.dimension(namespace)
+        if have is not None and int(dim) != have:
+            raise RuntimeError("Wrong dimensionality of the vectors")
+
     def add(self, vectors: Iterable[VectorProtocol], namespace: str) -> None:
         """reference index.py:50-67; the block is split over the parts (fewest live rows first)."""
         vectors = list(vectors)
         if not vectors:
             return
+        dims = {int(np.asarray(v.values).shape[0]) for v in vectors}
+        if len(dims) != 1:
+            raise RuntimeError("Wrong dimensionality of the vectors")
+        self._check_dim(namespace, dims.pop())
         sizes = split_block(len(vectors), [self._live(p, namespace) for p in self._parts])
         at = 0
         for part, n in zip(self._parts, sizes):
@@ -184,7 +196,7 @@ class MultiGpuIndex:
         if top_k < 1:
             return []
         q = np.asarray(query.values, dtype=np.float32).reshape(-1)
-        if q.shape[0] != holders[0][2].dim:
+        if any(q.shape[0] != ns.dim for _, _, ns in holders):
             return []                                  # the reference swallows the dimension error into [] (index.py:110-119)
         dists, rows, counts = self._fanout(holders, q[None, :], top_k, self._part_filters(holders, filter))
         return self._results(namespace, dists[0], rows[0], int(counts[0]), metric)
@@ -213,18 +225,31 @@ class MultiGpuIndex:
         return None
 
     def add_matrix(self, matrix: np.ndarray, namespace: str, ids: Optional[Sequence[UUID]] = None,
-                   columns: Optional[Mapping[str, Sequence]] = None) -> np.ndarray:
-        """Bulk ingest: the matrix is cut into one block per part.  Returns the rows' UUID bytes [n, 16]."""
+                   columns: Optional[Mapping[str, Sequence]] = None,
+                   metadata: Optional[Sequence[Optional[Mapping]]] = None) -> np.ndarray:
+        """Bulk ingest: the matrix is cut into one block per part; ``columns`` / ``metadata`` (as
+        ``GpuIndex.add_matrix``) are cut the same way.  Returns the rows' UUID bytes [n, 16]."""
         data = np.ascontiguousarray(matrix, dtype=np.float32)
         if data.ndim != 2:
             raise ValueError("matrix must be [n, dim]")
+        if data.shape[0] == 0:
+            return np.empty((0, 16), dtype=np.uint8)
+        self._check_dim(namespace, data.shape[1])
+        if ids is not None and len(ids) != data.shape[0]:
+            raise ValueError("len(ids) != rows")
+        if metadata is not None and len(metadata) != data.shape[0]:
+            raise ValueError("len(metadata) != rows")
+        for name, values in (columns or {}).items():
+            if len(values) != data.shape[0]:
+                raise ValueError(f"column {name!r} has {len(values)} values for {data.shape[0]} rows")
         out = np.empty((data.shape[0], 16), dtype=np.uint8)
         at = 0
         for part, n in zip(self._parts, split_block(data.shape[0], [self._live(p, namespace) for p in self._parts])):
             if n:
                 cols = {key: np.asarray(v)[at:at + n] for key, v in (columns or {}).items()}
                 out[at:at + n] = part.add_matrix(data[at:at + n], namespace, ids=ids[at:at + n] if ids is not None else None,
-                                                 columns=cols or None)
+                                                 columns=cols or None,
+                                                 metadata=metadata[at:at + n] if metadata is not None else None)
                 at += n
         return out
 
@@ -236,7 +261,7 @@ class MultiGpuIndex:
         nq = q.shape[0]
         holders = [h for h in self._holders(namespace) if self._live(h[1], namespace) > 0]
         k = min(int(top_k), sum(self._live(p, namespace) for _, p, _ in holders))
-        if k < 1 or q.shape[1] != holders[0][2].dim:
+        if k < 1 or any(q.shape[1] != ns.dim for _, _, ns in holders):
             return (np.full((nq, 0), -1, np.int64), np.empty((nq, 0), np.float32), np.zeros(nq, np.int32))
         dists, rows, counts = self._fanout(holders, q, k, self._part_filters(holders, filter))
         if (metric if metric is not None else self._space) == "cosine":
@@ -256,7 +281,7 @@ class MultiGpuIndex:
         if not holders:
             return []
         q = np.asarray(query.values, dtype=np.float32).reshape(-1)
-        if q.shape[0] != holders[0][2].dim:
+        if any(q.shape[0] != ns.dim for _, _, ns in holders):
             return []
         lists = []
         for (i, part, ns), flt in zip(holders, self._part_filters(holders, filter)):

@@ -156,8 +156,14 @@ class GpuQueryProcessor:
         id_bytes = _random_uuid_bytes(n)
         ids = [UUID(bytes=id_bytes[i].tobytes()) for i in range(n)]
         vecs = StoredVector.rows_of(data, ids, metadata)
-        self._storage.write_vectors(vecs, namespace)
+        # index first: it is the step that can refuse the block (wrong dimension, out of device memory); a block the
+        # index refused never reaches the storage, so the two cannot disagree
         self._index.add_matrix(data, namespace, ids=ids, metadata=metadata)
+        try:
+            self._storage.write_vectors(vecs, namespace)
+        except Exception:
+            self._index.remove(ids, namespace)
+            raise
         self._touch(namespace)
         return ids
 

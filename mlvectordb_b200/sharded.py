@@ -17,7 +17,7 @@ merge of the shards' top-k -- is checked in ``tests/test_gpu_parity.py``.
 from __future__ import annotations
 
 import ctypes as C
-from typing import Callable, Optional, Tuple
+from typing import Callable, Optional, Sequence, Tuple
 
 import numpy as np
 import torch
@@ -82,14 +82,23 @@ class ShardedIndex:
 
     def __init__(self, dim: int, space: str, total_rows: int, device: Optional[torch.device] = None, group=None,
                  local_search: Optional[Callable] = None, merge: Optional[Callable] = None, fused_exchange: bool = True,
-                 local_range: Optional[Callable] = None, order_hits: Optional[Callable] = None):
+                 local_range: Optional[Callable] = None, order_hits: Optional[Callable] = None,
+                 row_bases: Optional[Sequence[int]] = None, capacity: int = 0, shard=None):
+        """``row_bases`` (one per rank) switches from fixed contiguous blocks of ``total_rows`` to PART mode: rank r's
+        rows are numbered ``row_bases[r] + local row`` and the shard grows by appends (``ShardedGpuIndex``); ties are
+        then ordered by (distance, rank, local row)."""
         self.dim, self.space, self.total_rows = int(dim), space, int(total_rows)
         self.group = group
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
-        self.lo, self.hi = shard_range(self.total_rows, self.rank, self.world)
+        self.row_bases = [int(b) for b in row_bases] if row_bases is not None else None
+        if self.row_bases is not None:
+            assert len(self.row_bases) == self.world
+            self.lo, self.hi = self.row_bases[self.rank], None
+        else:
+            self.lo, self.hi = shard_range(self.total_rows, self.rank, self.world)
         self.device = device
-        self.shard = None
+        self.shard = shard          # injected stand-in (CPU tests); the real DeviceShard is created below
         # the two device steps are injectable so the collective plumbing can be exercised on CPU (gloo)
         self._local_search = local_search or self._device_local_search
         self._merge = merge or merge_topk_device
@@ -99,7 +108,8 @@ class ShardedIndex:
         self.exchange = None
         if local_search is None:
             from .shard import DeviceShard
-            self.shard = DeviceShard(dim, space, capacity=max(self.hi - self.lo, 1), device=device.index, row_base=self.lo)
+            cap = int(capacity) if self.hi is None else max(self.hi - self.lo, 1)
+            self.shard = DeviceShard(dim, space, capacity=cap, device=device.index, row_base=self.lo)
             if self.world > 1 and fused_exchange:
                 self._setup_exchange()
 
@@ -127,7 +137,7 @@ class ShardedIndex:
         flags = [None] * self.world
         dist.all_gather_object(flags, ok, group=self.group)
         if all(flags):
-            bases = [shard_range(self.total_rows, r, self.world)[0] for r in range(self.world)]
+            bases = self.row_bases or [shard_range(self.total_rows, r, self.world)[0] for r in range(self.world)]
             self.shard.attach_exchange(ex, bases)
             self.exchange = ex
         elif ex is not None:
@@ -206,6 +216,9 @@ class ShardedIndex:
             if (out[2] < 0).any():
                 raise RuntimeError("sharded search: a peer rank did not post its candidates within the exchange timeout")
             return out
+        if self.device is None:      # CPU plumbing tests (gloo): nothing to stage
+            d, r, c = self.search_device(torch.from_numpy(q), k)
+            return d.numpy(), r.numpy(), c.numpy()
         st = self._staging(nq, k)
         st["q"][:nq].copy_(torch.from_numpy(q))
         qd = st["q"][:nq].to(self.device, non_blocking=True)
@@ -224,14 +237,17 @@ class ShardedIndex:
         a caller that keeps two in flight hides each request's copies and launch latency behind the other's scan.
         Needs the fused exchange path (k small, batch < EXCHANGE_MAX_NQ); otherwise the search runs synchronously."""
         q = np.ascontiguousarray(queries, dtype=np.float32).reshape(-1, self.dim)
-        if self.shard is not None and q.shape[0] < self.EXCHANGE_MAX_NQ and (
+        if self.device is not None and self.shard is not None and q.shape[0] < self.EXCHANGE_MAX_NQ and (
                 self.world == 1 or (self.exchange is not None and self.shard.exchange_supported(k))):
             return self.shard.submit(q, k, exchange=self.world > 1)
         return _Done(self.search(q, k))
 
     # -- range search ------------------------------------------------------------------------
+    def _local_empty(self) -> bool:
+        return (self.shard.rows == 0) if self.hi is None else (self.hi == self.lo)
+
     def _device_local_range(self, queries: np.ndarray, radius: float):
-        if self.hi == self.lo:
+        if self._local_empty():
             return [(np.empty(0, np.float32), np.empty(0, np.int64)) for _ in range(queries.shape[0])]
         return self.shard.range_search(queries, radius)   # rows already carry row_base
 

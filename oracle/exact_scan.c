@@ -255,3 +255,166 @@ int orc_num_threads(void) {
     return 1;
 #endif
 }
+
+void orc_set_threads(int n) {
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}
+
+/* ------------------------------------------- streamed oracle over the synthetic generator
+ * Exact kNN / range search over generator rows first_row .. first_row+n-1 WITHOUT materialising
+ * them: every thread regenerates one row at a time (same syn_elem / syn_row_scale as
+ * orc_fill_synthetic), normalises it like orc_normalize when space == cosine, and scores it with
+ * orc_dist against all queries.  Bit-identical to orc_fill_synthetic -> orc_normalize -> orc_knn on
+ * the same rows (tests/test_oracle.py checks that), but a 10M x 768 pass costs seconds and no
+ * memory, so parity at BASELINE.json's full sizes (SURVEY.md 8d "run at full N") is affordable.
+ *   allow   optional bitmap over (row - first_row), LSB first; 1 = candidate (tombstones AND filter)
+ *   labels  generator row numbers
+ * Queries must already be normalised for cosine.
+ */
+static void syn_row(float *o, uint64_t key, uint64_t key2, uint64_t row, uint64_t d, int scaled, int space) {
+    float s = scaled ? syn_row_scale(key2, row) : 1.0f;
+    for (uint64_t c = 0; c < d; c++) {
+        float v = syn_elem(key, row, c, d);
+        o[c] = scaled ? v * s : v;
+    }
+    if (space == ORC_COSINE) {
+        float norm = 0.0f;
+        for (uint64_t i = 0; i < d; i++) norm += o[i] * o[i];
+        norm = 1.0f / (sqrtf(norm) + 1e-30f);
+        for (uint64_t i = 0; i < d; i++) o[i] = o[i] * norm;
+    }
+}
+
+void orc_knn_synthetic(uint64_t seed, uint64_t first_row, uint64_t n, uint64_t d, int scaled, const float *queries,
+                       size_t nq, int k, int space, int simd16, const uint32_t *allow, int64_t *out_labels,
+                       float *out_dists, int32_t *out_counts) {
+    const uint64_t key = splitmix64(seed), key2 = splitmix64(seed ^ 0xA5A5A5A5A5A5A5A5ULL);
+    int nthreads = 1;
+#ifdef _OPENMP
+    nthreads = omp_get_max_threads();
+#endif
+    orc_cand *heaps = (orc_cand *)malloc(sizeof(orc_cand) * (size_t)k * nq * nthreads);
+    int *counts = (int *)calloc((size_t)nthreads * nq, sizeof(int));
+#pragma omp parallel
+    {
+        int t = 0;
+#ifdef _OPENMP
+        t = omp_get_thread_num();
+#endif
+        float *row = (float *)malloc(sizeof(float) * d);
+        orc_cand *h = heaps + (size_t)t * nq * k;
+        int *cnt = counts + (size_t)t * nq;
+#pragma omp for schedule(static)
+        for (int64_t r = 0; r < (int64_t)n; r++) {
+            if (allow && !((allow[r >> 5] >> (r & 31)) & 1u)) continue;
+            syn_row(row, key, key2, first_row + (uint64_t)r, d, scaled, space);
+            for (size_t qi = 0; qi < nq; qi++) {
+                orc_cand c;
+                c.d = orc_dist(row, queries + qi * d, d, space, simd16);
+                c.l = (int64_t)(first_row + (uint64_t)r);
+                heap_push(h + qi * k, &cnt[qi], k, c);
+            }
+        }
+        free(row);
+    }
+    orc_cand *all = (orc_cand *)malloc(sizeof(orc_cand) * (size_t)k * nthreads);
+    for (size_t qi = 0; qi < nq; qi++) {
+        size_t total = 0;
+        for (int t = 0; t < nthreads; t++) {
+            int c = counts[(size_t)t * nq + qi];
+            memcpy(all + total, heaps + ((size_t)t * nq + qi) * k, sizeof(orc_cand) * c);
+            total += c;
+        }
+        qsort(all, total, sizeof(orc_cand), cand_cmp);
+        int m = total < (size_t)k ? (int)total : k;
+        for (int j = 0; j < k; j++) {
+            out_labels[qi * k + j] = j < m ? all[j].l : -1;
+            out_dists[qi * k + j] = j < m ? all[j].d : INFINITY;
+        }
+        out_counts[qi] = m;
+    }
+    free(all);
+    free(heaps);
+    free(counts);
+}
+
+/* Every candidate row with distance <= radius, ascending (distance, label).  out_counts[q] = total hits;
+ * at most max_hits of them (the smallest) are written to out_labels / out_dists [nq, max_hits]. */
+void orc_range_synthetic(uint64_t seed, uint64_t first_row, uint64_t n, uint64_t d, int scaled, const float *queries,
+                         size_t nq, float radius, int space, int simd16, const uint32_t *allow, uint64_t max_hits,
+                         int64_t *out_labels, float *out_dists, uint64_t *out_counts) {
+    const uint64_t key = splitmix64(seed), key2 = splitmix64(seed ^ 0xA5A5A5A5A5A5A5A5ULL);
+    int nthreads = 1;
+#ifdef _OPENMP
+    nthreads = omp_get_max_threads();
+#endif
+    /* per (thread, query) growable hit lists */
+    orc_cand **lists = (orc_cand **)calloc((size_t)nthreads * nq, sizeof(orc_cand *));
+    size_t *lens = (size_t *)calloc((size_t)nthreads * nq, sizeof(size_t));
+    size_t *caps = (size_t *)calloc((size_t)nthreads * nq, sizeof(size_t));
+#pragma omp parallel
+    {
+        int t = 0;
+#ifdef _OPENMP
+        t = omp_get_thread_num();
+#endif
+        float *row = (float *)malloc(sizeof(float) * d);
+#pragma omp for schedule(static)
+        for (int64_t r = 0; r < (int64_t)n; r++) {
+            if (allow && !((allow[r >> 5] >> (r & 31)) & 1u)) continue;
+            syn_row(row, key, key2, first_row + (uint64_t)r, d, scaled, space);
+            for (size_t qi = 0; qi < nq; qi++) {
+                float dist = orc_dist(row, queries + qi * d, d, space, simd16);
+                if (!(dist <= radius)) continue;
+                size_t s = (size_t)t * nq + qi;
+                if (lens[s] == caps[s]) {
+                    caps[s] = caps[s] ? caps[s] * 2 : 64;
+                    lists[s] = (orc_cand *)realloc(lists[s], sizeof(orc_cand) * caps[s]);
+                }
+                lists[s][lens[s]].d = dist;
+                lists[s][lens[s]].l = (int64_t)(first_row + (uint64_t)r);
+                lens[s]++;
+            }
+        }
+        free(row);
+    }
+    for (size_t qi = 0; qi < nq; qi++) {
+        size_t total = 0;
+        for (int t = 0; t < nthreads; t++) total += lens[(size_t)t * nq + qi];
+        orc_cand *all = (orc_cand *)malloc(sizeof(orc_cand) * (total ? total : 1));
+        size_t p = 0;
+        for (int t = 0; t < nthreads; t++) {
+            size_t s = (size_t)t * nq + qi;
+            if (lens[s]) memcpy(all + p, lists[s], sizeof(orc_cand) * lens[s]);
+            p += lens[s];
+            free(lists[s]);
+        }
+        qsort(all, total, sizeof(orc_cand), cand_cmp);
+        out_counts[qi] = total;
+        for (uint64_t j = 0; j < max_hits && j < total; j++) {
+            out_labels[qi * max_hits + j] = all[j].l;
+            out_dists[qi * max_hits + j] = all[j].d;
+        }
+        free(all);
+    }
+    free(lists);
+    free(lens);
+    free(caps);
+}
+
+/* distances of generator rows `labels[0..m)` (regenerated one by one) to one query: adjudication of ids
+ * that are in a result but not in the oracle's top-k (oracle/exact.py::check_topk_parity all_ref_scores) */
+void orc_distances_synthetic(uint64_t seed, const int64_t *labels, size_t m, uint64_t d, int scaled, const float *q,
+                             int space, int simd16, float *out) {
+    const uint64_t key = splitmix64(seed), key2 = splitmix64(seed ^ 0xA5A5A5A5A5A5A5A5ULL);
+    float *row = (float *)malloc(sizeof(float) * d);
+    for (size_t i = 0; i < m; i++) {
+        syn_row(row, key, key2, (uint64_t)labels[i], d, scaled, space);
+        out[i] = orc_dist(row, q, d, space, simd16);
+    }
+    free(row);
+}

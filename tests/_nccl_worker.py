@@ -126,6 +126,64 @@ def main():
             whole.close()
         idx.close()
 
+    def check_protocol_index():
+        """``ShardedGpuIndex`` (reference Index protocol, one process per GPU): every rank makes the same calls; the
+        answers equal a single ``GpuIndex`` holding all rows on rank 0 (ids; scores bit for bit)."""
+        from uuid import UUID
+        from mlvectordb_b200 import GpuIndex, VectorDTO
+        from mlvectordb_b200.sharded_index import ShardedGpuIndex
+
+        class V:
+            def __init__(self, uid, values, metadata):
+                self.id, self.values, self.metadata = uid, values, metadata
+
+        n, dim = 40_000, 64
+        X = synthetic.rows(21, 0, n, dim, scaled=True)
+        vecs = [V(UUID(int=10_000 + i), X[i], {"b": i % 10}) for i in range(n)]
+        sharded = ShardedGpuIndex(space="cosine", device=device)
+        single = GpuIndex(space="cosine", device=rank) if rank == 0 else None
+        for lo, hi in ((0, 5), (5, 10_000), (10_000, n)):
+            sharded.add(vecs[lo:hi], "ns")
+            if single:
+                single.add(vecs[lo:hi], "ns")
+        per_rank = sharded.info("ns")["rows_per_rank"]
+        assert sum(per_rank) == n and max(per_rank) - min(per_rank) <= 1
+        Q = synthetic.queries(22, 4, dim)
+        Q[0] = X[n - 3]
+
+        def compare(k, **kw):
+            for q in Q:
+                got = sharded.search(VectorDTO(values=q), k, "ns", "cosine", **kw)
+                if single:
+                    want = single.search(VectorDTO(values=q), k, "ns", "cosine", **kw)
+                    assert [h.vector_id for h in got] == [h.vector_id for h in want], f"k={k} {kw}"
+                    assert [h.score for h in got] == [h.score for h in want]
+
+        compare(10)                               # fused peer-memory exchange
+        compare(200)                              # NCCL all-gather + merge kernel
+        compare(10, filter={"b": 7})              # per-rank device predicate
+        pend = [sharded.search_async(VectorDTO(values=Q[i]), 10, "ns", "cosine") for i in range(2)]   # two in flight
+        for i, p in enumerate(pend):
+            got = p.result()
+            if single:
+                assert [h.vector_id for h in got] == [h.vector_id for h in single.search(VectorDTO(values=Q[i]), 10, "ns", "cosine")]
+        gone = [v.id for v in vecs[1::3]]
+        sharded.remove(gone, "ns")                # 33 % >= 0.2: every rank compacts its shard, id tables renumbered
+        if single:
+            single.remove(gone, "ns")
+        assert sharded.info("ns")["tombstones"] == 0 and sharded.info("ns")["live"] == n - len(gone)
+        compare(10)
+        got = sharded.range_search(VectorDTO(values=Q[1]), 0.75, "ns", "cosine")
+        if single:
+            want = single.range_search(VectorDTO(values=Q[1]), 0.75, "ns", "cosine")
+            assert [h.vector_id for h in got] == [h.vector_id for h in want] and len(want) > 0
+        sharded.rebuild({"fresh": vecs[:100]}, "l2")
+        hit = sharded.search(VectorDTO(values=X[42]), 1, "fresh", "l2")
+        assert hit[0].vector_id == vecs[42].id and hit[0].score == 0.0 and sharded.namespaces() == ["fresh"]
+        sharded.close()
+        if single:
+            single.close()
+
     def idx_range(n, r, w):
         from mlvectordb_b200.sharded import shard_range
         return shard_range(n, r, w)
@@ -140,6 +198,7 @@ def main():
     check_big_range(120_001, 16)                           # > 8192 hits per query: device-wide ordering
     check_filtered(150_001, 64, "cosine", 10, 4)           # filtered, fused exchange
     check_filtered(150_001, 64, "l2", 100, 3)              # filtered, NCCL merge path
+    check_protocol_index()                                 # reference Index protocol over the ranks
     dist.barrier()
     print(f"rank {rank} ok", flush=True)
     dist.destroy_process_group()

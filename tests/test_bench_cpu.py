@@ -19,6 +19,19 @@ def test_reference_arm_json_line():
     cb = line["cpu_baseline"]
     assert cb["kind"] == "port" and cb["cores"] >= 1 and "scaled by 0.5" in cb["sample"] and cb["value"] == line["value"]
     assert line["config"]["rows"] == 40000 and "workload" in line["config"]
+    assert line["config"]["queries_per_step"] == 32          # the GPU arm's step, not a shortened one
+
+
+def test_reference_arm_uses_every_core_under_torchrun_env():
+    """torchrun exports OMP_NUM_THREADS=1 to its workers; the reference arm must not inherit a 1-core baseline."""
+    env = dict(os.environ, OMP_NUM_THREADS="1", RANK="0", WORLD_SIZE="2")
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--rows", "20000", "--dim", "32",
+                          "--cpu-sample-rows", "20000", "--steps", "1", "--warmup", "1", "--queries-per-step", "4"],
+                         capture_output=True, text=True, timeout=300, cwd=ROOT, env=env)
+    assert out.returncode == 0, out.stderr[-2000:]
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    assert line["cpu_baseline"]["cores"] == len(os.sched_getaffinity(0))
+    assert line["cpu_baseline"]["row_prefix_used"] is False and line["config"]["queries_per_step"] == 4
 
 
 def test_reference_arm_other_ranks_exit_quietly():

@@ -277,9 +277,17 @@ def test_range_search_hit_lists_longer_than_one_sort_block():
     assert len(r0) == 12_001
     L, D = exact.range_search(X, Q, radius, "l2")
     for got_r, got_d, ref_r, ref_d in ((r0, d0, L[0], D[0]), (r1, d1, L[1], D[1])):
-        assert len(got_r) == len(ref_r)
-        assert set(got_r.tolist()) == set(np.asarray(ref_r).tolist()) or len(set(got_r.tolist()) ^ set(np.asarray(ref_r).tolist())) <= 4
+        # ids may differ only for rows whose oracle distance is within tolerance of the radius (each adjudicated)
+        tol = 1e-5 * abs(radius) + 1e-6
+        qi = 0 if got_r is r0 else 1
+        odd = sorted(set(got_r.tolist()) ^ set(np.asarray(ref_r).tolist()))
+        assert abs(len(got_r) - len(ref_r)) <= len(odd)
+        for row in odd:
+            assert abs(float(exact.distances(X[row:row + 1], Q[qi], "l2")[0]) - radius) <= 2 * tol, f"row {row} is not at the radius"
         assert np.all(np.diff(got_d) >= 0), "hits are not ascending"
+        keep = ~np.isin(got_r, odd)
+        ref_keep = ~np.isin(np.asarray(ref_r), odd)
+        assert got_r[keep].tolist() == np.asarray(ref_r)[ref_keep].tolist() or exact.scores_close(got_d[keep], np.asarray(ref_d)[ref_keep]).all()
     s.close()
 
 

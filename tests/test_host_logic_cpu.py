@@ -88,6 +88,27 @@ def test_snapshot_round_trip_host_side(tmp_path):
     back.remove([victim], "big")                     # the id map is rebuilt lazily from the restored id table
     assert victim not in {r.vector_id for r in back.search(VectorDTO(values=Q[0]), k, "big", "cosine")}
     assert back.is_rebuild_required("big") == idx.is_rebuild_required("big") or back.is_rebuild_required("big")
+    # saving over the snapshot writes a new generation beside the old one and switches the manifest last:
+    # a save that dies before the switch leaves the previous snapshot loadable, and stale files are cleaned up
+    import os
+    snap = str(tmp_path / "snap")
+    files0 = sorted(os.listdir(snap))
+    assert all(f.startswith("g0.") or f == "manifest.json" for f in files0)
+    import mlvectordb_b200.snapshot as snapshot
+    real_replace = os.replace
+    def boom(*a, **kw):
+        raise OSError("crash before the manifest switch")
+    snapshot.os.replace = boom
+    try:
+        with pytest.raises(OSError):
+            back.save(snap)
+    finally:
+        snapshot.os.replace = real_replace
+    again = GpuIndex.load(snap)                       # still the first snapshot (victim not yet removed in it)
+    assert again.info("big")["tombstones"] == len(gone)
+    m2 = back.save(snap)
+    assert m2["generation"] == 1 and all(f.startswith("g1.") or f == "manifest.json" for f in os.listdir(snap))
+    assert GpuIndex.load(snap).info("big")["tombstones"] == len(gone) + 1
 
 
 def test_http_surface_over_the_real_processor():
@@ -101,7 +122,7 @@ def test_http_surface_over_the_real_processor():
 
 
 class _V:
-    def __init__(self, values, metadata):
+    def __init__(self, values, metadata=None):
         import uuid
         self.id, self.values, self.metadata = uuid.uuid4(), np.asarray(values, np.float32), metadata
 
@@ -198,6 +219,34 @@ def test_multi_gpu_index_behind_the_query_processors():
     assert [h["metadata"]["t"] for h in hits] == ["y"]
     deleted = qp.delete([hits[0]["id"]])
     assert deleted == [hits[0]["id"]] and len(qp.find_similar(VectorDTO(values=[1, 0, 0]), 10)) == 3
+
+
+def test_multi_gpu_index_bulk_ingest_and_dimension_guard():
+    """``GpuQueryProcessor.upsert_matrix`` over a ``MultiGpuIndex`` (metadata cut per part), and a
+    wrong-dimension block is refused even by a part that does not hold the namespace yet -- before the storage sees it."""
+    from mlvectordb_b200 import GpuQueryProcessor, VectorDTO
+    from oracle import synthetic
+    many = _multi("cosine", n_parts=3)
+    storage = InMemoryStorage()
+    qp = GpuQueryProcessor(storage, many)
+    X = synthetic.rows(2, 0, 50, 8, scaled=True)
+    ids = qp.upsert_matrix(X, "bulk", metadata=[{"b": i % 4} for i in range(50)])
+    assert len(ids) == 50 and many.info("bulk")["rows"] == 50 and many.metadata_columns("bulk") == ["b"]
+    hits = qp.find_similar(VectorDTO(values=X[7].tolist()), 3, namespace="bulk", filter={"b": 3})
+    assert hits[0]["id"] == ids[7] and all(h["metadata"]["b"] == 3 for h in hits)
+    stored_before = qp.get_namespace_count("bulk")
+    with pytest.raises(RuntimeError, match="dimensionality"):
+        qp.upsert_matrix(synthetic.rows(2, 0, 2, 9), "bulk")           # 2 rows -> only two parts get a slice
+    assert qp.get_namespace_count("bulk") == stored_before and many.info("bulk")["rows"] == 50
+    one_row = _multi("l2", n_parts=3)
+    one_row.add([_V(np.ones(4))], "ns")                                  # lives on part 0 only
+    with pytest.raises(RuntimeError, match="dimensionality"):
+        one_row.add([_V(np.ones(5))], "ns")                              # would have landed on the empty part 1
+    with pytest.raises(RuntimeError, match="dimensionality"):
+        one_row.add([_V(np.ones(4)), _V(np.ones(5))], "fresh")
+    assert one_row.search(VectorDTO(values=[1.0] * 5), 1, "ns", "l2") == []
+    many.close()
+    one_row.close()
 
 
 def test_http_surface_over_a_multi_gpu_index():

@@ -186,3 +186,46 @@ def test_streaming_knn_equals_in_memory_and_range_semantics():
     assert Lr[0].tolist() == L1[0][:10].tolist()           # d <= radius is inclusive
     assert exact.check_topk_parity([1, 2], [0.5, 0.5 + 1e-9], [2, 1], [0.5, 0.5]) is None   # tie swap allowed
     assert exact.check_topk_parity([1, 3], [0.5, 0.9], [1, 2], [0.5, 0.6]) is not None
+
+
+@pytest.mark.parametrize("space,scaled", [("l2", False), ("ip", True), ("cosine", True)])
+def test_streamed_synthetic_oracle_equals_the_materialised_one(space, scaled):
+    """orc_knn_synthetic / orc_range_synthetic regenerate rows on the fly; they must be bit-identical to
+    fill_synthetic -> normalize -> knn on the same rows (that is what lets full-size GPU tests use them)."""
+    n, d, k, first = 20_000, 96, 10, 1000
+    Q = synthetic.queries(7, 5, d)
+    X = cscan.fill_synthetic(42, first, n, d, scaled)
+    Xn = cscan.normalize(X) if space == "cosine" else X
+    Qn = cscan.normalize(Q) if space == "cosine" else Q
+    L0, D0, C0 = cscan.knn(Xn, Qn, k, space, first_label=first)
+    L1, D1, C1 = cscan.knn_synthetic(42, first, n, d, scaled, Q, k, space)
+    assert np.array_equal(L0, L1) and np.array_equal(D0, D1) and np.array_equal(C0, C1)
+    mask = synthetic.buckets(3, 0, n) < 10
+    L2, D2, C2 = cscan.knn_synthetic(42, first, n, d, scaled, Q, k, space, allow=mask)
+    L3, D3, C3 = cscan.knn(Xn, Qn, k, space, allow_bitmap=synthetic.bitmap_from_mask(mask), first_label=first)
+    assert np.array_equal(L2, L3) and np.array_equal(D2, D3) and np.array_equal(C2, C3)
+    Lr, Dr = exact.knn(X, Q, k, space, allow=mask)      # and within tolerance of the numpy restatement
+    for i in range(5):
+        assert exact.check_topk_parity(L2[i] - first, D2[i], Lr[i], Dr[i]) is None
+    radius = float(D1[0, -1])
+    hits = cscan.range_synthetic(42, first, n, d, scaled, Q, radius, space, max_hits=4)   # forces the retry
+    assert hits[0][0].tolist() == L1[0].tolist() and np.array_equal(hits[0][1], D1[0])
+    Lx, Dx = exact.range_search(X, Q, radius, space)
+    for i in range(5):
+        assert len(hits[i][0]) == len(Lx[i]) or abs(len(hits[i][0]) - len(Lx[i])) <= 2   # ties at the radius
+    assert cscan.check_knn_synthetic(L1, D1, C1, 42, first, n, d, scaled, Q, k, space) is None
+    bad = L1.copy()
+    bad[2, 3] = first + n - 1
+    assert cscan.check_knn_synthetic(bad, D1, C1, 42, first, n, d, scaled, Q, k, space) is not None
+    assert np.array_equal(cscan.distances_synthetic(42, L1[1], d, scaled, Q[1], space), D1[1])
+
+
+def test_oracle_thread_count_ignores_omp_num_threads():
+    """torchrun exports OMP_NUM_THREADS=1; the reference arm must still use every core it may run on."""
+    code = ("import os, sys; sys.path.insert(0, %r); from oracle import cscan; "
+            "print(cscan.num_threads(), cscan.use_all_cores(), cscan.host_threads())" % ROOT)
+    out = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, OMP_NUM_THREADS="1"),
+                         capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0, out.stderr[-1000:]
+    before, after, cores = (int(x) for x in out.stdout.split())
+    assert before == 1 and after == cores

@@ -33,6 +33,24 @@ def test_world2_gloo_sharded_search(total_rows, k):
         assert f"rank {r} ok" in out
 
 
+def test_world2_gloo_sharded_protocol_index():
+    """``ShardedGpuIndex`` (the reference Index protocol, one process per GPU) call for call against a single-process
+    ``GpuIndex`` -- see tests/_gloo_index_worker.py."""
+    port = _free_port()
+    worker = os.path.join(ROOT, "tests", "_gloo_index_worker.py")
+    procs = [subprocess.Popen([sys.executable, worker, str(r), "2", str(port)], stdout=subprocess.PIPE, stderr=subprocess.PIPE,
+                              text=True, cwd=ROOT) for r in range(2)]
+    for r, p in enumerate(procs):
+        try:
+            out, err = p.communicate(timeout=240)
+        except subprocess.TimeoutExpired:
+            for q in procs:
+                q.kill()
+            raise
+        assert p.returncode == 0, err[-3000:]
+        assert f"rank {r} ok" in out
+
+
 def test_shard_range_partitions_rows():
     from mlvectordb_b200.sharded import shard_range
     for n in (0, 1, 7, 8, 9, 1000, 10_000_000):
