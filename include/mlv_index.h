@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define MLV_ABI_VERSION 2
+#define MLV_ABI_VERSION 3
 
 typedef struct mlv_index *mlv_index_t;
 
@@ -127,6 +127,9 @@ int mlv_index_clear(mlv_index_t h);
  *                          index.py:103-107 falls out of the scan, hnswlib's "cannot fill k"
  *                          RuntimeError (index.py:110-119) cannot occur.
  * 1 <= k <= MLV_MAX_K.  Blocks until the results are in the host buffers.
+ * A single query without a per-call bitmap takes the latency path: the raw query rides in the launch parameters,
+ * the kernel writes the final top-k into pinned host memory and raises a flag the call polls -- one launch, no
+ * copies, no preparation launch (set_tuning("fast_host", 0) disables it).
  */
 int mlv_index_search(mlv_index_t h, const float *queries, uint32_t nq, uint32_t k, const uint32_t *filter_bitmap,
                      float *out_dists, int64_t *out_rows, int32_t *out_counts);
@@ -308,6 +311,27 @@ int mlv_index_search_exchange(mlv_index_t h, const float *queries, uint32_t nq, 
                               float *out_dists, int64_t *out_rows, int32_t *out_counts);
 
 /*
+ * Sharded RANGE search (concatenation of the shards' hit lists) with the same fused
+ * peer-memory exchange: one kernel per query and rank -- local range scan, the last CTA sorts the rank's hits,
+ * stores them into every peer's exchange buffer, waits for the peers' lists and merges them ordered by
+ * (distance, global row).  Every rank receives the complete list.  A rank's list may hold up to
+ * MLV_RANGE_EXCHANGE_SLOTS / world hits; each query owns MLV_RANGE_EXCHANGE_SLOTS entries of out_dists / out_rows in
+ * the device variant (max_hits entries in the host variant, which blocks until the lists are in the host buffers).
+ * out_counts[q] = number of hits, or -- with bit 63 set -- a marker: MLV_RANGE_OVERFLOW | total when some rank found
+ * more hits than its share (nothing was written; use mlv_index_range_search per rank and exchange the lists
+ * yourself, as the Python host does through NCCL), all ones when a peer timed out.  Collective, like the kNN exchange.
+ */
+#define MLV_RANGE_EXCHANGE_SLOTS 8192u
+#define MLV_RANGE_OVERFLOW (1ull << 63)
+int mlv_index_range_exchange_supported(mlv_index_t h);
+int mlv_index_range_search_exchange_device(mlv_index_t h, const float *queries_dev, uint32_t nq, float radius,
+                                           const uint32_t *filter_bitmap_dev, float *out_dists_dev, int64_t *out_rows_dev,
+                                           uint64_t *out_counts_dev, void *stream);
+int mlv_index_range_search_exchange(mlv_index_t h, const float *queries, uint32_t nq, float radius,
+                                    const uint32_t *filter_bitmap, uint64_t max_hits, float *out_dists, int64_t *out_rows,
+                                    uint64_t *out_counts);
+
+/*
  * Measurement hooks (bench.py / profiles): when enabled, every search records CUDA events
  * around its scan kernel on the launching stream; mlv_index_scan_time_ms returns the sum
  * of the completed scan-kernel durations since the last call and how many launches that
@@ -322,7 +346,8 @@ int mlv_index_scan_time_ms(mlv_index_t h, double *total_ms, uint64_t *launches);
  * 0 = static round-robin), "tile_batch" tiles claimed per atomic, "fused" (1 = the last CTA does the
  * final select, 0 = separate select kernel), "gather" (-1 auto, 0 = filters stream every row and mask,
  * 1 = filters always gather; the tensor-core path compacts the passing rows accordingly), "staged_upload"
- * (1 = bulk mlv_index_add through two pinned chunks filled by worker threads, 0 = plain copy), and the
+ * (1 = bulk mlv_index_add through two pinned chunks filled by worker threads, 0 = plain copy), "fast_host" (1 = single-query
+ * mlv_index_search takes the one-launch latency path, 0 = always staged), and the
  * tensor-core keys listed at mlv_index_gemm_stats}.  Results never depend on these.
  */
 int mlv_index_set_tuning(mlv_index_t h, const char *key, int value);

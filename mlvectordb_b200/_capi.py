@@ -17,7 +17,7 @@ MLV_OK = 0
 MLV_E_INVALID, MLV_E_CUDA, MLV_E_NOMEM, MLV_E_UNSUPPORTED, MLV_E_NO_DEVICE = 1, 2, 3, 4, 5
 MLV_MAX_K = 1024
 METRIC_CODE = {"l2": 0, "ip": 1, "cosine": 2}
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 
 class IndexInfo(C.Structure):
@@ -118,6 +118,11 @@ SIGNATURES = {
     "mlv_index_search_exchange_device": (C.c_int, [_h, C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p,
                                                    C.c_void_p, C.c_void_p]),
     "mlv_index_search_exchange": (C.c_int, [_h, C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "mlv_index_range_exchange_supported": (C.c_int, [_h]),
+    "mlv_index_range_search_exchange_device": (C.c_int, [_h, C.c_void_p, C.c_uint32, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p,
+                                                         C.c_void_p, C.c_void_p]),
+    "mlv_index_range_search_exchange": (C.c_int, [_h, C.c_void_p, C.c_uint32, C.c_float, C.c_void_p, C.c_uint64, C.c_void_p,
+                                                  C.c_void_p, C.c_void_p]),
     "mlv_index_submit": (C.c_int, [_h, C.c_void_p, C.c_uint32, C.c_uint32, C.c_int, _u32p]),
     "mlv_index_collect": (C.c_int, [_h, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p]),
     "mlv_index_gemm_stats": (C.c_int, [_h, C.POINTER(GemmStats)]),

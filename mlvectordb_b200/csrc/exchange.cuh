@@ -23,7 +23,12 @@ constexpr uint32_t XCHG_SLOT_KEYS = XCHG_MAX_WORLD * XCHG_MAX_NQ * XCHG_MAX_K;  
 constexpr uint32_t XCHG_SLOTS = 4;
 // buffer layout (u64 words): keys[XCHG_SLOTS][XCHG_MAX_WORLD][XCHG_MAX_NQ][XCHG_MAX_K], flags[XCHG_SLOTS][XCHG_MAX_WORLD]
 constexpr uint32_t XCHG_FLAGS_OFF = XCHG_SLOTS * XCHG_SLOT_KEYS;
-constexpr uint32_t XCHG_WORDS = XCHG_FLAGS_OFF + XCHG_SLOTS * XCHG_MAX_WORLD;
+// ... and, for range searches, counts[XCHG_SLOTS][XCHG_MAX_WORLD]: how many hits a rank's list holds (bit 63: too many
+// for its share of the slot, the low bits then carry the true total)
+constexpr uint32_t XCHG_COUNTS_OFF = XCHG_FLAGS_OFF + XCHG_SLOTS * XCHG_MAX_WORLD;
+constexpr uint32_t XCHG_WORDS = XCHG_COUNTS_OFF + XCHG_SLOTS * XCHG_MAX_WORLD;
+constexpr unsigned long long RANGE_OVERFLOW = 1ull << 63;   // in a range count: the lists did not fit the exchange slot
+constexpr unsigned long long RANGE_TIMEOUT = ~0ull;         // range count when a peer never arrived
 // a peer that never arrives: flag an error, do not hang.  Default; MLV_EXCHANGE_TIMEOUT_MS / mlv_exchange_set_timeout_ms
 // change it (the wait holds the GPU, so a serving process wants it short; a skewed batch job wants it long).
 constexpr unsigned long long XCHG_TIMEOUT_NS = 5000000000ull;
@@ -110,6 +115,128 @@ __device__ __forceinline__ void exchange_and_merge(const ExchangeView& x, const 
         }
         named_bar_sync(1, nthr);
     }
+}
+
+// Bitonic network over a[0..P) (P a power of two) by the nthr threads of named barrier 1.
+__device__ __forceinline__ void cta_bitonic_sort(uint64_t* a, uint32_t P, uint32_t tid, uint32_t nthr) {
+    for (uint32_t size = 2; size <= P; size <<= 1) {
+        for (uint32_t stride = size >> 1; stride > 0; stride >>= 1) {
+            named_bar_sync(1, nthr);
+            for (uint32_t t = tid; t < (P >> 1); t += nthr) {
+                const uint32_t i = 2 * t - (t & (stride - 1));
+                const uint32_t j = i + stride;
+                const bool up = (i & size) == 0;
+                const uint64_t va = a[i], vb = a[j];
+                if ((va > vb) == up) {
+                    a[i] = vb;
+                    a[j] = va;
+                }
+            }
+        }
+    }
+    named_bar_sync(1, nthr);
+}
+
+// Range search across row shards: the exchange step of SURVEY.md section 8e for hit LISTS.  Every rank's share of an
+// exchange slot holds XCHG_SLOT_KEYS / world keys.  Called by `nthr` threads (named barrier 1) of the last CTA of a
+// rank's range scan: `a` is shared scratch of XCHG_SLOT_KEYS keys whose first n_local entries are this rank's hits
+// (distance | local row, any order); true_total is how many hits the scan found (> share: overflow).  The rank sorts
+// its list, stores it into every peer's buffer together with its count, publishes the sequence number, waits for the
+// peers and merges the world's lists ordered by (distance, rank, local row) = (distance, global row).  Writes the
+// merged hits and *out_count = their number; RANGE_OVERFLOW | (sum of the true totals) when some rank's list did not
+// fit (nothing else is written: the caller takes the all-gather path); RANGE_TIMEOUT when a peer never arrived.
+// s_cnt: shared, XCHG_MAX_WORLD + 3 words ([0..world] prefix sums of the counts, then overflow marker, timeout flag).
+__device__ __forceinline__ void range_exchange_and_merge(const ExchangeView& x, uint64_t* a, uint32_t n_local,
+                                                         unsigned long long true_total, float* out_dists, int64_t* out_rows,
+                                                         unsigned long long* out_count, uint32_t tid, uint32_t nthr,
+                                                         unsigned long long* s_cnt) {
+    const uint32_t share = XCHG_SLOT_KEYS / x.world;
+    const uint32_t parity = (uint32_t)(x.seq % XCHG_SLOTS);
+    const bool overflow = true_total > share;
+    if (!overflow && n_local) {
+        uint32_t P = 2;
+        while (P < n_local) P <<= 1;
+        for (uint32_t i = n_local + tid; i < P; i += nthr) a[i] = KEY_SENTINEL;
+        cta_bitonic_sort(a, P, tid, nthr);
+        for (uint32_t i = tid; i < x.world * n_local; i += nthr) {
+            const uint32_t dst = i / n_local, j = i - dst * n_local;
+            x.bufs[dst][(size_t)parity * XCHG_SLOT_KEYS + (size_t)x.rank * share + j] = a[j];
+        }
+    }
+    if (tid < x.world)
+        x.bufs[tid][XCHG_COUNTS_OFF + (size_t)parity * XCHG_MAX_WORLD + x.rank] = overflow ? (RANGE_OVERFLOW | true_total) : (unsigned long long)n_local;
+    if (tid == 0) s_cnt[XCHG_MAX_WORLD + 2] = 0;
+    __threadfence_system();
+    named_bar_sync(1, nthr);
+    if (tid < x.world) {
+        uint64_t* flag = x.bufs[tid] + XCHG_FLAGS_OFF + (size_t)parity * XCHG_MAX_WORLD + x.rank;
+        asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(flag), "l"(x.seq) : "memory");
+        const uint64_t* mine = x.bufs[x.rank] + XCHG_FLAGS_OFF + (size_t)parity * XCHG_MAX_WORLD + tid;
+        const unsigned long long t0 = global_timer_ns();
+        for (;;) {
+            uint64_t v;
+            asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(mine) : "memory");
+            if (v >= x.seq) break;
+            if (global_timer_ns() - t0 > x.timeout_ns) {
+                *x.error = 1;
+                s_cnt[XCHG_MAX_WORLD + 2] = 1;
+                break;
+            }
+        }
+    }
+    named_bar_sync(1, nthr);
+    if (s_cnt[XCHG_MAX_WORLD + 2]) {
+        if (tid == 0) *out_count = RANGE_TIMEOUT;
+        return;
+    }
+    const volatile uint64_t* slot = x.bufs[x.rank] + (size_t)parity * XCHG_SLOT_KEYS;
+    const volatile uint64_t* counts = x.bufs[x.rank] + XCHG_COUNTS_OFF + (size_t)parity * XCHG_MAX_WORLD;
+    if (tid == 0) {   // prefix sums of the ranks' counts; s_cnt[world] = total, s_cnt[XCHG_MAX_WORLD + 1] = overflow marker
+        unsigned long long sum = 0, any = 0, true_sum = 0;
+        for (uint32_t r = 0; r < x.world; r++) {
+            const unsigned long long c = counts[r];
+            s_cnt[r] = sum;
+            if (c & RANGE_OVERFLOW) any = 1;
+            true_sum += c & ~RANGE_OVERFLOW;
+            sum += (c & RANGE_OVERFLOW) ? 0 : c;
+        }
+        s_cnt[x.world] = sum;
+        s_cnt[XCHG_MAX_WORLD + 1] = any ? (RANGE_OVERFLOW | true_sum) : 0;
+    }
+    named_bar_sync(1, nthr);
+    if (s_cnt[XCHG_MAX_WORLD + 1]) {
+        if (tid == 0) *out_count = s_cnt[XCHG_MAX_WORLD + 1];
+        return;
+    }
+    const uint32_t total = (uint32_t)s_cnt[x.world];
+    // merge keys: (distance, position in the rank-major concatenation); every list is ascending (distance, row), so
+    // position order inside a rank is row order
+    for (uint32_t r = 0; r < x.world; r++) {
+        const uint32_t base = (uint32_t)s_cnt[r], n = (uint32_t)(s_cnt[r + 1] - s_cnt[r]);
+        for (uint32_t j = tid; j < n; j += nthr)
+            a[base + j] = (slot[(size_t)r * share + j] & 0xFFFFFFFF00000000ull) | (uint64_t)(r * share + j);
+    }
+    uint32_t P = 2;
+    while (P < total) P <<= 1;
+    named_bar_sync(1, nthr);
+    for (uint32_t i = total + tid; i < P; i += nthr) a[i] = KEY_SENTINEL;
+    cta_bitonic_sort(a, P, tid, nthr);
+    for (uint32_t i = tid; i < total; i += nthr) {
+        const uint64_t key = a[i];
+        const uint32_t pos = (uint32_t)key, r = pos / share;
+        out_dists[i] = key_dist(key);
+        out_rows[i] = (int64_t)(x.row_bases[r] + key_row(slot[pos]));
+    }
+    if (tid == 0) *out_count = total;
+}
+
+// A rank with nothing to scan still takes part in a range exchange (count 0).
+__global__ void __launch_bounds__(256, 1) range_exchange_only_kernel(const ExchangeView x, float* out_dists, int64_t* out_rows,
+                                                                     unsigned long long* out_count) {
+    extern __shared__ __align__(16) unsigned char xchg_smem_raw[];
+    __shared__ unsigned long long s_cnt[XCHG_MAX_WORLD + 3];
+    range_exchange_and_merge(x, reinterpret_cast<uint64_t*>(xchg_smem_raw), 0, 0, out_dists, out_rows, out_count, threadIdx.x,
+                             blockDim.x, s_cnt);
 }
 
 // A rank with nothing to scan (empty shard, everything tombstoned) still has to take part.

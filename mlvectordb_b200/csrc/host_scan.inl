@@ -113,6 +113,35 @@ cudaError_t launch_scan_m(const ScanParams& p, const ScanCfg& c, cudaStream_t st
     return cudaErrorInvalidValue;
 }
 
+template <int METRIC, int R, bool RANGE>
+cudaError_t launch_scan_iq_t(const ScanParams& p, const InlineQuery& iq, const ScanCfg& c, cudaStream_t st) {
+    auto kern = scan_kernel_iq<METRIC, R, RANGE>;
+    static size_t raised[64] = {0};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64 || raised[dev] < c.smem) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c.smem);
+        if (e != cudaSuccess) return e;
+        if (dev >= 0 && dev < 64) raised[dev] = c.smem;
+    }
+    kern<<<c.grid, c.threads, c.smem, st>>>(p, iq);
+    return cudaGetLastError();
+}
+template <int METRIC, bool RANGE>
+cudaError_t launch_scan_iq_m(const ScanParams& p, const InlineQuery& iq, const ScanCfg& c, cudaStream_t st) {
+    if (c.R == 1) return launch_scan_iq_t<METRIC, 1, RANGE>(p, iq, c, st);
+    if (c.R == 2) return launch_scan_iq_t<METRIC, 2, RANGE>(p, iq, c, st);
+    if (c.R == 4) return launch_scan_iq_t<METRIC, 4, RANGE>(p, iq, c, st);
+    return cudaErrorInvalidValue;
+}
+// one query, raw values in the launch parameters (c.NQ == 1)
+cudaError_t launch_scan_iq(mlv_index* h, const ScanParams& p, const InlineQuery& iq, const ScanCfg& c, bool range, cudaStream_t st) {
+    const bool l2 = h->metric == MLV_L2;
+    h->launches++;
+    if (range) return l2 ? launch_scan_iq_m<METRIC_L2, true>(p, iq, c, st) : launch_scan_iq_m<METRIC_IP, true>(p, iq, c, st);
+    return l2 ? launch_scan_iq_m<METRIC_L2, false>(p, iq, c, st) : launch_scan_iq_m<METRIC_IP, false>(p, iq, c, st);
+}
+
 cudaError_t launch_scan(mlv_index* h, const ScanParams& p, const ScanCfg& c, bool range, cudaStream_t st) {
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     if (h->timing) {
@@ -316,8 +345,19 @@ ScanParams scan_params(mlv_index* h, const ScanCfg& c, const FilterPlan& fp, Lan
 
 // qprep: prepared queries [nq, ld] in device memory; all output pointers in device memory.
 // exchange: merge with the other ranks' results over peer memory (caller checked exchange_ok).
+// inline_q: ONE raw host query carried in the launch parameters instead of qprep (nq == 1, dim <= SCAN_INLINE_MAX_DIM);
+// done_flag / done_value: completion flag (mapped host memory) the fused tail writes after the outputs.  Both need the
+// fused final select: *took_fast (nullable) reports whether the launch carried them; when it did not, nothing was
+// launched and the caller takes the staged path.
+struct FastArgs {
+    const float* inline_q = nullptr;
+    unsigned int* done_flag = nullptr;
+    unsigned int done_value = 0;
+    bool* took_fast = nullptr;
+};
+
 int search_prepared(mlv_index* h, const float* qprep, uint32_t nq, uint32_t k, const uint32_t* filter_dev, float* out_d,
-                    int64_t* out_r, int32_t* out_c, cudaStream_t st, bool exchange = false) {
+                    int64_t* out_r, int32_t* out_c, cudaStream_t st, bool exchange = false, const FastArgs* fast = nullptr) {
     Lane* ln = lane_for(h, st);
     FilterPlan fp;
     int rc = plan_filter(h, ln, filter_dev, st, &fp);
@@ -330,6 +370,11 @@ int search_prepared(mlv_index* h, const float* qprep, uint32_t nq, uint32_t k, c
     const bool fused = fused_ok(h, c, k) && (exchange || (uint64_t)c.grid * k <= 4096);
     if (exchange && !fused) return fail(h, MLV_E_UNSUPPORTED, "exchange search needs the fused final select");
     if (fused) c.smem = std::max(c.smem, fused_scratch_bytes(c, k));
+    if (fast) {
+        const bool ok = fused && nq == 1 && c.NQ == 1 && h->dim <= SCAN_INLINE_MAX_DIM && !h->timing;
+        if (fast->took_fast) *fast->took_fast = ok;
+        if (!ok) return MLV_OK;   // nothing launched: the caller stages the query and takes the general path
+    }
     const uint32_t F = SELECT_MAX_P / k;  // lists one select CTA can fold (>= 8)
     // bound the candidate scratch: chunk * grid * k keys
     uint32_t chunk = (uint32_t)std::max<size_t>(1, ((size_t)64 << 20) / ((size_t)c.grid * k * 8));
@@ -367,6 +412,17 @@ int search_prepared(mlv_index* h, const float* qprep, uint32_t nq, uint32_t k, c
                 p.out_rows = out_r + (size_t)(q0 + g0) * k;
                 p.out_counts = out_c + (q0 + g0);
                 if (exchange) p.xchg.seq = ++h->xseq;
+            }
+            if (fast) {
+                InlineQuery iq;
+                memcpy(iq.v, fast->inline_q, (size_t)h->dim * 4);
+                p.queries = nullptr;
+                p.dim = h->dim;
+                p.normalize = h->metric == MLV_COSINE;
+                p.done_flag = fast->done_flag;
+                p.done_value = fast->done_value;
+                CK(h, launch_scan_iq(h, p, iq, c, false, st));
+                continue;
             }
             CK(h, launch_scan(h, p, c, false, st));
         }

@@ -93,6 +93,9 @@ struct mlv_index {
     uint64_t compact_gen = 0;
     int tune_gather = -1;        // -1 auto, 0 never (stream + mask), 1 always when a filter is given
     HostBuf h_stage;
+    HostBuf h_range;             // mapped pinned result block of the sharded range search (written by the kernel)
+    unsigned int flag_seq = 0;   // completion-flag values of the batch-1 latency path (mlv_index_search)
+    int tune_fast_host = 1;      // 0 = mlv_index_search always stages (H2D, preparation launch, D2H, synchronise)
     HostBuf h_upload;            // two pinned chunks for bulk row uploads (upload_rows_staged)
     int tune_staged_upload = 1;  // 0 = plain cudaMemcpy from pageable memory
     AsyncSlot slots[MLV_ASYNC_SLOTS];

@@ -7,6 +7,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <atomic>
 #include <charconv>
 #include <cmath>
 #include <cstdio>
@@ -131,6 +132,7 @@ int mlv_index_destroy(mlv_index_t h) {
     drop_columns(h);
     drop_filter_pool(h);
     if (h->h_stage.p) cudaFreeHost(h->h_stage.p);
+    if (h->h_range.p) cudaFreeHost(h->h_range.p);
     if (h->h_upload.p) cudaFreeHost(h->h_upload.p);
     for (AsyncSlot& sl : h->slots) {
         if (sl.stream) cudaStreamSynchronize(sl.stream);
@@ -177,6 +179,7 @@ int mlv_index_set_tuning(mlv_index_t h, const char* key, int value) {
     else if (k == "gemm_bn") h->tune_gemm_bn = value;
     else if (k == "staged_upload") h->tune_staged_upload = value;
     else if (k == "gemm_passes") h->tune_gemm_passes = value;
+    else if (k == "fast_host") h->tune_fast_host = value;
     else return fail(h, MLV_E_INVALID, "unknown tuning key " + k);
     return MLV_OK;
 }
@@ -744,7 +747,35 @@ static int search_host_common(mlv_index_t h, const float* queries, uint32_t nq, 
     const size_t nk = (size_t)nq * k;
     const size_t out_bytes = nk * 4 + nk * 8 + (size_t)nq * 4;
     int rc;
-    if ((rc = ensure_host(h, h->h_stage, std::max(qbytes, out_bytes))) != MLV_OK) return rc;
+    if ((rc = ensure_host(h, h->h_stage, std::max(qbytes, out_bytes) + 64)) != MLV_OK) return rc;
+    if (nq == 1 && !filter_bitmap && h->rows != h->n_deleted && h->dim <= SCAN_INLINE_MAX_DIM && h->tune_fast_host &&
+        (!exchange || exchange_ok(h, k))) {
+        // Batch-1 latency path (BASELINE configs[0]): ONE launch and nothing else.  The raw query travels in the kernel
+        // parameters (padded / normalised inside the kernel), the fused tail writes the final top-k straight into this
+        // pinned, device-mapped staging block and raises a flag there; the host polls the flag (a short spin, then a
+        // stream synchronise for long scans) -- no H2D copy, no preparation launch, no D2H copy.
+        char* hs = (char*)h->h_stage.p;
+        unsigned int* flag = (unsigned int*)(hs + ((out_bytes + 63) & ~(size_t)63));
+        bool took = false;
+        FastArgs fa;
+        fa.inline_q = queries;
+        fa.done_flag = flag;
+        fa.done_value = ++h->flag_seq ? h->flag_seq : ++h->flag_seq;
+        fa.took_fast = &took;
+        rc = search_prepared(h, nullptr, 1, k, nullptr, (float*)(hs + nk * 8), (int64_t*)hs, (int32_t*)(hs + nk * 12), h->stream, exchange, &fa);
+        if (rc != MLV_OK) return rc;
+        if (took) {
+            volatile unsigned int* vf = flag;
+            bool seen = false;
+            for (int spin = 0; spin < 200000 && !seen; spin++) seen = *vf == fa.done_value;   // ~100-200 us of polling
+            if (!seen) CK(h, cudaStreamSynchronize(h->stream));
+            std::atomic_thread_fence(std::memory_order_acquire);
+            memcpy(out_rows, hs, nk * 8);
+            memcpy(out_dists, hs + nk * 8, nk * 4);
+            memcpy(out_counts, hs + nk * 12, (size_t)nq * 4);
+            return MLV_OK;
+        }
+    }
     if ((rc = ensure_dev(h, h->d_qraw, qbytes)) != MLV_OK) return rc;
     // one device block for the results (rows | dists | counts): a single copy brings them back
     if ((rc = ensure_dev(h, h->d_outr, out_bytes)) != MLV_OK) return rc;
@@ -935,6 +966,106 @@ int mlv_index_range_search(mlv_index_t h, const float* queries, uint32_t nq, flo
         CK(h, cudaMemcpyAsync(out_rows + (size_t)q * max_hits, dr, got * 8, cudaMemcpyDeviceToHost, h->stream));
     }
     CK(h, cudaStreamSynchronize(h->stream));
+    return MLV_OK;
+}
+
+static_assert(MLV_RANGE_EXCHANGE_SLOTS == XCHG_SLOT_KEYS, "header and exchange.cuh disagree on the range slot size");
+static_assert(MLV_RANGE_OVERFLOW == RANGE_OVERFLOW, "header and exchange.cuh disagree on the overflow marker");
+
+int mlv_index_range_exchange_supported(mlv_index_t h) {
+    if (!h) return 0;
+    return (h->xchg && h->xchg->connected && h->tune_dynamic && h->tune_fused) ? 1 : 0;
+}
+
+int mlv_index_range_search_exchange_device(mlv_index_t h, const float* queries_dev, uint32_t nq, float radius,
+                                           const uint32_t* filter_bitmap_dev, float* out_dists_dev, int64_t* out_rows_dev,
+                                           uint64_t* out_counts_dev, void* stream) {
+    if (!h || !queries_dev || !out_dists_dev || !out_rows_dev || !out_counts_dev || nq == 0) return fail(h, MLV_E_INVALID, "bad argument");
+    if (!mlv_index_range_exchange_supported(h)) return fail(h, MLV_E_UNSUPPORTED, "no connected exchange");
+    DeviceGuard g(h->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    ExchangeView x{};
+    fill_exchange(h, x);
+    const uint64_t share = XCHG_SLOT_KEYS / x.world;
+    int rc;
+    if (h->rows == h->n_deleted) {   // nothing to scan here, but the peers wait for this rank's (empty) list
+        CK(h, cudaFuncSetAttribute(range_exchange_only_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(XCHG_SLOT_KEYS * 8)));
+        for (uint32_t q = 0; q < nq; q++) {
+            x.seq = ++h->xseq;
+            range_exchange_only_kernel<<<1, 256, (size_t)XCHG_SLOT_KEYS * 8, st>>>(x, out_dists_dev + (size_t)q * XCHG_SLOT_KEYS,
+                                                                               out_rows_dev + (size_t)q * XCHG_SLOT_KEYS,
+                                                                               (unsigned long long*)out_counts_dev + q);
+            h->launches++;
+        }
+        CK(h, cudaGetLastError());
+        return MLV_OK;
+    }
+    if ((rc = ensure_dev(h, h->d_range, (size_t)nq * share * 8 + (size_t)nq * 8)) != MLV_OK) return rc;
+    unsigned long long* d_counts = (unsigned long long*)h->d_range.p;
+    uint64_t* d_keys = (uint64_t*)h->d_range.p + nq;
+    CK(h, cudaMemsetAsync(d_counts, 0, (size_t)nq * 8, st));
+    if ((rc = prep_queries(h, queries_dev, nq, st)) != MLV_OK) return rc;
+    Lane* ln = lane_for(h, st);
+    FilterPlan fp;
+    if ((rc = plan_filter(h, ln, filter_bitmap_dev, st, &fp)) != MLV_OK) return rc;
+    ScanCfg c;
+    if ((rc = choose_cfg(h, 1, 1, true, &c, fp.gather != nullptr)) != MLV_OK) return rc;
+    if ((rc = ensure_sched(h, ln)) != MLV_OK) return rc;
+    c.smem = std::max(c.smem, (size_t)XCHG_SLOT_KEYS * 8);   // the last CTA sorts / merges up to a slot's worth of keys
+    ScanParams p = scan_params(h, c, fp, ln, 1);
+    p.radius = radius;
+    p.max_hits = share;
+    p.fused = 1;
+    p.xchg = x;
+    for (uint32_t q = 0; q < nq; q++) {
+        p.queries = reinterpret_cast<const float4*>((const float*)ln->d_q.p + (size_t)q * h->ld);
+        p.nq_valid = 1;
+        p.range_counts = d_counts + q;
+        p.range_keys = d_keys + (size_t)q * share;
+        p.out_dists = out_dists_dev + (size_t)q * XCHG_SLOT_KEYS;
+        p.out_rows = out_rows_dev + (size_t)q * XCHG_SLOT_KEYS;
+        p.range_out_count = (unsigned long long*)out_counts_dev + q;
+        p.xchg.seq = ++h->xseq;
+        CK(h, launch_scan(h, p, c, true, st));
+    }
+    return MLV_OK;
+}
+
+int mlv_index_range_search_exchange(mlv_index_t h, const float* queries, uint32_t nq, float radius, const uint32_t* filter_bitmap,
+                                    uint64_t max_hits, float* out_dists, int64_t* out_rows, uint64_t* out_counts) {
+    if (!h || !queries || !out_counts || nq == 0 || (max_hits && (!out_dists || !out_rows))) return fail(h, MLV_E_INVALID, "bad argument");
+    if (!mlv_index_range_exchange_supported(h)) return fail(h, MLV_E_UNSUPPORTED, "no connected exchange");
+    DeviceGuard g(h->device);
+    const size_t qbytes = (size_t)nq * h->dim * 4;
+    // results land in pinned, device-mapped host memory straight from the kernel (a hit list is ~1 KB; the slot-sized
+    // device buffers would cost a 100 KB copy per query): counts | dists | rows
+    const size_t per_q = (size_t)XCHG_SLOT_KEYS * 12;
+    int rc;
+    if ((rc = ensure_host(h, h->h_range, (size_t)nq * (8 + per_q) + qbytes)) != MLV_OK) return rc;
+    if ((rc = ensure_dev(h, h->d_qraw, qbytes)) != MLV_OK) return rc;
+    uint64_t* hc = (uint64_t*)h->h_range.p;
+    float* hd = (float*)(hc + nq);
+    int64_t* hr = (int64_t*)((char*)hd + (size_t)nq * XCHG_SLOT_KEYS * 4);
+    char* hq = (char*)hr + (size_t)nq * XCHG_SLOT_KEYS * 8;
+    const uint32_t* filter_dev = nullptr;
+    if (filter_bitmap && h->rows) {
+        const size_t fb = ((h->rows + 31) / 32) * 4;
+        if ((rc = ensure_dev(h, h->d_filter, fb)) != MLV_OK) return rc;
+        CK(h, cudaMemcpyAsync(h->d_filter.p, filter_bitmap, fb, cudaMemcpyHostToDevice, h->stream));
+        filter_dev = (const uint32_t*)h->d_filter.p;
+    }
+    memcpy(hq, queries, qbytes);
+    CK(h, cudaMemcpyAsync(h->d_qraw.p, hq, qbytes, cudaMemcpyHostToDevice, h->stream));
+    rc = mlv_index_range_search_exchange_device(h, (const float*)h->d_qraw.p, nq, radius, filter_dev, hd, hr, hc, h->stream);
+    if (rc != MLV_OK) return rc;
+    CK(h, cudaStreamSynchronize(h->stream));
+    for (uint32_t q = 0; q < nq; q++) {
+        out_counts[q] = hc[q];
+        if (hc[q] & (1ull << 63)) continue;   // overflow / timeout marker: no hits were written
+        const uint64_t got = std::min<uint64_t>(hc[q], max_hits);
+        memcpy(out_dists + (size_t)q * max_hits, hd + (size_t)q * XCHG_SLOT_KEYS, got * 4);
+        memcpy(out_rows + (size_t)q * max_hits, hr + (size_t)q * XCHG_SLOT_KEYS, got * 8);
+    }
     return MLV_OK;
 }
 

@@ -78,6 +78,22 @@ struct ScanParams {
     // fused multi-GPU exchange (world > 1): the last CTA also writes its k best into every peer's
     // exchange buffer over NVLink, waits for the peers' lists and merges -- no NCCL call, no extra launch
     ExchangeView xchg;
+    // range mode with `fused`: the last CTA sorts this rank's hits and runs the range exchange (exchange.cuh);
+    // out_dists / out_rows then hold XCHG_SLOT_KEYS slots and range_out_count the merged count
+    unsigned long long* range_out_count;
+    // inline-query launches (scan_kernel_iq): the raw query rides in the kernel parameters; the CTA pads it and, for
+    // cosine, normalises it exactly like prep_queries_kernel -- no H2D copy, no preparation launch
+    uint32_t dim;
+    int normalize;
+    // completion flag in mapped pinned host memory (nullptr = none): written with done_value after the final outputs,
+    // so the host can poll instead of synchronising the stream
+    unsigned int* done_flag;
+    unsigned int done_value;
+};
+
+constexpr uint32_t SCAN_INLINE_MAX_DIM = 2048;   // floats of a query carried in the kernel parameters (8 KB)
+struct InlineQuery {
+    float v[SCAN_INLINE_MAX_DIM];
 };
 
 struct StageMeta {
@@ -187,8 +203,8 @@ __device__ __forceinline__ uint32_t sorted_count_below(const uint64_t* list, uin
     return lo;
 }
 
-template <int METRIC, int NQ, int R, bool RANGE>
-__global__ void __launch_bounds__(SCAN_MAX_THREADS, 1) scan_kernel(const ScanParams p) {
+template <int METRIC, int NQ, int R, bool RANGE, bool INLINE>
+__device__ __forceinline__ void scan_body(const ScanParams& p, const float* iq) {
     constexpr int V = R * NQ;
     static_assert(V <= 32 && (V & (V - 1)) == 0, "R*NQ must be a power of two <= 32");
     extern __shared__ __align__(128) unsigned char smem[];
@@ -220,14 +236,35 @@ __global__ void __launch_bounds__(SCAN_MAX_THREADS, 1) scan_kernel(const ScanPar
         }
         mbar_fence_init();
     }
-    // queries -> shared (missing queries of a short group repeat the last one; masked later)
-    for (uint32_t i = tid; i < NQ * ld4; i += blockDim.x) {
-        uint32_t qi = i / ld4, j = i - qi * ld4;
-        uint32_t src = qi < p.nq_valid ? qi : p.nq_valid - 1;
-        qs[i] = p.queries[(size_t)src * ld4 + j];
-    }
     if (!RANGE)
         for (uint32_t i = tid; i < (uint32_t)CW * NQ * lcap; i += blockDim.x) lists[i] = KEY_SENTINEL;
+    if (INLINE) {
+        // the raw query comes with the launch: pad it to ld and, for cosine, normalise it with prep_queries_kernel's
+        // exact arithmetic (lane l sums elements l, l+32, ... with fmaf, butterfly over the lanes, v * inv)
+        __shared__ float s_inv;
+        float* qf = reinterpret_cast<float*>(qs);
+        for (uint32_t j = tid; j < ld4 * 4; j += blockDim.x) qf[j] = j < p.dim ? iq[j] : 0.f;
+        __syncthreads();
+        if (p.normalize) {
+            if (warp == 0) {
+                float acc = 0.f;
+                for (uint32_t j = lane; j < p.dim; j += 32) acc = fmaf(qf[j], qf[j], acc);
+#pragma unroll
+                for (int off = 16; off >= 1; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+                if (lane == 0) s_inv = 1.0f / (sqrtf(acc) + 1e-30f);
+            }
+            __syncthreads();
+            const float inv = s_inv;
+            for (uint32_t j = tid; j < p.dim; j += blockDim.x) qf[j] = qf[j] * inv;
+        }
+    } else {
+        // queries -> shared (missing queries of a short group repeat the last one; masked later)
+        for (uint32_t i = tid; i < NQ * ld4; i += blockDim.x) {
+            uint32_t qi = i / ld4, j = i - qi * ld4;
+            uint32_t src = qi < p.nq_valid ? qi : p.nq_valid - 1;
+            qs[i] = p.queries[(size_t)src * ld4 + j];
+        }
+    }
     __syncthreads();
     if (p.timeline && tid == 0) p.timeline[blockIdx.x * 4 + 0] = global_timer_ns();
 
@@ -480,6 +517,7 @@ __global__ void __launch_bounds__(SCAN_MAX_THREADS, 1) scan_kernel(const ScanPar
     // ------------------------------------------------- last CTA: scheduler reset, fused final select
     __shared__ uint32_t s_ticket, s_m, s_valid;
     __shared__ unsigned long long s_T;
+    __shared__ unsigned long long s_rcnt[XCHG_MAX_WORLD + 3];
     named_bar_sync(1, CW * 32);  // every out_keys store of this CTA has been issued
     if (tid == 0) {
         __threadfence();
@@ -566,10 +604,37 @@ __global__ void __launch_bounds__(SCAN_MAX_THREADS, 1) scan_kernel(const ScanPar
             exchange_and_merge(x, top, p.nq_valid, k, p.out_dists, p.out_rows, p.out_counts, tid, nthr, &s_valid);
         }
     }
+    if (RANGE && p.fused) {
+        // range search across row shards: this rank's hits (appended to range_keys by every CTA; the ticket made them
+        // visible) are sorted here, exchanged over peer memory and merged -- one launch per query, no NCCL call
+        uint64_t* a = reinterpret_cast<uint64_t*>(smem);
+        const unsigned long long found = *reinterpret_cast<volatile unsigned long long*>(p.range_counts);
+        const unsigned long long share = XCHG_SLOT_KEYS / p.xchg.world;
+        const uint32_t n_local = (uint32_t)(found <= share ? found : 0);
+        for (uint32_t i = tid; i < n_local; i += nthr) a[i] = __ldcg(p.range_keys + i);
+        named_bar_sync(1, CW * 32);
+        range_exchange_and_merge(p.xchg, a, n_local, found, p.out_dists, p.out_rows, p.range_out_count, tid, nthr, s_rcnt);
+    }
+    if (p.done_flag) {   // results (possibly in mapped host memory) before the flag
+        __threadfence_system();
+        named_bar_sync(1, CW * 32);
+        if (tid == 0) asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p.done_flag), "r"(p.done_value) : "memory");
+    }
     if (tid == 0) {
         p.sched[0] = 0;
         p.sched[1] = 0;
     }
+}
+
+template <int METRIC, int NQ, int R, bool RANGE>
+__global__ void __launch_bounds__(SCAN_MAX_THREADS, 1) scan_kernel(const ScanParams p) {
+    scan_body<METRIC, NQ, R, RANGE, false>(p, nullptr);
+}
+// one query whose raw values travel in the launch parameters (batch-1 latency path)
+template <int METRIC, int R, bool RANGE>
+__global__ void __launch_bounds__(SCAN_MAX_THREADS, 1) scan_kernel_iq(const __grid_constant__ ScanParams p,
+                                                                      const __grid_constant__ InlineQuery iq) {
+    scan_body<METRIC, 1, R, RANGE, true>(p, iq.v);
 }
 
 }  // namespace mlv

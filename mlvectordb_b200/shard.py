@@ -204,6 +204,28 @@ class DeviceShard:
                                                      rows.ctypes.data, counts.ctypes.data))
         return dists, rows, counts
 
+    RANGE_OVERFLOW = 1 << 63
+
+    def range_exchange_supported(self) -> bool:
+        return bool(self._lib.mlv_index_range_exchange_supported(self._h))
+
+    def range_search_exchange(self, queries: np.ndarray, radius: float, max_hits: int = 8192):
+        """Collective: the GLOBAL hit lists of a row-sharded range search from one fused kernel per query
+        (``mlv_index_range_search_exchange``).  -> list per query of (dists, global rows), or None when some rank's list
+        did not fit its share of the exchange slot (every rank gets None: take the all-gather path)."""
+        q = np.ascontiguousarray(queries, dtype=np.float32).reshape(-1, self.dim)
+        nq = q.shape[0]
+        dists = np.empty((nq, max_hits), dtype=np.float32)
+        rows = np.empty((nq, max_hits), dtype=np.int64)
+        counts = np.zeros(nq, dtype=np.uint64)
+        self._ck(self._lib.mlv_index_range_search_exchange(self._h, q.ctypes.data, nq, C.c_float(radius), None, int(max_hits),
+                                                           dists.ctypes.data, rows.ctypes.data, counts.ctypes.data))
+        if (counts == np.uint64(0xFFFFFFFFFFFFFFFF)).any():
+            raise RuntimeError("sharded range search: a peer rank did not post its hits within the exchange timeout")
+        if (counts >= np.uint64(self.RANGE_OVERFLOW)).any():
+            return None
+        return [(dists[i, : int(counts[i])].copy(), rows[i, : int(counts[i])].copy()) for i in range(nq)]
+
     def range_search(self, queries: np.ndarray, radius: float, filt=None, max_hits: int = 1024):
         """-> list per query of (dists f32 [hits], rows i64 [hits]) ascending (d, row)."""
         q = np.ascontiguousarray(queries, dtype=np.float32)

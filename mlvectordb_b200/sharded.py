@@ -260,6 +260,13 @@ class ShardedIndex:
                 return self.range_search(queries, radius)
         q = np.ascontiguousarray(queries, dtype=np.float32).reshape(-1, self.dim)
         nq = q.shape[0]
+        if self.exchange is not None and self.shard.range_exchange_supported():
+            # one fused kernel per query and rank: local range scan, the last CTA sorts the hits, exchanges them over
+            # peer memory and merges (csrc/exchange.cuh); the lists come back in mapped host memory, one sync per call
+            fused = self.shard.range_search_exchange(q, float(radius))
+            if fused is not None:
+                return fused
+            # some rank found more hits than its share of the exchange slot (every rank saw that): all-gather path below
         local = self._local_range(q, float(radius))
         if self.world == 1:
             return local
@@ -284,9 +291,13 @@ class ShardedIndex:
         totals = all_counts.sum(axis=0)
         out = []
         for i in range(nq):
-            d, r = self._order_hits(gd[:, i, :].reshape(-1).contiguous(), gr[:, i, :].reshape(-1).contiguous())
+            # keyed by position in the rank-major concatenation (global rows may not fit the key's 32 row bits): every
+            # list is ascending (distance, row) and ranks ascend with row_base, so position order is row order
+            rows_i = gr[:, i, :].reshape(-1).contiguous()
+            pos = torch.where(rows_i >= 0, torch.arange(rows_i.numel(), dtype=torch.int64, device=rows_i.device), rows_i)
+            d, p = self._order_hits(gd[:, i, :].reshape(-1).contiguous(), pos)
             n = int(totals[i])
-            out.append((d[:n].cpu().numpy().copy(), r[:n].cpu().numpy().copy()))
+            out.append((d[:n].cpu().numpy().copy(), rows_i[p[:n]].cpu().numpy().copy()))
         return out
 
     def _device_order_hits(self, d: torch.Tensor, r: torch.Tensor):

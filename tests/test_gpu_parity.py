@@ -322,3 +322,59 @@ def test_searches_on_several_streams_share_one_handle():
             assert np.array_equal(r.cpu().numpy()[0], ref_r[j]), f"{n_streams} streams, query {j}"
             assert np.array_equal(d.cpu().numpy()[0], ref_d[j])
     s.close()
+
+
+@pytest.mark.parametrize("space", ["l2", "ip", "cosine"])
+@pytest.mark.parametrize("n,dim,k", [(10_000, 128, 10), (3000, 37, 5), (50_000, 768, 27), (700, 2048, 3), (200, 5, 1)])
+def test_single_query_latency_path_equals_the_staged_path(space, n, dim, k):
+    """``mlv_index_search`` with one query takes the one-launch path (raw query in the launch parameters, normalised in
+    the kernel, results written to mapped pinned memory, flag polled): bit-identical to the staged path
+    (H2D + prep_queries_kernel + scan + D2H), to a batch holding the same query, and within tolerance of the oracle."""
+    X = synthetic.rows(70 + dim, 0, n, dim, scaled=True)
+    Q = synthetic.queries(70 + dim, 6, dim) * np.float32(3.0)     # un-normalised queries: the in-kernel normalisation matters
+    Q[2] = X[n // 3]
+    s = _shard(dim, space)
+    s.add(X)
+    fast = [s.search(Q[i:i + 1], k) for i in range(6)]
+    s.set_tuning("fast_host", 0)
+    staged = [s.search(Q[i:i + 1], k) for i in range(6)]
+    s.set_tuning("fast_host", 1)
+    batch = s.search(Q[:4], k)
+    for i in range(6):
+        assert all(np.array_equal(a, b) for a, b in zip(fast[i], staged[i])), f"query {i}"
+    for i in range(4):
+        assert np.array_equal(fast[i][1][0], batch[1][i]) and np.array_equal(fast[i][0][0], batch[0][i])
+    L, D = exact.knn(X, Q, k, space)
+    for i in range(6):
+        msg = exact.check_topk_parity(fast[i][1][0], fast[i][0][0], L[i], D[i])
+        assert msg is None, msg
+    # tombstones and a bound prepared filter ride the same path
+    s.mark_deleted(np.arange(0, n, 5))
+    mask = np.arange(n) % 3 != 0
+    f = s.prepare_filter(mask)
+    a = s.search(Q[1:2], k, f)
+    s.set_tuning("fast_host", 0)
+    b = s.search(Q[1:2], k, f)
+    assert all(np.array_equal(x, y) for x, y in zip(a, b))
+    allow = mask & (np.arange(n) % 5 != 0)
+    Lf, Df = exact.knn(X, Q[1:2], k, space, allow=allow)
+    assert exact.check_topk_parity(a[1][0, :a[2][0]], a[0][0, :a[2][0]], Lf[0], Df[0]) is None
+    f.close()
+    s.close()
+
+
+def test_single_query_latency_path_many_calls_and_k_beyond_the_fused_tail():
+    """Flag values advance call by call; k too large for the fused tail falls back to the staged path silently."""
+    n, dim = 20_000, 64
+    X = synthetic.rows(5, 0, n, dim)
+    s = _shard(dim, "l2")
+    s.add(X)
+    Q = synthetic.queries(6, 50, dim)
+    ref = s.search(Q, 7)
+    for i in range(50):
+        d, r, c = s.search(Q[i:i + 1], 7)
+        assert np.array_equal(r[0], ref[1][i]) and np.array_equal(d[0], ref[0][i])
+    big = s.search(Q[:1], 200)                # 148 * 200 keys: separate select kernel
+    L, D = exact.knn(X, Q[:1], 200, "l2")
+    assert exact.check_topk_parity(big[1][0], big[0][0], L[0], D[0]) is None
+    s.close()
