@@ -360,11 +360,13 @@ int mlv_index_debug_timeline(mlv_index_t h, uint64_t *out, uint32_t max_ctas, ui
 /*
  * Tensor-core batch path (csrc/gemm_kernel.cuh): searches with nq >= 5 queries on a matrix of >= 1 GB (nq >= 9 on >= 16384 rows otherwise)
  * run as a tcgen05 GEMM that selects k + slack candidates per query, re-scores them in the
- * reference's arithmetic and certifies the result.  Two tiers: a one-pass TF32 GEMM (a third of the
- * tensor work, coarser approximate distances, wider slack), then the 3xTF32 GEMM for the queries the
- * first tier could not certify; what neither certifies is re-run by the exact scan, so results do
- * not depend on the path.  set_tuning keys: "gemm" (-1 auto, 0 never, 1 whenever the shape
- * allows), "gemm_min_nq", "gemm_passes" (0 both tiers, 1 one-pass tier then scan, 3 3xTF32 tier only).  This call returns cumulative counters
+ * reference's arithmetic and certifies the result.  Tiers: a one-pass GEMM on an fp16 SHADOW of the rows
+ * (kind::f16: the same 10 explicit mantissa bits as TF32 at twice the tensor rate; the shadow costs half
+ * the matrix again in HBM and is built lazily -- without room for it the one-pass TF32 GEMM on the fp32 rows
+ * takes its place), then the 3xTF32 GEMM for the queries the first tier could not certify; what neither
+ * certifies is re-run by the exact scan, so results do not depend on the path.  set_tuning keys: "gemm"
+ * (-1 auto, 0 never, 1 whenever the shape allows), "gemm_min_nq", "gemm_passes" (0 auto, 1 one-pass TF32 tier
+ * then scan, 2 fp16 tier then scan, 3 3xTF32 tier only).  This call returns cumulative counters
  * and, when timing is enabled, the summed device time of the GEMM launches since the last call.
  */
 typedef struct mlv_gemm_stats {
@@ -376,11 +378,12 @@ typedef struct mlv_gemm_stats {
     uint64_t rounds;              /* GEMM launches (one per round) */
     uint64_t fast_queries;        /* of `queries`, certified by the one-pass TF32 tier (no 3xTF32 work spent on them) */
     uint64_t gathered_searches;   /* of `searches`, filtered batches that multiplied a compacted copy of the passing rows */
+    uint64_t half_queries;        /* of `fast_queries`, certified by the fp16-shadow tier (kind::f16 on halves of the rows) */
 } mlv_gemm_stats_t;
 int mlv_index_gemm_stats(mlv_index_t h, mlv_gemm_stats_t *out);
 /*
- * Debug / parity tests: the APPROXIMATE distances the tensor-core kernel computes (3xTF32 GEMM form, or the
- * one-pass TF32 form after set_tuning("gemm_passes", 1); before the exact re-rank) for nq host queries against every stored row: out_approx[nq, rows],
+ * Debug / parity tests: the APPROXIMATE distances the tensor-core kernel computes (3xTF32 GEMM form, the
+ * one-pass TF32 form after set_tuning("gemm_passes", 1), the fp16-shadow form after set_tuning("gemm_passes", 2); before the exact re-rank) for nq host queries against every stored row: out_approx[nq, rows],
  * NaN for tombstoned rows.  1 <= rows <= 8192, dim >= 32.
  */
 int mlv_index_debug_gemm(mlv_index_t h, const float *queries, uint32_t nq, float *out_approx);

@@ -44,6 +44,7 @@ class GemmStats(C.Structure):
         ("rounds", C.c_uint64),
         ("fast_queries", C.c_uint64),
         ("gathered_searches", C.c_uint64),
+        ("half_queries", C.c_uint64),
     ]
 
 

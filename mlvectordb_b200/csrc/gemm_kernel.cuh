@@ -28,6 +28,7 @@
 // geometrically growing rounds, each followed by refine_kernel (keep the best k', set thr = a_k').
 #pragma once
 #include <cuda.h>
+#include <cuda_fp16.h>
 
 #include "common.cuh"
 #include "scan_kernel.cuh"
@@ -49,14 +50,24 @@ constexpr uint32_t GEMM_X_BYTES = GEMM_BM * GEMM_BK * 4;   // 16 KB
 // approximate distances are coarser (|a - exact| <= 2^-9 |x||q| instead of 2^-13), which the certificate
 // accounts for with a larger delta and the host with a larger candidate slack; queries it cannot certify are
 // re-run by the PASSES = 3 tier, and only what that cannot certify either goes to the scan.
+//
+// PASSES = 2 is the HALF tier: the same one-MMA-per-K-step pipeline on an fp16 SHADOW of the rows (kind::f16, K = 16 per
+// instruction: twice the products per tensor cycle and per operand byte of kind::tf32, so a pass over the rows costs
+// half of PASSES = 1 at the same shared-memory traffic per cycle).  fp16 keeps the same 10 explicit mantissa bits as
+// TF32, rounded to nearest instead of truncated, so its approximate distances are TWICE as tight as PASSES = 1's; its
+// 5-bit exponent is dealt with by power-of-two scales (one per matrix, one per query) that the epilogue divides out
+// exactly.  A K chunk is 64 halves (one 128-byte swizzle row), tiles are the same 16 KB / BN * 128 B.
+constexpr int GEMM_TIER_F16 = 2;
 template <int BN, int PASSES = 3>
 struct GemmShape {
     static constexpr uint32_t Q_BYTES = BN * GEMM_BK * 4;
     static constexpr uint32_t STAGE_BYTES = PASSES == 3 ? 2 * GEMM_X_BYTES + 2 * Q_BYTES : GEMM_X_BYTES + Q_BYTES;
     static constexpr int STAGES = PASSES == 3 ? (BN == 256 ? 2 : (BN == 128 ? 3 : 4)) : (BN == 256 ? 4 : 6);
-    static constexpr uint32_t SMEM_BYTES = 1024 + STAGES * STAGE_BYTES + 2 * BN * 4 + 256;
-    // kind::tf32, fp32 accumulate, A and B K-major, M = 128, N = BN
-    static constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(GEMM_BM >> 4) << 24);
+    static constexpr uint32_t SMEM_BYTES = 1024 + STAGES * STAGE_BYTES + 3 * BN * 4 + 256;
+    // fp32 accumulate, A and B K-major, M = 128, N = BN; operand format TF32 (kind::tf32) or F16 (kind::f16)
+    static constexpr uint32_t FMT = PASSES == GEMM_TIER_F16 ? 0u : 2u;
+    static constexpr uint32_t IDESC = (1u << 4) | (FMT << 7) | (FMT << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(GEMM_BM >> 4) << 24);
+    static constexpr uint32_t CHUNK_ELEMS = PASSES == GEMM_TIER_F16 ? 64 : 32;   // elements per 128-byte K chunk
 };
 constexpr float GEMM_DELTA_REL = 1.220703125e-4f;  // 2^-13: bound on |a - exact| / scale (see rerank_kernel), PASSES = 3
 // PASSES = 1: both operands truncated to 10 explicit mantissa bits -> |x~q~ - xq| < (2^-9 + 2^-20) |xq|, so the dot
@@ -66,6 +77,14 @@ constexpr float GEMM_DELTA_REL = 1.220703125e-4f;  // 2^-13: bound on |a - exact
 // 2 |x||q| <= (|x|max + |q|)^2 / 2, so the same bound halves relative to the l2 scale.
 __host__ __device__ inline float gemm_delta_rel_1pass(bool l2, uint32_t d) {
     const float e = 1.953125e-3f * (1.0f + 4.8828125e-4f) + (float)d * 2.384185791015625e-7f + 9.5367431640625e-7f;
+    return l2 ? 0.5f * e : e;
+}
+// PASSES = 2 (fp16 shadow): both operands ROUNDED to 11 significant bits -> |x~q~ - xq| <= (2^-10 + 2^-22) |xq|, i.e. the
+// dot product is off by <= 2^-10 (1 + 2^-12) |x||q|; elements below the fp16 normal range of the scaled matrix (less than
+// 2^-28 of the largest row norm) add at most 2^-25 / scale each, <= 2^-38 sqrt(d) |x|max |q| in total; products of
+// halves are exact in fp32 and the accumulation is bounded like the TF32 tier's (fewer, wider steps: the bound is kept).
+__host__ __device__ inline float gemm_delta_rel_f16(bool l2, uint32_t d) {
+    const float e = 9.765625e-4f * (1.0f + 2.44140625e-4f) + (float)d * 2.384185791015625e-7f + 9.5367431640625e-7f;
     return l2 ? 0.5f * e : e;
 }
 
@@ -83,6 +102,9 @@ struct GemmParams {
     uint64_t* cand;          // [nq_pad][cap]
     uint32_t* cand_cnt;      // [nq_pad]
     uint32_t cap;
+    // PASSES = 2: the accumulator holds (x * 2^sx) . (q * 2^sq); dot = acc * *x_unscale * q_unscale[query]
+    const float* x_unscale;  // device scalar 2^-sx, frozen when the shadow was converted
+    const float* q_unscale;  // [nq_pad] 2^-sq
 };
 
 // ---- PTX wrappers ---------------------------------------------------------------------------
@@ -101,6 +123,14 @@ __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence:
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tc_mma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
 }
 __device__ __forceinline__ void tc_mma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
     asm volatile(
@@ -149,9 +179,12 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
     extern __shared__ unsigned char gemm_smem_raw[];
     // SWIZZLE_128B tiles need 1024-byte alignment
     unsigned char* smem = gemm_smem_raw + ((1024u - (smem_u32(gemm_smem_raw) & 1023u)) & 1023u);
+    constexpr bool F16 = PASSES == GEMM_TIER_F16;
+    constexpr uint32_t CHUNK_ELEMS = GemmShape<GEMM_BN, PASSES>::CHUNK_ELEMS;
     float* thr_s = reinterpret_cast<float*>(smem + GEMM_STAGES * GEMM_STAGE_BYTES);  // [256]
     float* qn_s = thr_s + GEMM_BN;                                                    // [256]
-    uint64_t* bars = reinterpret_cast<uint64_t*>(qn_s + GEMM_BN);
+    float* us_s = qn_s + GEMM_BN;                                                     // [256] (PASSES = 2)
+    uint64_t* bars = reinterpret_cast<uint64_t*>(us_s + GEMM_BN);
     uint64_t* full = bars;                      // [S]  TMA bytes landed
     uint64_t* empty = bars + GEMM_STAGES;       // [S]  MMAs reading the stage retired
     uint64_t* conv = bars + 2 * GEMM_STAGES;    // [S]  hi/lo split written
@@ -200,10 +233,10 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
                     mbar_wait(&empty[stage], phase ^ 1);
                     unsigned char* sb = smem + (size_t)stage * GEMM_STAGE_BYTES;
                     mbar_arrive_expect_tx(&full[stage], GEMM_X_BYTES + (PASSES == 3 ? 2 : 1) * GEMM_Q_BYTES);
-                    tma_load_2d(sb, &tm_x, (int32_t)(kc * GEMM_BK), (int32_t)(rt * GEMM_BM), &full[stage]);
-                    tma_load_2d(sb + GEMM_Q_OFF, &tm_qhi, (int32_t)(kc * GEMM_BK), (int32_t)(qt * GEMM_BN), &full[stage]);
+                    tma_load_2d(sb, &tm_x, (int32_t)(kc * CHUNK_ELEMS), (int32_t)(rt * GEMM_BM), &full[stage]);
+                    tma_load_2d(sb + GEMM_Q_OFF, &tm_qhi, (int32_t)(kc * CHUNK_ELEMS), (int32_t)(qt * GEMM_BN), &full[stage]);
                     if (PASSES == 3)
-                        tma_load_2d(sb + GEMM_Q_OFF + GEMM_Q_BYTES, &tm_qlo, (int32_t)(kc * GEMM_BK), (int32_t)(qt * GEMM_BN),
+                        tma_load_2d(sb + GEMM_Q_OFF + GEMM_Q_BYTES, &tm_qlo, (int32_t)(kc * CHUNK_ELEMS), (int32_t)(qt * GEMM_BN),
                                     &full[stage]);
                     if (++stage == GEMM_STAGES) {
                         stage = 0;
@@ -238,6 +271,9 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
                             tc_mma_tf32(tmem_d, d_xlo + adv, d_qhi + adv, GEMM_IDESC, (kc | ks) != 0);
                             tc_mma_tf32(tmem_d, d_xhi + adv, d_qlo + adv, GEMM_IDESC, 1);
                             tc_mma_tf32(tmem_d, d_xhi + adv, d_qhi + adv, GEMM_IDESC, 1);
+                        } else if (F16) {
+                            // fp16 shadow tiles: 16 halves (the same 32 bytes) per instruction
+                            tc_mma_f16(tmem_d, d_xhi + adv, d_qhi + adv, GEMM_IDESC, (kc | ks) != 0);
                         } else {
                             // raw fp32 tiles: the tensor core truncates both operands to TF32 itself
                             tc_mma_tf32(tmem_d, d_xhi + adv, d_qhi + adv, GEMM_IDESC, (kc | ks) != 0);
@@ -296,9 +332,11 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
             const uint32_t rt = p.row_tile0 + it / p.n_qtiles, qt = it % p.n_qtiles;
             const uint32_t acc = local & 1, acc_phase = (local >> 1) & 1;
             named_bar_sync(2, 128);  // everyone finished reading thr_s / qn_s of the previous item
+            const float xus = F16 ? __ldg(p.x_unscale) : 1.0f;
             for (int i = et; i < GEMM_BN; i += 128) {
                 thr_s[i] = p.thr[qt * GEMM_BN + i];
                 qn_s[i] = p.q_norms[qt * GEMM_BN + i];
+                if (F16) us_s[i] = p.q_unscale[qt * GEMM_BN + i] * xus;   // powers of two: the product is exact
             }
             const uint32_t row = rt * GEMM_BM + quarter * 32 + lane;
             bool row_ok = row < p.n_rows;
@@ -319,7 +357,7 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
 #pragma unroll
                     for (int j = 0; j < 32; j++) {
                         const uint32_t ql = c * 32 + j;
-                        const float dot = __uint_as_float(v[j]);
+                        const float dot = F16 ? __uint_as_float(v[j]) * us_s[ql] : __uint_as_float(v[j]);
                         const float a = (METRIC == METRIC_L2) ? fmaf(-2.0f, dot, xn + qn_s[ql]) : 1.0f - dot;
                         if (a <= thr_s[ql]) {
                             const uint32_t qg = qt * GEMM_BN + ql;
@@ -374,6 +412,75 @@ __global__ void scatter_results_kernel(const uint32_t* __restrict__ idx, uint32_
         dd[o] = sd[i];
         dr[o] = sr[i];
         if (j == 0) dc[idx[r]] = sc[r];
+    }
+}
+
+// ---- fp16 shadow of the rows (PASSES = 2) ---------------------------------------------------------
+// scale exponent for a largest magnitude `m`: 2^s with m * 2^s in [2^13, 2^14) (fp16 overflows at 2^16: two bits of
+// headroom for rows appended after the scale was frozen); m == 0 or not finite -> 0
+__host__ __device__ inline int f16_scale_exp(float m) {
+    if (!(m > 0.f) || m > 3.0e38f) return 0;
+    int ex;
+    frexpf(m, &ex);   // m = f * 2^ex, f in [0.5, 1)
+    int s = 14 - ex;
+    return s < -100 ? -100 : (s > 100 ? 100 : s);
+}
+// st[0] = 2^-s (float, what the epilogue multiplies by), st[1] = s (int), st[2] = overflow flag (cleared).
+// max_norm2_bits == nullptr: unit rows (cosine).
+__global__ void f16_freeze_scale_kernel(const uint32_t* max_norm2_bits, uint32_t* st) {
+    const float xmax = max_norm2_bits ? sqrtf(__uint_as_float(*max_norm2_bits)) : 1.0f;
+    const int s = f16_scale_exp(xmax);
+    st[0] = __float_as_uint(ldexpf(1.0f, -s));
+    st[1] = (uint32_t)s;
+    st[2] = 0;
+}
+// rows [first, first + n) of the fp32 matrix -> halves (round to nearest) of value * 2^s, ld16 halves per row (zero padded).
+// A value the frozen scale cannot hold (rows much larger than any present when it was frozen) raises st[2].
+__global__ void convert_rows_f16_kernel(const float* __restrict__ rows, uint64_t first, uint64_t n, uint32_t ld, uint32_t ld16,
+                                        __half* __restrict__ out, uint32_t* st) {
+    const float scale = ldexpf(1.0f, (int)st[1]);
+    const uint32_t pairs = ld16 >> 1;
+    const uint64_t total = n * pairs;
+    bool over = false;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (uint64_t)gridDim.x * blockDim.x) {
+        const uint64_t r = i / pairs;
+        const uint32_t c = (uint32_t)(i - r * pairs) * 2;
+        const float* src = rows + (first + r) * ld;
+        const float a = c < ld ? src[c] * scale : 0.f, b = c + 1 < ld ? src[c + 1] * scale : 0.f;
+        over |= fabsf(a) > 65000.f || fabsf(b) > 65000.f;
+        reinterpret_cast<__half2*>(out + (first + r) * ld16)[c >> 1] = __floats2half2_rn(a, b);
+    }
+    if (over) st[2] = 1;
+}
+// Prepared queries [nq, ld] -> halves of q * 2^sq [nq_pad, ld16] (pad rows / columns zero), 2^-sq, |q|^2, initial thresholds,
+// cleared counters and flags.  One warp per (padded) query.
+__global__ void split_queries_f16_kernel(const float* __restrict__ q, __half* __restrict__ q16, float* __restrict__ unscale,
+                                         float* __restrict__ qn, float* __restrict__ thr, uint32_t* __restrict__ cnt,
+                                         uint32_t* __restrict__ flags, uint32_t nq, uint32_t nq_pad, uint32_t ld, uint32_t ld16) {
+    const uint32_t w = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (w >= nq_pad) return;
+    float s = 0.f, m = 0.f;
+    for (uint32_t j = lane; j < ld; j += 32) {
+        const float v = w < nq ? q[(size_t)w * ld + j] : 0.f;
+        s = fmaf(v, v, s);
+        m = fmaxf(m, fabsf(v));
+    }
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) {
+        s += __shfl_xor_sync(0xffffffffu, s, off);
+        m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, off));
+    }
+    const int sq = f16_scale_exp(m);
+    const float scale = ldexpf(1.0f, sq);
+    for (uint32_t j = lane; j < ld16; j += 32)
+        q16[(size_t)w * ld16 + j] = __float2half_rn((w < nq && j < ld) ? q[(size_t)w * ld + j] * scale : 0.f);
+    if (lane == 0) {
+        unscale[w] = ldexpf(1.0f, -sq);
+        qn[w] = s;
+        thr[w] = w < nq ? __int_as_float(0x7f800000) : __int_as_float(0xff800000);
+        cnt[w] = 0;
+        flags[w] = 0;
     }
 }
 

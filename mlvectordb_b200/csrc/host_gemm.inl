@@ -27,16 +27,22 @@ encode_tiled_fn get_encode_tiled() {
     return fn;
 }
 
+// halves per row of the fp16 shadow: rows stay 16-byte aligned (TMA) -> a multiple of 8
+uint32_t f16_ld(const mlv_index* h) { return (h->ld + 7u) & ~7u; }
+
 // fp32 matrix [n_rows, ld] row-major -> boxes of {GEMM_BK floats, box_rows rows}, 128-byte swizzle,
 // out-of-range elements read as zero (ragged last row tile, ld not a multiple of 32)
-int make_tile_map(mlv_index* h, CUtensorMap* map, const float* base, uint64_t n_rows, uint32_t box_rows) {
+// half = true: an fp16 matrix [n_rows, ld16] with boxes of {64 halves, box_rows rows} (the same 128-byte rows)
+int make_tile_map(mlv_index* h, CUtensorMap* map, const void* base, uint64_t n_rows, uint32_t box_rows, bool half = false) {
     encode_tiled_fn enc = get_encode_tiled();
     if (!enc) return fail(h, MLV_E_CUDA, "cuTensorMapEncodeTiled is not available from this driver");
-    const cuuint64_t gdim[2] = {h->ld, n_rows};
-    const cuuint64_t gstride[1] = {(cuuint64_t)h->ld * 4};
-    const cuuint32_t box[2] = {(cuuint32_t)GEMM_BK, box_rows};
+    const uint32_t ld = half ? f16_ld(h) : h->ld;
+    const cuuint64_t gdim[2] = {ld, n_rows};
+    const cuuint64_t gstride[1] = {(cuuint64_t)ld * (half ? 2 : 4)};
+    const cuuint32_t box[2] = {(cuuint32_t)(half ? 2 * GEMM_BK : GEMM_BK), box_rows};
     const cuuint32_t estr[2] = {1, 1};
-    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)base, gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+    CUresult r = enc(map, half ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)base, gdim, gstride, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE,
                      CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return fail(h, MLV_E_CUDA, "cuTensorMapEncodeTiled failed (" + std::to_string((int)r) + ")");
     return MLV_OK;
@@ -79,11 +85,13 @@ int ensure_row_norms(mlv_index* h, cudaStream_t st) {
         if ((rc = ensure_dev(h, h->d_maxn2, 4)) != MLV_OK) return rc;
         CK(h, cudaMemsetAsync(h->d_maxn2.p, 0, 4, st));
         h->norms_valid = 0;
+        h->f16_valid = 0;   // the shadow's scale follows the largest norm
     }
     if (h->d_norms.bytes < h->rows * 4) {
         // growing reallocates: recompute everything (rows rarely grow between large batches)
         if ((rc = ensure_dev(h, h->d_norms, std::max<uint64_t>(h->capacity, h->rows) * 4)) != MLV_OK) return rc;
         h->norms_valid = 0;
+        h->f16_valid = 0;
     }
     if (h->norms_valid == 0) CK(h, cudaMemsetAsync(h->d_maxn2.p, 0, 4, st));
     if (h->norms_valid < h->rows) {
@@ -117,7 +125,42 @@ cudaError_t launch_gemm_tp(const CUtensorMap& mx, const CUtensorMap& mqh, const 
 template <int METRIC>
 cudaError_t launch_gemm_t(const CUtensorMap& mx, const CUtensorMap& mqh, const CUtensorMap& mql, const GemmParams& gp, int grid,
                           cudaStream_t st, int bn, int passes = 3) {
+    if (passes == GEMM_TIER_F16) return launch_gemm_tp<METRIC, GEMM_TIER_F16>(mx, mqh, mql, gp, grid, st, bn);
     return passes == 1 ? launch_gemm_tp<METRIC, 1>(mx, mqh, mql, gp, grid, st, bn) : launch_gemm_tp<METRIC, 3>(mx, mqh, mql, gp, grid, st, bn);
+}
+
+// The fp16 shadow of the rows ([capacity, f16_ld] halves of value * 2^s) behind the HALF tier, built lazily like the row
+// norms: rows [0, f16_valid) are current; the scale is frozen when row 0 is converted (st[0..2] = 2^-s, s, overflow flag).
+// Returns MLV_OK with *usable = false when there is no room for it (the caller takes the TF32 tier).
+int ensure_f16_shadow(mlv_index* h, cudaStream_t st, bool* usable) {
+    *usable = false;
+    const uint32_t ld16 = f16_ld(h);
+    if (h->d_rows16.bytes < (size_t)h->rows * ld16 * 2) {
+        free_dev(h->d_rows16);
+        if (ensure_dev(h, h->d_rows16, (size_t)std::max<uint64_t>(h->capacity, h->rows) * ld16 * 2) != MLV_OK) {
+            h->err.clear();
+            cudaGetLastError();
+            return MLV_OK;
+        }
+        h->f16_valid = 0;
+    }
+    int rc;
+    if ((rc = ensure_dev(h, h->d_f16st, 16)) != MLV_OK) return rc;
+    if (h->f16_valid == 0) {
+        f16_freeze_scale_kernel<<<1, 1, 0, st>>>(h->metric == MLV_COSINE ? nullptr : (const uint32_t*)h->d_maxn2.p, (uint32_t*)h->d_f16st.p);
+        h->launches++;
+    }
+    if (h->f16_valid < h->rows) {
+        const uint64_t n = h->rows - h->f16_valid;
+        const uint64_t total = n * (ld16 / 2);
+        convert_rows_f16_kernel<<<(unsigned)std::min<uint64_t>((total + 255) / 256, (uint64_t)h->sm_count * 16), 256, 0, st>>>(
+            h->d_rows, h->f16_valid, n, h->ld, ld16, (__half*)h->d_rows16.p, (uint32_t*)h->d_f16st.p);
+        h->launches++;
+        CK(h, cudaGetLastError());
+        h->f16_valid = h->rows;
+    }
+    *usable = true;
+    return MLV_OK;
 }
 
 // candidates kept per query by the fast tier: its approximate distances are 16x coarser, so the exact k-th best must
@@ -139,6 +182,8 @@ struct GemmView {
     const uint32_t* live = nullptr;
     const uint32_t* filter = nullptr;
     const uint32_t* rowmap = nullptr;  // view row -> index row (nullptr = identity)
+    const void* rows16 = nullptr;      // fp16 shadow of `rows` (HALF tier), or nullptr
+    const float* x_unscale = nullptr;  // its frozen 2^-s (device scalar)
 };
 
 // One tier of the batch path: tcgen05 GEMM (PASSES = 1 or 3) selects k' candidates per query in geometrically growing
@@ -150,7 +195,9 @@ int search_gemm_tier(mlv_index* h, const float* qprep, uint32_t nq, uint32_t k, 
     const uint32_t ld = h->ld;
     const uint32_t GEMM_BN = gemm_tile_width(h, nq);
     const uint32_t nq_pad = (nq + GEMM_BN - 1) / GEMM_BN * GEMM_BN;
-    const uint32_t kprime = passes == 1 ? gemm_kprime_1pass(k) : gemm_kprime(k);
+    const bool half = passes == GEMM_TIER_F16;
+    const uint32_t ld16 = f16_ld(h);
+    const uint32_t kprime = (passes == 1 || half) ? gemm_kprime_1pass(k) : gemm_kprime(k);
     const uint32_t cap = std::min<uint32_t>(SELECT_MAX_P, pow2_ceil(8 * kprime));
     const uint32_t P = cap;  // power of two
     const bool l2 = h->metric == MLV_L2;
@@ -165,23 +212,31 @@ int search_gemm_tier(mlv_index* h, const float* qprep, uint32_t nq, uint32_t k, 
     uint32_t* cnt = (uint32_t*)(thr + nq_pad);
     uint32_t* flags = cnt + nq_pad;
     uint64_t* cand = (uint64_t*)h->d_cand.p;
+    // HALF tier: the Qhi area holds the fp16 queries, the Qlo area their 2^-sq
+    float* q_unscale = qlo;
     {
         const int wpb = 8;
-        split_queries_kernel<<<(nq_pad + wpb - 1) / wpb, wpb * 32, 0, st>>>(qprep, qhi, qlo, qn, thr, cnt, flags, nq, nq_pad, ld);
+        if (half)
+            split_queries_f16_kernel<<<(nq_pad + wpb - 1) / wpb, wpb * 32, 0, st>>>(qprep, (__half*)qhi, q_unscale, qn, thr, cnt, flags, nq,
+                                                                                    nq_pad, ld, ld16);
+        else
+            split_queries_kernel<<<(nq_pad + wpb - 1) / wpb, wpb * 32, 0, st>>>(qprep, qhi, qlo, qn, thr, cnt, flags, nq, nq_pad, ld);
         h->launches++;
         CK(h, cudaGetLastError());
     }
     CUtensorMap mx, mqh, mql;
-    if ((rc = make_tile_map(h, &mx, view.rows, view.n_rows, GEMM_BM)) != MLV_OK) return rc;
-    if ((rc = make_tile_map(h, &mqh, qhi, nq_pad, GEMM_BN)) != MLV_OK) return rc;
-    if ((rc = make_tile_map(h, &mql, qlo, nq_pad, GEMM_BN)) != MLV_OK) return rc;
+    if ((rc = make_tile_map(h, &mx, half ? view.rows16 : (const void*)view.rows, view.n_rows, GEMM_BM, half)) != MLV_OK) return rc;
+    if ((rc = make_tile_map(h, &mqh, qhi, nq_pad, GEMM_BN, half)) != MLV_OK) return rc;
+    if ((rc = make_tile_map(h, &mql, half ? qhi : qlo, nq_pad, GEMM_BN, half)) != MLV_OK) return rc;
     CK(h, cudaFuncSetAttribute(refine_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SELECT_MAX_P * 8)));
 
     GemmParams gp{};
     gp.n_rows = (uint32_t)view.n_rows;
     gp.nq = nq;
     gp.n_qtiles = nq_pad / GEMM_BN;
-    gp.n_kchunks = (ld + GEMM_BK - 1) / GEMM_BK;
+    gp.n_kchunks = half ? (ld16 + 2 * GEMM_BK - 1) / (2 * GEMM_BK) : (ld + GEMM_BK - 1) / GEMM_BK;
+    gp.x_unscale = view.x_unscale;
+    gp.q_unscale = q_unscale;
     gp.row_norms = l2 ? view.norms : nullptr;
     gp.q_norms = qn;
     gp.thr = thr;
@@ -251,7 +306,7 @@ int search_gemm_tier(mlv_index* h, const float* qprep, uint32_t nq, uint32_t k, 
     rp.out_counts = out_c;
     rp.row_base = h->row_base;
     rp.metric = h->metric;
-    rp.delta_rel = passes == 1 ? gemm_delta_rel_1pass(l2, ld) : GEMM_DELTA_REL;
+    rp.delta_rel = half ? gemm_delta_rel_f16(l2, ld) : (passes == 1 ? gemm_delta_rel_1pass(l2, ld) : GEMM_DELTA_REL);
     if (l2)
         rerank_kernel<METRIC_L2><<<nq, 256, (size_t)rp.P * 8, st>>>(rp);
     else
@@ -261,8 +316,16 @@ int search_gemm_tier(mlv_index* h, const float* qprep, uint32_t nq, uint32_t k, 
 
     // certificate check: the one synchronisation of this tier
     hflags.resize(nq);
+    uint32_t f16st[3] = {0, 0, 0};
     CK(h, cudaMemcpyAsync(hflags.data(), flags, (size_t)nq * 4, cudaMemcpyDeviceToHost, st));
+    if (half) CK(h, cudaMemcpyAsync(f16st, h->d_f16st.p, sizeof(f16st), cudaMemcpyDeviceToHost, st));
     CK(h, cudaStreamSynchronize(st));
+    if (half && f16st[2]) {
+        // rows far larger than any present when the shadow's scale was frozen overflowed fp16: nothing this tier
+        // selected can be trusted; the shadow is rebuilt with a fresh scale by the next batch
+        std::fill(hflags.begin(), hflags.end(), 2u);
+        h->f16_valid = 0;
+    }
     return MLV_OK;
 }
 
@@ -285,6 +348,7 @@ int search_gemm(mlv_index* h, const float* qprep, uint32_t nq, uint32_t k, const
     view.live = h->n_deleted ? h->d_live : nullptr;
     view.filter = filter_dev;
     bool short_bitmap = false;
+    uint32_t gathered_rows = 0;
     mlv_filter* bf = filter_dev ? nullptr : h->bound_filter;
     if (bf) {
         if (bf->compact_gen != h->compact_gen)
@@ -328,6 +392,7 @@ int search_gemm(mlv_index* h, const float* qprep, uint32_t nq, uint32_t k, const
             gather = false;   // no room for the copy beside the matrix: mask in the epilogue instead
         }
         if (gather) {
+            gathered_rows = m;
             float* gx = (float*)h->d_gx.p;
             float* gn = gx + (size_t)m * ld;
             const int wpb = 8;
@@ -352,13 +417,41 @@ int search_gemm(mlv_index* h, const float* qprep, uint32_t nq, uint32_t k, const
         h->gemm_fast_skip--;
         fast = false;
     }
-    if ((rc = search_gemm_tier(h, qprep, nq, k, fast ? 1 : 3, view, out_d, out_r, out_c, st, hflags)) != MLV_OK) return rc;
+    // first tier: the fp16 shadow (twice the rate of the TF32 pass and half its error) when there is room for it
+    int first_tier = fast ? 1 : 3;
+    if (fast && (h->tune_gemm_passes == 0 || h->tune_gemm_passes == GEMM_TIER_F16)) {
+        bool usable = false;
+        if ((rc = ensure_f16_shadow(h, st, &usable)) != MLV_OK) return rc;
+        if (usable && gathered_rows) {   // a filtered batch multiplies the compacted rows: their halves, same frozen scale
+            const uint32_t ld16 = f16_ld(h);
+            if (ensure_dev(h, h->d_gx16, (size_t)gathered_rows * ld16 * 2) != MLV_OK) {
+                usable = false;
+                h->err.clear();
+                cudaGetLastError();
+            } else {
+                const uint64_t total = (uint64_t)gathered_rows * (ld16 / 2);
+                convert_rows_f16_kernel<<<(unsigned)std::min<uint64_t>((total + 255) / 256, (uint64_t)h->sm_count * 16), 256, 0, st>>>(
+                    view.rows, 0, gathered_rows, ld, ld16, (__half*)h->d_gx16.p, (uint32_t*)h->d_f16st.p);
+                h->launches++;
+                CK(h, cudaGetLastError());
+                view.rows16 = h->d_gx16.p;
+            }
+        } else if (usable) {
+            view.rows16 = h->d_rows16.p;
+        }
+        if (usable) {
+            view.x_unscale = (const float*)h->d_f16st.p;
+            first_tier = GEMM_TIER_F16;
+        }
+    }
+    if ((rc = search_gemm_tier(h, qprep, nq, k, first_tier, view, out_d, out_r, out_c, st, hflags)) != MLV_OK) return rc;
     for (uint32_t q = 0; q < nq; q++)
         if (hflags[q]) failing.push_back(q);
     if (fast) {
         h->gemm_fast_queries += nq - failing.size();
+        if (first_tier == GEMM_TIER_F16) h->gemm_half_queries += nq - failing.size();
         if (h->tune_gemm_passes == 0 && failing.size() * 2 > nq) h->gemm_fast_skip = 8;
-        if (!failing.empty() && h->tune_gemm_passes != 1) {
+        if (!failing.empty() && h->tune_gemm_passes != 1 && h->tune_gemm_passes != GEMM_TIER_F16) {
             // second tier on the compacted failing queries; results scattered back to their slots
             const uint32_t nf = (uint32_t)failing.size();
             const size_t need = (size_t)nf * 4 + (size_t)nf * ld * 4 + (size_t)nf * k * 12 + (size_t)nf * 4 + 64;
@@ -392,6 +485,7 @@ int search_gemm(mlv_index* h, const float* qprep, uint32_t nq, uint32_t k, const
     // the dense copy of a filtered batch's rows can be a large fraction of the matrix: small ones are kept for the next
     // batch, large ones go back to the allocator (every tier has synchronised `st` after its last use of the copy)
     if (h->d_gx.bytes > ((size_t)1 << 30)) free_dev(h->d_gx);
+    if (h->d_gx16.bytes > ((size_t)1 << 29)) free_dev(h->d_gx16);
     return MLV_OK;
 }
 

@@ -125,7 +125,7 @@ int mlv_index_destroy(mlv_index_t h) {
     if (h->d_rows) cudaFree(h->d_rows);
     if (h->d_live) cudaFree(h->d_live);
     for (DevBuf* b : {&h->d_qraw, &h->d_filter, &h->d_outd, &h->d_outr, &h->d_outc, &h->d_misc, &h->d_range, &h->d_timeline,
-                      &h->d_norms, &h->d_gq, &h->d_cand, &h->d_maxn2, &h->d_sub, &h->d_gx})
+                      &h->d_norms, &h->d_gq, &h->d_cand, &h->d_maxn2, &h->d_sub, &h->d_gx, &h->d_rows16, &h->d_f16st, &h->d_gx16})
         free_dev(*b);
     for (Lane& l : h->lanes)
         for (DevBuf* b : {&l.d_q, &l.d_keys0, &l.d_keys1, &l.d_sched, &l.d_flist, &l.d_fscratch}) free_dev(*b);
@@ -358,6 +358,7 @@ int mlv_index_compact(mlv_index_t h, int64_t* old_to_new, uint64_t* new_rows) {
     h->rows = total;
     h->n_deleted = 0;
     h->norms_valid = 0;
+    h->f16_valid = 0;
     h->epoch++;
     h->compact_gen++;
     CK(h, cudaMemsetAsync(h->d_live, 0, h->live_words * 4, h->stream));
@@ -382,6 +383,7 @@ int mlv_index_clear(mlv_index_t h) {
     h->rows = 0;
     h->n_deleted = 0;
     h->norms_valid = 0;
+    h->f16_valid = 0;
     h->epoch++;
     h->compact_gen++;
     drop_columns(h);
@@ -747,7 +749,7 @@ static int search_host_common(mlv_index_t h, const float* queries, uint32_t nq, 
     const size_t nk = (size_t)nq * k;
     const size_t out_bytes = nk * 4 + nk * 8 + (size_t)nq * 4;
     int rc;
-    if ((rc = ensure_host(h, h->h_stage, std::max(qbytes, out_bytes) + 64)) != MLV_OK) return rc;
+    if ((rc = ensure_host(h, h->h_stage, std::max(qbytes, out_bytes) + 192)) != MLV_OK) return rc;
     if (nq == 1 && !filter_bitmap && h->rows != h->n_deleted && h->dim <= SCAN_INLINE_MAX_DIM && h->tune_fast_host &&
         (!exchange || exchange_ok(h, k))) {
         // Batch-1 latency path (BASELINE configs[0]): ONE launch and nothing else.  The raw query travels in the kernel
@@ -762,6 +764,7 @@ static int search_host_common(mlv_index_t h, const float* queries, uint32_t nq, 
         fa.done_flag = flag;
         fa.done_value = ++h->flag_seq ? h->flag_seq : ++h->flag_seq;
         fa.took_fast = &took;
+        *(volatile unsigned int*)flag = 0;   // nothing of this handle is in flight on the block: every call waits for its own results
         rc = search_prepared(h, nullptr, 1, k, nullptr, (float*)(hs + nk * 8), (int64_t*)hs, (int32_t*)(hs + nk * 12), h->stream, exchange, &fa);
         if (rc != MLV_OK) return rc;
         if (took) {
@@ -1108,7 +1111,7 @@ int mlv_index_info(mlv_index_t h, mlv_index_info_t* info) {
     info->row_base = h->row_base;
     size_t b = (size_t)h->capacity * h->ld * 4 + (size_t)h->live_words * 4;
     for (const DevBuf* d : {&h->d_qraw, &h->d_filter, &h->d_outd, &h->d_outr, &h->d_outc, &h->d_misc, &h->d_range, &h->d_norms,
-                            &h->d_gq, &h->d_cand, &h->d_maxn2})
+                            &h->d_gq, &h->d_cand, &h->d_maxn2, &h->d_rows16, &h->d_gx, &h->d_gx16})
         b += d->bytes;
     for (const Lane& l : h->lanes)
         for (const DevBuf* d : {&l.d_q, &l.d_keys0, &l.d_keys1, &l.d_sched, &l.d_flist, &l.d_fscratch}) b += d->bytes;
@@ -1191,6 +1194,7 @@ int mlv_index_gemm_stats(mlv_index_t h, mlv_gemm_stats_t* out) {
     out->queries = h->gemm_queries;
     out->fallback_queries = h->gemm_fallback_queries;
     out->fast_queries = h->gemm_fast_queries;
+    out->half_queries = h->gemm_half_queries;
     out->gathered_searches = h->gemm_gathered_searches;
     out->rounds = h->gemm_rounds;
     return MLV_OK;
