@@ -332,6 +332,12 @@ int mlv_index_range_search_exchange(mlv_index_t h, const float *queries, uint32_
                                     uint64_t *out_counts);
 
 /*
+ * Tracing: with MLV_NVTX=1 in the environment every entry point that touches the device (add, mark_deleted, compact,
+ * search*, submit / collect, range_search*, filter_create_where) and every tensor-core tier opens an NVTX range of its
+ * own name, so a profiler's timeline shows the host call around the kernels it launched.  Off by default.
+ */
+
+/*
  * Measurement hooks (bench.py / profiles): when enabled, every search records CUDA events
  * around its scan kernel on the launching stream; mlv_index_scan_time_ms returns the sum
  * of the completed scan-kernel durations since the last call and how many launches that
@@ -352,9 +358,11 @@ int mlv_index_scan_time_ms(mlv_index_t h, double *total_ms, uint64_t *launches);
  */
 int mlv_index_set_tuning(mlv_index_t h, const char *key, int value);
 /*
- * Debug: after set_tuning("timeline", 1) every top-k scan records four %globaltimer stamps (ns)
- * per CTA: start, first tile landed, last tile consumed, exit.  Copies 4 * n_ctas values of the
- * most recent scan into `out` (synchronises the device).
+ * Debug: after set_tuning("timeline", 1) every top-k scan records sixteen %globaltimer stamp slots (ns)
+ * per CTA: 0 start, 1 first tile landed, 2 last tile consumed, 3 lists folded, 4 ticket taken, and -- for the last CTA
+ * only, 0 elsewhere -- 5 final select done, 6 outputs written, 7 completion flag raised; finer ones: 8 own lists sorted,
+ * 9 every warp's lists sorted, last CTA 10 past the fence, 11 threshold known, 12 survivors gathered.  Copies 16 * n_ctas
+ * values of the most recent scan into `out` (synchronises the device).
  */
 int mlv_index_debug_timeline(mlv_index_t h, uint64_t *out, uint32_t max_ctas, uint32_t *n_ctas);
 /*

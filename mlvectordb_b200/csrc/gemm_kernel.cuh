@@ -63,7 +63,7 @@ struct GemmShape {
     static constexpr uint32_t Q_BYTES = BN * GEMM_BK * 4;
     static constexpr uint32_t STAGE_BYTES = PASSES == 3 ? 2 * GEMM_X_BYTES + 2 * Q_BYTES : GEMM_X_BYTES + Q_BYTES;
     static constexpr int STAGES = PASSES == 3 ? (BN == 256 ? 2 : (BN == 128 ? 3 : 4)) : (BN == 256 ? 4 : 6);
-    static constexpr uint32_t SMEM_BYTES = 1024 + STAGES * STAGE_BYTES + 3 * BN * 4 + 256;
+    static constexpr uint32_t SMEM_BYTES = 1024 + STAGES * STAGE_BYTES + 5 * BN * 4 + 256;
     // fp32 accumulate, A and B K-major, M = 128, N = BN; operand format TF32 (kind::tf32) or F16 (kind::f16)
     static constexpr uint32_t FMT = PASSES == GEMM_TIER_F16 ? 0u : 2u;
     static constexpr uint32_t IDESC = (1u << 4) | (FMT << 7) | (FMT << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(GEMM_BM >> 4) << 24);
@@ -105,6 +105,7 @@ struct GemmParams {
     // PASSES = 2: the accumulator holds (x * 2^sx) . (q * 2^sq); dot = acc * *x_unscale * q_unscale[query]
     const float* x_unscale;  // device scalar 2^-sx, frozen when the shadow was converted
     const float* q_unscale;  // [nq_pad] 2^-sq
+    int debug;               // profiling only (set_tuning "gemm_debug"): bit 0 = the epilogue drains nothing (results are wrong)
 };
 
 // ---- PTX wrappers ---------------------------------------------------------------------------
@@ -151,18 +152,116 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
     return d;
 }
 
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+// wait for every tcgen05.ld issued so far; the registers of the load being waited for are in/out operands, so no use
+// of them can be scheduled above the wait
+__device__ __forceinline__ void tmem_ld_wait(uint32_t (&v)[32]) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]), "+r"(v[7]), "+r"(v[8]),
+                   "+r"(v[9]), "+r"(v[10]), "+r"(v[11]), "+r"(v[12]), "+r"(v[13]), "+r"(v[14]), "+r"(v[15]), "+r"(v[16]),
+                   "+r"(v[17]), "+r"(v[18]), "+r"(v[19]), "+r"(v[20]), "+r"(v[21]), "+r"(v[22]), "+r"(v[23]), "+r"(v[24]),
+                   "+r"(v[25]), "+r"(v[26]), "+r"(v[27]), "+r"(v[28]), "+r"(v[29]), "+r"(v[30]), "+r"(v[31])
+                 :
+                 : "memory");
+}
+// issue only: the registers are valid after the next tmem_ld_wait()
+__device__ __forceinline__ void tmem_ld32_issue(uint32_t taddr, uint32_t (&v)[32]) {
     asm volatile(
         "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
         "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n\t"
-        "tcgen05.wait::ld.sync.aligned;"
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
         : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
           "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
           "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
           "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
         : "r"(taddr)
         : "memory");
+}
+
+// ---- epilogue pieces shared by both GEMM kernels ---------------------------------------------------------------------
+// Per query: the threshold test a <= thr solved for the raw accumulator value v (dot = us * v):
+//   l2      xn + qn - 2 us v <= thr   <=>   v - xn c2 >= c1,   c2 = 1 / (2 us),  c1 = (qn - thr) c2
+//   ip      1 - us v <= thr           <=>   v >= c1,           c1 = (1 - thr) / us
+// so a value costs one FFMA + one compare (ip: one compare) instead of three shared-memory loads and five operations.
+// The pre-test constants are RELAXED by 2^-19 of the magnitudes involved (16x the rounding of either form), so the
+// pre-test never rejects a value the exact test would accept; the rare 32-column chunks with a hit are re-examined with
+// the exact test -- the candidate sets are those of the plain loop, bit for bit.  Called by the 128 threads
+// (et = 0..127) that are about to drain a tile of query tile qt; the caller synchronises them afterwards.
+template <int METRIC, bool F16, int BN>
+__device__ __forceinline__ void epilogue_constants(const GemmParams& p, uint32_t qt, int et, float* thr_s, float* qn_s, float* us_s,
+                                                   float* c1_s, float* c2_s) {
+    const float xus = F16 ? __ldg(p.x_unscale) : 1.0f;
+    for (int i = et; i < BN; i += 128) {
+        const float thr = p.thr[qt * BN + i], qn = p.q_norms[qt * BN + i];
+        const float us = F16 ? p.q_unscale[qt * BN + i] * xus : 1.0f;   // powers of two: the product is exact
+        thr_s[i] = thr;
+        qn_s[i] = qn;
+        if (F16) us_s[i] = us;
+        const bool fin = fabsf(thr) <= 3.0e38f;
+        if (METRIC == METRIC_L2) {
+            const float c2 = 0.5f / us;
+            const float c1 = (qn - thr) * c2;
+            c2_s[i] = c2 * (1.0f - 1.9073486328125e-6f);
+            c1_s[i] = fin ? c1 - 1.9073486328125e-6f * c2 * (qn + fabsf(thr)) : c1;
+        } else {
+            const float c1 = (1.0f - thr) / us;
+            c1_s[i] = fin ? c1 - 1.9073486328125e-6f * (1.0f + fabsf(thr)) / us : c1;
+        }
+    }
+}
+
+// One thread = one row (TMEM lane) of a 128 x BN accumulator at taddr0: BN values, 32 per tcgen05.ld, two register
+// buffers so the load of chunk c + 1 is in flight while chunk c is tested.
+template <int METRIC, bool F16, int BN>
+__device__ __forceinline__ void epilogue_drain(const GemmParams& p, uint32_t taddr0, uint32_t qt, uint32_t row, bool row_ok, float xn,
+                                               const float* thr_s, const float* qn_s, const float* us_s, const float* c1_s,
+                                               const float* c2_s) {
+    const float nxn = -xn;
+    auto process = [&](const uint32_t(&v)[32], uint32_t c) {
+        if (!row_ok) return;
+        const float4* k1 = reinterpret_cast<const float4*>(c1_s + c * 32);
+        const float4* k2 = reinterpret_cast<const float4*>(c2_s + c * 32);
+        bool any = false;
+#pragma unroll
+        for (int j4 = 0; j4 < 8; j4++) {
+            const float4 a1 = k1[j4];
+            const float v0 = __uint_as_float(v[4 * j4]), v1 = __uint_as_float(v[4 * j4 + 1]);
+            const float v2 = __uint_as_float(v[4 * j4 + 2]), v3 = __uint_as_float(v[4 * j4 + 3]);
+            if (METRIC == METRIC_L2) {
+                const float4 a2 = k2[j4];
+                any |= fmaf(nxn, a2.x, v0) >= a1.x;
+                any |= fmaf(nxn, a2.y, v1) >= a1.y;
+                any |= fmaf(nxn, a2.z, v2) >= a1.z;
+                any |= fmaf(nxn, a2.w, v3) >= a1.w;
+            } else {
+                any |= v0 >= a1.x;
+                any |= v1 >= a1.y;
+                any |= v2 >= a1.z;
+                any |= v3 >= a1.w;
+            }
+        }
+        if (!any) return;
+#pragma unroll
+        for (int j = 0; j < 32; j++) {   // fully unrolled: v[] must stay in registers
+            const uint32_t ql = c * 32 + j;
+            const float dot = F16 ? __uint_as_float(v[j]) * us_s[ql] : __uint_as_float(v[j]);
+            const float a = (METRIC == METRIC_L2) ? fmaf(-2.0f, dot, xn + qn_s[ql]) : 1.0f - dot;
+            if (a <= thr_s[ql]) {
+                const uint32_t qg = qt * BN + ql;
+                const uint32_t pos = atomicAdd(p.cand_cnt + qg, 1u);
+                if (pos < p.cap) p.cand[(size_t)qg * p.cap + pos] = make_key(a, row);
+            }
+        }
+    };
+    uint32_t va[32], vb[32];
+    tmem_ld32_issue(taddr0, va);
+    for (uint32_t c = 0; c < BN / 32; c += 2) {   // BN / 32 is even
+        tmem_ld_wait(va);
+        tmem_ld32_issue(taddr0 + (c + 1) * 32, vb);
+        process(va, c);
+        tmem_ld_wait(vb);
+        if (c + 2 < BN / 32) tmem_ld32_issue(taddr0 + (c + 2) * 32, va);
+        process(vb, c + 1);
+    }
 }
 
 // ---- the GEMM + candidate-selection kernel ---------------------------------------------------
@@ -184,7 +283,9 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
     float* thr_s = reinterpret_cast<float*>(smem + GEMM_STAGES * GEMM_STAGE_BYTES);  // [256]
     float* qn_s = thr_s + GEMM_BN;                                                    // [256]
     float* us_s = qn_s + GEMM_BN;                                                     // [256] (PASSES = 2)
-    uint64_t* bars = reinterpret_cast<uint64_t*>(us_s + GEMM_BN);
+    float* c1_s = us_s + GEMM_BN;                                                     // [256] pre-test constants
+    float* c2_s = c1_s + GEMM_BN;                                                     // [256]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(c2_s + GEMM_BN);
     uint64_t* full = bars;                      // [S]  TMA bytes landed
     uint64_t* empty = bars + GEMM_STAGES;       // [S]  MMAs reading the stage retired
     uint64_t* conv = bars + 2 * GEMM_STAGES;    // [S]  hi/lo split written
@@ -332,14 +433,9 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
             const uint32_t rt = p.row_tile0 + it / p.n_qtiles, qt = it % p.n_qtiles;
             const uint32_t acc = local & 1, acc_phase = (local >> 1) & 1;
             named_bar_sync(2, 128);  // everyone finished reading thr_s / qn_s of the previous item
-            const float xus = F16 ? __ldg(p.x_unscale) : 1.0f;
-            for (int i = et; i < GEMM_BN; i += 128) {
-                thr_s[i] = p.thr[qt * GEMM_BN + i];
-                qn_s[i] = p.q_norms[qt * GEMM_BN + i];
-                if (F16) us_s[i] = p.q_unscale[qt * GEMM_BN + i] * xus;   // powers of two: the product is exact
-            }
+            epilogue_constants<METRIC, F16, GEMM_BN>(p, qt, et, thr_s, qn_s, us_s, c1_s, c2_s);
             const uint32_t row = rt * GEMM_BM + quarter * 32 + lane;
-            bool row_ok = row < p.n_rows;
+            bool row_ok = row < p.n_rows && !(p.debug & 1);
             float xn = 0.f;
             if (row_ok) {
                 if (p.live) row_ok = (__ldg(p.live + (row >> 5)) >> (row & 31)) & 1u;
@@ -350,23 +446,7 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
             mbar_wait(&tfull[acc], acc_phase);
             tc_fence_after();
             const uint32_t taddr0 = tmem_base + ((quarter * 32u) << 16) + acc * GEMM_BN;
-            for (uint32_t c = 0; c < GEMM_BN / 32; c++) {
-                uint32_t v[32];
-                tmem_ld32(taddr0 + c * 32, v);
-                if (row_ok) {
-#pragma unroll
-                    for (int j = 0; j < 32; j++) {
-                        const uint32_t ql = c * 32 + j;
-                        const float dot = F16 ? __uint_as_float(v[j]) * us_s[ql] : __uint_as_float(v[j]);
-                        const float a = (METRIC == METRIC_L2) ? fmaf(-2.0f, dot, xn + qn_s[ql]) : 1.0f - dot;
-                        if (a <= thr_s[ql]) {
-                            const uint32_t qg = qt * GEMM_BN + ql;
-                            const uint32_t pos = atomicAdd(p.cand_cnt + qg, 1u);
-                            if (pos < p.cap) p.cand[(size_t)qg * p.cap + pos] = make_key(a, row);
-                        }
-                    }
-                }
-            }
+            epilogue_drain<METRIC, F16, GEMM_BN>(p, taddr0, qt, row, row_ok, xn, thr_s, qn_s, us_s, c1_s, c2_s);
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&tempty[acc]);
@@ -375,6 +455,205 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
 
     tc_fence_before();
     __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+    }
+}
+
+// ---- the wide one-pass kernel: TWO row tiles per staged query tile -------------------------------------------------
+// ncu (r02) showed the one-pass tiers of gemm_topk_kernel pinned at the L2 -> SM delivery limit (xbar2l1tex 11.2 TB/s, the
+// chip's ~6300 B/clk; tensor pipe 35 - 43 % active): a 128 x 256 tile pulls (128 + 256) operand rows per K chunk.  This
+// kernel keeps TWO accumulators (2 x 256 TMEM columns = all 512) and feeds both from one staged query tile, so an item is
+// 256 rows x 256 queries and pulls (256 + 256) operand rows for twice the products: 2/3 of the bytes per product.  With
+// CL = 2 the two CTAs of a cluster work on the same query tile (four consecutive row tiles) and each loads HALF of it,
+// multicast into both CTAs' shared memory: (256 + 128) rows per 256 x 256 products, half of the single-tile kernel's.
+// The accumulators are not double-buffered any more; instead two groups of four epilogue warps drain them side by side,
+// and with the cheap pre-test (epilogue_drain) that drain is ~1/5 of the tile's tensor time.
+// PASSES is 1 (TF32 on the fp32 rows) or GEMM_TIER_F16 (fp16 shadow); BN is 256.  320 threads:
+//   warp 0 TMA producer | warp 1 MMA issuer | warps 2-5 drain accumulator 0 | warps 6-9 drain accumulator 1
+constexpr int GEMM2_BN = 256;
+constexpr int GEMM2_STAGES = 3;
+constexpr uint32_t GEMM2_Q_BYTES = GEMM2_BN * GEMM_BK * 4;                    // 32 KB
+constexpr uint32_t GEMM2_STAGE_BYTES = 2 * GEMM_X_BYTES + GEMM2_Q_BYTES;      // X0 | X1 | Q = 64 KB
+constexpr uint32_t GEMM2_SMEM_BYTES = 1024 + GEMM2_STAGES * GEMM2_STAGE_BYTES + 5 * GEMM2_BN * 4 + 256;
+
+__device__ __forceinline__ void tma_load_2d_mc(void* smem_dst, const CUtensorMap* map, int32_t c0, int32_t c1, uint64_t* bar, uint16_t mask) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], [%2], %5;" ::"r"(
+            smem_u32(smem_dst)),
+        "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "h"(mask)
+        : "memory");
+}
+__device__ __forceinline__ void tc_commit_mc(uint64_t* bar, uint16_t mask) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)),
+                 "h"(mask)
+                 : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+
+template <int METRIC, int PASSES, int CL>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm_topk2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_q, const GemmParams p) {
+    static_assert(PASSES == 1 || PASSES == GEMM_TIER_F16, "one-pass tiers only");
+    static_assert(CL == 1 || CL == 2, "cluster of one or two CTAs");
+    constexpr bool F16 = PASSES == GEMM_TIER_F16;
+    constexpr uint32_t CHUNK_ELEMS = F16 ? 64 : 32;
+    constexpr uint32_t IDESC = GemmShape<GEMM2_BN, PASSES>::IDESC;
+    constexpr uint32_t Q_OFF = 2 * GEMM_X_BYTES;
+    extern __shared__ unsigned char gemm_smem_raw[];
+    unsigned char* smem = gemm_smem_raw + ((1024u - (smem_u32(gemm_smem_raw) & 1023u)) & 1023u);
+    float* thr_s = reinterpret_cast<float*>(smem + GEMM2_STAGES * GEMM2_STAGE_BYTES);
+    float* qn_s = thr_s + GEMM2_BN;
+    float* us_s = qn_s + GEMM2_BN;
+    float* c1_s = us_s + GEMM2_BN;
+    float* c2_s = c1_s + GEMM2_BN;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(c2_s + GEMM2_BN);
+    uint64_t* full = bars;                       // [S]  TMA bytes landed (own loads + the peer's multicast half)
+    uint64_t* empty = bars + GEMM2_STAGES;       // [S]  every CTA of the cluster has retired the MMAs reading the stage
+    uint64_t* tfull = bars + 2 * GEMM2_STAGES;   // [1]  both accumulators complete
+    uint64_t* tempty = tfull + 1;                // [2]  accumulator a drained (4 warps each)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+
+    const int tid = threadIdx.x;
+    const int warp = tid >> 5;
+    const int lane = tid & 31;
+    const uint32_t crank = CL > 1 ? cluster_ctarank() : 0;
+    const uint16_t all_mask = (uint16_t)((1u << CL) - 1u);
+
+    if (tid == 0) {
+        for (int s = 0; s < GEMM2_STAGES; s++) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], CL);
+        }
+        mbar_init(tfull, 1);
+        mbar_init(&tempty[0], 4);
+        mbar_init(&tempty[1], 4);
+        mbar_fence_init();
+        tma_prefetch_desc(&tm_x);
+        tma_prefetch_desc(&tm_q);
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (CL > 1) cluster_sync_all();   // the peer's barriers exist before anything is multicast into this CTA
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    // items: (group of 2 * CL consecutive row tiles) x (query tile); the cluster's CTAs take the same item together
+    const uint32_t tiles = p.row_tile1 - p.row_tile0;
+    const uint32_t n_groups = (tiles + 2 * CL - 1) / (2 * CL);
+    const uint32_t n_items = n_groups * p.n_qtiles;
+    const uint32_t cluster_id = blockIdx.x / CL, n_clusters = gridDim.x / CL;
+
+    if (warp == 0) {
+        // ------------------------------------------------------------------ TMA producer
+        if (lane == 0) {
+            uint32_t stage = 0, phase = 0;
+            for (uint32_t it = cluster_id; it < n_items; it += n_clusters) {
+                const uint32_t grp = it / p.n_qtiles, qt = it % p.n_qtiles;
+                const uint32_t rt = p.row_tile0 + (grp * CL + crank) * 2;
+                for (uint32_t kc = 0; kc < p.n_kchunks; kc++) {
+                    mbar_wait(&empty[stage], phase ^ 1);
+                    unsigned char* sb = smem + (size_t)stage * GEMM2_STAGE_BYTES;
+                    mbar_arrive_expect_tx(&full[stage], GEMM2_STAGE_BYTES);
+                    tma_load_2d(sb, &tm_x, (int32_t)(kc * CHUNK_ELEMS), (int32_t)(rt * GEMM_BM), &full[stage]);
+                    tma_load_2d(sb + GEMM_X_BYTES, &tm_x, (int32_t)(kc * CHUNK_ELEMS), (int32_t)((rt + 1) * GEMM_BM), &full[stage]);
+                    if (CL == 1) {
+                        tma_load_2d(sb + Q_OFF, &tm_q, (int32_t)(kc * CHUNK_ELEMS), (int32_t)(qt * GEMM2_BN), &full[stage]);
+                    } else {
+                        // this CTA's half of the query tile (box of BN / 2 rows) lands in BOTH CTAs, at the same offset
+                        tma_load_2d_mc(sb + Q_OFF + crank * (GEMM2_Q_BYTES / 2), &tm_q, (int32_t)(kc * CHUNK_ELEMS),
+                                       (int32_t)(qt * GEMM2_BN + crank * (GEMM2_BN / 2)), &full[stage], all_mask);
+                    }
+                    if (++stage == GEMM2_STAGES) {
+                        stage = 0;
+                        phase ^= 1;
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ------------------------------------------------------------------ MMA issuer
+        if (lane == 0) {
+            uint32_t stage = 0, phase = 0, local = 0;
+            for (uint32_t it = cluster_id; it < n_items; it += n_clusters, local++) {
+                mbar_wait(&tempty[0], (local & 1) ^ 1);
+                mbar_wait(&tempty[1], (local & 1) ^ 1);
+                tc_fence_after();
+                for (uint32_t kc = 0; kc < p.n_kchunks; kc++) {
+                    mbar_wait(&full[stage], phase);
+                    tc_fence_after();
+                    const uint32_t sb = smem_u32(smem + (size_t)stage * GEMM2_STAGE_BYTES);
+                    const uint64_t d_x0 = umma_desc_sw128(sb), d_x1 = umma_desc_sw128(sb + GEMM_X_BYTES);
+                    const uint64_t d_q = umma_desc_sw128(sb + Q_OFF);
+#pragma unroll
+                    for (uint32_t ks = 0; ks < GEMM_BK / 8; ks++) {
+                        const uint64_t adv = (uint64_t)(ks * 2);
+                        if (F16) {
+                            tc_mma_f16(tmem_base, d_x0 + adv, d_q + adv, IDESC, (kc | ks) != 0);
+                            tc_mma_f16(tmem_base + GEMM2_BN, d_x1 + adv, d_q + adv, IDESC, (kc | ks) != 0);
+                        } else {
+                            tc_mma_tf32(tmem_base, d_x0 + adv, d_q + adv, IDESC, (kc | ks) != 0);
+                            tc_mma_tf32(tmem_base + GEMM2_BN, d_x1 + adv, d_q + adv, IDESC, (kc | ks) != 0);
+                        }
+                    }
+                    // the stage is reusable once these MMAs have read it -- in every CTA that was written into by a loader
+                    if (CL == 1)
+                        tc_commit(&empty[stage]);
+                    else
+                        tc_commit_mc(&empty[stage], all_mask);
+                    if (++stage == GEMM2_STAGES) {
+                        stage = 0;
+                        phase ^= 1;
+                    }
+                }
+                tc_commit(tfull);
+            }
+        }
+    } else {
+        // ------------------------------------------------------------------ epilogue: group 0 = warps 2-5, group 1 = warps 6-9
+        const int et = tid - 64;            // 0..255
+        const uint32_t grp_e = (uint32_t)(warp - 2) >> 2;
+        const uint32_t quarter = warp & 3;  // TMEM lanes this warp may read: 32*quarter .. +31
+        uint32_t local = 0;
+        for (uint32_t it = cluster_id; it < n_items; it += n_clusters, local++) {
+            const uint32_t grp = it / p.n_qtiles, qt = it % p.n_qtiles;
+            const uint32_t tile = p.row_tile0 + (grp * CL + crank) * 2 + grp_e;
+            named_bar_sync(2, 256);  // everyone finished reading the constants of the previous item
+            if (et < 128) epilogue_constants<METRIC, F16, GEMM2_BN>(p, qt, et, thr_s, qn_s, us_s, c1_s, c2_s);
+            const uint32_t row = tile * GEMM_BM + quarter * 32 + lane;
+            bool row_ok = tile < p.row_tile1 && row < p.n_rows && !(p.debug & 1);   // a group's last tiles may belong to the next round
+            float xn = 0.f;
+            if (row_ok) {
+                if (p.live) row_ok = (__ldg(p.live + (row >> 5)) >> (row & 31)) & 1u;
+                if (row_ok && p.filter) row_ok = (__ldg(p.filter + (row >> 5)) >> (row & 31)) & 1u;
+                if (METRIC == METRIC_L2 && row_ok) xn = __ldg(p.row_norms + row);
+            }
+            named_bar_sync(2, 256);
+            mbar_wait(tfull, local & 1);
+            tc_fence_after();
+            const uint32_t taddr0 = tmem_base + ((quarter * 32u) << 16) + grp_e * GEMM2_BN;
+            epilogue_drain<METRIC, F16, GEMM2_BN>(p, taddr0, qt, row, row_ok, xn, thr_s, qn_s, us_s, c1_s, c2_s);
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty[grp_e]);
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (CL > 1) cluster_sync_all();   // no CTA leaves while the peer may still multicast into it or arrive on its barriers
     if (warp == 1) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");

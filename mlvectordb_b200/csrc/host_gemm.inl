@@ -129,6 +129,33 @@ cudaError_t launch_gemm_t(const CUtensorMap& mx, const CUtensorMap& mqh, const C
     return passes == 1 ? launch_gemm_tp<METRIC, 1>(mx, mqh, mql, gp, grid, st, bn) : launch_gemm_tp<METRIC, 3>(mx, mqh, mql, gp, grid, st, bn);
 }
 
+// the wide kernel (two row tiles per staged query tile; CL = 2: clusters of two CTAs sharing the query tile by multicast)
+template <int METRIC, int PASSES, int CL>
+cudaError_t launch_gemm2_t(const CUtensorMap& mx, const CUtensorMap& mq, const GemmParams& gp, int grid, cudaStream_t st) {
+    auto kern = gemm_topk2_kernel<METRIC, PASSES, CL>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM2_SMEM_BYTES);
+    if (e != cudaSuccess) return e;
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.blockDim = dim3(GEMM_THREADS);
+    cfg.dynamicSmemBytes = GEMM2_SMEM_BYTES;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CL;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kern, mx, mq, gp);
+}
+template <int METRIC>
+cudaError_t launch_gemm2(const CUtensorMap& mx, const CUtensorMap& mq, const GemmParams& gp, int grid, cudaStream_t st, int passes, int cl) {
+    if (passes == GEMM_TIER_F16)
+        return cl == 2 ? launch_gemm2_t<METRIC, GEMM_TIER_F16, 2>(mx, mq, gp, grid, st) : launch_gemm2_t<METRIC, GEMM_TIER_F16, 1>(mx, mq, gp, grid, st);
+    return cl == 2 ? launch_gemm2_t<METRIC, 1, 2>(mx, mq, gp, grid, st) : launch_gemm2_t<METRIC, 1, 1>(mx, mq, gp, grid, st);
+}
+
 // The fp16 shadow of the rows ([capacity, f16_ld] halves of value * 2^s) behind the HALF tier, built lazily like the row
 // norms: rows [0, f16_valid) are current; the scale is frozen when row 0 is converted (st[0..2] = 2^-s, s, overflow flag).
 // Returns MLV_OK with *usable = false when there is no room for it (the caller takes the TF32 tier).
@@ -191,6 +218,7 @@ struct GemmView {
 // (or the candidate buffer overflowed): the caller re-runs those queries.  Synchronises `st` once (to read the flags).
 int search_gemm_tier(mlv_index* h, const float* qprep, uint32_t nq, uint32_t k, int passes, const GemmView& view, float* out_d,
                      int64_t* out_r, int32_t* out_c, cudaStream_t st, std::vector<uint32_t>& hflags) {
+    NvtxRange nvtx_range(passes == GEMM_TIER_F16 ? "gemm tier: fp16 shadow" : (passes == 1 ? "gemm tier: 1xTF32" : "gemm tier: 3xTF32"));
     int rc;
     const uint32_t ld = h->ld;
     const uint32_t GEMM_BN = gemm_tile_width(h, nq);
@@ -224,9 +252,11 @@ int search_gemm_tier(mlv_index* h, const float* qprep, uint32_t nq, uint32_t k, 
         h->launches++;
         CK(h, cudaGetLastError());
     }
+    // wide kernel (two row tiles per staged query tile) for the one-pass tiers of wide batches; cl = CTAs per cluster
+    const int wide_cl = (GEMM_BN == 256 && passes != 3 && h->tune_gemm_wide != 0) ? (h->tune_gemm_wide == 1 ? 1 : 2) : 0;
     CUtensorMap mx, mqh, mql;
     if ((rc = make_tile_map(h, &mx, half ? view.rows16 : (const void*)view.rows, view.n_rows, GEMM_BM, half)) != MLV_OK) return rc;
-    if ((rc = make_tile_map(h, &mqh, qhi, nq_pad, GEMM_BN, half)) != MLV_OK) return rc;
+    if ((rc = make_tile_map(h, &mqh, qhi, nq_pad, wide_cl == 2 ? GEMM_BN / 2 : GEMM_BN, half)) != MLV_OK) return rc;
     if ((rc = make_tile_map(h, &mql, half ? qhi : qlo, nq_pad, GEMM_BN, half)) != MLV_OK) return rc;
     CK(h, cudaFuncSetAttribute(refine_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SELECT_MAX_P * 8)));
 
@@ -237,6 +267,7 @@ int search_gemm_tier(mlv_index* h, const float* qprep, uint32_t nq, uint32_t k, 
     gp.n_kchunks = half ? (ld16 + 2 * GEMM_BK - 1) / (2 * GEMM_BK) : (ld + GEMM_BK - 1) / GEMM_BK;
     gp.x_unscale = view.x_unscale;
     gp.q_unscale = q_unscale;
+    gp.debug = h->tune_gemm_debug;
     gp.row_norms = l2 ? view.norms : nullptr;
     gp.q_norms = qn;
     gp.thr = thr;
@@ -259,8 +290,10 @@ int search_gemm_tier(mlv_index* h, const float* qprep, uint32_t nq, uint32_t k, 
         take = std::min(take, total_tiles - seen);
         gp.row_tile0 = seen;
         gp.row_tile1 = seen + take;
-        const uint64_t items = (uint64_t)take * gp.n_qtiles;
-        const int grid = (int)std::min<uint64_t>(items, (uint64_t)h->sm_count);
+        uint64_t items = (uint64_t)take * gp.n_qtiles;
+        if (wide_cl) items = (uint64_t)((take + 2 * wide_cl - 1) / (2 * wide_cl)) * gp.n_qtiles * wide_cl;   // CTAs that get an item
+        int grid = (int)std::min<uint64_t>(items, (uint64_t)h->sm_count);
+        if (wide_cl == 2) grid = std::max(2, grid & ~1);
         cudaEvent_t e0 = nullptr, e1 = nullptr;
         if (h->timing) {
             for (cudaEvent_t* ev : {&e0, &e1}) {
@@ -273,8 +306,11 @@ int search_gemm_tier(mlv_index* h, const float* qprep, uint32_t nq, uint32_t k, 
             }
             cudaEventRecord(e0, st);
         }
-        CK(h, l2 ? launch_gemm_t<METRIC_L2>(mx, mqh, mql, gp, grid, st, (int)GEMM_BN, passes)
-                 : launch_gemm_t<METRIC_IP>(mx, mqh, mql, gp, grid, st, (int)GEMM_BN, passes));
+        if (wide_cl)
+            CK(h, l2 ? launch_gemm2<METRIC_L2>(mx, mqh, gp, grid, st, passes, wide_cl) : launch_gemm2<METRIC_IP>(mx, mqh, gp, grid, st, passes, wide_cl));
+        else
+            CK(h, l2 ? launch_gemm_t<METRIC_L2>(mx, mqh, mql, gp, grid, st, (int)GEMM_BN, passes)
+                     : launch_gemm_t<METRIC_IP>(mx, mqh, mql, gp, grid, st, (int)GEMM_BN, passes));
         if (h->timing) {
             cudaEventRecord(e1, st);
             h->gemm_pending.emplace_back(e0, e1);
@@ -325,6 +361,7 @@ int search_gemm_tier(mlv_index* h, const float* qprep, uint32_t nq, uint32_t k, 
         // selected can be trusted; the shadow is rebuilt with a fresh scale by the next batch
         std::fill(hflags.begin(), hflags.end(), 2u);
         h->f16_valid = 0;
+        h->f16_overflowed = true;
     }
     return MLV_OK;
 }
@@ -450,7 +487,8 @@ int search_gemm(mlv_index* h, const float* qprep, uint32_t nq, uint32_t k, const
     if (fast) {
         h->gemm_fast_queries += nq - failing.size();
         if (first_tier == GEMM_TIER_F16) h->gemm_half_queries += nq - failing.size();
-        if (h->tune_gemm_passes == 0 && failing.size() * 2 > nq) h->gemm_fast_skip = 8;
+        if (h->tune_gemm_passes == 0 && failing.size() * 2 > nq && !h->f16_overflowed) h->gemm_fast_skip = 8;
+        h->f16_overflowed = false;   // an overflowed shadow says nothing about the data's neighbourhoods: no sitting out
         if (!failing.empty() && h->tune_gemm_passes != 1 && h->tune_gemm_passes != GEMM_TIER_F16) {
             // second tier on the compacted failing queries; results scattered back to their slots
             const uint32_t nf = (uint32_t)failing.size();

@@ -30,6 +30,7 @@ int choose_cfg(mlv_index* h, uint32_t nq, uint32_t k, bool range, ScanCfg* c, bo
     if (!range) {
         while (NQ < 8 && (uint32_t)NQ < nq) NQ <<= 1;
         while (NQ > 1 && ((size_t)NQ * lcap * CW * 8 > 65536 || R * NQ > 32)) NQ >>= 1;
+        if (NQ >= 4) CW = std::min(CW, SCAN_WIDE_CW);   // launch bounds of the wide instantiations (scan_max_threads)
     }
     const int max_stages = std::min(std::max(h->tune_max_stages, 2), 16);
     const size_t fixed = (size_t)NQ * rowbytes + (range ? 0 : (size_t)CW * NQ * lcap * 8) + (size_t)max_stages * 24 + 256;
@@ -301,7 +302,7 @@ bool fused_ok(const mlv_index* h, const ScanCfg& c, uint32_t k) {
     if (!h->tune_dynamic || !h->tune_fused) return false;
     return (uint64_t)c.grid * k <= SCAN_FUSED_MAX_KEYS;
 }
-size_t fused_scratch_bytes(const ScanCfg& c, uint32_t k) { return ((size_t)fused_cap(c, k) + (size_t)c.NQ * k) * 8; }
+size_t fused_scratch_bytes(const ScanCfg& c, uint32_t k) { return ((size_t)fused_cap(c, k) + (size_t)c.NQ * k + (size_t)c.grid) * 8; }
 
 // the exchange path must take the same decision on every rank, whatever its shard's grid is
 bool exchange_ok(const mlv_index* h, uint32_t k) {
@@ -354,6 +355,7 @@ struct FastArgs {
     unsigned int* done_flag = nullptr;
     unsigned int done_value = 0;
     bool* took_fast = nullptr;
+    uint4* tagged_out = nullptr;   // single GPU: tagged 16-byte result records instead of arrays + flag (scan_kernel.cuh)
 };
 
 int search_prepared(mlv_index* h, const float* qprep, uint32_t nq, uint32_t k, const uint32_t* filter_dev, float* out_d,
@@ -395,7 +397,8 @@ int search_prepared(mlv_index* h, const float* qprep, uint32_t nq, uint32_t k, c
     p.row_base = h->row_base;
     if (exchange) fill_exchange(h, p.xchg);
     if (h->tune_timeline) {
-        rc = ensure_dev(h, h->d_timeline, (size_t)c.grid * 4 * 8);
+        rc = ensure_dev(h, h->d_timeline, (size_t)c.grid * 16 * 8);
+        if (rc == MLV_OK) CK(h, cudaMemsetAsync(h->d_timeline.p, 0, (size_t)c.grid * 16 * 8, st));
         if (rc != MLV_OK) return rc;
         p.timeline = (unsigned long long*)h->d_timeline.p;
         h->last_grid = c.grid;
@@ -419,8 +422,10 @@ int search_prepared(mlv_index* h, const float* qprep, uint32_t nq, uint32_t k, c
                 p.queries = nullptr;
                 p.dim = h->dim;
                 p.normalize = h->metric == MLV_COSINE;
-                p.done_flag = fast->done_flag;
+                p.done_flag = fast->tagged_out && !exchange ? nullptr : fast->done_flag;
                 p.done_value = fast->done_value;
+                p.tagged_out = exchange ? nullptr : fast->tagged_out;
+                p.tag = fast->done_value;
                 CK(h, launch_scan_iq(h, p, iq, c, false, st));
                 continue;
             }

@@ -120,10 +120,13 @@ struct mlv_index {
     uint64_t norms_valid = 0;  // rows [0, norms_valid) of d_norms are current
     DevBuf d_rows16, d_f16st, d_gx16;  // fp16 shadow of the rows (HALF tier), its frozen scale / overflow flag, halves of a gathered copy
     uint64_t f16_valid = 0;    // rows [0, f16_valid) of the shadow are current
+    bool f16_overflowed = false;  // the last fp16-tier batch hit the overflow flag
     uint64_t gemm_half_queries = 0;  // queries certified by the fp16 tier
     int tune_gemm = -1;        // -1 auto, 0 never, 1 whenever the shape allows it
     int tune_gemm_min_nq = 0;  // 0 = auto (gemm_min_nq: 5 with the one-pass tier on a >= 1 GB matrix, else 9)
     int tune_gemm_bn = 0;      // queries per GEMM tile: 0 auto, or 64 / 128 / 256
+    int tune_gemm_debug = 0;   // profiling only: bit 0 = epilogue drains nothing (wrong results)
+    int tune_gemm_wide = 1;    // one-pass tiers of wide batches: 0 = single-tile kernel, 1 = two row tiles per query tile, 2 = + clusters of two CTAs
     int tune_gemm_passes = 0;  // 0 auto (fp16 shadow tier, then 3xTF32 for what it cannot certify), 1 one-pass TF32 tier then scan, 2 fp16 tier then scan, 3 3xTF32 only
     uint64_t gemm_fast_queries = 0;  // queries certified by the one-pass tier
     uint64_t gemm_gathered_searches = 0;  // filtered batches that multiplied a compacted copy of the passing rows

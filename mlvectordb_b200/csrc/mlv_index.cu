@@ -28,6 +28,28 @@
 
 using namespace mlv;
 
+// ---- NVTX ranges (tracing).  nvtx3 is header-only and binds to a profiler's injection library at
+// run time; with MLV_NVTX unset (default) a range is one branch on a cached flag.
+#include <nvtx3/nvToolsExt.h>
+namespace {
+struct NvtxRange {
+    bool on;
+    explicit NvtxRange(const char* name) : on(enabled()) {
+        if (on) nvtxRangePushA(name);
+    }
+    ~NvtxRange() {
+        if (on) nvtxRangePop();
+    }
+    static bool enabled() {
+        static const bool v = [] {
+            const char* s = getenv("MLV_NVTX");
+            return s && *s && *s != '0';
+        }();
+        return v;
+    }
+};
+}  // namespace
+
 #include "host_state.inl"
 #include "host_scan.inl"
 #include "host_gemm.inl"
@@ -89,6 +111,8 @@ int mlv_index_create(uint32_t dim, int metric, uint64_t capacity_hint, int devic
     h->tune_gemm_min_nq = env_int("MLV_GEMM_MIN_NQ", h->tune_gemm_min_nq);
     h->tune_gemm_bn = env_int("MLV_GEMM_BN", h->tune_gemm_bn);
     h->tune_gemm_passes = env_int("MLV_GEMM_PASSES", h->tune_gemm_passes);
+    h->tune_gemm_wide = env_int("MLV_GEMM_WIDE", h->tune_gemm_wide);
+    h->tune_gemm_debug = env_int("MLV_GEMM_DEBUG", h->tune_gemm_debug);
     DeviceGuard g(device);
     cudaDeviceProp prop;
     cudaError_t e = g.ok ? cudaGetDeviceProperties(&prop, device) : cudaErrorInvalidDevice;
@@ -180,6 +204,8 @@ int mlv_index_set_tuning(mlv_index_t h, const char* key, int value) {
     else if (k == "staged_upload") h->tune_staged_upload = value;
     else if (k == "gemm_passes") h->tune_gemm_passes = value;
     else if (k == "fast_host") h->tune_fast_host = value;
+    else if (k == "gemm_wide") h->tune_gemm_wide = value;
+    else if (k == "gemm_debug") h->tune_gemm_debug = value;
     else return fail(h, MLV_E_INVALID, "unknown tuning key " + k);
     return MLV_OK;
 }
@@ -233,6 +259,7 @@ static int upload_rows_staged(mlv_index_t h, float* dst, const float* rows, uint
 }
 
 static int add_common(mlv_index_t h, const float* rows, uint64_t n, uint64_t* first_row, cudaMemcpyKind kind, bool normalize = true) {
+    NvtxRange nvtx_range("mlv_index_add");
     if (!h || (!rows && n)) return MLV_E_INVALID;
     if (n == 0) {
         if (first_row) *first_row = h->rows;
@@ -265,6 +292,7 @@ int mlv_index_add_device(mlv_index_t h, const float* rows_dev, uint64_t n, uint6
 
 int mlv_index_add_synthetic(mlv_index_t h, uint64_t seed, uint64_t first_gen_row, uint64_t n, int scaled,
                             uint64_t* first_row) {
+    NvtxRange nvtx_range("mlv_index_add_synthetic");
     if (!h) return MLV_E_INVALID;
     if (n == 0) {
         if (first_row) *first_row = h->rows;
@@ -284,6 +312,7 @@ int mlv_index_add_synthetic(mlv_index_t h, uint64_t seed, uint64_t first_gen_row
 }
 
 int mlv_index_mark_deleted(mlv_index_t h, const uint64_t* rows, uint64_t n, uint64_t* newly_deleted) {
+    NvtxRange nvtx_range("mlv_index_mark_deleted");
     if (!h || (!rows && n)) return MLV_E_INVALID;
     if (newly_deleted) *newly_deleted = 0;
     if (n == 0 || h->rows == 0) return MLV_OK;
@@ -308,6 +337,7 @@ int mlv_index_mark_deleted(mlv_index_t h, const uint64_t* rows, uint64_t n, uint
 }
 
 int mlv_index_compact(mlv_index_t h, int64_t* old_to_new, uint64_t* new_rows) {
+    NvtxRange nvtx_range("mlv_index_compact");
     if (!h) return MLV_E_INVALID;
     DeviceGuard g(h->device);
     const uint64_t n = h->rows;
@@ -393,6 +423,7 @@ int mlv_index_clear(mlv_index_t h) {
 int mlv_index_search_device(mlv_index_t h, const float* queries_dev, uint32_t nq, uint32_t k,
                             const uint32_t* filter_bitmap_dev, float* out_dists_dev, int64_t* out_rows_dev,
                             int32_t* out_counts_dev, void* stream) {
+    NvtxRange nvtx_range("mlv_index_search_device");
     if (!h || !queries_dev || !out_dists_dev || !out_rows_dev || !out_counts_dev || nq == 0 || k == 0) return fail(h, MLV_E_INVALID, "bad argument");
     if (k > MLV_MAX_K) return fail(h, MLV_E_UNSUPPORTED, "k exceeds MLV_MAX_K");
     DeviceGuard g(h->device);
@@ -429,6 +460,7 @@ int mlv_filter_create(mlv_index_t h, const uint32_t* bitmap, uint64_t n_words, m
 }
 
 int mlv_filter_create_where(mlv_index_t h, const mlv_predicate_t* preds, uint32_t n_preds, mlv_filter_t* out) {
+    NvtxRange nvtx_range("mlv_filter_create_where");
     if (!h || !out || (!preds && n_preds)) return MLV_E_INVALID;
     *out = nullptr;
     if (n_preds > MLV_MAX_PREDICATES) return fail(h, MLV_E_UNSUPPORTED, "more than MLV_MAX_PREDICATES predicates");
@@ -713,6 +745,7 @@ int mlv_index_exchange_supported(mlv_index_t h, uint32_t k) {
 int mlv_index_search_exchange_device(mlv_index_t h, const float* queries_dev, uint32_t nq, uint32_t k,
                                      const uint32_t* filter_bitmap_dev, float* out_dists_dev, int64_t* out_rows_dev,
                                      int32_t* out_counts_dev, void* stream) {
+    NvtxRange nvtx_range("mlv_index_search_exchange_device");
     if (!h || !queries_dev || !out_dists_dev || !out_rows_dev || !out_counts_dev || nq == 0 || k == 0) return fail(h, MLV_E_INVALID, "bad argument");
     if (!exchange_ok(h, k)) return fail(h, MLV_E_UNSUPPORTED, "no connected exchange, or k too large for the fused exchange");
     DeviceGuard g(h->device);
@@ -742,6 +775,7 @@ int mlv_index_search_exchange_device(mlv_index_t h, const float* queries_dev, ui
 
 static int search_host_common(mlv_index_t h, const float* queries, uint32_t nq, uint32_t k, const uint32_t* filter_bitmap,
                               float* out_dists, int64_t* out_rows, int32_t* out_counts, bool exchange) {
+    NvtxRange nvtx_range("mlv_index_search");
     if (!h || !queries || !out_dists || !out_rows || !out_counts || nq == 0 || k == 0) return fail(h, MLV_E_INVALID, "bad argument");
     if (k > MLV_MAX_K) return fail(h, MLV_E_UNSUPPORTED, "k exceeds MLV_MAX_K");
     DeviceGuard g(h->device);
@@ -758,15 +792,46 @@ static int search_host_common(mlv_index_t h, const float* queries, uint32_t nq, 
         // stream synchronise for long scans) -- no H2D copy, no preparation launch, no D2H copy.
         char* hs = (char*)h->h_stage.p;
         unsigned int* flag = (unsigned int*)(hs + ((out_bytes + 63) & ~(size_t)63));
+        // single GPU: the results come as tagged 16-byte records at the start of the block (k records + a count record);
+        // an exchange search writes the three arrays and raises the flag behind a system fence
+        uint4* recs = (uint4*)hs;
+        const bool tagged = !exchange && (size_t)(k + 1) * 16 <= h->h_stage.bytes - 128;
         bool took = false;
         FastArgs fa;
         fa.inline_q = queries;
         fa.done_flag = flag;
         fa.done_value = ++h->flag_seq ? h->flag_seq : ++h->flag_seq;
         fa.took_fast = &took;
+        fa.tagged_out = tagged ? recs : nullptr;
         *(volatile unsigned int*)flag = 0;   // nothing of this handle is in flight on the block: every call waits for its own results
+        if (tagged) ((volatile unsigned int*)&recs[k])[1] = 0;
         rc = search_prepared(h, nullptr, 1, k, nullptr, (float*)(hs + nk * 8), (int64_t*)hs, (int32_t*)(hs + nk * 12), h->stream, exchange, &fa);
         if (rc != MLV_OK) return rc;
+        if (took && tagged) {
+            volatile unsigned int* vr = (volatile unsigned int*)recs;
+            const unsigned int tag = fa.done_value;
+            bool seen = false;
+            for (int spin = 0; spin < 200000 && !seen; spin++) seen = vr[4 * k + 1] == tag;   // ~100-200 us of polling
+            if (!seen) CK(h, cudaStreamSynchronize(h->stream));
+            std::atomic_thread_fence(std::memory_order_acquire);
+            const uint32_t count = std::min<uint32_t>((uint32_t)vr[4 * k], k);
+            for (uint32_t i = 0; i < k; i++) {
+                if (i < count) {
+                    // a record is complete once it carries the tag (one 16-byte store); after the stream synchronise all are
+                    for (int spin = 0; vr[4 * i + 1] != tag && spin < 100000000; spin++) {
+                    }
+                    std::atomic_thread_fence(std::memory_order_acquire);
+                    uint32_t bits = vr[4 * i];
+                    memcpy(&out_dists[i], &bits, 4);
+                    out_rows[i] = (int64_t)(((uint64_t)vr[4 * i + 3] << 32) | vr[4 * i + 2]);
+                } else {
+                    out_dists[i] = std::numeric_limits<float>::infinity();
+                    out_rows[i] = -1;
+                }
+            }
+            out_counts[0] = (int32_t)count;
+            return MLV_OK;
+        }
         if (took) {
             volatile unsigned int* vf = flag;
             bool seen = false;
@@ -821,6 +886,7 @@ int mlv_index_search_exchange(mlv_index_t h, const float* queries, uint32_t nq, 
 }
 
 int mlv_index_submit(mlv_index_t h, const float* queries, uint32_t nq, uint32_t k, int exchange, uint32_t* ticket) {
+    NvtxRange nvtx_range("mlv_index_submit");
     if (!h || !queries || !ticket || nq == 0 || k == 0) return fail(h, MLV_E_INVALID, "bad argument");
     if (k > MLV_MAX_K) return fail(h, MLV_E_UNSUPPORTED, "k exceeds MLV_MAX_K");
     DeviceGuard g(h->device);
@@ -873,6 +939,7 @@ int mlv_index_submit(mlv_index_t h, const float* queries, uint32_t nq, uint32_t 
 }
 
 int mlv_index_collect(mlv_index_t h, uint32_t ticket, float* out_dists, int64_t* out_rows, int32_t* out_counts) {
+    NvtxRange nvtx_range("mlv_index_collect");
     if (!h || ticket >= (uint32_t)MLV_ASYNC_SLOTS || !out_dists || !out_rows || !out_counts) return fail(h, MLV_E_INVALID, "bad argument");
     AsyncSlot& sl = h->slots[ticket];
     if (!sl.busy) return fail(h, MLV_E_INVALID, "no search in flight under this ticket");
@@ -890,6 +957,7 @@ int mlv_index_collect(mlv_index_t h, uint32_t ticket, float* out_dists, int64_t*
 int mlv_index_range_search_device(mlv_index_t h, const float* queries_dev, uint32_t nq, float radius,
                                   const uint32_t* filter_bitmap_dev, uint64_t max_hits, float* out_dists_dev,
                                   int64_t* out_rows_dev, uint64_t* out_counts_dev, void* stream) {
+    NvtxRange nvtx_range("mlv_index_range_search_device");
     if (!h || !queries_dev || !out_counts_dev || nq == 0 || (max_hits && (!out_dists_dev || !out_rows_dev))) return fail(h, MLV_E_INVALID, "bad argument");
     DeviceGuard g(h->device);
     cudaStream_t st = (cudaStream_t)stream;
@@ -931,6 +999,7 @@ int mlv_index_range_search_device(mlv_index_t h, const float* queries_dev, uint3
 
 int mlv_index_range_search(mlv_index_t h, const float* queries, uint32_t nq, float radius, const uint32_t* filter_bitmap,
                            uint64_t max_hits, float* out_dists, int64_t* out_rows, uint64_t* out_counts) {
+    NvtxRange nvtx_range("mlv_index_range_search");
     if (!h || !queries || !out_counts || nq == 0 || (max_hits && (!out_dists || !out_rows))) return fail(h, MLV_E_INVALID, "bad argument");
     DeviceGuard g(h->device);
     for (uint32_t q = 0; q < nq; q++) out_counts[q] = 0;
@@ -983,6 +1052,7 @@ int mlv_index_range_exchange_supported(mlv_index_t h) {
 int mlv_index_range_search_exchange_device(mlv_index_t h, const float* queries_dev, uint32_t nq, float radius,
                                            const uint32_t* filter_bitmap_dev, float* out_dists_dev, int64_t* out_rows_dev,
                                            uint64_t* out_counts_dev, void* stream) {
+    NvtxRange nvtx_range("mlv_index_range_search_exchange_device");
     if (!h || !queries_dev || !out_dists_dev || !out_rows_dev || !out_counts_dev || nq == 0) return fail(h, MLV_E_INVALID, "bad argument");
     if (!mlv_index_range_exchange_supported(h)) return fail(h, MLV_E_UNSUPPORTED, "no connected exchange");
     DeviceGuard g(h->device);
@@ -1224,17 +1294,30 @@ int mlv_index_debug_gemm(mlv_index_t h, const float* queries, uint32_t nq, float
     float* thr = qn + nq_pad;
     uint32_t* cnt = (uint32_t*)(thr + nq_pad);
     uint32_t* flags = cnt + nq_pad;
-    split_queries_kernel<<<(nq_pad + 7) / 8, 256, 0, st>>>((const float*)lane_for(h, st)->d_q.p, qhi, qlo, qn, thr, cnt, flags, nq, nq_pad, ld);
+    const int passes = h->tune_gemm_passes == 1 ? 1 : (h->tune_gemm_passes == GEMM_TIER_F16 ? GEMM_TIER_F16 : 3);   // which tier's distances
+    const bool half = passes == GEMM_TIER_F16;
+    const uint32_t ld16 = f16_ld(h);
+    if (half) {
+        bool usable = false;
+        if ((rc = ensure_f16_shadow(h, st, &usable)) != MLV_OK) return rc;
+        if (!usable) return fail(h, MLV_E_NOMEM, "no room for the fp16 shadow");
+        split_queries_f16_kernel<<<(nq_pad + 7) / 8, 256, 0, st>>>((const float*)lane_for(h, st)->d_q.p, (__half*)qhi, qlo, qn, thr, cnt, flags, nq,
+                                                                  nq_pad, ld, ld16);
+    } else {
+        split_queries_kernel<<<(nq_pad + 7) / 8, 256, 0, st>>>((const float*)lane_for(h, st)->d_q.p, qhi, qlo, qn, thr, cnt, flags, nq, nq_pad, ld);
+    }
     CK(h, cudaGetLastError());
     CUtensorMap mx, mqh, mql;
-    if ((rc = make_tile_map(h, &mx, h->d_rows, h->rows, GEMM_BM)) != MLV_OK) return rc;
-    if ((rc = make_tile_map(h, &mqh, qhi, nq_pad, GEMM_BN)) != MLV_OK) return rc;
-    if ((rc = make_tile_map(h, &mql, qlo, nq_pad, GEMM_BN)) != MLV_OK) return rc;
+    if ((rc = make_tile_map(h, &mx, half ? h->d_rows16.p : (const void*)h->d_rows, h->rows, GEMM_BM, half)) != MLV_OK) return rc;
+    if ((rc = make_tile_map(h, &mqh, qhi, nq_pad, GEMM_BN, half)) != MLV_OK) return rc;
+    if ((rc = make_tile_map(h, &mql, half ? qhi : qlo, nq_pad, GEMM_BN, half)) != MLV_OK) return rc;
     GemmParams gp{};
     gp.n_rows = (uint32_t)h->rows;
     gp.nq = nq;
     gp.n_qtiles = nq_pad / GEMM_BN;
-    gp.n_kchunks = (ld + GEMM_BK - 1) / GEMM_BK;
+    gp.n_kchunks = half ? (ld16 + 2 * GEMM_BK - 1) / (2 * GEMM_BK) : (ld + GEMM_BK - 1) / GEMM_BK;
+    gp.x_unscale = (const float*)h->d_f16st.p;
+    gp.q_unscale = qlo;
     gp.row_norms = h->metric == MLV_L2 ? (const float*)h->d_norms.p : nullptr;
     gp.q_norms = qn;
     gp.thr = thr;
@@ -1245,7 +1328,6 @@ int mlv_index_debug_gemm(mlv_index_t h, const float* queries, uint32_t nq, float
     gp.row_tile0 = 0;
     gp.row_tile1 = (uint32_t)((h->rows + GEMM_BM - 1) / GEMM_BM);
     const int grid = (int)std::min<uint64_t>((uint64_t)gp.row_tile1 * gp.n_qtiles, (uint64_t)h->sm_count);
-    const int passes = h->tune_gemm_passes == 1 ? 1 : 3;   // set_tuning("gemm_passes", 1): the one-pass tier's distances
     CK(h, h->metric == MLV_L2 ? launch_gemm_t<METRIC_L2>(mx, mqh, mql, gp, grid, st, (int)GEMM_BN, passes)
                               : launch_gemm_t<METRIC_IP>(mx, mqh, mql, gp, grid, st, (int)GEMM_BN, passes));
     h->launches += 3;
@@ -1270,7 +1352,7 @@ int mlv_index_debug_timeline(mlv_index_t h, uint64_t* out, uint32_t max_ctas, ui
     *n_ctas = n;
     if (n == 0 || !h->d_timeline.p) return MLV_OK;
     CK(h, cudaDeviceSynchronize());
-    CK(h, cudaMemcpy(out, h->d_timeline.p, (size_t)n * 4 * 8, cudaMemcpyDeviceToHost));
+    CK(h, cudaMemcpy(out, h->d_timeline.p, (size_t)n * 16 * 8, cudaMemcpyDeviceToHost));
     return MLV_OK;
 }
 

@@ -28,6 +28,14 @@ constexpr int METRIC_IP = 1;  // cosine == ip over rows/queries normalised at ad
 constexpr int SCAN_MAX_CW = 16;                          // consumer warps per CTA (runtime, <= this)
 constexpr int SCAN_MAX_PW = 4;                           // producer warps (1 unless gathering short rows)
 constexpr int SCAN_MAX_THREADS = (SCAN_MAX_CW + SCAN_MAX_PW) * 32;  // 640 -> ptxas may use up to 102 registers
+// 4 and 8 queries per pass hold R * NQ accumulators + NQ query float4s per lane: 102 registers spilled (r01: 44 - 116
+// bytes per thread).  Those instantiations run at most 8 consumer warps (each does 4 - 8x the math per row byte, so
+// half the warps still cover the shared-memory latency) and may use 170 registers.
+constexpr int SCAN_WIDE_CW = 8;
+template <int NQ>
+constexpr int scan_max_threads() {
+    return NQ >= 4 ? (SCAN_WIDE_CW + SCAN_MAX_PW) * 32 : SCAN_MAX_THREADS;
+}
 
 constexpr uint32_t SCAN_FUSED_MAX_KEYS = 8192;  // keys the last CTA folds (gridDim.x * k): k <= 55 on 148 SMs
 
@@ -89,6 +97,12 @@ struct ScanParams {
     // so the host can poll instead of synchronising the stream
     unsigned int* done_flag;
     unsigned int done_value;
+    // Tagged result records in mapped pinned host memory (nullptr = off; single GPU, one query): record i < k is
+    // {distance bits, tag, row low, row high}, record k is {count, tag, 0, 0}, each ONE 16-byte store.  A record is
+    // valid for the host as soon as it carries this launch's tag, so no system fence and no flag are needed (the
+    // fence + flag cost 4 us of a 27 us launch on a 10k-row namespace).
+    uint4* tagged_out;
+    unsigned int tag;
 };
 
 constexpr uint32_t SCAN_INLINE_MAX_DIM = 2048;   // floats of a query carried in the kernel parameters (8 KB)
@@ -189,6 +203,20 @@ __device__ __forceinline__ void warp_sort_list(uint64_t* list, uint32_t n, uint3
     __syncwarp();
 }
 
+// 32 keys, one per lane -> ascending across the lanes (bitonic network over shuffles)
+__device__ __forceinline__ uint64_t warp_bitonic_sort_u64(uint64_t v, int lane) {
+#pragma unroll
+    for (int size = 2; size <= 32; size <<= 1) {
+#pragma unroll
+        for (int stride = size >> 1; stride > 0; stride >>= 1) {
+            const uint64_t o = shfl_u64(v, lane ^ stride);
+            const bool keep_min = ((lane & size) == 0) == ((lane & stride) == 0);
+            v = (keep_min == (o < v)) ? o : v;
+        }
+    }
+    return v;
+}
+
 // number of keys of the ascending list[0..k) that are < key (strict) or <= key (!strict)
 __device__ __forceinline__ uint32_t sorted_count_below(const uint64_t* list, uint32_t k, uint64_t key, bool strict) {
     uint32_t lo = 0, hi = k;
@@ -266,7 +294,7 @@ __device__ __forceinline__ void scan_body(const ScanParams& p, const float* iq) 
         }
     }
     __syncthreads();
-    if (p.timeline && tid == 0) p.timeline[blockIdx.x * 4 + 0] = global_timer_ns();
+    if (p.timeline && tid == 0) p.timeline[blockIdx.x * 16 + 0] = global_timer_ns();
 
     if (warp >= CW) {
         // ------------------------------------------------------------------ producer(s)
@@ -373,7 +401,7 @@ __device__ __forceinline__ void scan_body(const ScanParams& p, const float* iq) 
             continue;
         }
         mbar_wait(&full[stage], phase);
-        if (p.timeline && tid == 0 && seq == 0) p.timeline[blockIdx.x * 4 + 1] = global_timer_ns();
+        if (p.timeline && tid == 0 && seq == 0) p.timeline[blockIdx.x * 16 + 1] = global_timer_ns();
         const int n = meta[stage].n_rows;
         if (n < 0) {
             finished |= 1u << owner;
@@ -470,7 +498,7 @@ __device__ __forceinline__ void scan_body(const ScanParams& p, const float* iq) 
         if (++rot == (uint32_t)CW) rot = 0;
         advance();
     }
-    if (p.timeline && tid == 0) p.timeline[blockIdx.x * 4 + 2] = global_timer_ns();
+    if (p.timeline && tid == 0) p.timeline[blockIdx.x * 16 + 2] = global_timer_ns();
     const uint32_t nthr = (uint32_t)CW * 32u;  // consumer threads (the producer warps have left)
     if (!RANGE) {
         // --------------------------------------------- fold the CW warp lists into one per query
@@ -481,37 +509,85 @@ __device__ __forceinline__ void scan_body(const ScanParams& p, const float* iq) 
                 const uint32_t n = __shfl_sync(0xffffffffu, cnt, __ffs(owners) - 1);
                 warp_sort_list(my_lists + (size_t)qi * lcap, n, lcap, lane);
             }
+        } else {
+            // k <= 32 unsorted keys per list: one key per lane, sorted in registers (a rank-by-counting fold over
+            // CW * k unsorted keys cost 7 us of a 12 us launch on a 10k-row namespace; the merge below costs < 1 us)
+            __syncwarp();
+            for (uint32_t qi = 0; qi < (uint32_t)NQ && qi < p.nq_valid; qi++) {
+                uint64_t* l = my_lists + (size_t)qi * lcap;
+                uint64_t v = (uint32_t)lane < k ? l[lane] : KEY_SENTINEL;
+                v = warp_bitonic_sort_u64(v, lane);
+                if ((uint32_t)lane < k) l[lane] = v;
+            }
         }
+        if (p.timeline && tid == 0) p.timeline[blockIdx.x * 16 + 8] = global_timer_ns();    // own lists sorted
         named_bar_sync(1, CW * 32);
+        if (p.timeline && tid == 0) p.timeline[blockIdx.x * 16 + 9] = global_timer_ns();    // every warp's lists sorted
         const uint32_t n_in = (uint32_t)CW * k;
+        __shared__ uint32_t s_fm;
+        __shared__ unsigned long long s_fT;
         for (uint32_t qi = 0; qi < p.nq_valid; qi++) {
             uint64_t* out = p.out_keys + ((size_t)qi * gridDim.x + blockIdx.x) * k;
+            if (buffered) {
+                for (uint32_t e = tid; e < n_in; e += nthr) {
+                    const uint32_t w = e / k, j = e - w * k;
+                    const uint64_t key = lists[((size_t)w * NQ + qi) * lcap + j];
+                    // CW ascending lists: rank = own position + keys below it in the other lists (binary
+                    // search); equal keys (sentinels only) are ordered by list, then position
+                    uint32_t rank = j;
+                    for (uint32_t w2 = 0; w2 < (uint32_t)CW; w2++)
+                        if (w2 != w) rank += sorted_count_below(lists + ((size_t)w2 * NQ + qi) * lcap, k, key, w2 > w);
+                    if (rank < k) out[rank] = key;  // the block's k best, ascending
+                }
+                continue;
+            }
+            // k <= 32, every warp list ascending.  The first ceil(k / CW) keys of each list are >= k keys, so the k-th
+            // smallest of that small pool bounds the block's k-th best: only keys <= it survive (about k of CW * k), and
+            // ranking the survivors is O(k^2) instead of O((CW k)^2).  Scratch: the ring, idle since the barrier above.
+            uint64_t* pool = reinterpret_cast<uint64_t*>(ring);   // [<= 64] pool, then [CW * k] survivors
+            uint64_t* surv = pool + 64;
+            const uint32_t take = (k + (uint32_t)CW - 1) / (uint32_t)CW;
+            const uint32_t P = min((uint32_t)CW * take, 64u);
+            if (tid < P) {
+                const uint32_t w = tid / take, j = tid - w * take;
+                pool[tid] = lists[((size_t)w * NQ + qi) * lcap + j];
+            }
+            if (tid == 0) s_fm = 0;
+            named_bar_sync(1, CW * 32);
+            if (tid < P) {
+                const uint64_t key = pool[tid];
+                uint32_t rank = 0;
+#pragma unroll 8
+                for (uint32_t i = 0; i < P; i++) {
+                    const uint64_t o = pool[i];
+                    rank += (o < key) || (o == key && i < tid);
+                }
+                if (rank == min(k, P) - 1) s_fT = key;
+            }
+            named_bar_sync(1, CW * 32);
+            const uint64_t T = s_fT;
             for (uint32_t e = tid; e < n_in; e += nthr) {
                 const uint32_t w = e / k, j = e - w * k;
                 const uint64_t key = lists[((size_t)w * NQ + qi) * lcap + j];
-                uint32_t rank;
-                if (buffered) {
-                    // CW ascending lists: rank = own position + keys below it in the other lists (binary
-                    // search); equal keys (sentinels only) are ordered by list, then position
-                    rank = j;
-                    for (uint32_t w2 = 0; w2 < (uint32_t)CW; w2++)
-                        if (w2 != w) rank += sorted_count_below(lists + ((size_t)w2 * NQ + qi) * lcap, k, key, w2 > w);
-                } else {
-                    // unsorted lists of k <= 32 keys: rank by counting
-                    rank = 0;
-                    for (uint32_t w2 = 0; w2 < (uint32_t)CW; w2++) {
-                        const uint64_t* l2 = lists + ((size_t)w2 * NQ + qi) * lcap;
-                        for (uint32_t j2 = 0; j2 < k; j2++) {
-                            const uint64_t o = l2[j2];
-                            rank += (o < key) || (o == key && (w2 * k + j2) < e);
-                        }
-                    }
+                if (key <= T && key != KEY_SENTINEL) surv[atomicAdd(&s_fm, 1u)] = key;
+            }
+            named_bar_sync(1, CW * 32);
+            const uint32_t m = s_fm;
+            for (uint32_t e = tid; e < m; e += nthr) {
+                const uint64_t key = surv[e];
+                uint32_t rank = 0;
+#pragma unroll 8
+                for (uint32_t i = 0; i < m; i++) {
+                    const uint64_t o = surv[i];
+                    rank += (o < key) || (o == key && i < e);
                 }
                 if (rank < k) out[rank] = key;  // the block's k best, ascending
             }
+            for (uint32_t r = m + tid; r < k; r += nthr) out[r] = KEY_SENTINEL;   // fewer than k rows seen
+            named_bar_sync(1, CW * 32);   // pool / surv are reused by the next query
         }
     }
-    if (p.timeline && tid == 0) p.timeline[blockIdx.x * 4 + 3] = global_timer_ns();
+    if (p.timeline && tid == 0) p.timeline[blockIdx.x * 16 + 3] = global_timer_ns();
     if (!p.sched) return;
 
     // ------------------------------------------------- last CTA: scheduler reset, fused final select
@@ -525,8 +601,10 @@ __device__ __forceinline__ void scan_body(const ScanParams& p, const float* iq) 
         s_ticket = atomicAdd(p.sched + 1, 1u);
     }
     named_bar_sync(1, CW * 32);
+    if (p.timeline && tid == 0) p.timeline[blockIdx.x * 16 + 4] = global_timer_ns();   // ticket taken
     if (s_ticket != gridDim.x - 1) return;
     __threadfence();
+    if (p.timeline && tid == 0) p.timeline[blockIdx.x * 16 + 10] = global_timer_ns();       // last CTA: past the fence
     if (!RANGE && p.fused) {
         // The ring is idle now: reuse it.  cand[fused_cap] | top[nq_valid][k]
         uint64_t* cand = reinterpret_cast<uint64_t*>(ring);
@@ -541,20 +619,50 @@ __device__ __forceinline__ void scan_body(const ScanParams& p, const float* iq) 
             named_bar_sync(1, CW * 32);
             // every block list is sorted, so its last key is its maximum; the global k-th best is at
             // most the smallest of those maxima: only keys <= T can be in the final top-k
-            for (uint32_t l = tid; l < n_lists; l += nthr) atomicMin(&s_T, (unsigned long long)__ldcg(keys + (size_t)l * k + k - 1));
+            // (148 threads doing a 64-bit atomicMin on one shared word is a CAS loop that cost ~5 us: reduce in the warp first)
+            {
+                uint64_t mine = KEY_SENTINEL;
+                for (uint32_t l = tid; l < n_lists; l += nthr) {
+                    const uint64_t v = __ldcg(keys + (size_t)l * k + k - 1);
+                    mine = v < mine ? v : mine;
+                }
+                mine = ~warp_max_u64(~mine);
+                if (lane == 0 && mine != KEY_SENTINEL) atomicMin(&s_T, (unsigned long long)mine);
+            }
+            // A much tighter bound when there are at least k lists: the k-th smallest of the lists' FIRST keys (k keys are
+            // <= it, so the global k-th best is too).  On 148 lists of 10 it leaves ~k survivors instead of ~250, whose
+            // O(m^2) ranking cost 7 us.  heads[] sits behind the candidate array.
+            if (n_lists >= k && n_lists <= nthr) {
+                uint64_t* heads = top + (size_t)p.nq_valid * k;
+                if (tid < n_lists) heads[tid] = __ldcg(keys + (size_t)tid * k);
+                named_bar_sync(1, CW * 32);
+                if (tid < n_lists) {
+                    const uint64_t key = heads[tid];
+                    uint32_t rank = 0;
+#pragma unroll 8
+                    for (uint32_t i = 0; i < n_lists; i++) {
+                        const uint64_t o = heads[i];
+                        rank += (o < key) || (o == key && i < tid);
+                    }
+                    if (rank == k - 1 && key != KEY_SENTINEL) atomicMin(&s_T, (unsigned long long)key);
+                }
+            }
             named_bar_sync(1, CW * 32);
+            if (p.timeline && tid == 0) p.timeline[blockIdx.x * 16 + 11] = global_timer_ns();   // threshold known
             const uint64_t T = s_T;
             for (uint32_t i = tid; i < n; i += nthr) {
                 const uint64_t key = __ldcg(keys + i);
                 if (key <= T) cand[atomicAdd(&s_m, 1u)] = key;
             }
             named_bar_sync(1, CW * 32);
+            if (p.timeline && tid == 0) p.timeline[blockIdx.x * 16 + 12] = global_timer_ns();   // survivors gathered
             const uint32_t m = s_m;
             if (m <= 512) {
                 // few survivors: rank by counting
                 for (uint32_t e = tid; e < m; e += nthr) {
                     const uint64_t key = cand[e];
                     uint32_t rank = 0;
+#pragma unroll 8
                     for (uint32_t i = 0; i < m; i++) {
                         const uint64_t o = cand[i];
                         rank += (o < key) || (o == key && i < e);
@@ -587,8 +695,25 @@ __device__ __forceinline__ void scan_body(const ScanParams& p, const float* iq) 
                 named_bar_sync(1, CW * 32);
             }
         }
+        if (p.timeline && tid == 0) p.timeline[blockIdx.x * 16 + 5] = global_timer_ns();   // last CTA: final select done
         const ExchangeView& x = p.xchg;
-        if (x.world <= 1) {
+        if (x.world <= 1 && p.tagged_out) {
+            for (uint32_t i = tid; i <= k; i += nthr) {
+                uint4 rec;
+                if (i < k) {
+                    const uint64_t key = top[i];
+                    const bool valid = key != KEY_SENTINEL;
+                    const unsigned long long row = valid ? (unsigned long long)(p.row_base + key_row(key)) : ~0ull;
+                    rec = make_uint4(valid ? __float_as_uint(key_dist(key)) : 0x7f800000u, p.tag, (uint32_t)row, (uint32_t)(row >> 32));
+                } else {
+                    uint32_t c = 0;
+                    for (uint32_t j = 0; j < k; j++) c += top[j] != KEY_SENTINEL;
+                    rec = make_uint4(c, p.tag, 0u, 0u);
+                }
+                asm volatile("st.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p.tagged_out + i), "r"(rec.x), "r"(rec.y), "r"(rec.z), "r"(rec.w)
+                             : "memory");
+            }
+        } else if (x.world <= 1) {
             for (uint32_t i = tid; i < p.nq_valid * k; i += nthr) {
                 const uint64_t key = top[i];
                 const bool valid = key != KEY_SENTINEL;
@@ -615,10 +740,12 @@ __device__ __forceinline__ void scan_body(const ScanParams& p, const float* iq) 
         named_bar_sync(1, CW * 32);
         range_exchange_and_merge(p.xchg, a, n_local, found, p.out_dists, p.out_rows, p.range_out_count, tid, nthr, s_rcnt);
     }
+    if (p.timeline && tid == 0) p.timeline[blockIdx.x * 16 + 6] = global_timer_ns();       // last CTA: outputs written
     if (p.done_flag) {   // results (possibly in mapped host memory) before the flag
         __threadfence_system();
         named_bar_sync(1, CW * 32);
         if (tid == 0) asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p.done_flag), "r"(p.done_value) : "memory");
+        if (p.timeline && tid == 0) p.timeline[blockIdx.x * 16 + 7] = global_timer_ns();   // flag raised
     }
     if (tid == 0) {
         p.sched[0] = 0;
@@ -627,7 +754,7 @@ __device__ __forceinline__ void scan_body(const ScanParams& p, const float* iq) 
 }
 
 template <int METRIC, int NQ, int R, bool RANGE>
-__global__ void __launch_bounds__(SCAN_MAX_THREADS, 1) scan_kernel(const ScanParams p) {
+__global__ void __launch_bounds__(scan_max_threads<NQ>(), 1) scan_kernel(const ScanParams p) {
     scan_body<METRIC, NQ, R, RANGE, false>(p, nullptr);
 }
 // one query whose raw values travel in the launch parameters (batch-1 latency path)

@@ -288,16 +288,26 @@ class GpuIndex:
             results.append(SearchResult(vector_id=ns.uuid_of(row), score=score))
         return results
 
-    def search_async(self, query: VectorDTO, top_k: int, namespace: str, metric: str) -> "PendingResults":
+    def search_async(self, query: VectorDTO, top_k: int, namespace: str, metric: str,
+                     filter: FilterArg = None) -> "PendingResults":
         """``search`` that returns at once; ``.result()`` gives the ``List[SearchResult]``.  A server that keeps
-        two requests in flight overlaps one request's copies / launch latency with the other's scan."""
+        two requests in flight overlaps one request's copies / launch latency with the other's scan.
+        ``filter``: metadata constraints or a prepared filter (row masks / callables: prepare them first with
+        ``prepare_filter`` -- the submit must not wait for a host-side evaluation); it stays bound to this search only."""
         ns = self._ns.get(namespace)
         active = (ns.total - ns.deleted) if ns is not None else 0
         k = min(int(top_k), active)
         q = np.asarray(query.values, dtype=np.float32).reshape(-1)
         if ns is None or k < 1 or q.shape[0] != ns.dim:
             return PendingResults(None, None, metric)
-        return PendingResults(ns.shard.submit(q[None, :], k), ns, metric)
+        prepared = self._filter_mask(ns, filter)
+        if prepared is not None and not isinstance(prepared, PreparedFilter):
+            prepared = ns.shard.prepare_filter(prepared)
+            ns.where_cache[("async", id(prepared))] = prepared   # kept alive until the namespace changes
+        from .shard import _bound
+        with _bound(ns.shard, prepared):      # the launch captures the filter's row list; the binding ends with the submit
+            pending = ns.shard.submit(q[None, :], k)
+        return PendingResults(pending, ns, metric)
 
     def rebuild(self, source: Mapping[str, Iterable[VectorProtocol]], metric: str) -> None:
         """reference index.py:131-162: drop everything, re-add ``source`` with ``space=metric``."""

@@ -327,8 +327,10 @@ class DeviceShard:
         self._ck(self._lib.mlv_index_set_tuning(self._h, key.encode(), int(value)))
 
     def debug_timeline(self, max_ctas: int = 1024) -> np.ndarray:
-        """[n_ctas, 4] globaltimer ns stamps of the last scan (needs set_tuning('timeline', 1))."""
-        out = np.zeros((max_ctas, 4), dtype=np.uint64)
+        """[n_ctas, 16] globaltimer ns stamps of the last scan (needs set_tuning('timeline', 1)): 0 start, 1 first tile,
+        2 last tile consumed, 3 lists folded, 4 ticket taken, for the last CTA 5 final select / 6 outputs / 7 flag, and finer
+        ones: 8 own lists sorted, 9 all lists sorted, last CTA 10 past the fence / 11 threshold / 12 survivors (0 = not taken)."""
+        out = np.zeros((max_ctas, 16), dtype=np.uint64)
         n = C.c_uint32()
         self._ck(self._lib.mlv_index_debug_timeline(self._h, out.ctypes.data_as(C.POINTER(C.c_uint64)), max_ctas, C.byref(n)))
         return out[: n.value]

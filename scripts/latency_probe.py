@@ -77,15 +77,25 @@ ms, n = shard.scan_time_ms()
 shard.set_timing(False)
 print(json.dumps({"scan_kernel_us_events": round(ms / n * 1e3, 2), "launches": n}), flush=True)
 shard.set_tuning("timeline", 1)
-for i in range(3):
-    shard.search(Q[i][None, :], a.k)
+for fast in (0, 1, 1):
+    shard.set_tuning("fast_host", fast)
+    shard.search(Q[5][None, :], a.k)
     t = shard.debug_timeline().astype(np.int64)
-    rel = (t - t[:, 0].min()) / 1e3
-    print(json.dumps({"ctas": int(t.shape[0]),
-                      "start_us[min,med,max]": [round(float(x), 1) for x in (rel[:, 0].min(), np.median(rel[:, 0]), rel[:, 0].max())],
-                      "first_tile_us[min,med,max]": [round(float(x), 1) for x in (rel[:, 1].min(), np.median(rel[:, 1]), rel[:, 1].max())],
-                      "last_tile_done_us[min,med,max]": [round(float(x), 1) for x in (rel[:, 2].min(), np.median(rel[:, 2]), rel[:, 2].max())],
-                      "exit_us[min,med,max]": [round(float(x), 1) for x in (rel[:, 3].min(), np.median(rel[:, 3]), rel[:, 3].max())]}), flush=True)
+    t0 = t[:, 0].min()
+    rel = np.where(t > 0, (t - t0) / 1e3, np.nan)
+    last = int(np.argmax(t[:, 5]))          # only the last CTA (ticket grid-1) stamps the final select
+    names = ["start", "first_tile", "last_tile_done", "folded", "ticket"]
+    out = {"fast_host": fast, "ctas": int(t.shape[0])}
+    for i, nm in enumerate(names):
+        out[nm + "_us[min,med,max]"] = [round(float(x), 2) for x in (np.nanmin(rel[:, i]), np.nanmedian(rel[:, i]), np.nanmax(rel[:, i]))]
+    out["last_cta_us[ticket,select_done,outputs,flag]"] = [round(float(x), 2) for x in rel[last, 4:8]]
+    out["last_cta_us[last_tile,own_sorted,all_sorted,folded,ticket,fence,threshold,survivors,select_done]"] = [
+        round(float(rel[last, i]), 2) for i in (2, 8, 9, 3, 4, 10, 11, 12, 5)]
+    print(json.dumps(out), flush=True)
+shard.set_tuning("timeline", 0)
+import subprocess  # noqa: E402
+print(json.dumps({"clocks": subprocess.run(["nvidia-smi", "--query-gpu=clocks.sm,clocks.max.sm,clocks.mem,power.draw", "--format=csv,noheader"],
+                                           capture_output=True, text=True).stdout.strip()}), flush=True)
 # reference points: an empty launch + sync, and a flag-poll round trip, through torch
 import torch  # noqa: E402
 

@@ -20,13 +20,13 @@ def _shard(dim, space, **kw):
 
 
 def _both_paths(s, Q, k, filt=None, stats=None):
-    """Scan path vs tensor-core path in every tier configuration: 3xTF32 only, one-pass tier + scan, and the
-    default (one-pass tier, 3xTF32 for what it cannot certify, scan for the rest).  Returns the default's results
-    and its scan fallbacks; ``stats`` (dict) receives the default's counter deltas."""
+    """Scan path vs tensor-core path in every tier configuration: 3xTF32 only, one-pass TF32 tier + scan, fp16-shadow
+    tier + scan, and the default (fp16-shadow tier, 3xTF32 for what it cannot certify, scan for the rest).  Returns the
+    default's results and its scan fallbacks; ``stats`` (dict) receives the default's counter deltas."""
     s.set_tuning("gemm", 0)
     ref = s.search(Q, k, filt)
     s.set_tuning("gemm", 1)
-    for passes in (3, 1, 0):
+    for passes in (3, 1, 2, 0):
         s.set_tuning("gemm_passes", passes)
         before = s.gemm_stats()
         got = s.search(Q, k, filt)
@@ -34,7 +34,9 @@ def _both_paths(s, Q, k, filt=None, stats=None):
         assert after["searches"] == before["searches"] + 1, "the batch did not take the tensor-core path"
         fallbacks = after["fallback_queries"] - before["fallback_queries"]
         fast = after["fast_queries"] - before["fast_queries"]
+        half = after["half_queries"] - before["half_queries"]
         assert fast == 0 if passes == 3 else fast <= len(Q)
+        assert half == (fast if passes in (0, 2) else 0), f"gemm_passes={passes}: {half} of {fast} first-tier queries on the fp16 shadow"
         for a, b, name in zip(got, ref, ("dists", "rows", "counts")):
             assert a.dtype == b.dtype and a.shape == b.shape
             assert np.array_equal(a, b, equal_nan=True), f"{name}: tensor-core path (gemm_passes={passes}) differs from the scan path"
@@ -253,7 +255,7 @@ def test_filtered_batch_multiplies_a_compacted_copy_of_the_passing_rows(space):
             before = s.gemm_stats()["gathered_searches"]
             got, _ = _both_paths(s, Q, k, filt)
             after = s.gemm_stats()["gathered_searches"]
-            assert (after - before == 3) == gathered, (cut, after - before)     # one per tier configuration
+            assert (after - before == 4) == gathered, (cut, after - before)     # one per tier configuration
             assert got[1][0, 0] == np.flatnonzero(mask & live)[77] and mask[got[1]].all() and live[got[1]].all()
         _assert_oracle((got[0][:4], got[1][:4], got[2][:4]), X, Q[:4], k, space, allow=mask & live)
         pf.close()
@@ -302,3 +304,120 @@ def test_one_pass_distances_stay_inside_the_certificate_bound(space):
         else:
             assert rel.max() < 0.1 * bound
         s.close()
+
+
+@pytest.mark.parametrize("space", ["l2", "ip"])
+def test_fp16_tier_distances_stay_inside_the_certificate_bound(space):
+    """The fp16-shadow tier rounds both operands to 11 significant bits (scaled by exact powers of two):
+    |a - exact| <= delta_rel * scale with delta_rel = 2^-10 (1 + 2^-12) + d 2^-22 (ip; half on the l2 scale).  Worst case
+    for round-to-nearest: every value just below a half step and all products of one sign; data spread over many
+    binades and data with huge / tiny magnitudes (the scales keep the halves in range) stay inside as well."""
+    n, dim, nq = 2048, 768, 64
+    rng = np.random.default_rng(3)
+    step = 2.0 ** -10
+    worst = lambda shape: ((1.0 + rng.integers(0, 1024, shape) * step + 0.5 * step * (1 - 2.0 ** -12))
+                           * 2.0 ** rng.integers(-2, 3, shape)).astype(np.float32)
+    benign = (synthetic.rows(4, 0, n, dim, scaled=True), synthetic.queries(4, nq, dim))
+    cases = [(worst((n, dim)), worst((nq, dim)), True),
+             (benign[0], benign[1], False),
+             (benign[0] * np.float32(3.0e6), benign[1] * np.float32(2.0e-7), False),       # far outside fp16's own range
+             (benign[0] * (2.0 ** rng.integers(-12, 1, (n, 1))).astype(np.float32), benign[1], False)]   # rows over 12 binades
+    for X, Q, expect_close in cases:
+        s = _shard(dim, space)
+        s.add(X)
+        s.set_tuning("gemm_passes", 2)
+        A = s.debug_gemm(Q)
+        X64, Q64 = X.astype(np.float64), Q.astype(np.float64)
+        dots = Q64 @ X64.T
+        xn, qn = np.sqrt((X64 ** 2).sum(1)), np.sqrt((Q64 ** 2).sum(1))
+        e = 2.0 ** -10 * (1 + 2.0 ** -12) + dim * 2.0 ** -22
+        if space == "l2":
+            true = (qn ** 2)[:, None] + (xn ** 2)[None, :] - 2 * dots
+            scale = (xn.max() + qn[:, None]) ** 2 * np.ones_like(dots)
+            bound = 0.5 * e
+        else:
+            true = 1 - dots
+            scale = xn.max() * qn[:, None] * np.ones_like(dots)
+            bound = e
+        rel = np.abs(A - true) / scale
+        assert not np.isnan(A).any() and np.isfinite(A).all()
+        assert rel.max() < bound, f"{space}: {rel.max():.3e} exceeds the certificate's delta {bound:.3e}"
+        if expect_close:
+            assert rel.max() > 0.2 * bound, f"worst-case input only reached {rel.max():.3e} of {bound:.3e}"
+        s.close()
+
+
+def test_fp16_shadow_follows_adds_deletes_compaction_and_rescales():
+    """The shadow is built lazily and must follow the matrix: appended rows are converted with the frozen scale, rows far
+    larger than anything seen when it was frozen overflow -> the batch is answered by the next tiers and the shadow is
+    rebuilt; compaction invalidates it.  Results stay bit-identical to the scan throughout."""
+    n, dim, nq, k = 20_000, 96, 40, 10
+    X = synthetic.rows(33, 0, n, dim, scaled=True)
+    Q = synthetic.queries(33, nq, dim)
+    s = _shard(dim, "l2")
+    s.add(X[: n // 2])
+
+    def check(expect_half=None):
+        s.set_tuning("gemm", 0)
+        ref = s.search(Q, k)
+        s.set_tuning("gemm", 1)
+        before = s.gemm_stats()
+        got = s.search(Q, k)
+        after = s.gemm_stats()
+        assert all(np.array_equal(a, b, equal_nan=True) for a, b in zip(got, ref))
+        half = after["half_queries"] - before["half_queries"]
+        if expect_half is not None:
+            assert (half > nq // 2) == expect_half, half
+        return got
+
+    check(True)
+    s.add(X[n // 2:])                                   # appended rows: converted incrementally
+    got = check(True)
+    _assert_oracle((got[0][:4], got[1][:4], got[2][:4]), X, Q[:4], k, "l2")
+    s.mark_deleted(got[1][:, 0])                        # the nearest row of every query goes away
+    check(True)
+    s.compact()
+    check(True)
+    first_big = s.rows
+    big = X[:50] * np.float32(1.0e4)                    # 2^13 x the frozen scale's headroom: fp16 overflow
+    s.add(big)
+    check(False)                                        # this batch: overflow flag -> 3xTF32 tier / scan
+    # (with those outliers in the matrix no one-pass tier can certify: its error bound is relative to the largest row)
+    s.mark_deleted(np.arange(first_big, first_big + 50))
+    s.compact()                                         # norms, largest norm and shadow are rebuilt: fresh scale
+    check(True)
+    s.close()
+
+
+@pytest.mark.parametrize("space", ["l2", "cosine"])
+def test_wide_kernel_and_cluster_multicast_equal_the_single_tile_kernel(space):
+    """Wide batches (>= 129 queries) run the one-pass tiers on gemm_topk2_kernel: two row tiles per staged query tile
+    (gemm_wide 1) and, with gemm_wide 2, clusters of two CTAs sharing the query tile through TMA multicast.  Odd row-tile
+    counts, a ragged K (dim % 64 != 0), two query tiles, tombstones: every variant returns the scan's bits."""
+    n, dim, nq, k = 60_050, 200, 300, 10
+    X = synthetic.rows(51, 0, n, dim, scaled=True)
+    Q = synthetic.queries(51, nq, dim)
+    Q[7] = X[n - 1]
+    s = _shard(dim, space)
+    s.add(X)
+    s.mark_deleted(np.arange(3, n, 11))
+    s.set_tuning("gemm", 0)
+    ref = s.search(Q, k)
+    s.set_tuning("gemm", 1)
+    for wide in (0, 1, 2):
+        s.set_tuning("gemm_wide", wide)
+        for passes in (2, 1, 0):
+            s.set_tuning("gemm_passes", passes)
+            before = s.gemm_stats()
+            got = s.search(Q, k)
+            after = s.gemm_stats()
+            assert after["searches"] == before["searches"] + 1
+            assert after["fast_queries"] - before["fast_queries"] >= nq * 9 // 10, (wide, passes)
+            for a, b, name in zip(got, ref, ("dists", "rows", "counts")):
+                assert np.array_equal(a, b, equal_nan=True), f"{name}: gemm_wide={wide} gemm_passes={passes} differs from the scan"
+    live = np.ones(n, bool)
+    live[3::11] = False
+    _assert_oracle((ref[0][:4], ref[1][:4], ref[2][:4]), X, Q[:4], k, space, allow=live)
+    if space != "cosine":
+        assert ref[1][7, 0] == n - 1 or not live[n - 1]
+    s.close()
