@@ -214,52 +214,52 @@ __device__ __forceinline__ void epilogue_constants(const GemmParams& p, uint32_t
 template <int METRIC, bool F16, int BN>
 __device__ __forceinline__ void epilogue_drain(const GemmParams& p, uint32_t taddr0, uint32_t qt, uint32_t row, bool row_ok, float xn,
                                                const float* thr_s, const float* qn_s, const float* us_s, const float* c1_s,
-                                               const float* c2_s) {
+                                               const float* c2_s, uint32_t c_begin = 0, uint32_t c_end = BN / 32) {
     const float nxn = -xn;
+    // A value that passes the relaxed pre-test is examined with the exact test right there (a branch that is almost
+    // never taken costs one issue slot); re-scanning the whole 32-column chunk after any hit cost more than the fast path
+    // itself: with thresholds that only tighten between rounds, ~20 % of the warp-chunks hold a hit.
+    auto hit = [&](float vj, uint32_t ql) {
+        const float dot = F16 ? vj * us_s[ql] : vj;
+        const float a = (METRIC == METRIC_L2) ? fmaf(-2.0f, dot, xn + qn_s[ql]) : 1.0f - dot;
+        if (a <= thr_s[ql]) {
+            const uint32_t qg = qt * BN + ql;
+            const uint32_t pos = atomicAdd(p.cand_cnt + qg, 1u);
+            if (pos < p.cap) p.cand[(size_t)qg * p.cap + pos] = make_key(a, row);
+        }
+    };
     auto process = [&](const uint32_t(&v)[32], uint32_t c) {
         if (!row_ok) return;
         const float4* k1 = reinterpret_cast<const float4*>(c1_s + c * 32);
         const float4* k2 = reinterpret_cast<const float4*>(c2_s + c * 32);
-        bool any = false;
 #pragma unroll
         for (int j4 = 0; j4 < 8; j4++) {
             const float4 a1 = k1[j4];
             const float v0 = __uint_as_float(v[4 * j4]), v1 = __uint_as_float(v[4 * j4 + 1]);
             const float v2 = __uint_as_float(v[4 * j4 + 2]), v3 = __uint_as_float(v[4 * j4 + 3]);
+            const uint32_t ql = c * 32 + 4 * j4;
             if (METRIC == METRIC_L2) {
                 const float4 a2 = k2[j4];
-                any |= fmaf(nxn, a2.x, v0) >= a1.x;
-                any |= fmaf(nxn, a2.y, v1) >= a1.y;
-                any |= fmaf(nxn, a2.z, v2) >= a1.z;
-                any |= fmaf(nxn, a2.w, v3) >= a1.w;
+                if (fmaf(nxn, a2.x, v0) >= a1.x) hit(v0, ql);
+                if (fmaf(nxn, a2.y, v1) >= a1.y) hit(v1, ql + 1);
+                if (fmaf(nxn, a2.z, v2) >= a1.z) hit(v2, ql + 2);
+                if (fmaf(nxn, a2.w, v3) >= a1.w) hit(v3, ql + 3);
             } else {
-                any |= v0 >= a1.x;
-                any |= v1 >= a1.y;
-                any |= v2 >= a1.z;
-                any |= v3 >= a1.w;
-            }
-        }
-        if (!any) return;
-#pragma unroll
-        for (int j = 0; j < 32; j++) {   // fully unrolled: v[] must stay in registers
-            const uint32_t ql = c * 32 + j;
-            const float dot = F16 ? __uint_as_float(v[j]) * us_s[ql] : __uint_as_float(v[j]);
-            const float a = (METRIC == METRIC_L2) ? fmaf(-2.0f, dot, xn + qn_s[ql]) : 1.0f - dot;
-            if (a <= thr_s[ql]) {
-                const uint32_t qg = qt * BN + ql;
-                const uint32_t pos = atomicAdd(p.cand_cnt + qg, 1u);
-                if (pos < p.cap) p.cand[(size_t)qg * p.cap + pos] = make_key(a, row);
+                if (v0 >= a1.x) hit(v0, ql);
+                if (v1 >= a1.y) hit(v1, ql + 1);
+                if (v2 >= a1.z) hit(v2, ql + 2);
+                if (v3 >= a1.w) hit(v3, ql + 3);
             }
         }
     };
     uint32_t va[32], vb[32];
-    tmem_ld32_issue(taddr0, va);
-    for (uint32_t c = 0; c < BN / 32; c += 2) {   // BN / 32 is even
+    tmem_ld32_issue(taddr0 + c_begin * 32, va);
+    for (uint32_t c = c_begin; c < c_end; c += 2) {   // an even number of 32-column chunks
         tmem_ld_wait(va);
         tmem_ld32_issue(taddr0 + (c + 1) * 32, vb);
         process(va, c);
         tmem_ld_wait(vb);
-        if (c + 2 < BN / 32) tmem_ld32_issue(taddr0 + (c + 2) * 32, va);
+        if (c + 2 < c_end) tmem_ld32_issue(taddr0 + (c + 2) * 32, va);
         process(vb, c + 1);
     }
 }
@@ -470,8 +470,12 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
 // multicast into both CTAs' shared memory: (256 + 128) rows per 256 x 256 products, half of the single-tile kernel's.
 // The accumulators are not double-buffered any more; instead two groups of four epilogue warps drain them side by side,
 // and with the cheap pre-test (epilogue_drain) that drain is ~1/5 of the tile's tensor time.
-// PASSES is 1 (TF32 on the fp32 rows) or GEMM_TIER_F16 (fp16 shadow); BN is 256.  320 threads:
-//   warp 0 TMA producer | warp 1 MMA issuer | warps 2-5 drain accumulator 0 | warps 6-9 drain accumulator 1
+// PASSES is 1 (TF32 on the fp32 rows) or GEMM_TIER_F16 (fp16 shadow); BN is 256.  576 threads:
+//   warp 0 TMA producer | warp 1 MMA issuer | warps 2-9 drain accumulator 0 | warps 10-17 drain accumulator 1
+// (a warp may only read the TMEM lanes 32 * (warp % 4) ..: the two warps of a group that share a lane quarter split the
+// 256 columns in halves.  With the MMAs and loads alone the kernel runs at 96 % of the bf16 tensor peak -- the drain is
+// what is left to hide, and it is latency-bound, so more warps shorten it.)
+constexpr int GEMM2_THREADS = 64 + 16 * 32;
 constexpr int GEMM2_BN = 256;
 constexpr int GEMM2_STAGES = 3;
 constexpr uint32_t GEMM2_Q_BYTES = GEMM2_BN * GEMM_BK * 4;                    // 32 KB
@@ -500,7 +504,7 @@ __device__ __forceinline__ uint32_t cluster_ctarank() {
 }
 
 template <int METRIC, int PASSES, int CL>
-__global__ void __launch_bounds__(GEMM_THREADS, 1)
+__global__ void __launch_bounds__(GEMM2_THREADS, 1)
 gemm_topk2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_q, const GemmParams p) {
     static_assert(PASSES == 1 || PASSES == GEMM_TIER_F16, "one-pass tiers only");
     static_assert(CL == 1 || CL == 2, "cluster of one or two CTAs");
@@ -534,8 +538,8 @@ gemm_topk2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
             mbar_init(&empty[s], CL);
         }
         mbar_init(tfull, 1);
-        mbar_init(&tempty[0], 4);
-        mbar_init(&tempty[1], 4);
+        mbar_init(&tempty[0], 8);
+        mbar_init(&tempty[1], 8);
         mbar_fence_init();
         tma_prefetch_desc(&tm_x);
         tma_prefetch_desc(&tm_q);
@@ -622,15 +626,16 @@ gemm_topk2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
             }
         }
     } else {
-        // ------------------------------------------------------------------ epilogue: group 0 = warps 2-5, group 1 = warps 6-9
-        const int et = tid - 64;            // 0..255
-        const uint32_t grp_e = (uint32_t)(warp - 2) >> 2;
+        // ------------------------------------------------------------------ epilogue: group 0 = warps 2-9, group 1 = warps 10-17
+        const int et = tid - 64;            // 0..511
+        const uint32_t grp_e = (uint32_t)(warp - 2) >> 3;
+        const uint32_t half = ((uint32_t)(warp - 2) >> 2) & 1u;   // which 128 of the accumulator's 256 columns
         const uint32_t quarter = warp & 3;  // TMEM lanes this warp may read: 32*quarter .. +31
         uint32_t local = 0;
         for (uint32_t it = cluster_id; it < n_items; it += n_clusters, local++) {
             const uint32_t grp = it / p.n_qtiles, qt = it % p.n_qtiles;
             const uint32_t tile = p.row_tile0 + (grp * CL + crank) * 2 + grp_e;
-            named_bar_sync(2, 256);  // everyone finished reading the constants of the previous item
+            named_bar_sync(2, 512);  // everyone finished reading the constants of the previous item
             if (et < 128) epilogue_constants<METRIC, F16, GEMM2_BN>(p, qt, et, thr_s, qn_s, us_s, c1_s, c2_s);
             const uint32_t row = tile * GEMM_BM + quarter * 32 + lane;
             bool row_ok = tile < p.row_tile1 && row < p.n_rows && !(p.debug & 1);   // a group's last tiles may belong to the next round
@@ -640,11 +645,12 @@ gemm_topk2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
                 if (row_ok && p.filter) row_ok = (__ldg(p.filter + (row >> 5)) >> (row & 31)) & 1u;
                 if (METRIC == METRIC_L2 && row_ok) xn = __ldg(p.row_norms + row);
             }
-            named_bar_sync(2, 256);
+            named_bar_sync(2, 512);
             mbar_wait(tfull, local & 1);
             tc_fence_after();
             const uint32_t taddr0 = tmem_base + ((quarter * 32u) << 16) + grp_e * GEMM2_BN;
-            epilogue_drain<METRIC, F16, GEMM2_BN>(p, taddr0, qt, row, row_ok, xn, thr_s, qn_s, us_s, c1_s, c2_s);
+            epilogue_drain<METRIC, F16, GEMM2_BN>(p, taddr0, qt, row, row_ok, xn, thr_s, qn_s, us_s, c1_s, c2_s, half * (GEMM2_BN / 64),
+                                                  (half + 1) * (GEMM2_BN / 64));
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&tempty[grp_e]);

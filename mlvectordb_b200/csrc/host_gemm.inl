@@ -137,7 +137,7 @@ cudaError_t launch_gemm2_t(const CUtensorMap& mx, const CUtensorMap& mq, const G
     if (e != cudaSuccess) return e;
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3((unsigned)grid);
-    cfg.blockDim = dim3(GEMM_THREADS);
+    cfg.blockDim = dim3(GEMM2_THREADS);
     cfg.dynamicSmemBytes = GEMM2_SMEM_BYTES;
     cfg.stream = st;
     cudaLaunchAttribute attr[1];

@@ -302,7 +302,7 @@ bool fused_ok(const mlv_index* h, const ScanCfg& c, uint32_t k) {
     if (!h->tune_dynamic || !h->tune_fused) return false;
     return (uint64_t)c.grid * k <= SCAN_FUSED_MAX_KEYS;
 }
-size_t fused_scratch_bytes(const ScanCfg& c, uint32_t k) { return ((size_t)fused_cap(c, k) + (size_t)c.NQ * k + (size_t)c.grid) * 8; }
+size_t fused_scratch_bytes(const ScanCfg& c, uint32_t k) { return ((size_t)fused_cap(c, k) + (size_t)c.NQ * k) * 8; }
 
 // the exchange path must take the same decision on every rank, whatever its shard's grid is
 bool exchange_ok(const mlv_index* h, uint32_t k) {

@@ -72,7 +72,34 @@ double run(const char* name, int grid, int threads, size_t smem, bool poll, int 
     return total / reps;
 }
 
+// SM clock actually seen by a short kernel launched in a tight host loop: clock64 ticks per globaltimer ns
+__global__ void clock_probe(unsigned long long* out) {
+    unsigned long long t0, t1;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t0));
+    const long long c0 = clock64();
+    while (clock64() - c0 < 20000) {
+    }
+    const long long c1 = clock64();
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t1));
+    out[0] = (unsigned long long)(c1 - c0);
+    out[1] = t1 - t0;
+}
+
 int main() {
+    {
+        unsigned long long* d;
+        cudaMalloc(&d, 16);
+        unsigned long long h[2] = {0, 0};
+        double mhz_first = 0, mhz_last = 0;
+        for (int i = 0; i < 2000; i++) {
+            clock_probe<<<1, 1>>>(d);
+            cudaMemcpy(h, d, 16, cudaMemcpyDeviceToHost);
+            const double mhz = h[1] ? (double)h[0] / (double)h[1] * 1e3 : 0;
+            if (i == 0) mhz_first = mhz;
+            mhz_last = mhz;
+        }
+        printf("{\"probe\": \"SM clock seen by short kernels (clock64 / globaltimer)\", \"first_launch_mhz\": %.0f, \"after_2000_launches_mhz\": %.0f}\n", mhz_first, mhz_last);
+    }
     run<Small>("1 CTA, small params", 1, 32, 0, true);
     run<Small>("1 CTA, small params", 1, 32, 0, false);
     run<Small>("148 CTAs x 640 thr, no smem", 148, 640, 0, true);
