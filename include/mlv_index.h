@@ -374,7 +374,11 @@ int mlv_index_debug_timeline(mlv_index_t h, uint64_t *out, uint32_t max_ctas, ui
  * takes its place), then the 3xTF32 GEMM for the queries the first tier could not certify; what neither
  * certifies is re-run by the exact scan, so results do not depend on the path.  set_tuning keys: "gemm"
  * (-1 auto, 0 never, 1 whenever the shape allows), "gemm_min_nq", "gemm_passes" (0 auto, 1 one-pass TF32 tier
- * then scan, 2 fp16 tier then scan, 3 3xTF32 tier only).  This call returns cumulative counters
+ * then scan, 2 fp16 tier then scan, 3 3xTF32 tier only), "gemm_wide" (which kernel runs the one-pass tiers of
+ * batches wider than 128 queries: 3 = CTA pairs, tcgen05 cta_group::2 (default); 1 = two row tiles per staged
+ * query tile; 2 = the same in clusters of two with the query tile by TMA multicast; 0 = the single-tile kernel),
+ * "gemm_debug" (profiling only: bit 0 = the epilogue compares nothing -- results are wrong; bit 1 = hits bypass
+ * the per-warp queue).  Results never depend on "gemm_wide" / "gemm_passes".  This call returns cumulative counters
  * and, when timing is enabled, the summed device time of the GEMM launches since the last call.
  */
 typedef struct mlv_gemm_stats {

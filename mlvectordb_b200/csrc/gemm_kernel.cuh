@@ -57,13 +57,25 @@ constexpr uint32_t GEMM_X_BYTES = GEMM_BM * GEMM_BK * 4;   // 16 KB
 // TF32, rounded to nearest instead of truncated, so its approximate distances are TWICE as tight as PASSES = 1's; its
 // 5-bit exponent is dealt with by power-of-two scales (one per matrix, one per query) that the epilogue divides out
 // exactly.  A K chunk is 64 halves (one 128-byte swizzle row), tiles are the same 16 KB / BN * 128 B.
+// per-warp queue of candidate hits (see hitq_flush below)
+constexpr uint32_t HITQ_CAP = 64;
+struct HitQueue {            // one per epilogue warp
+    uint64_t key[HITQ_CAP];
+    uint32_t q[HITQ_CAP];
+    uint32_t count;
+    uint32_t cap;            // the candidate buffers (copied from GemmParams so the out-of-line hit path needs no kernel parameters)
+    uint64_t* cand;
+    uint32_t* cand_cnt;
+    int direct;              // profiling (gemm_debug bit 1): append straight to the buffers, no queue
+    uint32_t pad[9];
+};
 constexpr int GEMM_TIER_F16 = 2;
 template <int BN, int PASSES = 3>
 struct GemmShape {
     static constexpr uint32_t Q_BYTES = BN * GEMM_BK * 4;
     static constexpr uint32_t STAGE_BYTES = PASSES == 3 ? 2 * GEMM_X_BYTES + 2 * Q_BYTES : GEMM_X_BYTES + Q_BYTES;
     static constexpr int STAGES = PASSES == 3 ? (BN == 256 ? 2 : (BN == 128 ? 3 : 4)) : (BN == 256 ? 4 : 6);
-    static constexpr uint32_t SMEM_BYTES = 1024 + STAGES * STAGE_BYTES + 5 * BN * 4 + 256;
+    static constexpr uint32_t SMEM_BYTES = 1024 + STAGES * STAGE_BYTES + 5 * BN * 4 + 256 + 4 * sizeof(HitQueue);
     // fp32 accumulate, A and B K-major, M = 128, N = BN; operand format TF32 (kind::tf32) or F16 (kind::f16)
     static constexpr uint32_t FMT = PASSES == GEMM_TIER_F16 ? 0u : 2u;
     static constexpr uint32_t IDESC = (1u << 4) | (FMT << 7) | (FMT << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(GEMM_BM >> 4) << 24);
@@ -211,46 +223,82 @@ __device__ __forceinline__ void epilogue_constants(const GemmParams& p, uint32_t
 
 // One thread = one row (TMEM lane) of a 128 x BN accumulator at taddr0: BN values, 32 per tcgen05.ld, two register
 // buffers so the load of chunk c + 1 is in flight while chunk c is tested.
+// Hits are queued per warp in shared memory and appended to the queries' candidate buffers 32 at a time: an append needs
+// the value its global atomicAdd returns, and waiting ~1000 cycles for that once per hit -- with thresholds that only tighten
+// between rounds about one value in a thousand is a hit, i.e. one per 32 x 32 chunk -- made the drain 2-3x longer than the
+// tile's MMAs.  One stall per 32 hits instead.
+__device__ __forceinline__ void hitq_flush(const GemmParams& p, HitQueue* hq, int lane) {
+    __syncwarp();
+    const uint32_t n = min(hq->count, HITQ_CAP);
+    for (uint32_t i = (uint32_t)lane; i < n; i += 32) {
+        const uint32_t qg = hq->q[i];
+        const uint32_t pos = atomicAdd(p.cand_cnt + qg, 1u);
+        if (pos < p.cap) p.cand[(size_t)qg * p.cap + pos] = hq->key[i];
+    }
+    __syncwarp();
+    if (lane == 0) hq->count = 0;
+    __syncwarp();
+}
+
+template <int METRIC, bool F16>
+__device__ __noinline__ void gemm_hit(HitQueue* hq, const float* thr_s, const float* qn_s, const float* us_s, float vj, uint32_t ql, float xn,
+                                      uint32_t row, uint32_t qbase) {
+    const float dot = F16 ? vj * us_s[ql] : vj;
+    const float a = (METRIC == METRIC_L2) ? fmaf(-2.0f, dot, xn + qn_s[ql]) : 1.0f - dot;
+    if (!(a <= thr_s[ql])) return;
+    const uint32_t qg = qbase + ql;
+    if (!hq->direct) {
+        const uint32_t slot = atomicAdd(&hq->count, 1u);
+        if (slot < HITQ_CAP) {
+            hq->key[slot] = make_key(a, row);
+            hq->q[slot] = qg;
+            return;
+        }
+    }
+    // queue full (a burst: the first round has no thresholds yet): straight to the buffer
+    const uint32_t pos = atomicAdd(hq->cand_cnt + qg, 1u);
+    if (pos < hq->cap) hq->cand[(size_t)qg * hq->cap + pos] = make_key(a, row);
+}
+
 template <int METRIC, bool F16, int BN>
 __device__ __forceinline__ void epilogue_drain(const GemmParams& p, uint32_t taddr0, uint32_t qt, uint32_t row, bool row_ok, float xn,
                                                const float* thr_s, const float* qn_s, const float* us_s, const float* c1_s,
-                                               const float* c2_s, uint32_t c_begin = 0, uint32_t c_end = BN / 32) {
+                                               const float* c2_s, HitQueue* hq, uint32_t c_begin = 0, uint32_t c_end = BN / 32) {
+    const int lane = threadIdx.x & 31;
     const float nxn = -xn;
-    // A value that passes the relaxed pre-test is examined with the exact test right there (a branch that is almost
-    // never taken costs one issue slot); re-scanning the whole 32-column chunk after any hit cost more than the fast path
-    // itself: with thresholds that only tighten between rounds, ~20 % of the warp-chunks hold a hit.
-    auto hit = [&](float vj, uint32_t ql) {
-        const float dot = F16 ? vj * us_s[ql] : vj;
-        const float a = (METRIC == METRIC_L2) ? fmaf(-2.0f, dot, xn + qn_s[ql]) : 1.0f - dot;
-        if (a <= thr_s[ql]) {
-            const uint32_t qg = qt * BN + ql;
-            const uint32_t pos = atomicAdd(p.cand_cnt + qg, 1u);
-            if (pos < p.cap) p.cand[(size_t)qg * p.cap + pos] = make_key(a, row);
-        }
-    };
+    // A value that passes the relaxed pre-test is examined with the exact test by gemm_hit -- OUT OF LINE: 64 inlined copies
+    // of the hit path made the drain loop several times larger than the instruction cache likes, and the rarely taken
+    // code slowed the always-taken code down.
+    auto hit = [&](float vj, uint32_t ql) { gemm_hit<METRIC, F16>(hq, thr_s, qn_s, us_s, vj, ql, xn, row, qt * BN); };
     auto process = [&](const uint32_t(&v)[32], uint32_t c) {
         if (!row_ok) return;
         const float4* k1 = reinterpret_cast<const float4*>(c1_s + c * 32);
         const float4* k2 = reinterpret_cast<const float4*>(c2_s + c * 32);
+        // branch-free pre-test: one bit per column (a compare and a predicated OR per value); the chunk's hits -- none in
+        // most chunks of most lanes -- are then walked bit by bit
+        uint32_t m = 0;
 #pragma unroll
         for (int j4 = 0; j4 < 8; j4++) {
             const float4 a1 = k1[j4];
             const float v0 = __uint_as_float(v[4 * j4]), v1 = __uint_as_float(v[4 * j4 + 1]);
             const float v2 = __uint_as_float(v[4 * j4 + 2]), v3 = __uint_as_float(v[4 * j4 + 3]);
-            const uint32_t ql = c * 32 + 4 * j4;
             if (METRIC == METRIC_L2) {
                 const float4 a2 = k2[j4];
-                if (fmaf(nxn, a2.x, v0) >= a1.x) hit(v0, ql);
-                if (fmaf(nxn, a2.y, v1) >= a1.y) hit(v1, ql + 1);
-                if (fmaf(nxn, a2.z, v2) >= a1.z) hit(v2, ql + 2);
-                if (fmaf(nxn, a2.w, v3) >= a1.w) hit(v3, ql + 3);
+                m |= fmaf(nxn, a2.x, v0) >= a1.x ? 1u << (4 * j4) : 0u;
+                m |= fmaf(nxn, a2.y, v1) >= a1.y ? 2u << (4 * j4) : 0u;
+                m |= fmaf(nxn, a2.z, v2) >= a1.z ? 4u << (4 * j4) : 0u;
+                m |= fmaf(nxn, a2.w, v3) >= a1.w ? 8u << (4 * j4) : 0u;
             } else {
-                if (v0 >= a1.x) hit(v0, ql);
-                if (v1 >= a1.y) hit(v1, ql + 1);
-                if (v2 >= a1.z) hit(v2, ql + 2);
-                if (v3 >= a1.w) hit(v3, ql + 3);
+                m |= v0 >= a1.x ? 1u << (4 * j4) : 0u;
+                m |= v1 >= a1.y ? 2u << (4 * j4) : 0u;
+                m |= v2 >= a1.z ? 4u << (4 * j4) : 0u;
+                m |= v3 >= a1.w ? 8u << (4 * j4) : 0u;
             }
         }
+        if (m == 0) return;
+#pragma unroll
+        for (int j = 0; j < 32; j++)   // fully unrolled: v[] must stay in registers
+            if (m & (1u << j)) hit(__uint_as_float(v[j]), c * 32 + j);
     };
     uint32_t va[32], vb[32];
     tmem_ld32_issue(taddr0 + c_begin * 32, va);
@@ -261,7 +309,11 @@ __device__ __forceinline__ void epilogue_drain(const GemmParams& p, uint32_t tad
         tmem_ld_wait(vb);
         if (c + 2 < c_end) tmem_ld32_issue(taddr0 + (c + 2) * 32, va);
         process(vb, c + 1);
+        __syncwarp();
+        if (hq->count >= 32) hitq_flush(p, hq, lane);   // warp-uniform: every lane reads the same word after the syncwarp
     }
+    __syncwarp();
+    if (hq->count) hitq_flush(p, hq, lane);
 }
 
 // ---- the GEMM + candidate-selection kernel ---------------------------------------------------
@@ -292,6 +344,7 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
     uint64_t* tfull = bars + 3 * GEMM_STAGES;   // [2]  accumulator complete
     uint64_t* tempty = tfull + 2;               // [2]  accumulator drained
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+    HitQueue* hqs = reinterpret_cast<HitQueue*>(reinterpret_cast<unsigned char*>(bars) + 256);   // [4] one per epilogue warp
 
     const int tid = threadIdx.x;
     const int warp = tid >> 5;
@@ -428,6 +481,15 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
         // ------------------------------------------------------------------ epilogue
         const int et = tid - 192;        // 0..127
         const uint32_t quarter = warp & 3;  // TMEM lanes this warp may read: 32*quarter .. +31
+        HitQueue* hq = hqs + (warp - 6);
+        if (lane == 0) {
+            hq->count = 0;
+            hq->cap = p.cap;
+            hq->cand = p.cand;
+            hq->cand_cnt = p.cand_cnt;
+            hq->direct = (p.debug >> 1) & 1;
+        }
+        __syncwarp();
         uint32_t local = 0;
         for (uint32_t it = blockIdx.x; it < n_items; it += gridDim.x, local++) {
             const uint32_t rt = p.row_tile0 + it / p.n_qtiles, qt = it % p.n_qtiles;
@@ -446,7 +508,7 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
             mbar_wait(&tfull[acc], acc_phase);
             tc_fence_after();
             const uint32_t taddr0 = tmem_base + ((quarter * 32u) << 16) + acc * GEMM_BN;
-            epilogue_drain<METRIC, F16, GEMM_BN>(p, taddr0, qt, row, row_ok, xn, thr_s, qn_s, us_s, c1_s, c2_s);
+            epilogue_drain<METRIC, F16, GEMM_BN>(p, taddr0, qt, row, row_ok, xn, thr_s, qn_s, us_s, c1_s, c2_s, hq);
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&tempty[acc]);
@@ -480,7 +542,7 @@ constexpr int GEMM2_BN = 256;
 constexpr int GEMM2_STAGES = 3;
 constexpr uint32_t GEMM2_Q_BYTES = GEMM2_BN * GEMM_BK * 4;                    // 32 KB
 constexpr uint32_t GEMM2_STAGE_BYTES = 2 * GEMM_X_BYTES + GEMM2_Q_BYTES;      // X0 | X1 | Q = 64 KB
-constexpr uint32_t GEMM2_SMEM_BYTES = 1024 + GEMM2_STAGES * GEMM2_STAGE_BYTES + 5 * GEMM2_BN * 4 + 256;
+constexpr uint32_t GEMM2_SMEM_BYTES = 1024 + GEMM2_STAGES * GEMM2_STAGE_BYTES + 5 * GEMM2_BN * 4 + 256 + 16 * sizeof(HitQueue);
 
 __device__ __forceinline__ void tma_load_2d_mc(void* smem_dst, const CUtensorMap* map, int32_t c0, int32_t c1, uint64_t* bar, uint16_t mask) {
     asm volatile(
@@ -525,6 +587,7 @@ gemm_topk2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
     uint64_t* tfull = bars + 2 * GEMM2_STAGES;   // [1]  both accumulators complete
     uint64_t* tempty = tfull + 1;                // [2]  accumulator a drained (4 warps each)
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+    HitQueue* hqs = reinterpret_cast<HitQueue*>(reinterpret_cast<unsigned char*>(bars) + 256);   // [16] one per epilogue warp
 
     const int tid = threadIdx.x;
     const int warp = tid >> 5;
@@ -631,6 +694,15 @@ gemm_topk2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
         const uint32_t grp_e = (uint32_t)(warp - 2) >> 3;
         const uint32_t half = ((uint32_t)(warp - 2) >> 2) & 1u;   // which 128 of the accumulator's 256 columns
         const uint32_t quarter = warp & 3;  // TMEM lanes this warp may read: 32*quarter .. +31
+        HitQueue* hq = hqs + (warp - 2);
+        if (lane == 0) {
+            hq->count = 0;
+            hq->cap = p.cap;
+            hq->cand = p.cand;
+            hq->cand_cnt = p.cand_cnt;
+            hq->direct = (p.debug >> 1) & 1;
+        }
+        __syncwarp();
         uint32_t local = 0;
         for (uint32_t it = cluster_id; it < n_items; it += n_clusters, local++) {
             const uint32_t grp = it / p.n_qtiles, qt = it % p.n_qtiles;
@@ -649,7 +721,7 @@ gemm_topk2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
             mbar_wait(tfull, local & 1);
             tc_fence_after();
             const uint32_t taddr0 = tmem_base + ((quarter * 32u) << 16) + grp_e * GEMM2_BN;
-            epilogue_drain<METRIC, F16, GEMM2_BN>(p, taddr0, qt, row, row_ok, xn, thr_s, qn_s, us_s, c1_s, c2_s, half * (GEMM2_BN / 64),
+            epilogue_drain<METRIC, F16, GEMM2_BN>(p, taddr0, qt, row, row_ok, xn, thr_s, qn_s, us_s, c1_s, c2_s, hq, half * (GEMM2_BN / 64),
                                                   (half + 1) * (GEMM2_BN / 64));
             tc_fence_before();
             __syncwarp();
@@ -663,6 +735,218 @@ gemm_topk2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
     if (warp == 1) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+    }
+}
+
+// ---- the CTA-pair one-pass kernel (tcgen05 cta_group::2) ----------------------------------------------------------
+// What bounds the one-pass tiers once the epilogue is cheap is the rate at which operand bytes ENTER an SM (~43 B/clk each
+// when all 148 pull from L2; r02 ncu: xbar2l1tex 11.2 TB/s whatever the kernel): a 128 x 256 tile per SM needs 96 B/clk at
+// full tensor rate, two row tiles per query tile 64 B/clk.  A CTA pair shares the B operand inside the tensor cores: the
+// pair computes D[256 x 256] per instruction, each SM holds its own 128 rows of X and only HALF of the query tile, so an
+// SM takes in (128 + 128) operand rows for its 128 x 256 products -- 64 B/clk with the accumulators still double-buffered
+// (the drain overlaps the next tile's MMAs), against 96 B/clk for gemm_topk_kernel.
+// 320 threads per CTA: warp 0 TMA producer (both CTAs; every load completes on the LEADER's barrier) | warp 1 MMA issuer
+// (leader CTA only) | warps 2-9 epilogue (two warps per TMEM lane quarter, 128 columns each).
+constexpr int GEMMP_BN = 256;
+constexpr int GEMMP_STAGES = 6;
+constexpr uint32_t GEMMP_QH_BYTES = (GEMMP_BN / 2) * GEMM_BK * 4;            // this CTA's half of the query tile: 16 KB
+constexpr uint32_t GEMMP_STAGE_BYTES = GEMM_X_BYTES + GEMMP_QH_BYTES;          // 32 KB
+constexpr uint32_t GEMMP_SMEM_BYTES = 1024 + GEMMP_STAGES * GEMMP_STAGE_BYTES + 5 * GEMMP_BN * 4 + 256 + 8 * sizeof(HitQueue);
+
+__device__ __forceinline__ uint32_t mapa_shared(uint32_t local_addr, uint32_t cta_rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_addr), "r"(cta_rank));
+    return r;
+}
+// 2-D tile load of a CTA pair: the bytes land in THIS CTA's shared memory, the transaction count on `bar_cluster_addr`
+// (a shared::cluster address: the leader's barrier)
+__device__ __forceinline__ void tma_load_2d_pair(void* smem_dst, const CUtensorMap* map, int32_t c0, int32_t c1, uint32_t bar_cluster_addr) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+            smem_u32(smem_dst)),
+        "l"(map), "r"(bar_cluster_addr), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void tc_commit_pair(uint64_t* bar, uint16_t mask) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)),
+                 "h"(mask)
+                 : "memory");
+}
+__device__ __forceinline__ void tc_mma_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate, bool f16) {
+    if (f16)
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "setp.ne.b32 p, %4, 0;\n\t"
+            "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+            "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+            : "memory");
+    else
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "setp.ne.b32 p, %4, 0;\n\t"
+            "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+            "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+            : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar_cluster_addr) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar_cluster_addr) : "memory");
+}
+
+template <int METRIC, int PASSES>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm_topk_pair_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_q, const GemmParams p) {
+    static_assert(PASSES == 1 || PASSES == GEMM_TIER_F16, "one-pass tiers only");
+    constexpr bool F16 = PASSES == GEMM_TIER_F16;
+    constexpr uint32_t CHUNK_ELEMS = F16 ? 64 : 32;
+    // fp32 accumulate, K-major operands, M = 256 (the pair), N = 256
+    constexpr uint32_t FMT = F16 ? 0u : 2u;
+    constexpr uint32_t IDESC = (1u << 4) | (FMT << 7) | (FMT << 10) | ((uint32_t)(GEMMP_BN >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+    extern __shared__ unsigned char gemm_smem_raw[];
+    unsigned char* smem = gemm_smem_raw + ((1024u - (smem_u32(gemm_smem_raw) & 1023u)) & 1023u);
+    float* thr_s = reinterpret_cast<float*>(smem + GEMMP_STAGES * GEMMP_STAGE_BYTES);
+    float* qn_s = thr_s + GEMMP_BN;
+    float* us_s = qn_s + GEMMP_BN;
+    float* c1_s = us_s + GEMMP_BN;
+    float* c2_s = c1_s + GEMMP_BN;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(c2_s + GEMMP_BN);
+    uint64_t* full = bars;                       // [S]  leader only: both CTAs' loads of the stage have landed
+    uint64_t* empty = bars + GEMMP_STAGES;       // [S]  both CTAs: the pair's MMAs reading the stage have retired
+    uint64_t* tfull = bars + 2 * GEMMP_STAGES;   // [2]  both CTAs: accumulator complete
+    uint64_t* tempty = tfull + 2;                // [2]  leader only: accumulator drained by both CTAs' epilogue warps
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+    HitQueue* hqs = reinterpret_cast<HitQueue*>(reinterpret_cast<unsigned char*>(bars) + 256);   // [8] one per epilogue warp
+
+    const int tid = threadIdx.x;
+    const int warp = tid >> 5;
+    const int lane = tid & 31;
+    const uint32_t crank = cluster_ctarank();
+    const bool leader = crank == 0;
+
+    if (tid == 0) {
+        for (int s = 0; s < GEMMP_STAGES; s++) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], 1);
+        }
+        for (int a = 0; a < 2; a++) {
+            mbar_init(&tfull[a], 1);
+            mbar_init(&tempty[a], 16);   // 8 epilogue warps in each of the two CTAs
+        }
+        mbar_fence_init();
+        tma_prefetch_desc(&tm_x);
+        tma_prefetch_desc(&tm_q);
+    }
+    if (warp == 1) {   // one warp of EACH CTA: the pair's allocation (same columns in both tensor memories)
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();   // both CTAs' barriers exist before any load / commit / arrive crosses over
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    // items: (pair of consecutive row tiles) x (query tile); CTA `crank` of the pair owns row tile 2 * grp + crank
+    const uint32_t tiles = p.row_tile1 - p.row_tile0;
+    const uint32_t n_items = ((tiles + 1) / 2) * p.n_qtiles;
+    const uint32_t pair_id = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
+
+    if (warp == 0) {
+        // ------------------------------------------------------------------ TMA producer (both CTAs)
+        if (lane == 0) {
+            uint32_t stage = 0, phase = 0;
+            for (uint32_t it = pair_id; it < n_items; it += n_pairs) {
+                const uint32_t grp = it / p.n_qtiles, qt = it % p.n_qtiles;
+                const uint32_t rt = p.row_tile0 + grp * 2 + crank;
+                for (uint32_t kc = 0; kc < p.n_kchunks; kc++) {
+                    mbar_wait(&empty[stage], phase ^ 1);
+                    unsigned char* sb = smem + (size_t)stage * GEMMP_STAGE_BYTES;
+                    const uint32_t lead_full = mapa_shared(smem_u32(&full[stage]), 0);
+                    if (leader) mbar_arrive_expect_tx(&full[stage], 2 * GEMMP_STAGE_BYTES);   // this CTA's bytes and the peer's
+                    tma_load_2d_pair(sb, &tm_x, (int32_t)(kc * CHUNK_ELEMS), (int32_t)(rt * GEMM_BM), lead_full);
+                    tma_load_2d_pair(sb + GEMM_X_BYTES, &tm_q, (int32_t)(kc * CHUNK_ELEMS),
+                                     (int32_t)(qt * GEMMP_BN + crank * (GEMMP_BN / 2)), lead_full);
+                    if (++stage == GEMMP_STAGES) {
+                        stage = 0;
+                        phase ^= 1;
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ------------------------------------------------------------------ MMA issuer (leader CTA, one thread, for both SMs)
+        if (leader && lane == 0) {
+            uint32_t stage = 0, phase = 0, local = 0;
+            for (uint32_t it = pair_id; it < n_items; it += n_pairs, local++) {
+                const uint32_t acc = local & 1, acc_phase = (local >> 1) & 1;
+                mbar_wait(&tempty[acc], acc_phase ^ 1);
+                tc_fence_after();
+                const uint32_t tmem_d = tmem_base + acc * GEMMP_BN;
+                for (uint32_t kc = 0; kc < p.n_kchunks; kc++) {
+                    mbar_wait(&full[stage], phase);
+                    tc_fence_after();
+                    const uint32_t sb = smem_u32(smem + (size_t)stage * GEMMP_STAGE_BYTES);
+                    const uint64_t d_x = umma_desc_sw128(sb), d_q = umma_desc_sw128(sb + GEMM_X_BYTES);
+#pragma unroll
+                    for (uint32_t ks = 0; ks < GEMM_BK / 8; ks++) {
+                        const uint64_t adv = (uint64_t)(ks * 2);
+                        tc_mma_pair(tmem_d, d_x + adv, d_q + adv, IDESC, (kc | ks) != 0, F16);
+                    }
+                    tc_commit_pair(&empty[stage], 3);   // the stage is free again in both CTAs
+                    if (++stage == GEMMP_STAGES) {
+                        stage = 0;
+                        phase ^= 1;
+                    }
+                }
+                tc_commit_pair(&tfull[acc], 3);          // both CTAs' epilogue warps may drain their 128 rows
+            }
+        }
+    } else {
+        // ------------------------------------------------------------------ epilogue (both CTAs): 8 warps, 128 rows x 256 queries
+        const int et = tid - 64;            // 0..255
+        const uint32_t half = ((uint32_t)(warp - 2) >> 2) & 1u;
+        const uint32_t quarter = warp & 3;
+        HitQueue* hq = hqs + (warp - 2);
+        if (lane == 0) {
+            hq->count = 0;
+            hq->cap = p.cap;
+            hq->cand = p.cand;
+            hq->cand_cnt = p.cand_cnt;
+            hq->direct = (p.debug >> 1) & 1;
+        }
+        __syncwarp();
+        uint32_t local = 0;
+        for (uint32_t it = pair_id; it < n_items; it += n_pairs, local++) {
+            const uint32_t grp = it / p.n_qtiles, qt = it % p.n_qtiles;
+            const uint32_t tile = p.row_tile0 + grp * 2 + crank;
+            const uint32_t acc = local & 1, acc_phase = (local >> 1) & 1;
+            named_bar_sync(2, 256);
+            if (et < 128) epilogue_constants<METRIC, F16, GEMMP_BN>(p, qt, et, thr_s, qn_s, us_s, c1_s, c2_s);
+            const uint32_t row = tile * GEMM_BM + quarter * 32 + lane;
+            bool row_ok = tile < p.row_tile1 && row < p.n_rows && !(p.debug & 1);
+            float xn = 0.f;
+            if (row_ok) {
+                if (p.live) row_ok = (__ldg(p.live + (row >> 5)) >> (row & 31)) & 1u;
+                if (row_ok && p.filter) row_ok = (__ldg(p.filter + (row >> 5)) >> (row & 31)) & 1u;
+                if (METRIC == METRIC_L2 && row_ok) xn = __ldg(p.row_norms + row);
+            }
+            named_bar_sync(2, 256);
+            mbar_wait(&tfull[acc], acc_phase);
+            tc_fence_after();
+            const uint32_t taddr0 = tmem_base + ((quarter * 32u) << 16) + acc * GEMMP_BN;
+            epilogue_drain<METRIC, F16, GEMMP_BN>(p, taddr0, qt, row, row_ok, xn, thr_s, qn_s, us_s, c1_s, c2_s, hq, half * (GEMMP_BN / 64),
+                                                  (half + 1) * (GEMMP_BN / 64));
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(mapa_shared(smem_u32(&tempty[acc]), 0));   // the leader's barrier
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();   // nobody leaves while the peer may still load, commit or arrive across
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
     }
 }
 

@@ -156,6 +156,31 @@ cudaError_t launch_gemm2(const CUtensorMap& mx, const CUtensorMap& mq, const Gem
     return cl == 2 ? launch_gemm2_t<METRIC, 1, 2>(mx, mq, gp, grid, st) : launch_gemm2_t<METRIC, 1, 1>(mx, mq, gp, grid, st);
 }
 
+// the CTA-pair kernel (cta_group::2: the pair shares the query tile inside the tensor cores)
+template <int METRIC, int PASSES>
+cudaError_t launch_gemm_pair_t(const CUtensorMap& mx, const CUtensorMap& mq, const GemmParams& gp, int grid, cudaStream_t st) {
+    auto kern = gemm_topk_pair_kernel<METRIC, PASSES>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMMP_SMEM_BYTES);
+    if (e != cudaSuccess) return e;
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.blockDim = dim3(GEMM_THREADS);
+    cfg.dynamicSmemBytes = GEMMP_SMEM_BYTES;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kern, mx, mq, gp);
+}
+template <int METRIC>
+cudaError_t launch_gemm_pair(const CUtensorMap& mx, const CUtensorMap& mq, const GemmParams& gp, int grid, cudaStream_t st, int passes) {
+    return passes == GEMM_TIER_F16 ? launch_gemm_pair_t<METRIC, GEMM_TIER_F16>(mx, mq, gp, grid, st) : launch_gemm_pair_t<METRIC, 1>(mx, mq, gp, grid, st);
+}
+
 // The fp16 shadow of the rows ([capacity, f16_ld] halves of value * 2^s) behind the HALF tier, built lazily like the row
 // norms: rows [0, f16_valid) are current; the scale is frozen when row 0 is converted (st[0..2] = 2^-s, s, overflow flag).
 // Returns MLV_OK with *usable = false when there is no room for it (the caller takes the TF32 tier).
@@ -253,10 +278,13 @@ int search_gemm_tier(mlv_index* h, const float* qprep, uint32_t nq, uint32_t k, 
         CK(h, cudaGetLastError());
     }
     // wide kernel (two row tiles per staged query tile) for the one-pass tiers of wide batches; cl = CTAs per cluster
-    const int wide_cl = (GEMM_BN == 256 && passes != 3 && h->tune_gemm_wide != 0) ? (h->tune_gemm_wide == 1 ? 1 : 2) : 0;
+    // tune_gemm_wide: 0 single-tile kernel, 1 two row tiles per query tile, 2 the same in clusters of two (query tile by
+    // multicast), 3 CTA pairs (cta_group::2, double-buffered accumulators)
+    const bool pair = GEMM_BN == 256 && passes != 3 && h->tune_gemm_wide == 3;
+    const int wide_cl = (GEMM_BN == 256 && passes != 3 && h->tune_gemm_wide != 0 && !pair) ? (h->tune_gemm_wide == 1 ? 1 : 2) : 0;
     CUtensorMap mx, mqh, mql;
     if ((rc = make_tile_map(h, &mx, half ? view.rows16 : (const void*)view.rows, view.n_rows, GEMM_BM, half)) != MLV_OK) return rc;
-    if ((rc = make_tile_map(h, &mqh, qhi, nq_pad, wide_cl == 2 ? GEMM_BN / 2 : GEMM_BN, half)) != MLV_OK) return rc;
+    if ((rc = make_tile_map(h, &mqh, qhi, nq_pad, (wide_cl == 2 || pair) ? GEMM_BN / 2 : GEMM_BN, half)) != MLV_OK) return rc;
     if ((rc = make_tile_map(h, &mql, half ? qhi : qlo, nq_pad, GEMM_BN, half)) != MLV_OK) return rc;
     CK(h, cudaFuncSetAttribute(refine_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SELECT_MAX_P * 8)));
 
@@ -293,7 +321,11 @@ int search_gemm_tier(mlv_index* h, const float* qprep, uint32_t nq, uint32_t k, 
         uint64_t items = (uint64_t)take * gp.n_qtiles;
         if (wide_cl) items = (uint64_t)((take + 2 * wide_cl - 1) / (2 * wide_cl)) * gp.n_qtiles * wide_cl;   // CTAs that get an item
         int grid = (int)std::min<uint64_t>(items, (uint64_t)h->sm_count);
-        if (wide_cl == 2) grid = std::max(2, grid & ~1);
+        if (pair) {
+            items = (uint64_t)((take + 1) / 2) * gp.n_qtiles * 2;
+            grid = (int)std::min<uint64_t>(items, (uint64_t)h->sm_count);
+        }
+        if (wide_cl == 2 || pair) grid = std::max(2, grid & ~1);
         cudaEvent_t e0 = nullptr, e1 = nullptr;
         if (h->timing) {
             for (cudaEvent_t* ev : {&e0, &e1}) {
@@ -306,7 +338,9 @@ int search_gemm_tier(mlv_index* h, const float* qprep, uint32_t nq, uint32_t k, 
             }
             cudaEventRecord(e0, st);
         }
-        if (wide_cl)
+        if (pair)
+            CK(h, l2 ? launch_gemm_pair<METRIC_L2>(mx, mqh, gp, grid, st, passes) : launch_gemm_pair<METRIC_IP>(mx, mqh, gp, grid, st, passes));
+        else if (wide_cl)
             CK(h, l2 ? launch_gemm2<METRIC_L2>(mx, mqh, gp, grid, st, passes, wide_cl) : launch_gemm2<METRIC_IP>(mx, mqh, gp, grid, st, passes, wide_cl));
         else
             CK(h, l2 ? launch_gemm_t<METRIC_L2>(mx, mqh, mql, gp, grid, st, (int)GEMM_BN, passes)

@@ -565,6 +565,7 @@ __device__ __forceinline__ void scan_body(const ScanParams& p, const float* iq) 
                 if (rank == min(k, P) - 1) s_fT = key;
             }
             named_bar_sync(1, CW * 32);
+            if (p.timeline && tid == 0) p.timeline[blockIdx.x * 16 + 13] = global_timer_ns();   // fold: pool threshold known
             const uint64_t T = s_fT;
             for (uint32_t e = tid; e < n_in; e += nthr) {
                 const uint32_t w = e / k, j = e - w * k;
@@ -572,7 +573,9 @@ __device__ __forceinline__ void scan_body(const ScanParams& p, const float* iq) 
                 if (key <= T && key != KEY_SENTINEL) surv[atomicAdd(&s_fm, 1u)] = key;
             }
             named_bar_sync(1, CW * 32);
+            if (p.timeline && tid == 0) p.timeline[blockIdx.x * 16 + 14] = global_timer_ns();   // fold: survivors gathered
             const uint32_t m = s_fm;
+            if (p.timeline && tid == 0) p.timeline[blockIdx.x * 16 + 15] = m;                   // (a count, not a time)
             for (uint32_t e = tid; e < m; e += nthr) {
                 const uint64_t key = surv[e];
                 uint32_t rank = 0;

@@ -89,8 +89,9 @@ for fast in (0, 1, 1):
     for i, nm in enumerate(names):
         out[nm + "_us[min,med,max]"] = [round(float(x), 2) for x in (np.nanmin(rel[:, i]), np.nanmedian(rel[:, i]), np.nanmax(rel[:, i]))]
     out["last_cta_us[ticket,select_done,outputs,flag]"] = [round(float(x), 2) for x in rel[last, 4:8]]
-    out["last_cta_us[last_tile,own_sorted,all_sorted,folded,ticket,fence,threshold,survivors,select_done]"] = [
-        round(float(rel[last, i]), 2) for i in (2, 8, 9, 3, 4, 10, 11, 12, 5)]
+    out["last_cta_us[last_tile,own_sorted,all_sorted,pool_thr,fold_survivors,folded,ticket,fence,threshold,survivors,select_done]"] = [
+        round(float(rel[last, i]), 2) for i in (2, 8, 9, 13, 14, 3, 4, 10, 11, 12, 5)]
+    out["fold_survivor_count[min,med,max]"] = [int(t[:, 15].min()), int(np.median(t[:, 15])), int(t[:, 15].max())]
     print(json.dumps(out), flush=True)
 shard.set_tuning("timeline", 0)
 import subprocess  # noqa: E402

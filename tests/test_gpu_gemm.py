@@ -404,7 +404,7 @@ def test_wide_kernel_and_cluster_multicast_equal_the_single_tile_kernel(space):
     s.set_tuning("gemm", 0)
     ref = s.search(Q, k)
     s.set_tuning("gemm", 1)
-    for wide in (0, 1, 2):
+    for wide in (0, 1, 2, 3):
         s.set_tuning("gemm_wide", wide)
         for passes in (2, 1, 0):
             s.set_tuning("gemm_passes", passes)
