@@ -179,6 +179,8 @@ def c3(ctx, a, hbm_peak, bf16_peak, peak_src):
     gemm_ms = st["gemm_ms"] / reps
     idx.shard.set_timing(False)
     d, r, c = (t.cpu().numpy() for t in res[0])
+    idx.search(Q, k)                   # warm-up: pinned staging is allocated by the first host-buffer call
+    ctx.barrier()
     t0 = time.perf_counter()
     e2e = idx.search(Q, k)
     e2e_ms = ctx.max_over_ranks((time.perf_counter() - t0) * 1e3)
@@ -195,15 +197,18 @@ def c3(ctx, a, hbm_peak, bf16_peak, peak_src):
     return {"name": "c3", "workload": f"{rows}x{dim} fp32 l2 k={k}, {nq}-query batches, rows sharded over {ctx.world} GPU(s) (BASELINE configs[2])",
             "value": nq / ms * 1e3, "unit": "queries/s", "higher_is_better": True, "ms_per_batch": ms, "n_gpus": ctx.world,
             "e2e_host_buffers_qps": nq / e2e_ms * 1e3, "e2e_api": "ShardedIndex.search(host ndarray [4096, 768], k)",
-            "tiers": {"one_pass_tf32_certified_per_batch": fast, "scan_fallback_per_batch": fallback,
+            "tiers": {"first_tier_certified_per_batch": fast, "first_tier": "fp16 shadow, CTA-pair kernel (tcgen05 cta_group::2 kind::f16)",
+                      "scan_fallback_per_batch": fallback,
                       "rank0_gemm_ms_per_batch": gemm_ms, "rank0_gemm_share_of_batch": gemm_ms / ms},
             "roofline": {"bound": "tensor", "achieved": f_alg_gpu / (ms * 1e-3) / 1e12, "peak": tf32_peak, "unit": "TFLOP/s",
                          "frac": f_alg_gpu / (ms * 1e-3) / 1e12 / tf32_peak,
                          "peak_source": peak_src + " bf16_tflops / 2 (TF32 dense = half of bf16)",
                          "tensor_pipe_work_multiplier": work_mult,
                          "kernel_only_TFLOPs": (f_alg_gpu * work_mult / (gemm_ms * 1e-3) / 1e12) if gemm_ms else None,
-                         "how": "per GPU: F_alg = 2*nq*local_rows*dim (fp32-equivalent useful flops) / batch time; the one-pass TF32 tier executes "
-                                "1 x F_alg on the tensor pipe, queries it cannot certify add 3 x F_alg (3xTF32)"},
+                         "frac_of_bf16_peak": f_alg_gpu / (ms * 1e-3) / 1e12 / bf16_peak,
+                         "how": "per GPU: F_alg = 2*nq*local_rows*dim (fp32-equivalent useful flops) / batch time; the first tier executes "
+                                "1 x F_alg on the tensor pipe as kind::f16 MMAs on an fp16 shadow of the rows (its roof is the bf16/fp16 peak, "
+                                "frac_of_bf16_peak; frac is against the TF32 peak north_star names), queries it cannot certify add 3 x F_alg (3xTF32)"},
             "parity": parity}
 
 

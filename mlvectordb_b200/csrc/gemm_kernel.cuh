@@ -1025,7 +1025,8 @@ __global__ void convert_rows_f16_kernel(const float* __restrict__ rows, uint64_t
 // cleared counters and flags.  One warp per (padded) query.
 __global__ void split_queries_f16_kernel(const float* __restrict__ q, __half* __restrict__ q16, float* __restrict__ unscale,
                                          float* __restrict__ qn, float* __restrict__ thr, uint32_t* __restrict__ cnt,
-                                         uint32_t* __restrict__ flags, uint32_t nq, uint32_t nq_pad, uint32_t ld, uint32_t ld16) {
+                                         uint32_t* __restrict__ flags, uint32_t* __restrict__ sorted_n, uint32_t nq, uint32_t nq_pad,
+                                         uint32_t ld, uint32_t ld16) {
     const uint32_t w = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (w >= nq_pad) return;
@@ -1050,6 +1051,7 @@ __global__ void split_queries_f16_kernel(const float* __restrict__ q, __half* __
         thr[w] = w < nq ? __int_as_float(0x7f800000) : __int_as_float(0xff800000);
         cnt[w] = 0;
         flags[w] = 0;
+        sorted_n[w] = 0;
     }
 }
 
@@ -1081,7 +1083,7 @@ __global__ void row_norms_kernel(const float* __restrict__ rows, uint64_t first,
 // cleared candidate counters and flags.  One warp per (padded) query.
 __global__ void split_queries_kernel(const float* __restrict__ q, float* __restrict__ qhi, float* __restrict__ qlo,
                                      float* __restrict__ qn, float* __restrict__ thr, uint32_t* __restrict__ cnt,
-                                     uint32_t* __restrict__ flags, uint32_t nq, uint32_t nq_pad, uint32_t ld) {
+                                     uint32_t* __restrict__ flags, uint32_t* __restrict__ sorted_n, uint32_t nq, uint32_t nq_pad, uint32_t ld) {
     const uint32_t w = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (w >= nq_pad) return;
@@ -1100,32 +1102,51 @@ __global__ void split_queries_kernel(const float* __restrict__ q, float* __restr
         thr[w] = w < nq ? __int_as_float(0x7f800000) : __int_as_float(0xff800000);
         cnt[w] = 0;
         flags[w] = 0;
+        sorted_n[w] = 0;
     }
 }
 
 // After a round: keep the kprime smallest keys of each query's buffer and tighten its threshold.
 // flags[q] bit 0 = the buffer overflowed (candidates were lost: the query falls back to the scan).
+// The first sorted_n[q] slots are what the previous refine kept -- already ascending -- so only the round's NEW hits are
+// sorted (a bitonic network in shared memory is bound by shared-memory bandwidth: 4096 queries x 1024 keys cost 190 us
+// per round) and the two ascending lists are merged by rank (binary search).  Shared memory: P + kprime keys.
 __global__ void __launch_bounds__(SELECT_THREADS, 1)
-refine_kernel(uint64_t* cand, uint32_t* cnt, float* thr, uint32_t* flags, uint32_t cap, uint32_t P, uint32_t kprime) {
+refine_kernel(uint64_t* cand, uint32_t* cnt, float* thr, uint32_t* flags, uint32_t* sorted_n, uint32_t cap, uint32_t P, uint32_t kprime) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    uint64_t* a = reinterpret_cast<uint64_t*>(smem_raw);
+    uint64_t* a = reinterpret_cast<uint64_t*>(smem_raw);   // new hits, padded to a power of two
     const uint32_t q = blockIdx.x;
     const uint32_t c = cnt[q];
     const uint32_t n = min(c, cap);
     if (n < kprime && c <= cap) return;  // fewer than k' candidates: keep all, threshold stays +inf (uniform per block)
+    const uint32_t s = min(sorted_n[q], n);
+    const uint32_t m = n - s;
     uint64_t* mine = cand + (size_t)q * cap;
-    // sort only as many slots as this query filled (typically k' + a few dozen of the `cap` slots)
-    uint32_t Pn = 2;
-    while (Pn < n) Pn <<= 1;
-    Pn = min(Pn, P);
-    for (uint32_t i = threadIdx.x; i < Pn; i += blockDim.x) a[i] = i < n ? mine[i] : KEY_SENTINEL;
-    bitonic_sort_smem(a, Pn);
+    uint32_t Pm = 2;
+    while (Pm < m) Pm <<= 1;
+    Pm = min(Pm, P);
+    uint64_t* o = a + Pm;                                   // the previous survivors (ascending), s <= kprime of them
+    for (uint32_t i = threadIdx.x; i < Pm; i += blockDim.x) a[i] = i < m ? mine[s + i] : KEY_SENTINEL;
+    for (uint32_t i = threadIdx.x; i < s; i += blockDim.x) o[i] = mine[i];
+    bitonic_sort_smem(a, Pm);
     const uint32_t keep = min(n, kprime);
-    for (uint32_t i = threadIdx.x; i < keep; i += blockDim.x) mine[i] = a[i];
+    for (uint32_t e = threadIdx.x; e < n; e += blockDim.x) {
+        uint64_t key;
+        uint32_t rank;
+        if (e < s) {
+            key = o[e];
+            rank = e + sorted_count_below(a, m, key, true);
+        } else {
+            key = a[e - s];
+            rank = (e - s) + sorted_count_below(o, s, key, false);
+        }
+        if (rank < keep) mine[rank] = key;
+        if (rank == kprime - 1) thr[q] = key_dist(key);
+    }
     if (threadIdx.x == 0) {
         cnt[q] = keep;
+        sorted_n[q] = keep;
         if (c > cap) flags[q] |= 1u;
-        if (n >= kprime) thr[q] = key_dist(a[kprime - 1]);
     }
 }
 

@@ -256,7 +256,7 @@ int search_gemm_tier(mlv_index* h, const float* qprep, uint32_t nq, uint32_t k, 
     const bool l2 = h->metric == MLV_L2;
     // scratch: Qhi | Qlo | qn | thr | cnt | flags
     const size_t qmat = (size_t)nq_pad * ld * 4;
-    if ((rc = ensure_dev(h, h->d_gq, 2 * qmat + (size_t)nq_pad * 16)) != MLV_OK) return rc;
+    if ((rc = ensure_dev(h, h->d_gq, 2 * qmat + (size_t)nq_pad * 20)) != MLV_OK) return rc;
     if ((rc = ensure_dev(h, h->d_cand, (size_t)nq_pad * cap * 8)) != MLV_OK) return rc;
     float* qhi = (float*)h->d_gq.p;
     float* qlo = qhi + (size_t)nq_pad * ld;
@@ -264,16 +264,17 @@ int search_gemm_tier(mlv_index* h, const float* qprep, uint32_t nq, uint32_t k, 
     float* thr = qn + nq_pad;
     uint32_t* cnt = (uint32_t*)(thr + nq_pad);
     uint32_t* flags = cnt + nq_pad;
+    uint32_t* sorted_n = flags + nq_pad;
     uint64_t* cand = (uint64_t*)h->d_cand.p;
     // HALF tier: the Qhi area holds the fp16 queries, the Qlo area their 2^-sq
     float* q_unscale = qlo;
     {
         const int wpb = 8;
         if (half)
-            split_queries_f16_kernel<<<(nq_pad + wpb - 1) / wpb, wpb * 32, 0, st>>>(qprep, (__half*)qhi, q_unscale, qn, thr, cnt, flags, nq,
-                                                                                    nq_pad, ld, ld16);
+            split_queries_f16_kernel<<<(nq_pad + wpb - 1) / wpb, wpb * 32, 0, st>>>(qprep, (__half*)qhi, q_unscale, qn, thr, cnt, flags,
+                                                                                    sorted_n, nq, nq_pad, ld, ld16);
         else
-            split_queries_kernel<<<(nq_pad + wpb - 1) / wpb, wpb * 32, 0, st>>>(qprep, qhi, qlo, qn, thr, cnt, flags, nq, nq_pad, ld);
+            split_queries_kernel<<<(nq_pad + wpb - 1) / wpb, wpb * 32, 0, st>>>(qprep, qhi, qlo, qn, thr, cnt, flags, sorted_n, nq, nq_pad, ld);
         h->launches++;
         CK(h, cudaGetLastError());
     }
@@ -286,7 +287,7 @@ int search_gemm_tier(mlv_index* h, const float* qprep, uint32_t nq, uint32_t k, 
     if ((rc = make_tile_map(h, &mx, half ? view.rows16 : (const void*)view.rows, view.n_rows, GEMM_BM, half)) != MLV_OK) return rc;
     if ((rc = make_tile_map(h, &mqh, qhi, nq_pad, (wide_cl == 2 || pair) ? GEMM_BN / 2 : GEMM_BN, half)) != MLV_OK) return rc;
     if ((rc = make_tile_map(h, &mql, half ? qhi : qlo, nq_pad, GEMM_BN, half)) != MLV_OK) return rc;
-    CK(h, cudaFuncSetAttribute(refine_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SELECT_MAX_P * 8)));
+    CK(h, cudaFuncSetAttribute(refine_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((SELECT_MAX_P + SELECT_MAX_P / 4) * 8)));
 
     GemmParams gp{};
     gp.n_rows = (uint32_t)view.n_rows;
@@ -349,7 +350,7 @@ int search_gemm_tier(mlv_index* h, const float* qprep, uint32_t nq, uint32_t k, 
             cudaEventRecord(e1, st);
             h->gemm_pending.emplace_back(e0, e1);
         }
-        refine_kernel<<<nq, refine_threads, (size_t)P * 8, st>>>(cand, cnt, thr, flags, cap, P, kprime);
+        refine_kernel<<<nq, refine_threads, (size_t)(P + kprime) * 8, st>>>(cand, cnt, thr, flags, sorted_n, cap, P, kprime);
         CK(h, cudaGetLastError());
         h->launches += 2;
         h->gemm_launches++;

@@ -1286,7 +1286,7 @@ int mlv_index_debug_gemm(mlv_index_t h, const float* queries, uint32_t nq, float
     const uint32_t nq_pad = (nq + GEMM_BN - 1) / GEMM_BN * GEMM_BN;
     const uint32_t cap = pow2_ceil((uint32_t)h->rows);
     const size_t qmat = (size_t)nq_pad * ld * 4;
-    if ((rc = ensure_dev(h, h->d_gq, 2 * qmat + (size_t)nq_pad * 16)) != MLV_OK) return rc;
+    if ((rc = ensure_dev(h, h->d_gq, 2 * qmat + (size_t)nq_pad * 20)) != MLV_OK) return rc;
     if ((rc = ensure_dev(h, h->d_cand, (size_t)nq_pad * cap * 8)) != MLV_OK) return rc;
     float* qhi = (float*)h->d_gq.p;
     float* qlo = qhi + (size_t)nq_pad * ld;
@@ -1294,6 +1294,7 @@ int mlv_index_debug_gemm(mlv_index_t h, const float* queries, uint32_t nq, float
     float* thr = qn + nq_pad;
     uint32_t* cnt = (uint32_t*)(thr + nq_pad);
     uint32_t* flags = cnt + nq_pad;
+    uint32_t* sorted_n = flags + nq_pad;
     const int passes = h->tune_gemm_passes == 1 ? 1 : (h->tune_gemm_passes == GEMM_TIER_F16 ? GEMM_TIER_F16 : 3);   // which tier's distances
     const bool half = passes == GEMM_TIER_F16;
     const uint32_t ld16 = f16_ld(h);
@@ -1301,10 +1302,10 @@ int mlv_index_debug_gemm(mlv_index_t h, const float* queries, uint32_t nq, float
         bool usable = false;
         if ((rc = ensure_f16_shadow(h, st, &usable)) != MLV_OK) return rc;
         if (!usable) return fail(h, MLV_E_NOMEM, "no room for the fp16 shadow");
-        split_queries_f16_kernel<<<(nq_pad + 7) / 8, 256, 0, st>>>((const float*)lane_for(h, st)->d_q.p, (__half*)qhi, qlo, qn, thr, cnt, flags, nq,
-                                                                  nq_pad, ld, ld16);
+        split_queries_f16_kernel<<<(nq_pad + 7) / 8, 256, 0, st>>>((const float*)lane_for(h, st)->d_q.p, (__half*)qhi, qlo, qn, thr, cnt, flags,
+                                                                  sorted_n, nq, nq_pad, ld, ld16);
     } else {
-        split_queries_kernel<<<(nq_pad + 7) / 8, 256, 0, st>>>((const float*)lane_for(h, st)->d_q.p, qhi, qlo, qn, thr, cnt, flags, nq, nq_pad, ld);
+        split_queries_kernel<<<(nq_pad + 7) / 8, 256, 0, st>>>((const float*)lane_for(h, st)->d_q.p, qhi, qlo, qn, thr, cnt, flags, sorted_n, nq, nq_pad, ld);
     }
     CK(h, cudaGetLastError());
     CUtensorMap mx, mqh, mql;
