@@ -339,9 +339,17 @@ int search_gemm_tier(mlv_index* h, const float* qprep, uint32_t nq, uint32_t k, 
             }
             cudaEventRecord(e0, st);
         }
-        if (pair)
-            CK(h, l2 ? launch_gemm_pair<METRIC_L2>(mx, mqh, gp, grid, st, passes) : launch_gemm_pair<METRIC_IP>(mx, mqh, gp, grid, st, passes));
-        else if (wide_cl)
+        if (pair) {
+            cudaError_t le = l2 ? launch_gemm_pair<METRIC_L2>(mx, mqh, gp, grid, st, passes) : launch_gemm_pair<METRIC_IP>(mx, mqh, gp, grid, st, passes);
+            if (le != cudaSuccess) {
+                // a device / partition that cannot co-schedule CTA pairs: nothing was launched -- this handle uses the
+                // single-tile kernel from now on, and this batch starts over with it (no round has completed yet or the
+                // thresholds simply carry over: candidate buffers are additive)
+                cudaGetLastError();
+                h->tune_gemm_wide = 0;
+                return search_gemm_tier(h, qprep, nq, k, passes, view, out_d, out_r, out_c, st, hflags);
+            }
+        } else if (wide_cl)
             CK(h, l2 ? launch_gemm2<METRIC_L2>(mx, mqh, gp, grid, st, passes, wide_cl) : launch_gemm2<METRIC_IP>(mx, mqh, gp, grid, st, passes, wide_cl));
         else
             CK(h, l2 ? launch_gemm_t<METRIC_L2>(mx, mqh, mql, gp, grid, st, (int)GEMM_BN, passes)

@@ -153,6 +153,12 @@ class DeviceShard:
         dists = np.empty((nq, k), dtype=np.float32)
         rows = np.empty((nq, k), dtype=np.int64)
         counts = np.empty(nq, dtype=np.int32)
+        if filt is None:      # the batch-1 latency path: nothing between the caller and the one launch but this call
+            st = self._lib.mlv_index_search(self._h, q.ctypes.data, nq, int(k), None, dists.ctypes.data, rows.ctypes.data,
+                                            counts.ctypes.data)
+            if st:
+                self._ck(st)
+            return dists, rows, counts
         fw = self._filter_words(filt)
         with _bound(self, filt):
             self._ck(self._lib.mlv_index_search(self._h, q.ctypes.data, nq, int(k), fw.ctypes.data if fw is not None else None,
