@@ -9,7 +9,10 @@ module turns metadata keys into columns and values into codes:
 * a key whose values are Python ``int`` (not ``bool``) inside the int32 range is stored **raw**, so
   ordered comparisons (``< <= > >= between``) work on it;
 * any other hashable value is **dictionary coded** (value -> 0, 1, 2 ... in order of first appearance;
-  Python equality decides: ``1 == 1.0 == True`` share a code); only ``==`` / ``!=`` make sense there;
+  Python equality decides: ``1 == 1.0 == True`` share a code).  ``==`` / ``!=`` compare codes; an ORDERED comparison
+  (``< <= > >= between``) needs order-preserving codes: when the dictionary's values are mutually comparable the index
+  re-codes the column by rank once (``reorder`` -> one column rewrite on the device) and the comparison becomes a
+  range of codes; values that cannot be ordered (mixed strings and numbers, NaN) keep the host fallback;
 * a key that cannot be represented (unhashable values, a raw column that meets a non-int value, more than
   ``MAX_COLUMNS`` keys) is marked *host only* and constraints on it are reported as not device-evaluable,
   so the caller falls back to evaluating the predicate against the stored metadata.
@@ -55,12 +58,18 @@ def _untag(t: Any):
 
 
 class _Column:
-    __slots__ = ("index", "kind", "codes")
+    __slots__ = ("index", "kind", "codes", "ordered", "top")
 
     def __init__(self, index: int, kind: str):
         self.index = index
         self.kind = kind                  # "raw" | "dict" | "host"
         self.codes: Dict[Any, int] = {}   # dict kind: value -> code
+        self.ordered = True               # dict kind: codes ascend with the values (Python <), so code ranges are value ranges
+        self.top: Any = None              # dict kind, ordered: the value holding the largest code
+
+
+def _orderable(v: Any) -> bool:
+    return not (isinstance(v, (float, np.floating)) and v != v)   # NaN orders with nothing
 
 
 class ColumnCodec:
@@ -108,7 +117,16 @@ class ColumnCodec:
                 code = len(c.codes)
                 if code > _I32_MAX:
                     return None
+                if c.ordered and code:      # does the new value extend the order?  (mixed types / NaN: it does not)
+                    try:
+                        c.ordered = bool(_orderable(v) and c.top < v)
+                    except TypeError:
+                        c.ordered = False
+                elif not code:
+                    c.ordered = _orderable(v)
                 c.codes[v] = code
+                if c.ordered:
+                    c.top = v
             return code
         except TypeError:                # unhashable
             return None
@@ -179,6 +197,41 @@ class ColumnCodec:
             return None
         return c.index, np.asarray(codes, dtype=np.int32)
 
+    # ------------------------------------------------------------------ ordered comparisons on dictionary columns
+    def unordered_columns(self, constraints: Mapping[str, Any]) -> List[str]:
+        """Dictionary columns that an ordered constraint of ``constraints`` touches while their codes are not in value
+        order: ``reorder`` them (and rewrite the device column) before asking for ``predicates``."""
+        out = []
+        for name, want in constraints.items():
+            if isinstance(want, tuple) and len(want) in (2, 3) and want[0] in PRED_OPS and want[0] not in ("==", "!="):
+                c = self._cols.get(name)
+                if c is not None and c.kind == "dict" and not c.ordered and len(c.codes) > 1:
+                    out.append(name)
+        return out
+
+    def reorder(self, name: str) -> Optional[np.ndarray]:
+        """Re-code dictionary column ``name`` by the rank of its values.  -> int32 array old code -> new code (the caller
+        rewrites the stored column through it), or None when the values cannot be ordered (they stay as they are and
+        ordered constraints on the column remain host-evaluated)."""
+        c = self._cols.get(name)
+        if c is None or c.kind != "dict":
+            return None
+        values = list(c.codes)
+        try:
+            if not all(_orderable(v) for v in values):
+                return None
+            ranked = sorted(values)
+            if any(not (a < b) for a, b in zip(ranked, ranked[1:])):     # a total, strict order or nothing
+                return None
+        except TypeError:
+            return None
+        perm = np.empty(len(values), dtype=np.int32)
+        for new, v in enumerate(ranked):
+            perm[c.codes[v]] = new
+        c.codes = {v: i for i, v in enumerate(ranked)}
+        c.ordered, c.top = True, (ranked[-1] if ranked else None)
+        return perm
+
     # ------------------------------------------------------------------ snapshot (snapshot.py)
     def to_json(self) -> dict:
         """JSON-able state.  Dictionary codes survive for str / int / float / bool / None values and tuples of
@@ -201,6 +254,12 @@ class ColumnCodec:
         for name, st in state["columns"].items():
             c = _Column(int(st["index"]), st["kind"])
             c.codes = {_untag(t): int(code) for t, code in st["codes"]}
+            by_code = sorted(c.codes, key=c.codes.get)
+            try:
+                c.ordered = all(_orderable(v) for v in by_code) and all(a < b for a, b in zip(by_code, by_code[1:]))
+            except TypeError:
+                c.ordered = False
+            c.top = by_code[-1] if (c.ordered and by_code) else None
             self._cols[name] = c
         return self
 
@@ -219,9 +278,15 @@ class ColumnCodec:
             c = self._cols.get(name)
             if c is None or c.kind == "host":
                 return None              # never seen here (rows may have been loaded without their metadata) / host only
+            if c.kind == "dict" and op not in ("==", "!="):
+                if not c.ordered:
+                    return None          # codes carry no order (yet: see unordered_columns / reorder)
+                pred = _dict_range_predicate(c, op, args)
+                if pred is None:
+                    return None
+                preds.append(pred)
+                continue
             if c.kind == "dict":
-                if op not in ("==", "!="):
-                    return None          # codes carry no order
                 try:
                     code = c.codes.get(args[0])
                 except TypeError:
@@ -249,6 +314,28 @@ class ColumnCodec:
         if len(preds) > MAX_PREDICATES:
             return None
         return preds
+
+
+def _dict_range_predicate(c: _Column, op: str, args) -> Optional[Predicate]:
+    """Ordered comparison on a dictionary column whose codes ascend with its values: a range of codes.  A bound that
+    does not compare with the values (``"a" < 3``) satisfies nothing, exactly as ``host_predicate`` decides it."""
+    import bisect
+    vals = list(c.codes)      # insertion order == code order == value order
+    try:
+        if not all(_orderable(a) for a in args):
+            return (c.index,) + _IMPOSSIBLE
+        if op == "between":
+            lo, hi = bisect.bisect_left(vals, args[0]), bisect.bisect_right(vals, args[1]) - 1
+            return (c.index, "between", lo, hi) if lo <= hi else (c.index,) + _IMPOSSIBLE
+        if op == "<":
+            return (c.index, "<", bisect.bisect_left(vals, args[0]), 0)
+        if op == "<=":
+            return (c.index, "<", bisect.bisect_right(vals, args[0]), 0)
+        if op == ">":
+            return (c.index, ">=", bisect.bisect_right(vals, args[0]), 0)
+        return (c.index, ">=", bisect.bisect_left(vals, args[0]), 0)
+    except TypeError:
+        return (c.index,) + _IMPOSSIBLE
 
 
 def _raw_predicate(column: int, op: str, vals) -> Optional[Predicate]:

@@ -211,6 +211,25 @@ class GpuIndex:
             return np.fromiter((bool(filt(ns.uuid_of(r))) for r in range(ns.n)), dtype=bool, count=ns.n)
         return filt
 
+    @staticmethod
+    def _order_columns(ns, constraints: Mapping) -> None:
+        """An ordered constraint on a dictionary-coded key needs codes that ascend with the values: re-code the column
+        by rank (one read + one write of 4 bytes per row; again only after new values broke the order)."""
+        from . import _capi
+        try:
+            names = ns.codec.unordered_columns(constraints)
+        except TypeError:
+            return
+        for name in names:
+            perm = ns.codec.reorder(name)
+            if perm is None or ns.n == 0:
+                continue
+            column = ns.codec.column_index(name)
+            codes = ns.shard.get_column(column, 0, ns.n)
+            has = codes != _capi.COLUMN_MISSING
+            codes[has] = perm[codes[has]]
+            ns.shard.set_column(column, codes, 0)
+
     def _where(self, ns: _Namespace, constraints: Mapping) -> PreparedFilter:
         try:
             key = tuple(sorted(constraints.items(), key=lambda kv: kv[0]))
@@ -219,6 +238,7 @@ class GpuIndex:
             key, cached = None, None
         if cached is not None:
             return cached
+        self._order_columns(ns, constraints)
         preds = ns.codec.predicates(constraints)
         if preds is None:
             raise NotDeviceEvaluable(f"constraints {dict(constraints)!r} cannot be evaluated on the device columns")

@@ -179,11 +179,27 @@ class ShardedGpuIndex:
         key = tuple(sorted(filt.items(), key=lambda kv: kv[0]))
         cached = ns.where_cache.get(key)
         if cached is None:
+            self._order_columns(ns, filt)
             preds = ns.codec.predicates(filt)
             if preds is None:
                 raise ValueError(f"constraints {dict(filt)!r} cannot be evaluated on the device columns")
             cached = ns.where_cache[key] = ns.searcher.shard.where(preds)
         return cached
+
+    def _order_columns(self, ns: _ShardedNamespace, constraints: Mapping) -> None:
+        """As ``GpuIndex._order_columns``: the codec is replicated, so every rank computes the same re-coding and applies
+        it to its own rows."""
+        from . import _capi
+        for name in ns.codec.unordered_columns(constraints):
+            perm = ns.codec.reorder(name)
+            n_local = ns.parts[self.rank].n
+            if perm is None or n_local == 0:
+                continue
+            column = ns.codec.column_index(name)
+            codes = ns.searcher.shard.get_column(column, 0, n_local)
+            has = codes != _capi.COLUMN_MISSING
+            codes[has] = perm[codes[has]]
+            ns.searcher.shard.set_column(column, codes, 0)
 
     def _results(self, ns: _ShardedNamespace, dists, rows, metric: str) -> List[SearchResult]:
         out = []

@@ -137,8 +137,10 @@ def test_index_filters_by_metadata_on_the_device(space):
     assert sorted(idx.metadata_columns("ns")) == ["bucket", "color"]
     q = VectorDTO(values=synthetic.queries(21, 1, dim)[0], metadata={})
     ns = idx._ns["ns"]
+    # ({"color": ("<", ...)}: an ORDERED constraint on a dictionary-coded key -- the column is re-coded by rank on the device)
     for cons in ({"color": "red"}, {"bucket": 3, "color": "blue"}, {"bucket": ("<", 5)}, {"bucket": ("between", 4, 9), "color": ("!=", "red")},
-                 {"color": "purple"}, {"bucket": 3.5}):
+                 {"color": "purple"}, {"bucket": 3.5}, {"color": ("<", "h")}, {"color": ("between", "c", "red"), "bucket": (">=", 10)},
+                 {"color": "red"}, {"color": (">", 7)}):
         assert idx.where("ns", cons) is not None
         mask = np.array([host_predicate(cons)(md) for md in mds])
         got = idx.search(q, k, "ns", space, filter=cons)
