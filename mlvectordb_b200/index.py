@@ -300,13 +300,12 @@ class GpuIndex:
         if q.shape[0] != ns.dim:
             return []  # the reference swallows hnswlib's dimension RuntimeError into [] (index.py:110-119)
         dists, rows, counts = ns.shard.search(q[None, :], top_k, self._filter_mask(ns, filter))
-        results: List[SearchResult] = []
-        for row, dist in zip(rows[0, : counts[0]].tolist(), dists[0, : counts[0]].tolist()):
-            score = float(dist)
-            if metric == "cosine":
-                score = 1 - score
-            results.append(SearchResult(vector_id=ns.uuid_of(row), score=score))
-        return results
+        c = int(counts[0])
+        raw = ns.ids[rows[0, :c]].tobytes()          # the hits' uuid bytes in one gather (label -> UUID, reference index.py:123)
+        scores = dists[0, :c].tolist()
+        if metric == "cosine":
+            return [SearchResult(vector_id=uuid_from_bytes(raw[16 * i: 16 * i + 16]), score=1 - scores[i]) for i in range(c)]
+        return [SearchResult(vector_id=uuid_from_bytes(raw[16 * i: 16 * i + 16]), score=scores[i]) for i in range(c)]
 
     def search_async(self, query: VectorDTO, top_k: int, namespace: str, metric: str,
                      filter: FilterArg = None) -> "PendingResults":
