@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define MLV_ABI_VERSION 3
+#define MLV_ABI_VERSION 4
 
 typedef struct mlv_index *mlv_index_t;
 
@@ -378,7 +378,12 @@ int mlv_index_debug_timeline(mlv_index_t h, uint64_t *out, uint32_t max_ctas, ui
  * batches wider than 128 queries: 3 = CTA pairs, tcgen05 cta_group::2 (default); 1 = two row tiles per staged
  * query tile; 2 = the same in clusters of two with the query tile by TMA multicast; 0 = the single-tile kernel),
  * "gemm_debug" (profiling only: bit 0 = the epilogue compares nothing -- results are wrong; bit 1 = hits bypass
- * the per-warp queue).  Results never depend on "gemm_wide" / "gemm_passes".  This call returns cumulative counters
+ * the per-warp queue), "gemm_predict" (1 default: the one-pass tiers' per-query thresholds are PREDICTED from the rows
+ * seen so far -- a round that has seen S of N rows thresholds at its max(32, 4 k' S / N)-th best instead of its k'-th,
+ * so later rounds append a fraction of the candidates; the last round verifies the prediction (k' candidates at or
+ * below the tightest threshold used) and a query that fails goes to the next tier, whose thresholds are the plain
+ * rule; predictions sit out 8, 16, ... batches after failing for more than an eighth of a batch; 0 = plain rule
+ * everywhere).  Results never depend on "gemm_wide" / "gemm_passes" / "gemm_predict".  This call returns cumulative counters
  * and, when timing is enabled, the summed device time of the GEMM launches since the last call.
  */
 typedef struct mlv_gemm_stats {
@@ -391,6 +396,7 @@ typedef struct mlv_gemm_stats {
     uint64_t fast_queries;        /* of `queries`, certified by the one-pass TF32 tier (no 3xTF32 work spent on them) */
     uint64_t gathered_searches;   /* of `searches`, filtered batches that multiplied a compacted copy of the passing rows */
     uint64_t half_queries;        /* of `fast_queries`, certified by the fp16-shadow tier (kind::f16 on halves of the rows) */
+    uint64_t mispredicted_queries; /* queries whose predicted thresholds failed the final check ("gemm_predict"); answered by the next tier */
 } mlv_gemm_stats_t;
 int mlv_index_gemm_stats(mlv_index_t h, mlv_gemm_stats_t *out);
 /*

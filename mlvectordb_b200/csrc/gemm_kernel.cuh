@@ -1106,19 +1106,33 @@ __global__ void split_queries_kernel(const float* __restrict__ q, float* __restr
     }
 }
 
-// After a round: keep the kprime smallest keys of each query's buffer and tighten its threshold.
-// flags[q] bit 0 = the buffer overflowed (candidates were lost: the query falls back to the scan).
+// After a round: keep the kprime smallest keys of each query's buffer and tighten its threshold to the jrank-th smallest.
+// jrank == kprime is the plain rule (a threshold no tighter than the k'-th best seen can never lose a top-k' row).
+// jrank < kprime PREDICTS the final k'-th best from the rows seen so far -- with S of N rows seen, the jrank-th best of S
+// sits where about jrank N / S rows of the whole matrix will, and the host keeps that at 4 k' or more -- so later rounds
+// append a fraction of the hits.  A prediction can be wrong (rows stored in an order that correlates with the query):
+// the last round's refine (final != 0) checks it -- k' candidates at or below the tightest threshold any round used,
+// which makes the kept k' exactly the k' best of ALL rows -- and sets flags[q] bit 2 otherwise (the query is answered by
+// the next tier, whose thresholds are the plain rule).  Thresholds only tighten (min), so the last one is the tightest.
+// flags[q] bit 0 = the buffer overflowed (candidates were lost: the query falls back as well).
 // The first sorted_n[q] slots are what the previous refine kept -- already ascending -- so only the round's NEW hits are
 // sorted (a bitonic network in shared memory is bound by shared-memory bandwidth: 4096 queries x 1024 keys cost 190 us
 // per round) and the two ascending lists are merged by rank (binary search).  Shared memory: P + kprime keys.
 __global__ void __launch_bounds__(SELECT_THREADS, 1)
-refine_kernel(uint64_t* cand, uint32_t* cnt, float* thr, uint32_t* flags, uint32_t* sorted_n, uint32_t cap, uint32_t P, uint32_t kprime) {
+refine_kernel(uint64_t* cand, uint32_t* cnt, float* thr, uint32_t* flags, uint32_t* sorted_n, uint32_t cap, uint32_t P, uint32_t kprime,
+              uint32_t jrank, int final) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     uint64_t* a = reinterpret_cast<uint64_t*>(smem_raw);   // new hits, padded to a power of two
     const uint32_t q = blockIdx.x;
     const uint32_t c = cnt[q];
     const uint32_t n = min(c, cap);
-    if (n < kprime && c <= cap) return;  // fewer than k' candidates: keep all, threshold stays +inf (uniform per block)
+    const float thr_old = thr[q];
+    if (n < jrank && c <= cap) {  // too few candidates for a threshold: keep all (uniform per block)
+        // ... fine while no threshold was ever applied (every passing row is here); otherwise a prediction starved it
+        // (the host passes jrank == kprime with final, and the re-rank does not need a short buffer sorted)
+        if (final && thr_old < __int_as_float(0x7f800000) && threadIdx.x == 0) atomicOr(&flags[q], 4u);
+        return;
+    }
     const uint32_t s = min(sorted_n[q], n);
     const uint32_t m = n - s;
     uint64_t* mine = cand + (size_t)q * cap;
@@ -1141,12 +1155,13 @@ refine_kernel(uint64_t* cand, uint32_t* cnt, float* thr, uint32_t* flags, uint32
             rank = (e - s) + sorted_count_below(o, s, key, false);
         }
         if (rank < keep) mine[rank] = key;
-        if (rank == kprime - 1) thr[q] = key_dist(key);
+        if (rank == jrank - 1) thr[q] = fminf(thr_old, key_dist(key));
+        if (final && rank == kprime - 1 && !(key_dist(key) <= thr_old)) atomicOr(&flags[q], 4u);
     }
     if (threadIdx.x == 0) {
         cnt[q] = keep;
         sorted_n[q] = keep;
-        if (c > cap) flags[q] |= 1u;
+        if (c > cap) atomicOr(&flags[q], 1u);
     }
 }
 

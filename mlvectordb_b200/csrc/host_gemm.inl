@@ -242,7 +242,7 @@ struct GemmView {
 // rounds, rerank_kernel scores them in the reference's arithmetic and certifies.  hflags[q] != 0 = not certified
 // (or the candidate buffer overflowed): the caller re-runs those queries.  Synchronises `st` once (to read the flags).
 int search_gemm_tier(mlv_index* h, const float* qprep, uint32_t nq, uint32_t k, int passes, const GemmView& view, float* out_d,
-                     int64_t* out_r, int32_t* out_c, cudaStream_t st, std::vector<uint32_t>& hflags) {
+                     int64_t* out_r, int32_t* out_c, cudaStream_t st, std::vector<uint32_t>& hflags, bool predict = false) {
     NvtxRange nvtx_range(passes == GEMM_TIER_F16 ? "gemm tier: fp16 shadow" : (passes == 1 ? "gemm tier: 1xTF32" : "gemm tier: 3xTF32"));
     int rc;
     const uint32_t ld = h->ld;
@@ -306,17 +306,29 @@ int search_gemm_tier(mlv_index* h, const float* qprep, uint32_t nq, uint32_t k, 
     gp.cand_cnt = cnt;
     gp.cap = cap;
 
-    // rounds: the first takes as many rows as a candidate buffer holds (no threshold yet), each
-    // later one (cap - k') / (4 k') times the rows seen so far, so a buffer is expected to stay
-    // at most a quarter full however the thresholds started
+    // Rounds.  Plain rule: the first takes as many rows as a candidate buffer holds (no threshold yet), each later one
+    // (cap - k') / (4 k') times the rows seen so far, so a buffer is expected to stay at most a quarter full however the
+    // thresholds started.  Predicted thresholds (refine_kernel): the first round is two tiles, a round that has seen S of
+    // the N rows thresholds at its j-th best, j = max(32, 4 k' S / N) capped at k' -- about 4 k' rows of the whole
+    // matrix are expected below it, and it is the k'-th best again once a quarter of the rows are seen -- and the next
+    // round takes min(8, (cap - k') / (4 j)) times the rows seen: a 10M-row pass appends ~2,000 candidates per query
+    // in 7 rounds instead of ~5,600 in 9.
     const uint32_t total_tiles = (uint32_t)((view.n_rows + GEMM_BM - 1) / GEMM_BM);
-    const double growth = (double)(cap - kprime) / (4.0 * kprime);
+    predict = predict && passes != 3 && kprime > 32;
+    auto rank_after = [&](uint32_t seen_tiles) -> uint32_t {
+        if (!predict || seen_tiles >= total_tiles) return kprime;
+        const double j = 4.0 * kprime * (double)seen_tiles / (double)total_tiles;
+        return (uint32_t)std::min<double>(kprime, std::max(32.0, std::ceil(j)));
+    };
+    uint32_t jrank = kprime;   // rank of the thresholds in force
     uint32_t seen = 0;
     // a query's buffer is typically a quarter full: 256 threads sort it, and many CTAs share an SM
     const int refine_threads = (int)std::min<uint32_t>(256, std::max<uint32_t>(P / 2, 32));
     while (seen < total_tiles) {
-        uint32_t take = seen == 0 ? std::max<uint32_t>(1, cap / GEMM_BM) : std::max<uint32_t>(1, (uint32_t)(seen * growth));
+        const double growth = std::min(predict ? 8.0 : 1e9, (double)(cap - kprime) / (4.0 * jrank));
+        uint32_t take = seen == 0 ? (predict ? 2u : std::max<uint32_t>(1, cap / GEMM_BM)) : std::max<uint32_t>(1, (uint32_t)(seen * growth));
         take = std::min(take, total_tiles - seen);
+        jrank = rank_after(seen + take);
         gp.row_tile0 = seen;
         gp.row_tile1 = seen + take;
         uint64_t items = (uint64_t)take * gp.n_qtiles;
@@ -347,7 +359,7 @@ int search_gemm_tier(mlv_index* h, const float* qprep, uint32_t nq, uint32_t k, 
                 // thresholds simply carry over: candidate buffers are additive)
                 cudaGetLastError();
                 h->tune_gemm_wide = 0;
-                return search_gemm_tier(h, qprep, nq, k, passes, view, out_d, out_r, out_c, st, hflags);
+                return search_gemm_tier(h, qprep, nq, k, passes, view, out_d, out_r, out_c, st, hflags, predict);
             }
         } else if (wide_cl)
             CK(h, l2 ? launch_gemm2<METRIC_L2>(mx, mqh, gp, grid, st, passes, wide_cl) : launch_gemm2<METRIC_IP>(mx, mqh, gp, grid, st, passes, wide_cl));
@@ -358,7 +370,8 @@ int search_gemm_tier(mlv_index* h, const float* qprep, uint32_t nq, uint32_t k, 
             cudaEventRecord(e1, st);
             h->gemm_pending.emplace_back(e0, e1);
         }
-        refine_kernel<<<nq, refine_threads, (size_t)(P + kprime) * 8, st>>>(cand, cnt, thr, flags, sorted_n, cap, P, kprime);
+        refine_kernel<<<nq, refine_threads, (size_t)(P + kprime) * 8, st>>>(cand, cnt, thr, flags, sorted_n, cap, P, kprime, jrank,
+                                                                            seen + take >= total_tiles ? 1 : 0);
         CK(h, cudaGetLastError());
         h->launches += 2;
         h->gemm_launches++;
@@ -524,13 +537,33 @@ int search_gemm(mlv_index* h, const float* qprep, uint32_t nq, uint32_t k, const
             first_tier = GEMM_TIER_F16;
         }
     }
-    if ((rc = search_gemm_tier(h, qprep, nq, k, first_tier, view, out_d, out_r, out_c, st, hflags)) != MLV_OK) return rc;
+    // predicted thresholds for the one-pass tier (not while they sit out after failing; a forced tier without a tier
+    // behind it keeps the plain rule, or a misprediction would send the query to the scan)
+    bool predict = fast && h->tune_gemm_predict != 0 && h->tune_gemm_passes == 0;
+    if (predict && h->gemm_predict_skip > 0) {
+        h->gemm_predict_skip--;
+        predict = false;
+    }
+    if ((rc = search_gemm_tier(h, qprep, nq, k, first_tier, view, out_d, out_r, out_c, st, hflags, predict)) != MLV_OK) return rc;
+    size_t mispredicted = 0;
     for (uint32_t q = 0; q < nq; q++)
-        if (hflags[q]) failing.push_back(q);
+        if (hflags[q]) {
+            failing.push_back(q);
+            mispredicted += (hflags[q] & 4u) ? 1 : 0;
+        }
+    if (predict) {
+        h->gemm_mispredicted_queries += mispredicted;
+        if (mispredicted * 8 > nq) {   // the rows' order correlates with the queries: the plain rule for 8, 16, ... batches
+            h->gemm_predict_backoff = std::min<uint32_t>(std::max<uint32_t>(8, h->gemm_predict_backoff * 2), 1u << 14);
+            h->gemm_predict_skip = h->gemm_predict_backoff;
+        } else {
+            h->gemm_predict_backoff = 0;
+        }
+    }
     if (fast) {
         h->gemm_fast_queries += nq - failing.size();
         if (first_tier == GEMM_TIER_F16) h->gemm_half_queries += nq - failing.size();
-        if (h->tune_gemm_passes == 0 && failing.size() * 2 > nq && !h->f16_overflowed) h->gemm_fast_skip = 8;
+        if (h->tune_gemm_passes == 0 && (failing.size() - mispredicted) * 2 > nq && !h->f16_overflowed) h->gemm_fast_skip = 8;
         h->f16_overflowed = false;   // an overflowed shadow says nothing about the data's neighbourhoods: no sitting out
         if (!failing.empty() && h->tune_gemm_passes != 1 && h->tune_gemm_passes != GEMM_TIER_F16) {
             // second tier on the compacted failing queries; results scattered back to their slots

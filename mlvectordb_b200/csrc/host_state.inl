@@ -131,6 +131,9 @@ struct mlv_index {
     uint64_t gemm_fast_queries = 0;  // queries certified by the one-pass tier
     uint64_t gemm_gathered_searches = 0;  // filtered batches that multiplied a compacted copy of the passing rows
     uint32_t gemm_fast_skip = 0;     // batches the one-pass tier sits out (it certified too little last time)
+    int tune_gemm_predict = 1;       // one-pass tiers: thresholds predicted from the rows seen so far (refine_kernel); 0 = the plain k'-th-best rule
+    uint32_t gemm_predict_skip = 0, gemm_predict_backoff = 0;   // batches predictions sit out after failing (rows stored in an order that correlates with the queries); doubles per failure
+    uint64_t gemm_mispredicted_queries = 0;   // queries whose predicted thresholds failed the final check (answered by the next tier)
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> gemm_pending;
     uint64_t gemm_searches = 0, gemm_queries = 0, gemm_fallback_queries = 0, gemm_rounds = 0, gemm_launches = 0;
     // columnar metadata (column_kernels.cuh): int32 code columns, allocated on first use

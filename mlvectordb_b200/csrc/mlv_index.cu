@@ -113,6 +113,7 @@ int mlv_index_create(uint32_t dim, int metric, uint64_t capacity_hint, int devic
     h->tune_gemm_passes = env_int("MLV_GEMM_PASSES", h->tune_gemm_passes);
     h->tune_gemm_wide = env_int("MLV_GEMM_WIDE", h->tune_gemm_wide);
     h->tune_gemm_debug = env_int("MLV_GEMM_DEBUG", h->tune_gemm_debug);
+    h->tune_gemm_predict = env_int("MLV_GEMM_PREDICT", h->tune_gemm_predict);
     DeviceGuard g(device);
     cudaDeviceProp prop;
     cudaError_t e = g.ok ? cudaGetDeviceProperties(&prop, device) : cudaErrorInvalidDevice;
@@ -206,6 +207,10 @@ int mlv_index_set_tuning(mlv_index_t h, const char* key, int value) {
     else if (k == "fast_host") h->tune_fast_host = value;
     else if (k == "gemm_wide") h->tune_gemm_wide = value;
     else if (k == "gemm_debug") h->tune_gemm_debug = value;
+    else if (k == "gemm_predict") {
+        h->tune_gemm_predict = value;
+        h->gemm_predict_skip = h->gemm_predict_backoff = 0;
+    }
     else return fail(h, MLV_E_INVALID, "unknown tuning key " + k);
     return MLV_OK;
 }
@@ -1265,6 +1270,7 @@ int mlv_index_gemm_stats(mlv_index_t h, mlv_gemm_stats_t* out) {
     out->fallback_queries = h->gemm_fallback_queries;
     out->fast_queries = h->gemm_fast_queries;
     out->half_queries = h->gemm_half_queries;
+    out->mispredicted_queries = h->gemm_mispredicted_queries;
     out->gathered_searches = h->gemm_gathered_searches;
     out->rounds = h->gemm_rounds;
     return MLV_OK;

@@ -3,7 +3,7 @@
 For --seconds S it draws random shapes (rows, dim, metric, k, batch width, tombstones, filters) and checks that
 every way the library can answer the same question returns the same BITS as the exact scan:
 
-  * tensor-core path in a random tier / kernel configuration (gemm_passes 0-3, gemm_wide 0-3) == scan path
+  * tensor-core path in a random tier / kernel configuration (gemm_passes 0-3, gemm_wide 0-3, gemm_predict 0/1) == scan path
   * one-launch latency path (single query) == staged path == row of a batch
   * gathered filter == stream + mask filter == per-call bitmap
   * range search at the k-th distance contains the kNN answer
@@ -76,6 +76,7 @@ while time.time() < t_end:
             passes, wide = int(rng.integers(0, 4)), int(rng.integers(0, 4))
             s.set_tuning("gemm_passes", passes)
             s.set_tuning("gemm_wide", wide)
+            s.set_tuning("gemm_predict", int(rng.integers(0, 2)))
             got = s.search(Q, k, filt)
             if not same(got, ref):
                 fail("tensor-core path != scan", passes=passes, wide=wide, filtered=filt is not None, **ctx)

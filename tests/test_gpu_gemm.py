@@ -153,6 +153,65 @@ def test_adversarial_row_order_falls_back_to_the_scan():
     s.close()
 
 
+def _counted(s, Q, k):
+    before = s.gemm_stats()
+    got = s.search(Q, k)
+    after = s.gemm_stats()
+    return got, {f: after[f] - before[f] for f in after if f != "gemm_ms"}
+
+
+def test_predicted_thresholds_equal_the_plain_rule_in_fewer_rounds():
+    """set_tuning("gemm_predict"): thresholds predicted from the rows seen so far append fewer candidates in fewer
+    rounds; the answers are those of the plain k'-th-best rule and of the scan, bit for bit, and on rows in random
+    order no prediction fails."""
+    n, dim, nq, k = 400_000, 128, 512, 10
+    s = _shard(dim, "l2", capacity=n)
+    s.add_synthetic(77, 0, n, scaled=True)
+    Q = synthetic.queries(78, nq, dim)
+    s.mark_deleted(np.arange(0, n, 9, dtype=np.uint64))
+    s.set_tuning("gemm", 0)
+    ref = s.search(Q, k)
+    s.set_tuning("gemm", 1)
+    seen = {}
+    for predict in (0, 1):
+        s.set_tuning("gemm_predict", predict)
+        got, d = _counted(s, Q, k)
+        assert all(np.array_equal(a, b, equal_nan=True) for a, b in zip(got, ref)), f"gemm_predict={predict}"
+        assert d["mispredicted_queries"] == 0 and d["half_queries"] >= nq * 9 // 10, d
+        seen[predict] = d
+    assert seen[1]["rounds"] < seen[0]["rounds"], seen
+    assert seen[1]["fallback_queries"] == seen[0]["fallback_queries"]
+    s.close()
+
+
+def test_mispredicted_thresholds_are_caught_and_back_off():
+    """Rows stored nearest-first around the queries' centre: the first tiles promise far more close rows than the matrix
+    holds, the predicted thresholds starve the candidate buffers, the last round's check catches it (the next tier
+    answers those queries) and predictions sit out 8, then 16 batches.  Answers stay the scan's bit for bit."""
+    n, dim, nq, k = 150_000, 64, 256, 10
+    rng = np.random.default_rng(12)
+    X = synthetic.rows(61, 0, n, dim)
+    c = synthetic.queries(61, 1, dim)[0]
+    X = np.ascontiguousarray(X[np.argsort(((X - c) ** 2).sum(1), kind="stable")])
+    Q = (c + 0.02 * rng.standard_normal((nq, dim))).astype(np.float32)
+    s = _shard(dim, "l2")
+    s.add(X)
+    s.set_tuning("gemm", 0)
+    ref = s.search(Q, k)
+    s.set_tuning("gemm", 1)
+    missed = []
+    for _ in range(11):
+        got, d = _counted(s, Q, k)
+        assert all(np.array_equal(a, b, equal_nan=True) for a, b in zip(got, ref))
+        missed.append(d["mispredicted_queries"])
+        if d["mispredicted_queries"] == 0:
+            assert d["half_queries"] >= nq * 9 // 10, d       # the plain rule certifies them on the fp16 tier
+    assert missed[0] > nq // 8 and missed[9] > nq // 8, missed
+    assert sum(1 for m in missed if m) == 2, missed           # batches 1-8 sat out, batch 10 sits out again (16)
+    _assert_oracle((got[0][:3], got[1][:3], got[2][:3]), X, Q[:3], k, "l2")
+    s.close()
+
+
 def test_large_batch_on_device_generated_rows():
     """200k x 768 generated on the device, 512 queries: the batch path equals the scan path bit for bit."""
     n, dim, nq = 200_000, 768, 512
