@@ -189,15 +189,33 @@ __device__ __forceinline__ void tmem_ld32_issue(uint32_t taddr, uint32_t (&v)[32
         : "memory");
 }
 
+// One column of the warp's 32 lanes (collective), waited for: the hit path re-reads the few values that passed the pre-test
+// instead of keeping the chunk's 32 registers addressable by a run-time index.  The wait also completes any chunk load
+// in flight, which is harmless (its own wait then returns at once).
+__device__ __forceinline__ uint32_t tmem_ld1_wait(uint32_t taddr) {
+    uint32_t v;
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];\n\t"
+        "tcgen05.wait::ld.sync.aligned;"
+        : "=r"(v)
+        : "r"(taddr)
+        : "memory");
+    return v;
+}
+
 // ---- epilogue pieces shared by both GEMM kernels ---------------------------------------------------------------------
-// Per query: the threshold test a <= thr solved for the raw accumulator value v (dot = us * v):
-//   l2      xn + qn - 2 us v <= thr   <=>   v - xn c2 >= c1,   c2 = 1 / (2 us),  c1 = (qn - thr) c2
-//   ip      1 - us v <= thr           <=>   v >= c1,           c1 = (1 - thr) / us
-// so a value costs one FFMA + one compare (ip: one compare) instead of three shared-memory loads and five operations.
-// The pre-test constants are RELAXED by 2^-19 of the magnitudes involved (16x the rounding of either form), so the
-// pre-test never rejects a value the exact test would accept; the rare 32-column chunks with a hit are re-examined with
-// the exact test -- the candidate sets are those of the plain loop, bit for bit.  Called by the 128 threads
-// (et = 0..127) that are about to drain a tile of query tile qt; the caller synchronises them afterwards.
+// Per query: the threshold test a <= thr solved so that a value costs ONE FFMA and half a three-input max
+// (dot = us * v, us the power-of-two unscale of the fp16 tier, 1 otherwise):
+//   l2      xn + qn - 2 us v <= thr   <=>   u = v d + e >= xn,   d = 2 us,  e = thr - qn
+//   ip      1 - us v <= thr           <=>   u = v d + e >= 0,    d = us,    e = thr - 1
+// A lane keeps the running max of u over a 32-column chunk and compares it ONCE with its row's right-hand side; only a
+// warp with a passing lane goes on to find the columns.  The chip runs this kernel at its power limit (1000 W, SM
+// clocks ~1.35-1.5 GHz; scripts/drain_diag.py), where the epilogue's instructions cost throughput even though they
+// overlap the MMAs in time: the previous form (FFMA + FSETP + SEL + LOP3 per value) was 2.3 of 20.7 ms.
+// The pre-test is RELAXED by 2^-19 of the magnitudes involved (e upwards, the row's side downwards: 8x the rounding of
+// either form), so it never rejects a value the exact test (gemm_hit) would accept -- the candidate sets are those of
+// the plain loop, bit for bit.  Called by the 128 threads (et = 0..127) that are about to drain a tile of query tile
+// qt; the caller synchronises them afterwards.  c1_s = e, c2_s = d (d is not read where it is the constant 1 or 2).
 template <int METRIC, bool F16, int BN>
 __device__ __forceinline__ void epilogue_constants(const GemmParams& p, uint32_t qt, int et, float* thr_s, float* qn_s, float* us_s,
                                                    float* c1_s, float* c2_s) {
@@ -208,17 +226,23 @@ __device__ __forceinline__ void epilogue_constants(const GemmParams& p, uint32_t
         thr_s[i] = thr;
         qn_s[i] = qn;
         if (F16) us_s[i] = us;
-        const bool fin = fabsf(thr) <= 3.0e38f;
+        const bool fin = fabsf(thr) <= 3.0e38f;   // +inf = no threshold yet, -inf = padding query: nothing to relax
         if (METRIC == METRIC_L2) {
-            const float c2 = 0.5f / us;
-            const float c1 = (qn - thr) * c2;
-            c2_s[i] = c2 * (1.0f - 1.9073486328125e-6f);
-            c1_s[i] = fin ? c1 - 1.9073486328125e-6f * c2 * (qn + fabsf(thr)) : c1;
+            const float e = thr - qn;
+            c1_s[i] = fin ? e + 1.9073486328125e-6f * (qn + fabsf(thr)) : e;
+            if (F16) c2_s[i] = 2.0f * us;
         } else {
-            const float c1 = (1.0f - thr) / us;
-            c1_s[i] = fin ? c1 - 1.9073486328125e-6f * (1.0f + fabsf(thr)) / us : c1;
+            const float e = thr - 1.0f;
+            c1_s[i] = fin ? e + 1.9073486328125e-6f * (1.0f + fabsf(thr)) : e;
+            if (F16) c2_s[i] = us;
         }
     }
+}
+
+__device__ __forceinline__ float fmax3(float a, float b, float c) {
+    float r;
+    asm("max.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));   // FMNMX3; a NaN operand is ignored
+    return r;
 }
 
 // One thread = one row (TMEM lane) of a 128 x BN accumulator at taddr0: BN values, 32 per tcgen05.ld, two register
@@ -241,7 +265,7 @@ __device__ __forceinline__ void hitq_flush(const GemmParams& p, HitQueue* hq, in
 }
 
 template <int METRIC, bool F16>
-__device__ __noinline__ void gemm_hit(HitQueue* hq, const float* thr_s, const float* qn_s, const float* us_s, float vj, uint32_t ql, float xn,
+__device__ __forceinline__ void gemm_hit(HitQueue* hq, const float* thr_s, const float* qn_s, const float* us_s, float vj, uint32_t ql, float xn,
                                       uint32_t row, uint32_t qbase) {
     const float dot = F16 ? vj * us_s[ql] : vj;
     const float a = (METRIC == METRIC_L2) ? fmaf(-2.0f, dot, xn + qn_s[ql]) : 1.0f - dot;
@@ -265,40 +289,52 @@ __device__ __forceinline__ void epilogue_drain(const GemmParams& p, uint32_t tad
                                                const float* thr_s, const float* qn_s, const float* us_s, const float* c1_s,
                                                const float* c2_s, HitQueue* hq, uint32_t c_begin = 0, uint32_t c_end = BN / 32) {
     const int lane = threadIdx.x & 31;
-    const float nxn = -xn;
-    // A value that passes the relaxed pre-test is examined with the exact test by gemm_hit -- OUT OF LINE: 64 inlined copies
-    // of the hit path made the drain loop several times larger than the instruction cache likes, and the rarely taken
-    // code slowed the always-taken code down.
+    // the row's side of the pre-test; NaN for a row that takes no part (tombstoned, filtered out, beyond the matrix or
+    // the round): every comparison with it is false
+    const float xr = !row_ok ? __int_as_float(0x7fc00000) : (METRIC == METRIC_L2 ? xn * (1.0f - 1.9073486328125e-6f) : 0.0f);
+    // A value that passes the relaxed pre-test is examined with the exact test by gemm_hit.  About one value in a
+    // thousand does, i.e. many 32 x 32 warp chunks hold one: walking a lane's 32 registers for its set bits (an unrolled
+    // chain of 32 predicated calls -- registers cannot be indexed at run time) cost ~200 issue slots per hit, 4.3 of
+    // 24.7 ms on 4M x 768 x 4096 (profiles/r02_drain_diag.jsonl).  Instead the warp walks the UNION of its lanes' bits and
+    // re-reads each such column from TMEM (one collective single-column tcgen05.ld): a handful of instructions per hit.
     auto hit = [&](float vj, uint32_t ql) { gemm_hit<METRIC, F16>(hq, thr_s, qn_s, us_s, vj, ql, xn, row, qt * BN); };
+    auto u_of = [&](uint32_t bits, float d, float e) -> float {
+        const float v = __uint_as_float(bits);
+        if (F16) return fmaf(v, d, e);
+        return METRIC == METRIC_L2 ? fmaf(v, 2.0f, e) : v + e;
+    };
+    const bool drain_off = p.debug & 1;   // profiling: TMEM loads only
     auto process = [&](const uint32_t(&v)[32], uint32_t c) {
-        if (!row_ok) return;
-        const float4* k1 = reinterpret_cast<const float4*>(c1_s + c * 32);
-        const float4* k2 = reinterpret_cast<const float4*>(c2_s + c * 32);
-        // branch-free pre-test: one bit per column (a compare and a predicated OR per value); the chunk's hits -- none in
-        // most chunks of most lanes -- are then walked bit by bit
+        if (drain_off) return;
+        const float4* ke = reinterpret_cast<const float4*>(c1_s + c * 32);
+        const float4* kd = reinterpret_cast<const float4*>(c2_s + c * 32);
+        float mx = __int_as_float(0xff800000);
+#pragma unroll
+        for (int j4 = 0; j4 < 8; j4++) {
+            const float4 e = ke[j4];
+            const float4 d = F16 ? kd[j4] : make_float4(0.f, 0.f, 0.f, 0.f);
+            mx = fmax3(mx, u_of(v[4 * j4], d.x, e.x), u_of(v[4 * j4 + 1], d.y, e.y));
+            mx = fmax3(mx, u_of(v[4 * j4 + 2], d.z, e.z), u_of(v[4 * j4 + 3], d.w, e.w));
+        }
+        if (!__any_sync(0xffffffffu, mx >= xr)) return;   // warp-uniform
+        // some lane holds a value that passes: one bit per column (the same arithmetic as above, so the same verdicts)
         uint32_t m = 0;
 #pragma unroll
         for (int j4 = 0; j4 < 8; j4++) {
-            const float4 a1 = k1[j4];
-            const float v0 = __uint_as_float(v[4 * j4]), v1 = __uint_as_float(v[4 * j4 + 1]);
-            const float v2 = __uint_as_float(v[4 * j4 + 2]), v3 = __uint_as_float(v[4 * j4 + 3]);
-            if (METRIC == METRIC_L2) {
-                const float4 a2 = k2[j4];
-                m |= fmaf(nxn, a2.x, v0) >= a1.x ? 1u << (4 * j4) : 0u;
-                m |= fmaf(nxn, a2.y, v1) >= a1.y ? 2u << (4 * j4) : 0u;
-                m |= fmaf(nxn, a2.z, v2) >= a1.z ? 4u << (4 * j4) : 0u;
-                m |= fmaf(nxn, a2.w, v3) >= a1.w ? 8u << (4 * j4) : 0u;
-            } else {
-                m |= v0 >= a1.x ? 1u << (4 * j4) : 0u;
-                m |= v1 >= a1.y ? 2u << (4 * j4) : 0u;
-                m |= v2 >= a1.z ? 4u << (4 * j4) : 0u;
-                m |= v3 >= a1.w ? 8u << (4 * j4) : 0u;
-            }
+            const float4 e = ke[j4];
+            const float4 d = F16 ? kd[j4] : make_float4(0.f, 0.f, 0.f, 0.f);
+            m |= u_of(v[4 * j4], d.x, e.x) >= xr ? 1u << (4 * j4) : 0u;
+            m |= u_of(v[4 * j4 + 1], d.y, e.y) >= xr ? 2u << (4 * j4) : 0u;
+            m |= u_of(v[4 * j4 + 2], d.z, e.z) >= xr ? 4u << (4 * j4) : 0u;
+            m |= u_of(v[4 * j4 + 3], d.w, e.w) >= xr ? 8u << (4 * j4) : 0u;
         }
-        if (m == 0) return;
-#pragma unroll
-        for (int j = 0; j < 32; j++)   // fully unrolled: v[] must stay in registers
-            if (m & (1u << j)) hit(__uint_as_float(v[j]), c * 32 + j);
+        uint32_t rest = __reduce_or_sync(0xffffffffu, m);   // warp-uniform
+        while (rest) {
+            const uint32_t j = (uint32_t)__ffs((int)rest) - 1u;
+            rest &= rest - 1u;
+            const float vj = __uint_as_float(tmem_ld1_wait(taddr0 + c * 32 + j));
+            if ((m >> j) & 1u) hit(vj, c * 32 + j);
+        }
     };
     uint32_t va[32], vb[32];
     tmem_ld32_issue(taddr0 + c_begin * 32, va);

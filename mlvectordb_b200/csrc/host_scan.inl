@@ -237,6 +237,7 @@ struct FilterPlan {
     const uint32_t* bitmap = nullptr;      // stream + mask
     const uint32_t* gather = nullptr;      // row list (live AND passing)
     const uint32_t* n_rows_dev = nullptr;  // its length (device)
+    uint64_t n_rows_host = 0;              // ... when the host has read it back (prepared filters), else 0
 };
 
 // filter_dev: per-call bitmap (ceil(rows/32) words) or null; a bound prepared filter applies when it is null.
@@ -263,6 +264,7 @@ int plan_filter(mlv_index* h, Lane* ln, const uint32_t* filter_dev, cudaStream_t
         }
         out->gather = (const uint32_t*)f->d_list.p;
         out->n_rows_dev = (const uint32_t*)f->d_scratch.p;  // low word of the u64 total
+        if (f->counted) out->n_rows_host = f->passing;
         return MLV_OK;
     }
     if (h->tune_gather == 0 && !want_list) {
@@ -283,11 +285,13 @@ int ensure_sched(mlv_index* h, Lane* ln) {
     return MLV_OK;
 }
 
-void fill_sched(mlv_index* h, Lane* ln, ScanParams& p) {
+void fill_sched(mlv_index* h, Lane* ln, ScanParams& p, uint64_t gathered_rows = 0) {
     p.sched = h->tune_dynamic ? (uint32_t*)ln->d_sched.p : nullptr;
-    // several tiles per claim only when there are plenty of claims per SM
+    // several tiles per claim only when there are plenty of claims per SM (a gathered scan walks the list's tiles, not
+    // the matrix's: 1 % of 10M x 384 is 21 tiles per SM, and claims of four left SMs idle for the last ~3 us of 50)
     uint32_t batch = (uint32_t)std::max(h->tune_tile_batch, 1);
-    while (batch > 1 && (uint64_t)p.n_tiles < 16ull * batch * (uint64_t)h->sm_count) batch >>= 1;
+    const uint64_t tiles = (p.gather && gathered_rows) ? (gathered_rows + p.tile_rows - 1) / p.tile_rows : (p.gather ? 0 : p.n_tiles);
+    while (batch > 1 && tiles < 16ull * batch * (uint64_t)h->sm_count) batch >>= 1;
     p.tile_batch = batch;
 }
 
@@ -340,7 +344,7 @@ ScanParams scan_params(mlv_index* h, const ScanCfg& c, const FilterPlan& fp, Lan
     p.gather = fp.gather;
     p.n_rows_dev = fp.n_rows_dev;
     p.evict_first = c.evict_first;
-    fill_sched(h, ln, p);
+    fill_sched(h, ln, p, fp.n_rows_host);
     return p;
 }
 
