@@ -57,17 +57,14 @@ constexpr uint32_t GEMM_X_BYTES = GEMM_BM * GEMM_BK * 4;   // 16 KB
 // TF32, rounded to nearest instead of truncated, so its approximate distances are TWICE as tight as PASSES = 1's; its
 // 5-bit exponent is dealt with by power-of-two scales (one per matrix, one per query) that the epilogue divides out
 // exactly.  A K chunk is 64 halves (one 128-byte swizzle row), tiles are the same 16 KB / BN * 128 B.
-// per-warp queue of candidate hits (see hitq_flush below)
-constexpr uint32_t HITQ_CAP = 64;
-struct HitQueue {            // one per epilogue warp
-    uint64_t key[HITQ_CAP];
-    uint32_t q[HITQ_CAP];
-    uint32_t count;
-    uint32_t cap;            // the candidate buffers (copied from GemmParams so the out-of-line hit path needs no kernel parameters)
-    uint64_t* cand;
-    uint32_t* cand_cnt;
-    int direct;              // profiling (gemm_debug bit 1): append straight to the buffers, no queue
-    uint32_t pad[9];
+// per-warp queue of candidate hits (see hitq_flush below): CAP entries, filled and flushed by its warp alone.  The hits
+// of one column (= one query) enter together as a GROUP; fc[e] = first entry of e's group << 16 | the group's size.
+template <uint32_t CAP>
+struct HitQueue {
+    uint64_t key[CAP];
+    uint32_t q[CAP];
+    uint32_t fc[CAP];
+    uint32_t gbase[CAP];   // slot the group's first hit got in its query's candidate buffer (indexed by the first entry)
 };
 constexpr int GEMM_TIER_F16 = 2;
 template <int BN, int PASSES = 3>
@@ -75,7 +72,8 @@ struct GemmShape {
     static constexpr uint32_t Q_BYTES = BN * GEMM_BK * 4;
     static constexpr uint32_t STAGE_BYTES = PASSES == 3 ? 2 * GEMM_X_BYTES + 2 * Q_BYTES : GEMM_X_BYTES + Q_BYTES;
     static constexpr int STAGES = PASSES == 3 ? (BN == 256 ? 2 : (BN == 128 ? 3 : 4)) : (BN == 256 ? 4 : 6);
-    static constexpr uint32_t SMEM_BYTES = 1024 + STAGES * STAGE_BYTES + 5 * BN * 4 + 256 + 4 * sizeof(HitQueue);
+    static constexpr uint32_t HITQ = 256;   // queue entries per epilogue warp (4 warps x 5 KB)
+    static constexpr uint32_t SMEM_BYTES = 1024 + STAGES * STAGE_BYTES + 5 * BN * 4 + 256 + 4 * sizeof(HitQueue<HITQ>);
     // fp32 accumulate, A and B K-major, M = 128, N = BN; operand format TF32 (kind::tf32) or F16 (kind::f16)
     static constexpr uint32_t FMT = PASSES == GEMM_TIER_F16 ? 0u : 2u;
     static constexpr uint32_t IDESC = (1u << 4) | (FMT << 7) | (FMT << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(GEMM_BM >> 4) << 24);
@@ -213,7 +211,7 @@ __device__ __forceinline__ uint32_t tmem_ld1_wait(uint32_t taddr) {
 // clocks ~1.35-1.5 GHz; scripts/drain_diag.py), where the epilogue's instructions cost throughput even though they
 // overlap the MMAs in time: the previous form (FFMA + FSETP + SEL + LOP3 per value) was 2.3 of 20.7 ms.
 // The pre-test is RELAXED by 2^-19 of the magnitudes involved (e upwards, the row's side downwards: 8x the rounding of
-// either form), so it never rejects a value the exact test (gemm_hit) would accept -- the candidate sets are those of
+// either form), so it never rejects a value the exact test (epilogue_drain) would accept -- the candidate sets are those of
 // the plain loop, bit for bit.  Called by the 128 threads (et = 0..127) that are about to drain a tile of query tile
 // qt; the caller synchronises them afterwards.  c1_s = e, c2_s = d (d is not read where it is the constant 1 or 2).
 template <int METRIC, bool F16, int BN>
@@ -247,57 +245,46 @@ __device__ __forceinline__ float fmax3(float a, float b, float c) {
 
 // One thread = one row (TMEM lane) of a 128 x BN accumulator at taddr0: BN values, 32 per tcgen05.ld, two register
 // buffers so the load of chunk c + 1 is in flight while chunk c is tested.
-// Hits are queued per warp in shared memory and appended to the queries' candidate buffers 32 at a time: an append needs
-// the value its global atomicAdd returns, and waiting ~1000 cycles for that once per hit -- with thresholds that only tighten
-// between rounds about one value in a thousand is a hit, i.e. one per 32 x 32 chunk -- made the drain 2-3x longer than the
-// tile's MMAs.  One stall per 32 hits instead.
-__device__ __forceinline__ void hitq_flush(const GemmParams& p, HitQueue* hq, int lane) {
+// Hits are queued per warp in shared memory and appended to the queries' candidate buffers a queue at a time: an append
+// needs the value its global atomicAdd returns, and waiting ~1000 cycles for that once per hit made the drain 2-3x longer
+// than the tile's MMAs.  The queue belongs to its warp alone and the hits of one column are found together (a ballot),
+// so the fill count is a warp-uniform REGISTER (no shared-memory atomics) and a column's hits reserve their slots with
+// ONE atomicAdd of their number: in the first rounds of a batch (no thresholds yet) every row is a hit, and 32 lanes
+// adding 1 to the same counter were serialised by the memory system at ~60 ns each -- 2 us per column, 250 us for a
+// single tile (scripts/dense_probe.py).
+template <uint32_t CAP>
+__device__ __forceinline__ void hitq_flush(const GemmParams& p, HitQueue<CAP>* hq, uint32_t n, int lane) {
     __syncwarp();
-    const uint32_t n = min(hq->count, HITQ_CAP);
+#pragma unroll 4
     for (uint32_t i = (uint32_t)lane; i < n; i += 32) {
-        const uint32_t qg = hq->q[i];
-        const uint32_t pos = atomicAdd(p.cand_cnt + qg, 1u);
-        if (pos < p.cap) p.cand[(size_t)qg * p.cap + pos] = hq->key[i];
+        const uint32_t fc = hq->fc[i];
+        if ((fc >> 16) == i) hq->gbase[i] = atomicAdd(p.cand_cnt + hq->q[i], fc & 0xffffu);
     }
     __syncwarp();
-    if (lane == 0) hq->count = 0;
+#pragma unroll 4
+    for (uint32_t i = (uint32_t)lane; i < n; i += 32) {
+        const uint32_t first = hq->fc[i] >> 16;
+        const uint32_t pos = hq->gbase[first] + (i - first);
+        if (pos < p.cap) p.cand[(size_t)hq->q[i] * p.cap + pos] = hq->key[i];
+    }
     __syncwarp();
 }
 
-template <int METRIC, bool F16>
-__device__ __forceinline__ void gemm_hit(HitQueue* hq, const float* thr_s, const float* qn_s, const float* us_s, float vj, uint32_t ql, float xn,
-                                      uint32_t row, uint32_t qbase) {
-    const float dot = F16 ? vj * us_s[ql] : vj;
-    const float a = (METRIC == METRIC_L2) ? fmaf(-2.0f, dot, xn + qn_s[ql]) : 1.0f - dot;
-    if (!(a <= thr_s[ql])) return;
-    const uint32_t qg = qbase + ql;
-    if (!hq->direct) {
-        const uint32_t slot = atomicAdd(&hq->count, 1u);
-        if (slot < HITQ_CAP) {
-            hq->key[slot] = make_key(a, row);
-            hq->q[slot] = qg;
-            return;
-        }
-    }
-    // queue full (a burst: the first round has no thresholds yet): straight to the buffer
-    const uint32_t pos = atomicAdd(hq->cand_cnt + qg, 1u);
-    if (pos < hq->cap) hq->cand[(size_t)qg * hq->cap + pos] = make_key(a, row);
-}
-
-template <int METRIC, bool F16, int BN>
+template <int METRIC, bool F16, int BN, uint32_t QCAP>
 __device__ __forceinline__ void epilogue_drain(const GemmParams& p, uint32_t taddr0, uint32_t qt, uint32_t row, bool row_ok, float xn,
                                                const float* thr_s, const float* qn_s, const float* us_s, const float* c1_s,
-                                               const float* c2_s, HitQueue* hq, uint32_t c_begin = 0, uint32_t c_end = BN / 32) {
+                                               const float* c2_s, HitQueue<QCAP>* hq, uint32_t c_begin = 0, uint32_t c_end = BN / 32) {
     const int lane = threadIdx.x & 31;
     // the row's side of the pre-test; NaN for a row that takes no part (tombstoned, filtered out, beyond the matrix or
     // the round): every comparison with it is false
     const float xr = !row_ok ? __int_as_float(0x7fc00000) : (METRIC == METRIC_L2 ? xn * (1.0f - 1.9073486328125e-6f) : 0.0f);
-    // A value that passes the relaxed pre-test is examined with the exact test by gemm_hit.  About one value in a
+    // A value that passes the relaxed pre-test is examined with the exact test below.  About one value in a
     // thousand does, i.e. many 32 x 32 warp chunks hold one: walking a lane's 32 registers for its set bits (an unrolled
     // chain of 32 predicated calls -- registers cannot be indexed at run time) cost ~200 issue slots per hit, 4.3 of
     // 24.7 ms on 4M x 768 x 4096 (profiles/r02_drain_diag.jsonl).  Instead the warp walks the UNION of its lanes' bits and
     // re-reads each such column from TMEM (one collective single-column tcgen05.ld): a handful of instructions per hit.
-    auto hit = [&](float vj, uint32_t ql) { gemm_hit<METRIC, F16>(hq, thr_s, qn_s, us_s, vj, ql, xn, row, qt * BN); };
+    uint32_t queued = 0;   // entries in this warp's queue (warp-uniform)
+    const uint32_t lt_mask = (1u << lane) - 1u;
     auto u_of = [&](uint32_t bits, float d, float e) -> float {
         const float v = __uint_as_float(bits);
         if (F16) return fmaf(v, d, e);
@@ -332,8 +319,26 @@ __device__ __forceinline__ void epilogue_drain(const GemmParams& p, uint32_t tad
         while (rest) {
             const uint32_t j = (uint32_t)__ffs((int)rest) - 1u;
             rest &= rest - 1u;
-            const float vj = __uint_as_float(tmem_ld1_wait(taddr0 + c * 32 + j));
-            if ((m >> j) & 1u) hit(vj, c * 32 + j);
+            const uint32_t ql = c * 32 + j;
+            const float vj = __uint_as_float(tmem_ld1_wait(taddr0 + ql));
+            // the exact test, in the arithmetic the thresholds were made in
+            const float dot = F16 ? vj * us_s[ql] : vj;
+            const float a = (METRIC == METRIC_L2) ? fmaf(-2.0f, dot, xn + qn_s[ql]) : 1.0f - dot;
+            const bool h = ((m >> j) & 1u) && (a <= thr_s[ql]);
+            const uint32_t hb = __ballot_sync(0xffffffffu, h);
+            if (hb == 0) continue;
+            if (queued + 32 > QCAP) {
+                hitq_flush<QCAP>(p, hq, queued, lane);
+                queued = 0;
+            }
+            const uint32_t nh = (uint32_t)__popc(hb);
+            if (h) {
+                const uint32_t slot = queued + __popc(hb & lt_mask);
+                hq->key[slot] = make_key(a, row);
+                hq->q[slot] = qt * BN + ql;
+                hq->fc[slot] = (queued << 16) | nh;
+            }
+            queued += nh;
         }
     };
     uint32_t va[32], vb[32];
@@ -345,11 +350,8 @@ __device__ __forceinline__ void epilogue_drain(const GemmParams& p, uint32_t tad
         tmem_ld_wait(vb);
         if (c + 2 < c_end) tmem_ld32_issue(taddr0 + (c + 2) * 32, va);
         process(vb, c + 1);
-        __syncwarp();
-        if (hq->count >= 32) hitq_flush(p, hq, lane);   // warp-uniform: every lane reads the same word after the syncwarp
     }
-    __syncwarp();
-    if (hq->count) hitq_flush(p, hq, lane);
+    if (queued) hitq_flush<QCAP>(p, hq, queued, lane);
 }
 
 // ---- the GEMM + candidate-selection kernel ---------------------------------------------------
@@ -380,7 +382,8 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
     uint64_t* tfull = bars + 3 * GEMM_STAGES;   // [2]  accumulator complete
     uint64_t* tempty = tfull + 2;               // [2]  accumulator drained
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
-    HitQueue* hqs = reinterpret_cast<HitQueue*>(reinterpret_cast<unsigned char*>(bars) + 256);   // [4] one per epilogue warp
+    using HitQ = HitQueue<GemmShape<GEMM_BN, PASSES>::HITQ>;
+    HitQ* hqs = reinterpret_cast<HitQ*>(reinterpret_cast<unsigned char*>(bars) + 256);   // [4] one per epilogue warp
 
     const int tid = threadIdx.x;
     const int warp = tid >> 5;
@@ -517,15 +520,7 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
         // ------------------------------------------------------------------ epilogue
         const int et = tid - 192;        // 0..127
         const uint32_t quarter = warp & 3;  // TMEM lanes this warp may read: 32*quarter .. +31
-        HitQueue* hq = hqs + (warp - 6);
-        if (lane == 0) {
-            hq->count = 0;
-            hq->cap = p.cap;
-            hq->cand = p.cand;
-            hq->cand_cnt = p.cand_cnt;
-            hq->direct = (p.debug >> 1) & 1;
-        }
-        __syncwarp();
+        HitQ* hq = hqs + (warp - 6);
         uint32_t local = 0;
         for (uint32_t it = blockIdx.x; it < n_items; it += gridDim.x, local++) {
             const uint32_t rt = p.row_tile0 + it / p.n_qtiles, qt = it % p.n_qtiles;
@@ -544,7 +539,7 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
             mbar_wait(&tfull[acc], acc_phase);
             tc_fence_after();
             const uint32_t taddr0 = tmem_base + ((quarter * 32u) << 16) + acc * GEMM_BN;
-            epilogue_drain<METRIC, F16, GEMM_BN>(p, taddr0, qt, row, row_ok, xn, thr_s, qn_s, us_s, c1_s, c2_s, hq);
+            epilogue_drain<METRIC, F16, GEMM_BN, GemmShape<GEMM_BN, PASSES>::HITQ>(p, taddr0, qt, row, row_ok, xn, thr_s, qn_s, us_s, c1_s, c2_s, hq);
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&tempty[acc]);
@@ -578,7 +573,8 @@ constexpr int GEMM2_BN = 256;
 constexpr int GEMM2_STAGES = 3;
 constexpr uint32_t GEMM2_Q_BYTES = GEMM2_BN * GEMM_BK * 4;                    // 32 KB
 constexpr uint32_t GEMM2_STAGE_BYTES = 2 * GEMM_X_BYTES + GEMM2_Q_BYTES;      // X0 | X1 | Q = 64 KB
-constexpr uint32_t GEMM2_SMEM_BYTES = 1024 + GEMM2_STAGES * GEMM2_STAGE_BYTES + 5 * GEMM2_BN * 4 + 256 + 16 * sizeof(HitQueue);
+constexpr uint32_t GEMM2_HITQ = 88;    // 16 warps x 1.7 KB: what the 227 KB leave beside the ring
+constexpr uint32_t GEMM2_SMEM_BYTES = 1024 + GEMM2_STAGES * GEMM2_STAGE_BYTES + 5 * GEMM2_BN * 4 + 256 + 16 * sizeof(HitQueue<GEMM2_HITQ>);
 
 __device__ __forceinline__ void tma_load_2d_mc(void* smem_dst, const CUtensorMap* map, int32_t c0, int32_t c1, uint64_t* bar, uint16_t mask) {
     asm volatile(
@@ -623,7 +619,8 @@ gemm_topk2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
     uint64_t* tfull = bars + 2 * GEMM2_STAGES;   // [1]  both accumulators complete
     uint64_t* tempty = tfull + 1;                // [2]  accumulator a drained (4 warps each)
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
-    HitQueue* hqs = reinterpret_cast<HitQueue*>(reinterpret_cast<unsigned char*>(bars) + 256);   // [16] one per epilogue warp
+    using HitQ = HitQueue<GEMM2_HITQ>;
+    HitQ* hqs = reinterpret_cast<HitQ*>(reinterpret_cast<unsigned char*>(bars) + 256);   // [16] one per epilogue warp
 
     const int tid = threadIdx.x;
     const int warp = tid >> 5;
@@ -730,15 +727,7 @@ gemm_topk2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
         const uint32_t grp_e = (uint32_t)(warp - 2) >> 3;
         const uint32_t half = ((uint32_t)(warp - 2) >> 2) & 1u;   // which 128 of the accumulator's 256 columns
         const uint32_t quarter = warp & 3;  // TMEM lanes this warp may read: 32*quarter .. +31
-        HitQueue* hq = hqs + (warp - 2);
-        if (lane == 0) {
-            hq->count = 0;
-            hq->cap = p.cap;
-            hq->cand = p.cand;
-            hq->cand_cnt = p.cand_cnt;
-            hq->direct = (p.debug >> 1) & 1;
-        }
-        __syncwarp();
+        HitQ* hq = hqs + (warp - 2);
         uint32_t local = 0;
         for (uint32_t it = cluster_id; it < n_items; it += n_clusters, local++) {
             const uint32_t grp = it / p.n_qtiles, qt = it % p.n_qtiles;
@@ -757,7 +746,7 @@ gemm_topk2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
             mbar_wait(tfull, local & 1);
             tc_fence_after();
             const uint32_t taddr0 = tmem_base + ((quarter * 32u) << 16) + grp_e * GEMM2_BN;
-            epilogue_drain<METRIC, F16, GEMM2_BN>(p, taddr0, qt, row, row_ok, xn, thr_s, qn_s, us_s, c1_s, c2_s, hq, half * (GEMM2_BN / 64),
+            epilogue_drain<METRIC, F16, GEMM2_BN, GEMM2_HITQ>(p, taddr0, qt, row, row_ok, xn, thr_s, qn_s, us_s, c1_s, c2_s, hq, half * (GEMM2_BN / 64),
                                                   (half + 1) * (GEMM2_BN / 64));
             tc_fence_before();
             __syncwarp();
@@ -787,7 +776,8 @@ constexpr int GEMMP_BN = 256;
 constexpr int GEMMP_STAGES = 6;
 constexpr uint32_t GEMMP_QH_BYTES = (GEMMP_BN / 2) * GEMM_BK * 4;            // this CTA's half of the query tile: 16 KB
 constexpr uint32_t GEMMP_STAGE_BYTES = GEMM_X_BYTES + GEMMP_QH_BYTES;          // 32 KB
-constexpr uint32_t GEMMP_SMEM_BYTES = 1024 + GEMMP_STAGES * GEMMP_STAGE_BYTES + 5 * GEMMP_BN * 4 + 256 + 8 * sizeof(HitQueue);
+constexpr uint32_t GEMMP_HITQ = 176;   // 8 warps x 3.4 KB
+constexpr uint32_t GEMMP_SMEM_BYTES = 1024 + GEMMP_STAGES * GEMMP_STAGE_BYTES + 5 * GEMMP_BN * 4 + 256 + 8 * sizeof(HitQueue<GEMMP_HITQ>);
 
 __device__ __forceinline__ uint32_t mapa_shared(uint32_t local_addr, uint32_t cta_rank) {
     uint32_t r;
@@ -850,7 +840,8 @@ gemm_topk_pair_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_con
     uint64_t* tfull = bars + 2 * GEMMP_STAGES;   // [2]  both CTAs: accumulator complete
     uint64_t* tempty = tfull + 2;                // [2]  leader only: accumulator drained by both CTAs' epilogue warps
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
-    HitQueue* hqs = reinterpret_cast<HitQueue*>(reinterpret_cast<unsigned char*>(bars) + 256);   // [8] one per epilogue warp
+    using HitQ = HitQueue<GEMMP_HITQ>;
+    HitQ* hqs = reinterpret_cast<HitQ*>(reinterpret_cast<unsigned char*>(bars) + 256);   // [8] one per epilogue warp
 
     const int tid = threadIdx.x;
     const int warp = tid >> 5;
@@ -941,15 +932,7 @@ gemm_topk_pair_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_con
         const int et = tid - 64;            // 0..255
         const uint32_t half = ((uint32_t)(warp - 2) >> 2) & 1u;
         const uint32_t quarter = warp & 3;
-        HitQueue* hq = hqs + (warp - 2);
-        if (lane == 0) {
-            hq->count = 0;
-            hq->cap = p.cap;
-            hq->cand = p.cand;
-            hq->cand_cnt = p.cand_cnt;
-            hq->direct = (p.debug >> 1) & 1;
-        }
-        __syncwarp();
+        HitQ* hq = hqs + (warp - 2);
         uint32_t local = 0;
         for (uint32_t it = pair_id; it < n_items; it += n_pairs, local++) {
             const uint32_t grp = it / p.n_qtiles, qt = it % p.n_qtiles;
@@ -969,7 +952,7 @@ gemm_topk_pair_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_con
             mbar_wait(&tfull[acc], acc_phase);
             tc_fence_after();
             const uint32_t taddr0 = tmem_base + ((quarter * 32u) << 16) + acc * GEMMP_BN;
-            epilogue_drain<METRIC, F16, GEMMP_BN>(p, taddr0, qt, row, row_ok, xn, thr_s, qn_s, us_s, c1_s, c2_s, hq, half * (GEMMP_BN / 64),
+            epilogue_drain<METRIC, F16, GEMMP_BN, GEMMP_HITQ>(p, taddr0, qt, row, row_ok, xn, thr_s, qn_s, us_s, c1_s, c2_s, hq, half * (GEMMP_BN / 64),
                                                   (half + 1) * (GEMMP_BN / 64));
             tc_fence_before();
             __syncwarp();
