@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define MLV_ABI_VERSION 4
+#define MLV_ABI_VERSION 5
 
 typedef struct mlv_index *mlv_index_t;
 
@@ -396,6 +396,8 @@ typedef struct mlv_gemm_stats {
     uint64_t gathered_searches;   /* of `searches`, filtered batches that multiplied a compacted copy of the passing rows */
     uint64_t half_queries;        /* of `fast_queries`, certified by the fp16-shadow tier (kind::f16 on halves of the rows) */
     uint64_t mispredicted_queries; /* queries whose predicted thresholds failed the final check ("gemm_predict"); answered by the next tier */
+    uint64_t half_scan_queries;    /* single queries answered through the shadow scan ("scan_half"; not a tensor-core path, counted here for one stats call) */
+    uint64_t half_scan_uncertified; /* of those, re-run by the fp32 scan launch queued behind (certificate failed / shadow overflowed) */
 } mlv_gemm_stats_t;
 int mlv_index_gemm_stats(mlv_index_t h, mlv_gemm_stats_t *out);
 /*

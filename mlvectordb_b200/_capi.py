@@ -17,7 +17,7 @@ MLV_OK = 0
 MLV_E_INVALID, MLV_E_CUDA, MLV_E_NOMEM, MLV_E_UNSUPPORTED, MLV_E_NO_DEVICE = 1, 2, 3, 4, 5
 MLV_MAX_K = 1024
 METRIC_CODE = {"l2": 0, "ip": 1, "cosine": 2}
-ABI_VERSION = 4
+ABI_VERSION = 5
 
 
 class IndexInfo(C.Structure):
@@ -46,6 +46,8 @@ class GemmStats(C.Structure):
         ("gathered_searches", C.c_uint64),
         ("half_queries", C.c_uint64),
         ("mispredicted_queries", C.c_uint64),
+        ("half_scan_queries", C.c_uint64),
+        ("half_scan_uncertified", C.c_uint64),
     ]
 
 

@@ -5,7 +5,7 @@
 // last CTA of a rank's scan writes its k best keys per query straight into every peer's buffer
 // (plain stores to peer-mapped addresses), publishes a sequence number with st.release.sys and
 // waits with ld.acquire.sys until every peer's sequence number has arrived in its own buffer;
-// then it merges the world * k candidates.  Slots are indexed by seq mod 4 and at most TWO exchange
+// then it merges the world * k candidates.  Slots are indexed by seq mod XCHG_SLOTS and at most TWO exchange
 // searches are in flight per handle (mlv_index_submit enforces it; the synchronous entry points run one
 // at a time): a rank can only reach search s+4 after it collected s+2, i.e. after every peer has
 // posted s+2, and a peer posts s+2 only after it finished reading slot s (two in flight: s+2 starts on
@@ -20,7 +20,8 @@ constexpr uint32_t XCHG_MAX_WORLD = 16;
 constexpr uint32_t XCHG_MAX_NQ = 8;   // queries per scan launch
 constexpr uint32_t XCHG_MAX_K = 64;   // the fused exchange handles k <= 64 (55 in practice: 148 SMs * k <= 8192 keys)
 constexpr uint32_t XCHG_SLOT_KEYS = XCHG_MAX_WORLD * XCHG_MAX_NQ * XCHG_MAX_K;  // u64 keys per parity slot
-constexpr uint32_t XCHG_SLOTS = 4;
+constexpr uint32_t XCHG_SLOTS = 8;   // a search may take two launches (first tier + conditional fp32): the same search
+                                     // distance between two uses of a slot as four slots gave one-launch searches
 // buffer layout (u64 words): keys[XCHG_SLOTS][XCHG_MAX_WORLD][XCHG_MAX_NQ][XCHG_MAX_K], flags[XCHG_SLOTS][XCHG_MAX_WORLD]
 constexpr uint32_t XCHG_FLAGS_OFF = XCHG_SLOTS * XCHG_SLOT_KEYS;
 // ... and, for range searches, counts[XCHG_SLOTS][XCHG_MAX_WORLD]: how many hits a rank's list holds (bit 63: too many
@@ -51,9 +52,12 @@ __device__ __forceinline__ unsigned long long global_timer_ns() {
 // Called by `nthr` threads (tid 0..nthr-1, synchronised with named barrier 1).  `top` holds this
 // rank's nq * k keys (local rows, ascending per query, KEY_SENTINEL padded).  Writes the global
 // top-k of every query.  *s_valid is a zeroed shared counter.
-__device__ __forceinline__ void exchange_and_merge(const ExchangeView& x, const uint64_t* top, uint32_t nq, uint32_t k,
-                                                   float* out_dists, int64_t* out_rows, int32_t* out_counts, uint32_t tid,
-                                                   uint32_t nthr, uint32_t* s_valid) {
+// with_marks: the ranks also exchange one word each -- `my_mark` -- in the last key slot of their query 0 (k < XCHG_MAX_K
+// then); the return value is the OR of all ranks' words, identical on every rank (0 without marks or after a timeout).
+__device__ __forceinline__ uint32_t exchange_and_merge(const ExchangeView& x, const uint64_t* top, uint32_t nq, uint32_t k,
+                                                       float* out_dists, int64_t* out_rows, int32_t* out_counts, uint32_t tid,
+                                                       uint32_t nthr, uint32_t* s_valid, bool with_marks = false,
+                                                       uint32_t my_mark = 0) {
     const uint32_t parity = (uint32_t)(x.seq % XCHG_SLOTS);
     const uint32_t per_peer = nq * k;
     for (uint32_t i = tid; i < x.world * per_peer; i += nthr) {
@@ -61,6 +65,8 @@ __device__ __forceinline__ void exchange_and_merge(const ExchangeView& x, const 
         const uint32_t qi = r / k, j = r - qi * k;
         x.bufs[dst][(size_t)parity * XCHG_SLOT_KEYS + ((size_t)x.rank * XCHG_MAX_NQ + qi) * XCHG_MAX_K + j] = top[r];
     }
+    if (with_marks && tid < x.world)
+        x.bufs[tid][(size_t)parity * XCHG_SLOT_KEYS + ((size_t)x.rank * XCHG_MAX_NQ) * XCHG_MAX_K + (XCHG_MAX_K - 1)] = my_mark;
     __threadfence_system();
     named_bar_sync(1, nthr);
     if (tid < x.world) {
@@ -83,9 +89,12 @@ __device__ __forceinline__ void exchange_and_merge(const ExchangeView& x, const 
     named_bar_sync(1, nthr);
     if (*s_valid & 0x80000000u) {  // a peer never arrived: report count -1 instead of a partial merge
         for (uint32_t qi = tid; qi < nq; qi += nthr) out_counts[qi] = -1;
-        return;
+        return 0;
     }
     const volatile uint64_t* slot = x.bufs[x.rank] + (size_t)parity * XCHG_SLOT_KEYS;
+    uint32_t marks = 0;
+    if (with_marks)
+        for (uint32_t r = 0; r < x.world; r++) marks |= (uint32_t)slot[((size_t)r * XCHG_MAX_NQ) * XCHG_MAX_K + (XCHG_MAX_K - 1)];
     const uint32_t mm = x.world * k;
     for (uint32_t qi = 0; qi < nq; qi++) {
         for (uint32_t e = tid; e < mm; e += nthr) {
@@ -115,6 +124,7 @@ __device__ __forceinline__ void exchange_and_merge(const ExchangeView& x, const 
         }
         named_bar_sync(1, nthr);
     }
+    return marks;
 }
 
 // Bitonic network over a[0..P) (P a power of two) by the nthr threads of named barrier 1.
@@ -240,14 +250,20 @@ __global__ void __launch_bounds__(256, 1) range_exchange_only_kernel(const Excha
 }
 
 // A rank with nothing to scan (empty shard, everything tombstoned) still has to take part.
+// cert / run_if: this rank's part of a {first tier, conditional fp32} pair of launches (scan_kernel.cuh, ScanParams::cert):
+// the first posts "certified" and records whether any rank was not, the second runs only in that case.
 __global__ void __launch_bounds__(256, 1) exchange_only_kernel(const ExchangeView x, uint32_t nq, uint32_t k, float* out_dists,
-                                                               int64_t* out_rows, int32_t* out_counts) {
+                                                               int64_t* out_rows, int32_t* out_counts, uint32_t* cert = nullptr,
+                                                               const uint32_t* run_if = nullptr) {
     __shared__ uint64_t top[XCHG_MAX_NQ * XCHG_MAX_K];
     __shared__ uint32_t s_valid;
+    if (run_if && *reinterpret_cast<const volatile uint32_t*>(run_if) == 0) return;
     for (uint32_t i = threadIdx.x; i < nq * k; i += blockDim.x) top[i] = KEY_SENTINEL;
     if (threadIdx.x == 0) s_valid = 0;
     __syncthreads();
-    exchange_and_merge(x, top, nq, k, out_dists, out_rows, out_counts, threadIdx.x, blockDim.x, &s_valid);
+    const uint32_t marks = exchange_and_merge(x, top, nq, k, out_dists, out_rows, out_counts, threadIdx.x, blockDim.x, &s_valid,
+                                              cert != nullptr, 0);
+    if (cert && threadIdx.x == 0) *cert = marks ? 1u : 0u;
 }
 
 }  // namespace mlv

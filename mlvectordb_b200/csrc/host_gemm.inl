@@ -29,6 +29,7 @@ encode_tiled_fn get_encode_tiled() {
 
 // halves per row of the fp16 shadow: rows stay 16-byte aligned (TMA) -> a multiple of 8
 uint32_t f16_ld(const mlv_index* h) { return (h->ld + 7u) & ~7u; }
+float gemm_delta_rel_f16_host(bool l2, uint32_t d) { return gemm_delta_rel_f16(l2, d); }
 
 // fp32 matrix [n_rows, ld] row-major -> boxes of {GEMM_BK floats, box_rows rows}, 128-byte swizzle,
 // out-of-range elements read as zero (ragged last row tile, ld not a multiple of 32)

@@ -18,9 +18,15 @@ uint32_t scan_list_cap(uint32_t k) {
     return p;
 }
 
-int choose_cfg(mlv_index* h, uint32_t nq, uint32_t k, bool range, ScanCfg* c, bool gather = false) {
-    const uint32_t ld4 = h->ld / 4;
-    const size_t rowbytes = (size_t)h->ld * 4;
+uint32_t f16_ld(const mlv_index* h);
+int ensure_f16_shadow(mlv_index* h, cudaStream_t st, bool* usable);
+int ensure_row_norms(mlv_index* h, cudaStream_t st);
+
+// half: the launch reads the fp16 shadow (rows of f16_ld halves; the query stays fp32 in shared memory)
+int choose_cfg(mlv_index* h, uint32_t nq, uint32_t k, bool range, ScanCfg* c, bool gather = false, bool half = false) {
+    const uint32_t ld4 = half ? f16_ld(h) / 8 : h->ld / 4;                    // 16-byte units per row
+    const size_t rowbytes = (size_t)ld4 * 16;
+    const size_t qbytes = half ? (size_t)f16_ld(h) * 4 : rowbytes;             // one query in shared memory
     const uint32_t lcap = scan_list_cap(k);
     int CW = h->tune_cw > 0 ? std::min(h->tune_cw, SCAN_MAX_CW) : (ld4 <= 64 ? 16 : 8);
     if (!range && k > 512) CW = std::min(CW, 4);  // 2048-slot buffers: 4 warps keep the lists at 64 KB
@@ -33,7 +39,7 @@ int choose_cfg(mlv_index* h, uint32_t nq, uint32_t k, bool range, ScanCfg* c, bo
         if (NQ >= 4) CW = std::min(CW, SCAN_WIDE_CW);   // launch bounds of the wide instantiations (scan_max_threads)
     }
     const int max_stages = std::min(std::max(h->tune_max_stages, 2), 16);
-    const size_t fixed = (size_t)NQ * rowbytes + (range ? 0 : (size_t)CW * NQ * lcap * 8) + (size_t)max_stages * 24 + 256;
+    const size_t fixed = (size_t)NQ * qbytes + (range ? 0 : (size_t)CW * NQ * lcap * 8) + (size_t)max_stages * 24 + 256;
     if (fixed + 2 * rowbytes > h->smem_optin)
         return fail(h, MLV_E_UNSUPPORTED, "dimension too large for the shared-memory ring of this build");
     const size_t avail = h->smem_optin - fixed;
@@ -73,7 +79,7 @@ int choose_cfg(mlv_index* h, uint32_t nq, uint32_t k, bool range, ScanCfg* c, bo
     c->T = (uint32_t)T;
     c->S = S;
     c->stage_f4 = (uint32_t)(stage / 16);
-    c->smem = (size_t)S * stage + (size_t)NQ * rowbytes + (range ? 0 : (size_t)CW * NQ * lcap * 8) + (size_t)S * 24;
+    c->smem = (size_t)S * stage + (size_t)NQ * qbytes + (range ? 0 : (size_t)CW * NQ * lcap * 8) + (size_t)S * 24;
     const uint64_t n_tiles = (h->rows + T - 1) / T;
     const int ctas = h->tune_ctas > 0 ? h->tune_ctas : h->sm_count;
     c->grid = (int)std::min<uint64_t>(n_tiles, (uint64_t)ctas);
@@ -111,6 +117,28 @@ cudaError_t launch_scan_m(const ScanParams& p, const ScanCfg& c, cudaStream_t st
         MLV_CASE(8, 1) MLV_CASE(8, 2) MLV_CASE(8, 4)
     }
 #undef MLV_CASE
+    return cudaErrorInvalidValue;
+}
+
+template <int METRIC, int R>
+cudaError_t launch_scan_half_t(const ScanParams& p, const ScanCfg& c, cudaStream_t st) {
+    auto kern = scan_kernel_half<METRIC, R>;
+    static size_t raised[64] = {0};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64 || raised[dev] < c.smem) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c.smem);
+        if (e != cudaSuccess) return e;
+        if (dev >= 0 && dev < 64) raised[dev] = c.smem;
+    }
+    kern<<<c.grid, c.threads, c.smem, st>>>(p);
+    return cudaGetLastError();
+}
+template <int METRIC>
+cudaError_t launch_scan_half_m(const ScanParams& p, const ScanCfg& c, cudaStream_t st) {
+    if (c.R == 1) return launch_scan_half_t<METRIC, 1>(p, c, st);
+    if (c.R == 2) return launch_scan_half_t<METRIC, 2>(p, c, st);
+    if (c.R == 4) return launch_scan_half_t<METRIC, 4>(p, c, st);
     return cudaErrorInvalidValue;
 }
 
@@ -362,12 +390,75 @@ struct FastArgs {
     uint4* tagged_out = nullptr;   // single GPU: tagged 16-byte result records instead of arrays + flag (scan_kernel.cuh)
 };
 
+// ---- shadow scan (scan_kernel_half) ------------------------------------------------------------------------------
+// A single query reads the fp16 shadow of the rows -- half the bytes of the HBM-bound pass -- keeps k' = 32 candidates,
+// and the last CTA re-scores them from the fp32 matrix in the scan's own arithmetic and certifies the answer like the
+// tensor-core tiers do.  An fp32 launch is queued right behind it and returns at once unless the certificate failed
+// (ScanParams::cert / run_if): the fallback is decided on the device, the call stays asynchronous and the results
+// are the fp32 scan's bit for bit either way.
+constexpr uint32_t HALF_SCAN_KPRIME = 32;
+constexpr uint32_t HALF_SCAN_MAX_K = 16;
+float gemm_delta_rel_f16_host(bool l2, uint32_t d);
+
+// the part of the decision that every rank of an exchange search shares (it fixes the number of launches per search)
+bool half_scan_proto(const mlv_index* h, uint32_t nq, uint32_t k) {
+    return h->tune_scan_half != 0 && nq == 1 && k <= HALF_SCAN_MAX_K && h->tune_dynamic && h->tune_fused &&
+           (uint64_t)h->sm_count * HALF_SCAN_KPRIME <= SCAN_FUSED_MAX_KEYS;
+}
+// ... and this rank's own: a matrix large enough for the saved bytes to matter (below ~256 MB the pass is a few tens of
+// microseconds and the second launch costs more than the bytes), no per-row gather, not sitting out
+bool half_scan_shape(const mlv_index* h, uint32_t nq, uint32_t k, bool gather) {
+    if (!half_scan_proto(h, nq, k) || gather || h->ld < 8) return false;
+    return h->tune_scan_half == 1 || (uint64_t)h->rows * h->ld * 4 >= (256ull << 20);
+}
+bool half_scan_local(const mlv_index* h, uint32_t nq, uint32_t k, bool gather) {
+    return half_scan_shape(h, nq, k, gather) && h->half_skip == 0;
+}
+// feedback from the kernels' pinned mirror: a shadow that certifies less than half of its queries sits out 64, 128, ...
+// searches (each uncertified query costs the fp32 pass on top); an overflowed shadow is rebuilt with a fresh scale
+void half_scan_policy(mlv_index* h) {
+    if (h->half_skip > 0) {
+        h->half_skip--;
+        return;
+    }
+    if (!h->h_half_stats.p) return;
+    const volatile uint32_t* m = (const volatile uint32_t*)h->h_half_stats.p;
+    const uint32_t q = m[0], u = m[1];
+    if (m[2]) {
+        ((volatile uint32_t*)h->h_half_stats.p)[2] = 0;
+        h->f16_valid = 0;
+    }
+    if (q - h->half_seen_q >= 16) {
+        if ((u - h->half_seen_u) * 2 > q - h->half_seen_q) {
+            h->half_backoff = std::min<uint32_t>(std::max<uint32_t>(64, h->half_backoff * 2), 1u << 16);
+            h->half_skip = h->half_backoff;
+        } else {
+            h->half_backoff = 0;
+        }
+        h->half_seen_q = q;
+        h->half_seen_u = u;
+    }
+}
+
 int search_prepared(mlv_index* h, const float* qprep, uint32_t nq, uint32_t k, const uint32_t* filter_dev, float* out_d,
                     int64_t* out_r, int32_t* out_c, cudaStream_t st, bool exchange = false, const FastArgs* fast = nullptr) {
     Lane* ln = lane_for(h, st);
     FilterPlan fp;
     int rc = plan_filter(h, ln, filter_dev, st, &fp);
     if (rc != MLV_OK) return rc;
+    // one policy step per search: the latency path asks first (with `fast`) and may come back staged
+    if (half_scan_shape(h, nq, k, fp.gather != nullptr)) {
+        if (fast) {
+            half_scan_policy(h);
+            h->half_stepped = true;
+        } else if (h->half_stepped) {
+            h->half_stepped = false;
+        } else {
+            half_scan_policy(h);
+        }
+    }
+    // two launches per search (first tier + conditional fp32)?  Across ranks the protocol decides, alone this rank does
+    const bool pair_proto = half_scan_proto(h, nq, k) && (exchange || half_scan_local(h, nq, k, fp.gather != nullptr));
     ScanCfg c;
     if ((rc = choose_cfg(h, nq, k, false, &c, fp.gather != nullptr)) != MLV_OK) return rc;
     if ((rc = ensure_sched(h, ln)) != MLV_OK) return rc;
@@ -377,7 +468,7 @@ int search_prepared(mlv_index* h, const float* qprep, uint32_t nq, uint32_t k, c
     if (exchange && !fused) return fail(h, MLV_E_UNSUPPORTED, "exchange search needs the fused final select");
     if (fused) c.smem = std::max(c.smem, fused_scratch_bytes(c, k));
     if (fast) {
-        const bool ok = fused && nq == 1 && c.NQ == 1 && h->dim <= SCAN_INLINE_MAX_DIM && !h->timing;
+        const bool ok = fused && nq == 1 && c.NQ == 1 && h->dim <= SCAN_INLINE_MAX_DIM && !h->timing && !pair_proto;
         if (fast->took_fast) *fast->took_fast = ok;
         if (!ok) return MLV_OK;   // nothing launched: the caller stages the query and takes the general path
     }
@@ -406,6 +497,108 @@ int search_prepared(mlv_index* h, const float* qprep, uint32_t nq, uint32_t k, c
         if (rc != MLV_OK) return rc;
         p.timeline = (unsigned long long*)h->d_timeline.p;
         h->last_grid = c.grid;
+    }
+
+    if (pair_proto && fused) {
+        // ---- first tier + conditional fp32 launch (one query) ----
+        if ((rc = ensure_dev(h, ln->d_cert, 4)) != MLV_OK) return rc;
+        bool use_half = half_scan_local(h, nq, k, fp.gather != nullptr);
+        ScanCfg ch{};
+        if (use_half) {
+            if (h->metric != MLV_COSINE && (rc = ensure_row_norms(h, st)) != MLV_OK) return rc;
+            if ((rc = ensure_f16_shadow(h, st, &use_half)) != MLV_OK) return rc;
+        }
+        if (use_half) {
+            if ((rc = choose_cfg(h, 1, HALF_SCAN_KPRIME, false, &ch, false, true)) != MLV_OK) return rc;
+            // the tail's scratch (candidates | k' approximate | 32 exact | k final keys) overlays the ring and must leave
+            // the query behind it alone
+            const size_t scratch = ((size_t)fused_cap(ch, HALF_SCAN_KPRIME) + HALF_SCAN_KPRIME + 32 + k) * 8;
+            use_half = scratch <= (size_t)ch.S * ch.stage_f4 * 16 && (uint64_t)ch.grid * HALF_SCAN_KPRIME <= SCAN_FUSED_MAX_KEYS;
+        }
+        if (use_half) {
+            if ((rc = ensure_dev(h, h->d_half_stats, 8)) != MLV_OK) return rc;
+            if (!h->h_half_stats.p) {
+                CK(h, cudaMemsetAsync(h->d_half_stats.p, 0, 8, st));
+                if ((rc = ensure_host(h, h->h_half_stats, 16)) != MLV_OK) return rc;
+                memset(h->h_half_stats.p, 0, 16);
+            }
+            if ((rc = ensure_dev(h, ln->d_keys0, (size_t)ch.grid * HALF_SCAN_KPRIME * 8)) != MLV_OK) return rc;
+        }
+        cudaEvent_t e0 = nullptr, e1 = nullptr;
+        const bool timing = h->timing;
+        if (timing) {   // one event pair around both launches: a search, not a launch, is what scan_time_ms averages
+            for (cudaEvent_t* ev : {&e0, &e1}) {
+                if (!h->event_pool.empty()) {
+                    *ev = h->event_pool.back();
+                    h->event_pool.pop_back();
+                } else {
+                    CK(h, cudaEventCreate(ev));
+                }
+            }
+            cudaEventRecord(e0, st);
+            h->timing = false;
+        }
+        p.queries = reinterpret_cast<const float4*>(qprep);
+        p.nq_valid = 1;
+        p.out_dists = out_d;
+        p.out_rows = out_r;
+        p.out_counts = out_c;
+        cudaError_t le;
+        if (use_half) {
+            ScanParams ph = scan_params(h, ch, fp, ln, HALF_SCAN_KPRIME);
+            ph.rows = reinterpret_cast<const float4*>(h->d_rows16.p);
+            ph.ld4 = f16_ld(h) / 8;
+            ph.rows_exact = reinterpret_cast<const float4*>(h->d_rows);
+            ph.ld4_exact = h->ld / 4;
+            ph.k_out = k;
+            ph.half_state = (const uint32_t*)h->d_f16st.p;
+            ph.row_norms = h->metric == MLV_L2 ? (const float*)h->d_norms.p : nullptr;
+            ph.max_norm2_bits = h->metric == MLV_COSINE ? nullptr : (const uint32_t*)h->d_maxn2.p;
+            ph.delta_rel = gemm_delta_rel_f16_host(h->metric == MLV_L2, h->ld);
+            ph.cosine = h->metric == MLV_COSINE;
+            ph.cert = (uint32_t*)ln->d_cert.p;
+            ph.half_stats = (uint32_t*)h->d_half_stats.p;
+            ph.half_stats_host = (volatile uint32_t*)h->h_half_stats.p;
+            ph.fused = 1;
+            ph.fused_cap = fused_cap(ch, HALF_SCAN_KPRIME);
+            ph.row_base = h->row_base;
+            ph.queries = p.queries;
+            ph.nq_valid = 1;
+            ph.out_keys = (uint64_t*)ln->d_keys0.p;
+            ph.out_dists = out_d;
+            ph.out_rows = out_r;
+            ph.out_counts = out_c;
+            ph.timeline = p.timeline;
+            if (exchange) {
+                fill_exchange(h, ph.xchg);
+                ph.xchg.seq = ++h->xseq;
+            }
+            le = h->metric == MLV_L2 ? launch_scan_half_m<METRIC_L2>(ph, ch, st) : launch_scan_half_m<METRIC_IP>(ph, ch, st);
+            h->launches++;
+            h->half_scan_launches++;
+        } else {
+            // (exchange only) this rank has no shadow to offer: its first launch is the fp32 scan, which always certifies
+            p.out_keys = (uint64_t*)ln->d_keys0.p;
+            p.cert = (uint32_t*)ln->d_cert.p;
+            p.xchg.seq = ++h->xseq;
+            le = launch_scan(h, p, c, false, st);
+            p.cert = nullptr;
+        }
+        if (le != cudaSuccess) {
+            h->timing = timing;
+            return fail_cuda(h, le, "scan launch");
+        }
+        p.out_keys = (uint64_t*)ln->d_keys0.p;
+        p.run_if = (const uint32_t*)ln->d_cert.p;
+        if (exchange) p.xchg.seq = ++h->xseq;
+        le = launch_scan(h, p, c, false, st);
+        h->timing = timing;
+        if (timing) {
+            cudaEventRecord(e1, st);
+            h->pending.emplace_back(e0, e1);
+        }
+        if (le != cudaSuccess) return fail_cuda(h, le, "scan launch");
+        return MLV_OK;
     }
 
     for (uint32_t q0 = 0; q0 < nq; q0 += chunk) {

@@ -23,6 +23,7 @@ struct Lane {
     uint64_t last_use = 0;
     DevBuf d_q, d_keys0, d_keys1, d_sched;
     DevBuf d_flist, d_fscratch;  // gather list built from a per-call filter bitmap
+    DevBuf d_cert;               // shadow scan: the word its conditional fp32 launch reads (scan_kernel.cuh, ScanParams::cert)
 };
 
 // One asynchronous host-buffer search in flight (mlv_index_submit / mlv_index_collect): its own
@@ -122,6 +123,14 @@ struct mlv_index {
     uint64_t f16_valid = 0;    // rows [0, f16_valid) of the shadow are current
     bool f16_overflowed = false;  // the last fp16-tier batch hit the overflow flag
     uint64_t gemm_half_queries = 0;  // queries certified by the fp16 tier
+    // shadow scan (single queries over the fp16 shadow, scan_kernel_half): -1 auto, 0 never, 1 whenever the shape allows
+    int tune_scan_half = -1;
+    DevBuf d_half_stats;             // device counters {queries, not certified}
+    HostBuf h_half_stats;            // their pinned mirror {queries, not certified, overflow flag}, written by the kernel
+    uint32_t half_seen_q = 0, half_seen_u = 0;   // mirror values at the last policy check
+    uint32_t half_skip = 0, half_backoff = 0;    // searches the shadow scan sits out after certifying too little
+    uint64_t half_scan_launches = 0;
+    bool half_stepped = false;                   // the latency-path probe of this search already stepped the policy
     int tune_gemm = -1;        // -1 auto, 0 never, 1 whenever the shape allows it
     int tune_gemm_min_nq = 0;  // 0 = auto (gemm_min_nq: 5 with the one-pass tier on a >= 1 GB matrix, else 9)
     int tune_gemm_bn = 0;      // queries per GEMM tile: 0 auto, or 64 / 128 / 256

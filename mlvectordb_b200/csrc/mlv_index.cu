@@ -114,6 +114,7 @@ int mlv_index_create(uint32_t dim, int metric, uint64_t capacity_hint, int devic
     h->tune_gemm_wide = env_int("MLV_GEMM_WIDE", h->tune_gemm_wide);
     h->tune_gemm_debug = env_int("MLV_GEMM_DEBUG", h->tune_gemm_debug);
     h->tune_gemm_predict = env_int("MLV_GEMM_PREDICT", h->tune_gemm_predict);
+    h->tune_scan_half = env_int("MLV_SCAN_HALF", h->tune_scan_half);
     DeviceGuard g(device);
     cudaDeviceProp prop;
     cudaError_t e = g.ok ? cudaGetDeviceProperties(&prop, device) : cudaErrorInvalidDevice;
@@ -150,14 +151,15 @@ int mlv_index_destroy(mlv_index_t h) {
     if (h->d_rows) cudaFree(h->d_rows);
     if (h->d_live) cudaFree(h->d_live);
     for (DevBuf* b : {&h->d_qraw, &h->d_filter, &h->d_outd, &h->d_outr, &h->d_outc, &h->d_misc, &h->d_range, &h->d_timeline,
-                      &h->d_norms, &h->d_gq, &h->d_cand, &h->d_maxn2, &h->d_sub, &h->d_gx, &h->d_rows16, &h->d_f16st, &h->d_gx16})
+                      &h->d_norms, &h->d_gq, &h->d_cand, &h->d_maxn2, &h->d_sub, &h->d_gx, &h->d_rows16, &h->d_f16st, &h->d_gx16, &h->d_half_stats})
         free_dev(*b);
     for (Lane& l : h->lanes)
-        for (DevBuf* b : {&l.d_q, &l.d_keys0, &l.d_keys1, &l.d_sched, &l.d_flist, &l.d_fscratch}) free_dev(*b);
+        for (DevBuf* b : {&l.d_q, &l.d_keys0, &l.d_keys1, &l.d_sched, &l.d_flist, &l.d_fscratch, &l.d_cert}) free_dev(*b);
     drop_columns(h);
     drop_filter_pool(h);
     if (h->h_stage.p) cudaFreeHost(h->h_stage.p);
     if (h->h_range.p) cudaFreeHost(h->h_range.p);
+    if (h->h_half_stats.p) cudaFreeHost(h->h_half_stats.p);
     if (h->h_upload.p) cudaFreeHost(h->h_upload.p);
     for (AsyncSlot& sl : h->slots) {
         if (sl.stream) cudaStreamSynchronize(sl.stream);
@@ -207,7 +209,10 @@ int mlv_index_set_tuning(mlv_index_t h, const char* key, int value) {
     else if (k == "fast_host") h->tune_fast_host = value;
     else if (k == "gemm_wide") h->tune_gemm_wide = value;
     else if (k == "gemm_debug") h->tune_gemm_debug = value;
-    else if (k == "gemm_predict") {
+    else if (k == "scan_half") {
+        h->tune_scan_half = value;
+        h->half_skip = h->half_backoff = 0;
+    } else if (k == "gemm_predict") {
         h->tune_gemm_predict = value;
         h->gemm_predict_skip = h->gemm_predict_backoff = 0;
     }
@@ -763,12 +768,21 @@ int mlv_index_search_exchange_device(mlv_index_t h, const float* queries_dev, ui
         ScanCfg c;
         int rc0 = choose_cfg(h, nq, k, false, &c);  // same query grouping as a scanning rank
         if (rc0 != MLV_OK) return rc0;
+        const bool pair = half_scan_proto(h, nq, k);   // the peers' searches take two launches: so does this rank's part
+        Lane* ln = lane_for(h, st);
+        if (pair && (rc0 = ensure_dev(h, ln->d_cert, 4)) != MLV_OK) return rc0;
         for (uint32_t g0 = 0; g0 < nq; g0 += c.NQ) {
             const uint32_t n = std::min<uint32_t>(c.NQ, nq - g0);
             x.seq = ++h->xseq;
             exchange_only_kernel<<<1, 256, 0, st>>>(x, n, k, out_dists_dev + (size_t)g0 * k, out_rows_dev + (size_t)g0 * k,
-                                                   out_counts_dev + g0);
+                                                   out_counts_dev + g0, pair ? (uint32_t*)ln->d_cert.p : nullptr, nullptr);
             h->launches++;
+            if (pair) {
+                x.seq = ++h->xseq;
+                exchange_only_kernel<<<1, 256, 0, st>>>(x, n, k, out_dists_dev + (size_t)g0 * k, out_rows_dev + (size_t)g0 * k,
+                                                       out_counts_dev + g0, nullptr, (const uint32_t*)ln->d_cert.p);
+                h->launches++;
+            }
         }
         CK(h, cudaGetLastError());
         return MLV_OK;
@@ -1271,6 +1285,14 @@ int mlv_index_gemm_stats(mlv_index_t h, mlv_gemm_stats_t* out) {
     out->fast_queries = h->gemm_fast_queries;
     out->half_queries = h->gemm_half_queries;
     out->mispredicted_queries = h->gemm_mispredicted_queries;
+    out->half_scan_queries = out->half_scan_uncertified = 0;
+    if (h->d_half_stats.p) {   // counters the shadow-scan kernels keep on the device
+        uint32_t hs[2] = {0, 0};
+        CK(h, cudaDeviceSynchronize());
+        CK(h, cudaMemcpy(hs, h->d_half_stats.p, 8, cudaMemcpyDeviceToHost));
+        out->half_scan_queries = hs[0];
+        out->half_scan_uncertified = hs[1];
+    }
     out->gathered_searches = h->gemm_gathered_searches;
     out->rounds = h->gemm_rounds;
     return MLV_OK;

@@ -103,6 +103,26 @@ struct ScanParams {
     // fence + flag cost 4 us of a 27 us launch on a 10k-row namespace).
     uint4* tagged_out;
     unsigned int tag;
+    // ---- shadow scan (HALF instantiations: one query, k' = k <= 32 candidates, fused tail) -------------------------
+    // rows / ld4 / stage_f4 describe the fp16 SHADOW of the matrix (halves of row * 2^s, ld4 = 16-byte units per row):
+    // the pass reads half the bytes and selects k' candidates by approximate distance; the last CTA re-scores them from
+    // the fp32 matrix in the scan's own arithmetic, keeps the best k_out and certifies the answer exactly like the
+    // tensor-core tiers (gemm_kernel.cuh): rows outside the candidates have a >= a_k', hence exact distance >= a_k' - delta.
+    const float4* rows_exact;        // the fp32 matrix [n_rows, ld4_exact]
+    uint32_t ld4_exact;              // float4 per fp32 row == float4 per prepared query
+    uint32_t k_out;                  // neighbours returned (<= k)
+    const uint32_t* half_state;      // {2^-s as float bits, s, overflow flag} (f16_freeze_scale_kernel)
+    const float* row_norms;          // |x|^2 per row (l2)
+    const uint32_t* max_norm2_bits;  // max |x|^2 (nullptr: unit rows)
+    float delta_rel;                 // bound on |a - exact| / scale
+    int cosine;                      // unit rows and queries: scale 1
+    // *cert (device word) = 1 when some query of this launch is not certified (on any rank of an exchange search), else
+    // 0: the fp32 launch queued right behind this one carries run_if = cert and returns at once when it reads 0 -- the
+    // fallback is decided on the device, no host synchronisation
+    uint32_t* cert;
+    const uint32_t* run_if;
+    uint32_t* half_stats;            // device counters {shadow-scan queries, not certified}
+    volatile uint32_t* half_stats_host;  // mapped pinned mirror {queries, not certified, overflow flag} (plain stores)
 };
 
 constexpr uint32_t SCAN_INLINE_MAX_DIM = 2048;   // floats of a query carried in the kernel parameters (8 KB)
@@ -231,11 +251,14 @@ __device__ __forceinline__ uint32_t sorted_count_below(const uint64_t* list, uin
     return lo;
 }
 
-template <int METRIC, int NQ, int R, bool RANGE, bool INLINE>
+template <int METRIC, int NQ, int R, bool RANGE, bool INLINE, bool HALF = false>
 __device__ __forceinline__ void scan_body(const ScanParams& p, const float* iq) {
     constexpr int V = R * NQ;
     static_assert(V <= 32 && (V & (V - 1)) == 0, "R*NQ must be a power of two <= 32");
+    static_assert(!HALF || (NQ == 1 && !RANGE && !INLINE), "the shadow scan takes one prepared query, top-k mode");
     extern __shared__ __align__(128) unsigned char smem[];
+    // fallback launch behind a shadow scan: nothing to do when that one certified its answer
+    if (p.run_if && *reinterpret_cast<const volatile uint32_t*>(p.run_if) == 0) return;
 
     const int tid = threadIdx.x;
     const int warp = tid >> 5;
@@ -252,11 +275,14 @@ __device__ __forceinline__ void scan_body(const ScanParams& p, const float* iq) 
     float4* qs = ring + (size_t)S * p.stage_f4;                                   // [NQ][ld4]
     const uint32_t lcap = p.list_cap;             // slots per (warp, query) list
     const bool buffered = lcap > k;               // append buffer + compaction instead of replace-max
-    uint64_t* lists = reinterpret_cast<uint64_t*>(qs + (size_t)NQ * ld4);         // [CW][NQ][lcap]
+    const uint32_t ldq4 = HALF ? 2 * ld4 : ld4;   // float4 per query in shared memory (HALF: ld4 counts 8-half units)
+    uint64_t* lists = reinterpret_cast<uint64_t*>(qs + (size_t)NQ * ldq4);        // [CW][NQ][lcap]
     uint64_t* full = lists + (RANGE ? 0 : (size_t)CW * NQ * lcap);                // [S]
     uint64_t* empty = full + S;                                                   // [S]
     StageMeta* meta = reinterpret_cast<StageMeta*>(empty + S);                    // [S]
 
+    float half_qn = 0.f;                                                           // HALF: |q|^2
+    const float half_us = HALF ? __uint_as_float(__ldg(p.half_state)) : 1.0f;      // HALF: 2^-s of the shadow
     if (tid == 0) {
         for (uint32_t s = 0; s < S; s++) {
             mbar_init(&full[s], 1);
@@ -285,6 +311,27 @@ __device__ __forceinline__ void scan_body(const ScanParams& p, const float* iq) 
             const float inv = s_inv;
             for (uint32_t j = tid; j < p.dim; j += blockDim.x) qf[j] = qf[j] * inv;
         }
+    } else if (HALF) {
+        // the fp32 prepared query, zero padded to the shadow's row length; |q|^2 for the l2 form and the certificate
+        __shared__ float s_qn_init;
+        for (uint32_t i = tid; i < ldq4; i += blockDim.x)
+            qs[i] = i < p.ld4_exact ? p.queries[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+        __syncthreads();
+        if (warp == 0) {
+            float acc = 0.f;
+            for (uint32_t j = lane; j < p.ld4_exact; j += 32) {
+                const float4 v = qs[j];
+                acc = fmaf(v.x, v.x, acc);
+                acc = fmaf(v.y, v.y, acc);
+                acc = fmaf(v.z, v.z, acc);
+                acc = fmaf(v.w, v.w, acc);
+            }
+#pragma unroll
+            for (int off = 16; off >= 1; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+            if (lane == 0) s_qn_init = acc;
+        }
+        __syncthreads();
+        half_qn = s_qn_init;
     } else {
         // queries -> shared (missing queries of a short group repeat the last one; masked later)
         for (uint32_t i = tid; i < NQ * ld4; i += blockDim.x) {
@@ -431,20 +478,60 @@ __device__ __forceinline__ void scan_body(const ScanParams& p, const float* iq) 
 #pragma unroll
             for (int i = 0; i < V; i++) acc[i] = 0.f;
             const float4* trow = tile + (size_t)base * ld4;
+            float xn = 0.f;
+            if (HALF && METRIC == METRIC_L2) xn = __ldg(p.row_norms + (p.gather ? row : pos));   // own slot's row; in flight during the dot products
+            if (HALF) {
+                // 8 halves of the row against 8 floats of the query per step; the sum is a plain dot product (the
+                // distance form is applied below): only candidates are chosen with it
+                float acc2[V];
+#pragma unroll
+                for (int i = 0; i < V; i++) acc2[i] = 0.f;
 #pragma unroll 2
-            for (uint32_t j = lane; j < ld4; j += 32) {
-                float4 q[NQ];
+                for (uint32_t j = lane; j < ld4; j += 32) {
+                    const float4 qa = qs[2 * j], qb = qs[2 * j + 1];
 #pragma unroll
-                for (int qi = 0; qi < NQ; qi++) q[qi] = qs[qi * ld4 + j];
+                    for (int r = 0; r < R; r++) {
+                        const float4 xr = trow[r * ld4 + j];
+                        const float2 f0 = __half22float2(*reinterpret_cast<const __half2*>(&xr.x));
+                        const float2 f1 = __half22float2(*reinterpret_cast<const __half2*>(&xr.y));
+                        const float2 f2 = __half22float2(*reinterpret_cast<const __half2*>(&xr.z));
+                        const float2 f3 = __half22float2(*reinterpret_cast<const __half2*>(&xr.w));
+                        // two chains per row: at the power-capped clock the consumers are bound by FMA latency, not issue
+                        float a = acc[r], b = acc2[r];
+                        a = fmaf(f0.x, qa.x, a);
+                        b = fmaf(f2.x, qb.x, b);
+                        a = fmaf(f0.y, qa.y, a);
+                        b = fmaf(f2.y, qb.y, b);
+                        a = fmaf(f1.x, qa.z, a);
+                        b = fmaf(f3.x, qb.z, b);
+                        a = fmaf(f1.y, qa.w, a);
+                        b = fmaf(f3.y, qb.w, b);
+                        acc[r] = a;
+                        acc2[r] = b;
+                    }
+                }
 #pragma unroll
-                for (int r = 0; r < R; r++) {
-                    const float4 x = trow[r * ld4 + j];
+                for (int r = 0; r < R; r++) acc[r] += acc2[r];
+            } else {
+#pragma unroll 2
+                for (uint32_t j = lane; j < ld4; j += 32) {
+                    float4 q[NQ];
 #pragma unroll
-                    for (int qi = 0; qi < NQ; qi++) acc[r * NQ + qi] = accum4<METRIC>(acc[r * NQ + qi], x, q[qi]);
+                    for (int qi = 0; qi < NQ; qi++) q[qi] = qs[qi * ld4 + j];
+#pragma unroll
+                    for (int r = 0; r < R; r++) {
+                        const float4 x = trow[r * ld4 + j];
+#pragma unroll
+                        for (int qi = 0; qi < NQ; qi++) acc[r * NQ + qi] = accum4<METRIC>(acc[r * NQ + qi], x, q[qi]);
+                    }
                 }
             }
             const float s = transpose_reduce<V>(acc, lane);
-            const float dist = (METRIC == METRIC_IP) ? 1.0f - s : s;
+            float dist;
+            if (HALF)   // approximate: the GEMM form on the shadow's dot product
+                dist = (METRIC == METRIC_IP) ? 1.0f - half_us * s : fmaf(-2.0f * half_us, s, xn + half_qn);
+            else
+                dist = (METRIC == METRIC_IP) ? 1.0f - s : s;
             const uint64_t key = make_key(dist, row);
             const bool ok = rep && q_ok && my_local < (uint32_t)n && ((wl & wf) >> (rowc & 31) & 1u);
             if (RANGE) {
@@ -692,8 +779,61 @@ __device__ __forceinline__ void scan_body(const ScanParams& p, const float* iq) 
                 named_bar_sync(1, CW * 32);
             }
         }
+        // what the output stage below reads: the final keys, kf per query
+        const uint64_t* fin = top;
+        uint32_t kf = k;
+        uint32_t my_uncert = 0;   // HALF: bit qi = query qi is not certified on this rank (same in every thread)
+        if (HALF) {
+            // ---- exact re-rank of the k' <= 32 candidates + certificate (see ScanParams) ----
+            __shared__ uint32_t s_uncert;
+            uint64_t* ex = top + (size_t)p.nq_valid * k;        // [nq][32] exact keys, unsorted
+            uint64_t* fx = ex + (size_t)p.nq_valid * 32;        // [nq][k_out] exact keys, ascending
+            if (tid == 0) s_uncert = 0;
+            for (uint32_t e = (uint32_t)warp; e < p.nq_valid * k; e += (uint32_t)CW) {
+                const uint32_t qi = e / k, i = e - qi * k;
+                const uint64_t key = top[e];
+                uint64_t out = KEY_SENTINEL;
+                if (key != KEY_SENTINEL) {   // warp-uniform
+                    const uint32_t row = key_row(key);
+                    const float4* xrow = p.rows_exact + (size_t)row * p.ld4_exact;
+                    const float4* qv = qs + (size_t)qi * ldq4;
+                    // the scan's own arithmetic: lane l sums float4 columns l, l + 32, ..., butterfly over the lanes
+                    float acc = 0.f;
+                    for (uint32_t j = lane; j < p.ld4_exact; j += 32) acc = accum4<METRIC>(acc, xrow[j], qv[j]);
+#pragma unroll
+                    for (int off = 16; off >= 1; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+                    out = make_key((METRIC == METRIC_IP) ? 1.0f - acc : acc, row);
+                }
+                if (lane == 0) ex[qi * 32 + i] = out;
+            }
+            named_bar_sync(1, CW * 32);
+            if ((uint32_t)warp < p.nq_valid) {
+                const uint32_t qi = (uint32_t)warp;
+                uint64_t v = (uint32_t)lane < k ? ex[qi * 32 + lane] : KEY_SENTINEL;
+                v = warp_bitonic_sort_u64(v, lane);
+                if ((uint32_t)lane < p.k_out) fx[qi * p.k_out + lane] = v;
+                const uint64_t last = top[qi * k + k - 1];                 // k'-th approximate key: sentinel = every row is a candidate
+                const uint64_t ek = shfl_u64(v, (int)p.k_out - 1);         // exact k-th best among the candidates
+                bool certified = true;
+                if (last != KEY_SENTINEL) {
+                    float scale = 1.0f;
+                    if (!p.cosine) {
+                        const float xmax = sqrtf(__uint_as_float(*p.max_norm2_bits)), qsn = sqrtf(half_qn);
+                        scale = (METRIC == METRIC_L2) ? (xmax + qsn) * (xmax + qsn) : xmax * qsn;
+                    }
+                    certified = (key_dist(last) - p.delta_rel * scale > key_dist(ek));   // false for NaN
+                }
+                if (__ldg(p.half_state + 2)) certified = false;   // the shadow overflowed fp16: nothing it selected can be trusted
+                if (lane == 0 && !certified) atomicOr(&s_uncert, 1u << qi);
+            }
+            named_bar_sync(1, CW * 32);
+            my_uncert = s_uncert;
+            fin = fx;
+            kf = p.k_out;
+        }
         if (p.timeline && tid == 0) p.timeline[blockIdx.x * 16 + 5] = global_timer_ns();   // last CTA: final select done
         const ExchangeView& x = p.xchg;
+        uint32_t any_uncert = my_uncert;
         if (x.world <= 1 && p.tagged_out) {
             for (uint32_t i = tid; i <= k; i += nthr) {
                 uint4 rec;
@@ -711,19 +851,34 @@ __device__ __forceinline__ void scan_body(const ScanParams& p, const float* iq) 
                              : "memory");
             }
         } else if (x.world <= 1) {
-            for (uint32_t i = tid; i < p.nq_valid * k; i += nthr) {
-                const uint64_t key = top[i];
+            for (uint32_t i = tid; i < p.nq_valid * kf; i += nthr) {
+                const uint64_t key = fin[i];
                 const bool valid = key != KEY_SENTINEL;
                 p.out_dists[i] = valid ? key_dist(key) : __int_as_float(0x7f800000);
                 p.out_rows[i] = valid ? (int64_t)(p.row_base + key_row(key)) : -1;
             }
             for (uint32_t qi = tid; qi < p.nq_valid; qi += nthr) {
                 int c = 0;
-                for (uint32_t j = 0; j < k; j++) c += top[qi * k + j] != KEY_SENTINEL;
+                for (uint32_t j = 0; j < kf; j++) c += fin[qi * kf + j] != KEY_SENTINEL;
                 p.out_counts[qi] = c;
             }
         } else {
-            exchange_and_merge(x, top, p.nq_valid, k, p.out_dists, p.out_rows, p.out_counts, tid, nthr, &s_valid);
+            // p.cert: this launch is the first of a {first tier, conditional fp32} pair -- the ranks also agree on whether
+            // any of them failed to certify (an fp32 first launch always certifies)
+            any_uncert = exchange_and_merge(x, fin, p.nq_valid, kf, p.out_dists, p.out_rows, p.out_counts, tid, nthr, &s_valid,
+                                            p.cert != nullptr, my_uncert);
+        }
+        if (p.cert && tid == 0) {
+            *p.cert = any_uncert ? 1u : 0u;
+            if (HALF) {
+                const uint32_t a = atomicAdd(p.half_stats, p.nq_valid) + p.nq_valid;
+                const uint32_t b = atomicAdd(p.half_stats + 1, (uint32_t)__popc(my_uncert)) + (uint32_t)__popc(my_uncert);
+                if (p.half_stats_host) {
+                    p.half_stats_host[0] = a;
+                    p.half_stats_host[1] = b;
+                    p.half_stats_host[2] = __ldg(p.half_state + 2);
+                }
+            }
         }
     }
     if (RANGE && p.fused) {
@@ -753,6 +908,11 @@ __device__ __forceinline__ void scan_body(const ScanParams& p, const float* iq) 
 template <int METRIC, int NQ, int R, bool RANGE>
 __global__ void __launch_bounds__(scan_max_threads<NQ>(), 1) scan_kernel(const ScanParams p) {
     scan_body<METRIC, NQ, R, RANGE, false>(p, nullptr);
+}
+// one query over the fp16 shadow of the rows, exact re-rank + certificate in the fused tail (ScanParams::rows_exact)
+template <int METRIC, int R>
+__global__ void __launch_bounds__(SCAN_MAX_THREADS, 1) scan_kernel_half(const ScanParams p) {
+    scan_body<METRIC, 1, R, false, false, true>(p, nullptr);
 }
 // one query whose raw values travel in the launch parameters (batch-1 latency path)
 template <int METRIC, int R, bool RANGE>

@@ -73,6 +73,38 @@ def main():
                 assert len(got[0][1]) >= 1
         idx.close()
 
+    def check_single(total_rows, dim, space, k, tiers):
+        """Single queries take a {first tier, conditional fp32} pair of launches on every rank (scan_kernel.cuh, shadow
+        scan); ``tiers[rank % len(tiers)]`` is this rank's "scan_half": 1 = fp16 shadow first, -1 = too small here, so
+        its first launch is the fp32 scan -- the ranks only have to agree on the number of launches."""
+        idx = ShardedIndex(dim, space, total_rows, device=device)
+        idx.add_synthetic(11, scaled=True)
+        idx.shard.set_tuning("scan_half", tiers[rank % len(tiers)])
+        nq = 7
+        Q = synthetic.queries(12, nq, dim)
+        if total_rows > 5:
+            Q[0] = synthetic.rows(11, total_rows - 2, 1, dim, scaled=True)[0]
+        got = [idx.search(Q[i:i + 1], k) for i in range(nq)]
+        handles = [idx.search_async(Q[i:i + 1], k) for i in range(2)]      # two in flight
+        got_async = [hnd.result() for hnd in handles]
+        st = idx.shard.gemm_stats()
+        if tiers[rank % len(tiers)] == 1 and idx.hi > idx.lo:
+            assert st["half_scan_queries"] >= nq, st
+        if rank == 0:
+            whole = DeviceShard(dim, space, capacity=total_rows, device=rank)
+            whole.add_synthetic(11, 0, total_rows, True)
+            whole.set_tuning("scan_half", 0)
+            for i in range(nq):
+                ref = whole.search(Q[i:i + 1], k)
+                for a, b in zip(got[i], ref):
+                    assert np.array_equal(a, b, equal_nan=True), f"single query {i} differs ({space}, tiers={tiers})"
+            for i in range(2):
+                ref = whole.search(Q[i:i + 1], k)
+                for a, b in zip(got_async[i], ref):
+                    assert np.array_equal(a, b, equal_nan=True), f"async single query {i} differs"
+            whole.close()
+        idx.close()
+
     def check_filtered(total_rows, dim, space, k, nq):
         """metadata column sharded with the rows, predicate evaluated per rank, filtered sharded search ==
         filtered unsharded search (fused exchange and NCCL paths)"""
@@ -198,6 +230,10 @@ def main():
     check_big_range(120_001, 16)                           # > 8192 hits per query: device-wide ordering
     check_filtered(150_001, 64, "cosine", 10, 4)           # filtered, fused exchange
     check_filtered(150_001, 64, "l2", 100, 3)              # filtered, NCCL merge path
+    check_single(200_003, 64, "cosine", 10, (1,))          # shadow scan on every rank + conditional fp32 launch
+    check_single(200_003, 96, "l2", 16, (1, -1))           # mixed: some ranks offer the shadow, some the fp32 scan
+    check_single(150_000, 64, "ip", 10, (-1,))             # nobody has a shadow: fp32 first launches, second ones skipped
+    check_single(1, 32, "l2", 1, (1,))                     # ranks 1.. hold nothing: exchange_only_kernel pairs
     check_protocol_index()                                 # reference Index protocol over the ranks
     dist.barrier()
     print(f"rank {rank} ok", flush=True)
