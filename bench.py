@@ -349,10 +349,14 @@ def run_ours(a):
     torch.cuda.synchronize()
     launches0 = shard.kernel_launches()
     merges0 = searcher.merge_launches if searcher else 0
+    half0 = shard.gemm_stats()
     sampler = ClockSampler(physical_gpu_index(ctx.local_rank))
     sampler.start()
     ms_total = ctx.timed(step_device, a.steps, streams)
     sampler.stop()
+    half1 = shard.gemm_stats()
+    half_q = half1["half_scan_queries"] - half0["half_scan_queries"]           # searches that read the fp16 shadow
+    half_u = half1["half_scan_uncertified"] - half0["half_scan_uncertified"]   # ... re-run by the fp32 launch behind
     launches = shard.kernel_launches() - launches0 + ((searcher.merge_launches - merges0) if searcher else 0)
     total_launches = int(ctx.sum_over_ranks(launches))
     n_queries = a.steps * qps_step
@@ -455,13 +459,35 @@ def run_ours(a):
                 traffic = json.load(f).get("dram_bytes_per_launch_at_bench_shape", {}).get(str(local_rows * a.dim * 4))
         except Exception:  # noqa: BLE001
             traffic = None
+    shadow = half_q * 2 >= n_queries      # the shadow scan answered (most of) the timed searches
+    kernel = "mlv::scan_kernel<ip,NQ=1,R> (TMA ring scan + fused top-k, final select"
+    moved = None
+    if shadow:
+        kernel = ("mlv::scan_kernel_half<ip,R> (TMA ring scan of the fp16 shadow of the rows + fused top-32, exact fp32 re-rank + "
+                  "certificate in the last CTA; an fp32 scan_kernel launch queued behind it returns at once unless the certificate failed")
+        ld16 = (a.dim + 7) // 8 * 8
+        # what the pass actually reads: the halves, the 32 re-ranked fp32 rows, and the fp32 pass of every uncertified query
+        moved = local_rows * ld16 * 2 + 32 * a.dim * 4 + (half_u / max(half_q, 1)) * bytes_per_launch
+        traffic_key = "dram_bytes_per_launch_shadow_scan"
+    else:
+        traffic_key = "dram_bytes_per_launch_at_bench_shape"
+    if os.path.exists(ncu_path):
+        try:
+            with open(ncu_path) as f:
+                traffic = json.load(f).get(traffic_key, {}).get(str(local_rows * a.dim * 4))
+        except Exception:  # noqa: BLE001
+            traffic = None
     roofline = {
-        "bound": "hbm", "kernel": "mlv::scan_kernel<ip,NQ=1,R> (TMA ring scan + fused top-k, final select"
-                                  + (", peer-memory exchange" if searcher is not None else "") + ")",
+        "bound": "hbm", "kernel": kernel + (", peer-memory exchange" if searcher is not None else "") + ")",
         "achieved": achieved, "peak": peak, "unit": "GB/s",
         "frac": achieved / peak, "peak_source": peak_src + " hbm_gbs, copy read+write", "traffic": traffic,
         "bytes_per_launch": bytes_per_launch, "launches_timed": n_queries, "mean_launch_ms": launch_ms,
-        "how": "algorithmic bytes per scan launch / (timed-region device time / scan launches in it)",
+        "how": "algorithmic bytes (SURVEY 8d: rows * dim * 4, the fp32 matrix) per search / (timed-region device time / searches in it)"
+               + ("; the shadow scan moves about half of them (bytes_moved_per_launch), so frac exceeds 1 by construction: "
+                  "frac_of_bytes_moved is the fraction of the HBM peak the pass actually sustains" if shadow else ""),
+        "bytes_moved_per_launch": moved,
+        "frac_of_bytes_moved": (moved / (launch_ms * 1e-3) / 1e9 / peak) if moved else None,
+        "shadow_scan": {"searches": int(half_q), "uncertified_rerun_in_fp32": int(half_u), "of_timed_searches": n_queries},
         "frac_of_nominal_8000": achieved / 8000.0,
         "one_query_in_flight": {"value": alone_steps * qps_step / (alone_ms / 1e3), "unit": UNIT,
                                 "how": "the same searches strictly one after another on one stream (device-timed)"},

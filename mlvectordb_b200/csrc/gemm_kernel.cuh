@@ -1004,15 +1004,6 @@ __global__ void scatter_results_kernel(const uint32_t* __restrict__ idx, uint32_
 }
 
 // ---- fp16 shadow of the rows (PASSES = 2) ---------------------------------------------------------
-// scale exponent for a largest magnitude `m`: 2^s with m * 2^s in [2^13, 2^14) (fp16 overflows at 2^16: two bits of
-// headroom for rows appended after the scale was frozen); m == 0 or not finite -> 0
-__host__ __device__ inline int f16_scale_exp(float m) {
-    if (!(m > 0.f) || m > 3.0e38f) return 0;
-    int ex;
-    frexpf(m, &ex);   // m = f * 2^ex, f in [0.5, 1)
-    int s = 14 - ex;
-    return s < -100 ? -100 : (s > 100 ? 100 : s);
-}
 // st[0] = 2^-s (float, what the epilogue multiplies by), st[1] = s (int), st[2] = overflow flag (cleared).
 // max_norm2_bits == nullptr: unit rows (cosine).
 __global__ void f16_freeze_scale_kernel(const uint32_t* max_norm2_bits, uint32_t* st) {

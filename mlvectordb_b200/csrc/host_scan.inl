@@ -22,16 +22,18 @@ uint32_t f16_ld(const mlv_index* h);
 int ensure_f16_shadow(mlv_index* h, cudaStream_t st, bool* usable);
 int ensure_row_norms(mlv_index* h, cudaStream_t st);
 
-// half: the launch reads the fp16 shadow (rows of f16_ld halves; the query stays fp32 in shared memory)
-int choose_cfg(mlv_index* h, uint32_t nq, uint32_t k, bool range, ScanCfg* c, bool gather = false, bool half = false) {
+// half: the launch reads the fp16 shadow (rows of f16_ld halves; the query stays fp32 in shared memory); 2 = with the
+// tensor-core consumers (16 rows per warp step, the query a second time as halves)
+int choose_cfg(mlv_index* h, uint32_t nq, uint32_t k, bool range, ScanCfg* c, bool gather = false, int half = 0) {
     const uint32_t ld4 = half ? f16_ld(h) / 8 : h->ld / 4;                    // 16-byte units per row
     const size_t rowbytes = (size_t)ld4 * 16;
-    const size_t qbytes = half ? (size_t)f16_ld(h) * 4 : rowbytes;             // one query in shared memory
+    const size_t qbytes = half ? (size_t)f16_ld(h) * 4 + (half == 2 ? rowbytes : 0) : rowbytes;   // one query in shared memory
     const uint32_t lcap = scan_list_cap(k);
-    int CW = h->tune_cw > 0 ? std::min(h->tune_cw, SCAN_MAX_CW) : (ld4 <= 64 ? 16 : 8);
+    int CW = h->tune_cw > 0 ? std::min(h->tune_cw, half == 2 ? 7 : SCAN_MAX_CW) : (half == 2 ? 4 : (ld4 <= 64 ? 16 : 8));
     if (!range && k > 512) CW = std::min(CW, 4);  // 2048-slot buffers: 4 warps keep the lists at 64 KB
     int R = h->tune_r ? h->tune_r : (ld4 <= 256 ? 4 : (ld4 <= 512 ? 2 : 1));
     if (R != 1 && R != 2 && R != 4) R = 1;
+    if (half == 2) R = 16;
     int NQ = 1;
     if (!range) {
         while (NQ < 8 && (uint32_t)NQ < nq) NQ <<= 1;
@@ -47,6 +49,9 @@ int choose_cfg(mlv_index* h, uint32_t nq, uint32_t k, bool range, ScanCfg* c, bo
     const size_t target = (size_t)(h->tune_stage_kb > 0 ? h->tune_stage_kb : (ld4 <= 32 ? 64 : 32)) * 1024;
     uint64_t m = std::max<uint64_t>(1, target / group_bytes);
     uint64_t T = (uint64_t)R * CW * m;
+    // tensor-core consumers: a warp takes 16 rows at a time and two warps keep up with the copies, so a tile is a
+    // multiple of 16 rows (~48 KB), not of 16 * CW
+    if (half == 2) T = 16 * std::max<uint64_t>(1, ((size_t)(h->tune_stage_kb > 0 ? h->tune_stage_kb : 48) * 1024) / (16 * rowbytes));
     if (T * rowbytes * 2 > avail) {
         T = (avail / 2 / rowbytes) / R * R;
         if (T == 0) {
@@ -135,7 +140,22 @@ cudaError_t launch_scan_half_t(const ScanParams& p, const ScanCfg& c, cudaStream
     return cudaGetLastError();
 }
 template <int METRIC>
+cudaError_t launch_scan_half_mma_t(const ScanParams& p, const ScanCfg& c, cudaStream_t st) {
+    auto kern = scan_kernel_half_mma<METRIC>;
+    static size_t raised[64] = {0};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64 || raised[dev] < c.smem) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c.smem);
+        if (e != cudaSuccess) return e;
+        if (dev >= 0 && dev < 64) raised[dev] = c.smem;
+    }
+    kern<<<c.grid, c.threads, c.smem, st>>>(p);
+    return cudaGetLastError();
+}
+template <int METRIC>
 cudaError_t launch_scan_half_m(const ScanParams& p, const ScanCfg& c, cudaStream_t st) {
+    if (c.R == 16) return launch_scan_half_mma_t<METRIC>(p, c, st);
     if (c.R == 1) return launch_scan_half_t<METRIC, 1>(p, c, st);
     if (c.R == 2) return launch_scan_half_t<METRIC, 2>(p, c, st);
     if (c.R == 4) return launch_scan_half_t<METRIC, 4>(p, c, st);
@@ -509,7 +529,10 @@ int search_prepared(mlv_index* h, const float* qprep, uint32_t nq, uint32_t k, c
             if ((rc = ensure_f16_shadow(h, st, &use_half)) != MLV_OK) return rc;
         }
         if (use_half) {
-            if ((rc = choose_cfg(h, 1, HALF_SCAN_KPRIME, false, &ch, false, true)) != MLV_OK) return rc;
+            // rows of whole 128-byte chunks: tensor-core consumers (the FMA consumers are FMA-latency bound at the
+            // power-capped clock: 6.5 of the fp32 pass's 7.4 TB/s)
+            const int half_kind = (f16_ld(h) % 64 == 0 && h->tune_scan_half_mma != 0) ? 2 : 1;
+            if ((rc = choose_cfg(h, 1, HALF_SCAN_KPRIME, false, &ch, false, half_kind)) != MLV_OK) return rc;
             // the tail's scratch (candidates | k' approximate | 32 exact | k final keys) overlays the ring and must leave
             // the query behind it alone
             const size_t scratch = ((size_t)fused_cap(ch, HALF_SCAN_KPRIME) + HALF_SCAN_KPRIME + 32 + k) * 8;

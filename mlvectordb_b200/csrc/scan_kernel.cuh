@@ -37,6 +37,16 @@ constexpr int scan_max_threads() {
     return NQ >= 4 ? (SCAN_WIDE_CW + SCAN_MAX_PW) * 32 : SCAN_MAX_THREADS;
 }
 
+// scale exponent for a largest magnitude `m`: 2^s with m * 2^s in [2^13, 2^14) (fp16 overflows at 2^16: two bits of
+// headroom for rows appended after the scale was frozen); m == 0 or not finite -> 0
+__host__ __device__ inline int f16_scale_exp(float m) {
+    if (!(m > 0.f) || m > 3.0e38f) return 0;
+    int ex;
+    frexpf(m, &ex);   // m = f * 2^ex, f in [0.5, 1)
+    int s = 14 - ex;
+    return s < -100 ? -100 : (s > 100 ? 100 : s);
+}
+
 constexpr uint32_t SCAN_FUSED_MAX_KEYS = 8192;  // keys the last CTA folds (gridDim.x * k): k <= 55 on 148 SMs
 
 struct ScanParams {
@@ -251,11 +261,23 @@ __device__ __forceinline__ uint32_t sorted_count_below(const uint64_t* list, uin
     return lo;
 }
 
-template <int METRIC, int NQ, int R, bool RANGE, bool INLINE, bool HALF = false>
+// D += A B: A 16 x 16 halves (row-major fragment a0..a3), B 16 x 8 halves (b0, b1), fp32 accumulators
+__device__ __forceinline__ void mma_m16n8k16_f16(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0,
+                                                 uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+                 : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+
+template <int METRIC, int NQ, int R, bool RANGE, bool INLINE, int HALF = 0>
 __device__ __forceinline__ void scan_body(const ScanParams& p, const float* iq) {
     constexpr int V = R * NQ;
     static_assert(V <= 32 && (V & (V - 1)) == 0, "R*NQ must be a power of two <= 32");
+    // HALF: 0 = the fp32 rows; 1 = the fp16 shadow, FMA consumers; 2 = the fp16 shadow, tensor-core consumers
+    // (mma.sync m16n8k16 on 16 rows x 64 halves per step, the query as halves too; rows of a multiple of 64 halves)
     static_assert(!HALF || (NQ == 1 && !RANGE && !INLINE), "the shadow scan takes one prepared query, top-k mode");
+    static_assert(HALF != 2 || R == 16, "the tensor-core consumers score 16 rows per step");
+    constexpr bool HMMA = HALF == 2;
     extern __shared__ __align__(128) unsigned char smem[];
     // fallback launch behind a shadow scan: nothing to do when that one certified its answer
     if (p.run_if && *reinterpret_cast<const volatile uint32_t*>(p.run_if) == 0) return;
@@ -276,13 +298,15 @@ __device__ __forceinline__ void scan_body(const ScanParams& p, const float* iq) 
     const uint32_t lcap = p.list_cap;             // slots per (warp, query) list
     const bool buffered = lcap > k;               // append buffer + compaction instead of replace-max
     const uint32_t ldq4 = HALF ? 2 * ld4 : ld4;   // float4 per query in shared memory (HALF: ld4 counts 8-half units)
-    uint64_t* lists = reinterpret_cast<uint64_t*>(qs + (size_t)NQ * ldq4);        // [CW][NQ][lcap]
+    // HMMA: the query once more as halves of q * 2^t ([ld4] 16-byte units), behind the fp32 copy the re-rank reads
+    const unsigned char* q16 = reinterpret_cast<const unsigned char*>(qs + (size_t)NQ * ldq4);
+    uint64_t* lists = reinterpret_cast<uint64_t*>(qs + (size_t)NQ * ldq4 + (HMMA ? ld4 : 0));   // [CW][NQ][lcap]
     uint64_t* full = lists + (RANGE ? 0 : (size_t)CW * NQ * lcap);                // [S]
     uint64_t* empty = full + S;                                                   // [S]
     StageMeta* meta = reinterpret_cast<StageMeta*>(empty + S);                    // [S]
 
     float half_qn = 0.f;                                                           // HALF: |q|^2
-    const float half_us = HALF ? __uint_as_float(__ldg(p.half_state)) : 1.0f;      // HALF: 2^-s of the shadow
+    float half_us = HALF ? __uint_as_float(__ldg(p.half_state)) : 1.0f;            // HALF: 2^-s of the shadow (x 2^-t of the query)
     if (tid == 0) {
         for (uint32_t s = 0; s < S; s++) {
             mbar_init(&full[s], 1);
@@ -313,7 +337,7 @@ __device__ __forceinline__ void scan_body(const ScanParams& p, const float* iq) 
         }
     } else if (HALF) {
         // the fp32 prepared query, zero padded to the shadow's row length; |q|^2 for the l2 form and the certificate
-        __shared__ float s_qn_init;
+        __shared__ float s_qn_init, s_q_unscale;
         for (uint32_t i = tid; i < ldq4; i += blockDim.x)
             qs[i] = i < p.ld4_exact ? p.queries[i] : make_float4(0.f, 0.f, 0.f, 0.f);
         __syncthreads();
@@ -329,9 +353,29 @@ __device__ __forceinline__ void scan_body(const ScanParams& p, const float* iq) 
 #pragma unroll
             for (int off = 16; off >= 1; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
             if (lane == 0) s_qn_init = acc;
+            if (HMMA) {
+                // halves of q * 2^t, t from the largest component (split_queries_f16_kernel's rule); zero padding stays zero
+                float m = 0.f;
+                for (uint32_t j = lane; j < p.ld4_exact; j += 32) {
+                    const float4 v = qs[j];
+                    m = fmaxf(m, fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w))));
+                }
+#pragma unroll
+                for (int off = 16; off >= 1; off >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, off));
+                const int sq = f16_scale_exp(m);
+                const float scale = ldexpf(1.0f, sq);
+                if (lane == 0) s_q_unscale = ldexpf(1.0f, -sq);
+                __half2* dst = reinterpret_cast<__half2*>(const_cast<unsigned char*>(q16));
+                for (uint32_t j = lane; j < ldq4; j += 32) {   // ldq4 float4 = ld16 floats -> ld16 halves
+                    const float4 v = qs[j];
+                    dst[2 * j] = __floats2half2_rn(v.x * scale, v.y * scale);
+                    dst[2 * j + 1] = __floats2half2_rn(v.z * scale, v.w * scale);
+                }
+            }
         }
         __syncthreads();
         half_qn = s_qn_init;
+        if (HMMA) half_us *= s_q_unscale;
     } else {
         // queries -> shared (missing queries of a short group repeat the last one; masked later)
         for (uint32_t i = tid; i < NQ * ld4; i += blockDim.x) {
@@ -423,9 +467,11 @@ __device__ __forceinline__ void scan_body(const ScanParams& p, const float* iq) 
 
     // ---------------------------------------------------------------------- consumers
     const int slot = lane_slot<V>(lane);     // which (row-in-group, query) total this lane ends up with
-    const int my_r = slot / NQ;
-    const int my_q = slot - my_r * NQ;
-    const bool rep = (lane & (32 / V - 1)) == 0;  // one representative lane per slot
+    // HMMA: lane (g, t) = (lane / 4, lane % 4) of the accumulator fragment holds rows g and g + 8; t == 0 speaks for
+    // row g, t == 1 for row g + 8
+    const int my_r = HMMA ? ((lane >> 2) + ((lane & 3) == 1 ? 8 : 0)) : slot / NQ;
+    const int my_q = HMMA ? 0 : slot - my_r * NQ;
+    const bool rep = HMMA ? (lane & 3) < 2 : (lane & (32 / V - 1)) == 0;  // one representative lane per slot
     const bool q_ok = (uint32_t)my_q < p.nq_valid;
     uint64_t thr = KEY_SENTINEL;                  // current k-th best of list (warp, my_q)
     uint64_t* my_lists = lists + (size_t)warp * NQ * lcap;
@@ -480,7 +526,40 @@ __device__ __forceinline__ void scan_body(const ScanParams& p, const float* iq) 
             const float4* trow = tile + (size_t)base * ld4;
             float xn = 0.f;
             if (HALF && METRIC == METRIC_L2) xn = __ldg(p.row_norms + (p.gather ? row : pos));   // own slot's row; in flight during the dot products
-            if (HALF) {
+            float s_mma = 0.f;
+            if constexpr (HMMA) {
+                // Tensor-core consumers.  The dot product does not care in which order k is walked, as long as rows and
+                // query agree: lane (g, t) feeds the fragment slots (row g / g + 8, k 2t.. and 2t + 8..) with the 16 bytes
+                // at offset 16 (t + 4 ((g & 1) ^ step)) of the rows' current 128-byte chunk, and the B fragment (column n
+                // = g) with the query's 16 bytes at the SAME offset -- so every quarter-warp reads 128 contiguous bytes
+                // of two rows (no bank conflicts on rows a multiple of 128 bytes apart), and column n of the result is
+                // right for the rows of n's parity.  Two steps cover the chunk; two accumulator sets halve the MMA chain.
+                const int g = lane >> 2, t = lane & 3;
+                const uint32_t rowbytes = ld4 * 16;
+                const unsigned char* r0 = reinterpret_cast<const unsigned char*>(tile) + (size_t)(base + g) * rowbytes;
+                const unsigned char* r1 = r0 + 8 * (size_t)rowbytes;
+                float c[4] = {0.f, 0.f, 0.f, 0.f}, d[4] = {0.f, 0.f, 0.f, 0.f};
+                const uint32_t o0 = (uint32_t)(t + 4 * (g & 1)) * 16, o1 = (uint32_t)(t + 4 * ((g & 1) ^ 1)) * 16;
+                for (uint32_t ch = 0; ch < rowbytes; ch += 128) {
+                    {
+                        const uint4 xa = *reinterpret_cast<const uint4*>(r0 + ch + o0);
+                        const uint4 xb = *reinterpret_cast<const uint4*>(r1 + ch + o0);
+                        const uint4 qv = *reinterpret_cast<const uint4*>(q16 + ch + o0);
+                        mma_m16n8k16_f16(c, xa.x, xb.x, xa.y, xb.y, qv.x, qv.y);
+                        mma_m16n8k16_f16(d, xa.z, xb.z, xa.w, xb.w, qv.z, qv.w);
+                    }
+                    {
+                        const uint4 xa = *reinterpret_cast<const uint4*>(r0 + ch + o1);
+                        const uint4 xb = *reinterpret_cast<const uint4*>(r1 + ch + o1);
+                        const uint4 qv = *reinterpret_cast<const uint4*>(q16 + ch + o1);
+                        mma_m16n8k16_f16(c, xa.x, xb.x, xa.y, xb.y, qv.x, qv.y);
+                        mma_m16n8k16_f16(d, xa.z, xb.z, xa.w, xb.w, qv.z, qv.w);
+                    }
+                }
+                // lane (g, t) holds C[g][2t], C[g][2t+1], C[g+8][2t], C[g+8][2t+1]: the column of the row's parity
+                const float lo = (g & 1) ? c[1] + d[1] : c[0] + d[0], hi = (g & 1) ? c[3] + d[3] : c[2] + d[2];
+                s_mma = t == 0 ? lo : hi;
+            } else if (HALF) {
                 // 8 halves of the row against 8 floats of the query per step; the sum is a plain dot product (the
                 // distance form is applied below): only candidates are chosen with it
                 float acc2[V];
@@ -526,7 +605,7 @@ __device__ __forceinline__ void scan_body(const ScanParams& p, const float* iq) 
                     }
                 }
             }
-            const float s = transpose_reduce<V>(acc, lane);
+            const float s = HMMA ? s_mma : transpose_reduce<V>(acc, lane);
             float dist;
             if (HALF)   // approximate: the GEMM form on the shadow's dot product
                 dist = (METRIC == METRIC_IP) ? 1.0f - half_us * s : fmaf(-2.0f * half_us, s, xn + half_qn);
@@ -912,7 +991,12 @@ __global__ void __launch_bounds__(scan_max_threads<NQ>(), 1) scan_kernel(const S
 // one query over the fp16 shadow of the rows, exact re-rank + certificate in the fused tail (ScanParams::rows_exact)
 template <int METRIC, int R>
 __global__ void __launch_bounds__(SCAN_MAX_THREADS, 1) scan_kernel_half(const ScanParams p) {
-    scan_body<METRIC, 1, R, false, false, true>(p, nullptr);
+    scan_body<METRIC, 1, R, false, false, 1>(p, nullptr);
+}
+// ... with tensor-core consumers (rows of a multiple of 64 halves): 16 rows per warp step
+template <int METRIC>
+__global__ void __launch_bounds__(256, 1) scan_kernel_half_mma(const ScanParams p) {   // <= 7 consumer warps + 1 producer
+    scan_body<METRIC, 1, 16, false, false, 2>(p, nullptr);
 }
 // one query whose raw values travel in the launch parameters (batch-1 latency path)
 template <int METRIC, int R, bool RANGE>

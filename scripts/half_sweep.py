@@ -40,8 +40,8 @@ def run(half, **kw):
 
 print(json.dumps(run(0)), flush=True)
 print(json.dumps(run(1)), flush=True)
-for cw in (8, 12, 16):
-    for r in (1, 2, 4):
+for cw in (2, 4, 6):
+    for r in (0,):
         for kb in (24, 48, 96):
             print(json.dumps(run(1, cw=cw, r=r, stage_kb=kb)), flush=True)
 for ms_ in (4, 16):

@@ -24,6 +24,12 @@ def _half_vs_plain(s, Q, k, filt=None):
     s.set_tuning("scan_half", 0)
     ref = [s.search(Q[i:i + 1], k, filt) for i in range(len(Q))]
     s.set_tuning("scan_half", 1)
+    if s.dim % 64 == 0:       # rows of whole 128-byte chunks take the tensor-core consumers: the FMA consumers must agree
+        s.set_tuning("scan_half_mma", 0)
+        for i in range(len(Q)):
+            assert _same(s.search(Q[i:i + 1], k, filt), ref[i]), f"query {i}: shadow scan (FMA consumers) differs from the fp32 scan"
+        s.set_tuning("scan_half_mma", 1)
+        s.set_tuning("scan_half", 1)      # (resets the sit-out state for the counted run)
     before = s.gemm_stats()
     got = [s.search(Q[i:i + 1], k, filt) for i in range(len(Q))]
     after = s.gemm_stats()
@@ -33,9 +39,9 @@ def _half_vs_plain(s, Q, k, filt=None):
 
 
 @pytest.mark.parametrize("space", ["l2", "ip", "cosine"])
-@pytest.mark.parametrize("k", [1, 10, 16])
-def test_shadow_scan_equals_the_fp32_scan_and_the_oracle(space, k):
-    n, dim, nq = 60_000, 96, 12
+@pytest.mark.parametrize("k,dim", [(1, 96), (10, 96), (16, 96), (10, 128), (16, 192), (10, 768)])
+def test_shadow_scan_equals_the_fp32_scan_and_the_oracle(space, k, dim):
+    n, nq = (60_000 if dim < 768 else 20_011), 12      # dim 96: FMA consumers; 128 / 192 / 768: tensor-core consumers
     X = synthetic.rows(71, 0, n, dim, scaled=True)
     Q = synthetic.queries(72, nq, dim)
     Q[3] = X[777]                       # a stored row: distance ~0 for l2 / cosine
@@ -123,8 +129,9 @@ def test_shadow_overflow_is_caught_on_the_device_and_the_shadow_rebuilt():
     s.add(X)
     _half_vs_plain(s, Q, k)                                # freezes the shadow's scale
     s.add(X[:40] * np.float32(3.0e4))                      # far beyond it: fp16 overflow when these rows are converted
-    got, used, uncert = _half_vs_plain(s, Q, k)
-    assert uncert >= 1                                     # flagged by the kernel, answered by the fp32 launch
+    before = s.gemm_stats()["half_scan_uncertified"]
+    _half_vs_plain(s, Q, k)
+    assert s.gemm_stats()["half_scan_uncertified"] > before   # flagged by the kernel, answered by the fp32 launch
     _half_vs_plain(s, Q, k)                                # the shadow is rebuilt with a new scale; still the fp32 bits
     # (with rows 3e4 times larger than the rest the certificate's margin -- relative to the largest norm -- is too wide
     # for ordinary neighbours; take the outliers away and the tier certifies again)
