@@ -353,8 +353,22 @@ int mlv_index_scan_time_ms(mlv_index_t h, double *total_ms, uint64_t *launches);
  * final select, 0 = separate select kernel), "gather" (-1 auto, 0 = filters stream every row and mask,
  * 1 = filters always gather; the tensor-core path compacts the passing rows accordingly), "staged_upload"
  * (1 = bulk mlv_index_add through two pinned chunks filled by worker threads, 0 = plain copy), "fast_host" (1 = single-query
- * mlv_index_search takes the one-launch latency path, 0 = always staged), and the
+ * mlv_index_search takes the one-launch latency path, 0 = always staged), "scan_half" / "scan_half_mma" (below), and the
  * tensor-core keys listed at mlv_index_gemm_stats}.  Results never depend on these.
+ *
+ * Shadow scan ("scan_half": -1 auto = matrices of 256 MB and more, 0 never, 1 whenever the shape allows).  A SINGLE
+ * query with k <= 16 (no gathered filter) reads an fp16 shadow of the rows -- half the bytes of the HBM-bound pass; the
+ * shadow (rows * 2^s, 2 bytes per element, built on first use and kept up to date like the row norms: + 50 % device
+ * memory; without room for it the search is the fp32 one) is the one the tensor-core tier uses -- keeps 32 candidates by
+ * approximate distance, and the last CTA re-scores them from the fp32 matrix in the scan's own arithmetic and certifies
+ * the answer (rows outside the candidates are at least the 32nd approximate distance minus the fp16 error bound away).
+ * An fp32 scan launch is queued right behind it and returns at once unless the certificate failed, so the fallback is
+ * decided on the device and the call stays asynchronous; the results are the fp32 scan's bit for bit either way.
+ * "scan_half_mma" (1 default): rows of whole 128-byte chunks are scored by tensor-core consumers (mma.sync), 0 = FMA
+ * consumers.  A shadow that certifies less than half of its searches sits out 64, 128, ... searches.  In an exchange
+ * search every rank issues the same two launches whether or not it has a shadow to read (the ranks agree on the
+ * certificate through the exchange itself), so "scan_half" must be 0 on all ranks or on none.
+ * mlv_index_gemm_stats reports half_scan_queries / half_scan_uncertified.
  */
 int mlv_index_set_tuning(mlv_index_t h, const char *key, int value);
 /*

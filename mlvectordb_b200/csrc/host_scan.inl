@@ -34,6 +34,7 @@ int choose_cfg(mlv_index* h, uint32_t nq, uint32_t k, bool range, ScanCfg* c, bo
     int R = h->tune_r ? h->tune_r : (ld4 <= 256 ? 4 : (ld4 <= 512 ? 2 : 1));
     if (R != 1 && R != 2 && R != 4) R = 1;
     if (half == 2) R = 16;
+    if (half == 1) CW = std::min(CW, SCAN_WIDE_CW);   // launch bounds of scan_kernel_half
     int NQ = 1;
     if (!range) {
         while (NQ < 8 && (uint32_t)NQ < nq) NQ <<= 1;

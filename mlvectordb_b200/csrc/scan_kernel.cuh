@@ -801,7 +801,23 @@ __device__ __forceinline__ void scan_body(const ScanParams& p, const float* iq) 
             // A much tighter bound when a warp's worth of lists holds at least k valid FIRST keys: sorted across the lanes,
             // the k-th of them has k keys <= it, so the global k-th best is too.  On 148 lists of 10 it leaves ~40
             // survivors instead of ~250 (whose O(m^2) ranking cost 7 us), for one register sort per warp.
-            if (k <= 32) {
+            if (k > 16 && k <= n_lists) {
+                // ... for larger k (the shadow scan's k' = 32) a warp's worth of heads says little (its k-th is its
+                // largest); the k-th smallest of ALL the heads does: ranked by counting in the still unused candidate
+                // array.  Without it ~1000 of 148 x 32 keys survived and went through the bitonic network (16 us).
+                for (uint32_t l = tid; l < n_lists; l += nthr) cand[l] = __ldcg(keys + (size_t)l * k);
+                named_bar_sync(1, CW * 32);
+                for (uint32_t l = tid; l < n_lists; l += nthr) {
+                    const uint64_t key = cand[l];
+                    uint32_t rank = 0;
+#pragma unroll 8
+                    for (uint32_t i = 0; i < n_lists; i++) {
+                        const uint64_t o = cand[i];
+                        rank += (o < key) || (o == key && i < l);
+                    }
+                    if (rank == k - 1 && key != KEY_SENTINEL) atomicMin(&s_T, (unsigned long long)key);
+                }
+            } else if (k <= 32) {
                 for (uint32_t l0 = (uint32_t)warp * 32u; l0 < n_lists; l0 += nthr) {
                     const uint32_t l = l0 + (uint32_t)lane;
                     uint64_t hd = l < n_lists ? __ldcg(keys + (size_t)l * k) : KEY_SENTINEL;
@@ -813,9 +829,15 @@ __device__ __forceinline__ void scan_body(const ScanParams& p, const float* iq) 
             named_bar_sync(1, CW * 32);
             if (p.timeline && tid == 0) p.timeline[blockIdx.x * 16 + 11] = global_timer_ns();   // threshold known
             const uint64_t T = s_T;
-            for (uint32_t i = tid; i < n; i += nthr) {
-                const uint64_t key = __ldcg(keys + i);
-                if (key <= T) cand[atomicAdd(&s_m, 1u)] = key;
+            // four independent loads per thread and step: with k' = 32 keys per block list (shadow scan) and few consumer
+            // warps this loop was 10 us of dependent L2 round trips
+            for (uint32_t i0 = tid; i0 < n; i0 += 4 * nthr) {
+                uint64_t key[4];
+#pragma unroll
+                for (int u = 0; u < 4; u++) key[u] = i0 + u * nthr < n ? __ldcg(keys + i0 + u * nthr) : KEY_SENTINEL;
+#pragma unroll
+                for (int u = 0; u < 4; u++)
+                    if (i0 + u * nthr < n && key[u] <= T) cand[atomicAdd(&s_m, 1u)] = key[u];
             }
             named_bar_sync(1, CW * 32);
             if (p.timeline && tid == 0) p.timeline[blockIdx.x * 16 + 12] = global_timer_ns();   // survivors gathered
@@ -868,22 +890,34 @@ __device__ __forceinline__ void scan_body(const ScanParams& p, const float* iq) 
             uint64_t* ex = top + (size_t)p.nq_valid * k;        // [nq][32] exact keys, unsorted
             uint64_t* fx = ex + (size_t)p.nq_valid * 32;        // [nq][k_out] exact keys, ascending
             if (tid == 0) s_uncert = 0;
-            for (uint32_t e = (uint32_t)warp; e < p.nq_valid * k; e += (uint32_t)CW) {
-                const uint32_t qi = e / k, i = e - qi * k;
-                const uint64_t key = top[e];
-                uint64_t out = KEY_SENTINEL;
-                if (key != KEY_SENTINEL) {   // warp-uniform
-                    const uint32_t row = key_row(key);
-                    const float4* xrow = p.rows_exact + (size_t)row * p.ld4_exact;
-                    const float4* qv = qs + (size_t)qi * ldq4;
-                    // the scan's own arithmetic: lane l sums float4 columns l, l + 32, ..., butterfly over the lanes
-                    float acc = 0.f;
-                    for (uint32_t j = lane; j < p.ld4_exact; j += 32) acc = accum4<METRIC>(acc, xrow[j], qv[j]);
+            // four candidates per warp at a time: their rows are four independent HBM round trips (a candidate at a time
+            // cost ~1.5 us each, 8 per warp); per candidate the scan's own arithmetic -- lane l sums float4 columns l,
+            // l + 32, ..., butterfly over the lanes
+            for (uint32_t e0 = (uint32_t)warp * 4u; e0 < p.nq_valid * k; e0 += (uint32_t)CW * 4u) {
+                uint64_t keys[4];
+                const float4* xrow[4];
+                float acc[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-                    for (int off = 16; off >= 1; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
-                    out = make_key((METRIC == METRIC_IP) ? 1.0f - acc : acc, row);
+                for (int u = 0; u < 4; u++) {
+                    keys[u] = e0 + u < p.nq_valid * k ? top[e0 + u] : KEY_SENTINEL;
+                    xrow[u] = p.rows_exact + (size_t)(keys[u] != KEY_SENTINEL ? key_row(keys[u]) : 0u) * p.ld4_exact;
                 }
-                if (lane == 0) ex[qi * 32 + i] = out;
+                const float4* qv = qs + (size_t)(e0 / k) * ldq4;   // k is a multiple of 4: the four share their query
+                for (uint32_t j = lane; j < p.ld4_exact; j += 32) {
+                    const float4 q4 = qv[j];
+#pragma unroll
+                    for (int u = 0; u < 4; u++) acc[u] = accum4<METRIC>(acc[u], __ldg(xrow[u] + j), q4);
+                }
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    float a = acc[u];
+#pragma unroll
+                    for (int off = 16; off >= 1; off >>= 1) a += __shfl_xor_sync(0xffffffffu, a, off);
+                    if (lane == 0 && e0 + u < p.nq_valid * k) {
+                        const uint32_t qi = (e0 + u) / k, i = (e0 + u) - qi * k;
+                        ex[qi * 32 + i] = keys[u] != KEY_SENTINEL ? make_key((METRIC == METRIC_IP) ? 1.0f - a : a, key_row(keys[u])) : KEY_SENTINEL;
+                    }
+                }
             }
             named_bar_sync(1, CW * 32);
             if ((uint32_t)warp < p.nq_valid) {
@@ -990,7 +1024,7 @@ __global__ void __launch_bounds__(scan_max_threads<NQ>(), 1) scan_kernel(const S
 }
 // one query over the fp16 shadow of the rows, exact re-rank + certificate in the fused tail (ScanParams::rows_exact)
 template <int METRIC, int R>
-__global__ void __launch_bounds__(SCAN_MAX_THREADS, 1) scan_kernel_half(const ScanParams p) {
+__global__ void __launch_bounds__(scan_max_threads<4>(), 1) scan_kernel_half(const ScanParams p) {   // <= 8 consumer warps
     scan_body<METRIC, 1, R, false, false, 1>(p, nullptr);
 }
 // ... with tensor-core consumers (rows of a multiple of 64 halves): 16 rows per warp step

@@ -4,6 +4,7 @@ For --seconds S it draws random shapes (rows, dim, metric, k, batch width, tombs
 every way the library can answer the same question returns the same BITS as the exact scan:
 
   * tensor-core path in a random tier / kernel configuration (gemm_passes 0-3, gemm_wide 0-3, gemm_predict 0/1) == scan path
+  * shadow scan (fp16 shadow + exact re-rank + certificate, FMA or tensor-core consumers) == fp32 scan
   * one-launch latency path (single query) == staged path == row of a batch
   * gathered filter == stream + mask filter == per-call bitmap
   * range search at the k-th distance contains the kNN answer
@@ -83,6 +84,14 @@ while time.time() < t_end:
             s.set_tuning("gemm", 0)
             s.set_tuning("gemm_passes", 0)
             s.set_tuning("gemm_wide", 3)
+        # shadow scan (single query, k <= 16) == fp32 scan
+        if k <= 16 and dim >= 8:
+            s.set_tuning("scan_half", 1)
+            s.set_tuning("scan_half_mma", int(rng.integers(0, 2)))
+            one = s.search(Q[:1], k, filt)
+            s.set_tuning("scan_half", 0)
+            if not same(one, tuple(x[:1] for x in ref)):
+                fail("shadow scan != fp32 scan", filtered=filt is not None, **ctx)
         # latency path == staged path == batch row
         if filt is None:
             fast = s.search(Q[:1], k)
