@@ -80,8 +80,28 @@ bool gemm_eligible(const mlv_index* h, uint32_t nq, uint32_t k) {
     return nq >= gemm_min_nq(h, k) && h->rows >= 16384;
 }
 
+// Order `st` behind the last norm / shadow maintenance if that ran on another stream; call before using either.
+int maint_wait(mlv_index* h, cudaStream_t st) {
+    if (!h->maint_gen) return MLV_OK;
+    Lane* ln = lane_for(h, st);
+    if (ln->seen_maint == h->maint_gen) return MLV_OK;
+    if (st != h->maint_stream) CK(h, cudaStreamWaitEvent(st, h->maint_event, 0));
+    ln->seen_maint = h->maint_gen;
+    return MLV_OK;
+}
+// ... and publish maintenance work just queued on `st`
+int maint_done(mlv_index* h, cudaStream_t st) {
+    if (!h->maint_event) CK(h, cudaEventCreateWithFlags(&h->maint_event, cudaEventDisableTiming));
+    CK(h, cudaEventRecord(h->maint_event, st));
+    h->maint_gen++;
+    h->maint_stream = st;
+    lane_for(h, st)->seen_maint = h->maint_gen;
+    return MLV_OK;
+}
+
 int ensure_row_norms(mlv_index* h, cudaStream_t st) {
     int rc;
+    if ((rc = maint_wait(h, st)) != MLV_OK) return rc;
     if (!h->d_maxn2.p) {
         if ((rc = ensure_dev(h, h->d_maxn2, 4)) != MLV_OK) return rc;
         CK(h, cudaMemsetAsync(h->d_maxn2.p, 0, 4, st));
@@ -103,6 +123,7 @@ int ensure_row_norms(mlv_index* h, cudaStream_t st) {
         h->launches++;
         CK(h, cudaGetLastError());
         h->norms_valid = h->rows;
+        if ((rc = maint_done(h, st)) != MLV_OK) return rc;
     }
     return MLV_OK;
 }
@@ -187,6 +208,10 @@ cudaError_t launch_gemm_pair(const CUtensorMap& mx, const CUtensorMap& mq, const
 // Returns MLV_OK with *usable = false when there is no room for it (the caller takes the TF32 tier).
 int ensure_f16_shadow(mlv_index* h, cudaStream_t st, bool* usable) {
     *usable = false;
+    {
+        const int rcw = maint_wait(h, st);
+        if (rcw != MLV_OK) return rcw;
+    }
     const uint32_t ld16 = f16_ld(h);
     if (h->d_rows16.bytes < (size_t)h->rows * ld16 * 2) {
         free_dev(h->d_rows16);
@@ -211,6 +236,7 @@ int ensure_f16_shadow(mlv_index* h, cudaStream_t st, bool* usable) {
         h->launches++;
         CK(h, cudaGetLastError());
         h->f16_valid = h->rows;
+        if ((rc = maint_done(h, st)) != MLV_OK) return rc;
     }
     *usable = true;
     return MLV_OK;

@@ -126,9 +126,9 @@ cudaError_t launch_scan_m(const ScanParams& p, const ScanCfg& c, cudaStream_t st
     return cudaErrorInvalidValue;
 }
 
-template <int METRIC, int R>
+template <int METRIC, int R, bool RANGE>
 cudaError_t launch_scan_half_t(const ScanParams& p, const ScanCfg& c, cudaStream_t st) {
-    auto kern = scan_kernel_half<METRIC, R>;
+    auto kern = scan_kernel_half<METRIC, R, RANGE>;
     static size_t raised[64] = {0};
     int dev = 0;
     cudaGetDevice(&dev);
@@ -140,9 +140,9 @@ cudaError_t launch_scan_half_t(const ScanParams& p, const ScanCfg& c, cudaStream
     kern<<<c.grid, c.threads, c.smem, st>>>(p);
     return cudaGetLastError();
 }
-template <int METRIC>
+template <int METRIC, bool RANGE>
 cudaError_t launch_scan_half_mma_t(const ScanParams& p, const ScanCfg& c, cudaStream_t st) {
-    auto kern = scan_kernel_half_mma<METRIC>;
+    auto kern = scan_kernel_half_mma<METRIC, RANGE>;
     static size_t raised[64] = {0};
     int dev = 0;
     cudaGetDevice(&dev);
@@ -154,12 +154,12 @@ cudaError_t launch_scan_half_mma_t(const ScanParams& p, const ScanCfg& c, cudaSt
     kern<<<c.grid, c.threads, c.smem, st>>>(p);
     return cudaGetLastError();
 }
-template <int METRIC>
+template <int METRIC, bool RANGE = false>
 cudaError_t launch_scan_half_m(const ScanParams& p, const ScanCfg& c, cudaStream_t st) {
-    if (c.R == 16) return launch_scan_half_mma_t<METRIC>(p, c, st);
-    if (c.R == 1) return launch_scan_half_t<METRIC, 1>(p, c, st);
-    if (c.R == 2) return launch_scan_half_t<METRIC, 2>(p, c, st);
-    if (c.R == 4) return launch_scan_half_t<METRIC, 4>(p, c, st);
+    if (c.R == 16) return launch_scan_half_mma_t<METRIC, RANGE>(p, c, st);
+    if (c.R == 1) return launch_scan_half_t<METRIC, 1, RANGE>(p, c, st);
+    if (c.R == 2) return launch_scan_half_t<METRIC, 2, RANGE>(p, c, st);
+    if (c.R == 4) return launch_scan_half_t<METRIC, 4, RANGE>(p, c, st);
     return cudaErrorInvalidValue;
 }
 
@@ -459,6 +459,67 @@ void half_scan_policy(mlv_index* h) {
         h->half_seen_q = q;
         h->half_seen_u = u;
     }
+}
+
+// Shadow RANGE scan: the decision (this rank's own -- nothing about it shows in an exchange) and the launch shape.
+// On success *use = true, *c holds the half configuration and p describes the shadow (radius etc. are the caller's).
+int half_range_setup(mlv_index* h, const FilterPlan& fp, Lane* ln, cudaStream_t st, bool* use, ScanCfg* c, ScanParams* p) {
+    *use = false;
+    if (h->tune_scan_half == 0 || fp.gather || h->ld < 8 || !h->tune_dynamic) return MLV_OK;
+    if (h->tune_scan_half != 1 && (uint64_t)h->rows * h->ld * 4 < (256ull << 20)) return MLV_OK;
+    int rc;
+    if (h->h_half_stats.p && ((volatile uint32_t*)h->h_half_stats.p)[2]) {   // a kernel met an overflowed shadow: rebuild it
+        ((volatile uint32_t*)h->h_half_stats.p)[2] = 0;
+        h->f16_valid = 0;
+    }
+    if (h->metric != MLV_COSINE && (rc = ensure_row_norms(h, st)) != MLV_OK) return rc;
+    bool usable = false;
+    if ((rc = ensure_f16_shadow(h, st, &usable)) != MLV_OK) return rc;
+    if (!usable) return MLV_OK;
+    if (!h->h_half_stats.p) {
+        if ((rc = ensure_dev(h, h->d_half_stats, 8)) != MLV_OK) return rc;
+        CK(h, cudaMemsetAsync(h->d_half_stats.p, 0, 8, st));
+        if ((rc = ensure_host(h, h->h_half_stats, 16)) != MLV_OK) return rc;
+        memset(h->h_half_stats.p, 0, 16);
+    }
+    const int half_kind = (f16_ld(h) % 64 == 0 && h->tune_scan_half_mma != 0) ? 2 : 1;
+    if ((rc = choose_cfg(h, 1, 1, true, c, false, half_kind)) != MLV_OK) return rc;
+    *p = scan_params(h, *c, fp, ln, 1);
+    p->rows = reinterpret_cast<const float4*>(h->d_rows16.p);
+    p->ld4 = f16_ld(h) / 8;
+    p->rows_exact = reinterpret_cast<const float4*>(h->d_rows);
+    p->ld4_exact = h->ld / 4;
+    p->half_state = (const uint32_t*)h->d_f16st.p;
+    p->row_norms = h->metric == MLV_L2 ? (const float*)h->d_norms.p : nullptr;
+    p->max_norm2_bits = h->metric == MLV_COSINE ? nullptr : (const uint32_t*)h->d_maxn2.p;
+    p->delta_rel = gemm_delta_rel_f16_host(h->metric == MLV_L2, h->ld);
+    p->cosine = h->metric == MLV_COSINE;
+    p->half_stats_host = (volatile uint32_t*)h->h_half_stats.p;
+    *use = true;
+    return MLV_OK;
+}
+cudaError_t launch_scan_half_range(mlv_index* h, const ScanParams& p, const ScanCfg& c, cudaStream_t st) {
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    if (h->timing) {
+        for (cudaEvent_t* ev : {&e0, &e1}) {
+            if (!h->event_pool.empty()) {
+                *ev = h->event_pool.back();
+                h->event_pool.pop_back();
+            } else {
+                cudaError_t e = cudaEventCreate(ev);
+                if (e != cudaSuccess) return e;
+            }
+        }
+        cudaEventRecord(e0, st);
+    }
+    const cudaError_t e = h->metric == MLV_L2 ? launch_scan_half_m<METRIC_L2, true>(p, c, st) : launch_scan_half_m<METRIC_IP, true>(p, c, st);
+    h->launches++;
+    h->half_scan_launches++;
+    if (h->timing) {
+        cudaEventRecord(e1, st);
+        h->pending.emplace_back(e0, e1);
+    }
+    return e;
 }
 
 int search_prepared(mlv_index* h, const float* qprep, uint32_t nq, uint32_t k, const uint32_t* filter_dev, float* out_d,

@@ -24,6 +24,7 @@ struct Lane {
     DevBuf d_q, d_keys0, d_keys1, d_sched;
     DevBuf d_flist, d_fscratch;  // gather list built from a per-call filter bitmap
     DevBuf d_cert;               // shadow scan: the word its conditional fp32 launch reads (scan_kernel.cuh, ScanParams::cert)
+    uint64_t seen_maint = 0;     // mlv_index::maint_gen this stream has been ordered behind
 };
 
 // One asynchronous host-buffer search in flight (mlv_index_submit / mlv_index_collect): its own
@@ -131,6 +132,11 @@ struct mlv_index {
     uint32_t half_seen_q = 0, half_seen_u = 0;   // mirror values at the last policy check
     uint32_t half_skip = 0, half_backoff = 0;    // searches the shadow scan sits out after certifying too little
     uint64_t half_scan_launches = 0;
+    // row norms and the fp16 shadow are (re)built on whichever stream first needs them; a search on ANOTHER stream that
+    // finds them "valid" must still be ordered behind that work
+    cudaEvent_t maint_event = nullptr;
+    uint64_t maint_gen = 0;
+    cudaStream_t maint_stream = nullptr;
     bool half_stepped = false;                   // the latency-path probe of this search already stepped the policy
     int tune_gemm = -1;        // -1 auto, 0 never, 1 whenever the shape allows it
     int tune_gemm_min_nq = 0;  // 0 = auto (gemm_min_nq: 5 with the one-pass tier on a >= 1 GB matrix, else 9)

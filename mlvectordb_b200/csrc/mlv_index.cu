@@ -161,6 +161,7 @@ int mlv_index_destroy(mlv_index_t h) {
     if (h->h_stage.p) cudaFreeHost(h->h_stage.p);
     if (h->h_range.p) cudaFreeHost(h->h_range.p);
     if (h->h_half_stats.p) cudaFreeHost(h->h_half_stats.p);
+    if (h->maint_event) cudaEventDestroy(h->maint_event);
     if (h->h_upload.p) cudaFreeHost(h->h_upload.p);
     for (AsyncSlot& sl : h->slots) {
         if (sl.stream) cudaStreamSynchronize(sl.stream);
@@ -1001,6 +1002,16 @@ int mlv_index_range_search_device(mlv_index_t h, const float* queries_dev, uint3
     if ((rc = choose_cfg(h, 1, 1, true, &c, fp.gather != nullptr)) != MLV_OK) return rc;
     if ((rc = ensure_sched(h, ln)) != MLV_OK) return rc;
     ScanParams p = scan_params(h, c, fp, ln, 1);
+    bool half = false;   // shadow range scan: half the bytes, candidates re-scored exactly in the kernel (scan_kernel.cuh)
+    {
+        ScanCfg ch;
+        ScanParams ph;
+        if ((rc = half_range_setup(h, fp, ln, st, &half, &ch, &ph)) != MLV_OK) return rc;
+        if (half) {
+            c = ch;
+            p = ph;
+        }
+    }
     p.radius = radius;
     p.max_hits = max_hits;
     for (uint32_t q = 0; q < nq; q++) {
@@ -1008,7 +1019,7 @@ int mlv_index_range_search_device(mlv_index_t h, const float* queries_dev, uint3
         p.nq_valid = 1;
         p.range_counts = d_counts + q;
         p.range_keys = d_keys + (size_t)q * slots;
-        CK(h, launch_scan(h, p, c, true, st));
+        CK(h, half ? launch_scan_half_range(h, p, c, st) : launch_scan(h, p, c, true, st));
     }
     CK(h, cudaFuncSetAttribute(range_finish_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SELECT_MAX_P * 8)));
     range_finish_kernel<<<nq, SELECT_THREADS, (size_t)SELECT_MAX_P * 8, st>>>(d_keys, d_counts, slots, max_hits, h->row_base, out_dists_dev,
@@ -1105,8 +1116,18 @@ int mlv_index_range_search_exchange_device(mlv_index_t h, const float* queries_d
     ScanCfg c;
     if ((rc = choose_cfg(h, 1, 1, true, &c, fp.gather != nullptr)) != MLV_OK) return rc;
     if ((rc = ensure_sched(h, ln)) != MLV_OK) return rc;
-    c.smem = std::max(c.smem, (size_t)XCHG_SLOT_KEYS * 8);   // the last CTA sorts / merges up to a slot's worth of keys
     ScanParams p = scan_params(h, c, fp, ln, 1);
+    bool half = false;   // this rank's own choice: its hit list is exact either way
+    {
+        ScanCfg ch;
+        ScanParams ph;
+        if ((rc = half_range_setup(h, fp, ln, st, &half, &ch, &ph)) != MLV_OK) return rc;
+        if (half) {
+            c = ch;
+            p = ph;
+        }
+    }
+    c.smem = std::max(c.smem, (size_t)XCHG_SLOT_KEYS * 8);   // the last CTA sorts / merges up to a slot's worth of keys
     p.radius = radius;
     p.max_hits = share;
     p.fused = 1;
@@ -1120,7 +1141,7 @@ int mlv_index_range_search_exchange_device(mlv_index_t h, const float* queries_d
         p.out_rows = out_rows_dev + (size_t)q * XCHG_SLOT_KEYS;
         p.range_out_count = (unsigned long long*)out_counts_dev + q;
         p.xchg.seq = ++h->xseq;
-        CK(h, launch_scan(h, p, c, true, st));
+        CK(h, half ? launch_scan_half_range(h, p, c, st) : launch_scan(h, p, c, true, st));
     }
     return MLV_OK;
 }

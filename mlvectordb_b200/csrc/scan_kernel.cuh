@@ -275,7 +275,7 @@ __device__ __forceinline__ void scan_body(const ScanParams& p, const float* iq) 
     static_assert(V <= 32 && (V & (V - 1)) == 0, "R*NQ must be a power of two <= 32");
     // HALF: 0 = the fp32 rows; 1 = the fp16 shadow, FMA consumers; 2 = the fp16 shadow, tensor-core consumers
     // (mma.sync m16n8k16 on 16 rows x 64 halves per step, the query as halves too; rows of a multiple of 64 halves)
-    static_assert(!HALF || (NQ == 1 && !RANGE && !INLINE), "the shadow scan takes one prepared query, top-k mode");
+    static_assert(!HALF || (NQ == 1 && !INLINE), "the shadow scan takes one prepared query");
     static_assert(HALF != 2 || R == 16, "the tensor-core consumers score 16 rows per step");
     constexpr bool HMMA = HALF == 2;
     extern __shared__ __align__(128) unsigned char smem[];
@@ -306,6 +306,7 @@ __device__ __forceinline__ void scan_body(const ScanParams& p, const float* iq) 
     StageMeta* meta = reinterpret_cast<StageMeta*>(empty + S);                    // [S]
 
     float half_qn = 0.f;                                                           // HALF: |q|^2
+    float half_margin = 0.f;                                                       // HALF range mode: candidate margin
     float half_us = HALF ? __uint_as_float(__ldg(p.half_state)) : 1.0f;            // HALF: 2^-s of the shadow (x 2^-t of the query)
     if (tid == 0) {
         for (uint32_t s = 0; s < S; s++) {
@@ -376,6 +377,20 @@ __device__ __forceinline__ void scan_body(const ScanParams& p, const float* iq) 
         __syncthreads();
         half_qn = s_qn_init;
         if (HMMA) half_us *= s_q_unscale;
+        if (RANGE) {
+            // shadow range scan: a row is a CANDIDATE when its approximate distance is within the fp16 error bound of the
+            // radius; candidates are re-scored from the fp32 matrix on the spot and tested exactly, so the hit list is the
+            // fp32 scan's by construction -- no certificate, no second launch.  An overflowed shadow makes every row a
+            // candidate (slow once, still exact; the host rebuilds the shadow when it sees the flag in the mirror).
+            float scale = 1.0f;
+            if (!p.cosine) {
+                const float xmax = sqrtf(__uint_as_float(*p.max_norm2_bits)), qsn = sqrtf(half_qn);
+                scale = (METRIC == METRIC_L2) ? (xmax + qsn) * (xmax + qsn) : xmax * qsn;
+            }
+            const bool over = __ldg(p.half_state + 2) != 0;
+            half_margin = over ? __int_as_float(0x7f800000) : p.delta_rel * scale;
+            if (over && p.half_stats_host && blockIdx.x == 0 && tid == 0) p.half_stats_host[2] = 1;
+        }
     } else {
         // queries -> shared (missing queries of a short group repeat the last one; masked later)
         for (uint32_t i = tid; i < NQ * ld4; i += blockDim.x) {
@@ -613,7 +628,25 @@ __device__ __forceinline__ void scan_body(const ScanParams& p, const float* iq) 
                 dist = (METRIC == METRIC_IP) ? 1.0f - s : s;
             const uint64_t key = make_key(dist, row);
             const bool ok = rep && q_ok && my_local < (uint32_t)n && ((wl & wf) >> (rowc & 31) & 1u);
-            if (RANGE) {
+            if (RANGE && HALF) {
+                // candidates (NaN included) -> exact distance by the whole warp, the scan's own arithmetic
+                unsigned cm = __ballot_sync(0xffffffffu, ok && !(dist > p.radius + half_margin));
+                while (cm) {
+                    const int src = __ffs(cm) - 1;
+                    cm &= cm - 1;
+                    const uint32_t crow = __shfl_sync(0xffffffffu, row, src);
+                    const float4* xrow = p.rows_exact + (size_t)crow * p.ld4_exact;
+                    float acc = 0.f;
+                    for (uint32_t j = lane; j < p.ld4_exact; j += 32) acc = accum4<METRIC>(acc, __ldg(xrow + j), qs[j]);
+#pragma unroll
+                    for (int off = 16; off >= 1; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+                    const float exact = (METRIC == METRIC_IP) ? 1.0f - acc : acc;
+                    if (lane == 0 && exact <= p.radius) {
+                        unsigned long long pos = atomicAdd(p.range_counts, 1ull);
+                        if (pos < p.max_hits) p.range_keys[pos] = make_key(exact, crow);
+                    }
+                }
+            } else if (RANGE) {
                 if (ok && dist <= p.radius) {
                     unsigned long long pos = atomicAdd(p.range_counts + my_q, 1ull);
                     if (pos < p.max_hits) p.range_keys[(size_t)my_q * p.max_hits + pos] = key;
@@ -1023,14 +1056,14 @@ __global__ void __launch_bounds__(scan_max_threads<NQ>(), 1) scan_kernel(const S
     scan_body<METRIC, NQ, R, RANGE, false>(p, nullptr);
 }
 // one query over the fp16 shadow of the rows, exact re-rank + certificate in the fused tail (ScanParams::rows_exact)
-template <int METRIC, int R>
+template <int METRIC, int R, bool RANGE = false>
 __global__ void __launch_bounds__(scan_max_threads<4>(), 1) scan_kernel_half(const ScanParams p) {   // <= 8 consumer warps
-    scan_body<METRIC, 1, R, false, false, 1>(p, nullptr);
+    scan_body<METRIC, 1, R, RANGE, false, 1>(p, nullptr);
 }
 // ... with tensor-core consumers (rows of a multiple of 64 halves): 16 rows per warp step
-template <int METRIC>
+template <int METRIC, bool RANGE = false>
 __global__ void __launch_bounds__(256, 1) scan_kernel_half_mma(const ScanParams p) {   // <= 7 consumer warps + 1 producer
-    scan_body<METRIC, 1, 16, false, false, 2>(p, nullptr);
+    scan_body<METRIC, 1, 16, RANGE, false, 2>(p, nullptr);
 }
 // one query whose raw values travel in the launch parameters (batch-1 latency path)
 template <int METRIC, int R, bool RANGE>

@@ -90,10 +90,19 @@ def main():
         st = idx.shard.gemm_stats()
         if tiers[rank % len(tiers)] == 1 and idx.hi > idx.lo:
             assert st["half_scan_queries"] >= nq, st
+        # range search with the same per-rank tiers (shadow range scan on some ranks, fp32 on others): radius = the 5th
+        # distance of query 0, agreed through rank 0
+        rad = torch.zeros(1, dtype=torch.float64, device=device)
+        if rank == 0:
+            rad[0] = float(got[0][0][0, min(4, int(got[0][2][0]) - 1)]) if int(got[0][2][0]) > 0 else 1.0
+        dist.broadcast(rad, 0)
+        got_range = idx.range_search(Q[:3], float(rad.item()))
         if rank == 0:
             whole = DeviceShard(dim, space, capacity=total_rows, device=rank)
             whole.add_synthetic(11, 0, total_rows, True)
             whole.set_tuning("scan_half", 0)
+            for (gd, gr), (hd, hr) in zip(got_range, whole.range_search(Q[:3], float(rad.item()))):
+                assert np.array_equal(gr, hr) and np.array_equal(gd, hd), f"sharded range (tiers={tiers}) differs from unsharded"
             for i in range(nq):
                 ref = whole.search(Q[i:i + 1], k)
                 for a, b in zip(got[i], ref):

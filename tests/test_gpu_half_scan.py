@@ -167,3 +167,44 @@ def test_device_api_two_streams_in_flight():
         d, r, c = (t.cpu().numpy() for t in outs[i])
         assert _same((d, r, c), ref[1][i]), i
     s.close()
+
+
+@pytest.mark.parametrize("space", ["l2", "ip", "cosine"])
+@pytest.mark.parametrize("dim", [96, 128])
+def test_shadow_range_scan_returns_the_fp32_hit_lists(space, dim):
+    """Range mode over the shadow: rows whose approximate distance is within the fp16 bound of the radius are re-scored
+    from the fp32 matrix inside the kernel and tested exactly -- the hit lists are the fp32 scan's, bit for bit, with
+    tombstones and a streamed filter, at radii that cut through crowded distances, and with an overflowed shadow."""
+    n, nq = 50_000, 6
+    X = synthetic.rows(91, 0, n, dim, scaled=(space != "l2"))
+    Q = synthetic.queries(92, nq, dim)
+    s = _shard(dim, space, capacity=n + 64)
+    s.add(X)
+    s.mark_deleted(np.arange(3, n, 11, dtype=np.uint64))
+    s.set_tuning("scan_half", 0)
+    d10, _, _ = s.search(Q, 40)
+
+    def both(radius, filt=None):
+        s.set_tuning("scan_half", 0)
+        ref = s.range_search(Q, radius, filt)
+        s.set_tuning("scan_half", 1)
+        got = s.range_search(Q, radius, filt)
+        assert len(got) == len(ref)
+        for (gd, gr), (rd, rr) in zip(got, ref):
+            assert np.array_equal(gr, rr) and np.array_equal(gd, rd)
+        return got
+
+    for j in (0, 9, 39):                                   # radius = an actual distance: the boundary row must be in
+        got = both(float(d10[0, j]))
+        assert len(got[0][1]) >= j + 1
+    mask = np.random.default_rng(3).random(n) < 0.5
+    pf = s.prepare_filter(mask)
+    s.set_tuning("gather", 0)
+    both(float(d10[1, 20]), pf)
+    s.set_tuning("gather", -1)
+    pf.close()
+    if space != "cosine":
+        s.add(X[:8] * np.float32(3.0e4))                   # overflows the frozen scale: every row becomes a candidate
+        both(float(d10[2, 15]))
+        both(float(d10[2, 15]))                            # ... and the shadow has been rebuilt
+    s.close()
