@@ -68,6 +68,8 @@ def parse_args():
     ap.add_argument("--queries-per-step", type=int, default=32)
     ap.add_argument("--inflight", type=int, default=2,
                     help="independent batch-1 queries in flight (one CUDA stream each); 1 = strictly one at a time")
+    ap.add_argument("--e2e-inflight", type=int, default=4,
+                    help="requests in flight through the asynchronous public API in the e2e measurement (1..4: the handle's async slots)")
     ap.add_argument("--cpu-sample-rows", type=int, default=1_000_000)
     ap.add_argument("--cpu-queries", type=int, default=48)
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -328,7 +330,9 @@ def run_ours(a):
     def api_search(j):
         return index.search(VectorDTO(values=Q[j], metadata={}), top_k=k, namespace=ns, metric=a.space)
 
-    def step_e2e(depth=inflight):
+    e2e_depth = max(1, min(a.e2e_inflight, 4))
+
+    def step_e2e(depth=e2e_depth):
         # host query in, host List[SearchResult] out, per query; `depth` requests in flight through the asynchronous
         # public API (search_async / .result()), 1 = the plain synchronous search() call
         last, pending = None, []
@@ -383,7 +387,7 @@ def run_ours(a):
         ctx.barrier()
         return n_queries / dt, out
 
-    e2e_value, last = time_e2e(inflight)
+    e2e_value, last = time_e2e(e2e_depth)
     e2e_sync_value, last_sync = time_e2e(1)
 
     # ---- parity gate (untimed): timed queries vs the streamed oracle over ALL rows -----------------------------------
@@ -502,7 +506,7 @@ def run_ours(a):
         "dtype": "f32", "data": "synthetic", "config": workload_config(a, world),
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": qps_step * a.dim * 4,
                 "d2h_bytes_per_step": qps_step * (k * 12 + 4),
-                "api": f"{api}.search_async(VectorDTO, top_k, namespace, metric).result() -> List[SearchResult], {inflight} requests in flight",
+                "api": f"{api}.search_async(VectorDTO, top_k, namespace, metric).result() -> List[SearchResult], {e2e_depth} requests in flight",
                 "one_request_at_a_time": {"value": e2e_sync_value, "unit": UNIT,
                                           "api": f"{api}.search(VectorDTO, top_k, namespace, metric) -> List[SearchResult]"}},
         "parity": parity, "roofline": roofline, "clocks": sampler.summary(), "gpu_launches": total_launches,

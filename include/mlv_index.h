@@ -287,8 +287,8 @@ int mlv_format_f32_json(const float *values, uint64_t n, char *out, uint64_t cap
  * A peer that does not arrive within the exchange timeout (5 s by default; MLV_EXCHANGE_TIMEOUT_MS in the
  * environment or mlv_exchange_set_timeout_ms) raises an error flag (mlv_exchange_check) instead of hanging
  * the GPU; the searches of that launch report count -1.  After a timeout the ranks' sequence numbers are out
- * of step: destroy and re-create the exchange on every rank.  At most two exchange searches may be in flight
- * per handle (mlv_index_submit refuses a third).
+ * of step: destroy and re-create the exchange on every rank.  At most four exchange searches may be in flight
+ * per handle (mlv_index_submit refuses a fifth).
  */
 typedef struct mlv_exchange *mlv_exchange_t;
 #define MLV_EXCHANGE_HANDLE_BYTES 64

@@ -5,11 +5,9 @@
 // last CTA of a rank's scan writes its k best keys per query straight into every peer's buffer
 // (plain stores to peer-mapped addresses), publishes a sequence number with st.release.sys and
 // waits with ld.acquire.sys until every peer's sequence number has arrived in its own buffer;
-// then it merges the world * k candidates.  Slots are indexed by seq mod XCHG_SLOTS and at most TWO exchange
+// then it merges the world * k candidates.  Slots are indexed by seq mod XCHG_SLOTS and at most XCHG_MAX_IN_FLIGHT exchange
 // searches are in flight per handle (mlv_index_submit enforces it; the synchronous entry points run one
-// at a time): a rank can only reach search s+4 after it collected s+2, i.e. after every peer has
-// posted s+2, and a peer posts s+2 only after it finished reading slot s (two in flight: s+2 starts on
-// a slot's stream after s left it, or after the host collected s).
+// at a time); the slot count follows from that (see XCHG_SLOTS).
 // The reference has no counterpart (single process; README.md:142-155 sketches sharding only).
 #pragma once
 #include "common.cuh"
@@ -20,8 +18,12 @@ constexpr uint32_t XCHG_MAX_WORLD = 16;
 constexpr uint32_t XCHG_MAX_NQ = 8;   // queries per scan launch
 constexpr uint32_t XCHG_MAX_K = 64;   // the fused exchange handles k <= 64 (55 in practice: 148 SMs * k <= 8192 keys)
 constexpr uint32_t XCHG_SLOT_KEYS = XCHG_MAX_WORLD * XCHG_MAX_NQ * XCHG_MAX_K;  // u64 keys per parity slot
-constexpr uint32_t XCHG_SLOTS = 8;   // a search may take two launches (first tier + conditional fp32): the same search
-                                     // distance between two uses of a slot as four slots gave one-launch searches
+// A search may take two launches (first tier + conditional fp32), i.e. two sequence numbers, and up to FOUR exchange
+// searches may be in flight per handle: a rank launches search i + 8 (the next user of search i's slots) only after it
+// collected search i + 4, i.e. after every peer posted i + 4 -- and a peer that posts i + 4 has at most i + 1 .. i + 3 still
+// in flight, so its read of search i's slot is over.  16 slots = 4 x (searches in flight).
+constexpr uint32_t XCHG_SLOTS = 16;
+constexpr int XCHG_MAX_IN_FLIGHT = 4;
 // buffer layout (u64 words): keys[XCHG_SLOTS][XCHG_MAX_WORLD][XCHG_MAX_NQ][XCHG_MAX_K], flags[XCHG_SLOTS][XCHG_MAX_WORLD]
 constexpr uint32_t XCHG_FLAGS_OFF = XCHG_SLOTS * XCHG_SLOT_KEYS;
 // ... and, for range searches, counts[XCHG_SLOTS][XCHG_MAX_WORLD]: how many hits a rank's list holds (bit 63: too many

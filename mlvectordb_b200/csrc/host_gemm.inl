@@ -69,6 +69,9 @@ bool gemm_1pass_ok(const mlv_index* h, uint32_t k);
 uint32_t gemm_min_nq(const mlv_index* h, uint32_t k) {
     if (h->tune_gemm_min_nq > 0) return (uint32_t)h->tune_gemm_min_nq;
     const bool big = (uint64_t)h->rows * h->ld * 4 >= (1ull << 30);
+    // with the fp16 shadow a pass over the rows costs HALF a one-query fp32 scan (10M x 768: 2.37 ms for up to 64 queries
+    // against 4.1 ms): two queries already pay for it -- and two shadow scans cost 4.3 ms (profiles/r02_batch_surface_768.jsonl)
+    if (gemm_1pass_ok(h, k) && big && h->tune_gemm_passes != 1 && h->tune_gemm_passes != 3 && h->d_rows16.p) return 2u;
     return gemm_1pass_ok(h, k) && big ? 5u : 9u;
 }
 

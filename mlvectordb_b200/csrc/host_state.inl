@@ -37,7 +37,7 @@ struct AsyncSlot {
     DevBuf d_q, d_out;
     uint32_t nq = 0, k = 0;
     bool busy = false;
-    bool exchange = false;   // an exchange search: at most two of those may be in flight (exchange.cuh slot reuse)
+    bool exchange = false;   // an exchange search: at most XCHG_MAX_IN_FLIGHT of those may be in flight (exchange.cuh slot reuse)
 };
 
 struct ScanCfg {

@@ -924,7 +924,7 @@ int mlv_index_submit(mlv_index_t h, const float* queries, uint32_t nq, uint32_t 
     if (exchange) {
         int flying = 0;
         for (const AsyncSlot& s2 : h->slots) flying += s2.busy && s2.exchange;
-        if (flying >= 2) return fail(h, MLV_E_UNSUPPORTED, "two exchange searches are in flight already: collect one first");
+        if (flying >= XCHG_MAX_IN_FLIGHT) return fail(h, MLV_E_UNSUPPORTED, "four exchange searches are in flight already: collect one first");
     }
     h->next_slot = (uint32_t)(idx + 1) % MLV_ASYNC_SLOTS;
     AsyncSlot& sl = h->slots[idx];

@@ -234,7 +234,7 @@ class ShardedIndex:
 
     def search_async(self, queries: np.ndarray, k: int):
         """Collective.  Start a search and return a handle whose ``.result()`` gives what ``search`` returns;
-        a caller that keeps two in flight hides each request's copies and launch latency behind the other's scan.
+        a caller that keeps a few in flight (at most four) hides each request's copies and launch latency behind the others' scans.
         Needs the fused exchange path (k small, batch < EXCHANGE_MAX_NQ); otherwise the search runs synchronously."""
         q = np.ascontiguousarray(queries, dtype=np.float32).reshape(-1, self.dim)
         if self.device is not None and self.shard is not None and q.shape[0] < self.EXCHANGE_MAX_NQ and (

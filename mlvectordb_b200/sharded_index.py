@@ -273,7 +273,7 @@ class ShardedGpuIndex:
 
     def search_async(self, query: VectorDTO, top_k: int, namespace: str, metric: str) -> PendingResults:
         """``search`` that returns at once (collective: every rank submits the same sequence); ``.result()`` gives the
-        ``List[SearchResult]``.  At most two in flight."""
+        ``List[SearchResult]``.  At most four in flight."""
         ns, q, k = self._prepare(query, top_k, namespace)
         if ns is None:
             return PendingResults(None, None, metric)

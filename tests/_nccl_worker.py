@@ -85,7 +85,7 @@ def main():
         if total_rows > 5:
             Q[0] = synthetic.rows(11, total_rows - 2, 1, dim, scaled=True)[0]
         got = [idx.search(Q[i:i + 1], k) for i in range(nq)]
-        handles = [idx.search_async(Q[i:i + 1], k) for i in range(2)]      # two in flight
+        handles = [idx.search_async(Q[i:i + 1], k) for i in range(4)]      # four in flight: the exchange's limit
         got_async = [hnd.result() for hnd in handles]
         st = idx.shard.gemm_stats()
         if tiers[rank % len(tiers)] == 1 and idx.hi > idx.lo:
@@ -107,7 +107,7 @@ def main():
                 ref = whole.search(Q[i:i + 1], k)
                 for a, b in zip(got[i], ref):
                     assert np.array_equal(a, b, equal_nan=True), f"single query {i} differs ({space}, tiers={tiers})"
-            for i in range(2):
+            for i in range(4):
                 ref = whole.search(Q[i:i + 1], k)
                 for a, b in zip(got_async[i], ref):
                     assert np.array_equal(a, b, equal_nan=True), f"async single query {i} differs"
