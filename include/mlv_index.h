@@ -389,8 +389,7 @@ int mlv_index_debug_timeline(mlv_index_t h, uint64_t *out, uint32_t max_ctas, ui
  * certifies is re-run by the exact scan, so results do not depend on the path.  set_tuning keys: "gemm"
  * (-1 auto, 0 never, 1 whenever the shape allows), "gemm_min_nq", "gemm_passes" (0 auto, 1 one-pass TF32 tier
  * then scan, 2 fp16 tier then scan, 3 3xTF32 tier only), "gemm_wide" (which kernel runs the one-pass tiers of
- * batches wider than 128 queries: 3 = CTA pairs, tcgen05 cta_group::2 (default); 1 = two row tiles per staged
- * query tile; 2 = the same in clusters of two with the query tile by TMA multicast; 0 = the single-tile kernel),
+ * batches wider than 128 queries: non-zero = CTA pairs, tcgen05 cta_group::2 (default); 0 = the single-tile kernel),
  * "gemm_debug" (profiling only: bit 0 = the epilogue compares nothing -- results are wrong), "gemm_predict" (1 default: the one-pass tiers' per-query thresholds are PREDICTED from the rows
  * seen so far -- a round that has seen S of N rows thresholds at its max(32, 4 k' S / N)-th best instead of its k'-th,
  * so later rounds append a fraction of the candidates; the last round verifies the prediction (k' candidates at or

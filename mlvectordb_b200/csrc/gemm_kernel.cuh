@@ -554,40 +554,11 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
     }
 }
 
-// ---- the wide one-pass kernel: TWO row tiles per staged query tile -------------------------------------------------
-// ncu (r02) showed the one-pass tiers of gemm_topk_kernel pinned at the L2 -> SM delivery limit (xbar2l1tex 11.2 TB/s, the
-// chip's ~6300 B/clk; tensor pipe 35 - 43 % active): a 128 x 256 tile pulls (128 + 256) operand rows per K chunk.  This
-// kernel keeps TWO accumulators (2 x 256 TMEM columns = all 512) and feeds both from one staged query tile, so an item is
-// 256 rows x 256 queries and pulls (256 + 256) operand rows for twice the products: 2/3 of the bytes per product.  With
-// CL = 2 the two CTAs of a cluster work on the same query tile (four consecutive row tiles) and each loads HALF of it,
-// multicast into both CTAs' shared memory: (256 + 128) rows per 256 x 256 products, half of the single-tile kernel's.
-// The accumulators are not double-buffered any more; instead two groups of four epilogue warps drain them side by side,
-// and with the cheap pre-test (epilogue_drain) that drain is ~1/5 of the tile's tensor time.
-// PASSES is 1 (TF32 on the fp32 rows) or GEMM_TIER_F16 (fp16 shadow); BN is 256.  576 threads:
-//   warp 0 TMA producer | warp 1 MMA issuer | warps 2-9 drain accumulator 0 | warps 10-17 drain accumulator 1
-// (a warp may only read the TMEM lanes 32 * (warp % 4) ..: the two warps of a group that share a lane quarter split the
-// 256 columns in halves.  With the MMAs and loads alone the kernel runs at 96 % of the bf16 tensor peak -- the drain is
-// what is left to hide, and it is latency-bound, so more warps shorten it.)
-constexpr int GEMM2_THREADS = 64 + 16 * 32;
-constexpr int GEMM2_BN = 256;
-constexpr int GEMM2_STAGES = 3;
-constexpr uint32_t GEMM2_Q_BYTES = GEMM2_BN * GEMM_BK * 4;                    // 32 KB
-constexpr uint32_t GEMM2_STAGE_BYTES = 2 * GEMM_X_BYTES + GEMM2_Q_BYTES;      // X0 | X1 | Q = 64 KB
-constexpr uint32_t GEMM2_HITQ = 88;    // 16 warps x 1.7 KB: what the 227 KB leave beside the ring
-constexpr uint32_t GEMM2_SMEM_BYTES = 1024 + GEMM2_STAGES * GEMM2_STAGE_BYTES + 5 * GEMM2_BN * 4 + 256 + 16 * sizeof(HitQueue<GEMM2_HITQ>);
+// (A "wide" single-CTA kernel -- two row tiles per staged query tile, 16 drain warps, optionally clusters of two sharing the
+// query tile by TMA multicast -- lived here during round 2: 57.5k q/s on config 3 against the CTA-pair kernel's 65 - 70k on
+// every shape measured, and its 576 threads left the rewritten epilogue 130 bytes of spills.  Removed; the numbers are in
+// profiles/README.md.)
 
-__device__ __forceinline__ void tma_load_2d_mc(void* smem_dst, const CUtensorMap* map, int32_t c0, int32_t c1, uint64_t* bar, uint16_t mask) {
-    asm volatile(
-        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], [%2], %5;" ::"r"(
-            smem_u32(smem_dst)),
-        "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "h"(mask)
-        : "memory");
-}
-__device__ __forceinline__ void tc_commit_mc(uint64_t* bar, uint16_t mask) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)),
-                 "h"(mask)
-                 : "memory");
-}
 __device__ __forceinline__ void cluster_sync_all() {
     asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
@@ -595,172 +566,6 @@ __device__ __forceinline__ uint32_t cluster_ctarank() {
     uint32_t r;
     asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
     return r;
-}
-
-template <int METRIC, int PASSES, int CL>
-__global__ void __launch_bounds__(GEMM2_THREADS, 1)
-gemm_topk2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_q, const GemmParams p) {
-    static_assert(PASSES == 1 || PASSES == GEMM_TIER_F16, "one-pass tiers only");
-    static_assert(CL == 1 || CL == 2, "cluster of one or two CTAs");
-    constexpr bool F16 = PASSES == GEMM_TIER_F16;
-    constexpr uint32_t CHUNK_ELEMS = F16 ? 64 : 32;
-    constexpr uint32_t IDESC = GemmShape<GEMM2_BN, PASSES>::IDESC;
-    constexpr uint32_t Q_OFF = 2 * GEMM_X_BYTES;
-    extern __shared__ unsigned char gemm_smem_raw[];
-    unsigned char* smem = gemm_smem_raw + ((1024u - (smem_u32(gemm_smem_raw) & 1023u)) & 1023u);
-    float* thr_s = reinterpret_cast<float*>(smem + GEMM2_STAGES * GEMM2_STAGE_BYTES);
-    float* qn_s = thr_s + GEMM2_BN;
-    float* us_s = qn_s + GEMM2_BN;
-    float* c1_s = us_s + GEMM2_BN;
-    float* c2_s = c1_s + GEMM2_BN;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(c2_s + GEMM2_BN);
-    uint64_t* full = bars;                       // [S]  TMA bytes landed (own loads + the peer's multicast half)
-    uint64_t* empty = bars + GEMM2_STAGES;       // [S]  every CTA of the cluster has retired the MMAs reading the stage
-    uint64_t* tfull = bars + 2 * GEMM2_STAGES;   // [1]  both accumulators complete
-    uint64_t* tempty = tfull + 1;                // [2]  accumulator a drained (4 warps each)
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
-    using HitQ = HitQueue<GEMM2_HITQ>;
-    HitQ* hqs = reinterpret_cast<HitQ*>(reinterpret_cast<unsigned char*>(bars) + 256);   // [16] one per epilogue warp
-
-    const int tid = threadIdx.x;
-    const int warp = tid >> 5;
-    const int lane = tid & 31;
-    const uint32_t crank = CL > 1 ? cluster_ctarank() : 0;
-    const uint16_t all_mask = (uint16_t)((1u << CL) - 1u);
-
-    if (tid == 0) {
-        for (int s = 0; s < GEMM2_STAGES; s++) {
-            mbar_init(&full[s], 1);
-            mbar_init(&empty[s], CL);
-        }
-        mbar_init(tfull, 1);
-        mbar_init(&tempty[0], 8);
-        mbar_init(&tempty[1], 8);
-        mbar_fence_init();
-        tma_prefetch_desc(&tm_x);
-        tma_prefetch_desc(&tm_q);
-    }
-    if (warp == 1) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u) : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-    }
-    tc_fence_before();
-    __syncthreads();
-    if (CL > 1) cluster_sync_all();   // the peer's barriers exist before anything is multicast into this CTA
-    tc_fence_after();
-    const uint32_t tmem_base = *tmem_slot;
-
-    // items: (group of 2 * CL consecutive row tiles) x (query tile); the cluster's CTAs take the same item together
-    const uint32_t tiles = p.row_tile1 - p.row_tile0;
-    const uint32_t n_groups = (tiles + 2 * CL - 1) / (2 * CL);
-    const uint32_t n_items = n_groups * p.n_qtiles;
-    const uint32_t cluster_id = blockIdx.x / CL, n_clusters = gridDim.x / CL;
-
-    if (warp == 0) {
-        // ------------------------------------------------------------------ TMA producer
-        if (lane == 0) {
-            uint32_t stage = 0, phase = 0;
-            for (uint32_t it = cluster_id; it < n_items; it += n_clusters) {
-                const uint32_t grp = it / p.n_qtiles, qt = it % p.n_qtiles;
-                const uint32_t rt = p.row_tile0 + (grp * CL + crank) * 2;
-                for (uint32_t kc = 0; kc < p.n_kchunks; kc++) {
-                    mbar_wait(&empty[stage], phase ^ 1);
-                    unsigned char* sb = smem + (size_t)stage * GEMM2_STAGE_BYTES;
-                    mbar_arrive_expect_tx(&full[stage], GEMM2_STAGE_BYTES);
-                    tma_load_2d(sb, &tm_x, (int32_t)(kc * CHUNK_ELEMS), (int32_t)(rt * GEMM_BM), &full[stage]);
-                    tma_load_2d(sb + GEMM_X_BYTES, &tm_x, (int32_t)(kc * CHUNK_ELEMS), (int32_t)((rt + 1) * GEMM_BM), &full[stage]);
-                    if (CL == 1) {
-                        tma_load_2d(sb + Q_OFF, &tm_q, (int32_t)(kc * CHUNK_ELEMS), (int32_t)(qt * GEMM2_BN), &full[stage]);
-                    } else {
-                        // this CTA's half of the query tile (box of BN / 2 rows) lands in BOTH CTAs, at the same offset
-                        tma_load_2d_mc(sb + Q_OFF + crank * (GEMM2_Q_BYTES / 2), &tm_q, (int32_t)(kc * CHUNK_ELEMS),
-                                       (int32_t)(qt * GEMM2_BN + crank * (GEMM2_BN / 2)), &full[stage], all_mask);
-                    }
-                    if (++stage == GEMM2_STAGES) {
-                        stage = 0;
-                        phase ^= 1;
-                    }
-                }
-            }
-        }
-    } else if (warp == 1) {
-        // ------------------------------------------------------------------ MMA issuer
-        if (lane == 0) {
-            uint32_t stage = 0, phase = 0, local = 0;
-            for (uint32_t it = cluster_id; it < n_items; it += n_clusters, local++) {
-                mbar_wait(&tempty[0], (local & 1) ^ 1);
-                mbar_wait(&tempty[1], (local & 1) ^ 1);
-                tc_fence_after();
-                for (uint32_t kc = 0; kc < p.n_kchunks; kc++) {
-                    mbar_wait(&full[stage], phase);
-                    tc_fence_after();
-                    const uint32_t sb = smem_u32(smem + (size_t)stage * GEMM2_STAGE_BYTES);
-                    const uint64_t d_x0 = umma_desc_sw128(sb), d_x1 = umma_desc_sw128(sb + GEMM_X_BYTES);
-                    const uint64_t d_q = umma_desc_sw128(sb + Q_OFF);
-#pragma unroll
-                    for (uint32_t ks = 0; ks < GEMM_BK / 8; ks++) {
-                        const uint64_t adv = (uint64_t)(ks * 2);
-                        if (F16) {
-                            tc_mma_f16(tmem_base, d_x0 + adv, d_q + adv, IDESC, (kc | ks) != 0);
-                            tc_mma_f16(tmem_base + GEMM2_BN, d_x1 + adv, d_q + adv, IDESC, (kc | ks) != 0);
-                        } else {
-                            tc_mma_tf32(tmem_base, d_x0 + adv, d_q + adv, IDESC, (kc | ks) != 0);
-                            tc_mma_tf32(tmem_base + GEMM2_BN, d_x1 + adv, d_q + adv, IDESC, (kc | ks) != 0);
-                        }
-                    }
-                    // the stage is reusable once these MMAs have read it -- in every CTA that was written into by a loader
-                    if (CL == 1)
-                        tc_commit(&empty[stage]);
-                    else
-                        tc_commit_mc(&empty[stage], all_mask);
-                    if (++stage == GEMM2_STAGES) {
-                        stage = 0;
-                        phase ^= 1;
-                    }
-                }
-                tc_commit(tfull);
-            }
-        }
-    } else {
-        // ------------------------------------------------------------------ epilogue: group 0 = warps 2-9, group 1 = warps 10-17
-        const int et = tid - 64;            // 0..511
-        const uint32_t grp_e = (uint32_t)(warp - 2) >> 3;
-        const uint32_t half = ((uint32_t)(warp - 2) >> 2) & 1u;   // which 128 of the accumulator's 256 columns
-        const uint32_t quarter = warp & 3;  // TMEM lanes this warp may read: 32*quarter .. +31
-        HitQ* hq = hqs + (warp - 2);
-        uint32_t local = 0;
-        for (uint32_t it = cluster_id; it < n_items; it += n_clusters, local++) {
-            const uint32_t grp = it / p.n_qtiles, qt = it % p.n_qtiles;
-            const uint32_t tile = p.row_tile0 + (grp * CL + crank) * 2 + grp_e;
-            named_bar_sync(2, 512);  // everyone finished reading the constants of the previous item
-            if (et < 128) epilogue_constants<METRIC, F16, GEMM2_BN>(p, qt, et, thr_s, qn_s, us_s, c1_s, c2_s);
-            const uint32_t row = tile * GEMM_BM + quarter * 32 + lane;
-            bool row_ok = tile < p.row_tile1 && row < p.n_rows && !(p.debug & 1);   // a group's last tiles may belong to the next round
-            float xn = 0.f;
-            if (row_ok) {
-                if (p.live) row_ok = (__ldg(p.live + (row >> 5)) >> (row & 31)) & 1u;
-                if (row_ok && p.filter) row_ok = (__ldg(p.filter + (row >> 5)) >> (row & 31)) & 1u;
-                if (METRIC == METRIC_L2 && row_ok) xn = __ldg(p.row_norms + row);
-            }
-            named_bar_sync(2, 512);
-            mbar_wait(tfull, local & 1);
-            tc_fence_after();
-            const uint32_t taddr0 = tmem_base + ((quarter * 32u) << 16) + grp_e * GEMM2_BN;
-            epilogue_drain<METRIC, F16, GEMM2_BN, GEMM2_HITQ>(p, taddr0, qt, row, row_ok, xn, thr_s, qn_s, us_s, c1_s, c2_s, hq, half * (GEMM2_BN / 64),
-                                                  (half + 1) * (GEMM2_BN / 64));
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&tempty[grp_e]);
-        }
-    }
-
-    tc_fence_before();
-    __syncthreads();
-    if (CL > 1) cluster_sync_all();   // no CTA leaves while the peer may still multicast into it or arrive on its barriers
-    if (warp == 1) {
-        tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
-    }
 }
 
 // ---- the CTA-pair one-pass kernel (tcgen05 cta_group::2) ----------------------------------------------------------

@@ -154,33 +154,6 @@ cudaError_t launch_gemm_t(const CUtensorMap& mx, const CUtensorMap& mqh, const C
     return passes == 1 ? launch_gemm_tp<METRIC, 1>(mx, mqh, mql, gp, grid, st, bn) : launch_gemm_tp<METRIC, 3>(mx, mqh, mql, gp, grid, st, bn);
 }
 
-// the wide kernel (two row tiles per staged query tile; CL = 2: clusters of two CTAs sharing the query tile by multicast)
-template <int METRIC, int PASSES, int CL>
-cudaError_t launch_gemm2_t(const CUtensorMap& mx, const CUtensorMap& mq, const GemmParams& gp, int grid, cudaStream_t st) {
-    auto kern = gemm_topk2_kernel<METRIC, PASSES, CL>;
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM2_SMEM_BYTES);
-    if (e != cudaSuccess) return e;
-    cudaLaunchConfig_t cfg{};
-    cfg.gridDim = dim3((unsigned)grid);
-    cfg.blockDim = dim3(GEMM2_THREADS);
-    cfg.dynamicSmemBytes = GEMM2_SMEM_BYTES;
-    cfg.stream = st;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = CL;
-    attr[0].val.clusterDim.y = 1;
-    attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
-    return cudaLaunchKernelEx(&cfg, kern, mx, mq, gp);
-}
-template <int METRIC>
-cudaError_t launch_gemm2(const CUtensorMap& mx, const CUtensorMap& mq, const GemmParams& gp, int grid, cudaStream_t st, int passes, int cl) {
-    if (passes == GEMM_TIER_F16)
-        return cl == 2 ? launch_gemm2_t<METRIC, GEMM_TIER_F16, 2>(mx, mq, gp, grid, st) : launch_gemm2_t<METRIC, GEMM_TIER_F16, 1>(mx, mq, gp, grid, st);
-    return cl == 2 ? launch_gemm2_t<METRIC, 1, 2>(mx, mq, gp, grid, st) : launch_gemm2_t<METRIC, 1, 1>(mx, mq, gp, grid, st);
-}
-
 // the CTA-pair kernel (cta_group::2: the pair shares the query tile inside the tensor cores)
 template <int METRIC, int PASSES>
 cudaError_t launch_gemm_pair_t(const CUtensorMap& mx, const CUtensorMap& mq, const GemmParams& gp, int grid, cudaStream_t st) {
@@ -308,14 +281,12 @@ int search_gemm_tier(mlv_index* h, const float* qprep, uint32_t nq, uint32_t k, 
         h->launches++;
         CK(h, cudaGetLastError());
     }
-    // wide kernel (two row tiles per staged query tile) for the one-pass tiers of wide batches; cl = CTAs per cluster
-    // tune_gemm_wide: 0 single-tile kernel, 1 two row tiles per query tile, 2 the same in clusters of two (query tile by
-    // multicast), 3 CTA pairs (cta_group::2, double-buffered accumulators)
-    const bool pair = GEMM_BN == 256 && passes != 3 && h->tune_gemm_wide == 3;
-    const int wide_cl = (GEMM_BN == 256 && passes != 3 && h->tune_gemm_wide != 0 && !pair) ? (h->tune_gemm_wide == 1 ? 1 : 2) : 0;
+    // one-pass tiers of batches wider than 128 queries: CTA pairs (tcgen05 cta_group::2, double-buffered accumulators);
+    // tune_gemm_wide 0 = the single-tile kernel
+    const bool pair = GEMM_BN == 256 && passes != 3 && h->tune_gemm_wide != 0;
     CUtensorMap mx, mqh, mql;
     if ((rc = make_tile_map(h, &mx, half ? view.rows16 : (const void*)view.rows, view.n_rows, GEMM_BM, half)) != MLV_OK) return rc;
-    if ((rc = make_tile_map(h, &mqh, qhi, nq_pad, (wide_cl == 2 || pair) ? GEMM_BN / 2 : GEMM_BN, half)) != MLV_OK) return rc;
+    if ((rc = make_tile_map(h, &mqh, qhi, nq_pad, pair ? GEMM_BN / 2 : GEMM_BN, half)) != MLV_OK) return rc;
     if ((rc = make_tile_map(h, &mql, half ? qhi : qlo, nq_pad, GEMM_BN, half)) != MLV_OK) return rc;
     CK(h, cudaFuncSetAttribute(refine_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((SELECT_MAX_P + SELECT_MAX_P / 4) * 8)));
 
@@ -362,13 +333,12 @@ int search_gemm_tier(mlv_index* h, const float* qprep, uint32_t nq, uint32_t k, 
         gp.row_tile0 = seen;
         gp.row_tile1 = seen + take;
         uint64_t items = (uint64_t)take * gp.n_qtiles;
-        if (wide_cl) items = (uint64_t)((take + 2 * wide_cl - 1) / (2 * wide_cl)) * gp.n_qtiles * wide_cl;   // CTAs that get an item
         int grid = (int)std::min<uint64_t>(items, (uint64_t)h->sm_count);
         if (pair) {
             items = (uint64_t)((take + 1) / 2) * gp.n_qtiles * 2;
             grid = (int)std::min<uint64_t>(items, (uint64_t)h->sm_count);
         }
-        if (wide_cl == 2 || pair) grid = std::max(2, grid & ~1);
+        if (pair) grid = std::max(2, grid & ~1);
         cudaEvent_t e0 = nullptr, e1 = nullptr;
         if (h->timing) {
             for (cudaEvent_t* ev : {&e0, &e1}) {
@@ -391,9 +361,7 @@ int search_gemm_tier(mlv_index* h, const float* qprep, uint32_t nq, uint32_t k, 
                 h->tune_gemm_wide = 0;
                 return search_gemm_tier(h, qprep, nq, k, passes, view, out_d, out_r, out_c, st, hflags, predict);
             }
-        } else if (wide_cl)
-            CK(h, l2 ? launch_gemm2<METRIC_L2>(mx, mqh, gp, grid, st, passes, wide_cl) : launch_gemm2<METRIC_IP>(mx, mqh, gp, grid, st, passes, wide_cl));
-        else
+        } else
             CK(h, l2 ? launch_gemm_t<METRIC_L2>(mx, mqh, mql, gp, grid, st, (int)GEMM_BN, passes)
                      : launch_gemm_t<METRIC_IP>(mx, mqh, mql, gp, grid, st, (int)GEMM_BN, passes));
         if (h->timing) {

@@ -39,7 +39,7 @@ int choose_cfg(mlv_index* h, uint32_t nq, uint32_t k, bool range, ScanCfg* c, bo
     if (!range) {
         while (NQ < 8 && (uint32_t)NQ < nq) NQ <<= 1;
         while (NQ > 1 && ((size_t)NQ * lcap * CW * 8 > 65536 || R * NQ > 32)) NQ >>= 1;
-        if (NQ >= 4) CW = std::min(CW, SCAN_WIDE_CW);   // launch bounds of the wide instantiations (scan_max_threads)
+        if (NQ >= 2) CW = std::min(CW, SCAN_WIDE_CW);   // launch bounds of the multi-query instantiations (scan_max_threads)
     }
     const int max_stages = std::min(std::max(h->tune_max_stages, 2), 16);
     const size_t fixed = (size_t)NQ * qbytes + (range ? 0 : (size_t)CW * NQ * lcap * 8) + (size_t)max_stages * 24 + 256;

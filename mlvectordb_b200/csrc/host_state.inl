@@ -142,7 +142,7 @@ struct mlv_index {
     int tune_gemm_min_nq = 0;  // 0 = auto (gemm_min_nq: 5 with the one-pass tier on a >= 1 GB matrix, else 9)
     int tune_gemm_bn = 0;      // queries per GEMM tile: 0 auto, or 64 / 128 / 256
     int tune_gemm_debug = 0;   // profiling only: bit 0 = epilogue drains nothing (wrong results)
-    int tune_gemm_wide = 3;    // one-pass tiers of wide batches: 0 = single-tile kernel, 1 = two row tiles per query tile, 2 = the same in clusters of two (multicast), 3 = CTA pairs (cta_group::2; default: fastest on every shape measured)
+    int tune_gemm_wide = 3;    // one-pass tiers of wide batches: 0 = single-tile kernel, anything else = CTA pairs (cta_group::2; fastest on every shape measured)
     int tune_gemm_passes = 0;  // 0 auto (fp16 shadow tier, then 3xTF32 for what it cannot certify), 1 one-pass TF32 tier then scan, 2 fp16 tier then scan, 3 3xTF32 only
     uint64_t gemm_fast_queries = 0;  // queries certified by the one-pass tier
     uint64_t gemm_gathered_searches = 0;  // filtered batches that multiplied a compacted copy of the passing rows

@@ -34,7 +34,7 @@ constexpr int SCAN_MAX_THREADS = (SCAN_MAX_CW + SCAN_MAX_PW) * 32;  // 640 -> pt
 constexpr int SCAN_WIDE_CW = 8;
 template <int NQ>
 constexpr int scan_max_threads() {
-    return NQ >= 4 ? (SCAN_WIDE_CW + SCAN_MAX_PW) * 32 : SCAN_MAX_THREADS;
+    return NQ >= 2 ? (SCAN_WIDE_CW + SCAN_MAX_PW) * 32 : SCAN_MAX_THREADS;   // (NQ = 2, R = 4 spilled 16 bytes at 96 registers)
 }
 
 // scale exponent for a largest magnitude `m`: 2^s with m * 2^s in [2^13, 2^14) (fp16 overflows at 2^16: two bits of
@@ -280,7 +280,7 @@ __device__ __forceinline__ void scan_body(const ScanParams& p, const float* iq) 
     constexpr bool HMMA = HALF == 2;
     extern __shared__ __align__(128) unsigned char smem[];
     // fallback launch behind a shadow scan: nothing to do when that one certified its answer
-    if (p.run_if && *reinterpret_cast<const volatile uint32_t*>(p.run_if) == 0) return;
+    if (NQ == 1 && p.run_if && *reinterpret_cast<const volatile uint32_t*>(p.run_if) == 0) return;   // (single queries only)
 
     const int tid = threadIdx.x;
     const int warp = tid >> 5;
@@ -834,7 +834,7 @@ __device__ __forceinline__ void scan_body(const ScanParams& p, const float* iq) 
             // A much tighter bound when a warp's worth of lists holds at least k valid FIRST keys: sorted across the lanes,
             // the k-th of them has k keys <= it, so the global k-th best is too.  On 148 lists of 10 it leaves ~40
             // survivors instead of ~250 (whose O(m^2) ranking cost 7 us), for one register sort per warp.
-            if (k > 16 && k <= n_lists) {
+            if (HALF && k > 16 && k <= n_lists) {
                 // ... for larger k (the shadow scan's k' = 32) a warp's worth of heads says little (its k-th is its
                 // largest); the k-th smallest of ALL the heads does: ranked by counting in the still unused candidate
                 // array.  Without it ~1000 of 148 x 32 keys survived and went through the bitonic network (16 us).
@@ -864,12 +864,13 @@ __device__ __forceinline__ void scan_body(const ScanParams& p, const float* iq) 
             const uint64_t T = s_T;
             // four independent loads per thread and step: with k' = 32 keys per block list (shadow scan) and few consumer
             // warps this loop was 10 us of dependent L2 round trips
-            for (uint32_t i0 = tid; i0 < n; i0 += 4 * nthr) {
-                uint64_t key[4];
+            constexpr int GU = HALF ? 4 : 1;   // (the fp32 instantiations have no registers to spare and 3x fewer keys)
+            for (uint32_t i0 = tid; i0 < n; i0 += GU * nthr) {
+                uint64_t key[GU];
 #pragma unroll
-                for (int u = 0; u < 4; u++) key[u] = i0 + u * nthr < n ? __ldcg(keys + i0 + u * nthr) : KEY_SENTINEL;
+                for (int u = 0; u < GU; u++) key[u] = i0 + u * nthr < n ? __ldcg(keys + i0 + u * nthr) : KEY_SENTINEL;
 #pragma unroll
-                for (int u = 0; u < 4; u++)
+                for (int u = 0; u < GU; u++)
                     if (i0 + u * nthr < n && key[u] <= T) cand[atomicAdd(&s_m, 1u)] = key[u];
             }
             named_bar_sync(1, CW * 32);
@@ -1012,9 +1013,9 @@ __device__ __forceinline__ void scan_body(const ScanParams& p, const float* iq) 
             // p.cert: this launch is the first of a {first tier, conditional fp32} pair -- the ranks also agree on whether
             // any of them failed to certify (an fp32 first launch always certifies)
             any_uncert = exchange_and_merge(x, fin, p.nq_valid, kf, p.out_dists, p.out_rows, p.out_counts, tid, nthr, &s_valid,
-                                            p.cert != nullptr, my_uncert);
+                                            NQ == 1 && p.cert != nullptr, my_uncert);
         }
-        if (p.cert && tid == 0) {
+        if (NQ == 1 && p.cert && tid == 0) {
             *p.cert = any_uncert ? 1u : 0u;
             if (HALF) {
                 const uint32_t a = atomicAdd(p.half_stats, p.nq_valid) + p.nq_valid;

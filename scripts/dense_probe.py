@@ -9,7 +9,7 @@ for rows in (256, 512, 2304, 20736):
     s.add_synthetic(42, 0, rows, False)
     s.set_timing(True)
     s.set_tuning("gemm", 1)
-    for wide in (3, 1, 0):
+    for wide in (3, 0):
         s.set_tuning("gemm_wide", wide)
         for predict in (1, 0):
             s.set_tuning("gemm_predict", predict)
