@@ -1013,15 +1013,31 @@ __global__ void __launch_bounds__(256, 1) rerank_kernel(const RerankParams p) {
     const float4* qv = p.queries + (size_t)q * p.ld4;
     for (uint32_t i = threadIdx.x; i < p.P; i += blockDim.x) a[i] = KEY_SENTINEL;
     __syncthreads();
-    for (uint32_t i = warp; i < n; i += (blockDim.x >> 5)) {
-        const uint32_t row = key_row(mine[i]);
-        const float4* x = p.rows + (size_t)row * p.ld4;
-        float acc = 0.f;
-        for (uint32_t j = lane; j < p.ld4; j += 32) acc = accum4<METRIC>(acc, x[j], qv[j]);
+    // four candidates per warp at a time: four independent row reads in flight (one at a time ran the 2.8 GB of a
+    // 4096 x 224-candidate batch at 4.3 TB/s); per candidate the arithmetic is unchanged
+    const uint32_t nw = blockDim.x >> 5;
+    for (uint32_t i0 = (uint32_t)warp * 4u; i0 < n; i0 += nw * 4u) {
+        uint32_t rows4[4];
+        const float4* x[4];
+        float acc[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-        for (int off = 16; off >= 1; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
-        const float dist = (METRIC == METRIC_IP) ? 1.0f - acc : acc;
-        if (lane == 0) a[i] = make_key(dist, row);
+        for (int u = 0; u < 4; u++) {
+            rows4[u] = key_row(mine[min(i0 + u, n - 1)]);
+            x[u] = p.rows + (size_t)rows4[u] * p.ld4;
+        }
+        for (uint32_t j = lane; j < p.ld4; j += 32) {
+            const float4 q4 = qv[j];
+#pragma unroll
+            for (int u = 0; u < 4; u++) acc[u] = accum4<METRIC>(acc[u], x[u][j], q4);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            float s = acc[u];
+#pragma unroll
+            for (int off = 16; off >= 1; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+            const float dist = (METRIC == METRIC_IP) ? 1.0f - s : s;
+            if (lane == 0 && i0 + u < n) a[i0 + u] = make_key(dist, rows4[u]);
+        }
     }
     bitonic_sort_smem(a, p.P);
     __shared__ int cnt_s;
