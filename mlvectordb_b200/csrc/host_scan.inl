@@ -467,6 +467,9 @@ int half_range_setup(mlv_index* h, const FilterPlan& fp, Lane* ln, cudaStream_t 
     *use = false;
     if (h->tune_scan_half == 0 || fp.gather || h->ld < 8 || !h->tune_dynamic) return MLV_OK;
     if (h->tune_scan_half != 1 && (uint64_t)h->rows * h->ld * 4 < (256ull << 20)) return MLV_OK;
+    // every hit is re-scored by a whole warp (one dependent HBM round trip each): radii that return more than a few per
+    // cent of the rows are cheaper on the fp32 pass.  The hint is the last host call's largest list.
+    if (h->tune_scan_half != 1 && h->range_hits_hint * 32 > h->rows) return MLV_OK;
     int rc;
     if (h->h_half_stats.p && ((volatile uint32_t*)h->h_half_stats.p)[2]) {   // a kernel met an overflowed shadow: rebuild it
         ((volatile uint32_t*)h->h_half_stats.p)[2] = 0;

@@ -137,6 +137,7 @@ struct mlv_index {
     cudaEvent_t maint_event = nullptr;
     uint64_t maint_gen = 0;
     cudaStream_t maint_stream = nullptr;
+    uint64_t range_hits_hint = 0;                // largest hit count of the last host range search
     bool half_stepped = false;                   // the latency-path probe of this search already stepped the policy
     int tune_gemm = -1;        // -1 auto, 0 never, 1 whenever the shape allows it
     int tune_gemm_min_nq = 0;  // 0 = auto (gemm_min_nq: 5 with the one-pass tier on a >= 1 GB matrix, else 9)

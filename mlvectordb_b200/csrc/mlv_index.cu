@@ -1056,6 +1056,8 @@ int mlv_index_range_search(mlv_index_t h, const float* queries, uint32_t nq, flo
     if (rc != MLV_OK) return rc;
     CK(h, cudaMemcpyAsync(out_counts, h->d_outc.p, (size_t)nq * 8, cudaMemcpyDeviceToHost, h->stream));
     CK(h, cudaStreamSynchronize(h->stream));
+    h->range_hits_hint = 0;   // how wide this caller's radii are (half_range_setup: the shadow range scan re-scores every hit)
+    for (uint32_t q = 0; q < nq; q++) h->range_hits_hint = std::max<uint64_t>(h->range_hits_hint, out_counts[q]);
     const uint64_t slots = std::max<uint64_t>(max_hits, 1);
     for (uint32_t q = 0; q < nq; q++) {
         const uint64_t got = std::min<uint64_t>(out_counts[q], max_hits);
