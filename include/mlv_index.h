@@ -346,7 +346,8 @@ int mlv_index_range_search_exchange(mlv_index_t h, const float *queries, uint32_
 int mlv_index_set_timing(mlv_index_t h, int enabled);
 int mlv_index_scan_time_ms(mlv_index_t h, double *total_ms, uint64_t *launches);
 /*
- * Experimental scan tuning (profiling sweeps): key in {"cw" consumer warps per CTA, "stage_kb"
+ * Experimental scan tuning (profiling sweeps): key in {"cw" consumer warps per CTA, "pw" producer warps of a gathered
+ * scan (0 = auto), "stage_kb"
  * ring-stage target size, "max_stages", "r" rows per warp step (0 = auto), "evict_first"
  * (-1 auto / 0 / 1), "ctas" grid size (0 = one per SM), "dynamic" (1 = work-stealing tile scheduler,
  * 0 = static round-robin), "tile_batch" tiles claimed per atomic, "fused" (1 = the last CTA does the
@@ -387,7 +388,7 @@ int mlv_index_debug_timeline(mlv_index_t h, uint64_t *out, uint32_t max_ctas, ui
  * the matrix again in HBM and is built lazily -- without room for it the one-pass TF32 GEMM on the fp32 rows
  * takes its place), then the 3xTF32 GEMM for the queries the first tier could not certify; what neither
  * certifies is re-run by the exact scan, so results do not depend on the path.  set_tuning keys: "gemm"
- * (-1 auto, 0 never, 1 whenever the shape allows), "gemm_min_nq", "gemm_passes" (0 auto, 1 one-pass TF32 tier
+ * (-1 auto, 0 never, 1 whenever the shape allows), "gemm_min_nq", "gemm_bn" (queries per tensor-core tile: 0 auto, 64 / 128 / 256), "gemm_passes" (0 auto, 1 one-pass TF32 tier
  * then scan, 2 fp16 tier then scan, 3 3xTF32 tier only), "gemm_wide" (which kernel runs the one-pass tiers of
  * batches wider than 128 queries: non-zero = CTA pairs, tcgen05 cta_group::2 (default); 0 = the single-tile kernel),
  * "gemm_debug" (profiling only: bit 0 = the epilogue compares nothing -- results are wrong), "gemm_predict" (1 default: the one-pass tiers' per-query thresholds are PREDICTED from the rows

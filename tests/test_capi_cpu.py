@@ -105,3 +105,14 @@ def test_float32_json_encoder_round_trips_without_a_gpu():
     small = C.create_string_buffer(8)
     one = np.ones(4, np.float32)
     assert lib.mlv_format_f32_json(one.ctypes.data, 4, small, len(small), C.byref(n)) == _capi.MLV_E_INVALID
+
+
+def test_every_tuning_key_is_documented_in_the_header():
+    """mlv_index_set_tuning's keys live in one if-chain; the header is the only place a caller can learn them."""
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    src = open(os.path.join(root, "mlvectordb_b200", "csrc", "mlv_index.cu")).read()
+    hdr = open(os.path.join(root, "include", "mlv_index.h")).read()
+    keys = sorted(set(re.findall(r'k == "([a-z0-9_]+)"', src)))
+    assert len(keys) >= 20
+    assert [k for k in keys if f'"{k}"' not in hdr] == []
