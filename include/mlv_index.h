@@ -358,7 +358,7 @@ int mlv_index_scan_time_ms(mlv_index_t h, double *total_ms, uint64_t *launches);
  * tensor-core keys listed at mlv_index_gemm_stats}.  Results never depend on these.
  *
  * Shadow scan ("scan_half": -1 auto = matrices of 256 MB and more, 0 never, 1 whenever the shape allows).  A SINGLE
- * query with k <= 16 (no gathered filter) reads an fp16 shadow of the rows -- half the bytes of the HBM-bound pass; the
+ * query with k <= 16 reads an fp16 shadow of the rows -- half the bytes of the HBM-bound pass; the
  * shadow (rows * 2^s, 2 bytes per element, built on first use and kept up to date like the row norms: + 50 % device
  * memory; without room for it the search is the fp32 one) is the one the tensor-core tier uses -- keeps 32 candidates by
  * approximate distance, and the last CTA re-scores them from the fp32 matrix in the scan's own arithmetic and certifies
@@ -366,7 +366,8 @@ int mlv_index_scan_time_ms(mlv_index_t h, double *total_ms, uint64_t *launches);
  * An fp32 scan launch is queued right behind it and returns at once unless the certificate failed, so the fallback is
  * decided on the device and the call stays asynchronous; the results are the fp32 scan's bit for bit either way.
  * "scan_half_mma" (1 default): rows of whole 128-byte chunks are scored by tensor-core consumers (mma.sync), 0 = FMA
- * consumers.  A shadow that certifies less than half of its searches sits out 64, 128, ... searches.  In an exchange
+ * consumers.  "scan_half_gather" (1 default): a gathered (selectively filtered) single query reads the shadow's rows too
+ * when they are at least 256 bytes and the row list is worth 1 GB of fp32 rows; 0 = gathered scans read the fp32 rows.  A shadow that certifies less than half of its searches sits out 64, 128, ... searches.  In an exchange
  * search every rank issues the same two launches whether or not it has a shadow to read (the ranks agree on the
  * certificate through the exchange itself), so "scan_half" must be 0 on all ranks or on none.
  * mlv_index_gemm_stats reports half_scan_queries / half_scan_uncertified.

@@ -428,13 +428,23 @@ bool half_scan_proto(const mlv_index* h, uint32_t nq, uint32_t k) {
 }
 // ... and this rank's own: a matrix large enough for the saved bytes to matter (below ~256 MB the pass is a few tens of
 // microseconds and the second launch costs more than the bytes), no per-row gather, not sitting out
-bool half_scan_shape(const mlv_index* h, uint32_t nq, uint32_t k, bool gather) {
-    if (!half_scan_proto(h, nq, k) || gather || h->ld < 8) return false;
+// gathered_rows: 0 = not a gathered scan; UINT64_MAX = gathered, list length unknown to the host; else the list length.
+// A gathered scan copies row by row: half-size rows halve the bytes per copy, not the copies, and a short list is all
+// start-up and tail (10M x 384: 1 % of the rows 53 -> 100 us, 10 % 250 -> 230 us, 50 % 1083 -> 705 us), so it pays from
+// 256-byte half rows up and from a list worth 1 GB of fp32 rows.
+bool half_scan_shape(const mlv_index* h, uint32_t nq, uint32_t k, uint64_t gathered_rows) {
+    if (!half_scan_proto(h, nq, k) || h->ld < 8) return false;
+    if (gathered_rows) {
+        if (!h->tune_scan_half_gather || f16_ld(h) < 128) return false;
+        if (h->tune_scan_half == 1) return true;
+        return gathered_rows != UINT64_MAX && gathered_rows * h->ld * 4 >= (1ull << 30);
+    }
     return h->tune_scan_half == 1 || (uint64_t)h->rows * h->ld * 4 >= (256ull << 20);
 }
-bool half_scan_local(const mlv_index* h, uint32_t nq, uint32_t k, bool gather) {
-    return half_scan_shape(h, nq, k, gather) && h->half_skip == 0;
+bool half_scan_local(const mlv_index* h, uint32_t nq, uint32_t k, uint64_t gathered_rows) {
+    return half_scan_shape(h, nq, k, gathered_rows) && h->half_skip == 0;
 }
+uint64_t gathered_rows_of(const FilterPlan& fp) { return fp.gather ? (fp.n_rows_host ? fp.n_rows_host : UINT64_MAX) : 0; }
 // feedback from the kernels' pinned mirror: a shadow that certifies less than half of its queries sits out 64, 128, ...
 // searches (each uncertified query costs the fp32 pass on top); an overflowed shadow is rebuilt with a fresh scale
 void half_scan_policy(mlv_index* h) {
@@ -532,7 +542,7 @@ int search_prepared(mlv_index* h, const float* qprep, uint32_t nq, uint32_t k, c
     int rc = plan_filter(h, ln, filter_dev, st, &fp);
     if (rc != MLV_OK) return rc;
     // one policy step per search: the latency path asks first (with `fast`) and may come back staged
-    if (half_scan_shape(h, nq, k, fp.gather != nullptr)) {
+    if (half_scan_shape(h, nq, k, gathered_rows_of(fp))) {
         if (fast) {
             half_scan_policy(h);
             h->half_stepped = true;
@@ -543,7 +553,7 @@ int search_prepared(mlv_index* h, const float* qprep, uint32_t nq, uint32_t k, c
         }
     }
     // two launches per search (first tier + conditional fp32)?  Across ranks the protocol decides, alone this rank does
-    const bool pair_proto = half_scan_proto(h, nq, k) && (exchange || half_scan_local(h, nq, k, fp.gather != nullptr));
+    const bool pair_proto = half_scan_proto(h, nq, k) && (exchange || half_scan_local(h, nq, k, gathered_rows_of(fp)));
     ScanCfg c;
     if ((rc = choose_cfg(h, nq, k, false, &c, fp.gather != nullptr)) != MLV_OK) return rc;
     if ((rc = ensure_sched(h, ln)) != MLV_OK) return rc;
@@ -587,7 +597,7 @@ int search_prepared(mlv_index* h, const float* qprep, uint32_t nq, uint32_t k, c
     if (pair_proto && fused) {
         // ---- first tier + conditional fp32 launch (one query) ----
         if ((rc = ensure_dev(h, ln->d_cert, 4)) != MLV_OK) return rc;
-        bool use_half = half_scan_local(h, nq, k, fp.gather != nullptr);
+        bool use_half = half_scan_local(h, nq, k, gathered_rows_of(fp));
         ScanCfg ch{};
         if (use_half) {
             if (h->metric != MLV_COSINE && (rc = ensure_row_norms(h, st)) != MLV_OK) return rc;
@@ -597,7 +607,7 @@ int search_prepared(mlv_index* h, const float* qprep, uint32_t nq, uint32_t k, c
             // rows of whole 128-byte chunks: tensor-core consumers (the FMA consumers are FMA-latency bound at the
             // power-capped clock: 6.5 of the fp32 pass's 7.4 TB/s)
             const int half_kind = (f16_ld(h) % 64 == 0 && h->tune_scan_half_mma != 0) ? 2 : 1;
-            if ((rc = choose_cfg(h, 1, HALF_SCAN_KPRIME, false, &ch, false, half_kind)) != MLV_OK) return rc;
+            if ((rc = choose_cfg(h, 1, HALF_SCAN_KPRIME, false, &ch, fp.gather != nullptr, half_kind)) != MLV_OK) return rc;
             // the tail's scratch (candidates | k' approximate | 32 exact | k final keys) overlays the ring and must leave
             // the query behind it alone
             const size_t scratch = ((size_t)fused_cap(ch, HALF_SCAN_KPRIME) + HALF_SCAN_KPRIME + 32 + k) * 8;

@@ -126,6 +126,7 @@ struct mlv_index {
     uint64_t gemm_half_queries = 0;  // queries certified by the fp16 tier
     // shadow scan (single queries over the fp16 shadow, scan_kernel_half): -1 auto, 0 never, 1 whenever the shape allows
     int tune_scan_half = -1;
+    int tune_scan_half_gather = 1;   // gathered (selectively filtered) single queries may read the shadow too (0 = fp32 rows)
     int tune_scan_half_mma = 1;      // tensor-core consumers when the shadow's rows are whole 128-byte chunks (0 = FMA consumers)
     DevBuf d_half_stats;             // device counters {queries, not certified}
     HostBuf h_half_stats;            // their pinned mirror {queries, not certified, overflow flag}, written by the kernel

@@ -116,6 +116,7 @@ int mlv_index_create(uint32_t dim, int metric, uint64_t capacity_hint, int devic
     h->tune_gemm_predict = env_int("MLV_GEMM_PREDICT", h->tune_gemm_predict);
     h->tune_scan_half = env_int("MLV_SCAN_HALF", h->tune_scan_half);
     h->tune_scan_half_mma = env_int("MLV_SCAN_HALF_MMA", h->tune_scan_half_mma);
+    h->tune_scan_half_gather = env_int("MLV_SCAN_HALF_GATHER", h->tune_scan_half_gather);
     DeviceGuard g(device);
     cudaDeviceProp prop;
     cudaError_t e = g.ok ? cudaGetDeviceProperties(&prop, device) : cudaErrorInvalidDevice;
@@ -212,6 +213,7 @@ int mlv_index_set_tuning(mlv_index_t h, const char* key, int value) {
     else if (k == "gemm_wide") h->tune_gemm_wide = value;
     else if (k == "gemm_debug") h->tune_gemm_debug = value;
     else if (k == "scan_half_mma") h->tune_scan_half_mma = value;
+    else if (k == "scan_half_gather") h->tune_scan_half_gather = value;
     else if (k == "scan_half") {
         h->tune_scan_half = value;
         h->half_skip = h->half_backoff = 0;

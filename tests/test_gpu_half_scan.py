@@ -79,7 +79,36 @@ def test_ragged_dimension_tombstones_and_a_streamed_filter():
     L, D = exact.knn(X, Q, k, "l2", allow=allow & mask)
     for i in range(nq):
         assert exact.check_topk_parity(got[i][1][0], got[i][0][0], L[i], D[i]) is None
-    s.set_tuning("gather", 1)                              # a gathered scan reads rows one by one: fp32 path
+    s.set_tuning("gather", 1)                              # a gathered scan copies row by row: 208-byte half rows stay fp32
+    _, used, _ = _half_vs_plain(s, Q, k, pf)
+    assert used == 0
+    pf.close()
+    s.close()
+
+
+@pytest.mark.parametrize("space,dim", [("l2", 128), ("cosine", 200), ("ip", 384)])
+def test_gathered_scan_over_the_shadow(space, dim):
+    """A selective prepared filter makes the scan copy only the passing rows; with half rows of 256 bytes and more those
+    copies read the shadow (FMA or tensor-core consumers), re-rank and certificate as ever: the fp32 gathered scan's bits."""
+    n, nq, k = 40_000, 8, 10
+    X = synthetic.rows(95, 0, n, dim, scaled=(space != "l2"))
+    Q = synthetic.queries(96, nq, dim)
+    s = _shard(dim, space)
+    s.add(X)
+    s.mark_deleted(np.arange(5, n, 13, dtype=np.uint64))
+    mask = np.random.default_rng(9).random(n) < 0.07
+    pf = s.prepare_filter(mask)
+    s.set_tuning("gather", 1)
+    got, used, uncert = _half_vs_plain(s, Q, k, pf)
+    assert used == nq and uncert <= 2, (used, uncert)
+    allow = mask.copy()
+    allow[5::13] = False
+    L, D = exact.knn(X, Q, k, space, allow=allow)
+    for i in range(nq):
+        c = int(got[i][2][0])
+        assert c == len(L[i])
+        assert exact.check_topk_parity(got[i][1][0, :c], got[i][0][0, :c], L[i], D[i]) is None
+    s.set_tuning("scan_half_gather", 0)
     _, used, _ = _half_vs_plain(s, Q, k, pf)
     assert used == 0
     pf.close()
