@@ -675,15 +675,20 @@ int search_prepared(mlv_index* h, const float* qprep, uint32_t nq, uint32_t k, c
             h->launches++;
             h->half_scan_launches++;
         } else {
-            // (exchange only) this rank has no shadow to offer: its first launch is the fp32 scan, which always certifies
+            // this rank has no shadow to offer after all (no room for it, or -- in an exchange search -- a shard too small to
+            // bother): its first launch is the fp32 scan, which always certifies
             p.out_keys = (uint64_t*)ln->d_keys0.p;
             p.cert = (uint32_t*)ln->d_cert.p;
-            p.xchg.seq = ++h->xseq;
+            if (exchange) p.xchg.seq = ++h->xseq;
             le = launch_scan(h, p, c, false, st);
             p.cert = nullptr;
         }
         if (le != cudaSuccess) {
             h->timing = timing;
+            if (timing) {
+                h->event_pool.push_back(e0);
+                h->event_pool.push_back(e1);
+            }
             return fail_cuda(h, le, "scan launch");
         }
         p.out_keys = (uint64_t*)ln->d_keys0.p;
